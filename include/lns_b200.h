@@ -1,0 +1,198 @@
+/*
+ * lns_b200.h -- C-ABI of liblns_b200.so: the sm_100a kernels behind the LNS latent-rollout hot path
+ * (autoencoder encode -> K latent-propagator steps -> decode).
+ *
+ * The reference (BaratiLab/LNS-Latent-Neural-PDE-Solver) is pure PyTorch and has no FFI layer of its
+ * own: its boundary is the nn.Module API.  The Python drop-in modules in
+ * /modules keep that API and call the functions below through ctypes (lns_b200/_C.py).  Every
+ * function cites the reference call sites whose ATen library calls it replaces.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types.  All pointers are DEVICE pointers owned by the caller
+ *    (PyTorch allocates); the library never allocates or frees device memory and keeps no device
+ *    state.  Exception: lns_last_error() returns a host string.
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*): no synchronisation,
+ *    no allocation, no host callback -> legal inside CUDA-graph capture.
+ *  - return value: 0 = OK, negative = error (LNS_E_*); text via lns_last_error().  An unsupported
+ *    shape / dtype is an error, never a silent fallback.
+ *  - activations are NHWC ("channel-last": [B][H][W][C], C contiguous) with an explicit batch stride in
+ *    ELEMENTS; dtype LNS_F32 or LNS_BF16.  NCHW fp32 exists only at the two ends of the path (the
+ *    reference's tensors are NCHW fp32, modules/autoencoder2d.py:69-72).
+ */
+#ifndef LNS_B200_H
+#define LNS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LNS_OK 0
+#define LNS_E_INVALID (-1)     /* bad argument / unsupported shape */
+#define LNS_E_CUDA (-2)        /* CUDA launch error, see lns_last_error() */
+#define LNS_E_UNSUPPORTED (-3) /* combination not implemented by this path */
+
+enum { LNS_F32 = 0, LNS_BF16 = 1 };
+enum { LNS_NHWC = 0, LNS_NCHW = 1 };
+enum { LNS_ACT_NONE = 0, LNS_ACT_SILU = 1, LNS_ACT_GELU = 2 };
+enum { LNS_PAD_ZEROS = 0, LNS_PAD_CIRCULAR = 1 };
+/* weight formats produced by lns_pack_conv_weight */
+enum {
+  LNS_W_SIMT_F32 = 0, /* [tap][Cin][Cout] fp32 (CUDA-core validation path, any Cin/Cout)      */
+  LNS_W_UMMA_BF16 = 1 /* [tap][Cin/64][Cout][64] bf16, K-major 128B-swizzled smem image for     */
+                      /* tcgen05.mma (needs Cin % 64 == 0 and Cout % 16 == 0)                   */
+};
+/* which engine executes lns_conv2d */
+enum { LNS_ENGINE_SIMT = 0, LNS_ENGINE_UMMA = 1 };
+
+const char* lns_version(void);
+const char* lns_last_error(void);
+/* sm count / compute capability of the current device; returns LNS_OK */
+int lns_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * lns_conv2d: one implicit-GEMM convolution  y = epilogue( conv( prologue( resize(x) ) ) )
+ *
+ * Replaces, in one kernel, the reference chains
+ *   F.pad (circular / constant) + nn.Conv2d 3x3 / 1x1, stride 1|2, dilation 1..3
+ *       modules/basics.py:249,252 (ResidualBlock), :326-328 (DownSampleBlock),
+ *       train_stage2_ns2d.py:34-41 (DilatedResidualBlock), modules/autoencoder2d_half_periodic.py:36-52
+ *   F.interpolate(scale_factor=2) / nn.Upsample(size) + conv   modules/basics.py:295-299,
+ *       modules/autoencoder2d.py:134-136   (nearest resize folded into the gather, never materialised)
+ *   nn.Linear / 1x1 conv                     modules/basics.py:345-348, modules/factorized_attention.py:114,140-142
+ *   GroupNorm/InstanceNorm apply + Swish/GELU in front of a conv (prologue: per-(sample,channel) affine
+ *       produced by lns_norm_finalize)      modules/basics.py:246-252
+ *   bias, conditioning shift, GELU/Swish, residual add behind a conv (epilogue)
+ *       train_stage2_ns2d.py:50-53, train_stage2_twophase_conditional.py:66-75
+ *
+ * index map: output pixel (yo,xo), tap (ky,kx) reads the VIRTUAL input (size Hv x Wv, the nearest-resized
+ * x) at yv = yo*stride + ky*dil - pad_t (same for x).  pad mode circular wraps yv mod Hv, zeros gives 0
+ * (after the prologue, exactly like padding the activated tensor).  source row = floor(yv*Hin/Hv).
+ * epilogue: v = acc + bias[n] + sample_bias[b][n] + pre_add[b,yo,xo,n];  v = act(v);  v += residual.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct LnsConvDesc {
+  /* input */
+  const void* x;
+  int32_t x_dtype, x_layout;
+  int32_t B, Hin, Win, Cin;
+  int64_t x_bstride;
+  int32_t Hv, Wv; /* virtual (resized) input size; == Hin,Win when there is no resize */
+  /* filter */
+  int32_t KH, KW, stride, dil, pad_t, pad_l, pad_mode_h, pad_mode_w;
+  const void* w; /* packed by lns_pack_conv_weight */
+  int32_t w_format;
+  int32_t engine;
+  const float* bias;        /* [Cout] or NULL */
+  const float* sample_bias; /* [B][Cout] or NULL */
+  /* prologue: x' = act(x*scale[b][c] + shift[b][c]); NULL scale = identity */
+  const float* pro_scale;
+  const float* pro_shift;
+  int32_t pro_act;
+  /* epilogue */
+  int32_t act;
+  const void* pre_add; /* NHWC [B][Hout][Wout][Cout] or NULL, added before the activation */
+  int32_t pre_add_dtype;
+  int64_t pre_add_bstride;
+  const void* residual; /* same shape as the output or NULL, added after the activation */
+  int32_t res_dtype;
+  int64_t res_bstride;
+  /* output */
+  void* y;
+  int32_t y_dtype, y_layout;
+  int32_t Hout, Wout, Cout;
+  int64_t y_bstride;
+} LnsConvDesc;
+
+int lns_conv2d(const LnsConvDesc* d, void* stream);
+
+/* Bytes of the packed image of an OIHW fp32 filter [Cout][Cin][KH][KW] in `format`. */
+int64_t lns_packed_weight_bytes(int Cout, int Cin, int KH, int KW, int format);
+/* Re-lay an OIHW fp32 device filter (nn.Conv2d.weight / nn.Linear.weight [out][in]) into `format`. */
+int lns_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, int format, void* out,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Normalisation: nn.GroupNorm(32,C,eps=1e-6) modules/basics.py:18-24; nn.GroupNorm(1,C)
+ * train_stage2_ns2d.py:33,45, modules/factorized_attention.py:113; nn.GroupNorm(8,C)
+ * modules/autoencoder2d.py:149; nn.InstanceNorm2d modules/factorized_attention.py:139.
+ * All of them become (1) per-(sample,channel) partial sums, (2) a tiny finalize that folds group
+ * statistics, gamma/beta and an optional per-(sample,channel) pre-scale into y = x*scale + shift,
+ * (3) the affine applied in the consuming conv's prologue or by lns_affine_act.
+ * ------------------------------------------------------------------------------------------------ */
+/* number of pixel chunks lns_chan_stats splits one sample into (deterministic, batch independent) */
+int lns_chan_stats_chunks(int H, int W);
+/* partial[b][chunk][c] = (sum, sum of squares) as float2 over the chunk's pixels of x */
+int lns_chan_stats(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, float* partial,
+                   void* stream);
+/* scale/shift [B][C] of GroupNorm(G, C, eps) applied to (x * prescale) (prescale [B][C] or NULL);
+ * gamma/beta [C] or NULL (no affine, InstanceNorm2d default). */
+int lns_norm_finalize(const float* partial, int B, int nchunk, int C, int HW, int G, float eps,
+                      const float* gamma, const float* beta, const float* prescale, float* scale,
+                      float* shift, void* stream);
+/* y = act(x*scale[b][c] + shift[b][c]) (+ NULL scale -> activation only); NHWC in/out */
+int lns_affine_act(const void* x, int x_dtype, int64_t x_bstride, int B, int HW, int C, const float* scale,
+                   const float* shift, int act, void* y, int y_dtype, int64_t y_bstride, void* stream);
+/* nn.LayerNorm over C per token, then + pe[token index within the sample]
+ * (SABlock: modules/basics.py:384-386 -- pe is added AFTER the norm; PoolingReducer LN
+ * modules/factorized_attention.py:80).  x,y: [B][n][C] rows; pe: [>=n][C] fp32 or NULL. */
+int lns_layernorm(const void* x, int x_dtype, int B, int n, int C, const float* gamma, const float* beta,
+                  float eps, const float* pe, void* y, int y_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SABlock attention core  softmax(q k^T * scale) v   modules/basics.py:395-398
+ * qkv: [B][n][3*heads*dh] rows (q | k | v, each (head, dh) major); out: [B][n][heads*dh]
+ * ------------------------------------------------------------------------------------------------ */
+int lns_attention(const void* qkv, int dtype, int B, int n, int heads, int dh, float scale, void* out,
+                  int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FABlock2D pieces  modules/factorized_attention.py:144-159
+ * ------------------------------------------------------------------------------------------------ */
+/* mean over one spatial axis: axis 0 -> out [B][W][C] (mean over H); axis 1 -> out [B][H][C] (PoolingReducer,
+ * modules/factorized_attention.py:86-94; the bias-free linears in front of the mean commute with it) */
+int lns_axis_mean(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int axis, float* out,
+                  void* stream);
+/* LowRankKernel: qk [B][n][2*heads*d] -> rotary with the host-computed tables cos_tab/sin_tab [n][d/2]
+ * (angle[i][f] = linspace(0,1,n)[i] * (scale/min_freq) * inv_freq[f]) ->
+ * K[b][h][i][j] = <q_i, k_j> * scaling   modules/factorized_attention.py:43-69, modules/embedding.py:163-186 */
+int lns_lowrank_kernel(const void* qk, int dtype, int B, int n, int heads, int d, const float* cos_tab,
+                       const float* sin_tab, float scaling, float* K, void* stream);
+/* axial contraction over axis 0 (H): out[b,i,m,(h,c)] = sum_j K[b,h,i,j] u[b,j,m,(h,c)]
+ *                   over axis 1 (W): out[b,i,l,(h,c)] = sum_m K[b,h,l,m] u[b,i,m,(h,c)]
+ * (the two einsums at modules/factorized_attention.py:157-158); u,out NHWC with C = heads*ch */
+int lns_axial_contract(const void* u, int dtype, int B, int H, int W, int heads, int ch, const float* K,
+                       int axis, void* out, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * layout / misc
+ * ------------------------------------------------------------------------------------------------ */
+/* NCHW fp32 <-> NHWC (fp32|bf16); bstrides in elements */
+int lns_nchw_to_nhwc(const float* x, int B, int C, int H, int W, int64_t x_bstride, void* y, int y_dtype,
+                     int64_t y_bstride, void* stream);
+int lns_nhwc_to_nchw(const void* x, int x_dtype, int B, int H, int W, int C, int64_t x_bstride, float* y,
+                     int64_t y_bstride, void* stream);
+/* sinusoidal embedding cat(cos(p f), sin(p f)), f_i = exp(-ln(max_period) i / (dim/2))
+ * modules/cond_utils.py:19-38 */
+int lns_fourier_embedding(const float* param, int B, int dim, float max_period, float* out, void* stream);
+/* y = x * (1 + gate[b][c]) -- conditional propagator gate, train_stage2_twophase_conditional.py:74 */
+int lns_channel_gate(const void* x, int dtype, int B, int HW, int C, const float* gate, void* y, int y_dtype,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spectral convolution (FNO layer) as truncated DFTs with the complex mode-weight multiply fused:
+ *   rfft2 -> corner blocks [:m1,:m2], [-m1:,:m2] x weights (x per-sample complex emb) -> irfft2
+ * modules/basics.py:129-148 (SpectralConv2d), modules/fourier_cond.py:52-81 (conditioned variant).
+ * x: NHWC [B][H][W][Ci]; w_modes: the two state_dict tensors weights1/weights2 [Ci][Co][m1][m2][2] re-laid
+ * (host side, once) as [block 0|1][m1][m2][Ci][Co][re,im] fp32; emb: NULL or [B][m1][m2][block][re,im] fp32, which
+ * is exactly FreqLinear's output (modules/fourier_cond.py:25-29) before view_as_complex; out: NHWC fp32
+ * [B][H][W][Co].  work: scratch of lns_spectral_work_bytes() bytes.  Needs 2*m1 <= H and m2 <= W/2+1.
+ * ------------------------------------------------------------------------------------------------ */
+int64_t lns_spectral_work_bytes(int B, int H, int W, int Ci, int Co, int m1, int m2);
+int lns_spectral_conv2d(const void* x, int x_dtype, int B, int H, int W, int Ci, int Co, int m1, int m2,
+                        const float* w_modes, const float* emb, void* work, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LNS_B200_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of liblns_b200.so (declared in include/lns_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.  The library is built by
+``lns_b200.build.build()`` (``python __graft_entry__.py`` does that)."""
+import ctypes
+import os
+
+from .build import LIB
+
+i32, i64, f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+vp = ctypes.c_void_p
+
+
+class LnsError(RuntimeError):
+    pass
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of LnsConvDesc (include/lns_b200.h)."""
+    _fields_ = [
+        ("x", vp), ("x_dtype", i32), ("x_layout", i32),
+        ("B", i32), ("Hin", i32), ("Win", i32), ("Cin", i32),
+        ("x_bstride", i64),
+        ("Hv", i32), ("Wv", i32),
+        ("KH", i32), ("KW", i32), ("stride", i32), ("dil", i32), ("pad_t", i32), ("pad_l", i32),
+        ("pad_mode_h", i32), ("pad_mode_w", i32),
+        ("w", vp), ("w_format", i32), ("engine", i32),
+        ("bias", vp), ("sample_bias", vp),
+        ("pro_scale", vp), ("pro_shift", vp), ("pro_act", i32),
+        ("act", i32),
+        ("pre_add", vp), ("pre_add_dtype", i32), ("pre_add_bstride", i64),
+        ("residual", vp), ("res_dtype", i32), ("res_bstride", i64),
+        ("y", vp), ("y_dtype", i32), ("y_layout", i32),
+        ("Hout", i32), ("Wout", i32), ("Cout", i32),
+        ("y_bstride", i64),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/lns_b200.h declares
+SIGNATURES = {
+    "lns_version": (ctypes.c_char_p, []),
+    "lns_last_error": (ctypes.c_char_p, []),
+    "lns_device_info": (i32, [ctypes.POINTER(i32)] * 3),
+    "lns_conv2d": (i32, [ctypes.POINTER(ConvDesc), vp]),
+    "lns_packed_weight_bytes": (i64, [i32, i32, i32, i32, i32]),
+    "lns_pack_conv_weight": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
+    "lns_chan_stats_chunks": (i32, [i32, i32]),
+    "lns_chan_stats": (i32, [vp, i32, i32, i32, i32, i32, i64, vp, vp]),
+    "lns_norm_finalize": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
+    "lns_affine_act": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, i32, vp, i32, i64, vp]),
+    "lns_layernorm": (i32, [vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp]),
+    "lns_attention": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, i32, vp]),
+    "lns_axis_mean": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, vp, vp]),
+    "lns_lowrank_kernel": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp]),
+    "lns_axial_contract": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
+    "lns_nchw_to_nhwc": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i64, vp]),
+    "lns_nhwc_to_nchw": (i32, [vp, i32, i32, i32, i32, i32, i64, vp, i64, vp]),
+    "lns_fourier_embedding": (i32, [vp, i32, i32, f32, vp, vp]),
+    "lns_channel_gate": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "lns_spectral_work_bytes": (i64, [i32, i32, i32, i32, i32, i32, i32]),
+    "lns_spectral_conv2d": (i32, [vp] + [i32] * 8 + [vp] * 5),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no CPU / eager fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise LnsError(f"{LIB} is missing: build it with `python __graft_entry__.py` "
+                           "(lns_b200 has no CPU or PyTorch-eager fallback)")
+        l = ctypes.CDLL(LIB)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().lns_last_error().decode(errors="replace")
+        raise LnsError(f"{what} failed (rc={rc}): {msg}")

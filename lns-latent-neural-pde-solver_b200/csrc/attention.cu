@@ -1,0 +1,217 @@
+// SABlock softmax attention core and the FABlock2D pieces (axis mean, low-rank kernel with rotary embedding,
+// axial contractions).  CUDA-core fp32 arithmetic with operands staged in shared memory; sequences here are tiny
+// (n <= 288 tokens for SABlock, n <= 96 per axis for FABlock2D), one (sample, head) fits in one CTA.
+#include "common.cuh"
+
+namespace lns {
+
+// ---- softmax(q k^T * scale) v -------------------------------------------------------------------------
+// grid (heads, B, qsplit), block 256 (8 warps, one query per warp at a time).
+// smem: K_s [n][dh+1], V_s [n][dh], q_s [8][dh], p_s [8][n]
+__global__ void __launch_bounds__(256) attention_kernel(const void* __restrict__ qkv, int dtype, int n, int heads, int dh,
+                                                         float scale, void* __restrict__ out, int out_dtype) {
+  extern __shared__ float sm[];
+  float* K_s = sm;
+  float* V_s = K_s + (size_t)n * (dh + 1);
+  float* q_s = V_s + (size_t)n * dh;
+  float* p_s = q_s + 8 * dh;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int hd = heads * dh;
+  const int64_t row_stride = 3 * (int64_t)hd;
+  const int64_t base = (int64_t)b * n * row_stride;
+  for (int e = threadIdx.x; e < n * dh; e += blockDim.x) {
+    int j = e / dh, d = e - j * dh;
+    K_s[j * (dh + 1) + d] = ld_as_float(qkv, dtype, base + j * row_stride + hd + h * dh + d);
+    V_s[j * dh + d] = ld_as_float(qkv, dtype, base + j * row_stride + 2 * hd + h * dh + d);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q_w = q_s + warp * dh;
+  float* p_w = p_s + warp * n;
+  const int qper = (n + gridDim.z - 1) / gridDim.z;
+  const int q0 = blockIdx.z * qper, q1 = min(n, q0 + qper);
+  for (int i = q0 + warp; i < q1; i += 8) {
+    for (int d = lane; d < dh; d += 32) q_w[d] = ld_as_float(qkv, dtype, base + i * row_stride + h * dh + d);
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) {
+      float s = 0.f;
+      const float* kr = K_s + j * (dh + 1);
+      for (int d = 0; d < dh; ++d) s = fmaf(q_w[d], kr[d], s);
+      s *= scale;
+      p_w[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      float e = expf(p_w[j] - mx);
+      p_w[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    for (int d = lane; d < dh; d += 32) {
+      float o = 0.f;
+      for (int j = 0; j < n; ++j) o = fmaf(p_w[j], V_s[j * dh + d], o);
+      st_from_float(out, out_dtype, ((int64_t)b * n + i) * hd + h * dh + d, o * inv);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- mean over one spatial axis -----------------------------------------------------------------------
+// grid (keep, B), block 256: thread -> (channel c, lane); fixed-order reduction.
+__global__ void __launch_bounds__(256) axis_mean_kernel(const void* __restrict__ x, int dtype, int H, int W, int C,
+                                                         int64_t bstride, int axis, float* __restrict__ out) {
+  extern __shared__ float red[];  // [rows][C]
+  const int rows = 256 / C;
+  const int c = threadIdx.x % C, lane = threadIdx.x / C;
+  const int keep = blockIdx.x, b = blockIdx.y;
+  const int L = axis == 0 ? H : W;
+  float s = 0.f;
+  if (lane < rows) {
+    for (int r = lane; r < L; r += rows) {
+      int64_t pix = axis == 0 ? ((int64_t)r * W + keep) : ((int64_t)keep * W + r);
+      s += ld_as_float(x, dtype, (int64_t)b * bstride + pix * C + c);
+    }
+    red[lane * C + c] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float a = 0.f;
+    for (int l = 0; l < rows; ++l) a += red[l * C + threadIdx.x];
+    int K = axis == 0 ? W : H;
+    out[((int64_t)b * K + keep) * C + threadIdx.x] = a / (float)L;
+  }
+}
+
+// ---- LowRankKernel: rotary + q k^T ----------------------------------------------------------------------
+// grid (heads, B), block 256. smem q_s, k_s: [n][d+1]
+__global__ void __launch_bounds__(256) lowrank_kernel(const void* __restrict__ qk, int dtype, int n, int heads, int d,
+                                                       const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                                       float scaling, float* __restrict__ Kout) {
+  extern __shared__ float sm[];
+  float* q_s = sm;
+  float* k_s = sm + (size_t)n * (d + 1);
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int hd = heads * d, half = d >> 1;
+  const int64_t row_stride = 2 * (int64_t)hd;
+  const int64_t base = (int64_t)b * n * row_stride;
+  // each work item rotates one (token, frequency) pair of q and of k
+  for (int e = threadIdx.x; e < n * half; e += blockDim.x) {
+    int i = e / half, f = e - i * half;
+    float cs = __ldg(cos_t + i * half + f), sn = __ldg(sin_t + i * half + f);
+    int64_t o = base + i * row_stride + h * d;
+    float q1 = ld_as_float(qk, dtype, o + f), q2 = ld_as_float(qk, dtype, o + f + half);
+    float k1 = ld_as_float(qk, dtype, o + hd + f), k2 = ld_as_float(qk, dtype, o + hd + f + half);
+    // t*cos + rotate_half(t)*sin with rotate_half(t) = cat(-t2, t1)   (modules/embedding.py:179-186)
+    q_s[i * (d + 1) + f] = q1 * cs - q2 * sn;
+    q_s[i * (d + 1) + f + half] = q2 * cs + q1 * sn;
+    k_s[i * (d + 1) + f] = k1 * cs - k2 * sn;
+    k_s[i * (d + 1) + f + half] = k2 * cs + k1 * sn;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    int i = e / n, j = e - i * n;
+    const float* qr = q_s + i * (d + 1);
+    const float* kr = k_s + j * (d + 1);
+    float s = 0.f;
+    for (int t = 0; t < d; ++t) s = fmaf(qr[t], kr[t], s);
+    Kout[(((int64_t)b * heads + h) * n + i) * n + j] = s * scaling;
+  }
+}
+
+// ---- axial contraction ---------------------------------------------------------------------------------
+// grid (lines, heads, B), block 256; ch <= 64.  smem: slab [n][ch], K_s [n][n]
+__global__ void __launch_bounds__(256) axial_contract_kernel(const void* __restrict__ u, int dtype, int H, int W,
+                                                              int heads, int ch, const float* __restrict__ Kmat,
+                                                              int axis, void* __restrict__ out, int out_dtype) {
+  extern __shared__ float sm[];
+  const int n = axis == 0 ? H : W;
+  float* slab = sm;
+  float* K_s = sm + (size_t)n * ch;
+  const int line = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int C = heads * ch;
+  const int64_t sbase = (int64_t)b * H * W * C + h * ch;
+  for (int e = threadIdx.x; e < n * ch; e += blockDim.x) {
+    int j = e / ch, c = e - j * ch;
+    int64_t pix = axis == 0 ? ((int64_t)j * W + line) : ((int64_t)line * W + j);
+    slab[e] = ld_as_float(u, dtype, sbase + pix * C + c);
+  }
+  const float* Kg = Kmat + ((int64_t)b * heads + h) * n * n;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) K_s[e] = __ldg(Kg + e);
+  __syncthreads();
+  const int c = threadIdx.x % ch, ig = threadIdx.x / ch, ngrp = blockDim.x / ch;
+  for (int i = ig; i < n; i += ngrp) {
+    float acc = 0.f;
+    const float* kr = K_s + i * n;
+    for (int j = 0; j < n; ++j) acc = fmaf(kr[j], slab[j * ch + c], acc);
+    int64_t pix = axis == 0 ? ((int64_t)i * W + line) : ((int64_t)line * W + i);
+    st_from_float(out, out_dtype, sbase + pix * C + c, acc);
+  }
+}
+
+}  // namespace lns
+
+extern "C" {
+
+int lns_attention(const void* qkv, int dtype, int B, int n, int heads, int dh, float scale, void* out, int out_dtype,
+                  void* stream) {
+  LNS_REQUIRE(qkv && out && B > 0 && n > 0 && heads > 0 && dh > 0, "lns_attention: bad arguments");
+  LNS_REQUIRE(B <= 65535, "lns_attention: batch %d exceeds grid limit, chunk the call", B);
+  size_t smem = ((size_t)n * (dh + 1) + (size_t)n * dh + 8 * dh + 8 * (size_t)n) * sizeof(float);
+  LNS_REQUIRE(smem <= 227 * 1024, "lns_attention: n=%d dh=%d needs %zu B shared memory", n, dh, smem);
+  { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+  int qsplit = 1;
+  while ((int64_t)B * heads * qsplit < 296 && qsplit * 8 < n) qsplit *= 2;
+  dim3 grid(heads, B, qsplit);
+  lns::attention_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(qkv, dtype, n, heads, dh, scale, out,
+                                                                                      out_dtype);
+  return lns::check_launch("attention_kernel");
+}
+
+int lns_axis_mean(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int axis, float* out,
+                  void* stream) {
+  LNS_REQUIRE(x && out && B > 0 && H > 0 && W > 0 && C > 0 && C <= 256 && (axis == 0 || axis == 1),
+              "lns_axis_mean: bad arguments (C=%d)", C);
+  LNS_REQUIRE(B <= 65535, "lns_axis_mean: batch %d exceeds grid limit, chunk the call", B);
+  int rows = 256 / C;
+  dim3 grid(axis == 0 ? W : H, B);
+  lns::axis_mean_kernel<<<grid, 256, (size_t)rows * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, dtype, H, W, C, bstride, axis, out);
+  return lns::check_launch("axis_mean_kernel");
+}
+
+int lns_lowrank_kernel(const void* qk, int dtype, int B, int n, int heads, int d, const float* cos_tab,
+                       const float* sin_tab, float scaling, float* K, void* stream) {
+  LNS_REQUIRE(qk && K && cos_tab && sin_tab && B > 0 && n > 0 && heads > 0 && d > 0 && d % 2 == 0,
+              "lns_lowrank_kernel: bad arguments");
+  LNS_REQUIRE(B <= 65535, "lns_lowrank_kernel: batch %d exceeds grid limit, chunk the call", B);
+  size_t smem = 2 * (size_t)n * (d + 1) * sizeof(float);
+  LNS_REQUIRE(smem <= 227 * 1024, "lns_lowrank_kernel: n=%d d=%d needs %zu B shared memory", n, d, smem);
+  { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::lowrank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+  dim3 grid(heads, B);
+  lns::lowrank_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(qk, dtype, n, heads, d, cos_tab,
+                                                                                    sin_tab, scaling, K);
+  return lns::check_launch("lowrank_kernel");
+}
+
+int lns_axial_contract(const void* u, int dtype, int B, int H, int W, int heads, int ch, const float* K, int axis,
+                       void* out, int out_dtype, void* stream) {
+  LNS_REQUIRE(u && out && K && B > 0 && H > 0 && W > 0 && heads > 0 && ch > 0 && ch <= 256 && 256 % ch == 0 &&
+                  (axis == 0 || axis == 1),
+              "lns_axial_contract: bad arguments (ch=%d)", ch);
+  LNS_REQUIRE(B <= 65535, "lns_axial_contract: batch %d exceeds grid limit, chunk the call", B);
+  int n = axis == 0 ? H : W;
+  size_t smem = ((size_t)n * ch + (size_t)n * n) * sizeof(float);
+  LNS_REQUIRE(smem <= 227 * 1024, "lns_axial_contract: n=%d needs %zu B shared memory", n, smem);
+  { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::axial_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+  dim3 grid(axis == 0 ? W : H, heads, B);
+  lns::axial_contract_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(u, dtype, H, W, heads, ch, K,
+                                                                                           axis, out, out_dtype);
+  return lns::check_launch("axial_contract_kernel");
+}
+
+}  // extern "C"

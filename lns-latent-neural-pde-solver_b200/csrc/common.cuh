@@ -1,0 +1,118 @@
+// Shared device/host helpers for liblns_b200.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/lns_b200.h"
+
+namespace lns {
+
+// ---- error plumbing ------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError -> LNS_E_CUDA (+ message) or LNS_OK
+
+#define LNS_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      lns::set_error(__VA_ARGS__);    \
+      return LNS_E_INVALID;           \
+    }                                 \
+  } while (0)
+
+// ---- dtype helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ float ld_as_float(const void* p, int dtype, int64_t i) {
+  if (dtype == LNS_F32) return __ldg(reinterpret_cast<const float*>(p) + i);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void st_from_float(void* p, int dtype, int64_t i, float v) {
+  if (dtype == LNS_F32)
+    reinterpret_cast<float*>(p)[i] = v;
+  else
+    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+// 4 consecutive elements (i must be a multiple of 4 and the pointer suitably aligned)
+__device__ __forceinline__ float4 ld4_as_float(const void* p, int dtype, int64_t i) {
+  if (dtype == LNS_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i));
+  uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i));
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4_from_float(void* p, int dtype, int64_t i, float4 v) {
+  if (dtype == LNS_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = v;
+  } else {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<uint32_t*>(&a);
+    raw.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = raw;
+  }
+}
+__host__ __device__ __forceinline__ int dtype_size(int dtype) { return dtype == LNS_F32 ? 4 : 2; }
+
+// ---- activations (exact forms, matching torch) ----------------------------------------------------
+// Swish  x*sigmoid(x)   modules/basics.py:27-29 ; nn.GELU() exact erf  train_stage2_ns2d.py:36
+__device__ __forceinline__ float act_silu(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float act_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == LNS_ACT_SILU) return act_silu(x);
+  if (act == LNS_ACT_GELU) return act_gelu(x);
+  return x;
+}
+
+// ---- reductions ----------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- conv index map shared by both conv engines -----------------------------------------------------
+struct ConvGeom {
+  int B, Hin, Win, Cin, Hv, Wv;
+  int KH, KW, stride, dil, pad_t, pad_l, circ_h, circ_w;
+  int Hout, Wout, Cout;
+  int64_t x_bstride, y_bstride;
+};
+// source pixel (ys,xs) of virtual coordinate (yv,xv); returns false when the tap falls in zero padding
+__device__ __forceinline__ bool conv_src(const ConvGeom& g, int yv, int xv, int& ys, int& xs) {
+  if (g.circ_h) {
+    yv = yv % g.Hv;
+    if (yv < 0) yv += g.Hv;
+  } else if (yv < 0 || yv >= g.Hv) {
+    return false;
+  }
+  if (g.circ_w) {
+    xv = xv % g.Wv;
+    if (xv < 0) xv += g.Wv;
+  } else if (xv < 0 || xv >= g.Wv) {
+    return false;
+  }
+  ys = (g.Hv == g.Hin) ? yv : (int)(((int64_t)yv * g.Hin) / g.Hv);
+  xs = (g.Wv == g.Win) ? xv : (int)(((int64_t)xv * g.Win) / g.Wv);
+  return true;
+}
+
+int conv2d_simt(const LnsConvDesc* d, cudaStream_t stream);
+int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream);
+int validate_conv(const LnsConvDesc* d);
+ConvGeom make_geom(const LnsConvDesc* d);
+
+}  // namespace lns

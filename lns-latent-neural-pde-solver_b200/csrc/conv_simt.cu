@@ -1,0 +1,236 @@
+// CUDA-core implicit-GEMM convolution: the fp32 validation engine (LNS_ENGINE_SIMT) and the engine for
+// the tiny-channel ends of the path (Cin or Cout in {1,3,4,16}) where a tensor-core tile would be >75% padding.
+// Also: filter re-layout kernels (lns_pack_conv_weight).
+//
+// GEMM view: M = B*Hout*Wout output pixels, N = Cout, K = KH*KW*Cin.  64 x BN tile per CTA, 16-deep K chunks,
+// 4 x (BN/16) accumulators per thread, fp32 FMA accumulation in a fixed order (deterministic, batch independent).
+#include "common.cuh"
+
+namespace lns {
+
+struct SimtParams {
+  ConvGeom g;
+  const void* x;
+  int x_dtype, x_layout;
+  const float* w;
+  const float* bias;
+  const float* sample_bias;
+  const float* pro_scale;
+  const float* pro_shift;
+  int pro_act;
+  int act;
+  const void* pre_add;
+  int pre_add_dtype;
+  int64_t pre_add_bstride;
+  const void* residual;
+  int res_dtype;
+  int64_t res_bstride;
+  void* y;
+  int y_dtype, y_layout;
+  int M;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams p) {
+  constexpr int BM = 64, BK = 16, TN = BN / 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const ConvGeom& g = p.g;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int HWo = g.Hout * g.Wout;
+  const int64_t chan_stride = (p.x_layout == LNS_NCHW) ? (int64_t)g.Hin * g.Win : 1;
+
+  // rows this thread gathers for the A tile: k_l fixed, 4 pixel rows
+  const int k_l = tid & 15;
+  int lb[4], ly[4], lx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + (tid >> 4) + 16 * i;
+    if (m < p.M) {
+      lb[i] = m / HWo;
+      int r = m - lb[i] * HWo;
+      ly[i] = r / g.Wout;
+      lx[i] = r - ly[i] * g.Wout;
+    } else {
+      lb[i] = -1; ly[i] = 0; lx[i] = 0;
+    }
+  }
+
+  float acc[4][TN];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[r][j] = 0.f;
+
+  const int taps = g.KH * g.KW;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int ky = tap / g.KW, kx = tap - ky * g.KW;
+    int64_t soff[4];
+    bool sval[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sval[i] = false;
+      soff[i] = 0;
+      if (lb[i] >= 0) {
+        int ys, xs;
+        if (conv_src(g, ly[i] * g.stride + ky * g.dil - g.pad_t, lx[i] * g.stride + kx * g.dil - g.pad_l, ys, xs)) {
+          sval[i] = true;
+          soff[i] = (int64_t)lb[i] * g.x_bstride +
+                    ((p.x_layout == LNS_NCHW) ? ((int64_t)ys * g.Win + xs) : ((int64_t)ys * g.Win + xs) * g.Cin);
+        }
+      }
+    }
+    for (int c0 = 0; c0 < g.Cin; c0 += BK) {
+      const int c = c0 + k_l;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = 0.f;
+        if (sval[i] && c < g.Cin) {
+          v = ld_as_float(p.x, p.x_dtype, soff[i] + (int64_t)c * chan_stride);
+          if (p.pro_scale) {
+            int64_t sc = (int64_t)lb[i] * g.Cin + c;
+            v = fmaf(v, __ldg(p.pro_scale + sc), __ldg(p.pro_shift + sc));
+          }
+          v = apply_act(v, p.pro_act);
+        }
+        As[k_l][(tid >> 4) + 16 * i] = v;
+      }
+      for (int e = tid; e < BK * BN; e += 256) {
+        int k = e / BN, n = e - k * BN;
+        int cc = c0 + k;
+        float v = 0.f;
+        if (cc < g.Cin && n0 + n < g.Cout) v = __ldg(p.w + ((int64_t)tap * g.Cin + cc) * g.Cout + n0 + n);
+        Bs[k][n] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        float b[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[r][j] = fmaf(a[r], b[j], acc[r][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int m = m0 + ty * 4 + r;
+    if (m >= p.M) continue;
+    int b = m / HWo;
+    int pix = m - b * HWo;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tx * TN + j;
+      if (n >= g.Cout) continue;
+      float v = acc[r][j];
+      if (p.bias) v += __ldg(p.bias + n);
+      if (p.sample_bias) v += __ldg(p.sample_bias + (int64_t)b * g.Cout + n);
+      if (p.pre_add) v += ld_as_float(p.pre_add, p.pre_add_dtype, (int64_t)b * p.pre_add_bstride + (int64_t)pix * g.Cout + n);
+      v = apply_act(v, p.act);
+      if (p.residual) v += ld_as_float(p.residual, p.res_dtype, (int64_t)b * p.res_bstride + (int64_t)pix * g.Cout + n);
+      int64_t o = (int64_t)b * g.y_bstride + ((p.y_layout == LNS_NCHW) ? ((int64_t)n * HWo + pix) : ((int64_t)pix * g.Cout + n));
+      st_from_float(p.y, p.y_dtype, o, v);
+    }
+  }
+}
+
+int conv2d_simt(const LnsConvDesc* d, cudaStream_t stream) {
+  LNS_REQUIRE(d->w_format == LNS_W_SIMT_F32, "lns_conv2d(simt): weights must be packed as LNS_W_SIMT_F32");
+  SimtParams p;
+  p.g = make_geom(d);
+  p.x = d->x; p.x_dtype = d->x_dtype; p.x_layout = d->x_layout;
+  p.w = reinterpret_cast<const float*>(d->w);
+  p.bias = d->bias; p.sample_bias = d->sample_bias;
+  p.pro_scale = d->pro_scale; p.pro_shift = d->pro_shift; p.pro_act = d->pro_act;
+  p.act = d->act;
+  p.pre_add = d->pre_add; p.pre_add_dtype = d->pre_add_dtype; p.pre_add_bstride = d->pre_add_bstride;
+  p.residual = d->residual; p.res_dtype = d->res_dtype; p.res_bstride = d->res_bstride;
+  p.y = d->y; p.y_dtype = d->y_dtype; p.y_layout = d->y_layout;
+  int64_t M = (int64_t)d->B * d->Hout * d->Wout;
+  LNS_REQUIRE(M < (1ll << 31), "lns_conv2d(simt): too many output pixels");
+  LNS_REQUIRE(!(d->pro_scale && !d->pro_shift), "lns_conv2d: pro_scale without pro_shift");
+  p.M = (int)M;
+  if (d->Cout <= 16) {
+    dim3 grid(cdiv(M, 64), cdiv(d->Cout, 16));
+    conv_simt_kernel<16><<<grid, 256, 0, stream>>>(p);
+  } else {
+    dim3 grid(cdiv(M, 64), cdiv(d->Cout, 64));
+    conv_simt_kernel<64><<<grid, 256, 0, stream>>>(p);
+  }
+  return check_launch("conv_simt_kernel");
+}
+
+// ---- filter re-layout ------------------------------------------------------------------------------
+__global__ void pack_simt_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, float* __restrict__ out) {
+  int64_t total = (int64_t)Cout * Cin * KH * KW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int n = (int)(i % Cout);
+    int64_t r = i / Cout;
+    int c = (int)(r % Cin);
+    int tap = (int)(r / Cin);
+    out[i] = w[((int64_t)n * Cin + c) * KH * KW + tap];
+  }
+}
+
+// [tap][Cin/64][Cout][64] bf16; inside each 128-byte row the eight 16-byte chunks are XOR-swizzled with (row & 7),
+// i.e. the image is byte-for-byte what tcgen05's SWIZZLE_128B K-major shared-memory layout expects.
+__global__ void pack_umma_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW,
+                                 __nv_bfloat16* __restrict__ out) {
+  int64_t total = (int64_t)Cout * Cin * KH * KW;
+  int slabs = Cin / 64;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int kk = (int)(i % 64);
+    int64_t r = i / 64;
+    int n = (int)(r % Cout);
+    r /= Cout;
+    int slab = (int)(r % slabs);
+    int tap = (int)(r / slabs);
+    int c = slab * 64 + kk;
+    float v = w[((int64_t)n * Cin + c) * KH * KW + tap];
+    int chunk = (kk >> 3) ^ (n & 7);
+    int64_t o = (((int64_t)tap * slabs + slab) * Cout + n) * 64 + chunk * 8 + (kk & 7);
+    out[o] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace lns
+
+extern "C" {
+
+int64_t lns_packed_weight_bytes(int Cout, int Cin, int KH, int KW, int format) {
+  int64_t n = (int64_t)Cout * Cin * KH * KW;
+  if (format == LNS_W_SIMT_F32) return n * 4;
+  if (format == LNS_W_UMMA_BF16) return (Cin % 64 == 0 && Cout % 16 == 0) ? n * 2 : -1;
+  return -1;
+}
+
+int lns_pack_conv_weight(const float* w, int Cout, int Cin, int KH, int KW, int format, void* out, void* stream) {
+  LNS_REQUIRE(w && out && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "lns_pack_conv_weight: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int64_t total = (int64_t)Cout * Cin * KH * KW;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  if (format == LNS_W_SIMT_F32) {
+    lns::pack_simt_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, KH, KW, reinterpret_cast<float*>(out));
+  } else if (format == LNS_W_UMMA_BF16) {
+    LNS_REQUIRE(Cin % 64 == 0 && Cout % 16 == 0, "lns_pack_conv_weight: UMMA format needs Cin%%64==0, Cout%%16==0 (got %d,%d)",
+                Cin, Cout);
+    lns::pack_umma_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, KH, KW, reinterpret_cast<__nv_bfloat16*>(out));
+  } else {
+    lns::set_error("lns_pack_conv_weight: unknown format %d", format);
+    return LNS_E_INVALID;
+  }
+  return lns::check_launch("pack kernel");
+}
+
+}  // extern "C"

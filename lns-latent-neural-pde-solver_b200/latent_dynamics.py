@@ -1,0 +1,83 @@
+"""``LatentDynamics`` -- the model-assembly class the reference defines inside each stage-2 script
+(train_stage2_ns2d.py:90-158, train_stage2_SW.py:91-159, train_stage2_twophase.py:91-159,
+train_stage2_twophase_conditional.py:124-193): frozen autoencoder + latent propagator, ``predict`` = encode ->
+K autoregressive propagator steps -> decode.  Same attribute names (``vq_ae`` / ``ae``, ``propagator``), hence the
+same state_dict keys; ``predict`` runs through ``lns_b200.rollout.Rollout``."""
+import torch
+import torch.nn as nn
+
+
+class LatentDynamics(nn.Module):
+    def __init__(self, args, kind=None):
+        super().__init__()
+        kind = kind or getattr(args, "kind", None)
+        if kind not in ("ns2d", "sw", "twophase", "twophase_cond"):
+            raise ValueError("kind must be one of ns2d, sw, twophase, twophase_cond")
+        self.kind = kind
+        from modules.propagator import SimpleCNN, CondSimpleCNN
+        if kind == "ns2d":
+            from modules.autoencoder2d import SimpleAutoencoder
+            self.vq_ae = SimpleAutoencoder(args)
+        elif kind == "sw":
+            from modules.autoencoder2d_half_periodic import SimpleAutoencoder
+            self.vq_ae = SimpleAutoencoder(args)
+        elif kind == "twophase":
+            from modules.autoencoder2d_nonsquared import SimpleAutoencoder
+            self.vq_ae = SimpleAutoencoder(args)
+        else:
+            from modules.autoencoder2d_nonsquared import SimpleAutoencoder
+            self.ae = SimpleAutoencoder(args)
+        self.latent_resolution = args.latent_resolution
+        self.latent_dim = args.latent_dim
+        if kind == "twophase_cond":
+            self.propagator = CondSimpleCNN(latent_dim=args.latent_dim, cond_emb_dim=args.latent_dim,
+                                            prop_n_block=args.prop_n_block, prop_n_embd=args.prop_n_embd,
+                                            dilation=args.dilation)
+        else:
+            self.propagator = SimpleCNN(
+                latent_dim=args.latent_dim, prop_n_block=args.prop_n_block, prop_n_embd=args.prop_n_embd,
+                dilation=args.dilation,
+                padding_mode="circular" if kind == "ns2d" else "zeros",
+                periodic_direction="x" if kind == "sw" else None)
+        self._rollouts = {}
+
+    @property
+    def autoencoder(self):
+        return self.ae if self.kind == "twophase_cond" else self.vq_ae
+
+    def load_autoencoder(self, args):
+        ae = self.autoencoder
+        ae.load_checkpoint(args.pretrained_checkpoint_path)
+        for p in ae.parameters():
+            p.requires_grad = False
+        ae.eval()
+
+    @torch.no_grad()
+    def x_to_z(self, x):
+        return self.autoencoder.encode(x)
+
+    @torch.no_grad()
+    def z_to_x(self, z):
+        return self.autoencoder.decode(z)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("the training rollout (needs backward kernels) is out of scope; use predict()")
+
+    @torch.no_grad()
+    def predict(self, x, steps, *args, to_x=False, **kw):
+        """Reference signature: predict(x, steps, to_x=False) / predict(x, steps, param, to_x=False).
+        Returns [B, steps, C, Ly, Lx] (to_x) or [B, steps, Cz, h, w], fp32."""
+        from .rollout import Rollout
+        param = None
+        if self.kind == "twophase_cond":
+            param = args[0] if args else kw["param"]
+        elif args:
+            to_x = args[0]
+        if x.dim() == 5:  # the SW / conditional scripts squeeze a singleton time axis (train_stage2_SW.py:144)
+            x = x.squeeze(1)
+        key = (x.shape[0], steps, bool(to_x), x.device)
+        ro = self._rollouts.get(key)
+        if ro is None:
+            ro = Rollout(self, batch=x.shape[0], steps=steps, to_x=to_x, use_graph=False)
+            self._rollouts[key] = ro
+        return ro(x, param) if param is not None else ro(x)

@@ -1,0 +1,434 @@
+"""Thin Python wrappers over the C-ABI kernels: activation handles (NHWC), weight packing caches and one function
+per library entry point.  PyTorch is used for device memory and streams only; all arithmetic on the path happens in
+liblns_b200.so.  Nothing here falls back to torch ops: a CPU tensor or a missing library raises."""
+import ctypes
+import math
+import threading
+from contextlib import contextmanager
+
+import torch
+
+from . import _C
+from ._C import ConvDesc, LnsError, check
+
+F32, BF16 = 0, 1
+NHWC, NCHW = 0, 1
+ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+PAD_ZEROS, PAD_CIRCULAR = 0, 1
+W_SIMT_F32, W_UMMA_BF16 = 0, 1
+ENGINE_SIMT, ENGINE_UMMA = 0, 1
+
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
+
+
+def dt_code(dtype):
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise LnsError(f"unsupported dtype {dtype}")
+
+
+# ---- precision policy --------------------------------------------------------------------------------
+class _State(threading.local):
+    def __init__(self):
+        self.precision = "bf16"
+        self.launches = 0
+
+
+_state = _State()
+
+
+def get_precision():
+    return _state.precision
+
+
+def set_precision(p):
+    """'bf16': bf16 activations, tcgen05 tensor-core GEMMs with fp32 accumulation (the fast path).
+    'fp32': fp32 activations and CUDA-core fp32 FMA GEMMs (the validation path, <=1e-5 vs the reference)."""
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _state.precision = p
+
+
+@contextmanager
+def precision(p):
+    old = _state.precision
+    set_precision(p)
+    try:
+        yield
+    finally:
+        _state.precision = old
+
+
+def act_dtype():
+    return torch.bfloat16 if _state.precision == "bf16" else torch.float32
+
+
+def launch_count():
+    """Number of liblns_b200 kernel launches issued by this thread so far (bench.py's gpu_launches)."""
+    return _state.launches
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise LnsError(f"{what}: lns_b200 runs on CUDA tensors only (there is no CPU fallback); got device {t.device}")
+
+
+# ---- activation handle ---------------------------------------------------------------------------------
+class Act:
+    """A [B,H,W,C] activation living in `t` (element (0,0,0,0) at t.data_ptr()); channel-last unless layout=NCHW.
+    `bstride` is the distance between samples in elements (lets the K latent states of a rollout interleave as
+    [B,K,...] without copies)."""
+    __slots__ = ("t", "B", "H", "W", "C", "bstride", "layout")
+
+    def __init__(self, t, B, H, W, C, bstride=None, layout=NHWC):
+        self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+        self.bstride = H * W * C if bstride is None else bstride
+        self.layout = layout
+
+    @property
+    def dtype(self):
+        return dt_code(self.t.dtype)
+
+    @property
+    def contiguous(self):
+        return self.bstride == self.H * self.W * self.C
+
+    @staticmethod
+    def empty(B, H, W, C, dtype, device):
+        return Act(torch.empty(B * H * W * C, dtype=dtype, device=device), B, H, W, C)
+
+    def like(self, C=None, dtype=None, H=None, W=None):
+        return Act.empty(self.B, H or self.H, W or self.W, C or self.C, dtype or self.t.dtype, self.t.device)
+
+    @staticmethod
+    def from_nchw(x):
+        """Wrap (no copy) an NCHW fp32 torch tensor."""
+        _need_cuda(x, "Act.from_nchw")
+        if x.dtype != torch.float32:
+            raise LnsError("NCHW inputs must be fp32")
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        return Act(x, B, H, W, C, layout=NCHW)
+
+    def to_nchw(self):
+        """-> NCHW fp32 torch tensor [B,C,H,W]."""
+        if self.layout == NCHW:
+            return self.t.view(self.B, self.C, self.H, self.W)
+        out = torch.empty(self.B, self.C, self.H, self.W, dtype=torch.float32, device=self.t.device)
+        rc = _C.lib().lns_nhwc_to_nchw(_ptr(self.t), self.dtype, self.B, self.H, self.W, self.C, self.bstride,
+                                       _ptr(out), self.C * self.H * self.W, _stream())
+        check(rc, "lns_nhwc_to_nchw")
+        _state.launches += 1
+        return out
+
+    def as_tokens(self):
+        """[B, H*W, C] torch view (contiguous NHWC only) -- for tests."""
+        assert self.layout == NHWC and self.contiguous
+        return self.t.view(self.B, self.H * self.W, self.C)
+
+    def to_torch_nhwc(self):
+        assert self.layout == NHWC and self.contiguous
+        return self.t.view(self.B, self.H, self.W, self.C)
+
+
+def nchw_to_act(x, dtype=None):
+    """NCHW fp32 torch tensor -> NHWC Act of `dtype` (one transposing kernel)."""
+    _need_cuda(x, "nchw_to_act")
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    out = Act.empty(B, H, W, C, dtype or act_dtype(), x.device)
+    rc = _C.lib().lns_nchw_to_nhwc(_ptr(x), B, C, H, W, C * H * W, _ptr(out.t), out.dtype, out.bstride, _stream())
+    check(rc, "lns_nchw_to_nhwc")
+    _state.launches += 1
+    return out
+
+
+# ---- weights ---------------------------------------------------------------------------------------------
+class PackedFilter:
+    """Device-side re-laid copies of one conv / linear filter (OIHW fp32 source), built lazily per format and
+    rebuilt when a source parameter changes (load_state_dict, .to(), optimizer step)."""
+
+    def __init__(self, weight_fn, bias_fn=None):
+        self._weight_fn = weight_fn  # () -> (fp32 OIHW tensor [Cout,Cin,KH,KW], version key)
+        self._bias_fn = bias_fn      # () -> (fp32 [Cout] tensor or None, version key)
+        self._cache = {}
+        self._bias = None
+        self._bias_key = None
+        self.shape = None
+
+    @staticmethod
+    def of(weight, bias=None):
+        """weight: nn.Parameter [Cout,Cin,KH,KW] or [Cout,Cin] (nn.Linear); bias: nn.Parameter [Cout] or None"""
+        def wfn():
+            w = weight.detach()
+            if w.dim() == 2:
+                w = w[:, :, None, None]
+            return w, (weight.data_ptr(), weight._version, weight.device)
+
+        def bfn():
+            if bias is None:
+                return None, None
+            return bias.detach(), (bias.data_ptr(), bias._version, bias.device)
+        return PackedFilter(wfn, bfn)
+
+    @staticmethod
+    def concat(weights, biases):
+        """Stack several [Cout_i, Cin] linears along Cout (q|k|v in one GEMM); a None bias contributes zeros."""
+        def wfn():
+            ws = [w.detach() for w in weights]
+            ws = [w[:, :, None, None] if w.dim() == 2 else w for w in ws]
+            return torch.cat(ws, 0), tuple((w.data_ptr(), w._version, w.device) for w in weights)
+
+        def bfn():
+            if all(b is None for b in biases):
+                return None, None
+            parts = []
+            for w, b in zip(weights, biases):
+                parts.append(b.detach().float() if b is not None
+                             else torch.zeros(w.shape[0], dtype=torch.float32, device=w.device))
+            return torch.cat(parts, 0), tuple((b.data_ptr(), b._version) if b is not None else None for b in biases)
+        return PackedFilter(wfn, bfn)
+
+    def dims(self):
+        w, _ = self._weight_fn()
+        return tuple(w.shape)
+
+    def get(self, fmt):
+        w, key = self._weight_fn()
+        _need_cuda(w, "PackedFilter")
+        ent = self._cache.get(fmt)
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        Cout, Cin, KH, KW = w.shape
+        nbytes = _C.lib().lns_packed_weight_bytes(Cout, Cin, KH, KW, fmt)
+        if nbytes < 0:
+            raise LnsError(f"filter {tuple(w.shape)} cannot be packed in format {fmt}")
+        src = w.contiguous().float()
+        out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        rc = _C.lib().lns_pack_conv_weight(_ptr(src), Cout, Cin, KH, KW, fmt, _ptr(out), _stream())
+        check(rc, "lns_pack_conv_weight")
+        _state.launches += 1
+        self._cache[fmt] = (key, out)
+        return out
+
+    def bias(self):
+        if self._bias_fn is None:
+            return None
+        b, key = self._bias_fn()
+        if b is None:
+            return None
+        if self._bias_key != key or self._bias is None:
+            self._bias = b.contiguous().float().clone()
+            self._bias_key = key
+        return self._bias
+
+
+# ---- conv ---------------------------------------------------------------------------------------------------
+def _umma_ok(x, Cin, Cout, y_layout):
+    return (_state.precision == "bf16" and x.layout == NHWC and x.t.dtype == torch.bfloat16 and Cin % 64 == 0
+            and Cout % 16 == 0 and y_layout == NHWC and x.bstride % 8 == 0)
+
+
+def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, PAD_ZEROS), virt=None, use_bias=True,
+           sample_bias=None, pro=None, act=ACT_NONE, pre_add=None, residual=None, out=None, out_dtype=None,
+           out_layout=NHWC, engine=None):
+    """y = act(conv(pro(resize(x))) + bias + sample_bias + pre_add) + residual.   (lns_conv2d)
+
+    pad = (top, bottom, left, right) on the virtual input; pad_mode = (mode_h, mode_w); virt = (Hv, Wv) nearest-resize
+    target (None: no resize); pro = (scale[B,C], shift[B,C], act) per-(sample,channel) affine applied to x first."""
+    Cout, Cin, KH, KW = filt.dims()
+    if Cin != x.C:
+        raise LnsError(f"conv2d: filter expects Cin={Cin}, activation has C={x.C}")
+    Hv, Wv = virt if virt is not None else (x.H, x.W)
+    pt, pb, pl, pr = pad
+    Hout = (Hv + pt + pb - dil * (KH - 1) - 1) // stride + 1
+    Wout = (Wv + pl + pr - dil * (KW - 1) - 1) // stride + 1
+    if engine is None:
+        engine = ENGINE_UMMA if _umma_ok(x, Cin, Cout, out_layout) else ENGINE_SIMT
+    if engine == ENGINE_UMMA and pro is not None:
+        # this engine gathers with cp.async (no transform in flight): materialise the normalised activation first
+        x = affine_act(x, pro[0], pro[1], pro[2])
+        pro = None
+    if out is None:
+        if out_dtype is None:
+            out_dtype = torch.float32 if out_layout == NCHW else act_dtype()
+        if out_layout == NCHW:
+            out = Act(torch.empty(x.B * Cout * Hout * Wout, dtype=out_dtype, device=x.t.device), x.B, Hout, Wout,
+                      Cout, layout=NCHW)
+        else:
+            out = Act.empty(x.B, Hout, Wout, Cout, out_dtype, x.t.device)
+    else:
+        if (out.B, out.H, out.W, out.C) != (x.B, Hout, Wout, Cout):
+            raise LnsError(f"conv2d: out shape {(out.B, out.H, out.W, out.C)} != {(x.B, Hout, Wout, Cout)}")
+    d = ConvDesc()
+    d.x, d.x_dtype, d.x_layout = x.t.data_ptr(), x.dtype, x.layout
+    d.B, d.Hin, d.Win, d.Cin, d.x_bstride = x.B, x.H, x.W, x.C, x.bstride
+    d.Hv, d.Wv = Hv, Wv
+    d.KH, d.KW, d.stride, d.dil, d.pad_t, d.pad_l = KH, KW, stride, dil, pt, pl
+    d.pad_mode_h, d.pad_mode_w = pad_mode
+    fmt = W_UMMA_BF16 if engine == ENGINE_UMMA else W_SIMT_F32
+    wbuf = filt.get(fmt)
+    d.w, d.w_format, d.engine = wbuf.data_ptr(), fmt, engine
+    bias = filt.bias() if use_bias else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.sample_bias = sample_bias.data_ptr() if sample_bias is not None else None
+    if pro is not None:
+        d.pro_scale = pro[0].data_ptr() if pro[0] is not None else None
+        d.pro_shift = pro[1].data_ptr() if pro[1] is not None else None
+        d.pro_act = pro[2]
+    d.act = act
+    if pre_add is not None:
+        d.pre_add, d.pre_add_dtype, d.pre_add_bstride = pre_add.t.data_ptr(), pre_add.dtype, pre_add.bstride
+    if residual is not None:
+        if (residual.B, residual.H, residual.W, residual.C) != (out.B, out.H, out.W, out.C):
+            raise LnsError("conv2d: residual shape mismatch")
+        d.residual, d.res_dtype, d.res_bstride = residual.t.data_ptr(), residual.dtype, residual.bstride
+    d.y, d.y_dtype, d.y_layout = out.t.data_ptr(), out.dtype, out.layout
+    d.Hout, d.Wout, d.Cout, d.y_bstride = Hout, Wout, Cout, out.bstride
+    rc = _C.lib().lns_conv2d(ctypes.byref(d), _stream())
+    check(rc, "lns_conv2d")
+    _state.launches += 1
+    return out
+
+
+# ---- normalisation ------------------------------------------------------------------------------------------
+def chan_stats(x):
+    """-> (partial [B,nchunk,C,2] fp32, nchunk)"""
+    nchunk = _C.lib().lns_chan_stats_chunks(x.H, x.W)
+    part = torch.empty(x.B * nchunk * x.C * 2, dtype=torch.float32, device=x.t.device)
+    rc = _C.lib().lns_chan_stats(_ptr(x.t), x.dtype, x.B, x.H, x.W, x.C, x.bstride, _ptr(part), _stream())
+    check(rc, "lns_chan_stats")
+    _state.launches += 1
+    return part, nchunk
+
+
+def group_norm_affine(x, groups, eps, gamma=None, beta=None, prescale=None):
+    """GroupNorm(groups) statistics of (x * prescale) folded with gamma/beta into per-(sample,channel) (scale, shift)."""
+    part, nchunk = chan_stats(x)
+    scale = torch.empty(x.B * x.C, dtype=torch.float32, device=x.t.device)
+    shift = torch.empty_like(scale)
+    g = gamma.detach().float().contiguous() if gamma is not None else None
+    b = beta.detach().float().contiguous() if beta is not None else None
+    rc = _C.lib().lns_norm_finalize(_ptr(part), x.B, nchunk, x.C, x.H * x.W, groups, float(eps), _ptr(g), _ptr(b),
+                                    _ptr(prescale), _ptr(scale), _ptr(shift), _stream())
+    check(rc, "lns_norm_finalize")
+    _state.launches += 1
+    return scale, shift
+
+
+def affine_act(x, scale, shift, act=ACT_NONE, out_dtype=None):
+    """y = act(x*scale[b,c] + shift[b,c]) as a new contiguous Act."""
+    out = x.like(dtype=out_dtype or x.t.dtype)
+    rc = _C.lib().lns_affine_act(_ptr(x.t), x.dtype, x.bstride, x.B, x.H * x.W, x.C, _ptr(scale), _ptr(shift), act,
+                                 _ptr(out.t), out.dtype, out.bstride, _stream())
+    check(rc, "lns_affine_act")
+    _state.launches += 1
+    return out
+
+
+def layernorm(x, gamma, beta, eps, pe=None, out_dtype=None):
+    """LayerNorm over C per pixel/token (+ pe[token]) -> new Act."""
+    assert x.contiguous and x.layout == NHWC
+    out = x.like(dtype=out_dtype or x.t.dtype)
+    g = gamma.detach().float().contiguous() if gamma is not None else None
+    b = beta.detach().float().contiguous() if beta is not None else None
+    rc = _C.lib().lns_layernorm(_ptr(x.t), x.dtype, x.B, x.H * x.W, x.C, _ptr(g), _ptr(b), float(eps), _ptr(pe),
+                                _ptr(out.t), out.dtype, _stream())
+    check(rc, "lns_layernorm")
+    _state.launches += 1
+    return out
+
+
+def channel_gate(x, gate):
+    assert x.contiguous and x.layout == NHWC
+    out = x.like()
+    rc = _C.lib().lns_channel_gate(_ptr(x.t), x.dtype, x.B, x.H * x.W, x.C, _ptr(gate), _ptr(out.t), out.dtype,
+                                   _stream())
+    check(rc, "lns_channel_gate")
+    _state.launches += 1
+    return out
+
+
+# ---- attention pieces -----------------------------------------------------------------------------------------
+def attention(qkv, heads, dh, scale, out_dtype=None):
+    """qkv: Act [B,H,W,3*heads*dh] (tokens = pixels) -> Act [B,H,W,heads*dh]"""
+    assert qkv.contiguous and qkv.C == 3 * heads * dh
+    out = qkv.like(C=heads * dh, dtype=out_dtype or qkv.t.dtype)
+    rc = _C.lib().lns_attention(_ptr(qkv.t), qkv.dtype, qkv.B, qkv.H * qkv.W, heads, dh, float(scale), _ptr(out.t),
+                                out.dtype, _stream())
+    check(rc, "lns_attention")
+    _state.launches += 1
+    return out
+
+
+def axis_mean(x, axis):
+    """axis 0: mean over H -> Act [B, W, 1, C] fp32; axis 1: mean over W -> Act [B, H, 1, C] fp32"""
+    keep = x.W if axis == 0 else x.H
+    out = Act.empty(x.B, keep, 1, x.C, torch.float32, x.t.device)
+    rc = _C.lib().lns_axis_mean(_ptr(x.t), x.dtype, x.B, x.H, x.W, x.C, x.bstride, axis, _ptr(out.t), _stream())
+    check(rc, "lns_axis_mean")
+    _state.launches += 1
+    return out
+
+
+def lowrank_kernel(qk, heads, d, cos_tab, sin_tab, scaling=1.0):
+    """qk: Act [B, n, 1, 2*heads*d] -> torch fp32 [B, heads, n, n]"""
+    assert qk.contiguous and qk.C == 2 * heads * d
+    n = qk.H * qk.W
+    K = torch.empty(qk.B, heads, n, n, dtype=torch.float32, device=qk.t.device)
+    rc = _C.lib().lns_lowrank_kernel(_ptr(qk.t), qk.dtype, qk.B, n, heads, d, _ptr(cos_tab), _ptr(sin_tab),
+                                     float(scaling), _ptr(K), _stream())
+    check(rc, "lns_lowrank_kernel")
+    _state.launches += 1
+    return K
+
+
+def axial_contract(u, K, heads, axis, out_dtype=None):
+    assert u.contiguous and u.layout == NHWC and u.C % heads == 0
+    out = u.like(dtype=out_dtype or u.t.dtype)
+    rc = _C.lib().lns_axial_contract(_ptr(u.t), u.dtype, u.B, u.H, u.W, heads, u.C // heads, _ptr(K), axis,
+                                     _ptr(out.t), out.dtype, _stream())
+    check(rc, "lns_axial_contract")
+    _state.launches += 1
+    return out
+
+
+# ---- misc ----------------------------------------------------------------------------------------------------
+def fourier_embedding(param, dim, max_period=10000.0):
+    """param: torch fp32 [B] on CUDA -> torch fp32 [B, dim]"""
+    _need_cuda(param, "fourier_embedding")
+    p = param.detach().float().contiguous()
+    out = torch.empty(p.shape[0], dim, dtype=torch.float32, device=p.device)
+    rc = _C.lib().lns_fourier_embedding(_ptr(p), p.shape[0], dim, float(max_period), _ptr(out), _stream())
+    check(rc, "lns_fourier_embedding")
+    _state.launches += 1
+    return out
+
+
+def rows_act(t):
+    """torch fp32 [B, C] -> Act [B,1,1,C] (no copy)"""
+    t = t.contiguous()
+    return Act(t, t.shape[0], 1, 1, t.shape[1])
+
+
+def spectral_conv2d(x, w_modes, m1, m2, Co, emb=None):
+    """x: Act NHWC [B,H,W,Ci]; w_modes: fp32 [2,m1,m2,Ci,Co,2]; emb: fp32 [B,m1,m2,2,2] or None -> Act fp32 [B,H,W,Co]"""
+    assert x.contiguous and x.layout == NHWC
+    nbytes = _C.lib().lns_spectral_work_bytes(x.B, x.H, x.W, x.C, Co, m1, m2)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=x.t.device)
+    out = Act.empty(x.B, x.H, x.W, Co, torch.float32, x.t.device)
+    rc = _C.lib().lns_spectral_conv2d(_ptr(x.t), x.dtype, x.B, x.H, x.W, x.C, Co, m1, m2, _ptr(w_modes), _ptr(emb),
+                                      _ptr(work), _ptr(out.t), _stream())
+    check(rc, "lns_spectral_conv2d")
+    _state.launches += 3
+    return out

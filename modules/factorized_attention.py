@@ -1,0 +1,126 @@
+"""Axial factorized attention -- drop-in for the reference's ``modules/factorized_attention.py``
+(``LowRankKernel`` :11-69, ``PoolingReducer`` :72-94, ``FABlock2D`` :97-159)."""
+import torch
+import torch.nn as nn
+
+from lns_b200 import ops
+
+from ._base import LnsModule, LnsError, conv_layer, filt_of, norm_affine
+from .embedding import RotaryEmbedding
+
+
+class LowRankKernel(LnsModule):
+    """K = rot(q) rot(k)^T per head along one axis, no softmax, no 1/sqrt(d) (reference :43-69)."""
+
+    def __init__(self, dim, dim_head, heads, use_rotary_emb=False, dropout=0, scaling=1, qk_norm=False):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        self.dim_head, self.heads = dim_head, heads
+        self.dropout = nn.Dropout(dropout) if dropout > 1e-6 else nn.Identity()
+        self.to_qk = nn.Linear(dim, dim_head * heads * 2, bias=False)
+        self.qk_norm = qk_norm
+        if qk_norm:
+            self.q_norm = nn.LayerNorm(dim_head, elementwise_affine=False)
+            self.k_norm = nn.LayerNorm(dim_head, elementwise_affine=False)
+        self.use_rotary_emb = use_rotary_emb
+        if use_rotary_emb:
+            self.pos_emb = RotaryEmbedding(dim_head)
+        self.scaling = scaling
+
+    def _tables(self, n, device):
+        """cos / sin [n, dim_head/2] for pos = linspace(0,1,n) (reference :47), cached per n."""
+        cache = self.__dict__.setdefault("_lns_rot", {})
+        key = (n, str(device), self.pos_emb.inv_freq._version if self.use_rotary_emb else 0)
+        if key not in cache:
+            if self.use_rotary_emb:
+                pos = torch.linspace(0, 1, n, device=device)  # fp32 like the reference
+                ang = self.pos_emb.angles(pos)
+                cache[key] = (ang.cos().float().contiguous(), ang.sin().float().contiguous())
+            else:
+                z = torch.zeros(n, self.dim_head // 2, device=device)
+                cache[key] = (torch.ones_like(z), z)
+        return cache[key]
+
+    def _fwd(self, u):
+        """u: Act [B, n, 1, dim] -> torch fp32 [B, heads, n, n]"""
+        if self.qk_norm:
+            raise LnsError("LowRankKernel: qk_norm=True is not on the rollout path")
+        n = u.H * u.W
+        qk = ops.conv2d(u, filt_of(self.to_qk), out_dtype=torch.float32)
+        cos_t, sin_t = self._tables(n, u.t.device)
+        return ops.lowrank_kernel(qk, self.heads, self.dim_head, cos_t, sin_t, self.scaling)
+
+
+class PoolingReducer(LnsModule):
+    """Linear -> mean over the other axis -> LN -> Linear -> GELU -> Linear (reference :72-94).  The bias-free input
+    linear commutes with the mean, so the mean is taken first (on the caller's side) and this block only sees
+    [B, n, 1, C] rows."""
+
+    def __init__(self, in_dim, hidden_dim, out_dim):
+        super().__init__()
+        self.to_in = nn.Linear(in_dim, hidden_dim, bias=False)
+        self.out_ffn = nn.Sequential(
+            nn.LayerNorm(hidden_dim),
+            nn.Linear(hidden_dim, hidden_dim * 2, bias=False),
+            nn.GELU(),
+            nn.Linear(hidden_dim * 2, out_dim, bias=True))
+
+    def _fwd(self, pooled):
+        f32 = torch.float32
+        h = ops.conv2d(pooled, filt_of(self.to_in), out_dtype=f32)
+        ln = self.out_ffn[0]
+        h = ops.layernorm(h, ln.weight, ln.bias, ln.eps)
+        h = ops.conv2d(h, filt_of(self.out_ffn[1]), act=ops.ACT_GELU, out_dtype=f32)
+        return ops.conv2d(h, filt_of(self.out_ffn[3]), out_dtype=f32)
+
+
+class _SwapAxes(nn.Module):
+    """Parameter-free placeholder for einops' Rearrange('b c nx ny -> b c ny nx') at index 0 of ``to_y`` -- keeps the
+    reducer at ``to_y.1`` so reference state_dict keys match."""
+
+    def forward(self, x):
+        return x.transpose(-1, -2)
+
+
+class FABlock2D(LnsModule):
+    """Factorized attention block (reference :97-159):
+        u = GN1(u); u_phi = in_proj(u) [heads*dim_head ch]; t = to_in(u)
+        u_x = reducer_x(mean_W t), u_y = reducer_y(mean_H t); K_x = kernel(u_x) [H,H], K_y = kernel(u_y) [W,W]
+        u_phi <- K_x (over H) then K_y (over W); InstanceNorm -> 1x1 -> GELU -> 1x1; + skip
+    """
+
+    def __init__(self, dim, dim_head, latent_dim, heads, dim_out, use_rope=True, kernel_multiplier=2, qk_norm=False):
+        super().__init__()
+        self.dim, self.latent_dim, self.heads = dim, latent_dim, heads
+        self.dim_head = dim_head
+        self.in_norm = nn.GroupNorm(1, dim)
+        self.in_proj = nn.Conv2d(dim, heads * dim_head, 1, 1, 0, bias=False)
+        self.to_in = nn.Sequential(nn.Conv2d(dim, dim, 1, 1, 0, bias=False))
+        self.to_x = nn.Sequential(PoolingReducer(dim, dim, latent_dim))
+        self.to_y = nn.Sequential(_SwapAxes(), PoolingReducer(dim, dim, latent_dim))
+        self.low_rank_kernel_x = LowRankKernel(latent_dim, dim_head * kernel_multiplier, heads,
+                                               use_rotary_emb=use_rope, qk_norm=qk_norm)
+        self.low_rank_kernel_y = LowRankKernel(latent_dim, dim_head * kernel_multiplier, heads,
+                                               use_rotary_emb=use_rope, qk_norm=qk_norm)
+        self.to_out = nn.Sequential(
+            nn.InstanceNorm2d(dim_head * heads),
+            nn.Conv2d(dim_head * heads, dim_out, 1, 1, 0, bias=False),
+            nn.GELU(),
+            nn.Conv2d(dim_out, dim_out, 1, 1, 0, bias=False))
+
+    def _fwd(self, u):
+        skip = u
+        s, t = norm_affine(u, self.in_norm)
+        un = ops.affine_act(u, s, t, ops.ACT_NONE)
+        u_phi = conv_layer(un, self.in_proj)
+        # mean over the other axis first (exact: to_in convs have no bias), then the two tiny linears
+        f32 = torch.float32
+        px = ops.conv2d(ops.axis_mean(un, axis=1), filt_of(self.to_in[0]), out_dtype=f32)   # rows indexed by H
+        py = ops.conv2d(ops.axis_mean(un, axis=0), filt_of(self.to_in[0]), out_dtype=f32)   # rows indexed by W
+        k_x = self.low_rank_kernel_x._fwd(self.to_x[0]._fwd(px))
+        k_y = self.low_rank_kernel_y._fwd(self.to_y[1]._fwd(py))
+        u_phi = ops.axial_contract(u_phi, k_x, self.heads, axis=0)
+        u_phi = ops.axial_contract(u_phi, k_y, self.heads, axis=1)
+        s, t = norm_affine(u_phi, self.to_out[0])
+        h = conv_layer(u_phi, self.to_out[1], pro=(s, t, ops.ACT_NONE), act=ops.ACT_GELU)
+        return conv_layer(h, self.to_out[3], residual=skip)
