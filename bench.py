@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- latent-rollout throughput (trajectory-steps/s) of the LNS hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ns2d|sw|twophase|twophase_cond]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, NCCL)
+
+One "step" = one full rollout of the per-GPU batch: autoencoder encode -> R autoregressive propagator steps -> decode of
+all R states (LatentDynamics.predict(x, R, to_x=True) of the reference), i.e. B*R trajectory-steps per GPU per step.
+Default workload = BASELINE.json's NS2d 64x64 large-batch rollout (config 5: R=20, B=1024 trajectories per GPU,
+trajectory-sharded, weak scaling), the configuration the metric's target is quoted on; other configs via --workload.
+
+Output: ONE JSON line (see the contract in the task description) with `value` (inputs resident in HBM, CUDA-graph
+replay, CUDA-event timing, max over ranks), `e2e` (same metric through the public API with pinned host buffers, H2D and
+D2H copies inside the timed region), `roofline` (dominant kernel = the tcgen05 3x3 implicit-GEMM conv, timed alone with
+CUDA events), `cpu_baseline` (the oracle port of the reference timed on the host cores), `clocks`, `gpu_launches`.
+`--impl reference` times the reference's CPU implementation (oracle port; the reference is pure Python/PyTorch) on the
+host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config, rollout steps R, trajectories per GPU, GFLOP per trajectory-step, label)
+    "ns2d": ("ns2d", 20, 1024, 1.4611, "NS2d 64x64 latent rollout, R=20, 1024 trajectories/GPU (BASELINE config 5)"),
+    "sw": ("sw", 20, 64, 8.5138, "shallow water 96x192 rollout, R=20, 64 trajectories/GPU (BASELINE config 2)"),
+    "twophase": ("twophase", 20, 128, 2.5532, "two-phase 61x121 rollout, R=20, 128 trajectories/GPU (BASELINE config 3)"),
+    "twophase_cond": ("twophase_cond", 50, 128, 2.4806,
+                      "two-phase conditional rollout, R=50, 128 trajectories/GPU (BASELINE config 4)"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ns2d", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="trajectories per GPU (default: workload's)")
+    ap.add_argument("--rollout-steps", type=int, default=None)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="skip the final all-gather of fields for N > 1")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ---- CPU reference (oracle port) ---------------------------------------------------------------------------------------
+def cpu_reference_throughput(workload, budget_s=20.0, min_runs=2, max_runs=5):
+    """trajectory-steps/s of the reference's CPU path (oracle port: same ATen CPU kernels in the same order as
+    LatentDynamics.predict) on all host cores, on a bounded sample (small batch, full R)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lns_oracle as O
+    from lns_b200.configs import get_config
+    from lns_b200.latent_dynamics import LatentDynamics
+    cfg_name, R, _, _, _ = WORKLOADS[workload]
+    cfg = get_config(cfg_name)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    sd = O.randomize_zero_init(LatentDynamics(cfg).state_dict())
+    B = {"ns2d": 8, "sw": 1, "twophase": 2, "twophase_cond": 1}[cfg_name]
+    x, param = O.make_inputs(cfg, B, seed=0)
+    t0 = time.perf_counter()
+    O.predict(sd, cfg, x, R, param=param, to_x=True)  # warm-up (also sizes the sample)
+    first = time.perf_counter() - t0
+    runs = max(min_runs, min(max_runs, int(budget_s / max(first, 1e-3))))
+    best = float("inf")
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        O.predict(sd, cfg, x, R, param=param, to_x=True)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": B * R / best, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port of LatentDynamics.predict, fp32, B={B}, R={R}, best of {runs} runs "
+                      f"({best:.2f} s each), torch {torch.__version__} CPU, {cores} threads"}
+
+
+# ---- clocks ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = max([int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---- dominant-kernel roofline ---------------------------------------------------------------------------------------------
+def conv_roofline(torch, ops, device, peaks, workload):
+    """Time the dominant kernel alone (tcgen05 implicit-GEMM 3x3 conv at the workload's largest layer) with CUDA events
+    on the launching stream; operands are larger than L2 so every launch streams from HBM."""
+    import math
+    shapes = {"ns2d": (64, 64, 64, 64, (1, 1)), "sw": (96, 192, 64, 64, (0, 1)),
+              "twophase": (61, 121, 64, 64, (0, 0)), "twophase_cond": (61, 121, 64, 64, (0, 0))}
+    H, W, Cin, Cout, modes = shapes[workload]
+    nb = max(8, (768 << 20) // (H * W * Cin * 2))  # ~768 MB of bf16 input: >> 126 MB L2
+    x = ops.Act(torch.randn(nb * H * W * Cin, device=device).bfloat16(), nb, H, W, Cin)
+    wt = torch.nn.Parameter(torch.randn(Cout, Cin, 3, 3, device=device) / math.sqrt(9 * Cin))
+    bs = torch.nn.Parameter(torch.zeros(Cout, device=device))
+    filt = ops.PackedFilter.of(wt, bs)
+    out = ops.Act.empty(nb, H, W, Cout, torch.bfloat16, device)
+    with ops.precision("bf16"):
+        for _ in range(3):
+            ops.conv2d(x, filt, pad=(1, 1, 1, 1), pad_mode=modes, out=out, engine=ops.ENGINE_UMMA)
+        torch.cuda.synchronize()
+        reps = 10
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            ops.conv2d(x, filt, pad=(1, 1, 1, 1), pad_mode=modes, out=out, engine=ops.ENGINE_UMMA)
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+    ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+    t = sum(ms) / len(ms) * 1e-3
+    flops = 2.0 * nb * H * W * Cout * 9 * Cin
+    achieved = flops / t / 1e12
+    peak = peaks["bf16_tflops"]  # burst figure: this kernel is timed alone
+    return {"bound": "tensor", "kernel": f"conv_umma_kernel<{Cout},4> 3x3 {Cin}->{Cout} @ {H}x{W}, batch {nb}",
+            "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+            "traffic": None, "avg_launch_ms": round(t * 1e3, 4), "peak_source": peaks["source"],
+            "hbm_gbs_at_algorithmic_bytes": round(nb * H * W * (Cin + Cout) * 2 / t / 1e9, 1)}
+
+
+# ---- main ---------------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    cfg_name, R, B, gflop_per_ts, label = WORKLOADS[args.workload]
+    R = args.rollout_steps or R
+    B = args.batch or B
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded sample per step; steps/warmup only scale the repeat count (the CPU path is batch-flat)
+        base = cpu_reference_throughput(args.workload, budget_s=min(60.0, 6.0 * max(1, args.steps)))
+        line = {"metric": "latent rollout trajectory-steps/sec", "impl": "reference", "value": round(base["value"], 3),
+                "unit": "trajectory-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": label, "rollout_steps": R},
+                "cpu_baseline": base,
+                "e2e": {"value": round(base["value"], 3), "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from lns_b200 import ops
+    from lns_b200.configs import get_config
+    from lns_b200.dist import gather_fields, init_from_env
+    from lns_b200.latent_dynamics import LatentDynamics
+    from lns_b200.rollout import Rollout
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lns_oracle as O  # only for seeded synthetic inputs / zero-init redraw and the cpu_baseline leg
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU path; use --impl reference for the CPU baseline)")
+    rank, local, world = init_from_env("nccl")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    peaks = load_peaks()
+
+    cfg = get_config(cfg_name)
+    torch.manual_seed(1234)
+    model = LatentDynamics(cfg).eval()
+    model.load_state_dict(O.randomize_zero_init(model.state_dict()))
+    model = model.to(device)
+    x_cpu, p_cpu = O.make_inputs(cfg, B, seed=rank)
+    x_pin = x_cpu.pin_memory()
+    p_pin = p_cpu.pin_memory() if p_cpu is not None else None
+    x_dev = x_cpu.to(device)
+    p_dev = p_cpu.to(device) if p_cpu is not None else None
+
+    ro = Rollout(model, batch=B, steps=R, to_x=True, precision=args.precision, use_graph=True)
+    with torch.no_grad():
+        ro.build()
+        ro(x_dev, p_dev)
+    torch.cuda.synchronize()
+    gather = world > 1 and not args.no_gather
+
+    def one_step():
+        out = ro(x_dev, p_dev)
+        if gather:
+            return gather_fields(out, B * world)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * B * R * args.steps / (elapsed_ms * 1e-3)
+
+    # end to end through the public API: pinned host input -> H2D -> rollout -> D2H of the predicted fields
+    out_host = torch.empty((B, R, ro.C, ro.Ly, ro.Lx), dtype=torch.float32).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        xd = x_pin.to(device, non_blocking=True)
+        pd = p_pin.to(device, non_blocking=True) if p_pin is not None else None
+        out = ro(xd, pd)
+        out_host.copy_(out, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * R * e2e_steps / (e2e_ms * 1e-3)
+    h2d = x_pin.numel() * 4 + (p_pin.numel() * 4 if p_pin is not None else 0)
+    d2h = out_host.numel() * 4
+
+    if rank == 0:
+        roof = conv_roofline(torch, ops, device, peaks, args.workload) if args.precision == "bf16" else None
+        tflops = value * gflop_per_ts / 1e3
+        line = {
+            "metric": "latent rollout trajectory-steps/sec", "value": round(value, 1), "unit": "trajectory-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": label, "rollout_steps": R, "trajectories_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"trajectory-sharded x{world}" + (", final all-gather of fields" if gather else ""),
+                       "l2": "per-step working set (activations) is far larger than the 126 MB L2; no explicit flush",
+                       "cuda_graph": True, "random_init_weights_seed": 1234},
+            "whole_path_tflops_per_gpu": round(tflops / world, 2),
+            "whole_path_frac_of_bf16_sustained": round(tflops / world / peaks["bf16_tflops_sustained"], 4),
+            "e2e": {"value": round(e2e_value, 1), "unit": "trajectory-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(ro.launches_per_call * args.steps),
+            "launches_per_step": int(ro.launches_per_call),
+            "clocks": clocks, "roofline": roof,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_throughput(args.workload, budget_s=15.0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

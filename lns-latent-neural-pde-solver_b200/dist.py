@@ -1,0 +1,79 @@
+"""Trajectory-sharded multi-GPU rollout: one process per GPU (torch.distributed, NCCL over NVLink 5 / NVSwitch).
+
+Trajectories never interact (every normalisation on the path is per sample, eval mode), so rank r
+simply rolls out its own contiguous slice of the batch with the single-GPU engine -- no per-step communication.  The
+only collective is the final all-gather of the predicted fields.  Host-side logic here is backend agnostic and is
+covered by world_size-2 gloo tests on CPU (tests/test_dist_cpu.py)."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(batch, rank, world):
+    """Contiguous, as-even-as-possible slice [lo, hi) of the trajectories owned by `rank` (ragged batches allowed)."""
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, local, world
+
+
+def gather_fields(local, batch, group=None):
+    """All-gather per-rank results [b_r, ...] (b_r from shard_bounds) into the full [batch, ...] tensor on every rank.
+    Equal shards use one all_gather_into_tensor; ragged shards pad to the largest shard."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = [shard_bounds(batch, r, world) for r in range(world)]
+    counts = [hi - lo for lo, hi in sizes]
+    tail = tuple(local.shape[1:])
+    if len(set(counts)) == 1:
+        out = torch.empty((batch,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    mx = max(counts)
+    padded = torch.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    buf = torch.empty((world * mx,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, padded, group=group)
+    return torch.cat([buf[r * mx:r * mx + counts[r]] for r in range(world)], 0)
+
+
+class ShardedRollout:
+    """Rolls out this rank's slice of a global batch and (optionally) all-gathers the fields."""
+
+    def __init__(self, model, global_batch, steps, to_x=True, precision=None, use_graph=True, group=None, **kw):
+        from .rollout import Rollout
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.global_batch = global_batch
+        self.lo, self.hi = shard_bounds(global_batch, self.rank, self.world)
+        self.local = Rollout(model, batch=self.hi - self.lo, steps=steps, to_x=to_x, precision=precision,
+                             use_graph=use_graph, **kw)
+
+    def __call__(self, x_global_or_local, param=None, gather=True):
+        x = x_global_or_local
+        if x.shape[0] == self.global_batch and self.world > 1:
+            x = x[self.lo:self.hi]
+            if param is not None:
+                param = param[self.lo:self.hi]
+        out = self.local(x, param)
+        return gather_fields(out, self.global_batch, self.group) if gather else out

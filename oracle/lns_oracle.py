@@ -1,0 +1,456 @@
+"""TEST INFRASTRUCTURE -- CPU restatement of the reference's latent-rollout algorithm.
+
+This file is the ORACLE the CUDA path is checked against.  It is imported only by ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs (``cpu_baseline`` / ``--impl reference``); the product
+(``modules/``, ``lns_b200/``) never imports it and has no CPU fallback.
+
+What it is: a functional restatement, on plain ``state_dict`` tensors, of
+``LatentDynamics.predict(x, steps, to_x)`` of BaratiLab/LNS-Latent-Neural-PDE-Solver for its four stage-2
+configurations.  All arithmetic of the reference lives in PyTorch library calls (conv2d, group_norm, softmax, einsum,
+rfft2, interpolate -- versions unpinned by the reference); the restatement calls the same ATen CPU operators in the
+same order, so it runs in fp32 (like the reference) or fp64 (ground truth).  Every function cites the reference
+file:line it follows.
+
+Pinning: the reference ships no tests, golden vectors or checkpoints ("parity unpinned by the reference").  The
+oracle is pinned instead against OUTPUTS OF THE REFERENCE ITSELF: ``oracle/make_golden.py`` imports the unmodified
+reference from /root/reference (through ``oracle/ref_shims.py``) in the build container, runs ``predict`` on seeded
+inputs, and commits the results under ``tests/golden/``; ``tests/test_oracle.py`` checks this file against them.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------------------
+class SD:
+    """Prefix view of a state_dict: SD(sd, 'vq_ae.encoder.model.3.')['block.2.weight']"""
+
+    def __init__(self, sd, prefix=""):
+        self.sd, self.prefix = sd, prefix
+
+    def __getitem__(self, k):
+        return self.sd[self.prefix + k]
+
+    def get(self, k):
+        return self.sd.get(self.prefix + k)
+
+    def sub(self, p):
+        return SD(self.sd, self.prefix + p + ".")
+
+    def has(self, k):
+        return (self.prefix + k) in self.sd
+
+    def has_prefix(self, p):
+        q = self.prefix + p + "."
+        return any(k.startswith(q) for k in self.sd)
+
+
+def swish(x):  # modules/basics.py:27-29
+    return x * torch.sigmoid(x)
+
+
+def pad2d(x, p_h, p_w, mode_h, mode_w):
+    """mode 'circular' | 'zeros' per axis (W first, then H, like HalfPeriodicConv2d.pad; order is irrelevant)."""
+    if p_w:
+        x = F.pad(x, (p_w, p_w, 0, 0), mode="circular") if mode_w == "circular" else F.pad(x, (p_w, p_w, 0, 0))
+    if p_h:
+        x = F.pad(x, (0, 0, p_h, p_h), mode="circular") if mode_h == "circular" else F.pad(x, (0, 0, p_h, p_h))
+    return x
+
+
+def conv3(x, w, b, modes, dilation=1, stride=1):
+    """3x3 conv, padding = dilation, per-axis padding mode (nn.Conv2d padding_mode / HalfPeriodicConv2d)."""
+    x = pad2d(x, dilation, dilation, modes[0], modes[1])
+    return F.conv2d(x, w, b, stride=stride, dilation=dilation)
+
+
+def conv1(x, w, b=None):
+    return F.conv2d(x, w, b)
+
+
+def gn(x, s, groups, eps):
+    return F.group_norm(x, groups, s["weight"], s["bias"], eps)
+
+
+def gn32(x, s):  # basics.GroupNorm: 32 groups, eps 1e-6 (modules/basics.py:18-24)
+    return F.group_norm(x, 32, s["gn.weight"], s["gn.bias"], 1e-6)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# blocks
+# ------------------------------------------------------------------------------------------------------------------
+def residual_block(x, s, modes):
+    """modules/basics.py:224-276 (state keys block.{0,3}.gn.*, block.{2,5}.*, channel_up.*)"""
+    h = conv3(swish(gn32(x, s.sub("block.0"))), s["block.2.weight"], s["block.2.bias"], modes)
+    h = conv3(swish(gn32(h, s.sub("block.3"))), s["block.5.weight"], s["block.5.bias"], modes)
+    skip = conv1(x, s["channel_up.weight"], s["channel_up.bias"]) if s.has("channel_up.weight") else x
+    return skip + h
+
+
+def hp_res_block(x, s, modes):
+    """modules/autoencoder2d_half_periodic.py:77-103"""
+    skip = conv1(x, s["channel_up.weight"], s["channel_up.bias"]) if s.has("channel_up.weight") else x
+    h = conv3(swish(gn32(x, s.sub("norm_act1.norm_act.0"))), s["conv1.weight"], s["conv1.bias"], modes)
+    h = conv3(swish(gn32(h, s.sub("norm_act2.norm_act.0"))), s["conv2.weight"], s["conv2.bias"], modes)
+    return h + skip
+
+
+def downsample(x, s, modes):
+    """modules/basics.py:302-328: circular -> pad (1,1,1,1) circular; zeros -> pad (0,1,0,1) constant; conv s2 p0"""
+    if modes[0] == "circular":
+        x = F.pad(x, (1, 1, 1, 1), mode="circular")
+    else:
+        x = F.pad(x, (0, 1, 0, 1))
+    return F.conv2d(x, s["conv_layer.weight"], s["conv_layer.bias"], stride=2)
+
+
+def upsample_block(x, s, modes):
+    """modules/basics.py:279-299 (also UpSampleBlock2D, autoencoder2d_half_periodic.py:55-65)"""
+    x = F.interpolate(x, scale_factor=2.0)
+    return conv3(x, s["conv_layer.weight"], s["conv_layer.bias"], modes)
+
+
+def sa_block(x, s, heads=8):
+    """modules/basics.py:331-404"""
+    b, c, hh, ww = x.shape
+    t = x.view(b, c, -1).transpose(1, 2).contiguous()
+    t_in = t
+    t = F.layer_norm(t, (c,), s["ln.weight"], s["ln.bias"], 1e-5)
+    if s.has("pe"):
+        t = t + s["pe"][:, :t.shape[1]]
+    q = F.linear(t, s["to_q.weight"])
+    k = F.linear(t, s["to_k.weight"])
+    v = F.linear(t, s["to_v.weight"], s["to_v.bias"])
+    d = q.shape[-1] // heads
+
+    def split(u):
+        return u.view(b, -1, heads, d).transpose(1, 2)
+    q, k, v = split(q), split(k), split(v)
+    attn = torch.einsum("bhid,bhjd->bhij", q, k) * (d ** (-0.5))
+    attn = F.softmax(attn, dim=-1)
+    out = torch.einsum("bhij,bhjd->bhid", attn, v).transpose(1, 2).reshape(b, -1, heads * d)
+    out = t_in + F.linear(out, s["proj_out.weight"], s["proj_out.bias"])
+    return out.transpose(1, 2).reshape(b, c, hh, ww)
+
+
+def _rotary(t, freqs):  # modules/embedding.py:179-186
+    t1, t2 = t.chunk(2, dim=-1)
+    return t * freqs.cos() + torch.cat((-t2, t1), dim=-1) * freqs.sin()
+
+
+def low_rank_kernel(u, s, heads=8):
+    """modules/factorized_attention.py:43-69; rotary: modules/embedding.py:163-176 (min_freq 1/64, scale 1)"""
+    b, n, _ = u.shape
+    pos = torch.linspace(0, 1, n).view(1, n)  # fp32 by construction in the reference
+    qk = F.linear(u, s["to_qk.weight"])
+    q, k = qk.split(qk.shape[-1] // 2, dim=-1)
+    d = q.shape[-1] // heads
+    q = q.view(b, n, heads, d).transpose(1, 2)
+    k = k.view(b, n, heads, d).transpose(1, 2)
+    inv_freq = s["pos_emb.inv_freq"]
+    tt = pos.type_as(inv_freq) * 64.0
+    fr = torch.einsum("...i,j->...ij", tt, inv_freq)
+    fr = torch.cat((fr, fr), dim=-1)[:, None]  # [1,1,n,d]
+    q, k = _rotary(q, fr), _rotary(k, fr)
+    return torch.einsum("bhid,bhjd->bhij", q, k)
+
+
+def pooling_reducer(x, s):
+    """modules/factorized_attention.py:72-94; x: [b c n m], pools m"""
+    t = F.linear(x.permute(0, 2, 3, 1), s["to_in.weight"]).mean(dim=2)
+    t = F.layer_norm(t, (t.shape[-1],), s["out_ffn.0.weight"], s["out_ffn.0.bias"], 1e-5)
+    t = F.gelu(F.linear(t, s["out_ffn.1.weight"]))
+    return F.linear(t, s["out_ffn.3.weight"], s["out_ffn.3.bias"])
+
+
+def fa_block(u, s, heads=8):
+    """modules/factorized_attention.py:144-159"""
+    skip = u
+    u = F.group_norm(u, 1, s["in_norm.weight"], s["in_norm.bias"], 1e-5)
+    u_phi = conv1(u, s["in_proj.weight"])
+    u = conv1(u, s["to_in.0.weight"])
+    u_x = pooling_reducer(u, s.sub("to_x.0"))
+    u_y = pooling_reducer(u.transpose(-1, -2), s.sub("to_y.1"))
+    k_x = low_rank_kernel(u_x, s.sub("low_rank_kernel_x"), heads)
+    k_y = low_rank_kernel(u_y, s.sub("low_rank_kernel_y"), heads)
+    b, hc, hh, ww = u_phi.shape
+    u_phi = u_phi.view(b, heads, hc // heads, hh, ww)
+    u_phi = torch.einsum("bhij,bhcjm->bhcim", k_x, u_phi)
+    u_phi = torch.einsum("bhlm,bhcim->bhcil", k_y, u_phi)
+    u_phi = u_phi.reshape(b, hc, hh, ww)
+    h = F.instance_norm(u_phi, eps=1e-5)
+    h = conv1(F.gelu(conv1(h, s["to_out.1.weight"])), s["to_out.3.weight"])
+    return h + skip
+
+
+def spectral_conv2d(x, s, emb12=None):
+    """modules/basics.py:129-148 and modules/fourier_cond.py:52-81 (emb12: complex [B,m1,m2,2])"""
+    w1 = torch.view_as_complex(s["weights1"].contiguous())
+    w2 = torch.view_as_complex(s["weights2"].contiguous())
+    m1, m2 = w1.shape[2], w1.shape[3]
+    x_ft = torch.fft.rfft2(x)
+    out_ft = torch.zeros(x.shape[0], w1.shape[1], x.size(-2), x.size(-1) // 2 + 1, dtype=x_ft.dtype)
+    a, b = x_ft[:, :, :m1, :m2], x_ft[:, :, -m1:, :m2]
+    if emb12 is not None:
+        a = a * emb12[..., 0].unsqueeze(1)
+        b = b * emb12[..., 1].unsqueeze(1)
+    out_ft[:, :, :m1, :m2] = torch.einsum("bixy,ioxy->boxy", a, w1)
+    out_ft[:, :, -m1:, :m2] = torch.einsum("bixy,ioxy->boxy", b, w2)
+    return torch.fft.irfft2(out_ft, s=(x.size(-2), x.size(-1)))
+
+
+def fourier_basic_block(x, s):
+    """modules/basics.py:531-583 (gelu, residual)"""
+    return x + F.gelu(spectral_conv2d(x, s.sub("fourier")) + conv1(x, s["conv.weight"], s["conv.bias"]))
+
+
+def cond_fourier_basic_block(x, emb, s):
+    """modules/fourier_cond.py:84-118"""
+    fl = s.sub("fourier.cond_emb")
+    w = s["fourier.weights1"]
+    m1, m2 = w.shape[2], w.shape[3]
+    h = torch.einsum("tc,cm->tm", emb, fl["weights"]) + fl["bias"]
+    emb12 = torch.view_as_complex(h.reshape(emb.shape[0], m1, m2, 2, 2).contiguous())
+    x1 = spectral_conv2d(x, s.sub("fourier"), emb12)
+    x2 = conv1(x, s["conv.weight"], s["conv.bias"])
+    e = F.linear(emb, s["cond_emb.weight"], s["cond_emb.bias"])[..., None, None]
+    return x + F.gelu(x1 + x2 + e)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# autoencoders
+# ------------------------------------------------------------------------------------------------------------------
+def _modes(cfg):
+    kind = cfg.kind
+    if kind == "sw":
+        return ("zeros", "circular") if cfg.periodic_direction == "x" else ("circular", "zeros")
+    return ("circular", "circular") if cfg.is_periodic else ("zeros", "zeros")
+
+
+def _layer_kinds(sd_view, n_layers_hint=64):
+    """Classify nn.Sequential entries of an Encoder/Decoder by their state_dict keys."""
+    kinds = {}
+    for i in range(n_layers_hint):
+        p = str(i)
+        if sd_view.has(p + ".block.2.weight"):
+            kinds[i] = "res"
+        elif sd_view.has(p + ".conv1.weight") and sd_view.has(p + ".norm_act1.norm_act.0.gn.weight"):
+            kinds[i] = "hpres"
+        elif sd_view.has(p + ".to_q.weight"):
+            kinds[i] = "sa"
+        elif sd_view.has(p + ".in_proj.weight") and sd_view.has(p + ".low_rank_kernel_x.to_qk.weight"):
+            kinds[i] = "fa"
+        elif sd_view.has(p + ".fourier.weights1"):
+            kinds[i] = "fourier"
+        elif sd_view.has(p + ".conv_layer.weight"):
+            kinds[i] = "resample"
+        elif sd_view.has(p + ".gn.weight"):
+            kinds[i] = "gn32"
+        elif sd_view.has(p + ".weight") and sd_view[p + ".weight"].dim() == 4:
+            kinds[i] = "conv"
+        elif sd_view.has(p + ".weight") and sd_view[p + ".weight"].dim() == 1:
+            kinds[i] = "gn"
+    return kinds
+
+
+def encode(sd, cfg, x, ae="vq_ae"):
+    """SimpleAutoencoder.encode: modules/autoencoder2d.py:174-177 (Encoder :16-72),
+    autoencoder2d_half_periodic.py:106-144, autoencoder2d_nonsquared.py:17-68"""
+    s = SD(sd, ae + ".encoder.model.")
+    modes = _modes(cfg)
+    kinds = _layer_kinds(s)
+    n = max(kinds) + 1
+    h = swish(conv1(x, s["0.weight"], s["0.bias"]))  # layers 0 (1x1) and 1 (Swish)
+    n_down = 0
+    for i in range(2, n):
+        k = kinds.get(i)
+        sub = s.sub(str(i))
+        if k == "conv":
+            w = sub["weight"]
+            h = conv3(h, w, sub["bias"], modes) if w.shape[-1] == 3 else conv1(h, w, sub["bias"])
+        elif k == "res":
+            h = residual_block(h, sub, modes)
+        elif k == "hpres":
+            h = hp_res_block(h, sub, modes)
+        elif k == "resample":  # encoder: always a down-sampling block
+            if cfg.kind == "sw":  # DownSampleBlock2d: HalfPeriodicConv2d stride 2 pad 1 (half_periodic.py:68-74)
+                h = conv3(h, sub["conv_layer.weight"], sub["conv_layer.bias"], modes, stride=2)
+            else:
+                h = downsample(h, sub, modes)
+            n_down += 1
+        elif k == "gn32":
+            h = swish(gn32(h, sub))  # GroupNorm followed by Swish (the parameter-free Swish has no keys)
+        elif k == "fourier":
+            h = fourier_basic_block(h, sub)
+        elif k == "sa":
+            h = sa_block(h, sub)
+        elif k == "fa":
+            h = fa_block(h, sub)
+        elif k is None:
+            continue
+        else:
+            raise RuntimeError(f"encoder layer {i}: unexpected kind {k}")
+    q = SD(sd, ae + ".quant_conv.")
+    return conv1(h, q["weight"], q["bias"])
+
+
+def decode(sd, cfg, z, ae="vq_ae"):
+    """SimpleAutoencoder.decode: modules/autoencoder2d.py:179-182 (Decoder :75-156),
+    autoencoder2d_half_periodic.py:147-230, autoencoder2d_nonsquared.py:148-247"""
+    pq = SD(sd, ae + ".post_quant_conv.")
+    h = conv1(z, pq["weight"], pq["bias"])
+    s = SD(sd, ae + ".decoder.model.")
+    modes = _modes(cfg)
+    kinds = _layer_kinds(s)
+    n = max(kinds) + 1
+    # the nn.Upsample(size=(Ly,Lx)) has no keys: it sits right after the LAST up-sampling block / last block of the
+    # channel loop, i.e. directly before the conv that follows the last keyed block-type entry
+    block_idx = [i for i in range(n) if kinds.get(i) in ("res", "hpres", "fa", "sa", "resample")]
+    last_block = max(block_idx)
+    i = 0
+    while i < n:
+        k = kinds.get(i)
+        sub = s.sub(str(i))
+        if k == "conv":
+            if i == last_block + 2:  # index last_block+1 is the key-less nn.Upsample
+                h = F.interpolate(h, size=(cfg.Ly, cfg.Lx), mode="nearest")
+            w = sub["weight"]
+            h = conv3(h, w, sub["bias"], modes) if w.shape[-1] == 3 else conv1(h, w, sub["bias"])
+        elif k == "res":
+            h = residual_block(h, sub, modes)
+        elif k == "hpres":
+            h = hp_res_block(h, sub, modes)
+        elif k == "resample":
+            h = upsample_block(h, sub, modes)
+        elif k == "sa":
+            h = sa_block(h, sub)
+        elif k == "fa":
+            h = fa_block(h, sub)
+        elif k == "fourier":
+            h = fourier_basic_block(h, sub)
+        elif k == "gn32":  # GroupNorm(32) + Swish before the output projection (SW / two-phase decoders)
+            h = swish(gn32(h, sub))
+        elif k == "gn":    # nn.GroupNorm(8, C) eps 1e-5 + Swish (NS2d decoder, modules/autoencoder2d.py:149-150)
+            h = swish(F.group_norm(h, 8, sub["weight"], sub["bias"], 1e-5))
+        i += 1
+    return h
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# propagators
+# ------------------------------------------------------------------------------------------------------------------
+def propagator_step(sd, cfg, z, cond_emb=None, prefix="propagator."):
+    """SimpleCNN.forward: train_stage2_ns2d.py:82-87 (blocks :25-53); conditional:
+    train_stage2_twophase_conditional.py:114-121 (blocks :66-75)"""
+    s = SD(sd, prefix)
+    modes = _modes(cfg) if cfg.kind != "twophase_cond" else ("zeros", "zeros")
+    dil = cfg.dilation
+    h = conv1(z, s["in_proj.weight"], s["in_proj.bias"])
+    for i in range(cfg.prop_n_block):
+        b = s.sub(f"net.{i}")
+        if cond_emb is None:
+            t = F.group_norm(h, 1, b["conv.0.weight"], b["conv.0.bias"], 1e-5)
+            t = F.gelu(conv3(t, b["conv.1.weight"], b["conv.1.bias"], modes))
+            t = F.gelu(conv3(t, b["conv.3.weight"], b["conv.3.bias"], modes, dilation=dil))
+            t = conv3(t, b["conv.5.weight"], b["conv.5.bias"], modes)
+            h = h + t
+        else:
+            emb_out = F.linear(cond_emb, b["cond_emb.weight"], b["cond_emb.bias"])[..., None, None]
+            t = F.group_norm(h, 1, b["conv1.0.weight"], b["conv1.0.bias"], 1e-5)
+            t = F.gelu(conv3(t, b["conv1.1.weight"], b["conv1.1.bias"], modes))
+            t = conv3(t, b["conv1.3.weight"], b["conv1.3.bias"], modes, dilation=dil) + emb_out
+            t = F.gelu(F.group_norm(t, 1, b["cond_conv1.0.weight"], b["cond_conv1.0.bias"], 1e-5))
+            h = h + conv3(t, b["cond_conv1.2.weight"], b["cond_conv1.2.bias"], modes)
+            g = F.group_norm(emb_out, 1, b["cond_conv2.0.weight"], b["cond_conv2.0.bias"], 1e-5)
+            g = conv1(F.gelu(conv1(g, b["cond_conv2.1.weight"], b["cond_conv2.1.bias"])),
+                      b["cond_conv2.3.weight"], b["cond_conv2.3.bias"])
+            h_in = h * (1.0 + g)
+            t = F.group_norm(h_in, 1, b["ffn.0.weight"], b["ffn.0.bias"], 1e-5)
+            h = h + conv1(F.gelu(conv1(t, b["ffn.1.weight"])), b["ffn.3.weight"])
+            continue
+        t = F.group_norm(h, 1, b["ffn.0.weight"], b["ffn.0.bias"], 1e-5)
+        h = h + conv1(F.gelu(conv1(t, b["ffn.1.weight"])), b["ffn.3.weight"])
+    h = gn32(h, s.sub("out_proj.0"))
+    return conv1(h, s["out_proj.1.weight"], s["out_proj.1.bias"])
+
+
+def fourier_embedding(t, dim, max_period=10000):
+    """modules/cond_utils.py:19-38"""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def cond_embedding(sd, cfg, param, dtype, prefix="propagator."):
+    """train_stage2_twophase_conditional.py:116 (cond_emb_proj MLP on the sinusoidal embedding)"""
+    s = SD(sd, prefix)
+    e = fourier_embedding(param, cfg.latent_dim).to(dtype)
+    e = F.gelu(F.linear(e, s["cond_emb_proj.0.weight"], s["cond_emb_proj.0.bias"]))
+    return F.linear(e, s["cond_emb_proj.2.weight"], s["cond_emb_proj.2.bias"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the rollout
+# ------------------------------------------------------------------------------------------------------------------
+def ae_name(cfg):
+    return "ae" if cfg.kind == "twophase_cond" else "vq_ae"
+
+
+@torch.no_grad()
+def predict(sd, cfg, x, steps, param=None, to_x=True, return_latents=False):
+    """LatentDynamics.predict: train_stage2_ns2d.py:143-158 / train_stage2_twophase_conditional.py:177-193.
+    (The reference's z.squeeze() at B == 1 is not mirrored: B >= 2 semantics are used for every B.)"""
+    ae = ae_name(cfg)
+    z = encode(sd, cfg, x, ae)
+    cond = cond_embedding(sd, cfg, param, x.dtype) if cfg.kind == "twophase_cond" else None
+    outs, lats = [], []
+    for _ in range(steps):
+        z = propagator_step(sd, cfg, z, cond)
+        lats.append(z)
+        if to_x:
+            outs.append(decode(sd, cfg, z, ae))
+    res = torch.stack(outs if to_x else lats, dim=1)
+    if return_latents:
+        return res, torch.stack(lats, dim=1)
+    return res
+
+
+def rel_l2(a, b, eps=1e-8):
+    """relative_lp_loss (training_utils.py:9-23) with p=2, reduced over (C,H,W): per-sample ||a-b|| / ||b||"""
+    dims = tuple(range(-3, 0))
+    num = ((a.double() - b.double()) ** 2).sum(dims)
+    den = (b.double() ** 2).sum(dims).clamp_min(eps)
+    return (num / den).sqrt()
+
+
+def to_dtype(sd, dtype):
+    return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+def randomize_zero_init(sd, seed=4321, std=0.02):
+    """The conditional propagator zero-initialises two convs per block (zero_module,
+    train_stage2_twophase_conditional.py:47-58); with exact zeros the conditional branches would be multiplied away and
+    a parity test would be vacuous.  Redraw every all-zero *weight* deterministically."""
+    g = torch.Generator().manual_seed(seed)
+    out = dict(sd)
+    for k in sorted(sd):
+        v = sd[k]
+        if v.is_floating_point() and v.numel() > 1 and ("cond_conv" in k) and float(v.abs().max()) == 0.0:
+            out[k] = torch.randn(v.shape, generator=g, dtype=torch.float32).to(v.dtype) * std
+    return out
+
+
+def make_inputs(cfg, batch, seed=0):
+    """Seeded synthetic inputs: x ~ N(0,1); vof channel (two-phase ch 3) and param ~ U[0,1]."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, cfg.in_channels, cfg.Ly, cfg.Lx, generator=g)
+    param = None
+    if cfg.kind in ("twophase", "twophase_cond"):
+        x[:, 3] = torch.rand(batch, cfg.Ly, cfg.Lx, generator=g)
+    if cfg.kind == "twophase_cond":
+        param = torch.rand(batch, generator=g)
+    return x, param

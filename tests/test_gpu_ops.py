@@ -1,0 +1,323 @@
+"""GPU parity tests of the individual C-ABI kernels (called through lns_b200.ops -> ctypes -> liblns_b200.so) against
+fp64 PyTorch CPU references of the same op.  fp32 results must agree to <= 1e-5 relative L2 (the fp32 validation
+path's bar), bf16 results to bf16 rounding."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def relerr(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def ops_mod():
+    from lns_b200 import ops
+    return ops
+
+
+def nhwc(x):  # NCHW cpu tensor -> contiguous NHWC cuda fp32 flat
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def act_from(x_nchw, dtype=torch.float32):
+    ops = ops_mod()
+    B, C, H, W = x_nchw.shape
+    t = nhwc(x_nchw).to(DEV).to(dtype).reshape(-1)
+    return ops.Act(t, B, H, W, C)
+
+
+def act_to_nchw(a):
+    return a.to_torch_nhwc().float().permute(0, 3, 1, 2).cpu()
+
+
+def ref_conv(x, w, b, stride, dil, pad, modes, virt=None):
+    """fp64 reference of lns_conv2d's index map using torch ops."""
+    x = x.double()
+    if virt is not None:
+        x = F.interpolate(x, size=virt, mode="nearest")
+    pt, pb, pl, pr = pad
+    if modes[1] == 1:
+        x = F.pad(x, (pl, pr, 0, 0), mode="circular")
+    else:
+        x = F.pad(x, (pl, pr, 0, 0))
+    if modes[0] == 1:
+        x = F.pad(x, (0, 0, pt, pb), mode="circular")
+    else:
+        x = F.pad(x, (0, 0, pt, pb))
+    return F.conv2d(x, w.double(), None if b is None else b.double(), stride=stride, dilation=dil)
+
+
+class Holder:
+    """minimal nn.Conv2d-like parameter holder for PackedFilter.of"""
+
+    def __init__(self, w, b):
+        self.weight = torch.nn.Parameter(w.to(DEV))
+        self.bias = torch.nn.Parameter(b.to(DEV)) if b is not None else None
+
+
+CONV_CASES = [
+    # B, Cin, Cout, H, W, k, stride, dil, pad(t,b,l,r), modes(h,w), virt
+    (2, 64, 64, 8, 8, 3, 1, 1, (1, 1, 1, 1), (1, 1), None),         # circular
+    (2, 128, 128, 8, 8, 3, 1, 2, (2, 2, 2, 2), (1, 1), None),       # circular, dilation 2 (NS2d propagator)
+    (3, 128, 128, 7, 15, 3, 1, 2, (2, 2, 2, 2), (0, 0), None),      # zeros, dilation 2, ragged (two-phase)
+    (2, 128, 128, 12, 24, 3, 1, 3, (3, 3, 3, 3), (0, 1), None),     # half periodic, dilation 3 (shallow water)
+    (2, 64, 64, 16, 16, 3, 2, 1, (1, 1, 1, 1), (1, 1), None),       # circular down-sample
+    (2, 64, 64, 15, 30, 3, 2, 1, (0, 1, 0, 1), (0, 0), None),       # zeros down-sample pad (0,1,0,1)
+    (2, 64, 64, 12, 24, 3, 2, 1, (1, 1, 1, 1), (0, 1), None),       # half-periodic stride 2 pad 1
+    (2, 64, 64, 8, 8, 3, 1, 1, (1, 1, 1, 1), (1, 1), (16, 16)),     # nearest x2 folded
+    (2, 64, 64, 14, 30, 3, 1, 1, (1, 1, 1, 1), (0, 0), (31, 61)),   # nearest to odd size
+    (2, 64, 128, 9, 9, 1, 1, 1, (0, 0, 0, 0), (0, 0), None),        # 1x1 channel_up
+    (1, 128, 16, 8, 8, 1, 1, 1, (0, 0, 0, 0), (0, 0), None),        # latent projection (N=16)
+    (2, 64, 512, 16, 16, 1, 1, 1, (0, 0, 0, 0), (0, 0), None),      # FABlock in_proj (N tiles)
+    (2, 512, 64, 16, 16, 1, 1, 1, (0, 0, 0, 0), (0, 0), None),      # FABlock to_out (8 K slabs)
+    (5, 64, 64, 64, 64, 3, 1, 1, (1, 1, 1, 1), (1, 1), None),       # many tiles
+]
+
+
+def _conv_case(case, seed=0):
+    B, Cin, Cout, H, W, k, stride, dil, pad, modes, virt = case
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g) * 0.1
+    return x, w, b
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt_fp32(case):
+    ops = ops_mod()
+    B, Cin, Cout, H, W, k, stride, dil, pad, modes, virt = case
+    x, w, b = _conv_case(case)
+    ref = ref_conv(x, w, b, stride, dil, pad, modes, virt)
+    with ops.precision("fp32"):
+        y = ops.conv2d(act_from(x), ops.PackedFilter.of(Holder(w, b).weight, Holder(w, b).bias), stride=stride, dil=dil,
+                       pad=pad, pad_mode=modes, virt=virt, engine=ops.ENGINE_SIMT)
+    torch.cuda.synchronize()
+    assert tuple(act_to_nchw(y).shape) == tuple(ref.shape)
+    assert relerr(act_to_nchw(y), ref) < 2e-6
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_umma_bf16(case):
+    """tcgen05 engine vs an fp64 conv of the SAME bf16-rounded operands: only fp32 accumulation order differs."""
+    ops = ops_mod()
+    B, Cin, Cout, H, W, k, stride, dil, pad, modes, virt = case
+    x, w, b = _conv_case(case, seed=1)
+    xb, wb = x.bfloat16().float(), w.bfloat16().float()
+    ref = ref_conv(xb, wb, b, stride, dil, pad, modes, virt)
+    h = Holder(w, b)
+    with ops.precision("bf16"):
+        y = ops.conv2d(act_from(x, torch.bfloat16), ops.PackedFilter.of(h.weight, h.bias), stride=stride, dil=dil,
+                       pad=pad, pad_mode=modes, virt=virt, engine=ops.ENGINE_UMMA, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert relerr(act_to_nchw(y), ref) < 5e-6
+    with ops.precision("bf16"):
+        y16 = ops.conv2d(act_from(x, torch.bfloat16), ops.PackedFilter.of(h.weight, h.bias), stride=stride, dil=dil,
+                         pad=pad, pad_mode=modes, virt=virt, engine=ops.ENGINE_UMMA)
+    torch.cuda.synchronize()
+    assert y16.t.dtype == torch.bfloat16
+    assert relerr(act_to_nchw(y16), ref) < 4e-3  # bf16 output rounding (2^-9 per element)
+
+
+@pytest.mark.parametrize("engine", ["simt", "umma"])
+def test_conv_epilogue_and_prologue(engine):
+    """bias + per-sample bias + pre-activation addend + GELU + residual; SiLU(affine(x)) prologue with zero padding"""
+    ops = ops_mod()
+    B, C, H, W = 3, 64, 10, 12
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(C, C, 3, 3, generator=g) / math.sqrt(C * 9)
+    b = torch.randn(C, generator=g) * 0.1
+    sb = torch.randn(B, C, generator=g) * 0.1
+    pre = torch.randn(B, C, H, W, generator=g)
+    res = torch.randn(B, C, H, W, generator=g)
+    sc = torch.rand(B, C, generator=g) + 0.5
+    sh = torch.randn(B, C, generator=g) * 0.2
+    dt = torch.float32 if engine == "simt" else torch.bfloat16
+    rd = (lambda t: t) if engine == "simt" else (lambda t: t.bfloat16().float())
+    xin = F.silu(rd(x).double() * sc[:, :, None, None].double() + sh[:, :, None, None].double())
+    if engine == "umma":
+        xin = xin.float().bfloat16().double()  # the umma path materialises the normalised activation in bf16
+    ref = F.conv2d(F.pad(xin, (1, 1, 1, 1)), rd(w).double(), b.double())
+    ref = F.gelu(ref + sb[:, :, None, None].double() + rd(pre).double()) + rd(res).double()
+    h = Holder(w, b)
+    with ops.precision("fp32" if engine == "simt" else "bf16"):
+        y = ops.conv2d(act_from(x, dt), ops.PackedFilter.of(h.weight, h.bias), pad=(1, 1, 1, 1),
+                       sample_bias=sb.to(DEV), pro=(sc.to(DEV).reshape(-1), sh.to(DEV).reshape(-1), ops.ACT_SILU),
+                       act=ops.ACT_GELU, pre_add=act_from(pre, dt), residual=act_from(res, dt),
+                       out_dtype=torch.float32,
+                       engine=ops.ENGINE_SIMT if engine == "simt" else ops.ENGINE_UMMA)
+    torch.cuda.synchronize()
+    assert relerr(act_to_nchw(y), ref) < (2e-6 if engine == "simt" else 2e-5)
+
+
+def test_conv_nchw_ends():
+    """Cin=1 NCHW fp32 lift (+Swish) and Cout=1 NCHW fp32 projection with a batch-strided output"""
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 1, 16, 16, generator=g)
+    w = torch.randn(64, 1, 1, 1, generator=g)
+    b = torch.randn(64, generator=g)
+    h = Holder(w, b)
+    with ops.precision("fp32"):
+        y = ops.conv2d(ops.Act.from_nchw(x.to(DEV)), ops.PackedFilter.of(h.weight, h.bias), act=ops.ACT_SILU)
+    ref = F.silu(F.conv2d(x.double(), w.double(), b.double()))
+    assert relerr(act_to_nchw(y), ref) < 2e-6
+    w2 = torch.randn(1, 64, 1, 1, generator=g) / 8
+    b2 = torch.randn(1, generator=g)
+    h2 = Holder(w2, b2)
+    out = torch.zeros(3, 2, 1, 16, 16, device=DEV)  # [B, K=2, C, H, W]; write slot k=1
+    dst = ops.Act(out.view(-1)[256:], 3, 16, 16, 1, bstride=2 * 256, layout=ops.NCHW)
+    with ops.precision("fp32"):
+        ops.conv2d(y, ops.PackedFilter.of(h2.weight, h2.bias), out=dst, out_layout=ops.NCHW)
+    ref2 = F.conv2d(ref, w2.double(), b2.double())
+    assert relerr(out[:, 1].cpu(), ref2) < 2e-6
+    assert float(out[:, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,groups,eps", [((3, 64, 8, 8), 32, 1e-6), ((2, 128, 7, 15), 1, 1e-5),
+                                               ((2, 64, 64, 64), 8, 1e-5), ((2, 512, 16, 16), 512, 1e-5),
+                                               ((2, 128, 1, 1), 1, 1e-5), ((1, 64, 96, 192), 32, 1e-6)])
+def test_group_norm(shape, groups, eps, dtype):
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(*shape, generator=g) * 1.7 + 0.3
+    gamma = torch.rand(shape[1], generator=g) + 0.5
+    beta = torch.randn(shape[1], generator=g)
+    xr = x.to(dtype).double()
+    ref = F.silu(F.group_norm(xr, groups, gamma.double(), beta.double(), eps))
+    a = act_from(x, dtype)
+    s, t = ops.group_norm_affine(a, groups, eps, gamma.to(DEV), beta.to(DEV))
+    y = ops.affine_act(a, s, t, ops.ACT_SILU, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert relerr(act_to_nchw(y), ref) < 3e-6
+
+
+def test_group_norm_prescale():
+    """GroupNorm(1) of x*(1+g) from the statistics of x (conditional propagator gate)"""
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 128, 7, 15, generator=g)
+    gate = torch.randn(2, 128, generator=g) * 0.3
+    gamma, beta = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
+    ref = F.group_norm(x.double() * (1 + gate.double())[:, :, None, None], 1, gamma.double(), beta.double(), 1e-5)
+    a = act_from(x)
+    s, t = ops.group_norm_affine(a, 1, 1e-5, gamma.to(DEV), beta.to(DEV), prescale=(1 + gate).to(DEV).reshape(-1))
+    y = ops.affine_act(a, s, t)
+    assert relerr(act_to_nchw(y), ref) < 3e-6
+
+
+def test_layernorm_pe():
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, 128, 8, 8, generator=g)
+    gamma, beta = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
+    pe = torch.randn(1, 80, 128, generator=g) * 0.02
+    tok = x.permute(0, 2, 3, 1).reshape(3, 64, 128).double()
+    ref = F.layer_norm(tok, (128,), gamma.double(), beta.double(), 1e-5) + pe[:, :64].double()
+    y = ops.layernorm(act_from(x), gamma.to(DEV), beta.to(DEV), 1e-5, pe=pe.to(DEV))
+    assert relerr(y.as_tokens().cpu(), ref) < 2e-6
+
+
+@pytest.mark.parametrize("n_hw", [(8, 8), (12, 24), (7, 15)])
+def test_attention(n_hw):
+    ops = ops_mod()
+    H, W = n_hw
+    n, heads, dh = H * W, 8, 64
+    g = torch.Generator().manual_seed(7)
+    qkv = torch.randn(2, n, 3 * heads * dh, generator=g)
+    q, k, v = [t.view(2, n, heads, dh).transpose(1, 2).double() for t in qkv.split(heads * dh, dim=-1)]
+    attn = F.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, dim=-1)
+    ref = (attn @ v).transpose(1, 2).reshape(2, n, heads * dh)
+    a = ops.Act(qkv.to(DEV).reshape(-1), 2, H, W, 3 * heads * dh)
+    y = ops.attention(a, heads, dh, dh ** -0.5)
+    assert relerr(y.as_tokens().cpu(), ref) < 2e-6
+
+
+def test_axis_mean_lowrank_contract():
+    ops = ops_mod()
+    import lns_oracle as O
+    g = torch.Generator().manual_seed(8)
+    B, H, W, heads, ch = 2, 12, 24, 8, 64
+    x = torch.randn(B, 64, H, W, generator=g)
+    a = act_from(x)
+    m1 = ops.axis_mean(a, axis=1).t.view(B, H, 64).cpu()
+    m0 = ops.axis_mean(a, axis=0).t.view(B, W, 64).cpu()
+    assert relerr(m1, x.double().mean(dim=3).permute(0, 2, 1)) < 1e-6
+    assert relerr(m0, x.double().mean(dim=2).permute(0, 2, 1)) < 1e-6
+    # low-rank kernel vs the oracle's (reference modules/factorized_attention.py:43-69)
+    from modules.factorized_attention import LowRankKernel
+    torch.manual_seed(0)
+    lrk = LowRankKernel(64, 128, heads, use_rotary_emb=True).to(DEV)
+    u = torch.randn(B, W, 64, generator=g)
+    sd = {k: v.cpu().double() for k, v in lrk.state_dict().items()}
+    ref = O.low_rank_kernel(u.double(), O.SD(sd), heads)
+    K = lrk._fwd(ops.Act(u.to(DEV).reshape(-1), B, W, 1, 64))
+    assert relerr(K.cpu(), ref) < 3e-6
+    # axial contractions
+    up = torch.randn(B, heads * ch, H, W, generator=g)
+    kx = torch.randn(B, heads, H, H, generator=g)
+    ky = torch.randn(B, heads, W, W, generator=g)
+    u5 = up.double().view(B, heads, ch, H, W)
+    r1 = torch.einsum("bhij,bhcjm->bhcim", kx.double(), u5)
+    r2 = torch.einsum("bhlm,bhcim->bhcil", ky.double(), r1)
+    a1 = ops.axial_contract(act_from(up), kx.to(DEV).contiguous(), heads, axis=0)
+    a2 = ops.axial_contract(a1, ky.to(DEV).contiguous(), heads, axis=1)
+    assert relerr(act_to_nchw(a1), r1.reshape(B, heads * ch, H, W)) < 2e-6
+    assert relerr(act_to_nchw(a2), r2.reshape(B, heads * ch, H, W)) < 3e-6
+
+
+def test_layout_roundtrip_and_embedding():
+    ops = ops_mod()
+    import lns_oracle as O
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 5, 7, 11, generator=g)
+    a = ops.nchw_to_act(x.to(DEV), torch.float32)
+    assert torch.equal(a.to_torch_nhwc().cpu(), x.permute(0, 2, 3, 1))
+    assert torch.equal(a.to_nchw().cpu(), x)
+    p = torch.rand(6, generator=g)
+    e = ops.fourier_embedding(p.to(DEV), 64)
+    assert relerr(e.cpu(), O.fourier_embedding(p, 64)) < 1e-6
+
+
+def test_spectral_blocks_vs_golden(golden_dir):
+    """FourierBasicBlock / CondFourierBasicBlock (truncated-DFT kernels) vs outputs of the reference modules"""
+    import os
+    ops = ops_mod()
+    from modules.basics import FourierBasicBlock
+    from modules.fourier_cond import CondFourierBasicBlock
+    fix = torch.load(os.path.join(golden_dir, "fourier_blocks.pt"))
+    blk = FourierBasicBlock(8, 8, modes=[4, 5])
+    blk.load_state_dict(fix["fourier_sd"], strict=True)
+    cblk = CondFourierBasicBlock(8, 8, modes=[4, 5])
+    cblk.load_state_dict(fix["cond_sd"], strict=True)
+    blk, cblk = blk.to(DEV).eval(), cblk.to(DEV).eval()
+    with torch.no_grad(), ops.precision("fp32"):
+        y = blk(fix["x"].to(DEV))
+        yc = cblk(fix["x"].to(DEV), fix["emb"].to(DEV))
+    assert relerr(y.cpu(), fix["fourier_out_fp64"]) < 1e-5
+    assert relerr(yc.cpu(), fix["cond_out_fp64"]) < 1e-5
+
+
+@pytest.mark.parametrize("H,W,m1,m2", [(64, 64, 16, 16), (61, 121, 16, 31), (32, 32, 6, 6)])
+def test_spectral_conv_shapes(H, W, m1, m2):
+    ops = ops_mod()
+    import lns_oracle as O
+    from modules.basics import SpectralConv2d
+    torch.manual_seed(1)
+    m = SpectralConv2d(16, 16, m1, m2).to(DEV)
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(2, 16, H, W, generator=g)
+    sd = {k: v.cpu().double() for k, v in m.state_dict().items()}
+    ref = O.spectral_conv2d(x.double(), O.SD(sd))
+    with torch.no_grad(), ops.precision("fp32"):
+        y = m(x.to(DEV))
+    assert relerr(y.cpu(), ref) < 1e-5

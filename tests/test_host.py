@@ -1,0 +1,119 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/lns_b200.h declares, argument
+validation fails loudly, configs / state_dict layouts match the reference's, no CPU fallback exists."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from lns_b200 import REPO_ROOT, _C, ops
+from lns_b200.configs import CONFIGS, get_config
+from lns_b200.latent_dynamics import LatentDynamics
+
+
+def declared_symbols():
+    text = open(os.path.join(REPO_ROOT, "include", "lns_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lns_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _C.lib()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/lns_b200.h but not exported"
+    assert set(names) == set(_C.SIGNATURES), set(names) ^ set(_C.SIGNATURES)
+    assert b"sm_100a" in lib.lns_version()
+
+
+def test_convdesc_layout_matches_header():
+    """ctypes mirror of LnsConvDesc: same field order as the C struct (guards against silent ABI drift)."""
+    text = open(os.path.join(REPO_ROOT, "include", "lns_b200.h")).read()
+    body = text[text.index("typedef struct LnsConvDesc {") + len("typedef struct LnsConvDesc {"):text.index("} LnsConvDesc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = re.sub(r"^(const\s+)?(void|float|int32_t|int64_t)\s*\*?", "", decl)
+        fields += [n.strip().lstrip("*").strip() for n in names.split(",")]
+    assert fields == [f[0] for f in _C.ConvDesc._fields_]
+
+
+def test_pure_host_entry_points():
+    lib = _C.lib()
+    assert lib.lns_chan_stats_chunks(64, 64) == 4 and lib.lns_chan_stats_chunks(8, 8) == 1
+    assert lib.lns_packed_weight_bytes(128, 128, 3, 3, ops.W_UMMA_BF16) == 128 * 128 * 9 * 2
+    assert lib.lns_packed_weight_bytes(128, 16, 1, 1, ops.W_UMMA_BF16) == -1  # Cin % 64 != 0 -> not packable
+    assert lib.lns_packed_weight_bytes(1, 64, 1, 1, ops.W_SIMT_F32) == 256
+    assert lib.lns_spectral_work_bytes(2, 61, 121, 64, 64, 16, 31) == 2 * 61 * 31 * 128 * 8
+
+
+def test_invalid_arguments_are_errors_not_fallbacks():
+    lib = _C.lib()
+    d = _C.ConvDesc()  # all-null descriptor
+    assert lib.lns_conv2d(ctypes.byref(d), None) == -1
+    assert b"null" in lib.lns_last_error()
+    assert lib.lns_chan_stats(None, 0, 1, 1, 1, 64, 64, None, None) == -1
+    assert lib.lns_spectral_conv2d(ctypes.c_void_p(16), 0, 1, 8, 8, 4, 4, 5, 3, ctypes.c_void_p(16), None,
+                                   ctypes.c_void_p(16), ctypes.c_void_p(16), None) == -1  # 2*m1 > H
+    assert b"modes1" in lib.lns_last_error()
+
+
+def test_cpu_tensors_raise():
+    with pytest.raises(ops.LnsError):
+        ops.nchw_to_act(torch.zeros(1, 1, 8, 8))
+    with pytest.raises(ops.LnsError):
+        ops.Act.from_nchw(torch.zeros(1, 1, 8, 8))
+    from modules.basics import ResidualBlock
+    blk = ResidualBlock(64, 64, num_dimensions=2, padding_mode="circular")
+    with pytest.raises(ops.LnsError):
+        blk(torch.zeros(1, 64, 8, 8))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_C, "_lib", None)
+    monkeypatch.setattr(_C, "LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(_C.LnsError, match="no CPU or PyTorch-eager fallback"):
+        _C.lib()
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_state_dict_layout(name):
+    """Key names / shapes the reference's checkpoints have and strict round trip."""
+    model = LatentDynamics(get_config(name))
+    sd = model.state_dict()
+    ae = "ae" if name == "twophase_cond" else "vq_ae"
+    n_expected = {"ns2d": 213, "sw": 228, "twophase": 187, "twophase_cond": 231}[name]
+    assert len(sd) == n_expected
+    assert f"{ae}.quant_conv.weight" in sd and f"{ae}.post_quant_conv.bias" in sd
+    assert sd["propagator.in_proj.weight"].shape == (128, model.latent_dim, 1, 1)
+    if name == "ns2d":
+        assert sd["vq_ae.decoder.model.2.pe"].shape == (1, 64, 128)
+        assert sd["vq_ae.decoder.model.2.to_q.weight"].shape == (512, 128)
+        assert sd["vq_ae.decoder.model.8.in_proj.weight"].shape == (512, 64, 1, 1)
+        assert sd["vq_ae.decoder.model.11.low_rank_kernel_x.to_qk.weight"].shape == (2048, 64)
+        assert sd["vq_ae.decoder.model.8.low_rank_kernel_y.pos_emb.inv_freq"].shape == (64,)
+        assert "propagator.net.2.ffn.3.weight" in sd and "propagator.net.0.ffn.1.bias" not in sd
+    if name == "twophase":
+        assert not any("low_rank_kernel" in k for k in sd)  # FABlock2D is never instantiated for two-phase
+        assert sd["vq_ae.decoder.model.2.pe"].shape == (1, 119, 128)
+    if name == "twophase_cond":
+        assert sd["propagator.net.3.cond_conv1.2.weight"].abs().max() == 0  # zero_module
+        assert sd["propagator.cond_emb_proj.2.weight"].shape == (64, 64)
+    clone = LatentDynamics(get_config(name))
+    assert not clone.load_state_dict(sd, strict=True).missing_keys
+
+
+def test_reference_defects_are_mirrored():
+    import argparse
+    from modules.propagator import SimpleMLP, SimpleResNet, ConditionalResNet
+    args = argparse.Namespace(latent_dim=4, latent_resolution=4, propagator_dim=32, is_periodic=True)
+    assert len(SimpleMLP(args).state_dict()) == 6
+    with pytest.raises(TypeError):
+        SimpleResNet(args)  # ResidualBlock without num_dimensions, modules/propagator.py:22-24
+    with pytest.raises(TypeError):
+        ConditionalResNet(args)

@@ -1,0 +1,76 @@
+"""CPU tests: the oracle restatement (oracle/lns_oracle.py) against golden vectors produced by the unmodified reference
+(oracle/make_golden.py).  This is what pins the oracle; the GPU parity tests then compare the CUDA path with it."""
+import hashlib
+import os
+
+import pytest
+import torch
+
+import lns_oracle as O
+from lns_b200.configs import get_config
+from lns_b200.latent_dynamics import LatentDynamics
+
+CONFIGS = ["ns2d", "sw", "twophase", "twophase_cond"]
+
+
+def _sha(t):
+    return hashlib.sha1(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()
+
+
+def build_state(name):
+    """Weights exactly as make_golden.py used them: seed 1234 through the drop-in constructors + redrawn zero-inits."""
+    cfg = get_config(name)
+    torch.manual_seed(1234)
+    model = LatentDynamics(cfg).eval()
+    return cfg, model, O.randomize_zero_init(model.state_dict())
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_weights_reproduce_reference_init(name, golden_dir):
+    """Same seed -> the drop-in modules hold bit-identical parameters to the reference's (names, shapes, values)."""
+    fix = torch.load(os.path.join(golden_dir, f"{name}_predict.pt"))
+    _, _, sd = build_state(name)
+    assert set(sd) == set(fix["state_sha1"])
+    bad = [k for k in sd if _sha(sd[k]) != fix["state_sha1"][k]]
+    assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_oracle_matches_reference_fp32(name, golden_dir):
+    fix = torch.load(os.path.join(golden_dir, f"{name}_predict.pt"))
+    cfg, _, sd = build_state(name)
+    x, param = O.make_inputs(cfg, fix["batch"], seed=fix["input_seed"])
+    y, z = O.predict(sd, cfg, x, fix["steps"], param=param, to_x=True, return_latents=True)
+    # same ATen CPU kernels in the same order: equal up to fp32 re-association inside oneDNN (thread count dependent)
+    ez = O.rel_l2(z.flatten(0, 1), fix["latent_fp32"].flatten(0, 1)).max().item()
+    ey = O.rel_l2(y[..., ::2, ::2].flatten(0, 1), fix["field_fp32_sub2"].flatten(0, 1)).max().item()
+    assert ez < 2e-5 and ey < 2e-5, (ez, ey)
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_oracle_matches_reference_fp64(name, golden_dir):
+    """fp64 oracle vs the fp64 copy of the reference: equal to ~1e-12 -> the restatement is the same function."""
+    fix = torch.load(os.path.join(golden_dir, f"{name}_predict.pt"))
+    cfg, _, sd = build_state(name)
+    x, param = O.make_inputs(cfg, fix["batch"], seed=fix["input_seed"])
+    sd64 = O.to_dtype(sd, torch.float64)
+    y, z = O.predict(sd64, cfg, x.double(), fix["steps"], param=None if param is None else param.double(),
+                     to_x=True, return_latents=True)
+    ez = O.rel_l2(z.flatten(0, 1), fix["latent_fp64"].flatten(0, 1)).max().item()
+    ey = O.rel_l2(y[..., ::2, ::2].flatten(0, 1), fix["field_fp64_sub2"].flatten(0, 1)).max().item()
+    # the conditional model's sinusoidal embedding is fp32 in the reference -> ~1e-8 there
+    tol = 1e-6 if name == "twophase_cond" else 1e-10
+    assert ez < tol and ey < tol, (ez, ey)
+
+
+def test_oracle_fourier_blocks(golden_dir):
+    fix = torch.load(os.path.join(golden_dir, "fourier_blocks.pt"))
+    x, emb = fix["x"], fix["emb"]
+    # the reference allocates out_ft as torch.cfloat regardless of the input dtype (modules/basics.py:134-141), so even
+    # its fp64 copy carries complex64 rounding in the spectral term; the oracle keeps complex128 -> agree to ~1e-8
+    y = O.fourier_basic_block(x.double(), O.SD(O.to_dtype(fix["fourier_sd"], torch.float64)))
+    assert O.rel_l2(y, fix["fourier_out_fp64"]).max().item() < 1e-7
+    y = O.cond_fourier_basic_block(x.double(), emb.double(), O.SD(O.to_dtype(fix["cond_sd"], torch.float64)))
+    assert O.rel_l2(y, fix["cond_out_fp64"]).max().item() < 1e-7
+    y = O.fourier_basic_block(x, O.SD(fix["fourier_sd"]))
+    assert O.rel_l2(y, fix["fourier_out"]).max().item() < 1e-5
