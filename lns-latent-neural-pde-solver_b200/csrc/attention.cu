@@ -153,6 +153,116 @@ __global__ void __launch_bounds__(256) axial_contract_kernel(const void* __restr
   }
 }
 
+
+// ---- axial contraction on tensor cores (bf16 in / bf16 out) -----------------------------------------------------------
+// out_line[i][c] = sum_j K[i][j] * slab_line[j][c]  is a GEMM with M = K = n (padded to 16), N = 64 channels per line.
+// Memory-bound (16 FLOP/B): the point of the tensor cores here is to keep the SM out of the way of the HBM stream.
+// grid (ceil(lines/8), heads, B), block 128: a CTA stages K (bf16) and 8 line slabs in shared memory with cp.async,
+// each warp owns 2 lines; mma.sync.m16n8k16 (bf16 x bf16 -> fp32) with ldmatrix / ldmatrix.trans operand fetch; results
+// go through a per-warp staging tile so that every global store is a full 128-byte channel row.
+constexpr int kAxLines = 8;      // lines per CTA
+constexpr int kAxSlabStride = 72;  // bf16 elements per slab row (64 + 8 pad: conflict-free ldmatrix)
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) axial_contract_mma_kernel(const __nv_bfloat16* __restrict__ u, int H, int W, int heads,
+                                                                  const float* __restrict__ Kmat, int axis,
+                                                                  __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int n = axis == 0 ? H : W;
+  const int lines = axis == 0 ? W : H;
+  const int n16 = (n + 15) & ~15;
+  const int kstride = n16 + 8;
+  __nv_bfloat16* K_s = reinterpret_cast<__nv_bfloat16*>(smraw);
+  __nv_bfloat16* slab = K_s + (size_t)n16 * kstride;                             // [kAxLines][n16][72]
+  __nv_bfloat16* stage = slab + (size_t)kAxLines * n16 * kAxSlabStride;            // [4 warps][16][72]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int line0 = blockIdx.x * kAxLines, h = blockIdx.y, b = blockIdx.z;
+  const int C = heads * 64;
+  const int64_t sbase = (int64_t)b * H * W * C + h * 64;
+
+  // K (fp32) -> bf16, zero padded to n16 x n16
+  const float* Kg = Kmat + ((int64_t)b * heads + h) * n * n;
+  for (int e = tid; e < n16 * n16; e += 128) {
+    int i = e / n16, j = e - i * n16;
+    float v = (i < n && j < n) ? __ldg(Kg + i * n + j) : 0.f;
+    K_s[i * kstride + j] = __float2bfloat16_rn(v);
+  }
+  // slabs: 8 x 16-byte chunks per (line, j) row
+  const int nl = min(kAxLines, lines - line0);
+  for (int e = tid; e < nl * n16 * 8; e += 128) {
+    int ch = e & 7;
+    int r = e >> 3;
+    int l = r / n16, j = r - l * n16;
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(slab + ((size_t)l * n16 + j) * kAxSlabStride + ch * 8);
+    if (j < n) {
+      int line = line0 + l;
+      int64_t pix = axis == 0 ? ((int64_t)j * W + line) : ((int64_t)line * W + j);
+      const __nv_bfloat16* src = u + sbase + pix * C + ch * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(slab + ((size_t)l * n16 + j) * kAxSlabStride + ch * 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  __nv_bfloat16* my_stage = stage + (size_t)warp * 16 * kAxSlabStride;
+  const int ktiles = n16 >> 4;
+  for (int l = warp * 2; l < warp * 2 + 2 && l < nl; ++l) {
+    const __nv_bfloat16* sl = slab + (size_t)l * n16 * kAxSlabStride;
+    const int line = line0 + l;
+    for (int mt = 0; mt < ktiles; ++mt) {
+      float acc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+      for (int kt = 0; kt < ktiles; ++kt) {
+        uint32_t a[4];
+        ldmatrix_x4((uint32_t)__cvta_generic_to_shared(K_s + (size_t)(mt * 16 + (lane & 15)) * kstride + kt * 16 + (lane >> 4) * 8),
+                    a[0], a[1], a[2], a[3]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          uint32_t b0, b1;
+          ldmatrix_x2_trans((uint32_t)__cvta_generic_to_shared(sl + (size_t)(kt * 16 + (lane & 15)) * kAxSlabStride + nt * 8), b0, b1);
+          mma_bf16_16816(acc[nt], a, b0, b1);
+        }
+      }
+      // fragment -> staging tile [16][64] (bf16)
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        int r = lane >> 2, c = nt * 8 + (lane & 3) * 2;
+        *reinterpret_cast<__nv_bfloat162*>(my_stage + r * kAxSlabStride + c) = __floats2bfloat162_rn(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<__nv_bfloat162*>(my_stage + (r + 8) * kAxSlabStride + c) = __floats2bfloat162_rn(acc[nt][2], acc[nt][3]);
+      }
+      __syncwarp();
+      // 4 rows per pass, 8 lanes x 16 bytes per row
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        int r = pass * 4 + (lane >> 3);
+        int i = mt * 16 + r;
+        if (i < n) {
+          int64_t pix = axis == 0 ? ((int64_t)i * W + line) : ((int64_t)line * W + i);
+          uint4 v = *reinterpret_cast<const uint4*>(my_stage + r * kAxSlabStride + (lane & 7) * 8);
+          *reinterpret_cast<uint4*>(out + sbase + pix * C + (lane & 7) * 8) = v;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace lns
 
 extern "C" {
@@ -205,12 +315,25 @@ int lns_axial_contract(const void* u, int dtype, int B, int H, int W, int heads,
               "lns_axial_contract: bad arguments (ch=%d)", ch);
   LNS_REQUIRE(B <= 65535, "lns_axial_contract: batch %d exceeds grid limit, chunk the call", B);
   int n = axis == 0 ? H : W;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == LNS_BF16 && out_dtype == LNS_BF16 && ch == 64) {
+    // tensor-core path (the bf16 rollout)
+    int n16 = (n + 15) & ~15;
+    int lines = axis == 0 ? W : H;
+    size_t smem_mma = ((size_t)n16 * (n16 + 8) + (size_t)lns::kAxLines * n16 * lns::kAxSlabStride +
+                       4 * 16 * (size_t)lns::kAxSlabStride) * sizeof(__nv_bfloat16);
+    LNS_REQUIRE(smem_mma <= 227 * 1024, "lns_axial_contract: n=%d needs %zu B shared memory", n, smem_mma);
+    { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::axial_contract_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+    dim3 grid(lns::cdiv(lines, lns::kAxLines), heads, B);
+    lns::axial_contract_mma_kernel<<<grid, 128, smem_mma, s>>>(reinterpret_cast<const __nv_bfloat16*>(u), H, W, heads, K, axis,
+                                                               reinterpret_cast<__nv_bfloat16*>(out));
+    return lns::check_launch("axial_contract_mma_kernel");
+  }
   size_t smem = ((size_t)n * ch + (size_t)n * n) * sizeof(float);
   LNS_REQUIRE(smem <= 227 * 1024, "lns_axial_contract: n=%d needs %zu B shared memory", n, smem);
   { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::axial_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
   dim3 grid(axis == 0 ? W : H, heads, B);
-  lns::axial_contract_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(u, dtype, H, W, heads, ch, K,
-                                                                                           axis, out, out_dtype);
+  lns::axial_contract_kernel<<<grid, 256, smem, s>>>(u, dtype, H, W, heads, ch, K, axis, out, out_dtype);
   return lns::check_launch("axial_contract_kernel");
 }
 

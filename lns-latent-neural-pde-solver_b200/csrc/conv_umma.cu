@@ -13,8 +13,8 @@
 //       dilation, stride 2, nearest up-sampling folded into the read (never materialised), ragged M tails.
 //   B tile (NT x 64): the filter was re-laid on the device once (lns_pack_conv_weight, LNS_W_UMMA_BF16) into exactly
 //       this swizzled image, so a K block of the filter is a linear copy.
-// Pipeline: STAGES-deep ring of (A,B) stages; mbarriers full[] (128 producer arrivals after
-// cp.async.wait_group + fence.proxy.async) and empty[] (tcgen05.commit); one elected thread of warp 4 issues
+// Pipeline: STAGES-deep ring of (A,B) stages; mbarriers full[] (128 asynchronous producer arrivals,
+// cp.async.mbarrier.arrive.noinc, + one fence.proxy.async on the consumer side) and empty[] (tcgen05.commit); one thread of warp 4 issues
 // tcgen05.mma (4 x K=16 per stage); the accumulator is handed to the epilogue through a third mbarrier.
 // Epilogue: warps 0-3 read their 32 TMEM lanes with tcgen05.ld (32x32b.x16), add bias / per-sample conditioning
 // bias / pre-activation addend, apply GELU|SiLU, add the residual, and store 32-byte bf16 (or 64-byte fp32) row
@@ -56,6 +56,11 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the mbarrier receives one arrival from this thread once all of its previously issued cp.async have landed
+// (asynchronous: the thread does not wait); .noinc = the arrival counts against the barrier's initial expected count
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -127,6 +132,9 @@ struct UmmaParams {
   int y_dtype;
   int M;
   int slabs;  // Cin / 64
+  uint32_t x_bstride8;  // input batch stride in 16-byte units
+  int resize;           // 0 none, 1 exact 2x nearest, 2 general nearest
+  float inv_wout, inv_hout, inv_hv, inv_wv;
 };
 
 constexpr int kUmmaThreads = 160;  // warps 0-3: producers + epilogue; warp 4: TMEM owner + MMA issuer
@@ -183,42 +191,73 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
 
   if (warp < 4) {
     // ============================== producers ==============================
-    const int chunk = tid & 7;      // 16-byte chunk (8 channels) of the 128-byte row
-    const int rbase = tid >> 3;     // rows rbase + 16*i, i = 0..7
+    // Thread t copies 16-byte chunk (t & 7) of rows (t >> 3) + 16*i, i = 0..7: the 8 lanes of a row read one full
+    // 128-byte line (coalesced).  The source pixel of a (row, tap) pair is the same for those 8 lanes, so lane
+    // (t & 7) computes it for row i = (t & 7) only and the group exchanges the 8 results with shuffles.  No integer
+    // division in the loop: rows are decoded incrementally from the tile's first pixel, circular wrap is a
+    // conditional add (host guarantees pad <= size), nearest resize is a shift (exact 2x) or an exact float divide.
+    const int chunk = tid & 7;
+    const int rbase = tid >> 3;
     const uint32_t sw_chunk = (uint32_t)((chunk ^ (rbase & 7)) << 4);
-    int yb[8], xb[8], bb[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int m = m0 + rbase + 16 * i;
-      if (m < p.M) {
-        int b = m / HWo;
-        int r = m - b * HWo;
-        int yo = r / g.Wout;
-        int xo = r - yo * g.Wout;
-        bb[i] = b;
-        yb[i] = yo * g.stride - g.pad_t;
-        xb[i] = xo * g.stride - g.pad_l;
-      } else {
-        bb[i] = -1; yb[i] = 0; xb[i] = 0;
-      }
+    const uint32_t cin8 = (uint32_t)(g.Cin >> 3);
+    // my row for the address computation: rbase + 16 * chunk
+    int my_yb, my_xb;
+    uint32_t my_base;
+    bool my_ok;
+    {
+      int b0 = m0 / HWo;
+      int r0 = m0 - b0 * HWo;
+      int y0 = r0 / g.Wout;
+      int x0 = r0 - y0 * g.Wout;
+      int rr = rbase + 16 * chunk;
+      // x0 + rr < Wout + 128, y0 + q < Hout + 128: small numbers -> exact float quotient
+      int t = x0 + rr;
+      int q = __float2int_rd(((float)t + 0.5f) * p.inv_wout);
+      int xo = t - q * g.Wout;
+      int t2 = y0 + q;
+      int q2 = __float2int_rd(((float)t2 + 0.5f) * p.inv_hout);
+      int yo = t2 - q2 * g.Hout;
+      int b = b0 + q2;
+      my_ok = (m0 + rr) < p.M;
+      my_yb = yo * g.stride - g.pad_t;
+      my_xb = xo * g.stride - g.pad_l;
+      my_base = (uint32_t)b * p.x_bstride8;
     }
     const int64_t w_kb_stride = (int64_t)g.Cout * 64;  // elements per (tap, slab) filter block
     const int b_chunks = n_valid * 8;                  // 16-byte chunks of the B tile
+    const unsigned grp = 0xFFu << (lane & 24);         // the 8 lanes that share my rows
     uint32_t soff[8];                                  // source offset in 16-byte units, 0xFFFFFFFF = zero fill
     int issued = 0;
     for (int tap = 0; tap < taps; ++tap) {
       const int ky = tap / g.KW, kx = tap - ky * g.KW;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        soff[i] = 0xFFFFFFFFu;
-        if (bb[i] >= 0) {
-          int ys, xs;
-          if (conv_src(g, yb[i] + ky * g.dil, xb[i] + kx * g.dil, ys, xs)) {
-            int64_t e = (int64_t)bb[i] * g.x_bstride + ((int64_t)ys * g.Win + xs) * g.Cin;
-            soff[i] = (uint32_t)(e >> 3);
-          }
+      uint32_t mine = 0xFFFFFFFFu;
+      {
+        int yv = my_yb + ky * g.dil, xv = my_xb + kx * g.dil;
+        bool ok = my_ok;
+        if (g.circ_h) {
+          yv += (yv < 0) ? g.Hv : 0;
+          yv -= (yv >= g.Hv) ? g.Hv : 0;
+        } else {
+          ok = ok && ((unsigned)yv < (unsigned)g.Hv);
         }
+        if (g.circ_w) {
+          xv += (xv < 0) ? g.Wv : 0;
+          xv -= (xv >= g.Wv) ? g.Wv : 0;
+        } else {
+          ok = ok && ((unsigned)xv < (unsigned)g.Wv);
+        }
+        if (p.resize == 1) {          // exact 2x nearest
+          yv >>= 1;
+          xv >>= 1;
+        } else if (p.resize == 2) {   // general nearest: floor(v * in / out), exact for these magnitudes
+          yv = __float2int_rd(((float)(yv * g.Hin) + 0.5f) * p.inv_hv);
+          xv = __float2int_rd(((float)(xv * g.Win) + 0.5f) * p.inv_wv);
+        }
+        if (ok) mine = my_base + (uint32_t)(yv * g.Win + xv) * cin8;
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) soff[i] = __shfl_sync(0xFFFFFFFFu, mine, (lane & 24) + i);
+      (void)grp;
       for (int slab = 0; slab < p.slabs; ++slab, ++issued) {
         const int s = issued % STAGES;
         if (issued >= STAGES) ptx::mbar_wait(empty_bar(s), ((issued / STAGES) & 1) ^ 1);
@@ -233,18 +272,11 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
         }
         const int4* wsrc = reinterpret_cast<const int4*>(p.w + (int64_t)issued * w_kb_stride + (int64_t)n0 * 64);
         for (int q = tid; q < b_chunks; q += 128) ptx::cp_async16(b_dst + (uint32_t)q * 16u, wsrc + q, 16u);
-        ptx::cp_async_commit();
-        if (issued >= STAGES - 1) {
-          ptx::cp_async_wait<STAGES - 1>();
-          ptx::fence_proxy_async();
-          ptx::mbar_arrive(full_bar((issued - (STAGES - 1)) % STAGES));
-        }
+        // completion is signalled asynchronously: no thread ever blocks on its own copies, so up to STAGES K blocks
+        // of loads are in flight per thread
+        ptx::cp_async_arrive_noinc(full_bar(s));
       }
     }
-    // drain: the last STAGES-1 groups (or all of them when nkb < STAGES-1)
-    ptx::cp_async_wait<0>();
-    ptx::fence_proxy_async();
-    for (int k = max(0, nkb - (STAGES - 1)); k < nkb; ++k) ptx::mbar_arrive(full_bar(k % STAGES));
 
     // ============================== epilogue ==============================
     ptx::mbar_wait(accum_bar, 0);
@@ -326,6 +358,7 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         ptx::mbar_wait(full_bar(s), (kb / STAGES) & 1);
+        ptx::fence_proxy_async();  // cp.async wrote the stage through the generic proxy; tcgen05.mma reads it via the async proxy
         ptx::tc_fence_after();
         const uint32_t a_addr = smem_base + s * L::kStageBytes;
         const uint64_t adesc = make_sw128_desc(a_addr);
@@ -399,6 +432,17 @@ int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
   p.y = d->y; p.y_dtype = d->y_dtype;
   p.M = (int)M;
   p.slabs = d->Cin / 64;
+  p.x_bstride8 = (uint32_t)(d->x_bstride >> 3);
+  p.resize = (d->Hv == d->Hin && d->Wv == d->Win) ? 0 : ((d->Hv == 2 * d->Hin && d->Wv == 2 * d->Win) ? 1 : 2);
+  p.inv_wout = 1.0f / (float)d->Wout; p.inv_hout = 1.0f / (float)d->Hout;
+  p.inv_hv = 1.0f / (float)d->Hv; p.inv_wv = 1.0f / (float)d->Wv;
+  // the in-kernel wrap is a single conditional add/subtract and the resize uses exact float quotients of small ints
+  LNS_REQUIRE(d->pad_t <= d->Hv && d->pad_l <= d->Wv &&
+                  (int64_t)(d->Hout - 1) * d->stride + (int64_t)(d->KH - 1) * d->dil - d->pad_t < 2ll * d->Hv &&
+                  (int64_t)(d->Wout - 1) * d->stride + (int64_t)(d->KW - 1) * d->dil - d->pad_l < 2ll * d->Wv,
+              "lns_conv2d(umma): padding/dilation larger than the grid is not supported");
+  LNS_REQUIRE((int64_t)d->Hv * d->Hin < (1 << 21) && (int64_t)d->Wv * d->Win < (1 << 21) && d->Hout < (1 << 20) &&
+                  d->Wout < (1 << 20), "lns_conv2d(umma): spatial size too large");
   if (d->Cout <= 64) return launch_umma<64, 4>(p, d->Cout, stream);
   if (d->Cout <= 128) return launch_umma<128, 3>(p, d->Cout, stream);
   return launch_umma<256, 3>(p, d->Cout, stream);

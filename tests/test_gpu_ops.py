@@ -321,3 +321,23 @@ def test_spectral_conv_shapes(H, W, m1, m2):
     with torch.no_grad(), ops.precision("fp32"):
         y = m(x.to(DEV))
     assert relerr(y.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (32, 32), (24, 48), (48, 96), (12, 24), (7, 15)])
+def test_axial_contract_tensor_core_bf16(H, W):
+    """mma.sync path (bf16 in/out) vs fp64 einsum of the same bf16-rounded operands"""
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(21)
+    B, heads, ch = 3, 8, 64
+    up = torch.randn(B, heads * ch, H, W, generator=g)
+    kx = torch.randn(B, heads, H, H, generator=g)
+    ky = torch.randn(B, heads, W, W, generator=g)
+    u5 = up.bfloat16().double().view(B, heads, ch, H, W)
+    r1 = torch.einsum("bhij,bhcjm->bhcim", kx.bfloat16().double(), u5)
+    a1 = ops.axial_contract(act_from(up, torch.bfloat16), kx.to(DEV).contiguous(), heads, axis=0)
+    assert a1.t.dtype == torch.bfloat16
+    assert relerr(act_to_nchw(a1), r1.reshape(B, heads * ch, H, W)) < 4e-3
+    r1b = act_to_nchw(a1).double().view(B, heads, ch, H, W)  # feed the kernel's own (bf16) intermediate to stage 2
+    r2 = torch.einsum("bhlm,bhcim->bhcil", ky.bfloat16().double(), r1b)
+    a2 = ops.axial_contract(a1, ky.to(DEV).contiguous(), heads, axis=1)
+    assert relerr(act_to_nchw(a2), r2.reshape(B, heads * ch, H, W)) < 4e-3
