@@ -44,7 +44,12 @@ enum {
                       /* tcgen05.mma (needs Cin % 64 == 0 and Cout % 16 == 0)                   */
 };
 /* which engine executes lns_conv2d */
-enum { LNS_ENGINE_SIMT = 0, LNS_ENGINE_UMMA = 1 };
+enum {
+  LNS_ENGINE_SIMT = 0, /* CUDA-core fp32 FMA (validation path; any shape)                                       */
+  LNS_ENGINE_UMMA = 1, /* tcgen05 implicit GEMM, per-tap gather (any kernel/stride/dilation/resize, Cin%64==0)  */
+  LNS_ENGINE_HALO = 2  /* tcgen05 implicit GEMM, shared-memory halo + resident filter: same-size 3x3 stride-1     */
+                       /* convs with Cin == 64, Cout in {64,128} (the full-resolution layers)                     */
+};
 
 const char* lns_version(void);
 const char* lns_last_error(void);

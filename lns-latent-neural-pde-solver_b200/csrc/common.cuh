@@ -112,6 +112,8 @@ __device__ __forceinline__ bool conv_src(const ConvGeom& g, int yv, int xv, int&
 
 int conv2d_simt(const LnsConvDesc* d, cudaStream_t stream);
 int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream);
+int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream);
+bool conv_halo_supported(const LnsConvDesc* d);
 int validate_conv(const LnsConvDesc* d);
 ConvGeom make_geom(const LnsConvDesc* d);
 

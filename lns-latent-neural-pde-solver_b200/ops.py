@@ -16,7 +16,7 @@ NHWC, NCHW = 0, 1
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAD_ZEROS, PAD_CIRCULAR = 0, 1
 W_SIMT_F32, W_UMMA_BF16 = 0, 1
-ENGINE_SIMT, ENGINE_UMMA = 0, 1
+ENGINE_SIMT, ENGINE_UMMA, ENGINE_HALO = 0, 1, 2
 
 _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
 
@@ -255,7 +255,10 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     Wout = (Wv + pl + pr - dil * (KW - 1) - 1) // stride + 1
     if engine is None:
         engine = ENGINE_UMMA if _umma_ok(x, Cin, Cout, out_layout) else ENGINE_SIMT
-    if engine == ENGINE_UMMA and pro is not None:
+        if (engine == ENGINE_UMMA and KH == 3 and KW == 3 and stride == 1 and Cin == 64 and Cout in (64, 128)
+                and pt == pb == pl == pr == dil and 1 <= dil <= 3 and Hout >= 16 and Wout >= 8):
+            engine = ENGINE_HALO  # full-resolution layers: shared-memory halo + resident filter
+    if engine in (ENGINE_UMMA, ENGINE_HALO) and pro is not None:
         # this engine gathers with cp.async (no transform in flight): materialise the normalised activation first
         x = affine_act(x, pro[0], pro[1], pro[2])
         pro = None
@@ -276,7 +279,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     d.Hv, d.Wv = Hv, Wv
     d.KH, d.KW, d.stride, d.dil, d.pad_t, d.pad_l = KH, KW, stride, dil, pt, pl
     d.pad_mode_h, d.pad_mode_w = pad_mode
-    fmt = W_UMMA_BF16 if engine == ENGINE_UMMA else W_SIMT_F32
+    fmt = W_UMMA_BF16 if engine in (ENGINE_UMMA, ENGINE_HALO) else W_SIMT_F32
     wbuf = filt.get(fmt)
     d.w, d.w_format, d.engine = wbuf.data_ptr(), fmt, engine
     bias = filt.bias() if use_bias else None

@@ -341,3 +341,43 @@ def test_axial_contract_tensor_core_bf16(H, W):
     r2 = torch.einsum("bhlm,bhcim->bhcil", ky.bfloat16().double(), r1b)
     a2 = ops.axial_contract(a1, ky.to(DEV).contiguous(), heads, axis=1)
     assert relerr(act_to_nchw(a2), r2.reshape(B, heads * ch, H, W)) < 4e-3
+
+
+HALO_CASES = [
+    # B, Cout, H, W, dil, modes(h,w), virt
+    (2, 64, 64, 64, 1, (1, 1), None),        # NS2d full resolution, circular
+    (3, 64, 32, 32, 1, (1, 1), None),
+    (2, 64, 16, 16, 1, (1, 1), (32, 32)),    # nearest x2 folded into the halo fill
+    (2, 128, 16, 16, 1, (1, 1), None),       # 64 -> 128 (encoder ResBlock)
+    (2, 64, 28, 60, 1, (0, 0), (61, 121)),   # two-phase: general nearest to an odd size, zero padding, ragged tiles
+    (2, 64, 61, 121, 1, (0, 0), None),       # ragged tiles in both directions
+    (2, 64, 48, 96, 1, (0, 1), None),        # shallow water: zeros in H, circular in W
+    (1, 64, 96, 192, 1, (0, 1), None),
+    (2, 64, 24, 24, 2, (1, 1), None),        # dilation 2
+    (2, 64, 24, 40, 3, (0, 1), None),        # dilation 3
+    (150, 64, 16, 16, 1, (1, 1), None),      # more tiles than SMs: persistent loop, ring wrap-around
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_halo_bf16(case):
+    """halo engine (resident filter, shifted-descriptor taps) vs fp64 conv of the same bf16-rounded operands, with the
+    full epilogue (bias, GELU, residual)"""
+    ops = ops_mod()
+    B, Cout, H, W, dil, modes, virt = case
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, 64, H, W, generator=g)
+    w = torch.randn(Cout, 64, 3, 3, generator=g) / 24.0
+    b = torch.randn(Cout, generator=g) * 0.1
+    Ho, Wo = virt if virt is not None else (H, W)
+    res = torch.randn(B, Cout, Ho, Wo, generator=g)
+    ref = ref_conv(x.bfloat16().float(), w.bfloat16().float(), b, 1, dil, (dil,) * 4, modes, virt)
+    ref = F.gelu(ref) + res.bfloat16().double()
+    h = Holder(w, b)
+    with ops.precision("bf16"):
+        y = ops.conv2d(act_from(x, torch.bfloat16), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4,
+                       pad_mode=modes, virt=virt, act=ops.ACT_GELU, residual=act_from(res, torch.bfloat16),
+                       engine=ops.ENGINE_HALO, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert tuple(act_to_nchw(y).shape) == tuple(ref.shape)
+    assert relerr(act_to_nchw(y), ref) < 5e-6

@@ -9,7 +9,8 @@ import torch  # noqa: E402
 
 from lns_b200 import ops  # noqa: E402
 
-H, W, Cin, Cout, nb, dil = [int(a) for a in (sys.argv[1:7] + ["64", "64", "64", "64", "256", "1"][len(sys.argv) - 1:])]
+H, W, Cin, Cout, nb, dil = [int(a) for a in (sys.argv[1:7] + ["64", "64", "64", "64", "256", "1"][len(sys.argv[1:7]):])]
+ENGINE = {"umma": ops.ENGINE_UMMA, "halo": ops.ENGINE_HALO}[sys.argv[7] if len(sys.argv) > 7 else "umma"]
 dev = "cuda:0"
 x = ops.Act(torch.randn(nb * H * W * Cin, device=dev).bfloat16(), nb, H, W, Cin)
 wt = torch.nn.Parameter(torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(9 * Cin))
@@ -18,14 +19,14 @@ filt = ops.PackedFilter.of(wt, bs)
 out = ops.Act.empty(nb, H, W, Cout, torch.bfloat16, dev)
 with ops.precision("bf16"):
     for _ in range(3):
-        ops.conv2d(x, filt, dil=dil, pad=(dil,) * 4, pad_mode=(1, 1), out=out, engine=ops.ENGINE_UMMA)
+        ops.conv2d(x, filt, dil=dil, pad=(dil,) * 4, pad_mode=(1, 1), out=out, engine=ENGINE)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        ops.conv2d(x, filt, dil=dil, pad=(dil,) * 4, pad_mode=(1, 1), out=out, engine=ops.ENGINE_UMMA)
+        ops.conv2d(x, filt, dil=dil, pad=(dil,) * 4, pad_mode=(1, 1), out=out, engine=ENGINE)
     e1.record()
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print(f"conv3x3 {Cin}->{Cout} @ {H}x{W} batch {nb} dil {dil}: {ms:.4f} ms, "
+print(f"[{sys.argv[7] if len(sys.argv) > 7 else chr(117)+chr(109)+chr(109)+chr(97)}] conv3x3 {Cin}->{Cout} @ {H}x{W} batch {nb} dil {dil}: {ms:.4f} ms, "
       f"{2.0 * nb * H * W * Cout * 9 * Cin / ms / 1e9:.1f} TFLOP/s")
