@@ -13,10 +13,12 @@
 //     tap (ky,kx) is the SAME bytes addressed with start += ((ky*d)*HW + kx*d)*128 and SBO = HW*128 (HW = halo width).
 // L2->SM traffic per tile drops from ~220 KB to 23 KB and the LSU work by 10x; the kernel becomes MMA/epilogue bound.
 //
-// Warp roles (288 threads): warps 0-3 halo producers, warp 4 TMEM owner + MMA issuer (one thread), warps 5-8 epilogue.
-// Pipelines: halo ring (HS stages; full = 128 async cp.async arrivals, empty = tcgen05.commit) and a double-buffered
-// TMEM accumulator (full = tcgen05.commit, empty = 128 epilogue arrivals): tile i's epilogue overlaps tile i+1's MMAs
-// and tile i+2's halo loads.
+// Warp roles (320 threads): warps 0-3 halo producers, warps 4-5 MMA issuers (warp 4 owns TMEM), warps 6-9 epilogue.
+// Pipelines: halo ring (HS stages; full = 128 async cp.async arrivals, empty = tcgen05.commit) and four TMEM
+// accumulators (full = tcgen05.commit, empty = 128 epilogue arrivals): epilogue, MMA issue, tensor pipe and halo loads
+// of different tiles all overlap.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lns {
@@ -83,6 +85,33 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Leader-predicated forms: the WHOLE warp runs the issue loop (warp-uniform control flow, so descriptor arithmetic can
+// live in the uniform datapath) and only the elected lane's instruction takes effect.
+__device__ __forceinline__ void umma_bf16_if(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t leader, uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar),
+      "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -92,6 +121,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 }  // namespace hptx
 
 // K-major SWIZZLE_128B descriptor with an explicit stride-byte-offset (distance between 8-row groups)
@@ -124,29 +166,31 @@ struct HaloParams {
   int stages;          // halo ring depth
   int resize;          // 0 none, 1 exact 2x nearest, 2 general nearest
   float inv_hw, inv_hv, inv_wv;
+  int debug;  // LNS_HALO_DEBUG bits (timing experiments only): 1 skip halo copies, 2 skip epilogue, 4 skip MMAs
 };
 
-constexpr int kHaloThreads = 288;
+// kIssuers MMA issue warps (tile it -> issuer it % kIssuers), kAccs TMEM accumulator buffers (tile it -> it % kAccs)
 constexpr int kTileH = 16, kTileW = 8;
 
-template <int NT>
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloParams p) {
+template <int NT, int kIssuers, int kAccs>
+__global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (hptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - hptx::smem_u32(smem_raw));
   constexpr uint32_t kWBytes = 9u * NT * 128u;
   const uint32_t w_base = smem_base;
   const uint32_t halo_base = smem_base + kWBytes;
-  const uint32_t bar_base = halo_base + (uint32_t)p.stages * (uint32_t)p.halo_bytes;
-  // barriers: w, halo_full[4], halo_empty[4], acc_full[2], acc_empty[2]; then the TMEM slot
+  const uint32_t stage_out = halo_base + (uint32_t)p.stages * (uint32_t)p.halo_bytes;  // 4 warps x 4 KB output staging
+  const uint32_t bar_base = stage_out + 4u * 4096u;
+  // barriers: w, halo_full[4], halo_empty[4], acc_full[4], acc_empty[4]; then the TMEM slot
   const uint32_t w_bar = bar_base;
   auto halo_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto halo_empty = [&](int s) { return bar_base + 8u * (5 + s); };
   auto acc_full = [&](int a) { return bar_base + 8u * (9 + a); };
-  auto acc_empty = [&](int a) { return bar_base + 8u * (11 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * 13;
+  auto acc_empty = [&](int a) { return bar_base + 8u * (13 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * 17;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + 8 * 13);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + 4 * 4096 + 8 * 17);
 
   const ConvGeom& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -158,14 +202,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloPa
       hptx::mbar_init(halo_full(s), 128);
       hptx::mbar_init(halo_empty(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kAccs; ++a) {
       hptx::mbar_init(acc_full(a), 1);
       hptx::mbar_init(acc_empty(a), 128);
     }
     hptx::fence_mbar_init();
   }
   if (warp == 4) {
-    hptx::tmem_alloc(tmem_slot, 2 * NT);
+    hptx::tmem_alloc(tmem_slot, kAccs * NT);
     hptx::tmem_relinquish();
   }
   hptx::tc_fence_before();
@@ -181,86 +225,133 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloPa
       for (int tap = 0; tap < 9; ++tap)
         hptx::bulk_g2s(w_base + (uint32_t)tap * NT * 128u, p.w + (int64_t)tap * g.Cout * 64, (uint32_t)NT * 128u, w_bar);
     }
+    // The halo is a rectangle and the source index map is separable: offset(hy, hx) = rowterm(hy) + colterm(hx).
+    // Per tile, lane l of every producer warp evaluates rowterm(l) and colterm(l) once (wrap / zero padding / nearest
+    // resize; -1 marks "outside -> zero fill"); every 16-byte copy then costs two shuffles and an add.  (The first
+    // version recomputed the full map per pixel: an 80-instruction dependent chain x 12 passes per tile made the
+    // producers -- not the tensor pipe -- the bottleneck: 25% tensor-pipe active in the round-1 profile.)
     const int chunk = tid & 7;
     const int npx = p.HH * p.HW;
+    const int q_first = tid >> 3;                       // pixel of pass 0; +16 per pass (q & 7 is pass invariant)
+    const uint32_t dst_first = (uint32_t)q_first * 128u + (uint32_t)((chunk ^ (q_first & 7)) << 4);
+    const int step_y = 16 / p.HW, step_x = 16 - step_y * p.HW;
+    const int hy_first = q_first / p.HW, hx_first = q_first - hy_first * p.HW;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int s = it % HS;
-      if (it >= HS) hptx::mbar_wait(halo_empty(s), ((it / HS) & 1) ^ 1);
       int tx = tile % p.tiles_x;
       int t2 = tile / p.tiles_x;
       int ty = t2 % p.tiles_y;
       int b = t2 / p.tiles_y;
-      const int yv0 = ty * kTileH - g.dil, xv0 = tx * kTileW - g.dil;  // virtual coords of halo pixel (0,0)
+      // separable source terms, one halo row / column per lane (HH <= 22, HW <= 14)
+      int rowterm, colterm;
+      {
+        int yv = ty * kTileH - g.dil + lane, xv = tx * kTileW - g.dil + lane;
+        if (g.circ_h) {
+          yv += (yv < 0) ? g.Hv : 0;
+          yv -= (yv >= g.Hv) ? g.Hv : 0;
+        }
+        if (g.circ_w) {
+          xv += (xv < 0) ? g.Wv : 0;
+          xv -= (xv >= g.Wv) ? g.Wv : 0;
+        }
+        const bool yok = (unsigned)yv < (unsigned)g.Hv, xok = (unsigned)xv < (unsigned)g.Wv;
+        if (p.resize == 1) {
+          yv >>= 1;
+          xv >>= 1;
+        } else if (p.resize == 2) {
+          yv = __float2int_rd(((float)(yv * g.Hin) + 0.5f) * p.inv_hv);
+          xv = __float2int_rd(((float)(xv * g.Win) + 0.5f) * p.inv_wv);
+        }
+        rowterm = yok ? yv * g.Win * 64 : -1;
+        colterm = xok ? xv * 64 : -1;
+      }
+      if (it >= HS) hptx::mbar_wait(halo_empty(s), ((it / HS) & 1) ^ 1);
       const uint32_t st = halo_base + (uint32_t)s * (uint32_t)p.halo_bytes;
       const __nv_bfloat16* xb = p.x + (int64_t)b * g.x_bstride + chunk * 8;
-      for (int q0 = 0; q0 < npx; q0 += 16) {
-        const int q = q0 + (tid >> 3);
-        if (q < npx) {
-          int hy = __float2int_rd(((float)q + 0.5f) * p.inv_hw);
-          int hx = q - hy * p.HW;
-          int yv = yv0 + hy, xv = xv0 + hx;
-          if (g.circ_h) {
-            yv += (yv < 0) ? g.Hv : 0;
-            yv -= (yv >= g.Hv) ? g.Hv : 0;
-          }
-          if (g.circ_w) {
-            xv += (xv < 0) ? g.Wv : 0;
-            xv -= (xv >= g.Wv) ? g.Wv : 0;
-          }
-          const bool ok = ((unsigned)yv < (unsigned)g.Hv) && ((unsigned)xv < (unsigned)g.Wv);
-          if (p.resize == 1) {
-            yv >>= 1;
-            xv >>= 1;
-          } else if (p.resize == 2) {
-            yv = __float2int_rd(((float)(yv * g.Hin) + 0.5f) * p.inv_hv);
-            xv = __float2int_rd(((float)(xv * g.Win) + 0.5f) * p.inv_wv);
-          }
-          const void* src = ok ? (const void*)(xb + ((int64_t)yv * g.Win + xv) * 64) : (const void*)p.x;
-          hptx::cp_async16(st + (uint32_t)q * 128u + (uint32_t)((chunk ^ (q & 7)) << 4), src, ok ? 16u : 0u);
+      int hy = hy_first, hx = hx_first;
+      uint32_t dst = st + dst_first;
+      const int npass = (npx + 15) >> 4;  // warp-uniform trip count: the shuffles below need every lane
+      int q = q_first;
+#pragma unroll 4
+      for (int pass = 0; pass < npass; ++pass, q += 16) {
+        const int rt = __shfl_sync(0xFFFFFFFFu, rowterm, hy & 31);
+        const int ct = __shfl_sync(0xFFFFFFFFu, colterm, hx & 31);
+        if (q < npx && !(p.debug & 1)) {
+          const bool ok = (rt | ct) >= 0;
+          const void* src = ok ? (const void*)(xb + (rt + ct)) : (const void*)p.x;
+          hptx::cp_async16(dst, src, ok ? 16u : 0u);
+        }
+        dst += 2048u;
+        hy += step_y;
+        hx += step_x;
+        if (hx >= p.HW) {
+          hx -= p.HW;
+          ++hy;
         }
       }
       hptx::cp_async_arrive_noinc(halo_full(s));
     }
-  } else if (warp == 4) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
+  } else if (warp < 4 + kIssuers) {
+    // ============================== MMA issuers ==============================
+    // Two issue warps: warp 4 takes even tiles, warp 5 odd tiles (a single issuer's instruction stream -- ~10 SASS
+    // instructions per 32-cycle MMA at N=64 -- was slower than the tensor pipe).  tcgen05.commit tracks the issuing
+    // thread's own MMAs, and the two warps never share an accumulator, so no ordering between them is needed.
+    // All 32 lanes run this loop; lane 0's tcgen05.mma / tcgen05.commit are the ones that execute.  Descriptors are
+    // (hi, lo) 32-bit pairs: hi (SBO | version | swizzle mode) is loop invariant, lo is the 16-byte-unit start
+    // address = stage base + a per-(tap, k) constant -> one add per operand per MMA instead of rebuilding 64-bit
+    // descriptors in a single thread (which made the issue thread the bottleneck: 25% tensor-pipe in the first profile).
+    {
+      const uint32_t leader = (lane == 0) ? 1u : 0u;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)g.Cout >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t sbo = (uint32_t)p.HW * 128u;
+      const uint32_t desc_hi_a = (((uint32_t)p.HW * 128u) >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t desc_hi_b = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t w_lo = (w_base & 0x3FFFFu) >> 4;
+      const uint32_t row_lo = ((uint32_t)(g.dil * p.HW) * 128u) >> 4;  // one dilated halo row
+      const uint32_t col_lo = ((uint32_t)g.dil * 128u) >> 4;           // one dilated halo column
       hptx::mbar_wait(w_bar, 0);
+      const int me = warp - 4;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int s = it % HS, a = it & 1;
-        if (it >= 2) hptx::mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1);
+        if ((it % kIssuers) != me) continue;
+        const int s = it % HS, a = it % kAccs;
+        if (it >= kAccs) hptx::mbar_wait(acc_empty(a), ((it / kAccs) & 1) ^ 1);
         hptx::mbar_wait(halo_full(s), (it / HS) & 1);
         hptx::fence_proxy_async();
         hptx::tc_fence_after();
-        const uint32_t st = halo_base + (uint32_t)s * (uint32_t)p.halo_bytes;
+        const uint32_t st_lo = ((halo_base + (uint32_t)s * (uint32_t)p.halo_bytes) & 0x3FFFFu) >> 4;
         const uint32_t d_tmem = tmem_acc + (uint32_t)(a * NT);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - ky * 3;
-          const uint32_t a_addr = st + (uint32_t)((ky * g.dil) * p.HW + kx * g.dil) * 128u;
-          const uint32_t b_addr = w_base + (uint32_t)tap * NT * 128u;
+          const uint32_t a_lo = st_lo + (uint32_t)ky * row_lo + (uint32_t)kx * col_lo;
+          const uint32_t b_lo = w_lo + (uint32_t)tap * ((uint32_t)NT * 128u >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            hptx::umma_bf16(d_tmem, make_desc_sbo(a_addr + k * 32, sbo), make_desc_sbo(b_addr + k * 32, 1024u), idesc,
-                            (tap | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            hptx::umma_bf16_if((p.debug & 4) ? 0u : leader, d_tmem, a_lo + 2u * k, desc_hi_a, b_lo + 2u * k, desc_hi_b, idesc,
+                               (tap | k) != 0 ? 1u : 0u);
         }
-        hptx::umma_commit(halo_empty(s));
-        hptx::umma_commit(acc_full(a));
+        hptx::umma_commit_if(leader, halo_empty(s));
+        hptx::umma_commit_if(leader, acc_full(a));
       }
     }
     __syncwarp();
   } else {
-    // ============================== epilogue (warps 5..8) ==============================
+    // ============================== epilogue (last 4 warps) ==============================
+    // TMEM lane = tile pixel (row m = 8*tile_row + tile_col), so a thread owns one pixel's channels.  Writing them
+    // straight to global memory makes every store instruction touch 32 different 128-byte lines.  bf16 outputs are
+    // therefore staged per 64-channel group through a per-warp 32 x 128 B tile (16-byte chunks XOR-swizzled with the
+    // row so both the row-wise writes and the line-wise reads are conflict free) and leave as full-line stores:
+    // 8 consecutive rows = 8 consecutive pixels = 1 KB contiguous in NHWC.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int m = quad * 32 + lane;
     const int ty_l = m >> 3, tx_l = m & 7;
+    const uint32_t my_stage = stage_out + (uint32_t)(warp - (4 + kIssuers)) * 4096u;
+    const uint32_t my_row_st = my_stage + (uint32_t)lane * 128u;
+    const int rd_row = lane >> 3, rd_chunk = lane & 7;  // read-back: 4 rows per pass, 8 lanes x 16 B per row
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int a = it & 1;
+      const int a = it % kAccs;
       int tx = tile % p.tiles_x;
       int t2 = tile / p.tiles_x;
       int ty = t2 % p.tiles_y;
@@ -271,65 +362,91 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloPa
       const int64_t yrow = (int64_t)b * g.y_bstride + pix * g.Cout;
       const int64_t prow = (int64_t)b * p.pre_add_bstride + pix * g.Cout;
       const int64_t rrow = (int64_t)b * p.res_bstride + pix * g.Cout;
-      hptx::mbar_wait(acc_full(a), (it >> 1) & 1);
+      hptx::mbar_wait(acc_full(a), (it / kAccs) & 1);
       hptx::tc_fence_after();
       const uint32_t t_lane = tmem_acc + (uint32_t)(a * NT) + ((uint32_t)(quad * 32) << 16);
-      for (int c0 = 0; c0 < g.Cout; c0 += 16) {
-        uint32_t raw[16];
-        __syncwarp();
-        hptx::tmem_ld16(t_lane + (uint32_t)c0, raw);
-        hptx::tmem_ld_wait();
-        if (row_ok) {
-          float v[16];
+      for (int cg = 0; cg < ((p.debug & 2) ? 0 : g.Cout); cg += 64) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+        for (int cc = 0; cc < 64; cc += 32) {
+          const int c0 = cg + cc;
+          uint32_t raw[32];
+          __syncwarp();
+          hptx::tmem_ld32(t_lane + (uint32_t)c0, raw);
+          hptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
+            for (int j = 0; j < 32; j += 4) {
               float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
               v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
             }
           }
-          if (p.sample_bias) {
+          if (row_ok) {
+            if (p.sample_bias) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 t = __ldg(reinterpret_cast<const float4*>(p.sample_bias + (int64_t)b * g.Cout + c0 + j));
-              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              for (int j = 0; j < 32; j += 4) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(p.sample_bias + (int64_t)b * g.Cout + c0 + j));
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              }
             }
-          }
-          if (p.pre_add) {
+            if (p.pre_add) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 t = ld4_as_float(p.pre_add, p.pre_add_dtype, prow + c0 + j);
-              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              for (int j = 0; j < 32; j += 4) {
+                float4 t = ld4_as_float(p.pre_add, p.pre_add_dtype, prow + c0 + j);
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              }
             }
           }
           if (p.act != LNS_ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
           }
-          if (p.residual) {
+          if (row_ok && p.residual) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
+            for (int j = 0; j < 32; j += 4) {
               float4 t = ld4_as_float(p.residual, p.res_dtype, rrow + c0 + j);
               v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
             }
           }
           if (p.y_dtype == LNS_BF16) {
-            uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int h4 = 0; h4 < 4; ++h4) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              const int ch = (cc >> 3) + h4;  // 16-byte chunk index inside the 128-byte staged row
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_st + (uint32_t)((ch ^ (lane & 7)) << 4)),
+                           "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
             }
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yrow + c0);
-            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
+          } else if (row_ok) {
             float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yrow + c0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
+        }
+        if (p.y_dtype == LNS_BF16) {
+          __syncwarp();
+          // staged row r = 4*pass + rd_row of this warp's quadrant = tile row quad*4 + pass/2, tile col 4*(pass&1) + rd_row
+          const int yq = ty * kTileH + quad * 4, xq = tx * kTileW + rd_row;
+          __nv_bfloat16* qbase = reinterpret_cast<__nv_bfloat16*>(p.y) + (int64_t)b * g.y_bstride +
+                                 ((int64_t)yq * g.Wout + xq) * g.Cout + cg + rd_chunk * 8;
+          const int64_t row_stride = (int64_t)g.Wout * g.Cout;
+          const bool interior = (ty + 1) * kTileH <= g.Hout && (tx + 1) * kTileW <= g.Wout;  // warp uniform
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int r = pass * 4 + rd_row;
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(my_stage + (uint32_t)r * 128u + (uint32_t)((rd_chunk ^ (r & 7)) << 4)));
+            if (interior || (yq + (pass >> 1) < g.Hout && xq + 4 * (pass & 1) < g.Wout))
+              *reinterpret_cast<uint4*>(qbase + (pass >> 1) * row_stride + (pass & 1) * 4 * g.Cout) = make_uint4(w0, w1, w2, w3);
+          }
+          __syncwarp();
         }
       }
       hptx::tc_fence_before();
@@ -341,7 +458,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloPa
   __syncthreads();
   if (warp == 4) {
     hptx::tc_fence_after();
-    hptx::tmem_dealloc(tmem_acc, 2 * NT);
+    hptx::tmem_dealloc(tmem_acc, kAccs * NT);
   }
 }
 
@@ -353,9 +470,9 @@ bool conv_halo_supported(const LnsConvDesc* d) {
          d->dil <= d->Hv && d->dil <= d->Wv;
 }
 
-template <int NT>
+template <int NT, int KI, int KA>
 static int launch_halo(const HaloParams& p, int smem_bytes, int grid, cudaStream_t stream) {
-  auto kern = conv_halo_kernel<NT>;
+  auto kern = conv_halo_kernel<NT, KI, KA>;
   static bool once = false;
   if (!once) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -365,7 +482,7 @@ static int launch_halo(const HaloParams& p, int smem_bytes, int grid, cudaStream
     }
     once = true;
   }
-  kern<<<grid, kHaloThreads, smem_bytes, stream>>>(p);
+  kern<<<grid, 32 * (4 + KI + 4), smem_bytes, stream>>>(p);
   return check_launch("conv_halo_kernel");
 }
 
@@ -403,8 +520,12 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
   p.inv_hw = 1.0f / (float)p.HW;
   p.inv_hv = 1.0f / (float)d->Hv;
   p.inv_wv = 1.0f / (float)d->Wv;
+  {
+    const char* dbg = getenv("LNS_HALO_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   const int NT = d->Cout;
-  const int fixed = 9 * NT * 128 + 256 + 1024;
+  const int fixed = 9 * NT * 128 + 4 * 4096 /*output staging*/ + 256 + 1024;
   int stages = (227 * 1024 - fixed) / p.halo_bytes;
   if (stages > 4) stages = 4;
   LNS_REQUIRE(stages >= 2, "lns_conv2d(halo): shared memory too small for dilation %d with Cout %d", d->dil, d->Cout);
@@ -422,8 +543,19 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
     sms = cached;
   }
   int grid = p.ntiles < sms ? p.ntiles : sms;
-  if (NT == 64) return launch_halo<64>(p, smem, grid, stream);
-  return launch_halo<128>(p, smem, grid, stream);
+  int cfg = 0;
+  {
+    const char* c = getenv("LNS_HALO_CFG");  // tuning: 0 = 1 issuer / 2 accumulators, 1 = 1/4, 2 = 2/4 (default, fastest on B200)
+    cfg = c ? atoi(c) : 2;
+  }
+  if (NT == 64) {
+    if (cfg == 1) return launch_halo<64, 1, 4>(p, smem, grid, stream);
+    if (cfg == 2) return launch_halo<64, 2, 4>(p, smem, grid, stream);
+    return launch_halo<64, 1, 2>(p, smem, grid, stream);
+  }
+  if (cfg == 1) return launch_halo<128, 1, 4>(p, smem, grid, stream);
+  if (cfg == 2) return launch_halo<128, 2, 4>(p, smem, grid, stream);
+  return launch_halo<128, 1, 2>(p, smem, grid, stream);
 }
 
 }  // namespace lns

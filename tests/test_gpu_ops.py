@@ -381,3 +381,10 @@ def test_conv_halo_bf16(case):
     torch.cuda.synchronize()
     assert tuple(act_to_nchw(y).shape) == tuple(ref.shape)
     assert relerr(act_to_nchw(y), ref) < 5e-6
+    with ops.precision("bf16"):  # bf16 output: the shared-memory staged, full-line store path of the epilogue
+        y16 = ops.conv2d(act_from(x, torch.bfloat16), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4,
+                         pad_mode=modes, virt=virt, act=ops.ACT_GELU, residual=act_from(res, torch.bfloat16),
+                         engine=ops.ENGINE_HALO)
+    torch.cuda.synchronize()
+    assert y16.t.dtype == torch.bfloat16
+    assert torch.equal(act_to_nchw(y16), act_to_nchw(y).bfloat16().float())  # same values, rounded once
