@@ -135,6 +135,11 @@ int lns_chan_stats(const void* x, int dtype, int B, int H, int W, int C, int64_t
 int lns_norm_finalize(const float* partial, int B, int nchunk, int C, int HW, int G, float eps,
                       const float* gamma, const float* beta, const float* prescale, float* scale,
                       float* shift, void* stream);
+/* statistics + finalize in one call: one fused kernel when the sample has <= 1024 pixels (lns_chan_stats_chunks == 1),
+ * otherwise lns_chan_stats + lns_norm_finalize through `partial_ws` (B*nchunk*C*2 floats; may be NULL when nchunk == 1) */
+int lns_group_norm_affine(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int G, float eps,
+                          const float* gamma, const float* beta, const float* prescale, float* partial_ws,
+                          float* scale, float* shift, void* stream);
 /* y = act(x*scale[b][c] + shift[b][c]) (+ NULL scale -> activation only); NHWC in/out */
 int lns_affine_act(const void* x, int x_dtype, int64_t x_bstride, int B, int HW, int C, const float* scale,
                    const float* shift, int act, void* y, int y_dtype, int64_t y_bstride, void* stream);
@@ -177,6 +182,12 @@ int lns_nchw_to_nhwc(const float* x, int B, int C, int H, int W, int64_t x_bstri
                      int64_t y_bstride, void* stream);
 int lns_nhwc_to_nchw(const void* x, int x_dtype, int B, int H, int W, int C, int64_t x_bstride, float* y,
                      int64_t y_bstride, void* stream);
+/* decoder output projection: y[b][n][pix] (NCHW fp32) = bias[n] + sum_c w[n][c] * act(x[b][pix][c]*scale[b][c] + shift[b][c]),
+ * Cout <= 4 -- the GroupNorm -> Swish -> Conv1x1(C -> in_channels) tail, modules/autoencoder2d.py:149-151.
+ * x NHWC (fp32|bf16); w [Cout][C] fp32 (the nn.Conv2d weight as is); scale/shift [B][C] or NULL. */
+int lns_pointwise_proj(const void* x, int dtype, int B, int HW, int C, int64_t x_bstride, const float* w,
+                       const float* bias, int Cout, const float* scale, const float* shift, int act, float* y,
+                       int64_t y_bstride, void* stream);
 /* sinusoidal embedding cat(cos(p f), sin(p f)), f_i = exp(-ln(max_period) i / (dim/2))
  * modules/cond_utils.py:19-38 */
 int lns_fourier_embedding(const float* param, int B, int dim, float max_period, float* out, void* stream);

@@ -47,6 +47,8 @@ SIGNATURES = {
     "lns_chan_stats_chunks": (i32, [i32, i32]),
     "lns_chan_stats": (i32, [vp, i32, i32, i32, i32, i32, i64, vp, vp]),
     "lns_norm_finalize": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
+    "lns_group_norm_affine": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, f32, vp, vp, vp, vp, vp, vp, vp]),
+    "lns_pointwise_proj": (i32, [vp, i32, i32, i32, i32, i64, vp, vp, i32, vp, vp, i32, vp, i64, vp]),
     "lns_affine_act": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, i32, vp, i32, i64, vp]),
     "lns_layernorm": (i32, [vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp]),
     "lns_attention": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, i32, vp]),

@@ -263,6 +263,134 @@ __global__ void __launch_bounds__(128) axial_contract_mma_kernel(const __nv_bflo
   }
 }
 
+
+// ---- SABlock attention on tensor cores (bf16 in / bf16 out, head dim 64) ---------------------------------------------
+// grid (heads, B), block 128.  Q, K, V head slices are staged in shared memory (bf16, 72-element rows: conflict-free
+// ldmatrix); each warp owns 16-query tiles and walks the keys in blocks of 64 with an online softmax (exp2, fp32
+// statistics): S = Q K^T and O += P V are mma.sync.m16n8k16, P never leaves registers (S accumulator fragments are
+// re-packed as the A operand of the second GEMM).
+constexpr int kAttStride = 72;
+
+__global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int n, int heads,
+                                                             float scale_log2e, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int n16 = (n + 15) & ~15;
+  const int nk = (n + 63) & ~63;  // keys padded to whole 64-key blocks (zero rows, masked below)
+  __nv_bfloat16* Q_s = reinterpret_cast<__nv_bfloat16*>(smraw);
+  __nv_bfloat16* K_s = Q_s + (size_t)n16 * kAttStride;
+  __nv_bfloat16* V_s = K_s + (size_t)nk * kAttStride;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int hd = heads * 64;
+  const int64_t row_stride = 3 * (int64_t)hd;
+  const __nv_bfloat16* base = qkv + (int64_t)b * n * row_stride + h * 64;
+  // stage Q | K | V : 8 x 16-byte chunks per token row
+  for (int e = tid; e < (n16 + 2 * nk) * 8; e += 128) {
+    int ch = e & 7, r = e >> 3;
+    int which, tok;
+    __nv_bfloat16* dst;
+    if (r < n16) { which = 0; tok = r; dst = Q_s + (size_t)tok * kAttStride; }
+    else if (r < n16 + nk) { which = 1; tok = r - n16; dst = K_s + (size_t)tok * kAttStride; }
+    else { which = 2; tok = r - n16 - nk; dst = V_s + (size_t)tok * kAttStride; }
+    if (tok < n) {
+      uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst + ch * 8);
+      const __nv_bfloat16* src = base + (int64_t)tok * row_stride + which * hd + ch * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(src) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dst + ch * 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  for (int mt = warp; mt < (n16 >> 4); mt += 4) {
+    // Q fragments for the 4 k-steps of d = 64
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ldmatrix_x4((uint32_t)__cvta_generic_to_shared(Q_s + (size_t)(mt * 16 + (lane & 15)) * kAttStride + ks * 16 + (lane >> 4) * 8),
+                  qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // running max / sum of rows g and g + 8
+    for (int kb = 0; kb < nk; kb += 64) {
+      float sacc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t b0, b1;
+          // K rows are keys, columns d: the (non-transposed) 8x8 tiles are exactly the col-major B fragments
+          asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1)
+                       : "r"((uint32_t)__cvta_generic_to_shared(K_s + (size_t)(kb + nt * 8 + (lane & 7)) * kAttStride + ks * 16 + ((lane >> 3) & 1) * 8)));
+          mma_bf16_16816(sacc[nt], qa[ks], b0, b1);
+        }
+      }
+      // scale, mask padded keys, block max
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        int key = kb + nt * 8 + t * 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v = sacc[nt][j] * scale_log2e;
+          if (key + (j & 1) >= n) v = -INFINITY;
+          sacc[nt][j] = v;
+        }
+        bm0 = fmaxf(bm0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        bm1 = fmaxf(bm1, fmaxf(sacc[nt][2], sacc[nt][3]));
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
+      const float c0 = exp2f(m0 - nm0), c1 = exp2f(m1 - nm1);  // first block: exp2(-inf) = 0
+      m0 = nm0; m1 = nm1;
+      l0 *= c0; l1 *= c1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sacc[nt][0] = exp2f(sacc[nt][0] - m0); sacc[nt][1] = exp2f(sacc[nt][1] - m0);
+        sacc[nt][2] = exp2f(sacc[nt][2] - m1); sacc[nt][3] = exp2f(sacc[nt][3] - m1);
+        rs0 += sacc[nt][0] + sacc[nt][1];
+        rs1 += sacc[nt][2] + sacc[nt][3];
+      }
+      l0 += rs0; l1 += rs1;
+      // O += P V over this key block: 4 k-steps of 16 keys
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[4];
+        __nv_bfloat162 h;
+        h = __floats2bfloat162_rn(sacc[2 * kk][0], sacc[2 * kk][1]); pa[0] = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(sacc[2 * kk][2], sacc[2 * kk][3]); pa[1] = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]); pa[2] = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]); pa[3] = *reinterpret_cast<uint32_t*>(&h);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          uint32_t b0, b1;
+          ldmatrix_x2_trans((uint32_t)__cvta_generic_to_shared(V_s + (size_t)(kb + kk * 16 + (lane & 15)) * kAttStride + nt * 8), b0, b1);
+          mma_bf16_16816(o[nt], pa, b0, b1);
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      int col = h * 64 + nt * 8 + t * 2;
+      if (r0 < n) *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)b * n + r0) * hd + col) = __floats2bfloat162_rn(o[nt][0] * i0, o[nt][1] * i0);
+      if (r1 < n) *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)b * n + r1) * hd + col) = __floats2bfloat162_rn(o[nt][2] * i1, o[nt][3] * i1);
+    }
+  }
+}
+
 }  // namespace lns
 
 extern "C" {
@@ -271,6 +399,19 @@ int lns_attention(const void* qkv, int dtype, int B, int n, int heads, int dh, f
                   void* stream) {
   LNS_REQUIRE(qkv && out && B > 0 && n > 0 && heads > 0 && dh > 0, "lns_attention: bad arguments");
   LNS_REQUIRE(B <= 65535, "lns_attention: batch %d exceeds grid limit, chunk the call", B);
+  if (dtype == LNS_BF16 && out_dtype == LNS_BF16 && dh == 64) {
+    // tensor-core path (the bf16 rollout)
+    int n16 = (n + 15) & ~15, nk = (n + 63) & ~63;
+    size_t smem_mma = ((size_t)n16 + 2 * (size_t)nk) * lns::kAttStride * sizeof(__nv_bfloat16);
+    if (smem_mma <= 227 * 1024) {
+      { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+      dim3 grid(heads, B);
+      lns::attention_mma_kernel<<<grid, 128, smem_mma, reinterpret_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const __nv_bfloat16*>(qkv), n, heads, scale * 1.4426950408889634f,
+          reinterpret_cast<__nv_bfloat16*>(out));
+      return lns::check_launch("attention_mma_kernel");
+    }
+  }
   size_t smem = ((size_t)n * (dh + 1) + (size_t)n * dh + 8 * dh + 8 * (size_t)n) * sizeof(float);
   LNS_REQUIRE(smem <= 227 * 1024, "lns_attention: n=%d dh=%d needs %zu B shared memory", n, dh, smem);
   { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }

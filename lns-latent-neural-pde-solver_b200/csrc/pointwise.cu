@@ -1,0 +1,168 @@
+// HBM-bound pointwise kernels at the full-resolution end of the decoder and the single-kernel GroupNorm statistics.
+#include "common.cuh"
+
+namespace lns {
+
+// ---- output projection: y[b][n][pix] = bias[n] + sum_c w[n][c] * act(x[b][pix][c]*scale[b][c] + shift[b][c]) ------------
+// (decoder tail GroupNorm -> Swish -> Conv1x1(C -> in_channels), modules/autoencoder2d.py:149-151).  One thread per pixel:
+// reads its C channels with 16-byte loads (a warp covers 32 consecutive pixels = one contiguous 4 KB / 8 KB span), keeps
+// the Cout <= 4 dot products in registers, writes NCHW fp32 (consecutive lanes -> consecutive addresses).  The per-sample
+// affine and the weights sit in shared memory.  grid (ceil(HW/256), B).
+template <int COUT>
+__global__ void __launch_bounds__(256) pointwise_proj_kernel(const void* __restrict__ x, int dtype, int HW, int C, int64_t x_bstride,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              const float* __restrict__ scale, const float* __restrict__ shift,
+                                                              int act, float* __restrict__ y, int64_t y_bstride) {
+  extern __shared__ float sm[];  // w [COUT][C], scale [C], shift [C]
+  float* w_s = sm;
+  float* sc_s = sm + COUT * C;
+  float* sh_s = sc_s + C;
+  const int b = blockIdx.y;
+  for (int e = threadIdx.x; e < COUT * C; e += 256) w_s[e] = w[e];
+  for (int e = threadIdx.x; e < C; e += 256) {
+    sc_s[e] = scale ? scale[(int64_t)b * C + e] : 1.f;
+    sh_s[e] = shift ? shift[(int64_t)b * C + e] : 0.f;
+  }
+  __syncthreads();
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= HW) return;
+  float acc[COUT];
+#pragma unroll
+  for (int n = 0; n < COUT; ++n) acc[n] = bias ? bias[n] : 0.f;
+  const int64_t base = (int64_t)b * x_bstride + (int64_t)pix * C;
+  for (int c = 0; c < C; c += 4) {
+    float4 v = ld4_as_float(x, dtype, base + c);
+    float u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = apply_act(fmaf(u[j], sc_s[c + j], sh_s[c + j]), act);
+#pragma unroll
+      for (int n = 0; n < COUT; ++n) acc[n] = fmaf(t, w_s[n * C + c + j], acc[n]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < COUT; ++n) y[(int64_t)b * y_bstride + (int64_t)n * HW + pix] = acc[n];
+}
+
+// ---- GroupNorm statistics + finalize in ONE kernel (samples of <= 1024 pixels: every layer below 64x64) ------------------
+// grid B, block 256.  Same deterministic reduction order as chan_stats_kernel + norm_finalize_kernel.
+__global__ void __launch_bounds__(256) gn_affine_small_kernel(const void* __restrict__ x, int dtype, int HW, int C, int64_t bstride,
+                                                               int G, float eps, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const float* __restrict__ prescale,
+                                                               float* __restrict__ scale, float* __restrict__ shift) {
+  extern __shared__ float red[];  // [rows][C][2] floats, then [C][2] doubles (aliased after the first phase)
+  const int cg = C >> 2;
+  const int rows = 256 / cg;
+  const int q = threadIdx.x % cg, lane = threadIdx.x / cg;
+  const int b = blockIdx.x;
+  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  if (lane < rows) {
+    // 4 independent 16-byte loads in flight per thread (the accumulation order stays p = lane, lane+rows, ...)
+    int p = lane;
+    for (; p + 3 * rows < HW; p += 4 * rows) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld4_as_float(x, dtype, (int64_t)b * bstride + (int64_t)(p + u * rows) * C + q * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[0] += v[u].x; ss[0] = fmaf(v[u].x, v[u].x, ss[0]);
+        s[1] += v[u].y; ss[1] = fmaf(v[u].y, v[u].y, ss[1]);
+        s[2] += v[u].z; ss[2] = fmaf(v[u].z, v[u].z, ss[2]);
+        s[3] += v[u].w; ss[3] = fmaf(v[u].w, v[u].w, ss[3]);
+      }
+    }
+    for (; p < HW; p += rows) {
+      float4 v = ld4_as_float(x, dtype, (int64_t)b * bstride + (int64_t)p * C + q * 4);
+      s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
+      s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
+      s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
+      s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[((lane * C) + q * 4 + j) * 2 + 0] = s[j];
+      red[((lane * C) + q * 4 + j) * 2 + 1] = ss[j];
+    }
+  }
+  __syncthreads();
+  double* csum = reinterpret_cast<double*>(red + (size_t)rows * C * 2);  // [C][2]
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double a = 0.0, a2 = 0.0;
+    for (int l = 0; l < rows; ++l) {
+      a += (double)red[((l * C) + c) * 2 + 0];
+      a2 += (double)red[((l * C) + c) * 2 + 1];
+    }
+    // the two-kernel path stores these partials as fp32 before the finalize: round identically
+    csum[c * 2 + 0] = (double)(float)a;
+    csum[c * 2 + 1] = (double)(float)a2;
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int gi = threadIdx.x; gi < G; gi += 256) {
+    double sum = 0.0, sumsq = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      int c = gi * cpg + j;
+      double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
+      sum += ps * csum[c * 2 + 0];
+      sumsq += ps * ps * csum[c * 2 + 1];
+    }
+    double n = (double)cpg * (double)HW;
+    double mean = sum / n;
+    double var = sumsq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    double rstd = 1.0 / sqrt(var + (double)eps);
+    for (int j = 0; j < cpg; ++j) {
+      int c = gi * cpg + j;
+      double ga = gamma ? (double)gamma[c] : 1.0;
+      double be = beta ? (double)beta[c] : 0.0;
+      double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
+      scale[(int64_t)b * C + c] = (float)(ps * rstd * ga);
+      shift[(int64_t)b * C + c] = (float)(be - mean * rstd * ga);
+    }
+  }
+}
+
+}  // namespace lns
+
+extern "C" {
+
+int lns_pointwise_proj(const void* x, int dtype, int B, int HW, int C, int64_t x_bstride, const float* w, const float* bias,
+                       int Cout, const float* scale, const float* shift, int act, float* y, int64_t y_bstride, void* stream) {
+  LNS_REQUIRE(x && w && y && B > 0 && HW > 0 && C > 0 && C % 4 == 0 && C <= 512 && Cout >= 1 && Cout <= 4 && B <= 65535,
+              "lns_pointwise_proj: bad arguments (C=%d, Cout=%d)", C, Cout);
+  LNS_REQUIRE(x_bstride % 4 == 0, "lns_pointwise_proj: batch stride must be a multiple of 4");
+  LNS_REQUIRE(!(scale && !shift), "lns_pointwise_proj: scale without shift");
+  dim3 grid(lns::cdiv(HW, 256), B);
+  size_t smem = ((size_t)Cout * C + 2 * (size_t)C) * sizeof(float);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (Cout) {
+    case 1: lns::pointwise_proj_kernel<1><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride); break;
+    case 2: lns::pointwise_proj_kernel<2><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride); break;
+    case 3: lns::pointwise_proj_kernel<3><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride); break;
+    default: lns::pointwise_proj_kernel<4><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride); break;
+  }
+  return lns::check_launch("pointwise_proj_kernel");
+}
+
+int lns_group_norm_affine(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int G, float eps,
+                          const float* gamma, const float* beta, const float* prescale, float* partial_ws, float* scale,
+                          float* shift, void* stream) {
+  LNS_REQUIRE(x && scale && shift && B > 0 && H > 0 && W > 0 && G > 0 && C % G == 0, "lns_group_norm_affine: bad arguments");
+  int cg = C / 4;
+  LNS_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024 && (cg & (cg - 1)) == 0,
+              "lns_group_norm_affine: C must be a power of two in [4,1024] (got %d)", C);
+  int nchunk = lns_chan_stats_chunks(H, W);
+  if (nchunk == 1) {
+    int rows = 256 / cg;
+    size_t smem = (size_t)rows * C * 2 * sizeof(float) + (size_t)C * 2 * sizeof(double);
+    lns::gn_affine_small_kernel<<<B, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, dtype, H * W, C, bstride, G, eps,
+                                                                                           gamma, beta, prescale, scale, shift);
+    return lns::check_launch("gn_affine_small_kernel");
+  }
+  LNS_REQUIRE(partial_ws != nullptr, "lns_group_norm_affine: workspace of B*nchunk*C*2 floats needed for H*W > 1024");
+  int rc = lns_chan_stats(x, dtype, B, H, W, C, bstride, partial_ws, stream);
+  if (rc) return rc;
+  return lns_norm_finalize(partial_ws, B, nchunk, C, H * W, G, eps, gamma, beta, prescale, scale, shift, stream);
+}
+
+}  // extern "C"

@@ -253,6 +253,10 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     pt, pb, pl, pr = pad
     Hout = (Hv + pt + pb - dil * (KH - 1) - 1) // stride + 1
     Wout = (Wv + pl + pr - dil * (KW - 1) - 1) // stride + 1
+    if (engine is None and KH == 1 and KW == 1 and Cout <= 4 and out_layout == NCHW and x.layout == NHWC and Cin % 4 == 0
+            and Cin <= 512 and stride == 1 and virt is None and act == ACT_NONE and pre_add is None and residual is None
+            and sample_bias is None and (out is None or out.t.dtype == torch.float32) and x.B <= 65535):
+        return _pointwise_proj(x, filt, use_bias, pro, out)
     if engine is None:
         engine = ENGINE_UMMA if _umma_ok(x, Cin, Cout, out_layout) else ENGINE_SIMT
         if (engine == ENGINE_UMMA and KH == 3 and KW == 3 and stride == 1 and Cin == 64 and Cout in (64, 128)
@@ -304,6 +308,27 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     return out
 
 
+def _pointwise_proj(x, filt, use_bias, pro, out):
+    """Cout <= 4 output projection (NHWC -> NCHW fp32) with the norm/activation prologue: lns_pointwise_proj."""
+    Cout, Cin, _, _ = filt.dims()
+    w = filt.get(W_SIMT_F32)  # [1 tap][Cin][Cout] fp32 == [Cin][Cout]; the kernel wants [Cout][Cin]
+    key = ("proj", w.data_ptr())
+    wt = filt._cache.get(key)
+    if wt is None:
+        wt = w.view(torch.float32).view(Cin, Cout).t().contiguous()
+        filt._cache[key] = wt
+    if out is None:
+        out = Act(torch.empty(x.B * Cout * x.H * x.W, dtype=torch.float32, device=x.t.device), x.B, x.H, x.W, Cout,
+                  layout=NCHW)
+    bias = filt.bias() if use_bias else None
+    sc, sh, pa = (pro if pro is not None else (None, None, ACT_NONE))
+    rc = _C.lib().lns_pointwise_proj(_ptr(x.t), x.dtype, x.B, x.H * x.W, Cin, x.bstride, _ptr(wt), _ptr(bias), Cout,
+                                     _ptr(sc), _ptr(sh), pa, _ptr(out.t), out.bstride, _stream())
+    check(rc, "lns_pointwise_proj")
+    _state.launches += 1
+    return out
+
+
 # ---- normalisation ------------------------------------------------------------------------------------------
 def chan_stats(x):
     """-> (partial [B,nchunk,C,2] fp32, nchunk)"""
@@ -316,16 +341,20 @@ def chan_stats(x):
 
 
 def group_norm_affine(x, groups, eps, gamma=None, beta=None, prescale=None):
-    """GroupNorm(groups) statistics of (x * prescale) folded with gamma/beta into per-(sample,channel) (scale, shift)."""
-    part, nchunk = chan_stats(x)
+    """GroupNorm(groups) statistics of (x * prescale) folded with gamma/beta into per-(sample,channel) (scale, shift).
+    One fused kernel for samples of <= 1024 pixels, statistics + finalize kernels above that."""
+    nchunk = _C.lib().lns_chan_stats_chunks(x.H, x.W)
+    part = None
+    if nchunk > 1:
+        part = torch.empty(x.B * nchunk * x.C * 2, dtype=torch.float32, device=x.t.device)
     scale = torch.empty(x.B * x.C, dtype=torch.float32, device=x.t.device)
     shift = torch.empty_like(scale)
     g = gamma.detach().float().contiguous() if gamma is not None else None
     b = beta.detach().float().contiguous() if beta is not None else None
-    rc = _C.lib().lns_norm_finalize(_ptr(part), x.B, nchunk, x.C, x.H * x.W, groups, float(eps), _ptr(g), _ptr(b),
-                                    _ptr(prescale), _ptr(scale), _ptr(shift), _stream())
-    check(rc, "lns_norm_finalize")
-    _state.launches += 1
+    rc = _C.lib().lns_group_norm_affine(_ptr(x.t), x.dtype, x.B, x.H, x.W, x.C, x.bstride, groups, float(eps), _ptr(g),
+                                        _ptr(b), _ptr(prescale), _ptr(part), _ptr(scale), _ptr(shift), _stream())
+    check(rc, "lns_group_norm_affine")
+    _state.launches += 1 if nchunk == 1 else 2
     return scale, shift
 
 

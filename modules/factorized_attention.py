@@ -46,7 +46,8 @@ class LowRankKernel(LnsModule):
         if self.qk_norm:
             raise LnsError("LowRankKernel: qk_norm=True is not on the rollout path")
         n = u.H * u.W
-        qk = ops.conv2d(u, filt_of(self.to_qk), out_dtype=torch.float32)
+        # [B, n, 2*heads*d]: fp32 on the validation path, bf16 (half the bytes; it is read once) on the bf16 path
+        qk = ops.conv2d(u, filt_of(self.to_qk), out_dtype=torch.float32 if u.t.dtype == torch.float32 else ops.act_dtype())
         cos_t, sin_t = self._tables(n, u.t.device)
         return ops.lowrank_kernel(qk, self.heads, self.dim_head, cos_t, sin_t, self.scaling)
 
@@ -71,7 +72,9 @@ class PoolingReducer(LnsModule):
         ln = self.out_ffn[0]
         h = ops.layernorm(h, ln.weight, ln.bias, ln.eps)
         h = ops.conv2d(h, filt_of(self.out_ffn[1]), act=ops.ACT_GELU, out_dtype=f32)
-        return ops.conv2d(h, filt_of(self.out_ffn[3]), out_dtype=f32)
+        # in the bf16 mode the result is stored as bf16 so that the 64 -> 2048 to_qk GEMM (the only sizeable GEMM of the
+        # pooled branch) runs on the tensor-core engine
+        return ops.conv2d(h, filt_of(self.out_ffn[3]), out_dtype=ops.act_dtype())
 
 
 class _SwapAxes(nn.Module):

@@ -388,3 +388,42 @@ def test_conv_halo_bf16(case):
     torch.cuda.synchronize()
     assert y16.t.dtype == torch.bfloat16
     assert torch.equal(act_to_nchw(y16), act_to_nchw(y).bfloat16().float())  # same values, rounded once
+
+
+@pytest.mark.parametrize("n_hw", [(8, 8), (12, 24), (7, 15)])
+def test_attention_tensor_core_bf16(n_hw):
+    """mma.sync flash-style attention (bf16 in/out) vs fp64 softmax attention of the same bf16-rounded q, k, v"""
+    ops = ops_mod()
+    H, W = n_hw
+    n, heads, dh = H * W, 8, 64
+    g = torch.Generator().manual_seed(17)
+    qkv = torch.randn(3, n, 3 * heads * dh, generator=g)
+    qr = qkv.bfloat16().double()
+    q, k, v = [t.view(3, n, heads, dh).transpose(1, 2) for t in qr.split(heads * dh, dim=-1)]
+    attn = F.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, dim=-1)
+    ref = (attn @ v).transpose(1, 2).reshape(3, n, heads * dh)
+    a = ops.Act(qkv.to(DEV).bfloat16().reshape(-1), 3, H, W, 3 * heads * dh)
+    y = ops.attention(a, heads, dh, dh ** -0.5)
+    assert y.t.dtype == torch.bfloat16
+    assert relerr(y.as_tokens().float().cpu(), ref) < 6e-3  # P and the output are rounded to bf16
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pointwise_projection(dtype):
+    """GroupNorm -> Swish -> Conv1x1(64 -> 3) decoder tail as one kernel, NCHW fp32 output into a strided slot"""
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(23)
+    B, C, H, W, Co = 3, 64, 20, 33, 3
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(Co, C, 1, 1, generator=g) / 8
+    b = torch.randn(Co, generator=g)
+    sc, sh = torch.rand(B, C, generator=g) + 0.5, torch.randn(B, C, generator=g) * 0.2
+    xin = F.silu(x.to(dtype).double() * sc[:, :, None, None].double() + sh[:, :, None, None].double())
+    ref = F.conv2d(xin, w.double(), b.double())
+    h = Holder(w, b)
+    out = torch.zeros(B, 2, Co, H, W, device=DEV)
+    dst = ops.Act(out.view(-1)[Co * H * W:], B, H, W, Co, bstride=2 * Co * H * W, layout=ops.NCHW)
+    ops.conv2d(act_from(x, dtype), ops.PackedFilter.of(h.weight, h.bias),
+               pro=(sc.to(DEV).reshape(-1), sh.to(DEV).reshape(-1), ops.ACT_SILU), out=dst, out_layout=ops.NCHW)
+    assert relerr(out[:, 1].cpu(), ref) < 3e-6
+    assert float(out[:, 0].abs().max()) == 0.0
