@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the final all-gather of fields for N > 1")
+    ap.add_argument("--decode-chunk", type=int, default=None, help="samples per decode launch group (default: engine's)")
     return ap.parse_args()
 
 
@@ -216,7 +217,8 @@ def main():
     x_dev = x_cpu.to(device)
     p_dev = p_cpu.to(device) if p_cpu is not None else None
 
-    ro = Rollout(model, batch=B, steps=R, to_x=True, precision=args.precision, use_graph=True)
+    ro = Rollout(model, batch=B, steps=R, to_x=True, precision=args.precision, use_graph=True,
+                 decode_chunk=args.decode_chunk)
     with torch.no_grad():
         ro.build()
         ro(x_dev, p_dev)

@@ -140,6 +140,12 @@ int lns_norm_finalize(const float* partial, int B, int nchunk, int C, int HW, in
 int lns_group_norm_affine(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int G, float eps,
                           const float* gamma, const float* beta, const float* prescale, float* partial_ws,
                           float* scale, float* shift, void* stream);
+/* GroupNorm statistics + apply + activation in ONE kernel for samples that fit in 48 KB of shared memory as fp32 (the
+ * latent-grid layers: 8x8x128, 7x15x64 ...): y = act(GroupNorm(G)(x * prescale)); lns_group_norm_act_supported() tells. */
+int lns_group_norm_act_supported(int H, int W, int C);
+int lns_group_norm_act(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int G, float eps,
+                       const float* gamma, const float* beta, const float* prescale, int act, void* y, int y_dtype,
+                       int64_t y_bstride, void* stream);
 /* y = act(x*scale[b][c] + shift[b][c]) (+ NULL scale -> activation only); NHWC in/out */
 int lns_affine_act(const void* x, int x_dtype, int64_t x_bstride, int B, int HW, int C, const float* scale,
                    const float* shift, int act, void* y, int y_dtype, int64_t y_bstride, void* stream);
@@ -173,6 +179,23 @@ int lns_lowrank_kernel(const void* qk, int dtype, int B, int n, int heads, int d
  * (the two einsums at modules/factorized_attention.py:157-158); u,out NHWC with C = heads*ch */
 int lns_axial_contract(const void* u, int dtype, int B, int H, int W, int heads, int ch, const float* K,
                        int axis, void* out, int out_dtype, void* stream);
+
+/* Fused FABlock2D core for the bf16 path (one CTA per (sample, head); u_phi never leaves shared memory):
+ *   in_proj (GroupNorm(1) folded into a per-sample filter/bias) -> contraction over H with Kx -> contraction over W with
+ *   Ky -> InstanceNorm2d (eps, no affine) -> out [B][H][W][heads*64] bf16, ready for to_out's 1x1 convs.
+ * u: NHWC bf16 [B][H][W][64] (the block's RAW input); gn_scale/gn_shift [B][64] from lns_group_norm_affine(G=1);
+ * w_in_proj: the nn.Conv2d weight [heads*64][64] fp32 as stored; Kx [B][heads][H][H], Ky [B][heads][W][W] fp32.
+ * modules/factorized_attention.py:146-158 + the InstanceNorm2d of :139.  lns_fablock_core_supported() tells whether the
+ * shape fits (H, W <= 48 and H*W*144 B + ~50 KB of shared memory); otherwise use the unfused entry points above. */
+int lns_fablock_core_supported(int H, int W, int dim, int dim_head);
+/* FABlock2D pre-pass: one read of the block input u [B][H][W][C] -> GroupNorm(1,C) affine scale/shift [B][C] AND the two
+ * pooled, normalised tensors pooled_x [B][H][C] = mean_W(GN(u)), pooled_y [B][W][C] = mean_H(GN(u)) (fp32) that
+ * PoolingReducer consumes (modules/factorized_attention.py:86-94,113) -- no normalised copy of u is written. */
+int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, int64_t bstride, float eps,
+                        const float* gamma, const float* beta, float* scale, float* shift, float* pooled_x,
+                        float* pooled_y, void* stream);
+int lns_fablock_core(const void* u, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
+                     const float* w_in_proj, const float* Kx, const float* Ky, float eps, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * layout / misc

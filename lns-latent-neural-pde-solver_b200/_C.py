@@ -48,6 +48,8 @@ SIGNATURES = {
     "lns_chan_stats": (i32, [vp, i32, i32, i32, i32, i32, i64, vp, vp]),
     "lns_norm_finalize": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
     "lns_group_norm_affine": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, f32, vp, vp, vp, vp, vp, vp, vp]),
+    "lns_group_norm_act_supported": (i32, [i32, i32, i32]),
+    "lns_group_norm_act": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, f32, vp, vp, vp, i32, vp, i32, i64, vp]),
     "lns_pointwise_proj": (i32, [vp, i32, i32, i32, i32, i64, vp, vp, i32, vp, vp, i32, vp, i64, vp]),
     "lns_affine_act": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, i32, vp, i32, i64, vp]),
     "lns_layernorm": (i32, [vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp]),
@@ -55,6 +57,9 @@ SIGNATURES = {
     "lns_axis_mean": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, vp, vp]),
     "lns_lowrank_kernel": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp]),
     "lns_axial_contract": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
+    "lns_fablock_core_supported": (i32, [i32, i32, i32, i32]),
+    "lns_fablock_prepass": (i32, [vp, i32, i32, i32, i32, i32, i64, f32, vp, vp, vp, vp, vp, vp, vp]),
+    "lns_fablock_core": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp]),
     "lns_nchw_to_nhwc": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i64, vp]),
     "lns_nhwc_to_nchw": (i32, [vp, i32, i32, i32, i32, i32, i64, vp, i64, vp]),
     "lns_fourier_embedding": (i32, [vp, i32, i32, f32, vp, vp]),

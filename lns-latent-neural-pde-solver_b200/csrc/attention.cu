@@ -391,6 +391,80 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
   }
 }
 
+
+// ---- LowRankKernel on tensor cores (bf16 q|k rows) ---------------------------------------------------------------------
+// K[b][h] = rot(q) rot(k)^T  is an n x n x d GEMM per (sample, head) with n <= 96, d = 128.  grid (heads, B), block 128:
+// the rotary embedding is applied while staging q and k (bf16) in shared memory, each warp owns 16-row tiles of K.
+__global__ void __launch_bounds__(128) lowrank_mma_kernel(const __nv_bfloat16* __restrict__ qk, int n, int heads, int d,
+                                                           const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                                           float scaling, float* __restrict__ Kout) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int n16 = (n + 15) & ~15;
+  const int stride = d + 8;
+  __nv_bfloat16* q_s = reinterpret_cast<__nv_bfloat16*>(smraw);
+  __nv_bfloat16* k_s = q_s + (size_t)n16 * stride;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int hd = heads * d, half = d >> 1;
+  const int64_t row_stride = 2 * (int64_t)hd;
+  const __nv_bfloat16* base = qk + (int64_t)b * n * row_stride + h * d;
+  // rotate pairs (f, f + d/2); 2 consecutive f per work item so that loads / stores are 4 bytes
+  for (int e = tid; e < n16 * (half >> 1); e += 128) {
+    const int i = e / (half >> 1), f = (e - i * (half >> 1)) * 2;
+    __nv_bfloat162 q1 = __floats2bfloat162_rn(0.f, 0.f), q2 = q1, k1 = q1, k2 = q1;
+    if (i < n) {
+      const __nv_bfloat16* r = base + (int64_t)i * row_stride;
+      float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(r + f));
+      float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(r + f + half));
+      float2 b1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(r + hd + f));
+      float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(r + hd + f + half));
+      const float c0 = __ldg(cos_t + i * half + f), c1 = __ldg(cos_t + i * half + f + 1);
+      const float s0 = __ldg(sin_t + i * half + f), s1 = __ldg(sin_t + i * half + f + 1);
+      q1 = __floats2bfloat162_rn(a1.x * c0 - a2.x * s0, a1.y * c1 - a2.y * s1);
+      q2 = __floats2bfloat162_rn(a2.x * c0 + a1.x * s0, a2.y * c1 + a1.y * s1);
+      k1 = __floats2bfloat162_rn(b1.x * c0 - b2.x * s0, b1.y * c1 - b2.y * s1);
+      k2 = __floats2bfloat162_rn(b2.x * c0 + b1.x * s0, b2.y * c1 + b1.y * s1);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(q_s + (size_t)i * stride + f) = q1;
+    *reinterpret_cast<__nv_bfloat162*>(q_s + (size_t)i * stride + f + half) = q2;
+    *reinterpret_cast<__nv_bfloat162*>(k_s + (size_t)i * stride + f) = k1;
+    *reinterpret_cast<__nv_bfloat162*>(k_s + (size_t)i * stride + f + half) = k2;
+  }
+  __syncthreads();
+  const int g = lane >> 2, t = lane & 3;
+  float* Kg = Kout + ((int64_t)b * heads + h) * n * n;
+  for (int mt = warp; mt < (n16 >> 4); mt += 4) {
+    for (int nb = 0; nb < n16; nb += 64) {
+      float acc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+      for (int ks = 0; ks < (d >> 4); ++ks) {
+        uint32_t a[4];
+        ldmatrix_x4((uint32_t)__cvta_generic_to_shared(q_s + (size_t)(mt * 16 + (lane & 15)) * stride + ks * 16 + (lane >> 4) * 8),
+                    a[0], a[1], a[2], a[3]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          if (nb + nt * 8 < n16) {
+            uint32_t b0, b1;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1)
+                         : "r"((uint32_t)__cvta_generic_to_shared(k_s + (size_t)(nb + nt * 8 + (lane & 7)) * stride + ks * 16 + ((lane >> 3) & 1) * 8)));
+            mma_bf16_16816(acc[nt], a, b0, b1);
+          }
+        }
+      }
+      const int i0 = mt * 16 + g, i1 = i0 + 8;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int j = nb + nt * 8 + t * 2;
+        if (i0 < n && j < n) Kg[i0 * n + j] = acc[nt][0] * scaling;
+        if (i0 < n && j + 1 < n) Kg[i0 * n + j + 1] = acc[nt][1] * scaling;
+        if (i1 < n && j < n) Kg[i1 * n + j] = acc[nt][2] * scaling;
+        if (i1 < n && j + 1 < n) Kg[i1 * n + j + 1] = acc[nt][3] * scaling;
+      }
+    }
+  }
+}
+
 }  // namespace lns
 
 extern "C" {
@@ -440,6 +514,18 @@ int lns_lowrank_kernel(const void* qk, int dtype, int B, int n, int heads, int d
   LNS_REQUIRE(qk && K && cos_tab && sin_tab && B > 0 && n > 0 && heads > 0 && d > 0 && d % 2 == 0,
               "lns_lowrank_kernel: bad arguments");
   LNS_REQUIRE(B <= 65535, "lns_lowrank_kernel: batch %d exceeds grid limit, chunk the call", B);
+  if (dtype == LNS_BF16 && d % 16 == 0) {
+    // tensor-core path (bf16 q|k from the tcgen05 to_qk GEMM)
+    int n16 = (n + 15) & ~15;
+    size_t smem_mma = 2 * (size_t)n16 * (d + 8) * sizeof(__nv_bfloat16);
+    if (smem_mma <= 227 * 1024) {
+      { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::lowrank_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+      dim3 grid(heads, B);
+      lns::lowrank_mma_kernel<<<grid, 128, smem_mma, reinterpret_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const __nv_bfloat16*>(qk), n, heads, d, cos_tab, sin_tab, scaling, K);
+      return lns::check_launch("lowrank_mma_kernel");
+    }
+  }
   size_t smem = 2 * (size_t)n * (d + 1) * sizeof(float);
   LNS_REQUIRE(smem <= 227 * 1024, "lns_lowrank_kernel: n=%d d=%d needs %zu B shared memory", n, d, smem);
   { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::lowrank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }

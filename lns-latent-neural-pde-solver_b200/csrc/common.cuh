@@ -64,6 +64,30 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == LNS_ACT_GELU) return act_gelu(x);
   return x;
 }
+// bf16 path: results are rounded to bf16 (2^-9) anyway, so the activations use the SFU fast paths
+// (ex2.approx / rcp.approx, ~2^-21 relative) and a 1.5e-7-accurate erf (Abramowitz-Stegun 7.1.26).  The exact forms
+// above stay on the fp32 validation path.  (The exact expf/erff made the elementwise kernels compute bound.)
+__device__ __forceinline__ float act_silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float act_gelu_fast(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float a = fabsf(z);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-a * a);
+  return 0.5f * x * (1.0f + copysignf(e, z));
+}
+__device__ __forceinline__ float apply_act_fast(float x, int act) {
+  if (act == LNS_ACT_SILU) return act_silu_fast(x);
+  if (act == LNS_ACT_GELU) return act_gelu_fast(x);
+  return x;
+}
+// exact on fp32 storage, fast on bf16 storage
+__device__ __forceinline__ float apply_act_for(float x, int act, int storage_dtype) {
+  return storage_dtype == LNS_BF16 ? apply_act_fast(x, act) : apply_act(x, act);
+}
 
 // ---- reductions ----------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
           }
           if (p.act != LNS_ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+            for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
           }
           if (row_ok && p.residual) {
 #pragma unroll

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
       }
       if (p.act != LNS_ACT_NONE) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+        for (int j = 0; j < 16; ++j) v[j] = apply_act_fast(v[j], p.act);
       }
       if (p.residual) {
 #pragma unroll

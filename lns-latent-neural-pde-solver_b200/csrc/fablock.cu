@@ -1,0 +1,476 @@
+// Fused core of FABlock2D (modules/factorized_attention.py:144-159) for the bf16 path.
+//
+// Unfused, the 8x channel-expanded tensor u_phi [B,H,W,512] makes five HBM round trips (in_proj write, two axial
+// contractions read+write, InstanceNorm statistics read, normalise read+write): ~9 MB per 32x32 sample, half of the
+// whole rollout's time in the round-1 timeline.  Here ONE CTA per (sample, head) keeps that head's slice
+// u_phi_h [H*W][64] (bf16, <= 166 KB) in shared memory from the in_proj GEMM to the normalised output:
+//   A  u_phi_h = u (raw, bf16) x (W_in_proj[h] * gn_scale[b]) + W_in_proj[h] . gn_shift[b]      (GroupNorm(1) folded
+//      into a per-sample filter and bias, so the raw activation feeds the tensor cores directly)
+//   B  contraction over H per image column   u[i,m,:] = sum_j Kx[h][i][j] u[j,m,:]   (in place, column private)
+//   C  contraction over W per image row      u[i,l,:] = sum_m Ky[h][l][m] u[i,m,:]   (in place, row private)
+//   D  InstanceNorm2d statistics per channel over the H*W pixels (this head's 64 channels are CTA local)
+//   E  normalise, write bf16 [B,H,W,512] (channels h*64..h*64+63) -- the only HBM write; to_out's 1x1 convs follow.
+// All GEMMs are mma.sync.m16n8k16 (bf16 x bf16 -> fp32) fed by ldmatrix; HBM traffic per sample drops from ~9 MB to
+// 128 KB in + 1 MB out.
+#include "common.cuh"
+
+namespace lns {
+
+namespace {
+constexpr int kUS = 72;  // bf16 elements per shared-memory row (64 + 8 pad -> conflict-free ldmatrix)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// In-place axial contraction of one line (an image column or row) held in U_s:
+//   out[i][c] = sum_j Kmat[i][j] * line[j][c],  line element j lives at U_s + base + j*step  (offsets in bf16 elements).
+// KT = ceil(n/16) k/m tiles.  The whole line (B fragments) is read into registers before anything is written.
+template <int KT>
+__device__ __forceinline__ void contract_line(__nv_bfloat16* U_s, int base, int step, int n, const __nv_bfloat16* K_s, int kstride,
+                                              int lane) {
+  uint32_t bf[KT][8][2];
+#pragma unroll
+  for (int kt = 0; kt < KT; ++kt) {
+    int j = kt * 16 + (lane & 15);
+    j = j < n ? j : n - 1;  // padded rows: multiplied by the zero-padded kernel columns
+    const __nv_bfloat16* rowp = U_s + (size_t)base + (size_t)j * step;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) ldsm_x2_trans(s32(rowp + nt * 8), bf[kt][nt][0], bf[kt][nt][1]);
+  }
+  __syncwarp();
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < KT; ++mt) {
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      uint32_t a[4];
+      ldsm_x4(s32(K_s + (size_t)(mt * 16 + (lane & 15)) * kstride + kt * 16 + (lane >> 4) * 8), a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma16816(acc[nt], a, bf[kt][nt][0], bf[kt][nt][1]);
+    }
+    const int i0 = mt * 16 + g, i1 = i0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (i0 < n)
+        *reinterpret_cast<__nv_bfloat162*>(U_s + (size_t)base + (size_t)i0 * step + nt * 8 + t * 2) = __floats2bfloat162_rn(acc[nt][0], acc[nt][1]);
+      if (i1 < n)
+        *reinterpret_cast<__nv_bfloat162*>(U_s + (size_t)base + (size_t)i1 * step + nt * 8 + t * 2) = __floats2bfloat162_rn(acc[nt][2], acc[nt][3]);
+    }
+  }
+  __syncwarp();
+}
+
+template <int KT>
+__device__ __forceinline__ void contract_axis(__nv_bfloat16* U_s, int lines, int line_mul, int step, int n, const __nv_bfloat16* K_s,
+                                              int kstride, int warp, int nwarp, int lane) {
+  for (int l = warp; l < lines; l += nwarp) contract_line<KT>(U_s, l * line_mul, step, n, K_s, kstride, lane);  // offsets in elements
+}
+}  // namespace
+
+// grid (heads, B), block 512 (256 when an axis needs 3 k-tiles: register budget); instruction-issue bound, so 4 warps per
+// scheduler instead of 2 buy latency hiding
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat16* __restrict__ u, int H, int W, int heads,
+                                                               const float* __restrict__ gn_scale, const float* __restrict__ gn_shift,
+                                                               const float* __restrict__ w_in, const float* __restrict__ Kx,
+                                                               const float* __restrict__ Ky, float eps,
+                                                               __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int HW = H * W;
+  const int H16 = (H + 15) & ~15, W16 = (W + 15) & ~15;
+  const int kxs = H16 + 8, kys = W16 + 8;
+  // u_phi_h: pixel (y, x) at y*RS + x*72 elements; RS = W*72 + 8 -- the extra 16 bytes per image row rotate the banks so that
+  // the 8 rows an ldmatrix / fragment store touches along a COLUMN (stride RS) fall into 8 different 16-byte bank groups
+  // (without it the column stride W*144 B is a multiple of 128 B: 8-way conflicts on every access of phase B)
+  const int RS = W * kUS + 8;
+  __nv_bfloat16* U_s = reinterpret_cast<__nv_bfloat16*>(smraw);          // [H][RS]  (raw input first, u_phi_h in place)
+  __nv_bfloat16* Ws_s = U_s + (size_t)H * RS;                            // [64 n][72 k]
+  __nv_bfloat16* Kx_s = Ws_s + 64 * kUS;                                 // [H16][H16+8]
+  __nv_bfloat16* Ky_s = Kx_s + (size_t)H16 * kxs;                        // [W16][W16+8]
+  float* bias_s = reinterpret_cast<float*>(Ky_s + (size_t)W16 * kys);    // [64]
+  float* red_s = bias_s + 64;                                            // [<=64 pixel groups][64][2]
+  float* stat_s = red_s + 64 * 64 * 2;                                   // [64][2] mean, rstd
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nthr = blockDim.x, nwarp = nthr >> 5, ppi = nthr >> 3;  // ppi: pixels covered per iteration at 8 lanes / pixel
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int C = heads * 64;
+  const __nv_bfloat16* ub = u + (int64_t)b * HW * 64;
+
+  // ---- setup: per-sample filter (GroupNorm scale folded in), bias (GroupNorm shift folded in), kernel matrices ----
+#pragma unroll 4
+  for (int e = tid; e < 64 * 64; e += nthr) {
+    int n = e >> 6, k = e & 63;
+    Ws_s[n * kUS + k] = __float2bfloat16_rn(__ldg(w_in + (int64_t)(h * 64 + n) * 64 + k) * __ldg(gn_scale + (int64_t)b * 64 + k));
+  }
+  {
+    // bias[n] = sum_k W[n][k] * shift[k]: 4 threads per output channel, 16 k each, fixed-order quad reduction
+    const int n = (tid >> 2) & 63, part = tid & 3;  // (threads >= 256 recompute the same values; only tid < 256 store)
+    float a = 0.f;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      float4 wv = __ldg(reinterpret_cast<const float4*>(w_in + (int64_t)(h * 64 + n) * 64 + part * 16 + q4 * 4));
+      float4 sv = __ldg(reinterpret_cast<const float4*>(gn_shift + (int64_t)b * 64 + part * 16 + q4 * 4));
+      a = fmaf(wv.x, sv.x, a); a = fmaf(wv.y, sv.y, a); a = fmaf(wv.z, sv.z, a); a = fmaf(wv.w, sv.w, a);
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    if (part == 0 && tid < 256) bias_s[n] = a;
+  }
+  {
+    const float* kg = Kx + ((int64_t)b * heads + h) * H * H;
+    for (int i = warp; i < H16; i += nwarp)
+      for (int j = lane; j < H16; j += 32)
+        Kx_s[i * kxs + j] = __float2bfloat16_rn((i < H && j < H) ? __ldg(kg + i * H + j) : 0.f);
+    kg = Ky + ((int64_t)b * heads + h) * W * W;
+    for (int i = warp; i < W16; i += nwarp)
+      for (int j = lane; j < W16; j += 32)
+        Ky_s[i * kys + j] = __float2bfloat16_rn((i < W && j < W) ? __ldg(kg + i * W + j) : 0.f);
+  }
+
+  // ---- phase A: u_phi_h = u x Ws^T + bias, IN PLACE.  The 1x1 in_proj is pointwise in space, so the raw rows are
+  // copied (cp.async, four commit groups = four quarters of the image) straight into the rows of U_s they will be replaced
+  // in; a warp transforms 16-row blocks (ldmatrix all A fragments of the block, then overwrite it) -- no staging buffer, no
+  // block-wide barrier per tile, and quarter q+1 is still landing while quarter q is being multiplied.
+  const int nblk = (HW + 15) >> 4;                 // 16-row blocks
+  const int blk_per_q = (nblk + 3) >> 2;
+  {
+    int y = 0, x = 0;  // this thread's first pixel: (tid >> 3); 8 lanes x 16 B per pixel row
+    const int ch = tid & 7;
+    int px = tid >> 3;
+    y = px / W;
+    x = px - y * W;
+    const int sy = ppi / W, sx = ppi - sy * W;
+    for (int q = 0; q < 4; ++q) {
+      const int px_end = min(HW, (q + 1) * blk_per_q * 16);
+      for (; px < px_end; px += ppi) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(U_s + (size_t)y * RS + (size_t)x * kUS + ch * 8)),
+                     "l"(ub + (int64_t)px * 64 + ch * 8) : "memory");
+        y += sy;
+        x += sx;
+        if (x >= W) {
+          x -= W;
+          ++y;
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t wf[4][8][2];  // B fragments of the per-sample filter: identical for every 16-row block -> loaded once
+  for (int q = 0; q < 4; ++q) {
+    if (q == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
+    else if (q == 1) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else if (q == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // quarter q has landed for every thread (q == 0 also publishes the setup writes)
+    if (q == 0) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          ldsm_x2(s32(Ws_s + (size_t)(nt * 8 + (lane & 7)) * kUS + ks * 16 + ((lane >> 3) & 1) * 8), wf[ks][nt][0], wf[ks][nt][1]);
+    }
+    const int blk_end = min(nblk, (q + 1) * blk_per_q);
+    for (int blk = q * blk_per_q + warp; blk < blk_end; blk += nwarp) {
+      // rows of this block: pixels blk*16 .. blk*16+15 (rows >= HW do not exist: clamp reads, skip writes)
+      int pr = blk * 16 + (lane & 15);
+      pr = pr < HW ? pr : HW - 1;
+      const int yr = pr / W;
+      const __nv_bfloat16* arow = U_s + (size_t)yr * RS + (size_t)(pr - yr * W) * kUS;
+      uint32_t a[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldsm_x4(s32(arow + ks * 16 + (lane >> 4) * 8), a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
+      float acc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma16816(acc[nt], a[ks], wf[ks][nt][0], wf[ks][nt][1]);
+      }
+      __syncwarp();  // every lane's ldmatrix of the raw rows is done before they are overwritten
+      const int r0 = blk * 16 + g, r1 = r0 + 8;
+      const int y0 = r0 / W, y1 = r1 / W;
+      const size_t o0 = (size_t)y0 * RS + (size_t)(r0 - y0 * W) * kUS, o1 = (size_t)y1 * RS + (size_t)(r1 - y1 * W) * kUS;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float bs0 = bias_s[nt * 8 + t * 2], bs1 = bias_s[nt * 8 + t * 2 + 1];
+        if (r0 < HW) *reinterpret_cast<__nv_bfloat162*>(U_s + o0 + nt * 8 + t * 2) = __floats2bfloat162_rn(acc[nt][0] + bs0, acc[nt][1] + bs1);
+        if (r1 < HW) *reinterpret_cast<__nv_bfloat162*>(U_s + o1 + nt * 8 + t * 2) = __floats2bfloat162_rn(acc[nt][2] + bs0, acc[nt][3] + bs1);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: contraction over H, one image column per warp at a time (element j of column m at m*72 + j*RS) ----
+  if (H16 == 16) contract_axis<1>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane);
+  else if (H16 == 32) contract_axis<2>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane);
+  else contract_axis<3>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane);
+  __syncthreads();
+  // ---- phase C: contraction over W, one image row per warp (element m of row i at i*RS + m*72) ----
+  if (W16 == 16) contract_axis<1>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane);
+  else if (W16 == 32) contract_axis<2>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane);
+  else contract_axis<3>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane);
+  __syncthreads();
+
+  // ---- phase D: InstanceNorm statistics (biased variance) of this head's 64 channels over the H*W pixels ----
+  // thread = (8-channel chunk, one of 32 pixel groups): 16-byte shared loads, fixed-order reduction over the 32 groups
+  {
+    const int ch = tid & 7, pg = tid >> 3;
+    float s[8], ss[8];
+#pragma unroll
+    for (int j2 = 0; j2 < 8; ++j2) s[j2] = ss[j2] = 0.f;
+    int px = pg;
+    int y = px / W, x = px - y * W;
+    const int sy = ppi / W, sx = ppi - sy * W;
+    for (; px < HW; px += ppi) {
+      uint4 raw = *reinterpret_cast<const uint4*>(U_s + (size_t)y * RS + (size_t)x * kUS + ch * 8);
+      uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j2]));
+        s[2 * j2] += f.x; ss[2 * j2] = fmaf(f.x, f.x, ss[2 * j2]);
+        s[2 * j2 + 1] += f.y; ss[2 * j2 + 1] = fmaf(f.y, f.y, ss[2 * j2 + 1]);
+      }
+      y += sy;
+      x += sx;
+      if (x >= W) {
+        x -= W;
+        ++y;
+      }
+    }
+#pragma unroll
+    for (int j2 = 0; j2 < 8; ++j2) {
+      red_s[(pg * 64 + ch * 8 + j2) * 2 + 0] = s[j2];
+      red_s[(pg * 64 + ch * 8 + j2) * 2 + 1] = ss[j2];
+    }
+  }
+  __syncthreads();
+  if (tid < 64) {
+    double s = 0.0, ss = 0.0;
+    for (int gq = 0; gq < ppi; ++gq) {
+      s += (double)red_s[(gq * 64 + tid) * 2 + 0];
+      ss += (double)red_s[(gq * 64 + tid) * 2 + 1];
+    }
+    double mean = s / (double)HW;
+    double var = ss / (double)HW - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat_s[tid * 2 + 0] = (float)mean;
+    stat_s[tid * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+
+  // ---- phase E: normalise and write channels [h*64, h*64+64) of out [B][HW][C]; 8 lanes x 16 B per pixel ----
+  __nv_bfloat16* ob = out + (int64_t)b * HW * C + h * 64;
+  const int stepy = ppi / W, stepx = ppi - stepy * W;  // the block advances ppi pixels per iteration
+  int py = (tid >> 3) / W, pxx = (tid >> 3) - py * W;
+  float mu[8], rs[8];  // this thread always handles the same 8 channels
+#pragma unroll
+  for (int j2 = 0; j2 < 8; ++j2) {
+    mu[j2] = stat_s[((tid & 7) * 8 + j2) * 2];
+    rs[j2] = stat_s[((tid & 7) * 8 + j2) * 2 + 1];
+  }
+  for (int e = tid; e < HW * 8; e += nthr) {
+    const int px = e >> 3, ch = e & 7;
+    uint4 raw = *reinterpret_cast<const uint4*>(U_s + (size_t)py * RS + (size_t)pxx * kUS + ch * 8);
+    py += stepy;
+    pxx += stepx;
+    if (pxx >= W) {
+      pxx -= W;
+      ++py;
+    }
+    uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
+      f.x = (f.x - mu[2 * j]) * rs[2 * j];
+      f.y = (f.y - mu[2 * j + 1]) * rs[2 * j + 1];
+      __nv_bfloat162 hh = __floats2bfloat162_rn(f.x, f.y);
+      o[j] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    *reinterpret_cast<uint4*>(ob + (int64_t)px * C + ch * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---- FABlock2D pre-pass: ONE read of the block input gives (1) the GroupNorm(1, C) affine and (2) the two pooled
+// tensors the low-rank kernels are built from.  Means commute with the per-channel affine, so
+//   mean_W(GN(u))[y][c] = scale[c] * mean_W(u)[y][c] + shift[c]   (same for mean_H): no normalised copy of u is needed.
+// grid B, block 256: thread = (channel quad q, pixel lane); one image row per iteration (row sums reduced through shared
+// memory in a fixed order, column sums and the totals stay in registers).  Deterministic, batch independent.
+constexpr int kPreMaxX = 8;
+__global__ void __launch_bounds__(256) fablock_prepass_kernel(const void* __restrict__ u, int dtype, int H, int W, int C, int64_t bstride,
+                                                               float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float* __restrict__ scale, float* __restrict__ shift,
+                                                               float* __restrict__ pooled_x, float* __restrict__ pooled_y) {
+  extern __shared__ float smf[];
+  const int cg = C >> 2, rows = 256 / cg;
+  float* red = smf;                              // [rows][C] row-sum partials of the current image row
+  float* rowsum = red + (size_t)rows * C;        // [H][C]
+  float* colsum = rowsum + (size_t)H * C;        // [W][C]
+  float* tot = colsum + (size_t)W * C;           // [rows][C][2] -> later [C][2]
+  float* ab = tot + (size_t)rows * C * 2;        // [C][2] scale, shift
+  const int b = blockIdx.x;
+  const int q = threadIdx.x % cg, lane = threadIdx.x / cg;
+  float cs[kPreMaxX][4];
+#pragma unroll
+  for (int i = 0; i < kPreMaxX; ++i) cs[i][0] = cs[i][1] = cs[i][2] = cs[i][3] = 0.f;
+  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  for (int y = 0; y < H; ++y) {
+    float rs[4] = {0, 0, 0, 0};
+    if (lane < rows) {
+#pragma unroll
+      for (int i = 0; i < kPreMaxX; ++i) {
+        const int x = lane + i * rows;
+        if (x < W) {
+          float4 v = ld4_as_float(u, dtype, (int64_t)b * bstride + ((int64_t)y * W + x) * C + q * 4);
+          rs[0] += v.x; rs[1] += v.y; rs[2] += v.z; rs[3] += v.w;
+          cs[i][0] += v.x; cs[i][1] += v.y; cs[i][2] += v.z; cs[i][3] += v.w;
+          ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]);
+          ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] += rs[j];
+        red[lane * C + q * 4 + j] = rs[j];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float a = 0.f;
+      for (int l = 0; l < rows; ++l) a += red[l * C + c];
+      rowsum[y * C + c] = a;
+    }
+    __syncthreads();
+  }
+  if (lane < rows) {
+#pragma unroll
+    for (int i = 0; i < kPreMaxX; ++i) {
+      const int x = lane + i * rows;
+      if (x < W) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) colsum[x * C + q * 4 + j] = cs[i][j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tot[((lane * C) + q * 4 + j) * 2 + 0] = s[j];
+      tot[((lane * C) + q * 4 + j) * 2 + 1] = ss[j];
+    }
+  }
+  __syncthreads();
+  // GroupNorm(1, C): one group over all channels; warp 0 reduces (fixed order)
+  if (threadIdx.x < 32) {
+    double sum = 0.0, sumsq = 0.0;
+    for (int c = threadIdx.x; c < C; c += 32) {
+      double a = 0.0, a2 = 0.0;
+      for (int l = 0; l < rows; ++l) {
+        a += (double)tot[((l * C) + c) * 2 + 0];
+        a2 += (double)tot[((l * C) + c) * 2 + 1];
+      }
+      sum += (double)(float)a;     // per-channel sums rounded to fp32 like the generic statistics kernels
+      sumsq += (double)(float)a2;
+    }
+    sum = warp_sum_d(sum);
+    sumsq = warp_sum_d(sumsq);
+    const double n = (double)C * (double)H * (double)W;
+    const double mean = sum / n;
+    double var = sumsq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    for (int c = threadIdx.x; c < C; c += 32) {
+      const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+      const float sc = (float)(rstd * ga), sh = (float)(be - mean * rstd * ga);
+      ab[c * 2 + 0] = sc;
+      ab[c * 2 + 1] = sh;
+      scale[(int64_t)b * C + c] = sc;
+      shift[(int64_t)b * C + c] = sh;
+    }
+  }
+  __syncthreads();
+  const float invW = 1.f / (float)W, invH = 1.f / (float)H;
+  for (int e = threadIdx.x; e < H * C; e += 256) {
+    const int c = e % C;
+    pooled_x[(int64_t)b * H * C + e] = fmaf(rowsum[e] * invW, ab[c * 2], ab[c * 2 + 1]);
+  }
+  for (int e = threadIdx.x; e < W * C; e += 256) {
+    const int c = e % C;
+    pooled_y[(int64_t)b * W * C + e] = fmaf(colsum[e] * invH, ab[c * 2], ab[c * 2 + 1]);
+  }
+}
+
+static size_t fablock_smem(int H, int W) {
+  const int HW = H * W, H16 = (H + 15) & ~15, W16 = (W + 15) & ~15;
+  size_t bf = (size_t)H * (W * kUS + 8) + 64 * kUS + (size_t)H16 * (H16 + 8) + (size_t)W16 * (W16 + 8);
+  return bf * sizeof(__nv_bfloat16) + (64 + 64 * 64 * 2 + 64 * 2) * sizeof(float);
+}
+
+}  // namespace lns
+
+extern "C" {
+
+int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, int64_t bstride, float eps, const float* gamma,
+                        const float* beta, float* scale, float* shift, float* pooled_x, float* pooled_y, void* stream) {
+  LNS_REQUIRE(u && scale && shift && pooled_x && pooled_y && B > 0 && H > 0 && W > 0, "lns_fablock_prepass: bad arguments");
+  int cg = C / 4;
+  LNS_REQUIRE(C % 4 == 0 && C >= 4 && C <= 256 && (cg & (cg - 1)) == 0, "lns_fablock_prepass: C must be a power of two in [4,256]");
+  int rows = 256 / cg;
+  LNS_REQUIRE(W <= lns::kPreMaxX * rows, "lns_fablock_prepass: W=%d too wide for C=%d", W, C);
+  LNS_REQUIRE(bstride % 4 == 0, "lns_fablock_prepass: batch stride must be a multiple of 4");
+  size_t smem = ((size_t)rows * C + (size_t)H * C + (size_t)W * C + (size_t)rows * C * 2 + 2 * (size_t)C) * sizeof(float);
+  LNS_REQUIRE(smem <= 200 * 1024, "lns_fablock_prepass: %dx%dx%d needs %zu B shared memory", H, W, C, smem);
+  { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::fablock_prepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); once = true; } }
+  lns::fablock_prepass_kernel<<<B, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(u, dtype, H, W, C, bstride, eps, gamma, beta,
+                                                                                         scale, shift, pooled_x, pooled_y);
+  return lns::check_launch("fablock_prepass_kernel");
+}
+
+int lns_fablock_core_supported(int H, int W, int dim, int dim_head) {
+  return dim == 64 && dim_head == 64 && H <= 48 && W <= 48 && H >= 1 && W >= 1 && lns::fablock_smem(H, W) <= 227 * 1024;
+}
+
+int lns_fablock_core(const void* u, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
+                     const float* w_in_proj, const float* Kx, const float* Ky, float eps, void* out, void* stream) {
+  LNS_REQUIRE(u && gn_scale && gn_shift && w_in_proj && Kx && Ky && out && B > 0 && heads > 0, "lns_fablock_core: bad arguments");
+  LNS_REQUIRE(lns_fablock_core_supported(H, W, 64, 64), "lns_fablock_core: %dx%d does not fit the fused kernel (use the unfused ops)", H, W);
+  LNS_REQUIRE(B <= 65535, "lns_fablock_core: batch %d exceeds grid limit, chunk the call", B);
+  LNS_REQUIRE((reinterpret_cast<uintptr_t>(u) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "lns_fablock_core: alignment");
+  size_t smem = lns::fablock_smem(H, W);
+  {
+    static bool once = false;
+    if (!once) {
+      cudaFuncSetAttribute(lns::fablock_core_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(lns::fablock_core_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      once = true;
+    }
+  }
+  dim3 grid(heads, B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (H <= 32 && W <= 32)  // <= 2 k-tiles per axis: fits 128 registers per thread
+    lns::fablock_core_kernel<512><<<grid, 512, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(u), H, W, heads, gn_scale, gn_shift,
+                                                            w_in_proj, Kx, Ky, eps, reinterpret_cast<__nv_bfloat16*>(out));
+  else
+    lns::fablock_core_kernel<256><<<grid, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(u), H, W, heads, gn_scale, gn_shift,
+                                                            w_in_proj, Kx, Ky, eps, reinterpret_cast<__nv_bfloat16*>(out));
+  return lns::check_launch("fablock_core_kernel");
+}
+
+}  // extern "C"

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const void* __restrict_
   }
 }
 
-// grid B, block 256: thread per group.
+// grid B, block 256: one WARP per group (lanes stride over the group's channels, fixed-order shuffle reduction in fp64)
 __global__ void __launch_bounds__(256) norm_finalize_kernel(const float2* __restrict__ partial, int nchunk, int C, int HW,
                                                              int G, float eps, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta,
@@ -52,9 +52,10 @@ __global__ void __launch_bounds__(256) norm_finalize_kernel(const float2* __rest
                                                              float* __restrict__ scale, float* __restrict__ shift) {
   const int b = blockIdx.x;
   const int cpg = C / G;
-  for (int gi = threadIdx.x; gi < G; gi += blockDim.x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int gi = warp; gi < G; gi += 8) {
     double sum = 0.0, sumsq = 0.0;
-    for (int j = 0; j < cpg; ++j) {
+    for (int j = lane; j < cpg; j += 32) {
       int c = gi * cpg + j;
       double cs = 0.0, css = 0.0;
       for (int k = 0; k < nchunk; ++k) {
@@ -66,12 +67,14 @@ __global__ void __launch_bounds__(256) norm_finalize_kernel(const float2* __rest
       sum += ps * cs;
       sumsq += ps * ps * css;
     }
+    sum = warp_sum_d(sum);
+    sumsq = warp_sum_d(sumsq);
     double n = (double)cpg * (double)HW;
     double mean = sum / n;
     double var = sumsq / n - mean * mean;
     if (var < 0.0) var = 0.0;
     double rstd = 1.0 / sqrt(var + (double)eps);
-    for (int j = 0; j < cpg; ++j) {
+    for (int j = lane; j < cpg; j += 32) {
       int c = gi * cpg + j;
       double ga = gamma ? (double)gamma[c] : 1.0;
       double be = beta ? (double)beta[c] : 0.0;
@@ -99,8 +102,8 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const void* __restrict_
       v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
       v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
     }
-    v.x = apply_act(v.x, act); v.y = apply_act(v.y, act);
-    v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+    v.x = apply_act_for(v.x, act, y_dtype); v.y = apply_act_for(v.y, act, y_dtype);
+    v.z = apply_act_for(v.z, act, y_dtype); v.w = apply_act_for(v.w, act, y_dtype);
     st4_from_float(y, y_dtype, b * y_bstride + r * 4, v);
   }
 }

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256) pointwise_proj_kernel(const void* __restr
                                                               const float* __restrict__ w, const float* __restrict__ bias,
                                                               const float* __restrict__ scale, const float* __restrict__ shift,
                                                               int act, float* __restrict__ y, int64_t y_bstride) {
+  // 8 lanes per pixel: a warp instruction reads 4 whole pixels' channel chunks (full lines), each lane owns a strided set
+  // of 4-channel groups, the COUT partial dot products are combined with 3 shuffles; 32 pixels per 256-thread CTA pass.
   extern __shared__ float sm[];  // w [COUT][C], scale [C], shift [C]
   float* w_s = sm;
   float* sc_s = sm + COUT * C;
@@ -24,24 +26,40 @@ __global__ void __launch_bounds__(256) pointwise_proj_kernel(const void* __restr
     sh_s[e] = shift ? shift[(int64_t)b * C + e] : 0.f;
   }
   __syncthreads();
-  const int pix = blockIdx.x * 256 + threadIdx.x;
-  if (pix >= HW) return;
-  float acc[COUT];
+  const int sub = threadIdx.x & 7;
+  const int pix0 = blockIdx.x * 256;  // 256 pixels per CTA, 8 passes of 32
+#pragma unroll 2
+  for (int pass = 0; pass < 8; ++pass) {
+    const int pix = pix0 + pass * 32 + (threadIdx.x >> 3);
+    float acc[COUT];
 #pragma unroll
-  for (int n = 0; n < COUT; ++n) acc[n] = bias ? bias[n] : 0.f;
-  const int64_t base = (int64_t)b * x_bstride + (int64_t)pix * C;
-  for (int c = 0; c < C; c += 4) {
-    float4 v = ld4_as_float(x, dtype, base + c);
-    float u[4] = {v.x, v.y, v.z, v.w};
+    for (int n = 0; n < COUT; ++n) acc[n] = 0.f;
+    if (pix < HW) {
+      const int64_t base = (int64_t)b * x_bstride + (int64_t)pix * C;
+      for (int c = sub * 4; c < C; c += 32) {
+        float4 v = ld4_as_float(x, dtype, base + c);
+        float u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float t = apply_act(fmaf(u[j], sc_s[c + j], sh_s[c + j]), act);
+        for (int j = 0; j < 4; ++j) {
+          float t = apply_act_for(fmaf(u[j], sc_s[c + j], sh_s[c + j]), act, dtype);
 #pragma unroll
-      for (int n = 0; n < COUT; ++n) acc[n] = fmaf(t, w_s[n * C + c + j], acc[n]);
+          for (int n = 0; n < COUT; ++n) acc[n] = fmaf(t, w_s[n * C + c + j], acc[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) {
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
+    }
+    if (pix < HW && sub < COUT) {
+      float v = acc[0];
+#pragma unroll
+      for (int n = 1; n < COUT; ++n) v = (sub == n) ? acc[n] : v;
+      y[(int64_t)b * y_bstride + (int64_t)sub * HW + pix] = v + (bias ? bias[sub] : 0.f);
     }
   }
-#pragma unroll
-  for (int n = 0; n < COUT; ++n) y[(int64_t)b * y_bstride + (int64_t)n * HW + pix] = acc[n];
 }
 
 // ---- GroupNorm statistics + finalize in ONE kernel (samples of <= 1024 pixels: every layer below 64x64) ------------------
@@ -98,26 +116,116 @@ __global__ void __launch_bounds__(256) gn_affine_small_kernel(const void* __rest
   }
   __syncthreads();
   const int cpg = C / G;
-  for (int gi = threadIdx.x; gi < G; gi += 256) {
+  const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+  for (int gi = warp; gi < G; gi += 8) {  // one warp per group, same order as norm_finalize_kernel
     double sum = 0.0, sumsq = 0.0;
-    for (int j = 0; j < cpg; ++j) {
+    for (int j = wl; j < cpg; j += 32) {
       int c = gi * cpg + j;
       double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
       sum += ps * csum[c * 2 + 0];
       sumsq += ps * ps * csum[c * 2 + 1];
     }
+    sum = warp_sum_d(sum);
+    sumsq = warp_sum_d(sumsq);
     double n = (double)cpg * (double)HW;
     double mean = sum / n;
     double var = sumsq / n - mean * mean;
     if (var < 0.0) var = 0.0;
     double rstd = 1.0 / sqrt(var + (double)eps);
-    for (int j = 0; j < cpg; ++j) {
+    for (int j = wl; j < cpg; j += 32) {
       int c = gi * cpg + j;
       double ga = gamma ? (double)gamma[c] : 1.0;
       double be = beta ? (double)beta[c] : 0.0;
       double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
       scale[(int64_t)b * C + c] = (float)(ps * rstd * ga);
       shift[(int64_t)b * C + c] = (float)(be - mean * rstd * ga);
+    }
+  }
+}
+
+// ---- GroupNorm + activation in ONE kernel for samples that fit in shared memory (<= 48 KB: the 8x8 / 7x15 latent-grid
+// layers of the propagator and coarse decoder): one CTA per sample stages it, reduces, normalises, writes.  Replaces
+// gn_affine_small + affine_act (two launches, two reads) when the consumer is a tcgen05 conv.
+__global__ void __launch_bounds__(256) gn_act_small_kernel(const void* __restrict__ x, int dtype, int HW, int C, int64_t bstride,
+                                                            int G, float eps, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float* __restrict__ prescale,
+                                                            int act, void* __restrict__ y, int y_dtype, int64_t y_bstride) {
+  extern __shared__ float smf[];  // sample [HW*C] fp32, then red [rows][C][2], csum [C][2], ab [C][2]
+  float* xs = smf;
+  float* red = xs + (size_t)HW * C;
+  const int cg = C >> 2, rows = 256 / cg;
+  float* csum = red + (size_t)rows * C * 2;
+  float* ab = csum + (size_t)C * 2;
+  const int b = blockIdx.x;
+  const int q = threadIdx.x % cg, lane = threadIdx.x / cg;
+  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  if (lane < rows) {
+    for (int p = lane; p < HW; p += rows) {
+      float4 v = ld4_as_float(x, dtype, (int64_t)b * bstride + (int64_t)p * C + q * 4);
+      *reinterpret_cast<float4*>(xs + (size_t)p * C + q * 4) = v;
+      s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
+      s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
+      s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
+      s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[((lane * C) + q * 4 + j) * 2 + 0] = s[j];
+      red[((lane * C) + q * 4 + j) * 2 + 1] = ss[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double a = 0.0, a2 = 0.0;
+    for (int l = 0; l < rows; ++l) {
+      a += (double)red[((l * C) + c) * 2 + 0];
+      a2 += (double)red[((l * C) + c) * 2 + 1];
+    }
+    csum[c * 2 + 0] = (float)a;   // rounded like the two-kernel path's fp32 partials
+    csum[c * 2 + 1] = (float)a2;
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+  for (int gi = warp; gi < G; gi += 8) {  // one warp per group
+    double sum = 0.0, sumsq = 0.0;
+    for (int j = wl; j < cpg; j += 32) {
+      int c = gi * cpg + j;
+      double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
+      sum += ps * (double)csum[c * 2 + 0];
+      sumsq += ps * ps * (double)csum[c * 2 + 1];
+    }
+    sum = warp_sum_d(sum);
+    sumsq = warp_sum_d(sumsq);
+    double n = (double)cpg * (double)HW;
+    double mean = sum / n;
+    double var = sumsq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    double rstd = 1.0 / sqrt(var + (double)eps);
+    for (int j = wl; j < cpg; j += 32) {
+      int c = gi * cpg + j;
+      double ga = gamma ? (double)gamma[c] : 1.0;
+      double be = beta ? (double)beta[c] : 0.0;
+      double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
+      ab[c * 2 + 0] = (float)(ps * rstd * ga);
+      ab[c * 2 + 1] = (float)(be - mean * rstd * ga);
+    }
+  }
+  __syncthreads();
+  if (lane < rows) {
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc[j] = ab[(q * 4 + j) * 2 + 0];
+      sh[j] = ab[(q * 4 + j) * 2 + 1];
+    }
+    for (int p = lane; p < HW; p += rows) {
+      float4 v = *reinterpret_cast<const float4*>(xs + (size_t)p * C + q * 4);
+      v.x = apply_act_for(fmaf(v.x, sc[0], sh[0]), act, y_dtype);
+      v.y = apply_act_for(fmaf(v.y, sc[1], sh[1]), act, y_dtype);
+      v.z = apply_act_for(fmaf(v.z, sc[2], sh[2]), act, y_dtype);
+      v.w = apply_act_for(fmaf(v.w, sc[3], sh[3]), act, y_dtype);
+      st4_from_float(y, y_dtype, (int64_t)b * y_bstride + (int64_t)p * C + q * 4, v);
     }
   }
 }
@@ -142,6 +250,27 @@ int lns_pointwise_proj(const void* x, int dtype, int B, int HW, int C, int64_t x
     default: lns::pointwise_proj_kernel<4><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride); break;
   }
   return lns::check_launch("pointwise_proj_kernel");
+}
+
+int lns_group_norm_act_supported(int H, int W, int C) {
+  int cg = C / 4;
+  if (C % 4 != 0 || C < 4 || C > 1024 || (cg & (cg - 1)) != 0) return 0;
+  size_t smem = ((size_t)H * W * C + (size_t)(256 / cg) * C * 2 + 4 * (size_t)C) * sizeof(float);
+  return smem <= 48 * 1024;
+}
+
+int lns_group_norm_act(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int G, float eps,
+                       const float* gamma, const float* beta, const float* prescale, int act, void* y, int y_dtype,
+                       int64_t y_bstride, void* stream) {
+  LNS_REQUIRE(x && y && B > 0 && G > 0 && C % G == 0, "lns_group_norm_act: bad arguments");
+  LNS_REQUIRE(lns_group_norm_act_supported(H, W, C), "lns_group_norm_act: sample %dx%dx%d does not fit (use "
+              "lns_group_norm_affine + lns_affine_act)", H, W, C);
+  LNS_REQUIRE(bstride % 4 == 0 && y_bstride % 4 == 0, "lns_group_norm_act: batch strides must be multiples of 4");
+  int cg = C / 4;
+  size_t smem = ((size_t)H * W * C + (size_t)(256 / cg) * C * 2 + 4 * (size_t)C) * sizeof(float);
+  lns::gn_act_small_kernel<<<B, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, dtype, H * W, C, bstride, G, eps, gamma,
+                                                                                      beta, prescale, act, y, y_dtype, y_bstride);
+  return lns::check_launch("gn_act_small_kernel");
 }
 
 int lns_group_norm_affine(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int G, float eps,

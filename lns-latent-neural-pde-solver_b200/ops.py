@@ -34,6 +34,24 @@ class _State(threading.local):
     def __init__(self):
         self.precision = "bf16"
         self.launches = 0
+        self.timeline = None  # list of (label, start_event, end_event) when profiling (tools/timeline.py)
+
+
+def _mark(label):
+    """Profiling hook: returns a closer that records a CUDA-event pair around one library call (eager mode only)."""
+    tl = _state.timeline
+    if tl is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return (label, e0)
+
+
+def _done(tok):
+    if tok is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        _state.timeline.append((tok[0], tok[1], e1))
 
 
 _state = _State()
@@ -233,6 +251,28 @@ class PackedFilter:
         return self._bias
 
 
+def composed_filter(first, second):
+    """PackedFilter of  second(1x1) o first(kxk)  -- two convolutions with no non-linearity between them are one
+    convolution: W'[o][i][tap] = sum_m W2[o][m] W1[m][i][tap],  b' = W2 b1 + b2  (composed in fp64, stored fp32)."""
+    def wfn():
+        w1, k1 = first._weight_fn()
+        w2, k2 = second._weight_fn()
+        w = torch.einsum("om,mikl->oikl", w2[:, :, 0, 0].double(), w1.double()).float()
+        return w, (k1, k2)
+
+    def bfn():
+        w2, k2 = second._weight_fn()
+        b1, kb1 = first._bias_fn() if first._bias_fn else (None, None)
+        b2, kb2 = second._bias_fn() if second._bias_fn else (None, None)
+        b = torch.zeros(w2.shape[0], dtype=torch.float64, device=w2.device)
+        if b1 is not None:
+            b = b + w2[:, :, 0, 0].double() @ b1.double()
+        if b2 is not None:
+            b = b + b2.double()
+        return b.float(), (k2, kb1, kb2)
+    return PackedFilter(wfn, bfn)
+
+
 # ---- conv ---------------------------------------------------------------------------------------------------
 def _umma_ok(x, Cin, Cout, y_layout):
     return (_state.precision == "bf16" and x.layout == NHWC and x.t.dtype == torch.bfloat16 and Cin % 64 == 0
@@ -262,8 +302,15 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
         if (engine == ENGINE_UMMA and KH == 3 and KW == 3 and stride == 1 and Cin == 64 and Cout in (64, 128)
                 and pt == pb == pl == pr == dil and 1 <= dil <= 3 and Hout >= 16 and Wout >= 8):
             engine = ENGINE_HALO  # full-resolution layers: shared-memory halo + resident filter
+    if isinstance(pro, LazyNorm):
+        if pro.x is not x:
+            raise LnsError("conv2d: the pending normalisation belongs to a different activation")
+        if engine in (ENGINE_UMMA, ENGINE_HALO):
+            x = pro.materialize()  # these engines gather with cp.async (no transform in flight)
+            pro = None
+        else:
+            pro = pro.as_tuple()
     if engine in (ENGINE_UMMA, ENGINE_HALO) and pro is not None:
-        # this engine gathers with cp.async (no transform in flight): materialise the normalised activation first
         x = affine_act(x, pro[0], pro[1], pro[2])
         pro = None
     if out is None:
@@ -302,8 +349,13 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
         d.residual, d.res_dtype, d.res_bstride = residual.t.data_ptr(), residual.dtype, residual.bstride
     d.y, d.y_dtype, d.y_layout = out.t.data_ptr(), out.dtype, out.layout
     d.Hout, d.Wout, d.Cout, d.y_bstride = Hout, Wout, Cout, out.bstride
+    tok = _mark(f"conv e{engine} {KH}x{KW} s{stride} d{dil} {Cin}->{Cout} @{Hout}x{Wout}"
+                f"{' up' if virt is not None else ''}{' pro' if pro is not None else ''}"
+                f"{' act' if act else ''}{' res' if residual is not None else ''} "
+                f"{'bf16' if x.t.dtype == torch.bfloat16 else 'f32'}->{'bf16' if out.t.dtype == torch.bfloat16 else 'f32'}")
     rc = _C.lib().lns_conv2d(ctypes.byref(d), _stream())
     check(rc, "lns_conv2d")
+    _done(tok)
     _state.launches += 1
     return out
 
@@ -321,10 +373,14 @@ def _pointwise_proj(x, filt, use_bias, pro, out):
         out = Act(torch.empty(x.B * Cout * x.H * x.W, dtype=torch.float32, device=x.t.device), x.B, x.H, x.W, Cout,
                   layout=NCHW)
     bias = filt.bias() if use_bias else None
+    if isinstance(pro, LazyNorm):
+        pro = pro.as_tuple()
     sc, sh, pa = (pro if pro is not None else (None, None, ACT_NONE))
+    tok = _mark(f"proj @{x.H}x{x.W}")
     rc = _C.lib().lns_pointwise_proj(_ptr(x.t), x.dtype, x.B, x.H * x.W, Cin, x.bstride, _ptr(wt), _ptr(bias), Cout,
                                      _ptr(sc), _ptr(sh), pa, _ptr(out.t), out.bstride, _stream())
     check(rc, "lns_pointwise_proj")
+    _done(tok)
     _state.launches += 1
     return out
 
@@ -351,19 +407,61 @@ def group_norm_affine(x, groups, eps, gamma=None, beta=None, prescale=None):
     shift = torch.empty_like(scale)
     g = gamma.detach().float().contiguous() if gamma is not None else None
     b = beta.detach().float().contiguous() if beta is not None else None
+    tok = _mark(f"gn_stats C{x.C} @{x.H}x{x.W}")
     rc = _C.lib().lns_group_norm_affine(_ptr(x.t), x.dtype, x.B, x.H, x.W, x.C, x.bstride, groups, float(eps), _ptr(g),
                                         _ptr(b), _ptr(prescale), _ptr(part), _ptr(scale), _ptr(shift), _stream())
     check(rc, "lns_group_norm_affine")
+    _done(tok)
     _state.launches += 1 if nchunk == 1 else 2
     return scale, shift
+
+
+class LazyNorm:
+    """A GroupNorm-family normalisation (+ activation) of `x` that has not been executed yet.  The consumer decides how:
+    a CUDA-core conv folds the per-(sample,channel) affine into its gather (`as_tuple`), a tcgen05 conv needs the
+    normalised tensor (`materialize`: ONE fused statistics+apply kernel when the sample fits in shared memory, else
+    statistics kernel + affine kernel)."""
+
+    def __init__(self, x, groups, eps, gamma=None, beta=None, prescale=None, act=ACT_NONE):
+        self.x, self.groups, self.eps, self.gamma, self.beta, self.prescale, self.act = x, groups, eps, gamma, beta, prescale, act
+        self._affine = None
+
+    def affine(self):
+        if self._affine is None:
+            self._affine = group_norm_affine(self.x, self.groups, self.eps, self.gamma, self.beta, self.prescale)
+        return self._affine
+
+    def as_tuple(self):
+        s, t = self.affine()
+        return (s, t, self.act)
+
+    def materialize(self, out_dtype=None):
+        x = self.x
+        if (self._affine is None and x.layout == NHWC
+                and _C.lib().lns_group_norm_act_supported(x.H, x.W, x.C) and x.bstride % 4 == 0):
+            out = x.like(dtype=out_dtype or x.t.dtype)
+            g = self.gamma.detach().float().contiguous() if self.gamma is not None else None
+            b = self.beta.detach().float().contiguous() if self.beta is not None else None
+            tok = _mark(f"gn_act_fused C{x.C} @{x.H}x{x.W}")
+            rc = _C.lib().lns_group_norm_act(_ptr(x.t), x.dtype, x.B, x.H, x.W, x.C, x.bstride, self.groups, float(self.eps),
+                                             _ptr(g), _ptr(b), _ptr(self.prescale), self.act, _ptr(out.t), out.dtype,
+                                             out.bstride, _stream())
+            check(rc, "lns_group_norm_act")
+            _done(tok)
+            _state.launches += 1
+            return out
+        s, t = self.affine()
+        return affine_act(x, s, t, self.act, out_dtype=out_dtype)
 
 
 def affine_act(x, scale, shift, act=ACT_NONE, out_dtype=None):
     """y = act(x*scale[b,c] + shift[b,c]) as a new contiguous Act."""
     out = x.like(dtype=out_dtype or x.t.dtype)
+    tok = _mark(f"affine_act C{x.C} @{x.H}x{x.W}")
     rc = _C.lib().lns_affine_act(_ptr(x.t), x.dtype, x.bstride, x.B, x.H * x.W, x.C, _ptr(scale), _ptr(shift), act,
                                  _ptr(out.t), out.dtype, out.bstride, _stream())
     check(rc, "lns_affine_act")
+    _done(tok)
     _state.launches += 1
     return out
 
@@ -374,9 +472,11 @@ def layernorm(x, gamma, beta, eps, pe=None, out_dtype=None):
     out = x.like(dtype=out_dtype or x.t.dtype)
     g = gamma.detach().float().contiguous() if gamma is not None else None
     b = beta.detach().float().contiguous() if beta is not None else None
+    tok = _mark(f"layernorm")
     rc = _C.lib().lns_layernorm(_ptr(x.t), x.dtype, x.B, x.H * x.W, x.C, _ptr(g), _ptr(b), float(eps), _ptr(pe),
                                 _ptr(out.t), out.dtype, _stream())
     check(rc, "lns_layernorm")
+    _done(tok)
     _state.launches += 1
     return out
 
@@ -396,9 +496,11 @@ def attention(qkv, heads, dh, scale, out_dtype=None):
     """qkv: Act [B,H,W,3*heads*dh] (tokens = pixels) -> Act [B,H,W,heads*dh]"""
     assert qkv.contiguous and qkv.C == 3 * heads * dh
     out = qkv.like(C=heads * dh, dtype=out_dtype or qkv.t.dtype)
+    tok = _mark(f"attention")
     rc = _C.lib().lns_attention(_ptr(qkv.t), qkv.dtype, qkv.B, qkv.H * qkv.W, heads, dh, float(scale), _ptr(out.t),
                                 out.dtype, _stream())
     check(rc, "lns_attention")
+    _done(tok)
     _state.launches += 1
     return out
 
@@ -407,8 +509,10 @@ def axis_mean(x, axis):
     """axis 0: mean over H -> Act [B, W, 1, C] fp32; axis 1: mean over W -> Act [B, H, 1, C] fp32"""
     keep = x.W if axis == 0 else x.H
     out = Act.empty(x.B, keep, 1, x.C, torch.float32, x.t.device)
+    tok = _mark(f"axis_mean")
     rc = _C.lib().lns_axis_mean(_ptr(x.t), x.dtype, x.B, x.H, x.W, x.C, x.bstride, axis, _ptr(out.t), _stream())
     check(rc, "lns_axis_mean")
+    _done(tok)
     _state.launches += 1
     return out
 
@@ -418,9 +522,11 @@ def lowrank_kernel(qk, heads, d, cos_tab, sin_tab, scaling=1.0):
     assert qk.contiguous and qk.C == 2 * heads * d
     n = qk.H * qk.W
     K = torch.empty(qk.B, heads, n, n, dtype=torch.float32, device=qk.t.device)
+    tok = _mark(f"lowrank")
     rc = _C.lib().lns_lowrank_kernel(_ptr(qk.t), qk.dtype, qk.B, n, heads, d, _ptr(cos_tab), _ptr(sin_tab),
                                      float(scaling), _ptr(K), _stream())
     check(rc, "lns_lowrank_kernel")
+    _done(tok)
     _state.launches += 1
     return K
 
@@ -428,9 +534,47 @@ def lowrank_kernel(qk, heads, d, cos_tab, sin_tab, scaling=1.0):
 def axial_contract(u, K, heads, axis, out_dtype=None):
     assert u.contiguous and u.layout == NHWC and u.C % heads == 0
     out = u.like(dtype=out_dtype or u.t.dtype)
+    tok = _mark(f"axial C{u.C} @{u.H}x{u.W}")
     rc = _C.lib().lns_axial_contract(_ptr(u.t), u.dtype, u.B, u.H, u.W, heads, u.C // heads, _ptr(K), axis,
                                      _ptr(out.t), out.dtype, _stream())
     check(rc, "lns_axial_contract")
+    _done(tok)
+    _state.launches += 1
+    return out
+
+
+def fablock_core_supported(x, dim_head):
+    return (x.t.dtype == torch.bfloat16 and x.layout == NHWC and x.contiguous
+            and bool(_C.lib().lns_fablock_core_supported(x.H, x.W, x.C, dim_head)))
+
+
+def fablock_prepass(u, eps, gamma, beta):
+    """-> (scale [B*C], shift [B*C], pooled_x Act [B,H,1,C] fp32, pooled_y Act [B,W,1,C] fp32) in one read of u."""
+    dev = u.t.device
+    scale = torch.empty(u.B * u.C, dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    px = Act.empty(u.B, u.H, 1, u.C, torch.float32, dev)
+    py = Act.empty(u.B, u.W, 1, u.C, torch.float32, dev)
+    g = gamma.detach().float().contiguous() if gamma is not None else None
+    b = beta.detach().float().contiguous() if beta is not None else None
+    tok = _mark(f"fablock_prepass @{u.H}x{u.W}")
+    rc = _C.lib().lns_fablock_prepass(_ptr(u.t), u.dtype, u.B, u.H, u.W, u.C, u.bstride, float(eps), _ptr(g), _ptr(b),
+                                      _ptr(scale), _ptr(shift), _ptr(px.t), _ptr(py.t), _stream())
+    check(rc, "lns_fablock_prepass")
+    _done(tok)
+    _state.launches += 1
+    return scale, shift, px, py
+
+
+def fablock_core(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps):
+    """Fused in_proj -> axial contractions -> InstanceNorm of FABlock2D (bf16 path): Act [B,H,W,64] -> [B,H,W,heads*64]."""
+    out = Act.empty(u.B, u.H, u.W, heads * 64, torch.bfloat16, u.t.device)
+    w = w_in_proj.detach().float().contiguous()
+    tok = _mark(f"fablock_core @{u.H}x{u.W}")
+    rc = _C.lib().lns_fablock_core(_ptr(u.t), u.B, u.H, u.W, heads, _ptr(gn_scale), _ptr(gn_shift), _ptr(w), _ptr(Kx),
+                                   _ptr(Ky), float(eps), _ptr(out.t), _stream())
+    check(rc, "lns_fablock_core")
+    _done(tok)
     _state.launches += 1
     return out
 

@@ -86,7 +86,7 @@ class Rollout:
                 if self.out is None:
                     self.out = torch.empty(B, K, self.C, self.Ly, self.Lx, dtype=torch.float32, device=self.device)
                 out_flat = self.out.view(-1)
-                chunk = self.decode_chunk or max(8, min(n, (4 << 20) // (self.Ly * self.Lx)))
+                chunk = self.decode_chunk or max(8, min(n, (16 << 20) // (self.Ly * self.Lx)))
                 for c0 in range(0, n, chunk):
                     m = min(chunk, n - c0)
                     zin = Act(self.zs[c0 * hwc:], m, h, w, Cz)

@@ -73,6 +73,16 @@ def conv_layer(x, conv, **kw):
     return ops.conv2d(x, filt_of(conv), **geo)
 
 
+def lazy_norm(x, norm, act=ops.ACT_NONE, prescale=None):
+    """Pending GroupNorm-family normalisation (+ activation) of x, to be consumed by the next conv (ops.LazyNorm)."""
+    gn = getattr(norm, "gn", norm)
+    if isinstance(gn, nn.GroupNorm):
+        return ops.LazyNorm(x, gn.num_groups, gn.eps, gn.weight, gn.bias, prescale, act)
+    if isinstance(gn, nn.InstanceNorm2d):
+        return ops.LazyNorm(x, x.C, gn.eps, gn.weight, gn.bias, prescale, act)
+    raise LnsError(f"unsupported norm {type(norm).__name__}")
+
+
 def norm_affine(x, norm, prescale=None):
     """(scale, shift) of a GroupNorm-family module applied to x: basics.GroupNorm (wrapper with .gn), nn.GroupNorm,
     nn.InstanceNorm2d (no affine, per-channel groups)."""
@@ -114,6 +124,21 @@ def run_layers(layers, x, final_out=None, final_layout=ops.NHWC, final_dtype=Non
         nxt = layers[i + 1] if i + 1 < n else None
         if isinstance(layer, nn.Conv2d):
             kw = {}
+            # conv kxk directly followed by a conv 1x1 (no activation between): one conv with the composed filter
+            # (bf16 path only; the fp32 validation path keeps the reference's two steps)
+            if (ops.get_precision() == "bf16" and isinstance(nxt, nn.Conv2d) and nxt.kernel_size == (1, 1)
+                    and layer.kernel_size[0] > 1 and nxt.stride == (1, 1) and i + 1 < n - 1
+                    and not hasattr(nxt, "periodic_direction")):
+                key = "_lns_composed_%d" % id(nxt)
+                filt = layer.__dict__.get(key)
+                if filt is None:
+                    filt = ops.composed_filter(filt_of(layer), filt_of(nxt))
+                    layer.__dict__[key] = filt
+                geo = conv_geometry(layer)
+                x = ops.conv2d(x, filt, pro=pro, virt=virt, **geo)
+                pro, virt = None, None
+                i += 2
+                continue
             a = act_code(nxt) if nxt is not None else None
             if a is not None:
                 kw["act"] = a
@@ -129,30 +154,29 @@ def run_layers(layers, x, final_out=None, final_layout=ops.NHWC, final_dtype=Non
         elif _is_norm(layer):
             if pro is not None or virt is not None:
                 raise LnsError("run_layers: norm after a pending norm/resize is not supported")
-            scale, shift = norm_affine(x, layer)
             a = act_code(nxt) if nxt is not None else None
             if a is not None:
                 i += 1
-            pro = (scale, shift, a or ops.ACT_NONE)
+            pro = lazy_norm(x, layer, a or ops.ACT_NONE)
         elif isinstance(layer, nn.Upsample):
             if layer.mode != "nearest" or layer.size is None:
                 raise LnsError("only nn.Upsample(size=..., mode='nearest') is implemented")
             if pro is not None:
-                x = ops.affine_act(x, *pro)
+                x = _flush(x, pro)
                 pro = None
             virt = tuple(layer.size)
         elif act_code(layer) is not None:
             if virt is not None:
                 raise LnsError("run_layers: activation after a pending resize is not supported")
             if pro is not None:
-                x = ops.affine_act(x, *pro)
+                x = _flush(x, pro)
                 pro = None
             pro = (None, None, act_code(layer))
         elif hasattr(layer, "_fwd"):
             if virt is not None:
                 raise LnsError("run_layers: resize must be followed by a conv")
             if pro is not None:
-                x = ops.affine_act(x, *pro)
+                x = _flush(x, pro)
                 pro = None
             x = layer._fwd(x)
         elif isinstance(layer, nn.Identity):
@@ -163,8 +187,12 @@ def run_layers(layers, x, final_out=None, final_layout=ops.NHWC, final_dtype=Non
     if virt is not None:
         raise LnsError("run_layers: trailing resize")
     if pro is not None:
-        x = ops.affine_act(x, *pro)
+        x = _flush(x, pro)
     return x
+
+
+def _flush(x, pro):
+    return pro.materialize() if isinstance(pro, ops.LazyNorm) else ops.affine_act(x, *pro)
 
 
 def latent_dtype(channels):

@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from lns_b200 import ops
 
-from ._base import LnsModule, run_layers, conv_layer, norm_affine, latent_dtype
+from ._base import LnsModule, run_layers, conv_layer, norm_affine, lazy_norm, latent_dtype
 from .basics import GroupNorm, Swish, FourierBasicBlock, SABlock
 from .factorized_attention import FABlock2D
 
@@ -21,11 +21,10 @@ class NormSwish(LnsModule):
         self.norm_act = nn.Sequential(GroupNorm(in_channels), Swish())
 
     def _affine(self, x):
-        s, t = norm_affine(x, self.norm_act[0])
-        return (s, t, ops.ACT_SILU)
+        return lazy_norm(x, self.norm_act[0], ops.ACT_SILU)
 
     def _fwd(self, x):
-        return ops.affine_act(x, *self._affine(x))
+        return self._affine(x).materialize()
 
 
 class HalfPeriodicConv2d(nn.Conv2d, LnsModule):

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from lns_b200 import ops
 
-from ._base import LnsModule, LnsError, conv_layer, norm_affine, pad_modes, filt_of
+from ._base import LnsModule, LnsError, conv_layer, norm_affine, lazy_norm, pad_modes, filt_of
 from .cond_utils import zero_module, ConditionedBlock  # noqa: F401  (re-exported like the reference does)
 
 
@@ -60,11 +60,9 @@ class ResidualBlock(LnsModule):
 
     def _fwd(self, x):
         gn1, _, conv1, gn2, _, conv2 = self.block
-        s, t = norm_affine(x, gn1)
-        h = conv_layer(x, conv1, pro=(s, t, ops.ACT_SILU))
-        s, t = norm_affine(h, gn2)
+        h = conv_layer(x, conv1, pro=lazy_norm(x, gn1, ops.ACT_SILU))
         skip = conv_layer(x, self.channel_up) if self.in_channels != self.out_channels else x
-        return conv_layer(h, conv2, pro=(s, t, ops.ACT_SILU), residual=skip)
+        return conv_layer(h, conv2, pro=lazy_norm(h, gn2, ops.ACT_SILU), residual=skip)
 
 
 class UpSampleBlock(LnsModule):

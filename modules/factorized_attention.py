@@ -113,17 +113,30 @@ class FABlock2D(LnsModule):
 
     def _fwd(self, u):
         skip = u
-        s, t = norm_affine(u, self.in_norm)
-        un = ops.affine_act(u, s, t, ops.ACT_NONE)
-        u_phi = conv_layer(un, self.in_proj)
-        # mean over the other axis first (exact: to_in convs have no bias), then the two tiny linears
         f32 = torch.float32
-        px = ops.conv2d(ops.axis_mean(un, axis=1), filt_of(self.to_in[0]), out_dtype=f32)   # rows indexed by H
-        py = ops.conv2d(ops.axis_mean(un, axis=0), filt_of(self.to_in[0]), out_dtype=f32)   # rows indexed by W
+        inorm = self.to_out[0]
+        fused = (ops.get_precision() == "bf16" and self.in_proj.out_channels == self.heads * 64
+                 and ops.fablock_core_supported(u, self.dim_head) and inorm.weight is None)
+        if fused:
+            # one read of u: GroupNorm(1) affine + both pooled tensors (means commute with the per-channel affine)
+            s, t, mx, my = ops.fablock_prepass(u, self.in_norm.eps, self.in_norm.weight, self.in_norm.bias)
+        else:
+            s, t = norm_affine(u, self.in_norm)
+            un = ops.affine_act(u, s, t, ops.ACT_NONE)
+            mx, my = ops.axis_mean(un, axis=1), ops.axis_mean(un, axis=0)
+        # mean over the other axis first (exact: to_in convs have no bias), then the two tiny linears
+        px = ops.conv2d(mx, filt_of(self.to_in[0]), out_dtype=f32)   # rows indexed by H
+        py = ops.conv2d(my, filt_of(self.to_in[0]), out_dtype=f32)   # rows indexed by W
         k_x = self.low_rank_kernel_x._fwd(self.to_x[0]._fwd(px))
         k_y = self.low_rank_kernel_y._fwd(self.to_y[1]._fwd(py))
-        u_phi = ops.axial_contract(u_phi, k_x, self.heads, axis=0)
-        u_phi = ops.axial_contract(u_phi, k_y, self.heads, axis=1)
-        s, t = norm_affine(u_phi, self.to_out[0])
-        h = conv_layer(u_phi, self.to_out[1], pro=(s, t, ops.ACT_NONE), act=ops.ACT_GELU)
+        if fused:
+            # in_proj -> contraction over H -> contraction over W -> InstanceNorm, u_phi stays in shared memory
+            u_n = ops.fablock_core(u, s, t, self.in_proj.weight, k_x, k_y, self.heads, inorm.eps)
+            h = conv_layer(u_n, self.to_out[1], act=ops.ACT_GELU)
+        else:
+            u_phi = conv_layer(un, self.in_proj)
+            u_phi = ops.axial_contract(u_phi, k_x, self.heads, axis=0)
+            u_phi = ops.axial_contract(u_phi, k_y, self.heads, axis=1)
+            s2, t2 = norm_affine(u_phi, inorm)
+            h = conv_layer(u_phi, self.to_out[1], pro=(s2, t2, ops.ACT_NONE), act=ops.ACT_GELU)
         return conv_layer(h, self.to_out[3], residual=skip)

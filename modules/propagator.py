@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from lns_b200 import ops
 
-from ._base import LnsModule, LnsError, conv_layer, filt_of, norm_affine
+from ._base import LnsModule, LnsError, conv_layer, filt_of, norm_affine, lazy_norm
 from .basics import GroupNorm, ResidualBlock, Swish
 from .cond_utils import zero_module, fourier_embedding
 
@@ -47,13 +47,11 @@ class DilatedResidualBlock(LnsModule):
 def dilated_block_fwd(blk, x):
     """Works on this module's class and on the reference scripts' structurally identical one."""
     gn, c1, _, c2, _, c3 = blk.conv
-    s, t = norm_affine(x, gn)
-    h = conv_layer(x, c1, pro=(s, t, ops.ACT_NONE), act=ops.ACT_GELU)
+    h = conv_layer(x, c1, pro=lazy_norm(x, gn), act=ops.ACT_GELU)
     h = conv_layer(h, c2, act=ops.ACT_GELU)
     x = conv_layer(h, c3, residual=x)
     gn2, f1, _, f2 = blk.ffn
-    s, t = norm_affine(x, gn2)
-    h = conv_layer(x, f1, pro=(s, t, ops.ACT_NONE), act=ops.ACT_GELU)
+    h = conv_layer(x, f1, pro=lazy_norm(x, gn2), act=ops.ACT_GELU)
     return conv_layer(h, f2, residual=x)
 
 
@@ -62,8 +60,7 @@ def simple_cnn_fwd(net, z, out=None, out_dtype=None):
     z = conv_layer(z, net.in_proj)
     for blk in net.net:
         z = dilated_block_fwd(blk, z)
-    s, t = norm_affine(z, net.out_proj[0])
-    return conv_layer(z, net.out_proj[1], pro=(s, t, ops.ACT_NONE), out=out,
+    return conv_layer(z, net.out_proj[1], pro=lazy_norm(z, net.out_proj[0]), out=out,
                       out_dtype=out_dtype if out is None else None)
 
 
@@ -132,16 +129,13 @@ def cond_block_prepare(blk, cond_rows):
 def cond_block_fwd(blk, x, prepared):
     shift, one_plus_gate = prepared
     gn, c1, _, c2 = blk.conv1
-    s, t = norm_affine(x, gn)
-    h = conv_layer(x, c1, pro=(s, t, ops.ACT_NONE), act=ops.ACT_GELU)
+    h = conv_layer(x, c1, pro=lazy_norm(x, gn), act=ops.ACT_GELU)
     h = conv_layer(h, c2, sample_bias=shift)
     gn1, _, cz = blk.cond_conv1
-    s, t = norm_affine(h, gn1)
-    x = conv_layer(h, cz, pro=(s, t, ops.ACT_GELU), residual=x)
+    x = conv_layer(h, cz, pro=lazy_norm(h, gn1, ops.ACT_GELU), residual=x)
     # GN1(x * (1 + gate)): per-channel statistics of x rescale exactly, so the gate only enters the finalize kernel
     gn2, f1, _, f2 = blk.ffn
-    s, t = ops.group_norm_affine(x, gn2.num_groups, gn2.eps, gn2.weight, gn2.bias, prescale=one_plus_gate)
-    h = conv_layer(x, f1, pro=(s, t, ops.ACT_NONE), act=ops.ACT_GELU)
+    h = conv_layer(x, f1, pro=lazy_norm(x, gn2, prescale=one_plus_gate), act=ops.ACT_GELU)
     return conv_layer(h, f2, residual=x)
 
 
@@ -181,8 +175,7 @@ def cond_cnn_fwd(net, z, prepared, out=None, out_dtype=None):
     z = conv_layer(z, net.in_proj)
     for blk, prep in zip(net.net, prepared):
         z = cond_block_fwd(blk, z, prep)
-    s, t = norm_affine(z, net.out_proj[0])
-    return conv_layer(z, net.out_proj[1], pro=(s, t, ops.ACT_NONE), out=out,
+    return conv_layer(z, net.out_proj[1], pro=lazy_norm(z, net.out_proj[0]), out=out,
                       out_dtype=out_dtype if out is None else None)
 
 

@@ -427,3 +427,88 @@ def test_pointwise_projection(dtype):
                pro=(sc.to(DEV).reshape(-1), sh.to(DEV).reshape(-1), ops.ACT_SILU), out=dst, out_layout=ops.NCHW)
     assert relerr(out[:, 1].cpu(), ref) < 3e-6
     assert float(out[:, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (32, 32), (24, 48), (12, 20)])
+def test_fablock_fused_vs_unfused_and_oracle(H, W):
+    """Fused FABlock2D core (shared-memory resident u_phi) == the unfused kernel sequence (bf16 tolerance) and agrees
+    with the fp64 oracle of the reference block at bf16 accuracy."""
+    ops = ops_mod()
+    import lns_oracle as O
+    from modules.factorized_attention import FABlock2D
+    torch.manual_seed(3)
+    blk = FABlock2D(64, 64, 64, 8, 64).to(DEV).eval()
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(3, 64, H, W, generator=g)
+    sd = {k: v.cpu().double() for k, v in blk.state_dict().items()}
+    ref = O.fa_block(x.double(), O.SD(sd))
+    a = act_from(x, torch.bfloat16)
+    assert ops.fablock_core_supported(a, 64)
+    with torch.no_grad(), ops.precision("bf16"):
+        fused = act_to_nchw(blk._fwd(a))
+        # force the unfused path
+        orig = ops.fablock_core_supported
+        ops.fablock_core_supported = lambda *aa, **kk: False
+        try:
+            unfused = act_to_nchw(blk._fwd(a))
+        finally:
+            ops.fablock_core_supported = orig
+    e_f, e_u = relerr(fused, ref), relerr(unfused, ref)
+    print(f"\\n[FABlock2D {H}x{W} bf16] fused vs fp64 oracle {e_f:.2e}, unfused {e_u:.2e}, fused vs unfused {relerr(fused, unfused):.2e}")
+    assert e_f < 3e-2 and e_u < 3e-2
+    assert relerr(fused, unfused) < 2e-2
+
+
+@pytest.mark.parametrize("n", [16, 32, 24, 48, 15])
+def test_lowrank_kernel_tensor_core_bf16(n):
+    """mma.sync LowRankKernel (bf16 q|k) vs the fp64 oracle evaluated on the same bf16-rounded q|k"""
+    ops = ops_mod()
+    import lns_oracle as O
+    from modules.factorized_attention import LowRankKernel
+    torch.manual_seed(0)
+    lrk = LowRankKernel(64, 128, 8, use_rotary_emb=True).to(DEV)
+    g = torch.Generator().manual_seed(51)
+    qk = torch.randn(3, n, 2048, generator=g)
+    cos_t, sin_t = lrk._tables(n, torch.device(DEV))
+    K = ops.lowrank_kernel(ops.Act(qk.to(DEV).bfloat16().reshape(-1), 3, n, 1, 2048), 8, 128, cos_t, sin_t, 1.0)
+    # reference: rotary + q k^T in fp64 on the bf16-rounded projections
+    qr = qk.bfloat16().double()
+    q, k = qr.split(1024, dim=-1)
+    q = q.view(3, n, 8, 128).transpose(1, 2)
+    k = k.view(3, n, 8, 128).transpose(1, 2)
+    pos = torch.linspace(0, 1, n).double() * 64.0
+    fr = pos[:, None] * lrk.pos_emb.inv_freq.cpu().double()[None, :]
+    fr = torch.cat((fr, fr), dim=-1)[None, None]
+    ref = torch.einsum("bhid,bhjd->bhij", O._rotary(q, fr), O._rotary(k, fr))
+    assert relerr(K.cpu(), ref) < 5e-3  # rotated q, k are rounded to bf16 before the tensor-core product
+
+
+def test_conv_composition_3x3_then_1x1():
+    """conv1x1(conv3x3(x)) as ONE conv with the composed filter (decoder tail of the NS2d autoencoder)"""
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(61)
+    x = torch.randn(2, 64, 16, 16, generator=g)
+    w1, b1 = torch.randn(64, 64, 3, 3, generator=g) / 24, torch.randn(64, generator=g) * 0.1
+    w2, b2 = torch.randn(64, 64, 1, 1, generator=g) / 8, torch.randn(64, generator=g) * 0.1
+    ref = F.conv2d(ref_conv(x, w1, b1, 1, 1, (1, 1, 1, 1), (1, 1)), w2.double(), b2.double())
+    h1, h2 = Holder(w1, b1), Holder(w2, b2)
+    filt = ops.composed_filter(ops.PackedFilter.of(h1.weight, h1.bias), ops.PackedFilter.of(h2.weight, h2.bias))
+    with ops.precision("fp32"):
+        y = ops.conv2d(act_from(x), filt, pad=(1, 1, 1, 1), pad_mode=(1, 1), engine=ops.ENGINE_SIMT)
+    assert relerr(act_to_nchw(y), ref) < 3e-6
+
+
+@pytest.mark.parametrize("shape,groups", [((5, 128, 8, 8), 1), ((5, 128, 8, 8), 32), ((3, 64, 7, 15), 32)])
+def test_group_norm_act_fused_small(shape, groups):
+    """single-kernel statistics + normalise + activation == the two-kernel path, bit for bit"""
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(71)
+    x = torch.randn(*shape, generator=g) * 1.3 + 0.2
+    gamma, beta = (torch.rand(shape[1], generator=g) + 0.5).to(DEV), torch.randn(shape[1], generator=g).to(DEV)
+    a = act_from(x, torch.bfloat16)
+    fused = ops.LazyNorm(a, groups, 1e-5, gamma, beta, None, ops.ACT_GELU).materialize()
+    s, t = ops.group_norm_affine(a, groups, 1e-5, gamma, beta)
+    two = ops.affine_act(a, s, t, ops.ACT_GELU)
+    assert torch.equal(fused.t, two.t)
+    ref = F.gelu(F.group_norm(x.bfloat16().double(), groups, gamma.cpu().double(), beta.cpu().double(), 1e-5))
+    assert relerr(act_to_nchw(fused), ref) < 4e-3
