@@ -157,11 +157,18 @@ def conv_roofline(torch, ops, device, peaks, workload):
     t = sum(ms) / len(ms) * 1e-3
     flops = 2.0 * nb * H * W * Cout * 9 * Cin
     achieved = flops / t / 1e12
+    traffic = None  # dram read+write bytes per launch from the committed ncu --set full capture of this exact shape
+    tp = os.path.join(ROOT, "profiles", "r01_halo_traffic.json")
+    if workload == "ns2d" and os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("algorithmic_bytes") == nb * H * W * (Cin + Cout) * 2:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     peak = peaks["bf16_tflops"]  # burst figure: this kernel is timed alone
     return {"bound": "tensor", "kernel": f"conv_halo_kernel<{Cout}> (tcgen05, smem halo + resident filter) 3x3 {Cin}->{Cout} "
                                         f"@ {H}x{W}, batch {nb}",
             "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-            "traffic": None, "avg_launch_ms": round(t * 1e3, 4), "peak_source": peaks["source"],
+            "traffic": traffic, "algorithmic_bytes": nb * H * W * (Cin + Cout) * 2, "algorithmic_flops": flops,
+            "avg_launch_ms": round(t * 1e3, 4), "peak_source": peaks["source"],
             "hbm_gbs_at_algorithmic_bytes": round(nb * H * W * (Cin + Cout) * 2 / t / 1e9, 1)}
 
 

@@ -174,30 +174,33 @@ def nchw_to_act(x, dtype=None):
 # ---- weights ---------------------------------------------------------------------------------------------
 class PackedFilter:
     """Device-side re-laid copies of one conv / linear filter (OIHW fp32 source), built lazily per format and
-    rebuilt when a source parameter changes (load_state_dict, .to(), optimizer step)."""
+    rebuilt when a source parameter changes (load_state_dict, .to(), optimizer step).  `key_fn` is a cheap fingerprint
+    of the source parameters (data_ptr, version, device); the source tensors are only touched on a cache miss."""
 
-    def __init__(self, weight_fn, bias_fn=None):
-        self._weight_fn = weight_fn  # () -> (fp32 OIHW tensor [Cout,Cin,KH,KW], version key)
-        self._bias_fn = bias_fn      # () -> (fp32 [Cout] tensor or None, version key)
+    def __init__(self, weight_fn, bias_fn=None, key_fn=None, shape=None):
+        self._weight_fn = weight_fn  # () -> fp32 OIHW tensor [Cout,Cin,KH,KW]
+        self._bias_fn = bias_fn      # () -> fp32 [Cout] tensor or None
+        self._key_fn = key_fn        # () -> hashable fingerprint of the sources
         self._cache = {}
         self._bias = None
         self._bias_key = None
-        self.shape = None
+        self._shape = shape
+
+    @staticmethod
+    def _fp(t):
+        return None if t is None else (t.data_ptr(), t._version, str(t.device))
 
     @staticmethod
     def of(weight, bias=None):
         """weight: nn.Parameter [Cout,Cin,KH,KW] or [Cout,Cin] (nn.Linear); bias: nn.Parameter [Cout] or None"""
         def wfn():
             w = weight.detach()
-            if w.dim() == 2:
-                w = w[:, :, None, None]
-            return w, (weight.data_ptr(), weight._version, weight.device)
+            return w[:, :, None, None] if w.dim() == 2 else w
 
         def bfn():
-            if bias is None:
-                return None, None
-            return bias.detach(), (bias.data_ptr(), bias._version, bias.device)
-        return PackedFilter(wfn, bfn)
+            return None if bias is None else bias.detach()
+        shape = tuple(weight.shape) if weight.dim() == 4 else (weight.shape[0], weight.shape[1], 1, 1)
+        return PackedFilter(wfn, bfn, lambda: (PackedFilter._fp(weight), PackedFilter._fp(bias)), shape)
 
     @staticmethod
     def concat(weights, biases):
@@ -205,28 +208,33 @@ class PackedFilter:
         def wfn():
             ws = [w.detach() for w in weights]
             ws = [w[:, :, None, None] if w.dim() == 2 else w for w in ws]
-            return torch.cat(ws, 0), tuple((w.data_ptr(), w._version, w.device) for w in weights)
+            return torch.cat(ws, 0)
 
         def bfn():
             if all(b is None for b in biases):
-                return None, None
-            parts = []
-            for w, b in zip(weights, biases):
-                parts.append(b.detach().float() if b is not None
-                             else torch.zeros(w.shape[0], dtype=torch.float32, device=w.device))
-            return torch.cat(parts, 0), tuple((b.data_ptr(), b._version) if b is not None else None for b in biases)
-        return PackedFilter(wfn, bfn)
+                return None
+            parts = [b.detach().float() if b is not None else torch.zeros(w.shape[0], dtype=torch.float32, device=w.device)
+                     for w, b in zip(weights, biases)]
+            return torch.cat(parts, 0)
+        w0 = weights[0]
+        shape = (sum(w.shape[0] for w in weights), w0.shape[1]) + ((1, 1) if w0.dim() == 2 else tuple(w0.shape[2:]))
+        return PackedFilter(wfn, bfn, lambda: tuple(PackedFilter._fp(t) for t in list(weights) + list(biases)), shape)
+
+    def key(self):
+        return self._key_fn() if self._key_fn is not None else None
 
     def dims(self):
-        w, _ = self._weight_fn()
-        return tuple(w.shape)
+        if self._shape is None:
+            self._shape = tuple(self._weight_fn().shape)
+        return self._shape
 
     def get(self, fmt):
-        w, key = self._weight_fn()
-        _need_cuda(w, "PackedFilter")
+        key = self.key()
         ent = self._cache.get(fmt)
         if ent is not None and ent[0] == key:
             return ent[1]
+        w = self._weight_fn()
+        _need_cuda(w, "PackedFilter")
         Cout, Cin, KH, KW = w.shape
         nbytes = _C.lib().lns_packed_weight_bytes(Cout, Cin, KH, KW, fmt)
         if nbytes < 0:
@@ -242,12 +250,11 @@ class PackedFilter:
     def bias(self):
         if self._bias_fn is None:
             return None
-        b, key = self._bias_fn()
-        if b is None:
-            return None
-        if self._bias_key != key or self._bias is None:
-            self._bias = b.contiguous().float().clone()
-            self._bias_key = key
+        key = self.key()
+        if self._bias_key != key or self._bias_key is None:
+            b = self._bias_fn()
+            self._bias = None if b is None else b.contiguous().float().clone()
+            self._bias_key = key if key is not None else object()
         return self._bias
 
 
@@ -255,22 +262,21 @@ def composed_filter(first, second):
     """PackedFilter of  second(1x1) o first(kxk)  -- two convolutions with no non-linearity between them are one
     convolution: W'[o][i][tap] = sum_m W2[o][m] W1[m][i][tap],  b' = W2 b1 + b2  (composed in fp64, stored fp32)."""
     def wfn():
-        w1, k1 = first._weight_fn()
-        w2, k2 = second._weight_fn()
-        w = torch.einsum("om,mikl->oikl", w2[:, :, 0, 0].double(), w1.double()).float()
-        return w, (k1, k2)
+        w1, w2 = first._weight_fn(), second._weight_fn()
+        return torch.einsum("om,mikl->oikl", w2[:, :, 0, 0].double(), w1.double()).float()
 
     def bfn():
-        w2, k2 = second._weight_fn()
-        b1, kb1 = first._bias_fn() if first._bias_fn else (None, None)
-        b2, kb2 = second._bias_fn() if second._bias_fn else (None, None)
+        w2 = second._weight_fn()
+        b1 = first._bias_fn() if first._bias_fn else None
+        b2 = second._bias_fn() if second._bias_fn else None
         b = torch.zeros(w2.shape[0], dtype=torch.float64, device=w2.device)
         if b1 is not None:
             b = b + w2[:, :, 0, 0].double() @ b1.double()
         if b2 is not None:
             b = b + b2.double()
-        return b.float(), (k2, kb1, kb2)
-    return PackedFilter(wfn, bfn)
+        return b.float()
+    d1, d2 = first.dims(), second.dims()
+    return PackedFilter(wfn, bfn, lambda: (first.key(), second.key()), (d2[0], d1[1], d1[2], d1[3]))
 
 
 # ---- conv ---------------------------------------------------------------------------------------------------
@@ -364,11 +370,11 @@ def _pointwise_proj(x, filt, use_bias, pro, out):
     """Cout <= 4 output projection (NHWC -> NCHW fp32) with the norm/activation prologue: lns_pointwise_proj."""
     Cout, Cin, _, _ = filt.dims()
     w = filt.get(W_SIMT_F32)  # [1 tap][Cin][Cout] fp32 == [Cin][Cout]; the kernel wants [Cout][Cin]
-    key = ("proj", w.data_ptr())
-    wt = filt._cache.get(key)
-    if wt is None:
-        wt = w.view(torch.float32).view(Cin, Cout).t().contiguous()
-        filt._cache[key] = wt
+    ent = filt._cache.get("proj")
+    if ent is None or ent[0] != w.data_ptr():
+        ent = (w.data_ptr(), w.view(torch.float32).view(Cin, Cout).t().contiguous())
+        filt._cache["proj"] = ent
+    wt = ent[1]
     if out is None:
         out = Act(torch.empty(x.B * Cout * x.H * x.W, dtype=torch.float32, device=x.t.device), x.B, x.H, x.W, Cout,
                   layout=NCHW)
@@ -553,7 +559,7 @@ def fablock_prepass(u, eps, gamma, beta):
     dev = u.t.device
     scale = torch.empty(u.B * u.C, dtype=torch.float32, device=dev)
     shift = torch.empty_like(scale)
-    px = Act.empty(u.B, u.H, 1, u.C, torch.float32, dev)
+    px = Act.empty(u.B, u.H, 1, u.C, torch.float32, dev)   # fp32: tiny, and feeds per-sample low-rank kernels
     py = Act.empty(u.B, u.W, 1, u.C, torch.float32, dev)
     g = gamma.detach().float().contiguous() if gamma is not None else None
     b = beta.detach().float().contiguous() if beta is not None else None

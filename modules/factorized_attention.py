@@ -67,7 +67,7 @@ class PoolingReducer(LnsModule):
             nn.Linear(hidden_dim * 2, out_dim, bias=True))
 
     def _fwd(self, pooled):
-        f32 = torch.float32
+        f32 = pooled.t.dtype  # fp32 on the validation path, bf16 on the fast path (decided by FABlock2D)
         h = ops.conv2d(pooled, filt_of(self.to_in), out_dtype=f32)
         ln = self.out_ffn[0]
         h = ops.layernorm(h, ln.weight, ln.bias, ln.eps)
@@ -124,9 +124,12 @@ class FABlock2D(LnsModule):
             s, t = norm_affine(u, self.in_norm)
             un = ops.affine_act(u, s, t, ops.ACT_NONE)
             mx, my = ops.axis_mean(un, axis=1), ops.axis_mean(un, axis=0)
-        # mean over the other axis first (exact: to_in convs have no bias), then the two tiny linears
-        px = ops.conv2d(mx, filt_of(self.to_in[0]), out_dtype=f32)   # rows indexed by H
-        py = ops.conv2d(my, filt_of(self.to_in[0]), out_dtype=f32)   # rows indexed by W
+        # mean over the other axis first (exact: to_in convs have no bias), then the two tiny linears.  On the bf16 path the
+        # pooled branch is stored in bf16 from here on, so that its 64/128-wide linears run on the tensor-core engine
+        # (on the CUDA-core engine they were 8 % of the rollout).
+        pd = ops.act_dtype() if fused else f32
+        px = ops.conv2d(mx, filt_of(self.to_in[0]), out_dtype=pd)   # rows indexed by H
+        py = ops.conv2d(my, filt_of(self.to_in[0]), out_dtype=pd)   # rows indexed by W
         k_x = self.low_rank_kernel_x._fwd(self.to_x[0]._fwd(px))
         k_y = self.low_rank_kernel_y._fwd(self.to_y[1]._fwd(py))
         if fused:

@@ -27,11 +27,12 @@ class FreqLinear(LnsModule):
             w, b = self.weights, self.bias
 
             def wfn():  # [Ccond, 4 m1 m2] -> OIHW [4 m1 m2, Ccond, 1, 1]
-                return w.detach().t()[:, :, None, None], (w.data_ptr(), w._version, w.device)
+                return w.detach().t()[:, :, None, None]
 
             def bfn():
-                return b.detach().reshape(-1), (b.data_ptr(), b._version, b.device)
-            f = ops.PackedFilter(wfn, bfn)
+                return b.detach().reshape(-1)
+            f = ops.PackedFilter(wfn, bfn, lambda: (ops.PackedFilter._fp(w), ops.PackedFilter._fp(b)),
+                                 (w.shape[1], w.shape[0], 1, 1))
             self.__dict__["_lns_f"] = f
         return f
 
