@@ -181,7 +181,11 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
   const uint32_t w_base = smem_base;
   const uint32_t halo_base = smem_base + kWBytes;
   const uint32_t stage_out = halo_base + (uint32_t)p.stages * (uint32_t)p.halo_bytes;  // 4 warps x 4 KB output staging
-  const uint32_t bar_base = stage_out + 4u * 4096u;
+  // bias folded into the GEMM: one extra K=16 MMA per tile, A = a "ones" tile (8 rows, every row group aliases it through
+  // SBO = 0) with 1.0 in k = 0, 1; B = [Cout][k] with bias split as bf16 hi (k = 0) + lo (k = 1): hi + lo is exact to 2^-17.
+  const uint32_t bias_b = stage_out + 4u * 4096u;          // NT x 128 B, swizzled K-major like the filter
+  const uint32_t ones_a = bias_b + (uint32_t)NT * 128u;    // 8 x 128 B
+  const uint32_t bar_base = ones_a + 1024u;
   // barriers: w, halo_full[4], halo_empty[4], acc_full[4], acc_empty[4]; then the TMEM slot
   const uint32_t w_bar = bar_base;
   auto halo_full = [&](int s) { return bar_base + 8u * (1 + s); };
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
   auto acc_empty = [&](int a) { return bar_base + 8u * (13 + a); };
   const uint32_t tmem_slot = bar_base + 8u * 17;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + 4 * 4096 + 8 * 17);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + 4 * 4096 + NT * 128 + 1024 + 8 * 17);
 
   const ConvGeom& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
   if (tid == 0) {
     hptx::mbar_init(w_bar, 1);
     for (int s = 0; s < 4; ++s) {
-      hptx::mbar_init(halo_full(s), 128);
+      hptx::mbar_init(halo_full(s), 32);
       hptx::mbar_init(halo_empty(s), 1);
     }
     for (int a = 0; a < kAccs; ++a) {
@@ -211,6 +215,27 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
   if (warp == 4) {
     hptx::tmem_alloc(tmem_slot, kAccs * NT);
     hptx::tmem_relinquish();
+  }
+  if (p.bias) {
+    uint8_t* bb = smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + 4 * 4096;
+    for (int e = tid; e < NT * 8; e += blockDim.x) {  // 16-byte chunks of the bias B tile
+      const int n = e >> 3, ch = e & 7;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ch == 0 && n < g.Cout) {
+        const float bv = __ldg(p.bias + n);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
+        v.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+      }
+      *reinterpret_cast<uint4*>(bb + n * 128 + ((ch ^ (n & 7)) << 4)) = v;
+    }
+    for (int e = tid; e < 8 * 8; e += blockDim.x) {   // the ones tile
+      const int r = e >> 3, ch = e & 7;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ch == 0) v.x = 0x3F803F80u;  // bf16 (1.0, 1.0)
+      *reinterpret_cast<uint4*>(bb + NT * 128 + r * 128 + ((ch ^ r) << 4)) = v;
+    }
+    hptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
   }
   hptx::tc_fence_before();
   __syncthreads();
@@ -230,19 +255,25 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
     // resize; -1 marks "outside -> zero fill"); every 16-byte copy then costs two shuffles and an add.  (The first
     // version recomputed the full map per pixel: an 80-instruction dependent chain x 12 passes per tile made the
     // producers -- not the tensor pipe -- the bottleneck: 25% tensor-pipe active in the round-1 profile.)
-    const int chunk = tid & 7;
+    // One producer WARP per tile: warp w (< HS) takes tiles it = w, w+HS, ... and therefore always fills ring stage w.
+    // (One warp per STAGE matters: mbarrier parity waits are only race free when the waits on a barrier are issued in phase
+    // order by one agent.)  The per-tile fixed work (tile decode, separable terms, barrier round trip) is paid once per tile
+    // by one warp instead of by all four, and HS tiles are in flight independently.  8 lanes x 16 B per pixel, 4 pixels/pass.
+    const int chunk = lane & 7;
     const int npx = p.HH * p.HW;
-    const int q_first = tid >> 3;                       // pixel of pass 0; +16 per pass (q & 7 is pass invariant)
-    const uint32_t dst_first = (uint32_t)q_first * 128u + (uint32_t)((chunk ^ (q_first & 7)) << 4);
-    const int step_y = 16 / p.HW, step_x = 16 - step_y * p.HW;
+    const int q_first = lane >> 3;                      // pixel of pass 0; +4 per pass
+    const int step_y = 4 / p.HW, step_x = 4 - step_y * p.HW;
     const int hy_first = q_first / p.HW, hx_first = q_first - hy_first * p.HW;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int s = it % HS;
-      int tx = tile % p.tiles_x;
-      int t2 = tile / p.tiles_x;
-      int ty = t2 % p.tiles_y;
-      int b = t2 / p.tiles_y;
+    const int npass = (npx + 3) >> 2;
+    // incremental tile decode: tile = (b * tiles_y + ty) * tiles_x + tx advances by 4 * gridDim.x per visit of this warp
+    int tile = (warp < HS) ? blockIdx.x + warp * (int)gridDim.x : p.ntiles;  // warps >= HS have no stage: idle
+    int tx = tile % p.tiles_x, t2 = tile / p.tiles_x;
+    int ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
+    const int adv = HS * (int)gridDim.x;
+    const int adv_x = adv % p.tiles_x, adv_t2 = adv / p.tiles_x;
+    const int adv_y = adv_t2 % p.tiles_y, adv_b = adv_t2 / p.tiles_y;
+    for (int it = warp; tile < p.ntiles; it += HS, tile += adv) {
+      const int s = warp;  // == it % HS
       // separable source terms, one halo row / column per lane (HH <= 22, HW <= 14)
       int rowterm, colterm;
       {
@@ -270,19 +301,16 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
       const uint32_t st = halo_base + (uint32_t)s * (uint32_t)p.halo_bytes;
       const __nv_bfloat16* xb = p.x + (int64_t)b * g.x_bstride + chunk * 8;
       int hy = hy_first, hx = hx_first;
-      uint32_t dst = st + dst_first;
-      const int npass = (npx + 15) >> 4;  // warp-uniform trip count: the shuffles below need every lane
       int q = q_first;
 #pragma unroll 4
-      for (int pass = 0; pass < npass; ++pass, q += 16) {
+      for (int pass = 0; pass < npass; ++pass, q += 4) {
         const int rt = __shfl_sync(0xFFFFFFFFu, rowterm, hy & 31);
         const int ct = __shfl_sync(0xFFFFFFFFu, colterm, hx & 31);
         if (q < npx && !(p.debug & 1)) {
           const bool ok = (rt | ct) >= 0;
           const void* src = ok ? (const void*)(xb + (rt + ct)) : (const void*)p.x;
-          hptx::cp_async16(dst, src, ok ? 16u : 0u);
+          hptx::cp_async16(st + (uint32_t)q * 128u + (uint32_t)((chunk ^ (q & 7)) << 4), src, ok ? 16u : 0u);
         }
-        dst += 2048u;
         hy += step_y;
         hx += step_x;
         if (hx >= p.HW) {
@@ -291,6 +319,12 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
         }
       }
       hptx::cp_async_arrive_noinc(halo_full(s));
+      // next tile of this warp
+      tx += adv_x;
+      if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+      ty += adv_y;
+      if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
+      b += adv_b;
     }
   } else if (warp < 4 + kIssuers) {
     // ============================== MMA issuers ==============================
@@ -331,6 +365,9 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
             hptx::umma_bf16_if((p.debug & 4) ? 0u : leader, d_tmem, a_lo + 2u * k, desc_hi_a, b_lo + 2u * k, desc_hi_b, idesc,
                                (tap | k) != 0 ? 1u : 0u);
         }
+        if (p.bias)
+          hptx::umma_bf16_if(leader, d_tmem, (ones_a & 0x3FFFFu) >> 4, (1u << 14) | (2u << 29) /* SBO = 0 */,
+                             (bias_b & 0x3FFFFu) >> 4, desc_hi_b, idesc, 1u);
         hptx::umma_commit_if(leader, halo_empty(s));
         hptx::umma_commit_if(leader, acc_full(a));
       }
@@ -350,12 +387,19 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
     const uint32_t my_row_st = my_stage + (uint32_t)lane * 128u;
     const int rd_row = lane >> 3, rd_chunk = lane & 7;  // read-back: 4 rows per pass, 8 lanes x 16 B per row
     int it = 0;
+    int tx, ty, b;
+    {
+      const int t0 = blockIdx.x;
+      tx = t0 % p.tiles_x;
+      const int t2 = t0 / p.tiles_x;
+      ty = t2 % p.tiles_y;
+      b = t2 / p.tiles_y;
+    }
+    const int eadv = (int)gridDim.x;
+    const int eadv_x = eadv % p.tiles_x, eadv_t2 = eadv / p.tiles_x;
+    const int eadv_y = eadv_t2 % p.tiles_y, eadv_b = eadv_t2 / p.tiles_y;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int a = it % kAccs;
-      int tx = tile % p.tiles_x;
-      int t2 = tile / p.tiles_x;
-      int ty = t2 % p.tiles_y;
-      int b = t2 / p.tiles_y;
       const int yo = ty * kTileH + ty_l, xo = tx * kTileW + tx_l;
       const bool row_ok = yo < g.Hout && xo < g.Wout;
       const int64_t pix = (int64_t)yo * g.Wout + xo;
@@ -376,13 +420,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-            }
-          }
+          // (bias: already in the accumulator -- folded into the GEMM by the issue warps)
           if (row_ok) {
             if (p.sample_bias) {
 #pragma unroll
@@ -451,6 +489,11 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
       }
       hptx::tc_fence_before();
       hptx::mbar_arrive(acc_empty(a));
+      tx += eadv_x;
+      if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+      ty += eadv_y;
+      if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
+      b += eadv_b;
     }
   }
 
@@ -525,7 +568,7 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
     p.debug = dbg ? atoi(dbg) : 0;
   }
   const int NT = d->Cout;
-  const int fixed = 9 * NT * 128 + 4 * 4096 /*output staging*/ + 256 + 1024;
+  const int fixed = 9 * NT * 128 + 4 * 4096 /*output staging*/ + NT * 128 + 1024 /*bias + ones tiles*/ + 256 + 1024;
   int stages = (227 * 1024 - fixed) / p.halo_bytes;
   if (stages > 4) stages = 4;
   LNS_REQUIRE(stages >= 2, "lns_conv2d(halo): shared memory too small for dilation %d with Cout %d", d->dil, d->Cout);
