@@ -39,9 +39,9 @@ __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta
 // In-place axial contraction of one line (an image column or row) held in U_s:
 //   out[i][c] = sum_j Kmat[i][j] * line[j][c],  line element j lives at U_s + base + j*step  (offsets in bf16 elements).
 // KT = ceil(n/16) k/m tiles.  The whole line (B fragments) is read into registers before anything is written.
-template <int KT>
+template <int KT, bool STATS>
 __device__ __forceinline__ void contract_line(__nv_bfloat16* U_s, int base, int step, int n, const __nv_bfloat16* K_s, int kstride,
-                                              int lane) {
+                                              int lane, float* st) {
   uint32_t bf[KT][8][2];
 #pragma unroll
   for (int kt = 0; kt < KT; ++kt) {
@@ -66,21 +66,29 @@ __device__ __forceinline__ void contract_line(__nv_bfloat16* U_s, int base, int 
       for (int nt = 0; nt < 8; ++nt) mma16816(acc[nt], a, bf[kt][nt][0], bf[kt][nt][1]);
     }
     const int i0 = mt * 16 + g, i1 = i0 + 8;
+    const bool v0 = i0 < n, v1 = i1 < n;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      if (i0 < n)
+      if (v0)
         *reinterpret_cast<__nv_bfloat162*>(U_s + (size_t)base + (size_t)i0 * step + nt * 8 + t * 2) = __floats2bfloat162_rn(acc[nt][0], acc[nt][1]);
-      if (i1 < n)
+      if (v1)
         *reinterpret_cast<__nv_bfloat162*>(U_s + (size_t)base + (size_t)i1 * step + nt * 8 + t * 2) = __floats2bfloat162_rn(acc[nt][2], acc[nt][3]);
+      if (STATS) {  // InstanceNorm sums of channels nt*8 + 2t, +1 (fp32 values, before the bf16 rounding of the store)
+        const float a0 = v0 ? acc[nt][0] : 0.f, a1 = v0 ? acc[nt][1] : 0.f, a2 = v1 ? acc[nt][2] : 0.f, a3 = v1 ? acc[nt][3] : 0.f;
+        st[nt * 4 + 0] += a0 + a2;
+        st[nt * 4 + 1] += a1 + a3;
+        st[nt * 4 + 2] = fmaf(a0, a0, fmaf(a2, a2, st[nt * 4 + 2]));
+        st[nt * 4 + 3] = fmaf(a1, a1, fmaf(a3, a3, st[nt * 4 + 3]));
+      }
     }
   }
   __syncwarp();
 }
 
-template <int KT>
+template <int KT, bool STATS>
 __device__ __forceinline__ void contract_axis(__nv_bfloat16* U_s, int lines, int line_mul, int step, int n, const __nv_bfloat16* K_s,
-                                              int kstride, int warp, int nwarp, int lane) {
-  for (int l = warp; l < lines; l += nwarp) contract_line<KT>(U_s, l * line_mul, step, n, K_s, kstride, lane);  // offsets in elements
+                                              int kstride, int warp, int nwarp, int lane, float* st) {
+  for (int l = warp; l < lines; l += nwarp) contract_line<KT, STATS>(U_s, l * line_mul, step, n, K_s, kstride, lane, st);
 }
 }  // namespace
 
@@ -113,11 +121,45 @@ __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat
   const int C = heads * 64;
   const __nv_bfloat16* ub = u + (int64_t)b * HW * 64;
 
+  // ---- phase A loads first: the raw input streams in (cp.async, four commit groups = four quarters of the image) while the
+  // setup below runs.  The 1x1 in_proj is pointwise in space, so the rows are copied straight into the rows of U_s they will
+  // be replaced in: no staging buffer, no block-wide barrier per tile.
+  const int nblk = (HW + 15) >> 4;                 // 16-row blocks
+  const int blk_per_q = (nblk + 3) >> 2;
+  const float invW = 1.0f / (float)W;
+  {
+    const int ch = tid & 7;
+    int px = tid >> 3;                             // 8 lanes x 16 B per pixel row
+    int y = __float2int_rd(((float)px + 0.5f) * invW), x = px - y * W;
+    const int sy = ppi / W, sx = ppi - sy * W;
+    for (int q = 0; q < 4; ++q) {
+      const int px_end = min(HW, (q + 1) * blk_per_q * 16);
+      for (; px < px_end; px += ppi) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(U_s + (size_t)y * RS + (size_t)x * kUS + ch * 8)),
+                     "l"(ub + (int64_t)px * 64 + ch * 8) : "memory");
+        y += sy;
+        x += sx;
+        if (x >= W) {
+          x -= W;
+          ++y;
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+
   // ---- setup: per-sample filter (GroupNorm scale folded in), bias (GroupNorm shift folded in), kernel matrices ----
-#pragma unroll 4
-  for (int e = tid; e < 64 * 64; e += nthr) {
-    int n = e >> 6, k = e & 63;
-    Ws_s[n * kUS + k] = __float2bfloat16_rn(__ldg(w_in + (int64_t)(h * 64 + n) * 64 + k) * __ldg(gn_scale + (int64_t)b * 64 + k));
+  for (int e = tid; e < 64 * 8; e += nthr) {       // (output channel n, 8-wide k chunk): 16-byte shared stores
+    const int n = e >> 3, kc = e & 7;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_in + (int64_t)(h * 64 + n) * 64 + kc * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_in + (int64_t)(h * 64 + n) * 64 + kc * 8 + 4));
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(gn_scale + (int64_t)b * 64 + kc * 8));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(gn_scale + (int64_t)b * 64 + kc * 8 + 4));
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(w0.x * s0.x, w0.y * s0.y), p1 = __floats2bfloat162_rn(w0.z * s0.z, w0.w * s0.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(w1.x * s1.x, w1.y * s1.y), p3 = __floats2bfloat162_rn(w1.z * s1.z, w1.w * s1.w);
+    *reinterpret_cast<uint4*>(Ws_s + n * kUS + kc * 8) =
+        make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
+                   *reinterpret_cast<uint32_t*>(&p3));
   }
   {
     // bias[n] = sum_k W[n][k] * shift[k]: 4 threads per output channel, 16 k each, fixed-order quad reduction
@@ -144,34 +186,7 @@ __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat
         Ky_s[i * kys + j] = __float2bfloat16_rn((i < W && j < W) ? __ldg(kg + i * W + j) : 0.f);
   }
 
-  // ---- phase A: u_phi_h = u x Ws^T + bias, IN PLACE.  The 1x1 in_proj is pointwise in space, so the raw rows are
-  // copied (cp.async, four commit groups = four quarters of the image) straight into the rows of U_s they will be replaced
-  // in; a warp transforms 16-row blocks (ldmatrix all A fragments of the block, then overwrite it) -- no staging buffer, no
-  // block-wide barrier per tile, and quarter q+1 is still landing while quarter q is being multiplied.
-  const int nblk = (HW + 15) >> 4;                 // 16-row blocks
-  const int blk_per_q = (nblk + 3) >> 2;
-  {
-    int y = 0, x = 0;  // this thread's first pixel: (tid >> 3); 8 lanes x 16 B per pixel row
-    const int ch = tid & 7;
-    int px = tid >> 3;
-    y = px / W;
-    x = px - y * W;
-    const int sy = ppi / W, sx = ppi - sy * W;
-    for (int q = 0; q < 4; ++q) {
-      const int px_end = min(HW, (q + 1) * blk_per_q * 16);
-      for (; px < px_end; px += ppi) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(U_s + (size_t)y * RS + (size_t)x * kUS + ch * 8)),
-                     "l"(ub + (int64_t)px * 64 + ch * 8) : "memory");
-        y += sy;
-        x += sx;
-        if (x >= W) {
-          x -= W;
-          ++y;
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-  }
+  // ---- phase A: u_phi_h = u x Ws^T + bias, in place, 16-row blocks per warp ----
   const int g = lane >> 2, t = lane & 3;
   uint32_t wf[4][8][2];  // B fragments of the per-sample filter: identical for every 16-row block -> loaded once
   for (int q = 0; q < 4; ++q) {
@@ -192,7 +207,7 @@ __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat
       // rows of this block: pixels blk*16 .. blk*16+15 (rows >= HW do not exist: clamp reads, skip writes)
       int pr = blk * 16 + (lane & 15);
       pr = pr < HW ? pr : HW - 1;
-      const int yr = pr / W;
+      const int yr = __float2int_rd(((float)pr + 0.5f) * invW);  // exact: pr < 2^20
       const __nv_bfloat16* arow = U_s + (size_t)yr * RS + (size_t)(pr - yr * W) * kUS;
       uint32_t a[4][4];
 #pragma unroll
@@ -207,106 +222,101 @@ __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat
       }
       __syncwarp();  // every lane's ldmatrix of the raw rows is done before they are overwritten
       const int r0 = blk * 16 + g, r1 = r0 + 8;
-      const int y0 = r0 / W, y1 = r1 / W;
-      const size_t o0 = (size_t)y0 * RS + (size_t)(r0 - y0 * W) * kUS, o1 = (size_t)y1 * RS + (size_t)(r1 - y1 * W) * kUS;
+      const int y0 = __float2int_rd(((float)r0 + 0.5f) * invW), y1 = __float2int_rd(((float)r1 + 0.5f) * invW);
+      __nv_bfloat16* o0 = U_s + (size_t)y0 * RS + (size_t)(r0 - y0 * W) * kUS + t * 2;
+      __nv_bfloat16* o1 = U_s + (size_t)y1 * RS + (size_t)(r1 - y1 * W) * kUS + t * 2;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const float bs0 = bias_s[nt * 8 + t * 2], bs1 = bias_s[nt * 8 + t * 2 + 1];
-        if (r0 < HW) *reinterpret_cast<__nv_bfloat162*>(U_s + o0 + nt * 8 + t * 2) = __floats2bfloat162_rn(acc[nt][0] + bs0, acc[nt][1] + bs1);
-        if (r1 < HW) *reinterpret_cast<__nv_bfloat162*>(U_s + o1 + nt * 8 + t * 2) = __floats2bfloat162_rn(acc[nt][2] + bs0, acc[nt][3] + bs1);
+        const float2 bs = *reinterpret_cast<const float2*>(bias_s + nt * 8 + t * 2);
+        if (r0 < HW) *reinterpret_cast<__nv_bfloat162*>(o0 + nt * 8) = __floats2bfloat162_rn(acc[nt][0] + bs.x, acc[nt][1] + bs.y);
+        if (r1 < HW) *reinterpret_cast<__nv_bfloat162*>(o1 + nt * 8) = __floats2bfloat162_rn(acc[nt][2] + bs.x, acc[nt][3] + bs.y);
       }
     }
   }
   __syncthreads();
 
   // ---- phase B: contraction over H, one image column per warp at a time (element j of column m at m*72 + j*RS) ----
-  if (H16 == 16) contract_axis<1>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane);
-  else if (H16 == 32) contract_axis<2>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane);
-  else contract_axis<3>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane);
+  float st[32];  // phase C: per-thread InstanceNorm partial sums: [nt][sum(2t), sum(2t+1), sumsq(2t), sumsq(2t+1)]
+#pragma unroll
+  for (int i = 0; i < 32; ++i) st[i] = 0.f;
+  if (H16 == 16) contract_axis<1, false>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane, st);
+  else if (H16 == 32) contract_axis<2, false>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane, st);
+  else contract_axis<3, false>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane, st);
   __syncthreads();
-  // ---- phase C: contraction over W, one image row per warp (element m of row i at i*RS + m*72) ----
-  if (W16 == 16) contract_axis<1>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane);
-  else if (W16 == 32) contract_axis<2>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane);
-  else contract_axis<3>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane);
-  __syncthreads();
+  // ---- phase C: contraction over W, one image row per warp (element m of row i at i*RS + m*72); its epilogue also
+  // accumulates the InstanceNorm sums of the 16 channels a thread holds (no separate statistics pass over the tile) ----
+  if (W16 == 16) contract_axis<1, true>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane, st);
+  else if (W16 == 32) contract_axis<2, true>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane, st);
+  else contract_axis<3, true>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane, st);
 
-  // ---- phase D: InstanceNorm statistics (biased variance) of this head's 64 channels over the H*W pixels ----
-  // thread = (8-channel chunk, one of 32 pixel groups): 16-byte shared loads, fixed-order reduction over the 32 groups
-  {
-    const int ch = tid & 7, pg = tid >> 3;
-    float s[8], ss[8];
+  // ---- phase D: reduce the partial sums: over the 8 lanes that share t (shuffles), then over the warps (fixed order) ----
 #pragma unroll
-    for (int j2 = 0; j2 < 8; ++j2) s[j2] = ss[j2] = 0.f;
-    int px = pg;
-    int y = px / W, x = px - y * W;
-    const int sy = ppi / W, sx = ppi - sy * W;
-    for (; px < HW; px += ppi) {
-      uint4 raw = *reinterpret_cast<const uint4*>(U_s + (size_t)y * RS + (size_t)x * kUS + ch * 8);
-      uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  for (int i = 0; i < 32; ++i) {
+    st[i] += __shfl_xor_sync(0xffffffffu, st[i], 4);
+    st[i] += __shfl_xor_sync(0xffffffffu, st[i], 8);
+    st[i] += __shfl_xor_sync(0xffffffffu, st[i], 16);
+  }
+  if (lane < 4) {  // g == 0: channels nt*8 + 2*lane, +1
 #pragma unroll
-      for (int j2 = 0; j2 < 4; ++j2) {
-        float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j2]));
-        s[2 * j2] += f.x; ss[2 * j2] = fmaf(f.x, f.x, ss[2 * j2]);
-        s[2 * j2 + 1] += f.y; ss[2 * j2 + 1] = fmaf(f.y, f.y, ss[2 * j2 + 1]);
-      }
-      y += sy;
-      x += sx;
-      if (x >= W) {
-        x -= W;
-        ++y;
-      }
-    }
-#pragma unroll
-    for (int j2 = 0; j2 < 8; ++j2) {
-      red_s[(pg * 64 + ch * 8 + j2) * 2 + 0] = s[j2];
-      red_s[(pg * 64 + ch * 8 + j2) * 2 + 1] = ss[j2];
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = nt * 8 + lane * 2;
+      red_s[(warp * 64 + c) * 2 + 0] = st[nt * 4 + 0];
+      red_s[(warp * 64 + c + 1) * 2 + 0] = st[nt * 4 + 1];
+      red_s[(warp * 64 + c) * 2 + 1] = st[nt * 4 + 2];
+      red_s[(warp * 64 + c + 1) * 2 + 1] = st[nt * 4 + 3];
     }
   }
   __syncthreads();
   if (tid < 64) {
-    double s = 0.0, ss = 0.0;
-    for (int gq = 0; gq < ppi; ++gq) {
-      s += (double)red_s[(gq * 64 + tid) * 2 + 0];
-      ss += (double)red_s[(gq * 64 + tid) * 2 + 1];
+    double sm = 0.0, ss = 0.0;
+    for (int w = 0; w < nwarp; ++w) {
+      sm += (double)red_s[(w * 64 + tid) * 2 + 0];
+      ss += (double)red_s[(w * 64 + tid) * 2 + 1];
     }
-    double mean = s / (double)HW;
+    const double mean = sm / (double)HW;
     double var = ss / (double)HW - mean * mean;
     if (var < 0.0) var = 0.0;
-    stat_s[tid * 2 + 0] = (float)mean;
-    stat_s[tid * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    stat_s[tid * 2 + 0] = (float)rstd;                 // scale
+    stat_s[tid * 2 + 1] = (float)(-mean * rstd);       // shift
   }
   __syncthreads();
 
   // ---- phase E: normalise and write channels [h*64, h*64+64) of out [B][HW][C]; 8 lanes x 16 B per pixel ----
-  __nv_bfloat16* ob = out + (int64_t)b * HW * C + h * 64;
-  const int stepy = ppi / W, stepx = ppi - stepy * W;  // the block advances ppi pixels per iteration
-  int py = (tid >> 3) / W, pxx = (tid >> 3) - py * W;
-  float mu[8], rs[8];  // this thread always handles the same 8 channels
+  {
+    const int ch = tid & 7;
+    float na[8], nb[8];  // this thread always handles the same 8 channels: y = x * na + nb
 #pragma unroll
-  for (int j2 = 0; j2 < 8; ++j2) {
-    mu[j2] = stat_s[((tid & 7) * 8 + j2) * 2];
-    rs[j2] = stat_s[((tid & 7) * 8 + j2) * 2 + 1];
-  }
-  for (int e = tid; e < HW * 8; e += nthr) {
-    const int px = e >> 3, ch = e & 7;
-    uint4 raw = *reinterpret_cast<const uint4*>(U_s + (size_t)py * RS + (size_t)pxx * kUS + ch * 8);
-    py += stepy;
-    pxx += stepx;
-    if (pxx >= W) {
-      pxx -= W;
-      ++py;
+    for (int j2 = 0; j2 < 8; ++j2) {
+      na[j2] = stat_s[(ch * 8 + j2) * 2];
+      nb[j2] = stat_s[(ch * 8 + j2) * 2 + 1];
     }
-    uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-    uint32_t o[4];
+    int px = tid >> 3;
+    int py = __float2int_rd(((float)px + 0.5f) * invW), pxx = px - py * W;
+    const int stepy = ppi / W, stepx = ppi - stepy * W;
+    const __nv_bfloat16* sp = U_s + (size_t)py * RS + (size_t)pxx * kUS + ch * 8;
+    const int sadv = stepy * RS + stepx * kUS, swrap = RS - W * kUS;  // element advance per iteration / extra on row wrap
+    __nv_bfloat16* gp = out + ((int64_t)b * HW + px) * C + h * 64 + ch * 8;
+    const int64_t gadv = (int64_t)ppi * C;
+    for (; px < HW; px += ppi) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(sp);
+      uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
-      f.x = (f.x - mu[2 * j]) * rs[2 * j];
-      f.y = (f.y - mu[2 * j + 1]) * rs[2 * j + 1];
-      __nv_bfloat162 hh = __floats2bfloat162_rn(f.x, f.y);
-      o[j] = *reinterpret_cast<uint32_t*>(&hh);
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
+        __nv_bfloat162 hh = __floats2bfloat162_rn(fmaf(f.x, na[2 * j], nb[2 * j]), fmaf(f.y, na[2 * j + 1], nb[2 * j + 1]));
+        o[j] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      *reinterpret_cast<uint4*>(gp) = make_uint4(o[0], o[1], o[2], o[3]);
+      gp += gadv;
+      sp += sadv;
+      pxx += stepx;
+      if (pxx >= W) {
+        pxx -= W;
+        sp += swrap;
+      }
     }
-    *reinterpret_cast<uint4*>(ob + (int64_t)px * C + ch * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -464,7 +474,7 @@ int lns_fablock_core(const void* u, int B, int H, int W, int heads, const float*
   }
   dim3 grid(heads, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (H <= 32 && W <= 32)  // <= 2 k-tiles per axis: fits 128 registers per thread
+  if (H <= 32 && W <= 32 && H * W > 256)  // <= 2 k-tiles per axis: fits 128 registers per thread; small images: 2+ CTAs/SM
     lns::fablock_core_kernel<512><<<grid, 512, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(u), H, W, heads, gn_scale, gn_shift,
                                                             w_in_proj, Kx, Ky, eps, reinterpret_cast<__nv_bfloat16*>(out));
   else
