@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--workload", default="ns2d", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="trajectories per GPU (default: workload's)")
     ap.add_argument("--rollout-steps", type=int, default=None)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the final all-gather of fields for N > 1")
     ap.add_argument("--decode-chunk", type=int, default=None, help="samples per decode launch group (default: engine's)")
@@ -297,7 +297,7 @@ def main():
             "metric": "latent rollout trajectory-steps/sec", "value": round(value, 1), "unit": "trajectory-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": label, "rollout_steps": R, "trajectories_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"trajectory-sharded x{world}" + (", final all-gather of fields" if gather else ""),
                        "l2": "per-step working set (activations) is far larger than the 126 MB L2; no explicit flush",

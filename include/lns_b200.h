@@ -33,15 +33,22 @@ extern "C" {
 #define LNS_E_CUDA (-2)        /* CUDA launch error, see lns_last_error() */
 #define LNS_E_UNSUPPORTED (-3) /* combination not implemented by this path */
 
-enum { LNS_F32 = 0, LNS_BF16 = 1 };
+enum {
+  LNS_F32 = 0,
+  LNS_BF16 = 1,
+  LNS_TF32 = 2 /* stored as fp32, every value rounded to nearest TF32 (10-bit mantissa) when written: the storage type of
+                  the tf32 precision mode, whose convolutions run on tcgen05.mma.kind::tf32 (which ignores the low 13 bits) */
+};
 enum { LNS_NHWC = 0, LNS_NCHW = 1 };
 enum { LNS_ACT_NONE = 0, LNS_ACT_SILU = 1, LNS_ACT_GELU = 2 };
 enum { LNS_PAD_ZEROS = 0, LNS_PAD_CIRCULAR = 1 };
 /* weight formats produced by lns_pack_conv_weight */
 enum {
   LNS_W_SIMT_F32 = 0, /* [tap][Cin][Cout] fp32 (CUDA-core validation path, any Cin/Cout)      */
-  LNS_W_UMMA_BF16 = 1 /* [tap][Cin/64][Cout][64] bf16, K-major 128B-swizzled smem image for     */
-                      /* tcgen05.mma (needs Cin % 64 == 0 and Cout % 16 == 0)                   */
+  LNS_W_UMMA_BF16 = 1, /* [tap][Cin/64][Cout][64] bf16, K-major 128B-swizzled smem image for     */
+                       /* tcgen05.mma (needs Cin % 64 == 0 and Cout % 16 == 0)                   */
+  LNS_W_UMMA_TF32 = 2  /* [tap][Cin/32][Cout][32] fp32 rounded to TF32, same swizzled image, for   */
+                       /* tcgen05.mma.kind::tf32 (needs Cin % 32 == 0 and Cout % 16 == 0)         */
 };
 /* which engine executes lns_conv2d */
 enum {

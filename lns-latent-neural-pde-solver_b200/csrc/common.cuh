@@ -22,19 +22,27 @@ int check_launch(const char* what);  // cudaGetLastError -> LNS_E_CUDA (+ messag
   } while (0)
 
 // ---- dtype helpers -------------------------------------------------------------------------------
+// LNS_TF32 storage = fp32 words whose values were rounded to nearest TF32 when written (loads are plain fp32 loads)
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ float ld_as_float(const void* p, int dtype, int64_t i) {
-  if (dtype == LNS_F32) return __ldg(reinterpret_cast<const float*>(p) + i);
+  if (dtype != LNS_BF16) return __ldg(reinterpret_cast<const float*>(p) + i);
   return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
 }
 __device__ __forceinline__ void st_from_float(void* p, int dtype, int64_t i, float v) {
   if (dtype == LNS_F32)
     reinterpret_cast<float*>(p)[i] = v;
+  else if (dtype == LNS_TF32)
+    reinterpret_cast<float*>(p)[i] = round_tf32(v);
   else
     reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
 }
 // 4 consecutive elements (i must be a multiple of 4 and the pointer suitably aligned)
 __device__ __forceinline__ float4 ld4_as_float(const void* p, int dtype, int64_t i) {
-  if (dtype == LNS_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i));
+  if (dtype != LNS_BF16) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i));
   uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i));
   __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
   __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
@@ -44,6 +52,9 @@ __device__ __forceinline__ float4 ld4_as_float(const void* p, int dtype, int64_t
 __device__ __forceinline__ void st4_from_float(void* p, int dtype, int64_t i, float4 v) {
   if (dtype == LNS_F32) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = v;
+  } else if (dtype == LNS_TF32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) =
+        make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
   } else {
     __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
     __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
@@ -53,7 +64,7 @@ __device__ __forceinline__ void st4_from_float(void* p, int dtype, int64_t i, fl
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = raw;
   }
 }
-__host__ __device__ __forceinline__ int dtype_size(int dtype) { return dtype == LNS_F32 ? 4 : 2; }
+__host__ __device__ __forceinline__ int dtype_size(int dtype) { return dtype == LNS_BF16 ? 2 : 4; }
 
 // ---- activations (exact forms, matching torch) ----------------------------------------------------
 // Swish  x*sigmoid(x)   modules/basics.py:27-29 ; nn.GELU() exact erf  train_stage2_ns2d.py:36

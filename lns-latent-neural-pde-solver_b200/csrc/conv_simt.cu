@@ -203,6 +203,25 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, int Cout, int Cin,
   }
 }
 
+// [tap][Cin/32][Cout][32] fp32 rounded to nearest TF32; 16-byte chunks (4 values) XOR-swizzled with (row & 7)
+__global__ void pack_umma_tf32_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, float* __restrict__ out) {
+  int64_t total = (int64_t)Cout * Cin * KH * KW;
+  int slabs = Cin / 32;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int kk = (int)(i % 32);
+    int64_t r = i / 32;
+    int n = (int)(r % Cout);
+    r /= Cout;
+    int slab = (int)(r % slabs);
+    int tap = (int)(r / slabs);
+    int c = slab * 32 + kk;
+    float v = round_tf32(w[((int64_t)n * Cin + c) * KH * KW + tap]);
+    int chunk = (kk >> 2) ^ (n & 7);
+    int64_t o = (((int64_t)tap * slabs + slab) * Cout + n) * 32 + chunk * 4 + (kk & 3);
+    out[o] = v;
+  }
+}
+
 }  // namespace lns
 
 extern "C" {
@@ -211,6 +230,7 @@ int64_t lns_packed_weight_bytes(int Cout, int Cin, int KH, int KW, int format) {
   int64_t n = (int64_t)Cout * Cin * KH * KW;
   if (format == LNS_W_SIMT_F32) return n * 4;
   if (format == LNS_W_UMMA_BF16) return (Cin % 64 == 0 && Cout % 16 == 0) ? n * 2 : -1;
+  if (format == LNS_W_UMMA_TF32) return (Cin % 32 == 0 && Cout % 16 == 0) ? n * 4 : -1;
   return -1;
 }
 
@@ -226,6 +246,10 @@ int lns_pack_conv_weight(const float* w, int Cout, int Cin, int KH, int KW, int 
     LNS_REQUIRE(Cin % 64 == 0 && Cout % 16 == 0, "lns_pack_conv_weight: UMMA format needs Cin%%64==0, Cout%%16==0 (got %d,%d)",
                 Cin, Cout);
     lns::pack_umma_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, KH, KW, reinterpret_cast<__nv_bfloat16*>(out));
+  } else if (format == LNS_W_UMMA_TF32) {
+    LNS_REQUIRE(Cin % 32 == 0 && Cout % 16 == 0, "lns_pack_conv_weight: TF32 format needs Cin%%32==0, Cout%%16==0 (got %d,%d)",
+                Cin, Cout);
+    lns::pack_umma_tf32_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, KH, KW, reinterpret_cast<float*>(out));
   } else {
     lns::set_error("lns_pack_conv_weight: unknown format %d", format);
     return LNS_E_INVALID;

@@ -85,6 +85,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same for fp32 operands read as TF32 (K = 8 per instruction = the same 32 bytes of a swizzled row)
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -114,11 +125,15 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
+// kind::tf32: D=f32, A=B=tf32 (format code 2)
+__device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 struct UmmaParams {
   ConvGeom g;
-  const __nv_bfloat16* x;
-  const __nv_bfloat16* w;
+  const void* x;  // bf16 (ESZ 2) or fp32/tf32 (ESZ 4) NHWC
+  const void* w;  // packed [tap][slab][Cout][128 B]
   const float* bias;
   const float* sample_bias;
   int act;
@@ -131,7 +146,7 @@ struct UmmaParams {
   void* y;
   int y_dtype;
   int M;
-  int slabs;  // Cin / 64
+  int slabs;  // Cin / (128 / ESZ): 128-byte K blocks per pixel
   uint32_t x_bstride8;  // input batch stride in 16-byte units
   int resize;           // 0 none, 1 exact 2x nearest, 2 general nearest
   float inv_wout, inv_hout, inv_hv, inv_wv;
@@ -148,7 +163,7 @@ struct UmmaSmem {
   static constexpr int kTotal = kBarOffset + 256 /*barriers + tmem ptr*/ + 1024 /*alignment slack*/;
 };
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, int ESZ>
 __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParams p) {
   using L = UmmaSmem<NT, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -199,7 +214,7 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
     const int chunk = tid & 7;
     const int rbase = tid >> 3;
     const uint32_t sw_chunk = (uint32_t)((chunk ^ (rbase & 7)) << 4);
-    const uint32_t cin8 = (uint32_t)(g.Cin >> 3);
+    const uint32_t cin8 = (uint32_t)((g.Cin * ESZ) >> 4);  // 16-byte chunks per pixel
     // my row for the address computation: rbase + 16 * chunk
     int my_yb, my_xb;
     uint32_t my_base;
@@ -223,7 +238,7 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
       my_xb = xo * g.stride - g.pad_l;
       my_base = (uint32_t)b * p.x_bstride8;
     }
-    const int64_t w_kb_stride = (int64_t)g.Cout * 64;  // elements per (tap, slab) filter block
+    const int64_t w_kb_stride = (int64_t)g.Cout * 128;  // BYTES per (tap, slab) filter block
     const int b_chunks = n_valid * 8;                  // 16-byte chunks of the B tile
     const unsigned grp = 0xFFu << (lane & 24);         // the 8 lanes that share my rows
     uint32_t soff[8];                                  // source offset in 16-byte units, 0xFFFFFFFF = zero fill
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
           const void* src = ok ? (const void*)(xsrc + soff[i]) : (const void*)p.x;
           ptx::cp_async16(a_dst + (uint32_t)((rbase + 16 * i) * 128) + sw_chunk, src, ok ? 16u : 0u);
         }
-        const int4* wsrc = reinterpret_cast<const int4*>(p.w + (int64_t)issued * w_kb_stride + (int64_t)n0 * 64);
+        const int4* wsrc = reinterpret_cast<const int4*>(reinterpret_cast<const uint8_t*>(p.w) + (int64_t)issued * w_kb_stride + (int64_t)n0 * 128);
         for (int q = tid; q < b_chunks; q += 128) ptx::cp_async16(b_dst + (uint32_t)q * 16u, wsrc + q, 16u);
         // completion is signalled asynchronously: no thread ever blocks on its own copies, so up to STAGES K blocks
         // of loads are in flight per thread
@@ -324,7 +339,7 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
       }
       if (p.act != LNS_ACT_NONE) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act_fast(v[j], p.act);
+        for (int j = 0; j < 16; ++j) v[j] = ESZ == 2 ? apply_act_fast(v[j], p.act) : apply_act(v[j], p.act);
       }
       if (p.residual) {
 #pragma unroll
@@ -344,6 +359,10 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       } else {
+        if (p.y_dtype == LNS_TF32) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
+        }
         float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yrow + c0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -354,7 +373,7 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
   } else {
     // ============================== MMA issuer (warp 4, one thread) ==============================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16((uint32_t)n_valid);
+      const uint32_t idesc = ESZ == 2 ? make_idesc_bf16((uint32_t)n_valid) : make_idesc_tf32((uint32_t)n_valid);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         ptx::mbar_wait(full_bar(s), (kb / STAGES) & 1);
@@ -366,7 +385,10 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          ptx::umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          if (ESZ == 2)
+            ptx::umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          else
+            ptx::umma_tf32(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
         }
         ptx::umma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
       }
@@ -382,10 +404,10 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
   }
 }
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, int ESZ>
 static int launch_umma(const UmmaParams& p, int Cout, cudaStream_t stream) {
   using L = UmmaSmem<NT, STAGES>;
-  auto kern = conv_umma_kernel<NT, STAGES>;
+  auto kern = conv_umma_kernel<NT, STAGES, ESZ>;
   static bool once = false;  // per template instance (one process per GPU; never repeated under graph capture)
   if (!once) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -401,10 +423,13 @@ static int launch_umma(const UmmaParams& p, int Cout, cudaStream_t stream) {
 }
 
 int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
-  LNS_REQUIRE(d->w_format == LNS_W_UMMA_BF16, "lns_conv2d(umma): weights must be packed as LNS_W_UMMA_BF16");
-  LNS_REQUIRE(d->x_dtype == LNS_BF16 && d->x_layout == LNS_NHWC, "lns_conv2d(umma): input must be NHWC bf16");
+  const bool tf32 = d->w_format == LNS_W_UMMA_TF32;
+  const int esz = tf32 ? 4 : 2, kblk = 128 / esz;  // channels per 128-byte K block
+  LNS_REQUIRE(d->w_format == LNS_W_UMMA_BF16 || tf32, "lns_conv2d(umma): weights must be packed as LNS_W_UMMA_BF16 / _TF32");
+  LNS_REQUIRE(d->x_layout == LNS_NHWC && (tf32 ? d->x_dtype != LNS_BF16 : d->x_dtype == LNS_BF16),
+              "lns_conv2d(umma): input must be NHWC bf16 (bf16 filter) or NHWC fp32/tf32 (tf32 filter)");
   LNS_REQUIRE(d->y_layout == LNS_NHWC, "lns_conv2d(umma): output must be NHWC");
-  LNS_REQUIRE(d->Cin % 64 == 0 && d->Cout % 16 == 0, "lns_conv2d(umma): needs Cin%%64==0 and Cout%%16==0 (got %d,%d)",
+  LNS_REQUIRE(d->Cin % kblk == 0 && d->Cout % 16 == 0, "lns_conv2d(umma): needs Cin%%%d==0 and Cout%%16==0 (got %d,%d)", kblk,
               d->Cin, d->Cout);
   LNS_REQUIRE(d->pro_scale == nullptr && d->pro_act == LNS_ACT_NONE,
               "lns_conv2d(umma): prologue affine is not fused in this engine; apply lns_affine_act first");
@@ -419,20 +444,20 @@ int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
   int64_t M = (int64_t)d->B * d->Hout * d->Wout;
   LNS_REQUIRE(M < (1ll << 31), "lns_conv2d(umma): too many output pixels");
   int64_t x_elems = (int64_t)(d->B - 1) * d->x_bstride + (int64_t)d->Hin * d->Win * d->Cin;
-  LNS_REQUIRE((x_elems >> 3) < 0xFFFFFFFFll, "lns_conv2d(umma): input too large for 32-bit chunk offsets");
+  LNS_REQUIRE(((x_elems * esz) >> 4) < 0xFFFFFFFFll, "lns_conv2d(umma): input too large for 32-bit chunk offsets");
 
   UmmaParams p;
   p.g = make_geom(d);
-  p.x = reinterpret_cast<const __nv_bfloat16*>(d->x);
-  p.w = reinterpret_cast<const __nv_bfloat16*>(d->w);
+  p.x = d->x;
+  p.w = d->w;
   p.bias = d->bias; p.sample_bias = d->sample_bias;
   p.act = d->act;
   p.pre_add = d->pre_add; p.pre_add_dtype = d->pre_add_dtype; p.pre_add_bstride = d->pre_add_bstride;
   p.residual = d->residual; p.res_dtype = d->res_dtype; p.res_bstride = d->res_bstride;
   p.y = d->y; p.y_dtype = d->y_dtype;
   p.M = (int)M;
-  p.slabs = d->Cin / 64;
-  p.x_bstride8 = (uint32_t)(d->x_bstride >> 3);
+  p.slabs = d->Cin / kblk;
+  p.x_bstride8 = (uint32_t)((d->x_bstride * esz) >> 4);
   p.resize = (d->Hv == d->Hin && d->Wv == d->Win) ? 0 : ((d->Hv == 2 * d->Hin && d->Wv == 2 * d->Win) ? 1 : 2);
   p.inv_wout = 1.0f / (float)d->Wout; p.inv_hout = 1.0f / (float)d->Hout;
   p.inv_hv = 1.0f / (float)d->Hv; p.inv_wv = 1.0f / (float)d->Wv;
@@ -443,9 +468,14 @@ int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
               "lns_conv2d(umma): padding/dilation larger than the grid is not supported");
   LNS_REQUIRE((int64_t)d->Hv * d->Hin < (1 << 21) && (int64_t)d->Wv * d->Win < (1 << 21) && d->Hout < (1 << 20) &&
                   d->Wout < (1 << 20), "lns_conv2d(umma): spatial size too large");
-  if (d->Cout <= 64) return launch_umma<64, 4>(p, d->Cout, stream);
-  if (d->Cout <= 128) return launch_umma<128, 3>(p, d->Cout, stream);
-  return launch_umma<256, 3>(p, d->Cout, stream);
+  if (tf32) {
+    if (d->Cout <= 64) return launch_umma<64, 4, 4>(p, d->Cout, stream);
+    if (d->Cout <= 128) return launch_umma<128, 3, 4>(p, d->Cout, stream);
+    return launch_umma<256, 3, 4>(p, d->Cout, stream);
+  }
+  if (d->Cout <= 64) return launch_umma<64, 4, 2>(p, d->Cout, stream);
+  if (d->Cout <= 128) return launch_umma<128, 3, 2>(p, d->Cout, stream);
+  return launch_umma<256, 3, 2>(p, d->Cout, stream);
 }
 
 }  // namespace lns

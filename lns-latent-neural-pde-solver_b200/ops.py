@@ -11,11 +11,12 @@ import torch
 from . import _C
 from ._C import ConvDesc, LnsError, check
 
-F32, BF16 = 0, 1
+F32, BF16, TF32_CODE = 0, 1, 2
+TF32 = "tf32"  # storage sentinel: fp32 words holding TF32-rounded values (LNS_TF32); accepted wherever a dtype is
 NHWC, NCHW = 0, 1
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAD_ZEROS, PAD_CIRCULAR = 0, 1
-W_SIMT_F32, W_UMMA_BF16 = 0, 1
+W_SIMT_F32, W_UMMA_BF16, W_UMMA_TF32 = 0, 1, 2
 ENGINE_SIMT, ENGINE_UMMA, ENGINE_HALO = 0, 1, 2
 
 _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
@@ -63,9 +64,11 @@ def get_precision():
 
 def set_precision(p):
     """'bf16': bf16 activations, tcgen05 tensor-core GEMMs with fp32 accumulation (the fast path).
+    'tf32': fp32 storage rounded to TF32 at every write, tcgen05.mma.kind::tf32 GEMMs with fp32 accumulation (the
+            tensor-core path that meets the 2e-3 per-step bound; half the MMA rate and twice the bytes of bf16).
     'fp32': fp32 activations and CUDA-core fp32 FMA GEMMs (the validation path, <=1e-5 vs the reference)."""
-    if p not in ("bf16", "fp32"):
-        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if p not in ("bf16", "fp32", "tf32"):
+        raise ValueError("precision must be 'bf16', 'tf32' or 'fp32'")
     _state.precision = p
 
 
@@ -80,7 +83,9 @@ def precision(p):
 
 
 def act_dtype():
-    return torch.bfloat16 if _state.precision == "bf16" else torch.float32
+    if _state.precision == "bf16":
+        return torch.bfloat16
+    return TF32 if _state.precision == "tf32" else torch.float32
 
 
 def launch_count():
@@ -106,16 +111,23 @@ class Act:
     """A [B,H,W,C] activation living in `t` (element (0,0,0,0) at t.data_ptr()); channel-last unless layout=NCHW.
     `bstride` is the distance between samples in elements (lets the K latent states of a rollout interleave as
     [B,K,...] without copies)."""
-    __slots__ = ("t", "B", "H", "W", "C", "bstride", "layout")
+    __slots__ = ("t", "B", "H", "W", "C", "bstride", "layout", "tf32")
 
-    def __init__(self, t, B, H, W, C, bstride=None, layout=NHWC):
+    def __init__(self, t, B, H, W, C, bstride=None, layout=NHWC, tf32=False):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
         self.bstride = H * W * C if bstride is None else bstride
         self.layout = layout
+        self.tf32 = tf32  # fp32 words holding TF32-rounded values: kernels round to nearest TF32 when they write it
 
     @property
     def dtype(self):
-        return dt_code(self.t.dtype)
+        """LNS_* storage code passed to the library"""
+        return TF32_CODE if self.tf32 else dt_code(self.t.dtype)
+
+    @property
+    def adtype(self):
+        """what to pass as `dtype=` to get another Act of the same storage type"""
+        return TF32 if self.tf32 else self.t.dtype
 
     @property
     def contiguous(self):
@@ -123,10 +135,12 @@ class Act:
 
     @staticmethod
     def empty(B, H, W, C, dtype, device):
-        return Act(torch.empty(B * H * W * C, dtype=dtype, device=device), B, H, W, C)
+        tf = isinstance(dtype, str) and dtype == TF32
+        return Act(torch.empty(B * H * W * C, dtype=torch.float32 if tf else dtype, device=device), B, H, W, C, tf32=tf)
 
     def like(self, C=None, dtype=None, H=None, W=None):
-        return Act.empty(self.B, H or self.H, W or self.W, C or self.C, dtype or self.t.dtype, self.t.device)
+        return Act.empty(self.B, H or self.H, W or self.W, C or self.C, dtype if dtype is not None else self.adtype,
+                         self.t.device)
 
     @staticmethod
     def from_nchw(x):
@@ -281,8 +295,13 @@ def composed_filter(first, second):
 
 # ---- conv ---------------------------------------------------------------------------------------------------
 def _umma_ok(x, Cin, Cout, y_layout):
-    return (_state.precision == "bf16" and x.layout == NHWC and x.t.dtype == torch.bfloat16 and Cin % 64 == 0
-            and Cout % 16 == 0 and y_layout == NHWC and x.bstride % 8 == 0)
+    if x.layout != NHWC or y_layout != NHWC or Cout % 16 != 0 or x.bstride % 8 != 0:
+        return False
+    if _state.precision == "bf16":
+        return x.t.dtype == torch.bfloat16 and Cin % 64 == 0
+    if _state.precision == "tf32":  # fp32 words are read as TF32 by tcgen05.mma.kind::tf32
+        return x.t.dtype == torch.float32 and Cin % 32 == 0
+    return False
 
 
 def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, PAD_ZEROS), virt=None, use_bias=True,
@@ -305,7 +324,8 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
         return _pointwise_proj(x, filt, use_bias, pro, out)
     if engine is None:
         engine = ENGINE_UMMA if _umma_ok(x, Cin, Cout, out_layout) else ENGINE_SIMT
-        if (engine == ENGINE_UMMA and KH == 3 and KW == 3 and stride == 1 and Cin == 64 and Cout in (64, 128)
+        if (engine == ENGINE_UMMA and x.t.dtype == torch.bfloat16 and KH == 3 and KW == 3 and stride == 1 and Cin == 64
+                and Cout in (64, 128)
                 and pt == pb == pl == pr == dil and 1 <= dil <= 3 and Hout >= 16 and Wout >= 8):
             engine = ENGINE_HALO  # full-resolution layers: shared-memory halo + resident filter
     if isinstance(pro, LazyNorm):
@@ -323,7 +343,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
         if out_dtype is None:
             out_dtype = torch.float32 if out_layout == NCHW else act_dtype()
         if out_layout == NCHW:
-            out = Act(torch.empty(x.B * Cout * Hout * Wout, dtype=out_dtype, device=x.t.device), x.B, Hout, Wout,
+            out = Act(torch.empty(x.B * Cout * Hout * Wout, dtype=torch.float32, device=x.t.device), x.B, Hout, Wout,
                       Cout, layout=NCHW)
         else:
             out = Act.empty(x.B, Hout, Wout, Cout, out_dtype, x.t.device)
@@ -336,7 +356,9 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     d.Hv, d.Wv = Hv, Wv
     d.KH, d.KW, d.stride, d.dil, d.pad_t, d.pad_l = KH, KW, stride, dil, pt, pl
     d.pad_mode_h, d.pad_mode_w = pad_mode
-    fmt = W_UMMA_BF16 if engine in (ENGINE_UMMA, ENGINE_HALO) else W_SIMT_F32
+    fmt = W_SIMT_F32
+    if engine in (ENGINE_UMMA, ENGINE_HALO):
+        fmt = W_UMMA_BF16 if x.t.dtype == torch.bfloat16 else W_UMMA_TF32
     wbuf = filt.get(fmt)
     d.w, d.w_format, d.engine = wbuf.data_ptr(), fmt, engine
     bias = filt.bias() if use_bias else None
@@ -445,7 +467,7 @@ class LazyNorm:
         x = self.x
         if (self._affine is None and x.layout == NHWC
                 and _C.lib().lns_group_norm_act_supported(x.H, x.W, x.C) and x.bstride % 4 == 0):
-            out = x.like(dtype=out_dtype or x.t.dtype)
+            out = x.like(dtype=out_dtype)
             g = self.gamma.detach().float().contiguous() if self.gamma is not None else None
             b = self.beta.detach().float().contiguous() if self.beta is not None else None
             tok = _mark(f"gn_act_fused C{x.C} @{x.H}x{x.W}")
@@ -462,7 +484,7 @@ class LazyNorm:
 
 def affine_act(x, scale, shift, act=ACT_NONE, out_dtype=None):
     """y = act(x*scale[b,c] + shift[b,c]) as a new contiguous Act."""
-    out = x.like(dtype=out_dtype or x.t.dtype)
+    out = x.like(dtype=out_dtype)
     tok = _mark(f"affine_act C{x.C} @{x.H}x{x.W}")
     rc = _C.lib().lns_affine_act(_ptr(x.t), x.dtype, x.bstride, x.B, x.H * x.W, x.C, _ptr(scale), _ptr(shift), act,
                                  _ptr(out.t), out.dtype, out.bstride, _stream())
@@ -475,7 +497,7 @@ def affine_act(x, scale, shift, act=ACT_NONE, out_dtype=None):
 def layernorm(x, gamma, beta, eps, pe=None, out_dtype=None):
     """LayerNorm over C per pixel/token (+ pe[token]) -> new Act."""
     assert x.contiguous and x.layout == NHWC
-    out = x.like(dtype=out_dtype or x.t.dtype)
+    out = x.like(dtype=out_dtype)
     g = gamma.detach().float().contiguous() if gamma is not None else None
     b = beta.detach().float().contiguous() if beta is not None else None
     tok = _mark(f"layernorm")
@@ -501,7 +523,7 @@ def channel_gate(x, gate):
 def attention(qkv, heads, dh, scale, out_dtype=None):
     """qkv: Act [B,H,W,3*heads*dh] (tokens = pixels) -> Act [B,H,W,heads*dh]"""
     assert qkv.contiguous and qkv.C == 3 * heads * dh
-    out = qkv.like(C=heads * dh, dtype=out_dtype or qkv.t.dtype)
+    out = qkv.like(C=heads * dh, dtype=out_dtype)
     tok = _mark(f"attention")
     rc = _C.lib().lns_attention(_ptr(qkv.t), qkv.dtype, qkv.B, qkv.H * qkv.W, heads, dh, float(scale), _ptr(out.t),
                                 out.dtype, _stream())
@@ -539,7 +561,7 @@ def lowrank_kernel(qk, heads, d, cos_tab, sin_tab, scaling=1.0):
 
 def axial_contract(u, K, heads, axis, out_dtype=None):
     assert u.contiguous and u.layout == NHWC and u.C % heads == 0
-    out = u.like(dtype=out_dtype or u.t.dtype)
+    out = u.like(dtype=out_dtype)
     tok = _mark(f"axial C{u.C} @{u.H}x{u.W}")
     rc = _C.lib().lns_axial_contract(_ptr(u.t), u.dtype, u.B, u.H, u.W, heads, u.C // heads, _ptr(K), axis,
                                      _ptr(out.t), out.dtype, _stream())

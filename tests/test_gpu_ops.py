@@ -512,3 +512,28 @@ def test_group_norm_act_fused_small(shape, groups):
     assert torch.equal(fused.t, two.t)
     ref = F.gelu(F.group_norm(x.bfloat16().double(), groups, gamma.cpu().double(), beta.cpu().double(), 1e-5))
     assert relerr(act_to_nchw(fused), ref) < 4e-3
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_umma_tf32(case):
+    """tcgen05.mma.kind::tf32 engine vs fp64 conv of the SAME TF32-rounded operands (fp32 accumulation order only)"""
+    ops = ops_mod()
+    B, Cin, Cout, H, W, k, stride, dil, pad, modes, virt = case
+    x, w, b = _conv_case(case, seed=2)
+
+    def rt(t):  # round to nearest TF32 (10-bit mantissa), ties away from zero like cvt.rna
+        i = t.contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    ref = ref_conv(rt(x), rt(w), b, stride, dil, pad, modes, virt)
+    h = Holder(w, b)
+    with ops.precision("tf32"):
+        a = act_from(rt(x))
+        a.tf32 = True
+        y = ops.conv2d(a, ops.PackedFilter.of(h.weight, h.bias), stride=stride, dil=dil, pad=pad, pad_mode=modes,
+                       virt=virt, engine=ops.ENGINE_UMMA, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert relerr(act_to_nchw(y), ref) < 5e-6
+    with ops.precision("tf32"):
+        y2 = ops.conv2d(a, ops.PackedFilter.of(h.weight, h.bias), stride=stride, dil=dil, pad=pad, pad_mode=modes, virt=virt)
+    assert y2.tf32 and y2.t.dtype == torch.float32
+    assert torch.equal(act_to_nchw(y2), rt(act_to_nchw(y)))  # stored values are the TF32 roundings

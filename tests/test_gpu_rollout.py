@@ -120,7 +120,32 @@ def test_predict_bf16_vs_oracle(name):
     assert e_enc < 3e-2 and e_prop < 3e-2 and e_dec < 5e-2 and max(drift) < 1e-1
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", CONFIGS)
+def test_stages_tf32_teacher_forced(name):
+    """tf32 mode (tcgen05.mma.kind::tf32, TF32-rounded fp32 storage): the tensor-core path that meets the north_star's
+    per-step bound: propagator step <= 2e-3; encode / decode are reported (1.3e-3 / 2.1e-3 expected)."""
+    ops = ops_mod()
+    cfg, model, sd = build(name)
+    sd64 = O.to_dtype(sd, torch.float64)
+    x, param = O.make_inputs(cfg, 3, seed=15)
+    ae = O.ae_name(cfg)
+    z_ref = O.encode(sd64, cfg, x.double(), ae)
+    cond = O.cond_embedding(sd64, cfg, param.double(), torch.float64) if param is not None else None
+    z1_ref = O.propagator_step(sd64, cfg, z_ref, cond)
+    y_ref = O.decode(sd64, cfg, z1_ref, ae)
+    with torch.no_grad(), ops.precision("tf32"):
+        z = model.autoencoder.encode(x.to(DEV))
+        z1 = model.propagator(z_ref.float().to(DEV)) if param is None else \
+            model.propagator(z_ref.float().to(DEV), param.to(DEV))
+        y = model.autoencoder.decode(z1_ref.float().to(DEV))
+    e_enc = O.rel_l2(z.cpu(), z_ref).max().item()
+    e_prop = O.rel_l2(z1.cpu(), z1_ref).max().item()
+    e_dec = O.rel_l2(y.cpu(), y_ref).max().item()
+    print(f"\n[tf32 {name}] teacher-forced: encode {e_enc:.2e}  propagator-step {e_prop:.2e}  decode {e_dec:.2e}")
+    assert e_prop < 2e-3 and e_enc < 4e-3 and e_dec < 4e-3
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "tf32"])
 def test_graph_replay_equals_eager_and_is_batch_independent(prec):
     """(1) the CUDA-graph replay returns exactly what the eager launch sequence returns; (2) a trajectory's result does
     not depend on which batch it is in -- the property that makes trajectory sharding across GPUs exact."""
