@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--workload", default="ns2d", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="trajectories per GPU (default: workload's)")
     ap.add_argument("--rollout-steps", type=int, default=None)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the final all-gather of fields for N > 1")
     ap.add_argument("--decode-chunk", type=int, default=None, help="samples per decode launch group (default: engine's)")
@@ -129,7 +129,7 @@ class ClockSampler:
 
 
 # ---- dominant-kernel roofline ---------------------------------------------------------------------------------------------
-def conv_roofline(torch, ops, device, peaks, workload):
+def conv_roofline(torch, ops, device, peaks, workload, precision="bf16"):
     """Time the dominant kernel alone (tcgen05 implicit-GEMM 3x3 conv at the workload's largest layer) with CUDA events
     on the launching stream; operands are larger than L2 so every launch streams from HBM."""
     import math
@@ -137,12 +137,13 @@ def conv_roofline(torch, ops, device, peaks, workload):
               "twophase": (61, 121, 64, 64, (0, 0)), "twophase_cond": (61, 121, 64, 64, (0, 0))}
     H, W, Cin, Cout, modes = shapes[workload]
     nb = max(8, (768 << 20) // (H * W * Cin * 2))  # ~768 MB of bf16 input: >> 126 MB L2
-    x = ops.Act(torch.randn(nb * H * W * Cin, device=device).bfloat16(), nb, H, W, Cin)
+    dt16 = torch.float16 if precision == "fp16" else torch.bfloat16
+    x = ops.Act(torch.randn(nb * H * W * Cin, device=device).to(dt16), nb, H, W, Cin)
     wt = torch.nn.Parameter(torch.randn(Cout, Cin, 3, 3, device=device) / math.sqrt(9 * Cin))
     bs = torch.nn.Parameter(torch.zeros(Cout, device=device))
     filt = ops.PackedFilter.of(wt, bs)
-    out = ops.Act.empty(nb, H, W, Cout, torch.bfloat16, device)
-    with ops.precision("bf16"):
+    out = ops.Act.empty(nb, H, W, Cout, dt16, device)
+    with ops.precision(precision):
         for _ in range(3):
             ops.conv2d(x, filt, pad=(1, 1, 1, 1), pad_mode=modes, out=out)
         torch.cuda.synchronize()
@@ -291,13 +292,13 @@ def main():
     d2h = out_host.numel() * 4
 
     if rank == 0:
-        roof = conv_roofline(torch, ops, device, peaks, args.workload) if args.precision == "bf16" else None
+        roof = conv_roofline(torch, ops, device, peaks, args.workload, args.precision) if args.precision in ("bf16", "fp16") else None
         tflops = value * gflop_per_ts / 1e3
         line = {
             "metric": "latent rollout trajectory-steps/sec", "value": round(value, 1), "unit": "trajectory-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": label, "rollout_steps": R, "trajectories_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"trajectory-sharded x{world}" + (", final all-gather of fields" if gather else ""),
                        "l2": "per-step working set (activations) is far larger than the 126 MB L2; no explicit flush",

@@ -16,7 +16,7 @@
  *  - return value: 0 = OK, negative = error (LNS_E_*); text via lns_last_error().  An unsupported
  *    shape / dtype is an error, never a silent fallback.
  *  - activations are NHWC ("channel-last": [B][H][W][C], C contiguous) with an explicit batch stride in
- *    ELEMENTS; dtype LNS_F32 or LNS_BF16.  NCHW fp32 exists only at the two ends of the path (the
+ *    ELEMENTS; dtype LNS_F32, LNS_TF32, LNS_BF16 or LNS_F16.  NCHW fp32 exists only at the two ends of the path (the
  *    reference's tensors are NCHW fp32, modules/autoencoder2d.py:69-72).
  */
 #ifndef LNS_B200_H
@@ -38,6 +38,10 @@ enum {
   LNS_BF16 = 1,
   LNS_TF32 = 2 /* stored as fp32, every value rounded to nearest TF32 (10-bit mantissa) when written: the storage type of
                   the tf32 precision mode, whose convolutions run on tcgen05.mma.kind::tf32 (which ignores the low 13 bits) */
+  ,
+  LNS_F16 = 3 /* IEEE half (11-bit significand): the storage type of the fp16 precision mode -- the same tensor-core kernels
+                 and HBM bytes as LNS_BF16 (tcgen05.mma.kind::f16 takes either format) with TF32-class rounding error;
+                 conversions saturate to +-65504 */
 };
 enum { LNS_NHWC = 0, LNS_NCHW = 1 };
 enum { LNS_ACT_NONE = 0, LNS_ACT_SILU = 1, LNS_ACT_GELU = 2 };
@@ -47,8 +51,9 @@ enum {
   LNS_W_SIMT_F32 = 0, /* [tap][Cin][Cout] fp32 (CUDA-core validation path, any Cin/Cout)      */
   LNS_W_UMMA_BF16 = 1, /* [tap][Cin/64][Cout][64] bf16, K-major 128B-swizzled smem image for     */
                        /* tcgen05.mma (needs Cin % 64 == 0 and Cout % 16 == 0)                   */
-  LNS_W_UMMA_TF32 = 2  /* [tap][Cin/32][Cout][32] fp32 rounded to TF32, same swizzled image, for   */
+  LNS_W_UMMA_TF32 = 2, /* [tap][Cin/32][Cout][32] fp32 rounded to TF32, same swizzled image, for   */
                        /* tcgen05.mma.kind::tf32 (needs Cin % 32 == 0 and Cout % 16 == 0)         */
+  LNS_W_UMMA_F16 = 3   /* LNS_W_UMMA_BF16's layout with IEEE-half elements (for LNS_F16 activations) */
 };
 /* which engine executes lns_conv2d */
 enum {
@@ -190,7 +195,7 @@ int lns_axial_contract(const void* u, int dtype, int B, int H, int W, int heads,
 /* Fused FABlock2D core for the bf16 path (one CTA per (sample, head); u_phi never leaves shared memory):
  *   in_proj (GroupNorm(1) folded into a per-sample filter/bias) -> contraction over H with Kx -> contraction over W with
  *   Ky -> InstanceNorm2d (eps, no affine) -> out [B][H][W][heads*64] bf16, ready for to_out's 1x1 convs.
- * u: NHWC bf16 [B][H][W][64] (the block's RAW input); gn_scale/gn_shift [B][64] from lns_group_norm_affine(G=1);
+ * u: NHWC [B][H][W][64], dtype LNS_BF16 or LNS_F16 (the block's RAW input; out has the same dtype); gn_scale/gn_shift [B][64] from lns_group_norm_affine(G=1);
  * w_in_proj: the nn.Conv2d weight [heads*64][64] fp32 as stored; Kx [B][heads][H][H], Ky [B][heads][W][W] fp32.
  * modules/factorized_attention.py:146-158 + the InstanceNorm2d of :139.  lns_fablock_core_supported() tells whether the
  * shape fits (H, W <= 48 and H*W*144 B + ~50 KB of shared memory); otherwise use the unfused entry points above. */
@@ -201,7 +206,7 @@ int lns_fablock_core_supported(int H, int W, int dim, int dim_head);
 int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, int64_t bstride, float eps,
                         const float* gamma, const float* beta, float* scale, float* shift, float* pooled_x,
                         float* pooled_y, void* stream);
-int lns_fablock_core(const void* u, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
+int lns_fablock_core(const void* u, int dtype, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
                      const float* w_in_proj, const float* Kx, const float* Ky, float eps, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -45,7 +45,7 @@ int validate_conv(const LnsConvDesc* d) {
   LNS_REQUIRE(d->KH >= 1 && d->KH <= 7 && d->KW >= 1 && d->KW <= 7, "lns_conv2d: unsupported filter %dx%d", d->KH,
               d->KW);
   LNS_REQUIRE(d->stride >= 1 && d->dil >= 1, "lns_conv2d: bad stride/dilation");
-  LNS_REQUIRE(d->x_dtype >= LNS_F32 && d->x_dtype <= LNS_TF32 && d->y_dtype >= LNS_F32 && d->y_dtype <= LNS_TF32,
+  LNS_REQUIRE(d->x_dtype >= LNS_F32 && d->x_dtype <= LNS_F16 && d->y_dtype >= LNS_F32 && d->y_dtype <= LNS_F16,
               "lns_conv2d: bad dtype");
   // every output pixel's taps must stay inside the padded virtual input
   int64_t ymax = (int64_t)(d->Hout - 1) * d->stride + (int64_t)(d->KH - 1) * d->dil - d->pad_t;
@@ -54,8 +54,8 @@ int validate_conv(const LnsConvDesc* d) {
               "lns_conv2d: output height %d inconsistent with input", d->Hout);
   LNS_REQUIRE(d->pad_mode_w == LNS_PAD_CIRCULAR || xmax < (int64_t)d->Wv + d->Wv,
               "lns_conv2d: output width %d inconsistent with input", d->Wout);
-  if (d->x_layout == LNS_NCHW) LNS_REQUIRE(d->x_dtype != LNS_BF16, "lns_conv2d: NCHW input must be fp32");
-  if (d->y_layout == LNS_NCHW) LNS_REQUIRE(d->y_dtype != LNS_BF16, "lns_conv2d: NCHW output must be fp32");
+  if (d->x_layout == LNS_NCHW) LNS_REQUIRE(!lns::is_h16_host(d->x_dtype), "lns_conv2d: NCHW input must be fp32");
+  if (d->y_layout == LNS_NCHW) LNS_REQUIRE(!lns::is_h16_host(d->y_dtype), "lns_conv2d: NCHW output must be fp32");
   return LNS_OK;
 }
 

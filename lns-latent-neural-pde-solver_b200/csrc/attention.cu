@@ -169,13 +169,22 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_
 __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+// F16 = false: bf16 operands, true: IEEE-half operands (same rate, same fragment layout)
+template <bool F16>
+__device__ __forceinline__ void mma_h16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  if (F16)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(128) axial_contract_mma_kernel(const __nv_bfloat16* __restrict__ u, int H, int W, int heads,
                                                                   const float* __restrict__ Kmat, int axis,
                                                                   __nv_bfloat16* __restrict__ out) {
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(128) axial_contract_mma_kernel(const __nv_bflo
   for (int e = tid; e < n16 * n16; e += 128) {
     int i = e / n16, j = e - i * n16;
     float v = (i < n && j < n) ? __ldg(Kg + i * n + j) : 0.f;
-    K_s[i * kstride + j] = __float2bfloat16_rn(v);
+    reinterpret_cast<uint16_t*>(K_s)[i * kstride + j] = to_h16<F16>(v);
   }
   // slabs: 8 x 16-byte chunks per (line, j) row
   const int nl = min(kAxLines, lines - line0);
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(128) axial_contract_mma_kernel(const __nv_bflo
         for (int nt = 0; nt < 8; ++nt) {
           uint32_t b0, b1;
           ldmatrix_x2_trans((uint32_t)__cvta_generic_to_shared(sl + (size_t)(kt * 16 + (lane & 15)) * kAxSlabStride + nt * 8), b0, b1);
-          mma_bf16_16816(acc[nt], a, b0, b1);
+          mma_h16_16816<F16>(acc[nt], a, b0, b1);
         }
       }
       // fragment -> staging tile [16][64] (bf16)
@@ -244,8 +253,8 @@ __global__ void __launch_bounds__(128) axial_contract_mma_kernel(const __nv_bflo
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         int r = lane >> 2, c = nt * 8 + (lane & 3) * 2;
-        *reinterpret_cast<__nv_bfloat162*>(my_stage + r * kAxSlabStride + c) = __floats2bfloat162_rn(acc[nt][0], acc[nt][1]);
-        *reinterpret_cast<__nv_bfloat162*>(my_stage + (r + 8) * kAxSlabStride + c) = __floats2bfloat162_rn(acc[nt][2], acc[nt][3]);
+        *reinterpret_cast<uint32_t*>(my_stage + r * kAxSlabStride + c) = pack2_h16<F16>(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<uint32_t*>(my_stage + (r + 8) * kAxSlabStride + c) = pack2_h16<F16>(acc[nt][2], acc[nt][3]);
       }
       __syncwarp();
       // 4 rows per pass, 8 lanes x 16 bytes per row
@@ -271,6 +280,7 @@ __global__ void __launch_bounds__(128) axial_contract_mma_kernel(const __nv_bflo
 // re-packed as the A operand of the second GEMM).
 constexpr int kAttStride = 72;
 
+template <bool F16>
 __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int n, int heads,
                                                              float scale_log2e, __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t smraw[];
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
           // K rows are keys, columns d: the (non-transposed) 8x8 tiles are exactly the col-major B fragments
           asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1)
                        : "r"((uint32_t)__cvta_generic_to_shared(K_s + (size_t)(kb + nt * 8 + (lane & 7)) * kAttStride + ks * 16 + ((lane >> 3) & 1) * 8)));
-          mma_bf16_16816(sacc[nt], qa[ks], b0, b1);
+          mma_h16_16816<F16>(sacc[nt], qa[ks], b0, b1);
         }
       }
       // scale, mask padded keys, block max
@@ -365,16 +375,15 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         uint32_t pa[4];
-        __nv_bfloat162 h;
-        h = __floats2bfloat162_rn(sacc[2 * kk][0], sacc[2 * kk][1]); pa[0] = *reinterpret_cast<uint32_t*>(&h);
-        h = __floats2bfloat162_rn(sacc[2 * kk][2], sacc[2 * kk][3]); pa[1] = *reinterpret_cast<uint32_t*>(&h);
-        h = __floats2bfloat162_rn(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]); pa[2] = *reinterpret_cast<uint32_t*>(&h);
-        h = __floats2bfloat162_rn(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]); pa[3] = *reinterpret_cast<uint32_t*>(&h);
+        pa[0] = pack2_h16<F16>(sacc[2 * kk][0], sacc[2 * kk][1]);
+        pa[1] = pack2_h16<F16>(sacc[2 * kk][2], sacc[2 * kk][3]);
+        pa[2] = pack2_h16<F16>(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+        pa[3] = pack2_h16<F16>(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
           uint32_t b0, b1;
           ldmatrix_x2_trans((uint32_t)__cvta_generic_to_shared(V_s + (size_t)(kb + kk * 16 + (lane & 15)) * kAttStride + nt * 8), b0, b1);
-          mma_bf16_16816(o[nt], pa, b0, b1);
+          mma_h16_16816<F16>(o[nt], pa, b0, b1);
         }
       }
     }
@@ -385,8 +394,8 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       int col = h * 64 + nt * 8 + t * 2;
-      if (r0 < n) *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)b * n + r0) * hd + col) = __floats2bfloat162_rn(o[nt][0] * i0, o[nt][1] * i0);
-      if (r1 < n) *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)b * n + r1) * hd + col) = __floats2bfloat162_rn(o[nt][2] * i1, o[nt][3] * i1);
+      if (r0 < n) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * n + r0) * hd + col) = pack2_h16<F16>(o[nt][0] * i0, o[nt][1] * i0);
+      if (r1 < n) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * n + r1) * hd + col) = pack2_h16<F16>(o[nt][2] * i1, o[nt][3] * i1);
     }
   }
 }
@@ -395,6 +404,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
 // ---- LowRankKernel on tensor cores (bf16 q|k rows) ---------------------------------------------------------------------
 // K[b][h] = rot(q) rot(k)^T  is an n x n x d GEMM per (sample, head) with n <= 96, d = 128.  grid (heads, B), block 128:
 // the rotary embedding is applied while staging q and k (bf16) in shared memory, each warp owns 16-row tiles of K.
+template <bool F16>
 __global__ void __launch_bounds__(128) lowrank_mma_kernel(const __nv_bfloat16* __restrict__ qk, int n, int heads, int d,
                                                            const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                                            float scaling, float* __restrict__ Kout) {
@@ -411,24 +421,24 @@ __global__ void __launch_bounds__(128) lowrank_mma_kernel(const __nv_bfloat16* _
   // rotate pairs (f, f + d/2); 2 consecutive f per work item so that loads / stores are 4 bytes
   for (int e = tid; e < n16 * (half >> 1); e += 128) {
     const int i = e / (half >> 1), f = (e - i * (half >> 1)) * 2;
-    __nv_bfloat162 q1 = __floats2bfloat162_rn(0.f, 0.f), q2 = q1, k1 = q1, k2 = q1;
+    uint32_t q1 = 0u, q2 = 0u, k1 = 0u, k2 = 0u;
     if (i < n) {
       const __nv_bfloat16* r = base + (int64_t)i * row_stride;
-      float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(r + f));
-      float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(r + f + half));
-      float2 b1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(r + hd + f));
-      float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(r + hd + f + half));
+      float2 a1 = unpack2_h16<F16>(*reinterpret_cast<const uint32_t*>(r + f));
+      float2 a2 = unpack2_h16<F16>(*reinterpret_cast<const uint32_t*>(r + f + half));
+      float2 b1 = unpack2_h16<F16>(*reinterpret_cast<const uint32_t*>(r + hd + f));
+      float2 b2 = unpack2_h16<F16>(*reinterpret_cast<const uint32_t*>(r + hd + f + half));
       const float c0 = __ldg(cos_t + i * half + f), c1 = __ldg(cos_t + i * half + f + 1);
       const float s0 = __ldg(sin_t + i * half + f), s1 = __ldg(sin_t + i * half + f + 1);
-      q1 = __floats2bfloat162_rn(a1.x * c0 - a2.x * s0, a1.y * c1 - a2.y * s1);
-      q2 = __floats2bfloat162_rn(a2.x * c0 + a1.x * s0, a2.y * c1 + a1.y * s1);
-      k1 = __floats2bfloat162_rn(b1.x * c0 - b2.x * s0, b1.y * c1 - b2.y * s1);
-      k2 = __floats2bfloat162_rn(b2.x * c0 + b1.x * s0, b2.y * c1 + b1.y * s1);
+      q1 = pack2_h16<F16>(a1.x * c0 - a2.x * s0, a1.y * c1 - a2.y * s1);
+      q2 = pack2_h16<F16>(a2.x * c0 + a1.x * s0, a2.y * c1 + a1.y * s1);
+      k1 = pack2_h16<F16>(b1.x * c0 - b2.x * s0, b1.y * c1 - b2.y * s1);
+      k2 = pack2_h16<F16>(b2.x * c0 + b1.x * s0, b2.y * c1 + b1.y * s1);
     }
-    *reinterpret_cast<__nv_bfloat162*>(q_s + (size_t)i * stride + f) = q1;
-    *reinterpret_cast<__nv_bfloat162*>(q_s + (size_t)i * stride + f + half) = q2;
-    *reinterpret_cast<__nv_bfloat162*>(k_s + (size_t)i * stride + f) = k1;
-    *reinterpret_cast<__nv_bfloat162*>(k_s + (size_t)i * stride + f + half) = k2;
+    *reinterpret_cast<uint32_t*>(q_s + (size_t)i * stride + f) = q1;
+    *reinterpret_cast<uint32_t*>(q_s + (size_t)i * stride + f + half) = q2;
+    *reinterpret_cast<uint32_t*>(k_s + (size_t)i * stride + f) = k1;
+    *reinterpret_cast<uint32_t*>(k_s + (size_t)i * stride + f + half) = k2;
   }
   __syncthreads();
   const int g = lane >> 2, t = lane & 3;
@@ -448,7 +458,7 @@ __global__ void __launch_bounds__(128) lowrank_mma_kernel(const __nv_bfloat16* _
             uint32_t b0, b1;
             asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1)
                          : "r"((uint32_t)__cvta_generic_to_shared(k_s + (size_t)(nb + nt * 8 + (lane & 7)) * stride + ks * 16 + ((lane >> 3) & 1) * 8)));
-            mma_bf16_16816(acc[nt], a, b0, b1);
+            mma_h16_16816<F16>(acc[nt], a, b0, b1);
           }
         }
       }
@@ -473,14 +483,15 @@ int lns_attention(const void* qkv, int dtype, int B, int n, int heads, int dh, f
                   void* stream) {
   LNS_REQUIRE(qkv && out && B > 0 && n > 0 && heads > 0 && dh > 0, "lns_attention: bad arguments");
   LNS_REQUIRE(B <= 65535, "lns_attention: batch %d exceeds grid limit, chunk the call", B);
-  if (dtype == LNS_BF16 && out_dtype == LNS_BF16 && dh == 64) {
+  if (lns::is_h16_host(dtype) && out_dtype == dtype && dh == 64) {
     // tensor-core path (the bf16 rollout)
     int n16 = (n + 15) & ~15, nk = (n + 63) & ~63;
     size_t smem_mma = ((size_t)n16 + 2 * (size_t)nk) * lns::kAttStride * sizeof(__nv_bfloat16);
     if (smem_mma <= 227 * 1024) {
-      { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+      { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); cudaFuncSetAttribute(lns::attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
       dim3 grid(heads, B);
-      lns::attention_mma_kernel<<<grid, 128, smem_mma, reinterpret_cast<cudaStream_t>(stream)>>>(
+      auto kern = dtype == LNS_F16 ? lns::attention_mma_kernel<true> : lns::attention_mma_kernel<false>;
+      kern<<<grid, 128, smem_mma, reinterpret_cast<cudaStream_t>(stream)>>>(
           reinterpret_cast<const __nv_bfloat16*>(qkv), n, heads, scale * 1.4426950408889634f,
           reinterpret_cast<__nv_bfloat16*>(out));
       return lns::check_launch("attention_mma_kernel");
@@ -514,14 +525,15 @@ int lns_lowrank_kernel(const void* qk, int dtype, int B, int n, int heads, int d
   LNS_REQUIRE(qk && K && cos_tab && sin_tab && B > 0 && n > 0 && heads > 0 && d > 0 && d % 2 == 0,
               "lns_lowrank_kernel: bad arguments");
   LNS_REQUIRE(B <= 65535, "lns_lowrank_kernel: batch %d exceeds grid limit, chunk the call", B);
-  if (dtype == LNS_BF16 && d % 16 == 0) {
+  if (lns::is_h16_host(dtype) && d % 16 == 0) {
     // tensor-core path (bf16 q|k from the tcgen05 to_qk GEMM)
     int n16 = (n + 15) & ~15;
     size_t smem_mma = 2 * (size_t)n16 * (d + 8) * sizeof(__nv_bfloat16);
     if (smem_mma <= 227 * 1024) {
-      { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::lowrank_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+      { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::lowrank_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); cudaFuncSetAttribute(lns::lowrank_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
       dim3 grid(heads, B);
-      lns::lowrank_mma_kernel<<<grid, 128, smem_mma, reinterpret_cast<cudaStream_t>(stream)>>>(
+      auto kern = dtype == LNS_F16 ? lns::lowrank_mma_kernel<true> : lns::lowrank_mma_kernel<false>;
+      kern<<<grid, 128, smem_mma, reinterpret_cast<cudaStream_t>(stream)>>>(
           reinterpret_cast<const __nv_bfloat16*>(qk), n, heads, d, cos_tab, sin_tab, scaling, K);
       return lns::check_launch("lowrank_mma_kernel");
     }
@@ -543,16 +555,17 @@ int lns_axial_contract(const void* u, int dtype, int B, int H, int W, int heads,
   LNS_REQUIRE(B <= 65535, "lns_axial_contract: batch %d exceeds grid limit, chunk the call", B);
   int n = axis == 0 ? H : W;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == LNS_BF16 && out_dtype == LNS_BF16 && ch == 64) {
+  if (lns::is_h16_host(dtype) && out_dtype == dtype && ch == 64) {
     // tensor-core path (the bf16 rollout)
     int n16 = (n + 15) & ~15;
     int lines = axis == 0 ? W : H;
     size_t smem_mma = ((size_t)n16 * (n16 + 8) + (size_t)lns::kAxLines * n16 * lns::kAxSlabStride +
                        4 * 16 * (size_t)lns::kAxSlabStride) * sizeof(__nv_bfloat16);
     LNS_REQUIRE(smem_mma <= 227 * 1024, "lns_axial_contract: n=%d needs %zu B shared memory", n, smem_mma);
-    { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::axial_contract_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+    { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::axial_contract_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); cudaFuncSetAttribute(lns::axial_contract_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
     dim3 grid(lns::cdiv(lines, lns::kAxLines), heads, B);
-    lns::axial_contract_mma_kernel<<<grid, 128, smem_mma, s>>>(reinterpret_cast<const __nv_bfloat16*>(u), H, W, heads, K, axis,
+    auto kern = dtype == LNS_F16 ? lns::axial_contract_mma_kernel<true> : lns::axial_contract_mma_kernel<false>;
+    kern<<<grid, 128, smem_mma, s>>>(reinterpret_cast<const __nv_bfloat16*>(u), H, W, heads, K, axis,
                                                                reinterpret_cast<__nv_bfloat16*>(out));
     return lns::check_launch("axial_contract_mma_kernel");
   }

@@ -1,6 +1,7 @@
 // Shared device/host helpers for liblns_b200.so (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -28,9 +29,43 @@ __device__ __forceinline__ float round_tf32(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return __uint_as_float(r);
 }
+// 16-bit storage: LNS_BF16 (8-bit mantissa, fp32 range) or LNS_F16 (11-bit mantissa; conversions SATURATE to +-65504
+// instead of overflowing to inf).  Both feed tcgen05.mma.kind::f16 / mma.sync at the same rate; kernels take the format as
+// a template flag (F16) or, in the byte-moving ones, as the runtime dtype.  Pointers to either are typed __nv_bfloat16*
+// (an opaque 16-bit element) -- only these helpers interpret the bits.
+__device__ __forceinline__ bool is_h16(int dtype) { return dtype == LNS_BF16 || dtype == LNS_F16; }
+static inline bool is_h16_host(int dtype) { return dtype == LNS_BF16 || dtype == LNS_F16; }
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2_h16(float lo, float hi) {
+  uint32_t r;
+  if (F16) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    r = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return r;
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack2_h16(uint32_t raw) {
+  if (F16) return __half22float2(*reinterpret_cast<__half2*>(&raw));
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&raw));
+}
+template <bool F16>
+__device__ __forceinline__ uint16_t to_h16(float v) { return (uint16_t)(pack2_h16<F16>(v, 0.f) & 0xFFFFu); }
+template <bool F16>
+__device__ __forceinline__ float from_h16(uint16_t raw) { return unpack2_h16<F16>((uint32_t)raw).x; }
+__device__ __forceinline__ uint32_t pack2_rt(int dtype, float lo, float hi) {
+  return dtype == LNS_F16 ? pack2_h16<true>(lo, hi) : pack2_h16<false>(lo, hi);
+}
+__device__ __forceinline__ float2 unpack2_rt(int dtype, uint32_t raw) {
+  return dtype == LNS_F16 ? unpack2_h16<true>(raw) : unpack2_h16<false>(raw);
+}
+
 __device__ __forceinline__ float ld_as_float(const void* p, int dtype, int64_t i) {
-  if (dtype != LNS_BF16) return __ldg(reinterpret_cast<const float*>(p) + i);
-  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  if (!is_h16(dtype)) return __ldg(reinterpret_cast<const float*>(p) + i);
+  const uint16_t raw = reinterpret_cast<const uint16_t*>(p)[i];
+  return dtype == LNS_F16 ? from_h16<true>(raw) : from_h16<false>(raw);
 }
 __device__ __forceinline__ void st_from_float(void* p, int dtype, int64_t i, float v) {
   if (dtype == LNS_F32)
@@ -38,15 +73,13 @@ __device__ __forceinline__ void st_from_float(void* p, int dtype, int64_t i, flo
   else if (dtype == LNS_TF32)
     reinterpret_cast<float*>(p)[i] = round_tf32(v);
   else
-    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+    reinterpret_cast<uint16_t*>(p)[i] = dtype == LNS_F16 ? to_h16<true>(v) : to_h16<false>(v);
 }
 // 4 consecutive elements (i must be a multiple of 4 and the pointer suitably aligned)
 __device__ __forceinline__ float4 ld4_as_float(const void* p, int dtype, int64_t i) {
-  if (dtype != LNS_BF16) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i));
-  uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i));
-  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
-  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
-  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  if (!is_h16(dtype)) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i));
+  uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p) + i));
+  float2 fa = unpack2_rt(dtype, raw.x), fb = unpack2_rt(dtype, raw.y);
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
 __device__ __forceinline__ void st4_from_float(void* p, int dtype, int64_t i, float4 v) {
@@ -56,15 +89,13 @@ __device__ __forceinline__ void st4_from_float(void* p, int dtype, int64_t i, fl
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) =
         make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
   } else {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
-    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
     uint2 raw;
-    raw.x = *reinterpret_cast<uint32_t*>(&a);
-    raw.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = raw;
+    raw.x = pack2_rt(dtype, v.x, v.y);
+    raw.y = pack2_rt(dtype, v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p) + i) = raw;
   }
 }
-__host__ __device__ __forceinline__ int dtype_size(int dtype) { return dtype == LNS_BF16 ? 2 : 4; }
+__host__ __device__ __forceinline__ int dtype_size(int dtype) { return (dtype == LNS_BF16 || dtype == LNS_F16) ? 2 : 4; }
 
 // ---- activations (exact forms, matching torch) ----------------------------------------------------
 // Swish  x*sigmoid(x)   modules/basics.py:27-29 ; nn.GELU() exact erf  train_stage2_ns2d.py:36
@@ -95,9 +126,9 @@ __device__ __forceinline__ float apply_act_fast(float x, int act) {
   if (act == LNS_ACT_GELU) return act_gelu_fast(x);
   return x;
 }
-// exact on fp32 storage, fast on bf16 storage
+// exact on fp32 storage, fast on 16-bit storage
 __device__ __forceinline__ float apply_act_for(float x, int act, int storage_dtype) {
-  return storage_dtype == LNS_BF16 ? apply_act_fast(x, act) : apply_act(x, act);
+  return is_h16(storage_dtype) ? apply_act_fast(x, act) : apply_act(x, act);
 }
 
 // ---- reductions ----------------------------------------------------------------------------------

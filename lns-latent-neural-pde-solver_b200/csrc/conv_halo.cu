@@ -160,6 +160,7 @@ struct HaloParams {
   int64_t res_bstride;
   void* y;
   int y_dtype;
+  int x_f16;  // operands (input, filter) are IEEE half instead of bf16
   int tiles_x, tiles_y, ntiles;
   int HH, HW;          // halo height / width in pixels: 16 + 2d, 8 + 2d
   int halo_bytes;      // per stage, multiple of 1024
@@ -223,16 +224,20 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
       uint4 v = make_uint4(0, 0, 0, 0);
       if (ch == 0 && n < g.Cout) {
         const float bv = __ldg(p.bias + n);
-        const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
-        v.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+        if (p.x_f16) {
+          const uint16_t hi = to_h16<true>(bv), lo = to_h16<true>(bv - from_h16<true>(hi));
+          v.x = (uint32_t)hi | ((uint32_t)lo << 16);
+        } else {
+          const uint16_t hi = to_h16<false>(bv), lo = to_h16<false>(bv - from_h16<false>(hi));
+          v.x = (uint32_t)hi | ((uint32_t)lo << 16);
+        }
       }
       *reinterpret_cast<uint4*>(bb + n * 128 + ((ch ^ (n & 7)) << 4)) = v;
     }
     for (int e = tid; e < 8 * 8; e += blockDim.x) {   // the ones tile
       const int r = e >> 3, ch = e & 7;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (ch == 0) v.x = 0x3F803F80u;  // bf16 (1.0, 1.0)
+      if (ch == 0) v.x = p.x_f16 ? 0x3C003C00u : 0x3F803F80u;  // (1.0, 1.0) in f16 / bf16
       *reinterpret_cast<uint4*>(bb + NT * 128 + r * 128 + ((ch ^ r) << 4)) = v;
     }
     hptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -337,7 +342,9 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
     // descriptors in a single thread (which made the issue thread the bottleneck: 25% tensor-pipe in the first profile).
     {
       const uint32_t leader = (lane == 0) ? 1u : 0u;
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)g.Cout >> 3) << 17) | ((128u >> 4) << 24);
+      // kind::f16 instruction descriptor: D = f32, A/B format 1 = bf16 or 0 = f16, K-major, N, M = 128
+      const uint32_t fmt_ab = p.x_f16 ? 0u : ((1u << 7) | (1u << 10));
+      const uint32_t idesc = (1u << 4) | fmt_ab | (((uint32_t)g.Cout >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t desc_hi_a = (((uint32_t)p.HW * 128u) >> 4) | (1u << 14) | (2u << 29);
       const uint32_t desc_hi_b = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t w_lo = (w_base & 0x3FFFFu) >> 4;
@@ -381,6 +388,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
     // row so both the row-wise writes and the line-wise reads are conflict free) and leave as full-line stores:
     // 8 consecutive rows = 8 consecutive pixels = 1 KB contiguous in NHWC.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const bool y16 = is_h16(p.y_dtype);
     const int m = quad * 32 + lane;
     const int ty_l = m >> 3, tx_l = m & 7;
     const uint32_t my_stage = stage_out + (uint32_t)(warp - (4 + kIssuers)) * 4096u;
@@ -448,14 +456,16 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
               v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
             }
           }
-          if (p.y_dtype == LNS_BF16) {
+          if (y16) {
 #pragma unroll
             for (int h4 = 0; h4 < 4; ++h4) {
               uint32_t pk[4];
+              if (p.y_dtype == LNS_F16) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                for (int j = 0; j < 4; ++j) pk[j] = pack2_h16<true>(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pk[j] = pack2_h16<false>(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
               }
               const int ch = (cc >> 3) + h4;  // 16-byte chunk index inside the 128-byte staged row
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_st + (uint32_t)((ch ^ (lane & 7)) << 4)),
@@ -467,7 +477,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         }
-        if (p.y_dtype == LNS_BF16) {
+        if (y16) {
           __syncwarp();
           // staged row r = 4*pass + rd_row of this warp's quadrant = tile row quad*4 + pass/2, tile col 4*(pass&1) + rd_row
           const int yq = ty * kTileH + quad * 4, xq = tx * kTileW + rd_row;
@@ -508,8 +518,9 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
 bool conv_halo_supported(const LnsConvDesc* d) {
   return d->KH == 3 && d->KW == 3 && d->stride == 1 && d->Cin == 64 && (d->Cout == 64 || d->Cout == 128) &&
          d->pad_t == d->dil && d->pad_l == d->dil && d->Hout == d->Hv && d->Wout == d->Wv && d->dil >= 1 &&
-         d->dil <= 3 && d->x_dtype == LNS_BF16 && d->x_layout == LNS_NHWC && d->y_layout == LNS_NHWC &&
-         d->pro_scale == nullptr && d->pro_act == LNS_ACT_NONE && d->w_format == LNS_W_UMMA_BF16 &&
+         d->dil <= 3 && is_h16_host(d->x_dtype) && d->x_layout == LNS_NHWC && d->y_layout == LNS_NHWC &&
+         d->pro_scale == nullptr && d->pro_act == LNS_ACT_NONE &&
+         d->w_format == (d->x_dtype == LNS_F16 ? LNS_W_UMMA_F16 : LNS_W_UMMA_BF16) &&
          d->dil <= d->Hv && d->dil <= d->Wv;
 }
 
@@ -531,7 +542,7 @@ static int launch_halo(const HaloParams& p, int smem_bytes, int grid, cudaStream
 
 int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
   LNS_REQUIRE(conv_halo_supported(d),
-              "lns_conv2d(halo): needs a same-size 3x3 stride-1 conv, Cin=64, Cout in {64,128}, pad=dil<=3, NHWC bf16 "
+              "lns_conv2d(halo): needs a same-size 3x3 stride-1 conv, Cin=64, Cout in {64,128}, pad=dil<=3, NHWC bf16/f16 "
               "input, UMMA-packed weights, no fused prologue");
   LNS_REQUIRE(d->x_bstride % 8 == 0 && d->y_bstride % 8 == 0, "lns_conv2d(halo): batch strides must be multiples of 8");
   LNS_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->y) & 15) == 0 &&
@@ -551,6 +562,7 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
   p.pre_add = d->pre_add; p.pre_add_dtype = d->pre_add_dtype; p.pre_add_bstride = d->pre_add_bstride;
   p.residual = d->residual; p.res_dtype = d->res_dtype; p.res_bstride = d->res_bstride;
   p.y = d->y; p.y_dtype = d->y_dtype;
+  p.x_f16 = d->x_dtype == LNS_F16 ? 1 : 0;
   p.tiles_x = cdiv(d->Wout, kTileW);
   p.tiles_y = cdiv(d->Hout, kTileH);
   int64_t nt = (int64_t)p.tiles_x * p.tiles_y * d->B;

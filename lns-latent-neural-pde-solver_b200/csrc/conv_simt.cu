@@ -184,8 +184,9 @@ __global__ void pack_simt_kernel(const float* __restrict__ w, int Cout, int Cin,
 
 // [tap][Cin/64][Cout][64] bf16; inside each 128-byte row the eight 16-byte chunks are XOR-swizzled with (row & 7),
 // i.e. the image is byte-for-byte what tcgen05's SWIZZLE_128B K-major shared-memory layout expects.
-__global__ void pack_umma_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW,
-                                 __nv_bfloat16* __restrict__ out) {
+// (f16 != 0: IEEE-half elements instead of bf16 -- LNS_W_UMMA_F16)
+__global__ void pack_umma_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int f16,
+                                 uint16_t* __restrict__ out) {
   int64_t total = (int64_t)Cout * Cin * KH * KW;
   int slabs = Cin / 64;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -199,7 +200,7 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, int Cout, int Cin,
     float v = w[((int64_t)n * Cin + c) * KH * KW + tap];
     int chunk = (kk >> 3) ^ (n & 7);
     int64_t o = (((int64_t)tap * slabs + slab) * Cout + n) * 64 + chunk * 8 + (kk & 7);
-    out[o] = __float2bfloat16_rn(v);
+    out[o] = f16 ? to_h16<true>(v) : to_h16<false>(v);
   }
 }
 
@@ -229,7 +230,7 @@ extern "C" {
 int64_t lns_packed_weight_bytes(int Cout, int Cin, int KH, int KW, int format) {
   int64_t n = (int64_t)Cout * Cin * KH * KW;
   if (format == LNS_W_SIMT_F32) return n * 4;
-  if (format == LNS_W_UMMA_BF16) return (Cin % 64 == 0 && Cout % 16 == 0) ? n * 2 : -1;
+  if (format == LNS_W_UMMA_BF16 || format == LNS_W_UMMA_F16) return (Cin % 64 == 0 && Cout % 16 == 0) ? n * 2 : -1;
   if (format == LNS_W_UMMA_TF32) return (Cin % 32 == 0 && Cout % 16 == 0) ? n * 4 : -1;
   return -1;
 }
@@ -242,10 +243,11 @@ int lns_pack_conv_weight(const float* w, int Cout, int Cin, int KH, int KW, int 
   if (blocks > 4096) blocks = 4096;
   if (format == LNS_W_SIMT_F32) {
     lns::pack_simt_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, KH, KW, reinterpret_cast<float*>(out));
-  } else if (format == LNS_W_UMMA_BF16) {
+  } else if (format == LNS_W_UMMA_BF16 || format == LNS_W_UMMA_F16) {
     LNS_REQUIRE(Cin % 64 == 0 && Cout % 16 == 0, "lns_pack_conv_weight: UMMA format needs Cin%%64==0, Cout%%16==0 (got %d,%d)",
                 Cin, Cout);
-    lns::pack_umma_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, KH, KW, reinterpret_cast<__nv_bfloat16*>(out));
+    lns::pack_umma_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, KH, KW, format == LNS_W_UMMA_F16 ? 1 : 0,
+                                                 reinterpret_cast<uint16_t*>(out));
   } else if (format == LNS_W_UMMA_TF32) {
     LNS_REQUIRE(Cin % 32 == 0 && Cout % 16 == 0, "lns_pack_conv_weight: TF32 format needs Cin%%32==0, Cout%%16==0 (got %d,%d)",
                 Cin, Cout);

@@ -125,6 +125,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
+// same with A=B=f16 (format code 0)
+__device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 // kind::tf32: D=f32, A=B=tf32 (format code 2)
 __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
@@ -132,7 +134,7 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n) {
 
 struct UmmaParams {
   ConvGeom g;
-  const void* x;  // bf16 (ESZ 2) or fp32/tf32 (ESZ 4) NHWC
+  const void* x;  // bf16 / f16 (ESZ 2) or fp32/tf32 (ESZ 4) NHWC
   const void* w;  // packed [tap][slab][Cout][128 B]
   const float* bias;
   const float* sample_bias;
@@ -145,6 +147,7 @@ struct UmmaParams {
   int64_t res_bstride;
   void* y;
   int y_dtype;
+  int x_f16;  // 16-bit operands are IEEE half instead of bf16
   int M;
   int slabs;  // Cin / (128 / ESZ): 128-byte K blocks per pixel
   uint32_t x_bstride8;  // input batch stride in 16-byte units
@@ -348,12 +351,14 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
           v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
         }
       }
-      if (p.y_dtype == LNS_BF16) {
+      if (is_h16(p.y_dtype)) {
         uint32_t pk[8];
+        if (p.y_dtype == LNS_F16) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int j = 0; j < 8; ++j) pk[j] = pack2_h16<true>(v[2 * j], v[2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = pack2_h16<false>(v[2 * j], v[2 * j + 1]);
         }
         uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yrow + c0);
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -373,7 +378,8 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
   } else {
     // ============================== MMA issuer (warp 4, one thread) ==============================
     if (lane == 0) {
-      const uint32_t idesc = ESZ == 2 ? make_idesc_bf16((uint32_t)n_valid) : make_idesc_tf32((uint32_t)n_valid);
+      const uint32_t idesc = ESZ == 2 ? (p.x_f16 ? make_idesc_f16((uint32_t)n_valid) : make_idesc_bf16((uint32_t)n_valid))
+                                      : make_idesc_tf32((uint32_t)n_valid);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         ptx::mbar_wait(full_bar(s), (kb / STAGES) & 1);
@@ -425,9 +431,10 @@ static int launch_umma(const UmmaParams& p, int Cout, cudaStream_t stream) {
 int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
   const bool tf32 = d->w_format == LNS_W_UMMA_TF32;
   const int esz = tf32 ? 4 : 2, kblk = 128 / esz;  // channels per 128-byte K block
-  LNS_REQUIRE(d->w_format == LNS_W_UMMA_BF16 || tf32, "lns_conv2d(umma): weights must be packed as LNS_W_UMMA_BF16 / _TF32");
-  LNS_REQUIRE(d->x_layout == LNS_NHWC && (tf32 ? d->x_dtype != LNS_BF16 : d->x_dtype == LNS_BF16),
-              "lns_conv2d(umma): input must be NHWC bf16 (bf16 filter) or NHWC fp32/tf32 (tf32 filter)");
+  const bool f16 = d->w_format == LNS_W_UMMA_F16;
+  LNS_REQUIRE(d->w_format == LNS_W_UMMA_BF16 || f16 || tf32, "lns_conv2d(umma): weights must be packed as LNS_W_UMMA_BF16 / _F16 / _TF32");
+  LNS_REQUIRE(d->x_layout == LNS_NHWC && (tf32 ? !is_h16_host(d->x_dtype) : d->x_dtype == (f16 ? LNS_F16 : LNS_BF16)),
+              "lns_conv2d(umma): input must be NHWC bf16 / f16 (matching the filter format) or NHWC fp32/tf32 (tf32 filter)");
   LNS_REQUIRE(d->y_layout == LNS_NHWC, "lns_conv2d(umma): output must be NHWC");
   LNS_REQUIRE(d->Cin % kblk == 0 && d->Cout % 16 == 0, "lns_conv2d(umma): needs Cin%%%d==0 and Cout%%16==0 (got %d,%d)", kblk,
               d->Cin, d->Cout);
@@ -455,6 +462,7 @@ int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
   p.pre_add = d->pre_add; p.pre_add_dtype = d->pre_add_dtype; p.pre_add_bstride = d->pre_add_bstride;
   p.residual = d->residual; p.res_dtype = d->res_dtype; p.res_bstride = d->res_bstride;
   p.y = d->y; p.y_dtype = d->y_dtype;
+  p.x_f16 = f16 ? 1 : 0;
   p.M = (int)M;
   p.slabs = d->Cin / kblk;
   p.x_bstride8 = (uint32_t)((d->x_bstride * esz) >> 4);

@@ -28,18 +28,26 @@ __device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r
 __device__ __forceinline__ void ldsm_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
+// F16 = false: bf16 operands / storage, true: IEEE half
+template <bool F16>
 __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  if (F16)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // In-place axial contraction of one line (an image column or row) held in U_s:
 //   out[i][c] = sum_j Kmat[i][j] * line[j][c],  line element j lives at U_s + base + j*step  (offsets in bf16 elements).
 // KT = ceil(n/16) k/m tiles.  The whole line (B fragments) is read into registers before anything is written.
-template <int KT, bool STATS>
+template <int KT, bool STATS, bool F16>
 __device__ __forceinline__ void contract_line(__nv_bfloat16* U_s, int base, int step, int n, const __nv_bfloat16* K_s, int kstride,
                                               int lane, float* st) {
   uint32_t bf[KT][8][2];
@@ -63,16 +71,16 @@ __device__ __forceinline__ void contract_line(__nv_bfloat16* U_s, int base, int 
       uint32_t a[4];
       ldsm_x4(s32(K_s + (size_t)(mt * 16 + (lane & 15)) * kstride + kt * 16 + (lane >> 4) * 8), a[0], a[1], a[2], a[3]);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) mma16816(acc[nt], a, bf[kt][nt][0], bf[kt][nt][1]);
+      for (int nt = 0; nt < 8; ++nt) mma16816<F16>(acc[nt], a, bf[kt][nt][0], bf[kt][nt][1]);
     }
     const int i0 = mt * 16 + g, i1 = i0 + 8;
     const bool v0 = i0 < n, v1 = i1 < n;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       if (v0)
-        *reinterpret_cast<__nv_bfloat162*>(U_s + (size_t)base + (size_t)i0 * step + nt * 8 + t * 2) = __floats2bfloat162_rn(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<uint32_t*>(U_s + (size_t)base + (size_t)i0 * step + nt * 8 + t * 2) = pack2_h16<F16>(acc[nt][0], acc[nt][1]);
       if (v1)
-        *reinterpret_cast<__nv_bfloat162*>(U_s + (size_t)base + (size_t)i1 * step + nt * 8 + t * 2) = __floats2bfloat162_rn(acc[nt][2], acc[nt][3]);
+        *reinterpret_cast<uint32_t*>(U_s + (size_t)base + (size_t)i1 * step + nt * 8 + t * 2) = pack2_h16<F16>(acc[nt][2], acc[nt][3]);
       if (STATS) {  // InstanceNorm sums of channels nt*8 + 2t, +1 (fp32 values, before the bf16 rounding of the store)
         const float a0 = v0 ? acc[nt][0] : 0.f, a1 = v0 ? acc[nt][1] : 0.f, a2 = v1 ? acc[nt][2] : 0.f, a3 = v1 ? acc[nt][3] : 0.f;
         st[nt * 4 + 0] += a0 + a2;
@@ -85,16 +93,16 @@ __device__ __forceinline__ void contract_line(__nv_bfloat16* U_s, int base, int 
   __syncwarp();
 }
 
-template <int KT, bool STATS>
+template <int KT, bool STATS, bool F16>
 __device__ __forceinline__ void contract_axis(__nv_bfloat16* U_s, int lines, int line_mul, int step, int n, const __nv_bfloat16* K_s,
                                               int kstride, int warp, int nwarp, int lane, float* st) {
-  for (int l = warp; l < lines; l += nwarp) contract_line<KT, STATS>(U_s, l * line_mul, step, n, K_s, kstride, lane, st);
+  for (int l = warp; l < lines; l += nwarp) contract_line<KT, STATS, F16>(U_s, l * line_mul, step, n, K_s, kstride, lane, st);
 }
 }  // namespace
 
 // grid (heads, B), block 512 (256 when an axis needs 3 k-tiles: register budget); instruction-issue bound, so 4 warps per
 // scheduler instead of 2 buy latency hiding
-template <int NTHR>
+template <int NTHR, bool F16>
 __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat16* __restrict__ u, int H, int W, int heads,
                                                                const float* __restrict__ gn_scale, const float* __restrict__ gn_shift,
                                                                const float* __restrict__ w_in, const float* __restrict__ Kx,
@@ -155,11 +163,9 @@ __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_in + (int64_t)(h * 64 + n) * 64 + kc * 8 + 4));
     const float4 s0 = __ldg(reinterpret_cast<const float4*>(gn_scale + (int64_t)b * 64 + kc * 8));
     const float4 s1 = __ldg(reinterpret_cast<const float4*>(gn_scale + (int64_t)b * 64 + kc * 8 + 4));
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(w0.x * s0.x, w0.y * s0.y), p1 = __floats2bfloat162_rn(w0.z * s0.z, w0.w * s0.w);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(w1.x * s1.x, w1.y * s1.y), p3 = __floats2bfloat162_rn(w1.z * s1.z, w1.w * s1.w);
     *reinterpret_cast<uint4*>(Ws_s + n * kUS + kc * 8) =
-        make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
-                   *reinterpret_cast<uint32_t*>(&p3));
+        make_uint4(pack2_h16<F16>(w0.x * s0.x, w0.y * s0.y), pack2_h16<F16>(w0.z * s0.z, w0.w * s0.w),
+                   pack2_h16<F16>(w1.x * s1.x, w1.y * s1.y), pack2_h16<F16>(w1.z * s1.z, w1.w * s1.w));
   }
   {
     // bias[n] = sum_k W[n][k] * shift[k]: 4 threads per output channel, 16 k each, fixed-order quad reduction
@@ -179,11 +185,11 @@ __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat
     const float* kg = Kx + ((int64_t)b * heads + h) * H * H;
     for (int i = warp; i < H16; i += nwarp)
       for (int j = lane; j < H16; j += 32)
-        Kx_s[i * kxs + j] = __float2bfloat16_rn((i < H && j < H) ? __ldg(kg + i * H + j) : 0.f);
+        reinterpret_cast<uint16_t*>(Kx_s)[i * kxs + j] = to_h16<F16>((i < H && j < H) ? __ldg(kg + i * H + j) : 0.f);
     kg = Ky + ((int64_t)b * heads + h) * W * W;
     for (int i = warp; i < W16; i += nwarp)
       for (int j = lane; j < W16; j += 32)
-        Ky_s[i * kys + j] = __float2bfloat16_rn((i < W && j < W) ? __ldg(kg + i * W + j) : 0.f);
+        reinterpret_cast<uint16_t*>(Ky_s)[i * kys + j] = to_h16<F16>((i < W && j < W) ? __ldg(kg + i * W + j) : 0.f);
   }
 
   // ---- phase A: u_phi_h = u x Ws^T + bias, in place, 16-row blocks per warp ----
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) mma16816(acc[nt], a[ks], wf[ks][nt][0], wf[ks][nt][1]);
+        for (int nt = 0; nt < 8; ++nt) mma16816<F16>(acc[nt], a[ks], wf[ks][nt][0], wf[ks][nt][1]);
       }
       __syncwarp();  // every lane's ldmatrix of the raw rows is done before they are overwritten
       const int r0 = blk * 16 + g, r1 = r0 + 8;
@@ -228,8 +234,8 @@ __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const float2 bs = *reinterpret_cast<const float2*>(bias_s + nt * 8 + t * 2);
-        if (r0 < HW) *reinterpret_cast<__nv_bfloat162*>(o0 + nt * 8) = __floats2bfloat162_rn(acc[nt][0] + bs.x, acc[nt][1] + bs.y);
-        if (r1 < HW) *reinterpret_cast<__nv_bfloat162*>(o1 + nt * 8) = __floats2bfloat162_rn(acc[nt][2] + bs.x, acc[nt][3] + bs.y);
+        if (r0 < HW) *reinterpret_cast<uint32_t*>(o0 + nt * 8) = pack2_h16<F16>(acc[nt][0] + bs.x, acc[nt][1] + bs.y);
+        if (r1 < HW) *reinterpret_cast<uint32_t*>(o1 + nt * 8) = pack2_h16<F16>(acc[nt][2] + bs.x, acc[nt][3] + bs.y);
       }
     }
   }
@@ -239,15 +245,15 @@ __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat
   float st[32];  // phase C: per-thread InstanceNorm partial sums: [nt][sum(2t), sum(2t+1), sumsq(2t), sumsq(2t+1)]
 #pragma unroll
   for (int i = 0; i < 32; ++i) st[i] = 0.f;
-  if (H16 == 16) contract_axis<1, false>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane, st);
-  else if (H16 == 32) contract_axis<2, false>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane, st);
-  else contract_axis<3, false>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane, st);
+  if (H16 == 16) contract_axis<1, false, F16>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane, st);
+  else if (H16 == 32) contract_axis<2, false, F16>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane, st);
+  else contract_axis<3, false, F16>(U_s, W, kUS, RS, H, Kx_s, kxs, warp, nwarp, lane, st);
   __syncthreads();
   // ---- phase C: contraction over W, one image row per warp (element m of row i at i*RS + m*72); its epilogue also
   // accumulates the InstanceNorm sums of the 16 channels a thread holds (no separate statistics pass over the tile) ----
-  if (W16 == 16) contract_axis<1, true>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane, st);
-  else if (W16 == 32) contract_axis<2, true>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane, st);
-  else contract_axis<3, true>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane, st);
+  if (W16 == 16) contract_axis<1, true, F16>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane, st);
+  else if (W16 == 32) contract_axis<2, true, F16>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane, st);
+  else contract_axis<3, true, F16>(U_s, H, RS, kUS, W, Ky_s, kys, warp, nwarp, lane, st);
 
   // ---- phase D: reduce the partial sums: over the 8 lanes that share t (shuffles), then over the warps (fixed order) ----
 #pragma unroll
@@ -304,9 +310,8 @@ __global__ void __launch_bounds__(NTHR, 1) fablock_core_kernel(const __nv_bfloat
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
-        __nv_bfloat162 hh = __floats2bfloat162_rn(fmaf(f.x, na[2 * j], nb[2 * j]), fmaf(f.y, na[2 * j + 1], nb[2 * j + 1]));
-        o[j] = *reinterpret_cast<uint32_t*>(&hh);
+        const float2 f = unpack2_h16<F16>(w[j]);
+        o[j] = pack2_h16<F16>(fmaf(f.x, na[2 * j], nb[2 * j]), fmaf(f.y, na[2 * j + 1], nb[2 * j + 1]));
       }
       *reinterpret_cast<uint4*>(gp) = make_uint4(o[0], o[1], o[2], o[3]);
       gp += gadv;
@@ -457,9 +462,10 @@ int lns_fablock_core_supported(int H, int W, int dim, int dim_head) {
   return dim == 64 && dim_head == 64 && H <= 48 && W <= 48 && H >= 1 && W >= 1 && lns::fablock_smem(H, W) <= 227 * 1024;
 }
 
-int lns_fablock_core(const void* u, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
+int lns_fablock_core(const void* u, int dtype, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
                      const float* w_in_proj, const float* Kx, const float* Ky, float eps, void* out, void* stream) {
   LNS_REQUIRE(u && gn_scale && gn_shift && w_in_proj && Kx && Ky && out && B > 0 && heads > 0, "lns_fablock_core: bad arguments");
+  LNS_REQUIRE(lns::is_h16_host(dtype), "lns_fablock_core: u/out must be LNS_BF16 or LNS_F16 (got dtype %d)", dtype);
   LNS_REQUIRE(lns_fablock_core_supported(H, W, 64, 64), "lns_fablock_core: %dx%d does not fit the fused kernel (use the unfused ops)", H, W);
   LNS_REQUIRE(B <= 65535, "lns_fablock_core: batch %d exceeds grid limit, chunk the call", B);
   LNS_REQUIRE((reinterpret_cast<uintptr_t>(u) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "lns_fablock_core: alignment");
@@ -467,19 +473,25 @@ int lns_fablock_core(const void* u, int B, int H, int W, int heads, const float*
   {
     static bool once = false;
     if (!once) {
-      cudaFuncSetAttribute(lns::fablock_core_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(lns::fablock_core_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(lns::fablock_core_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(lns::fablock_core_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(lns::fablock_core_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(lns::fablock_core_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       once = true;
     }
   }
   dim3 grid(heads, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (H <= 32 && W <= 32 && H * W > 256)  // <= 2 k-tiles per axis: fits 128 registers per thread; small images: 2+ CTAs/SM
-    lns::fablock_core_kernel<512><<<grid, 512, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(u), H, W, heads, gn_scale, gn_shift,
-                                                            w_in_proj, Kx, Ky, eps, reinterpret_cast<__nv_bfloat16*>(out));
-  else
-    lns::fablock_core_kernel<256><<<grid, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(u), H, W, heads, gn_scale, gn_shift,
-                                                            w_in_proj, Kx, Ky, eps, reinterpret_cast<__nv_bfloat16*>(out));
+  const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(u);
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
+  const bool f16 = dtype == LNS_F16;
+  if (H <= 32 && W <= 32 && H * W > 256) {  // <= 2 k-tiles per axis: fits 128 registers per thread; small images: 2+ CTAs/SM
+    auto kern = f16 ? lns::fablock_core_kernel<512, true> : lns::fablock_core_kernel<512, false>;
+    kern<<<grid, 512, smem, st>>>(up, H, W, heads, gn_scale, gn_shift, w_in_proj, Kx, Ky, eps, op);
+  } else {
+    auto kern = f16 ? lns::fablock_core_kernel<256, true> : lns::fablock_core_kernel<256, false>;
+    kern<<<grid, 256, smem, st>>>(up, H, W, heads, gn_scale, gn_shift, w_in_proj, Kx, Ky, eps, op);
+  }
   return lns::check_launch("fablock_core_kernel");
 }
 

@@ -11,15 +11,16 @@ import torch
 from . import _C
 from ._C import ConvDesc, LnsError, check
 
-F32, BF16, TF32_CODE = 0, 1, 2
+F32, BF16, TF32_CODE, F16 = 0, 1, 2, 3
 TF32 = "tf32"  # storage sentinel: fp32 words holding TF32-rounded values (LNS_TF32); accepted wherever a dtype is
 NHWC, NCHW = 0, 1
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAD_ZEROS, PAD_CIRCULAR = 0, 1
-W_SIMT_F32, W_UMMA_BF16, W_UMMA_TF32 = 0, 1, 2
+W_SIMT_F32, W_UMMA_BF16, W_UMMA_TF32, W_UMMA_F16 = 0, 1, 2, 3
 ENGINE_SIMT, ENGINE_UMMA, ENGINE_HALO = 0, 1, 2
 
-_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
+H16_DTYPES = (torch.bfloat16, torch.float16)  # the 16-bit storage types of the tensor-core paths
 
 
 def dt_code(dtype):
@@ -27,6 +28,8 @@ def dt_code(dtype):
         return F32
     if dtype == torch.bfloat16:
         return BF16
+    if dtype == torch.float16:
+        return F16
     raise LnsError(f"unsupported dtype {dtype}")
 
 
@@ -64,11 +67,15 @@ def get_precision():
 
 def set_precision(p):
     """'bf16': bf16 activations, tcgen05 tensor-core GEMMs with fp32 accumulation (the fast path).
+    'fp16': IEEE-half activations and GEMM operands through the SAME kernels, bytes and tensor-core rate as 'bf16'
+            (tcgen05.mma.kind::f16 takes either format) with an 11-bit significand: TF32-class rounding error, i.e. the
+            16-bit path that meets the 2e-3 per-step bound.  Conversions saturate at +-65504 (the residual stream of a
+            trained model must stay inside the half range; norm statistics, softmax and latents are fp32 as in 'bf16').
     'tf32': fp32 storage rounded to TF32 at every write, tcgen05.mma.kind::tf32 GEMMs with fp32 accumulation (the
             tensor-core path that meets the 2e-3 per-step bound; half the MMA rate and twice the bytes of bf16).
     'fp32': fp32 activations and CUDA-core fp32 FMA GEMMs (the validation path, <=1e-5 vs the reference)."""
-    if p not in ("bf16", "fp32", "tf32"):
-        raise ValueError("precision must be 'bf16', 'tf32' or 'fp32'")
+    if p not in ("bf16", "fp16", "fp32", "tf32"):
+        raise ValueError("precision must be 'bf16', 'fp16', 'tf32' or 'fp32'")
     _state.precision = p
 
 
@@ -85,7 +92,14 @@ def precision(p):
 def act_dtype():
     if _state.precision == "bf16":
         return torch.bfloat16
+    if _state.precision == "fp16":
+        return torch.float16
     return TF32 if _state.precision == "tf32" else torch.float32
+
+
+def fast16():
+    """True on the 16-bit tensor-core paths ('bf16' / 'fp16'), which share every kernel and fusion decision."""
+    return _state.precision in ("bf16", "fp16")
 
 
 def launch_count():
@@ -297,8 +311,8 @@ def composed_filter(first, second):
 def _umma_ok(x, Cin, Cout, y_layout):
     if x.layout != NHWC or y_layout != NHWC or Cout % 16 != 0 or x.bstride % 8 != 0:
         return False
-    if _state.precision == "bf16":
-        return x.t.dtype == torch.bfloat16 and Cin % 64 == 0
+    if fast16():
+        return x.t.dtype == act_dtype() and Cin % 64 == 0
     if _state.precision == "tf32":  # fp32 words are read as TF32 by tcgen05.mma.kind::tf32
         return x.t.dtype == torch.float32 and Cin % 32 == 0
     return False
@@ -324,7 +338,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
         return _pointwise_proj(x, filt, use_bias, pro, out)
     if engine is None:
         engine = ENGINE_UMMA if _umma_ok(x, Cin, Cout, out_layout) else ENGINE_SIMT
-        if (engine == ENGINE_UMMA and x.t.dtype == torch.bfloat16 and KH == 3 and KW == 3 and stride == 1 and Cin == 64
+        if (engine == ENGINE_UMMA and x.t.dtype in H16_DTYPES and KH == 3 and KW == 3 and stride == 1 and Cin == 64
                 and Cout in (64, 128)
                 and pt == pb == pl == pr == dil and 1 <= dil <= 3 and Hout >= 16 and Wout >= 8):
             engine = ENGINE_HALO  # full-resolution layers: shared-memory halo + resident filter
@@ -358,7 +372,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     d.pad_mode_h, d.pad_mode_w = pad_mode
     fmt = W_SIMT_F32
     if engine in (ENGINE_UMMA, ENGINE_HALO):
-        fmt = W_UMMA_BF16 if x.t.dtype == torch.bfloat16 else W_UMMA_TF32
+        fmt = {torch.bfloat16: W_UMMA_BF16, torch.float16: W_UMMA_F16}.get(x.t.dtype, W_UMMA_TF32)
     wbuf = filt.get(fmt)
     d.w, d.w_format, d.engine = wbuf.data_ptr(), fmt, engine
     bias = filt.bias() if use_bias else None
@@ -380,7 +394,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     tok = _mark(f"conv e{engine} {KH}x{KW} s{stride} d{dil} {Cin}->{Cout} @{Hout}x{Wout}"
                 f"{' up' if virt is not None else ''}{' pro' if pro is not None else ''}"
                 f"{' act' if act else ''}{' res' if residual is not None else ''} "
-                f"{'bf16' if x.t.dtype == torch.bfloat16 else 'f32'}->{'bf16' if out.t.dtype == torch.bfloat16 else 'f32'}")
+                f"{'h16' if x.t.dtype in H16_DTYPES else 'f32'}->{'h16' if out.t.dtype in H16_DTYPES else 'f32'}")
     rc = _C.lib().lns_conv2d(ctypes.byref(d), _stream())
     check(rc, "lns_conv2d")
     _done(tok)
@@ -572,7 +586,7 @@ def axial_contract(u, K, heads, axis, out_dtype=None):
 
 
 def fablock_core_supported(x, dim_head):
-    return (x.t.dtype == torch.bfloat16 and x.layout == NHWC and x.contiguous
+    return (x.t.dtype in H16_DTYPES and x.layout == NHWC and x.contiguous
             and bool(_C.lib().lns_fablock_core_supported(x.H, x.W, x.C, dim_head)))
 
 
@@ -595,11 +609,11 @@ def fablock_prepass(u, eps, gamma, beta):
 
 
 def fablock_core(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps):
-    """Fused in_proj -> axial contractions -> InstanceNorm of FABlock2D (bf16 path): Act [B,H,W,64] -> [B,H,W,heads*64]."""
-    out = Act.empty(u.B, u.H, u.W, heads * 64, torch.bfloat16, u.t.device)
+    """Fused in_proj -> axial contractions -> InstanceNorm of FABlock2D (16-bit paths): Act [B,H,W,64] -> [B,H,W,heads*64]."""
+    out = Act.empty(u.B, u.H, u.W, heads * 64, u.t.dtype, u.t.device)
     w = w_in_proj.detach().float().contiguous()
     tok = _mark(f"fablock_core @{u.H}x{u.W}")
-    rc = _C.lib().lns_fablock_core(_ptr(u.t), u.B, u.H, u.W, heads, _ptr(gn_scale), _ptr(gn_shift), _ptr(w), _ptr(Kx),
+    rc = _C.lib().lns_fablock_core(_ptr(u.t), u.dtype, u.B, u.H, u.W, heads, _ptr(gn_scale), _ptr(gn_shift), _ptr(w), _ptr(Kx),
                                    _ptr(Ky), float(eps), _ptr(out.t), _stream())
     check(rc, "lns_fablock_core")
     _done(tok)

@@ -126,7 +126,7 @@ def run_layers(layers, x, final_out=None, final_layout=ops.NHWC, final_dtype=Non
             kw = {}
             # conv kxk directly followed by a conv 1x1 (no activation between): one conv with the composed filter
             # (bf16 path only; the fp32 validation path keeps the reference's two steps)
-            if (ops.get_precision() == "bf16" and isinstance(nxt, nn.Conv2d) and nxt.kernel_size == (1, 1)
+            if (ops.fast16() and isinstance(nxt, nn.Conv2d) and nxt.kernel_size == (1, 1)
                     and layer.kernel_size[0] > 1 and nxt.stride == (1, 1) and i + 1 < n - 1
                     and not hasattr(nxt, "periodic_direction")):
                 key = "_lns_composed_%d" % id(nxt)

@@ -115,7 +115,7 @@ class FABlock2D(LnsModule):
         skip = u
         f32 = torch.float32
         inorm = self.to_out[0]
-        fused = (ops.get_precision() == "bf16" and self.in_proj.out_channels == self.heads * 64
+        fused = (ops.fast16() and self.in_proj.out_channels == self.heads * 64
                  and ops.fablock_core_supported(u, self.dim_head) and inorm.weight is None)
         if fused:
             # one read of u: GroupNorm(1) affine + both pooled tensors (means commute with the per-channel affine)

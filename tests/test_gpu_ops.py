@@ -537,3 +537,106 @@ def test_conv_umma_tf32(case):
         y2 = ops.conv2d(a, ops.PackedFilter.of(h.weight, h.bias), stride=stride, dil=dil, pad=pad, pad_mode=modes, virt=virt)
     assert y2.tf32 and y2.t.dtype == torch.float32
     assert torch.equal(act_to_nchw(y2), rt(act_to_nchw(y)))  # stored values are the TF32 roundings
+
+
+# ---- fp16 precision mode: the same 16-bit kernels with IEEE-half operands (LNS_F16) -------------------------------------
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_umma_f16(case):
+    """tcgen05 gather engine with f16 operands vs an fp64 conv of the SAME f16-rounded operands"""
+    ops = ops_mod()
+    B, Cin, Cout, H, W, k, stride, dil, pad, modes, virt = case
+    x, w, b = _conv_case(case, seed=1)
+    ref = ref_conv(x.half().float(), w.half().float(), b, stride, dil, pad, modes, virt)
+    h = Holder(w, b)
+    with ops.precision("fp16"):
+        y = ops.conv2d(act_from(x, torch.float16), ops.PackedFilter.of(h.weight, h.bias), stride=stride, dil=dil,
+                       pad=pad, pad_mode=modes, virt=virt, engine=ops.ENGINE_UMMA, out_dtype=torch.float32)
+        y16 = ops.conv2d(act_from(x, torch.float16), ops.PackedFilter.of(h.weight, h.bias), stride=stride, dil=dil,
+                         pad=pad, pad_mode=modes, virt=virt, engine=ops.ENGINE_UMMA)
+    torch.cuda.synchronize()
+    assert relerr(act_to_nchw(y), ref) < 5e-6
+    assert y16.t.dtype == torch.float16
+    assert relerr(act_to_nchw(y16), ref) < 5e-4  # f16 output rounding (2^-12 per element)
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_halo_f16(case):
+    """halo engine with f16 operands (bias folded into the GEMM as f16 hi+lo), full epilogue"""
+    ops = ops_mod()
+    B, Cout, H, W, dil, modes, virt = case
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, 64, H, W, generator=g)
+    w = torch.randn(Cout, 64, 3, 3, generator=g) / 24.0
+    b = torch.randn(Cout, generator=g) * 0.1
+    Ho, Wo = virt if virt is not None else (H, W)
+    res = torch.randn(B, Cout, Ho, Wo, generator=g)
+    ref = ref_conv(x.half().float(), w.half().float(), b, 1, dil, (dil,) * 4, modes, virt)
+    ref = F.gelu(ref) + res.half().double()
+    h = Holder(w, b)
+    with ops.precision("fp16"):
+        y = ops.conv2d(act_from(x, torch.float16), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4,
+                       pad_mode=modes, virt=virt, act=ops.ACT_GELU, residual=act_from(res, torch.float16),
+                       engine=ops.ENGINE_HALO, out_dtype=torch.float32)
+        y16 = ops.conv2d(act_from(x, torch.float16), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4,
+                         pad_mode=modes, virt=virt, act=ops.ACT_GELU, residual=act_from(res, torch.float16),
+                         engine=ops.ENGINE_HALO)
+    torch.cuda.synchronize()
+    assert relerr(act_to_nchw(y), ref) < 5e-6
+    assert y16.t.dtype == torch.float16
+    assert torch.equal(act_to_nchw(y16), act_to_nchw(y).half().float())  # same values, rounded once
+
+
+def test_f16_saturates_instead_of_overflowing():
+    """conversions to LNS_F16 clamp to +-65504 (an inf would poison every norm statistic downstream)"""
+    ops = ops_mod()
+    x = torch.full((1, 64, 4, 4), 300.0)
+    a = act_from(x, torch.float32)
+    scale = torch.full((64,), 1000.0, device=DEV)
+    shift = torch.zeros(64, device=DEV)
+    y = ops.affine_act(a, scale, shift, ops.ACT_NONE, out_dtype=torch.float16)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.t).all() and float(y.t.float().max()) == 65504.0
+
+
+@pytest.mark.parametrize("n_hw", [(8, 8), (12, 24), (7, 15)])
+def test_attention_tensor_core_f16(n_hw):
+    ops = ops_mod()
+    H, W = n_hw
+    n, heads, dh = H * W, 8, 64
+    g = torch.Generator().manual_seed(17)
+    qkv = torch.randn(3, n, 3 * heads * dh, generator=g)
+    qr = qkv.half().double()
+    q, k, v = [t.view(3, n, heads, dh).transpose(1, 2) for t in qr.split(heads * dh, dim=-1)]
+    attn = F.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, dim=-1)
+    ref = (attn @ v).transpose(1, 2).reshape(3, n, heads * dh)
+    a = ops.Act(qkv.to(DEV).half().reshape(-1), 3, H, W, 3 * heads * dh)
+    y = ops.attention(a, heads, dh, dh ** -0.5)
+    assert y.t.dtype == torch.float16
+    assert relerr(y.as_tokens().float().cpu(), ref) < 8e-4  # P and the output are rounded to f16
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (32, 32), (24, 48), (12, 20)])
+def test_fablock_fused_f16(H, W):
+    """Fused FABlock2D core with f16 storage / operands vs the fp64 oracle of the reference block, and vs the unfused path"""
+    ops = ops_mod()
+    import lns_oracle as O
+    from modules.factorized_attention import FABlock2D
+    torch.manual_seed(3)
+    blk = FABlock2D(64, 64, 64, 8, 64).to(DEV).eval()
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(3, 64, H, W, generator=g)
+    sd = {k: v.cpu().double() for k, v in blk.state_dict().items()}
+    ref = O.fa_block(x.double(), O.SD(sd))
+    a = act_from(x, torch.float16)
+    assert ops.fablock_core_supported(a, 64)
+    with torch.no_grad(), ops.precision("fp16"):
+        fused = act_to_nchw(blk._fwd(a))
+        orig = ops.fablock_core_supported
+        ops.fablock_core_supported = lambda *aa, **kk: False
+        try:
+            unfused = act_to_nchw(blk._fwd(a))
+        finally:
+            ops.fablock_core_supported = orig
+    e_f, e_u = relerr(fused, ref), relerr(unfused, ref)
+    print(f"\n[FABlock2D {H}x{W} f16] fused vs fp64 oracle {e_f:.2e}, unfused {e_u:.2e}, fused vs unfused {relerr(fused, unfused):.2e}")
+    assert e_f < 4e-3 and e_u < 4e-3
