@@ -152,8 +152,8 @@ int lns_norm_finalize(const float* partial, int B, int nchunk, int C, int HW, in
 int lns_group_norm_affine(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int G, float eps,
                           const float* gamma, const float* beta, const float* prescale, float* partial_ws,
                           float* scale, float* shift, void* stream);
-/* GroupNorm statistics + apply + activation in ONE kernel for samples that fit in 48 KB of shared memory as fp32 (the
- * latent-grid layers: 8x8x128, 7x15x64 ...): y = act(GroupNorm(G)(x * prescale)); lns_group_norm_act_supported() tells. */
+/* GroupNorm statistics + apply + activation in ONE kernel for samples of <= 16384 elements, staged raw in shared memory (the
+ * latent-grid layers: 8x8x128, 7x15x128 ...): y = act(GroupNorm(G)(x * prescale)); lns_group_norm_act_supported() tells. */
 int lns_group_norm_act_supported(int H, int W, int C);
 int lns_group_norm_act(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int G, float eps,
                        const float* gamma, const float* beta, const float* prescale, int act, void* y, int y_dtype,

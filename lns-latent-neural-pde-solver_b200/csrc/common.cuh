@@ -95,6 +95,29 @@ __device__ __forceinline__ void st4_from_float(void* p, int dtype, int64_t i, fl
     *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p) + i) = raw;
   }
 }
+// N independent 4-element loads with ALL loads issued before the first conversion.  (Calling ld4_as_float in an unrolled
+// loop under a per-element predicate makes ptxas emit load -> convert -> next load: one exposed memory latency per element,
+// found with ncu in the GroupNorm and FABlock pre-pass kernels.)  off[i] must be a valid (clamped) element offset even when
+// ok[i] is false; invalid elements come back as zeros.
+template <int N>
+__device__ __forceinline__ void ld4n_as_float(const void* p, int dtype, const int64_t (&off)[N], const bool (&ok)[N], float4 (&v)[N]) {
+  if (is_h16(dtype)) {
+    uint2 raw[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) raw[i] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p) + off[i]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float2 fa = unpack2_rt(dtype, raw[i].x), fb = unpack2_rt(dtype, raw[i].y);
+      v[i] = ok[i] ? make_float4(fa.x, fa.y, fb.x, fb.y) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + off[i]));
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (!ok[i]) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
 __host__ __device__ __forceinline__ int dtype_size(int dtype) { return (dtype == LNS_BF16 || dtype == LNS_F16) ? 2 : 4; }
 
 // ---- activations (exact forms, matching torch) ----------------------------------------------------

@@ -76,25 +76,24 @@ __global__ void __launch_bounds__(256) gn_affine_small_kernel(const void* __rest
   float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
   if (lane < rows) {
     // 4 independent 16-byte loads in flight per thread (the accumulation order stays p = lane, lane+rows, ...)
-    int p = lane;
-    for (; p + 3 * rows < HW; p += 4 * rows) {
-      float4 v[4];
+    for (int pb = lane; pb < HW; pb += 8 * rows) {
+      int64_t off[8];
+      bool ok[8];
+      float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ld4_as_float(x, dtype, (int64_t)b * bstride + (int64_t)(p + u * rows) * C + q * 4);
+      for (int u = 0; u < 8; ++u) {
+        const int p = pb + u * rows;
+        ok[u] = p < HW;
+        off[u] = (int64_t)b * bstride + (int64_t)(ok[u] ? p : pb) * C + q * 4;
+      }
+      ld4n_as_float<8>(x, dtype, off, ok, v);  // every load issued before the first use
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         s[0] += v[u].x; ss[0] = fmaf(v[u].x, v[u].x, ss[0]);
         s[1] += v[u].y; ss[1] = fmaf(v[u].y, v[u].y, ss[1]);
         s[2] += v[u].z; ss[2] = fmaf(v[u].z, v[u].z, ss[2]);
         s[3] += v[u].w; ss[3] = fmaf(v[u].w, v[u].w, ss[3]);
       }
-    }
-    for (; p < HW; p += rows) {
-      float4 v = ld4_as_float(x, dtype, (int64_t)b * bstride + (int64_t)p * C + q * 4);
-      s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
-      s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
-      s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
-      s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -143,36 +142,60 @@ __global__ void __launch_bounds__(256) gn_affine_small_kernel(const void* __rest
   }
 }
 
-// ---- GroupNorm + activation in ONE kernel for samples that fit in shared memory (<= 48 KB: the 8x8 / 7x15 latent-grid
-// layers of the propagator and coarse decoder): one CTA per sample stages it, reduces, normalises, writes.  Replaces
-// gn_affine_small + affine_act (two launches, two reads) when the consumer is a tcgen05 conv.
+// ---- GroupNorm + activation in ONE kernel for small samples (<= 16384 elements: the 8x8 / 7x15 latent-grid layers of the
+// propagator and coarse decoder): one CTA per sample copies the RAW sample into shared memory with cp.async (every byte in
+// flight at once, no conversion on the way in), reduces, normalises and writes.  Replaces gn_affine_small + affine_act (two
+// launches, two reads) when the consumer is a tcgen05 conv.  History: v1 staged fp32 with one dependent load per loop trip
+// (latency bound, 21 us for 16 MB); v2 kept the sample in registers with fully unrolled dtype/activation switches: 6 240
+// SASS instructions, 80 registers -> instruction-cache misses and 3 CTAs/SM made it 2x SLOWER (ncu: 27% no_instruction
+// stalls).  v3 (this): small loops, 16-26 KB of shared memory, 8 CTAs/SM.
+__device__ __forceinline__ float4 lds4_as_float(const void* p, int dtype, int i) {  // shared/generic memory, no __ldg
+  if (!is_h16(dtype)) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+  const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p) + i);
+  const float2 fa = unpack2_rt(dtype, raw.x), fb = unpack2_rt(dtype, raw.y);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
 __global__ void __launch_bounds__(256) gn_act_small_kernel(const void* __restrict__ x, int dtype, int HW, int C, int64_t bstride,
                                                             int G, float eps, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, const float* __restrict__ prescale,
-                                                            int act, void* __restrict__ y, int y_dtype, int64_t y_bstride) {
-  extern __shared__ float smf[];  // sample [HW*C] fp32, then red [rows][C][2], csum [C][2], ab [C][2]
-  float* xs = smf;
-  float* red = xs + (size_t)HW * C;
+                                                            int act, void* __restrict__ y, int y_dtype, int64_t y_bstride, double inv_n) {
+  extern __shared__ __align__(16) uint8_t smraw[];  // raw sample, then red [rows][C][2], csum [C][2], ab [C][2] (floats)
+  const int esz = dtype_size(dtype);
+  const int nbytes = HW * C * esz;
+  float* red = reinterpret_cast<float*>(smraw + ((nbytes + 15) & ~15));
   const int cg = C >> 2, rows = 256 / cg;
   float* csum = red + (size_t)rows * C * 2;
   float* ab = csum + (size_t)C * 2;
   const int b = blockIdx.x;
   const int q = threadIdx.x % cg, lane = threadIdx.x / cg;
+  {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(x) + (int64_t)b * bstride * esz;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smraw);
+    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)nbytes) & 15) == 0) {
+      for (int o = threadIdx.x * 16; o < nbytes; o += 256 * 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
+    } else {  // C % 4 == 0 and batch strides % 4 == 0 guarantee 8-byte granularity
+      for (int o = threadIdx.x * 8; o < nbytes; o += 256 * 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + o), "l"(src + o) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
   float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-  if (lane < rows) {
-    for (int p = lane; p < HW; p += rows) {
-      float4 v = ld4_as_float(x, dtype, (int64_t)b * bstride + (int64_t)p * C + q * 4);
-      *reinterpret_cast<float4*>(xs + (size_t)p * C + q * 4) = v;
-      s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
-      s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
-      s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
-      s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
-    }
+#pragma unroll 2
+  for (int p = lane; p < HW; p += rows) {  // same accumulation order as the statistics kernels: p = lane, lane + rows, ...
+    const float4 v = lds4_as_float(smraw, dtype, p * C + q * 4);
+    s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
+    s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
+    s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
+    s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
+  }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      red[((lane * C) + q * 4 + j) * 2 + 0] = s[j];
-      red[((lane * C) + q * 4 + j) * 2 + 1] = ss[j];
-    }
+  for (int j = 0; j < 4; ++j) {
+    red[((lane * C) + q * 4 + j) * 2 + 0] = s[j];
+    red[((lane * C) + q * 4 + j) * 2 + 1] = ss[j];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
@@ -187,46 +210,81 @@ __global__ void __launch_bounds__(256) gn_act_small_kernel(const void* __restric
   __syncthreads();
   const int cpg = C / G;
   const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
-  for (int gi = warp; gi < G; gi += 8) {  // one warp per group
-    double sum = 0.0, sumsq = 0.0;
-    for (int j = wl; j < cpg; j += 32) {
-      int c = gi * cpg + j;
-      double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
-      sum += ps * (double)csum[c * 2 + 0];
-      sumsq += ps * ps * (double)csum[c * 2 + 1];
+  if (cpg <= 16) {
+    // narrow groups (GroupNorm(32, C)): one THREAD per group, channels in order (a warp per group would spend ten 64-bit
+    // shuffles to add 2-4 numbers, four groups in sequence per warp)
+    for (int gi = threadIdx.x; gi < G; gi += 256) {
+      double sum = 0.0, sumsq = 0.0;
+      for (int j = 0; j < cpg; ++j) {
+        const int c = gi * cpg + j;
+        const double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
+        sum += ps * (double)csum[c * 2 + 0];
+        sumsq += ps * ps * (double)csum[c * 2 + 1];
+      }
+      const double mean = sum * inv_n;
+      double var = sumsq * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double ve = var + (double)eps;
+      double rstd = (double)rsqrtf((float)ve);
+      rstd = rstd * (1.5 - 0.5 * ve * rstd * rstd);
+      rstd = rstd * (1.5 - 0.5 * ve * rstd * rstd);
+      for (int j = 0; j < cpg; ++j) {
+        const int c = gi * cpg + j;
+        const double ga = gamma ? (double)gamma[c] : 1.0;
+        const double be = beta ? (double)beta[c] : 0.0;
+        const double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
+        ab[c * 2 + 0] = (float)(ps * rstd * ga);
+        ab[c * 2 + 1] = (float)(be - mean * rstd * ga);
+      }
     }
-    sum = warp_sum_d(sum);
-    sumsq = warp_sum_d(sumsq);
-    double n = (double)cpg * (double)HW;
-    double mean = sum / n;
-    double var = sumsq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    double rstd = 1.0 / sqrt(var + (double)eps);
-    for (int j = wl; j < cpg; j += 32) {
-      int c = gi * cpg + j;
-      double ga = gamma ? (double)gamma[c] : 1.0;
-      double be = beta ? (double)beta[c] : 0.0;
-      double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
-      ab[c * 2 + 0] = (float)(ps * rstd * ga);
-      ab[c * 2 + 1] = (float)(be - mean * rstd * ga);
+  } else {
+    for (int gi = warp; gi < G; gi += 8) {  // wide groups (GroupNorm(1, C)): one warp per group
+      double sum = 0.0, sumsq = 0.0;
+      for (int j = wl; j < cpg; j += 32) {
+        int c = gi * cpg + j;
+        double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
+        sum += ps * (double)csum[c * 2 + 0];
+        sumsq += ps * ps * (double)csum[c * 2 + 1];
+      }
+      sum = warp_sum_d(sum);
+      sumsq = warp_sum_d(sumsq);
+      // (fp64 divide / sqrt are ~500-cycle software sequences on the critical path of every CTA: reciprocal count from the
+      //  host, rsqrt seeded in fp32 and refined by two Newton steps in fp64 -> relative error < 1e-15)
+      double mean = sum * inv_n;
+      double var = sumsq * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double ve = var + (double)eps;
+      double rstd = (double)rsqrtf((float)ve);
+      rstd = rstd * (1.5 - 0.5 * ve * rstd * rstd);
+      rstd = rstd * (1.5 - 0.5 * ve * rstd * rstd);
+      for (int j = wl; j < cpg; j += 32) {
+        int c = gi * cpg + j;
+        double ga = gamma ? (double)gamma[c] : 1.0;
+        double be = beta ? (double)beta[c] : 0.0;
+        double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
+        ab[c * 2 + 0] = (float)(ps * rstd * ga);
+        ab[c * 2 + 1] = (float)(be - mean * rstd * ga);
+      }
     }
   }
   __syncthreads();
-  if (lane < rows) {
-    float sc[4], sh[4];
+  float sc[4], sh[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sc[j] = ab[(q * 4 + j) * 2 + 0];
-      sh[j] = ab[(q * 4 + j) * 2 + 1];
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = ab[(q * 4 + j) * 2 + 0];
+    sh[j] = ab[(q * 4 + j) * 2 + 1];
+  }
+  const bool fast = is_h16(y_dtype);
+#pragma unroll 2
+  for (int p = lane; p < HW; p += rows) {
+    float4 v = lds4_as_float(smraw, dtype, p * C + q * 4);
+    v.x = fmaf(v.x, sc[0], sh[0]); v.y = fmaf(v.y, sc[1], sh[1]); v.z = fmaf(v.z, sc[2], sh[2]); v.w = fmaf(v.w, sc[3], sh[3]);
+    if (fast) {
+      v.x = apply_act_fast(v.x, act); v.y = apply_act_fast(v.y, act); v.z = apply_act_fast(v.z, act); v.w = apply_act_fast(v.w, act);
+    } else {
+      v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
     }
-    for (int p = lane; p < HW; p += rows) {
-      float4 v = *reinterpret_cast<const float4*>(xs + (size_t)p * C + q * 4);
-      v.x = apply_act_for(fmaf(v.x, sc[0], sh[0]), act, y_dtype);
-      v.y = apply_act_for(fmaf(v.y, sc[1], sh[1]), act, y_dtype);
-      v.z = apply_act_for(fmaf(v.z, sc[2], sh[2]), act, y_dtype);
-      v.w = apply_act_for(fmaf(v.w, sc[3], sh[3]), act, y_dtype);
-      st4_from_float(y, y_dtype, (int64_t)b * y_bstride + (int64_t)p * C + q * 4, v);
-    }
+    st4_from_float(y, y_dtype, (int64_t)b * y_bstride + (int64_t)p * C + q * 4, v);
   }
 }
 
@@ -255,8 +313,7 @@ int lns_pointwise_proj(const void* x, int dtype, int B, int HW, int C, int64_t x
 int lns_group_norm_act_supported(int H, int W, int C) {
   int cg = C / 4;
   if (C % 4 != 0 || C < 4 || C > 1024 || (cg & (cg - 1)) != 0) return 0;
-  size_t smem = ((size_t)H * W * C + (size_t)(256 / cg) * C * 2 + 4 * (size_t)C) * sizeof(float);
-  return smem <= 48 * 1024;
+  return (int64_t)H * W * C <= 16384;  // <= 64 KB of shared memory as fp32, 32 KB as bf16 / f16
 }
 
 int lns_group_norm_act(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int G, float eps,
@@ -267,9 +324,12 @@ int lns_group_norm_act(const void* x, int dtype, int B, int H, int W, int C, int
               "lns_group_norm_affine + lns_affine_act)", H, W, C);
   LNS_REQUIRE(bstride % 4 == 0 && y_bstride % 4 == 0, "lns_group_norm_act: batch strides must be multiples of 4");
   int cg = C / 4;
-  size_t smem = ((size_t)H * W * C + (size_t)(256 / cg) * C * 2 + 4 * (size_t)C) * sizeof(float);
+  const int rows = 256 / cg;
+  size_t smem = (((size_t)H * W * C * lns::dtype_size(dtype) + 15) & ~(size_t)15) + ((size_t)rows * C * 2 + 4 * (size_t)C) * sizeof(float);
+  { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::gn_act_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); once = true; } }
   lns::gn_act_small_kernel<<<B, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, dtype, H * W, C, bstride, G, eps, gamma,
-                                                                                      beta, prescale, act, y, y_dtype, y_bstride);
+                                                                                      beta, prescale, act, y, y_dtype, y_bstride,
+                                                                                      1.0 / ((double)(C / G) * (double)H * (double)W));
   return lns::check_launch("gn_act_small_kernel");
 }
 
