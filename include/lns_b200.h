@@ -209,6 +209,18 @@ int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, in
 int lns_fablock_core(const void* u, int dtype, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
                      const float* w_in_proj, const float* Kx, const float* Ky, float eps, void* out, void* stream);
 
+/* FABlock2D in ONE kernel per sample (csrc/fablock_full.cu): lns_fablock_core's phases with the InstanceNorm2d folded into
+ * to_out[1] and BOTH 1x1 convolutions of to_out on tcgen05 -- the fp32 accumulator of all H*W pixels x 64 output channels
+ * stays in tensor memory across the heads, the [H][W][heads*64] tensor never exists in HBM:
+ *   out = Conv1x1_2( GELU( Conv1x1_1( InstanceNorm( Ky . Kx . in_proj(GN(u)) ) ) ) ) + u
+ * (modules/factorized_attention.py:146-159 except the pooled branch that produces Kx, Ky).  w_out1: to_out.1.weight
+ * [64][heads*64] fp32, w_out2: to_out.3.weight [64][64] fp32 (neither has a bias in the reference).  u/out NHWC
+ * [B][H][W][64], LNS_BF16 or LNS_F16.  Needs H, W <= 32 (H * ceil8(W) <= 1024 pixel rows = 512 TMEM columns). */
+int lns_fablock_full_supported(int H, int W, int dim, int dim_head, int dim_out);
+int lns_fablock_full(const void* u, int dtype, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
+                     const float* w_in_proj, const float* Kx, const float* Ky, float eps, const float* w_out1,
+                     const float* w_out2, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * layout / misc
  * ------------------------------------------------------------------------------------------------ */

@@ -621,6 +621,27 @@ def fablock_core(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps):
     return out
 
 
+def fablock_full_supported(x, dim_head, dim_out):
+    return (x.t.dtype in H16_DTYPES and x.layout == NHWC and x.contiguous
+            and bool(_C.lib().lns_fablock_full_supported(x.H, x.W, x.C, dim_head, dim_out)))
+
+
+def fablock_full(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps, w_out1, w_out2):
+    """Whole FABlock2D after the pooled branch in one kernel per sample (16-bit paths): Act [B,H,W,64] -> Act [B,H,W,64]
+    = to_out(InstanceNorm(Ky . Kx . in_proj(GN(u)))) + u, with to_out's two 1x1 convs on tcgen05 / TMEM."""
+    out = u.like()
+    wi = w_in_proj.detach().float().contiguous()
+    w1 = w_out1.detach().float().reshape(w_out1.shape[0], -1).contiguous()
+    w2 = w_out2.detach().float().reshape(w_out2.shape[0], -1).contiguous()
+    tok = _mark(f"fablock_full @{u.H}x{u.W}")
+    rc = _C.lib().lns_fablock_full(_ptr(u.t), u.dtype, u.B, u.H, u.W, heads, _ptr(gn_scale), _ptr(gn_shift), _ptr(wi), _ptr(Kx),
+                                   _ptr(Ky), float(eps), _ptr(w1), _ptr(w2), _ptr(out.t), _stream())
+    check(rc, "lns_fablock_full")
+    _done(tok)
+    _state.launches += 1
+    return out
+
+
 # ---- misc ----------------------------------------------------------------------------------------------------
 def fourier_embedding(param, dim, max_period=10000.0):
     """param: torch fp32 [B] on CUDA -> torch fp32 [B, dim]"""

@@ -132,6 +132,12 @@ class FABlock2D(LnsModule):
         py = ops.conv2d(my, filt_of(self.to_in[0]), out_dtype=pd)   # rows indexed by W
         k_x = self.low_rank_kernel_x._fwd(self.to_x[0]._fwd(px))
         k_y = self.low_rank_kernel_y._fwd(self.to_y[1]._fwd(py))
+        if (fused and self.to_out[1].bias is None and self.to_out[3].bias is None
+                and ops.fablock_full_supported(u, self.dim_head, self.to_out[3].out_channels)
+                and self.to_out[1].out_channels == 64):
+            # everything up to the block output in one kernel per sample: to_out's convs on tcgen05, accumulators in TMEM
+            return ops.fablock_full(u, s, t, self.in_proj.weight, k_x, k_y, self.heads, inorm.eps, self.to_out[1].weight,
+                                    self.to_out[3].weight)
         if fused:
             # in_proj -> contraction over H -> contraction over W -> InstanceNorm, u_phi stays in shared memory
             u_n = ops.fablock_core(u, s, t, self.in_proj.weight, k_x, k_y, self.heads, inorm.eps)

@@ -429,7 +429,7 @@ def test_pointwise_projection(dtype):
     assert float(out[:, 0].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("H,W", [(16, 16), (32, 32), (24, 48), (12, 20)])
+@pytest.mark.parametrize("H,W", [(16, 16), (32, 32), (24, 48), (12, 20), (8, 8), (30, 17)])
 def test_fablock_fused_vs_unfused_and_oracle(H, W):
     """Fused FABlock2D core (shared-memory resident u_phi) == the unfused kernel sequence (bf16 tolerance) and agrees
     with the fp64 oracle of the reference block at bf16 accuracy."""
@@ -445,18 +445,20 @@ def test_fablock_fused_vs_unfused_and_oracle(H, W):
     a = act_from(x, torch.bfloat16)
     assert ops.fablock_core_supported(a, 64)
     with torch.no_grad(), ops.precision("bf16"):
-        fused = act_to_nchw(blk._fwd(a))
-        # force the unfused path
-        orig = ops.fablock_core_supported
-        ops.fablock_core_supported = lambda *aa, **kk: False
+        fused = act_to_nchw(blk._fwd(a))  # whole-block kernel (fablock_full) when H, W <= 32, else the fused core
+        orig_full, orig = ops.fablock_full_supported, ops.fablock_core_supported
+        ops.fablock_full_supported = lambda *aa, **kk: False
         try:
+            core = act_to_nchw(blk._fwd(a))  # fused core + two conv launches
+            ops.fablock_core_supported = lambda *aa, **kk: False
             unfused = act_to_nchw(blk._fwd(a))
         finally:
-            ops.fablock_core_supported = orig
-    e_f, e_u = relerr(fused, ref), relerr(unfused, ref)
-    print(f"\\n[FABlock2D {H}x{W} bf16] fused vs fp64 oracle {e_f:.2e}, unfused {e_u:.2e}, fused vs unfused {relerr(fused, unfused):.2e}")
-    assert e_f < 3e-2 and e_u < 3e-2
-    assert relerr(fused, unfused) < 2e-2
+            ops.fablock_full_supported, ops.fablock_core_supported = orig_full, orig
+    e_f, e_c, e_u = relerr(fused, ref), relerr(core, ref), relerr(unfused, ref)
+    print(f"[FABlock2D {H}x{W} bf16] whole-block kernel vs fp64 oracle {e_f:.2e}, fused core {e_c:.2e}, unfused {e_u:.2e}, "
+          f"whole-block vs unfused {relerr(fused, unfused):.2e}")
+    assert e_f < 3e-2 and e_c < 3e-2 and e_u < 3e-2
+    assert relerr(fused, unfused) < 2e-2 and relerr(core, unfused) < 2e-2
 
 
 @pytest.mark.parametrize("n", [16, 32, 24, 48, 15])
@@ -631,12 +633,14 @@ def test_fablock_fused_f16(H, W):
     assert ops.fablock_core_supported(a, 64)
     with torch.no_grad(), ops.precision("fp16"):
         fused = act_to_nchw(blk._fwd(a))
-        orig = ops.fablock_core_supported
-        ops.fablock_core_supported = lambda *aa, **kk: False
+        orig_full, orig = ops.fablock_full_supported, ops.fablock_core_supported
+        ops.fablock_full_supported = lambda *aa, **kk: False
         try:
+            core = act_to_nchw(blk._fwd(a))
+            ops.fablock_core_supported = lambda *aa, **kk: False
             unfused = act_to_nchw(blk._fwd(a))
         finally:
-            ops.fablock_core_supported = orig
-    e_f, e_u = relerr(fused, ref), relerr(unfused, ref)
-    print(f"\n[FABlock2D {H}x{W} f16] fused vs fp64 oracle {e_f:.2e}, unfused {e_u:.2e}, fused vs unfused {relerr(fused, unfused):.2e}")
-    assert e_f < 4e-3 and e_u < 4e-3
+            ops.fablock_full_supported, ops.fablock_core_supported = orig_full, orig
+    e_f, e_c, e_u = relerr(fused, ref), relerr(core, ref), relerr(unfused, ref)
+    print(f"[FABlock2D {H}x{W} f16] whole-block kernel vs fp64 oracle {e_f:.2e}, fused core {e_c:.2e}, unfused {e_u:.2e}")
+    assert e_f < 4e-3 and e_c < 4e-3 and e_u < 4e-3
