@@ -209,6 +209,18 @@ int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, in
 int lns_fablock_core(const void* u, int dtype, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
                      const float* w_in_proj, const float* Kx, const float* Ky, float eps, void* out, void* stream);
 
+/* FABlock2D pooled branch of one axis in ONE kernel (csrc/fa_axis.cu): pooled [B][n][64] fp32 (lns_fablock_prepass) ->
+ * K [B][heads][n][n] fp32.  Replaces to_in (1x1 conv), PoolingReducer (Linear, LayerNorm, Linear+GELU, Linear+bias),
+ * LowRankKernel.to_qk, the rotary embedding and q k^T (modules/factorized_attention.py:43-94,114-121).  Host-prepared
+ * operands: w1t [64][64] = (reducer.to_in.weight @ to_in.weight)^T (the two bias-free linears composed), wf1t [64][128] and
+ * wf2t [128][64] = out_ffn.1 / out_ffn.3 weights transposed, bf2 [64], wqk16 [2*heads*128][64] = to_qk.weight as LNS_BF16 or
+ * LNS_F16 (dtype16), cos/sin tables [n][64] as for lns_lowrank_kernel.  The small layers run in fp32, to_qk and q k^T on
+ * tensor cores with 16-bit operands.  Needs dim = hidden = latent = 64, dim_head*kernel_multiplier = 128, n <= 64. */
+int lns_fa_axis_kernel_supported(int n, int dim, int hidden, int latent, int heads, int d);
+int lns_fa_axis_kernel(const float* pooled, int dtype16, int B, int n, int heads, const float* w1t, const float* ln_g,
+                       const float* ln_b, float ln_eps, const float* wf1t, const float* wf2t, const float* bf2,
+                       const void* wqk16, const float* cos_tab, const float* sin_tab, float scaling, float* K, void* stream);
+
 /* FABlock2D in ONE kernel per sample (csrc/fablock_full.cu): lns_fablock_core's phases with the InstanceNorm2d folded into
  * to_out[1] and BOTH 1x1 convolutions of to_out on tcgen05 -- the fp32 accumulator of all H*W pixels x 64 output channels
  * stays in tensor memory across the heads, the [H][W][heads*64] tensor never exists in HBM:

@@ -621,6 +621,25 @@ def fablock_core(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps):
     return out
 
 
+def fa_axis_kernel_supported(n, dim, hidden, latent, heads, d):
+    return bool(_C.lib().lns_fa_axis_kernel_supported(n, dim, hidden, latent, heads, d))
+
+
+def fa_axis_kernel(pooled, heads, w1t, ln_g, ln_b, ln_eps, wf1t, wf2t, bf2, wqk16, cos_tab, sin_tab, scaling=1.0):
+    """Pooled branch of one FABlock2D axis in one kernel: pooled Act [B,n,1,64] fp32 -> torch fp32 [B, heads, n, n]."""
+    assert pooled.contiguous and pooled.t.dtype == torch.float32 and pooled.C == 64
+    n = pooled.H * pooled.W
+    K = torch.empty(pooled.B, heads, n, n, dtype=torch.float32, device=pooled.t.device)
+    tok = _mark("fa_axis")
+    rc = _C.lib().lns_fa_axis_kernel(_ptr(pooled.t), dt_code(wqk16.dtype), pooled.B, n, heads, _ptr(w1t), _ptr(ln_g), _ptr(ln_b),
+                                     float(ln_eps), _ptr(wf1t), _ptr(wf2t), _ptr(bf2), _ptr(wqk16), _ptr(cos_tab), _ptr(sin_tab),
+                                     float(scaling), _ptr(K), _stream())
+    check(rc, "lns_fa_axis_kernel")
+    _done(tok)
+    _state.launches += 1
+    return K
+
+
 def fablock_full_supported(x, dim_head, dim_out):
     return (x.t.dtype in H16_DTYPES and x.layout == NHWC and x.contiguous
             and bool(_C.lib().lns_fablock_full_supported(x.H, x.W, x.C, dim_head, dim_out)))

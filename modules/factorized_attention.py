@@ -127,11 +127,63 @@ class FABlock2D(LnsModule):
         # mean over the other axis first (exact: to_in convs have no bias), then the two tiny linears.  On the bf16 path the
         # pooled branch is stored in bf16 from here on, so that its 64/128-wide linears run on the tensor-core engine
         # (on the CUDA-core engine they were 8 % of the rollout).
+        if fused:
+            kk = self._axis_kernels(mx, my)
+            if kk is not None:
+                return self._finish(u, skip, s, t, kk[0], kk[1], inorm, fused)
         pd = ops.act_dtype() if fused else f32
         px = ops.conv2d(mx, filt_of(self.to_in[0]), out_dtype=pd)   # rows indexed by H
         py = ops.conv2d(my, filt_of(self.to_in[0]), out_dtype=pd)   # rows indexed by W
         k_x = self.low_rank_kernel_x._fwd(self.to_x[0]._fwd(px))
         k_y = self.low_rank_kernel_y._fwd(self.to_y[1]._fwd(py))
+        return self._finish(u, skip, s, t, k_x, k_y, inorm, fused, un=None if fused else un)
+
+    def _axis_operands(self, reducer, lrk, dt16):
+        """Host-prepared operands of lns_fa_axis_kernel for one axis, cached until a source parameter changes."""
+        srcs = [self.to_in[0].weight, reducer.to_in.weight, reducer.out_ffn[0].weight, reducer.out_ffn[0].bias,
+                reducer.out_ffn[1].weight, reducer.out_ffn[3].weight, reducer.out_ffn[3].bias, lrk.to_qk.weight]
+        key = (dt16,) + tuple((t.data_ptr(), t._version, str(t.device)) for t in srcs)
+        cache = self.__dict__.setdefault("_lns_axis", {})
+        ent = cache.get(id(reducer))
+        if ent is None or ent[0] != key:
+            with torch.no_grad():
+                w_in = self.to_in[0].weight.detach().double().reshape(self.dim, self.dim)
+                w1 = reducer.to_in.weight.detach().double() @ w_in          # both bias-free: one 64x64 linear
+                ops_ = dict(
+                    w1t=w1.t().contiguous().float(),
+                    ln_g=reducer.out_ffn[0].weight.detach().float().contiguous(),
+                    ln_b=reducer.out_ffn[0].bias.detach().float().contiguous(),
+                    wf1t=reducer.out_ffn[1].weight.detach().float().t().contiguous(),
+                    wf2t=reducer.out_ffn[3].weight.detach().float().t().contiguous(),
+                    bf2=reducer.out_ffn[3].bias.detach().float().contiguous(),
+                    wqk16=lrk.to_qk.weight.detach().to(dt16).contiguous())
+            ent = (key, ops_)
+            cache[id(reducer)] = ent
+        return ent[1]
+
+    def _axis_kernels(self, mx, my):
+        """(K_x, K_y) through the one-kernel-per-axis pooled branch, or None when the block's shape is not covered."""
+        rx, ry = self.to_x[0], self.to_y[1]
+        lx, ly = self.low_rank_kernel_x, self.low_rank_kernel_y
+        ok = (not lx.qk_norm and not ly.qk_norm
+              and rx.out_ffn[1].bias is None and rx.out_ffn[3].bias is not None
+              and ry.out_ffn[1].bias is None and ry.out_ffn[3].bias is not None
+              and rx.out_ffn[1].out_features == 128 and ry.out_ffn[1].out_features == 128
+              and rx.to_in.out_features == 64 and ry.to_in.out_features == 64
+              and ops.fa_axis_kernel_supported(max(mx.H, my.H), self.dim, 64, self.latent_dim, self.heads, lx.dim_head)
+              and lx.dim_head == ly.dim_head and lx.heads == self.heads and ly.heads == self.heads)
+        if not ok:
+            return None
+        dt16 = ops.act_dtype()
+        out = []
+        for pooled, red, lrk in ((mx, rx, lx), (my, ry, ly)):
+            o = self._axis_operands(red, lrk, dt16)
+            cos_t, sin_t = lrk._tables(pooled.H * pooled.W, pooled.t.device)
+            out.append(ops.fa_axis_kernel(pooled, self.heads, o["w1t"], o["ln_g"], o["ln_b"], red.out_ffn[0].eps, o["wf1t"],
+                                          o["wf2t"], o["bf2"], o["wqk16"], cos_t, sin_t, lrk.scaling))
+        return out
+
+    def _finish(self, u, skip, s, t, k_x, k_y, inorm, fused, un=None):
         if (fused and self.to_out[1].bias is None and self.to_out[3].bias is None
                 and ops.fablock_full_supported(u, self.dim_head, self.to_out[3].out_channels)
                 and self.to_out[1].out_channels == 64):

@@ -644,3 +644,36 @@ def test_fablock_fused_f16(H, W):
     e_f, e_c, e_u = relerr(fused, ref), relerr(core, ref), relerr(unfused, ref)
     print(f"[FABlock2D {H}x{W} f16] whole-block kernel vs fp64 oracle {e_f:.2e}, fused core {e_c:.2e}, unfused {e_u:.2e}")
     assert e_f < 4e-3 and e_c < 4e-3 and e_u < 4e-3
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("H,W,B", [(32, 32, 5), (16, 16, 9), (12, 20, 3), (48, 24, 2)])
+def test_fa_axis_kernel_vs_fp64(H, W, B, prec):
+    """One-kernel pooled branch (to_in -> PoolingReducer -> to_qk -> rotary -> q k^T) vs the same chain in fp64 torch"""
+    ops = ops_mod()
+    from modules.factorized_attention import FABlock2D
+    torch.manual_seed(5)
+    blk = FABlock2D(64, 64, 64, 8, 64).to(DEV).eval()
+    g = torch.Generator().manual_seed(43)
+    results = []
+    with torch.no_grad(), ops.precision(prec):
+        mx = ops.Act(torch.randn(B * H * 64, generator=g).to(DEV), B, H, 1, 64)
+        my = ops.Act(torch.randn(B * W * 64, generator=g).to(DEV), B, W, 1, 64)
+        kk = blk._axis_kernels(mx, my)
+        assert kk is not None
+        for pooled, red, lrk, K in ((mx, blk.to_x[0], blk.low_rank_kernel_x, kk[0]), (my, blk.to_y[1], blk.low_rank_kernel_y, kk[1])):
+            n = pooled.H
+            x = pooled.t.view(B, n, 64).double().cpu()
+            w = lambda t: t.detach().double().cpu()
+            t1 = x @ w(blk.to_in[0].weight).view(64, 64).t() @ w(red.to_in.weight).t()
+            t1 = F.layer_norm(t1, (64,), w(red.out_ffn[0].weight), w(red.out_ffn[0].bias), red.out_ffn[0].eps)
+            z = F.gelu(t1 @ w(red.out_ffn[1].weight).t()) @ w(red.out_ffn[3].weight).t() + w(red.out_ffn[3].bias)
+            qk = z @ w(lrk.to_qk.weight).t()
+            q, k = [v.view(B, n, 8, 128).transpose(1, 2) for v in qk.split(1024, dim=-1)]
+            cos_t, sin_t = [v.double().cpu() for v in lrk._tables(n, DEV)]
+            rot = lambda v: torch.cat([v[..., :64] * cos_t - v[..., 64:] * sin_t, v[..., 64:] * cos_t + v[..., :64] * sin_t], -1)
+            ref = rot(q) @ rot(k).transpose(-1, -2)
+            assert tuple(K.shape) == (B, 8, n, n)
+            results.append(relerr(K.cpu(), ref))
+    print(f"[fa_axis {H}x{W} {prec}] K_x {results[0]:.2e} K_y {results[1]:.2e}")
+    assert max(results) < (6e-3 if prec == "bf16" else 8e-4)
