@@ -93,6 +93,29 @@ def cpu_reference_throughput(workload, budget_s=20.0, min_runs=2, max_runs=5):
                       f"({best:.2f} s each), torch {torch.__version__} CPU, {cores} threads"}
 
 
+def parity_check(model, cfg, precision, device):
+    """Teacher-forced per-stage relative L2 of the GPU path (at `precision`) against the fp64 oracle on 2 trajectories: part of
+    the cpu_baseline leg (the oracle is only ever the checker).  Returns {"encode", "propagator_step", "decode"}."""
+    import torch
+    import lns_oracle as O
+    from lns_b200 import ops
+    sd64 = O.to_dtype({k: v.detach().cpu() for k, v in model.state_dict().items()}, torch.float64)
+    x, param = O.make_inputs(cfg, 2, seed=77)
+    ae = O.ae_name(cfg)
+    z_ref = O.encode(sd64, cfg, x.double(), ae)
+    cond = O.cond_embedding(sd64, cfg, param.double(), torch.float64) if param is not None else None
+    z1_ref = O.propagator_step(sd64, cfg, z_ref, cond)
+    y_ref = O.decode(sd64, cfg, z1_ref, ae)
+    with torch.no_grad(), ops.precision(precision):
+        z = model.autoencoder.encode(x.to(device))
+        z1 = model.propagator(z_ref.float().to(device)) if param is None else \
+            model.propagator(z_ref.float().to(device), param.to(device))
+        y = model.autoencoder.decode(z1_ref.float().to(device))
+    return {"vs": "fp64 oracle of the reference, teacher-forced per stage, 2 trajectories, max rel-L2",
+            "encode": float(O.rel_l2(z.cpu(), z_ref).max()), "propagator_step": float(O.rel_l2(z1.cpu(), z1_ref).max()),
+            "decode": float(O.rel_l2(y.cpu(), y_ref).max())}
+
+
 # ---- clocks ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -171,6 +194,75 @@ def conv_roofline(torch, ops, device, peaks, workload, precision="bf16"):
             "traffic": traffic, "algorithmic_bytes": nb * H * W * (Cin + Cout) * 2, "algorithmic_flops": flops,
             "avg_launch_ms": round(t * 1e3, 4), "peak_source": peaks["source"],
             "hbm_gbs_at_algorithmic_bytes": round(nb * H * W * (Cin + Cout) * 2 / t / 1e9, 1)}
+
+
+def time_share(pattern):
+    """share of the step's kernel time of kernels whose name contains `pattern`, from the committed ncu launch list"""
+    tp = os.path.join(ROOT, "profiles", "r01_launches_bench.txt")
+    if not os.path.exists(tp):
+        return None
+    tot = 0.0
+    for ln in open(tp):
+        parts = ln.split()
+        if len(parts) > 3 and parts[1] == "ms" and parts[2].endswith("%") and pattern in ln:
+            tot += float(parts[2].rstrip("%"))
+    return round(tot / 100.0, 4) if tot else None
+
+
+def kernels_by_time(torch, ops, device, peaks, roof):
+    """The three kernels with the largest share of the NS2d step's time, each timed alone (CUDA events, operands > L2 or
+    one CTA wave per SM) against the measured bf16 tensor peak.  Shares come from profiles/r01_launches_bench.txt."""
+    import math
+    out = []
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        return sum(ev[i].elapsed_time(ev[i + 1]) for i in range(reps)) / reps * 1e-3
+
+    with torch.no_grad(), ops.precision("bf16"):
+        # FABlock2D whole-block kernel, 32x32, 4096 samples (one decode chunk)
+        nb, H, W = 4096, 32, 32
+        u = ops.Act(torch.randn(nb * H * W * 64, device=device).bfloat16(), nb, H, W, 64)
+        sc, sh = torch.rand(nb * 64, device=device) + 0.5, torch.randn(nb * 64, device=device) * 0.1
+        w = torch.nn.Parameter(torch.randn(512, 64, device=device) / 8)
+        w1 = torch.nn.Parameter(torch.randn(64, 512, 1, 1, device=device) / 22)
+        w2 = torch.nn.Parameter(torch.randn(64, 64, 1, 1, device=device) / 8)
+        kx = torch.randn(nb, 8, H, H, device=device) / H ** 0.5
+        ky = torch.randn(nb, 8, W, W, device=device) / W ** 0.5
+        t = timed(lambda: ops.fablock_full(u, sc, sh, w, kx, ky, 8, 1e-5, w1, w2))
+        fl = nb * (2.0 * H * W * 64 * 512 * 2 + 2.0 * 8 * (H * H * W + H * W * W) * 64 + 2.0 * H * W * 64 * 64)
+        by = nb * (2 * H * W * 64 * 2 + 8 * (H * H + W * W) * 4)
+        out.append({"kernel": "fablock_full_kernel<512> (FABlock2D per sample, mma.sync phases + tcgen05 to_out, TMEM-resident "
+                              "accumulator) 32x32, batch 4096", "share_of_step": time_share("fablock_full_kernel"),
+                    "bound": "tensor", "achieved": round(fl / t / 1e12, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": round(fl / t / 1e12 / peaks["bf16_tflops"], 4), "avg_launch_ms": round(t * 1e3, 4),
+                    "algorithmic_bytes": by, "hbm_gbs_at_algorithmic_bytes": round(by / t / 1e9, 1)})
+        del u, kx, ky
+        # propagator conv: 3x3 128->128 circular @ 8x8, 1024 trajectories (gather engine)
+        nb, H, W, C = 1024, 8, 8, 128
+        x = ops.Act(torch.randn(nb * H * W * C, device=device).bfloat16(), nb, H, W, C)
+        wt = torch.nn.Parameter(torch.randn(C, C, 3, 3, device=device) / math.sqrt(9 * C))
+        bs = torch.nn.Parameter(torch.zeros(C, device=device))
+        filt = ops.PackedFilter.of(wt, bs)
+        y = ops.Act.empty(nb, H, W, C, torch.bfloat16, device)
+        t = timed(lambda: ops.conv2d(x, filt, pad=(1, 1, 1, 1), pad_mode=(1, 1), act=ops.ACT_GELU, out=y), reps=20)
+        fl = 2.0 * nb * H * W * C * 9 * C
+        out.append({"kernel": "conv_umma_kernel<128,3> (tcgen05 gather engine) 3x3 128->128 circular @ 8x8, batch 1024 "
+                              "(L2-resident: 17 MB in + 17 MB out)", "share_of_step": time_share("conv_umma_kernel<128"),
+                    "bound": "tensor", "achieved": round(fl / t / 1e12, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": round(fl / t / 1e12 / peaks["bf16_tflops"], 4), "avg_launch_ms": round(t * 1e3, 4)})
+    out.append({"kernel": roof["kernel"], "share_of_step": time_share("conv_halo_kernel"), "bound": "tensor",
+                "achieved": roof["achieved"], "peak": roof["peak"], "unit": "TFLOP/s", "frac": roof["frac"],
+                "avg_launch_ms": roof["avg_launch_ms"]})
+    return out
 
 
 # ---- main ---------------------------------------------------------------------------------------------------------------------
@@ -311,8 +403,11 @@ def main():
             "launches_per_step": int(ro.launches_per_call),
             "clocks": clocks, "roofline": roof,
         }
+        if roof is not None and args.workload == "ns2d" and args.precision == "bf16":
+            line["roofline_by_time"] = kernels_by_time(torch, ops, device, peaks, roof)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_throughput(args.workload, budget_s=15.0)
+            line["parity"] = parity_check(model, cfg, args.precision, device)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -254,6 +254,14 @@ int lns_fourier_embedding(const float* param, int B, int dim, float max_period, 
 int lns_channel_gate(const void* x, int dtype, int B, int HW, int C, const float* gate, void* y, int y_dtype,
                      void* stream);
 
+/* Validation metric right behind the path: per frame f = (trajectory, step, channel) of two fp32
+ * tensors laid out like the rollout result [B][K][C][Ly][Lx] (P = Ly*Lx contiguous values per frame):
+ *   out[f] = (sum (pred-target)^2, sum target^2, sum target)
+ * from which relative_lp_loss (training_utils.py:9-23, reduce_dim (3,4) frame-wise and (1,3,4) sequence-wise,
+ * train_stage2_ns2d.py:254-257) of the affinely de-normalised fields follows on the host without the fields ever leaving the
+ * device.  One read of both tensors, deterministic. */
+int lns_frame_sums(const float* pred, const float* target, int64_t frames, int P, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Spectral convolution (FNO layer) as truncated DFTs with the complex mode-weight multiply fused:
  *   rfft2 -> corner blocks [:m1,:m2], [-m1:,:m2] x weights (x per-sample complex emb) -> irfft2

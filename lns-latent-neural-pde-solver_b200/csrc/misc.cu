@@ -51,9 +51,68 @@ __global__ void fourier_embedding_kernel(const float* __restrict__ param, int B,
   }
 }
 
+// Validation metric partial sums, one read of prediction and target: for every frame f (a contiguous run of P fp32 values =
+// one (trajectory, step, channel) image) out[f] = (sum (a-b)^2, sum b^2, sum b).  relative_lp_loss (training_utils.py:9-23)
+// after the datasets' affine de-normalisation x*std + mean (dataset/ns2d_fno_stage2_simpleae.py:78-79) follows on the host:
+//   sum (a'-b')^2 = std^2 sum (a-b)^2,   sum b'^2 = std^2 sum b^2 + 2 std mean sum b + P mean^2.
+// grid F (frames), block 256; fixed-order reduction (deterministic).
+__global__ void __launch_bounds__(256) frame_sums_kernel(const float* __restrict__ a, const float* __restrict__ b, int P,
+                                                         float* __restrict__ out) {
+  __shared__ double red[8][3];
+  const int64_t base = (int64_t)blockIdx.x * P;
+  float d2 = 0.f, b2 = 0.f, b1 = 0.f;
+  if ((P & 3) == 0 && ((reinterpret_cast<uintptr_t>(a + base) | reinterpret_cast<uintptr_t>(b + base)) & 15) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(a + base);
+    const float4* b4 = reinterpret_cast<const float4*>(b + base);
+    for (int i = threadIdx.x; i < P / 4; i += 256 * 4) {  // 4 pairs of 16-byte loads in flight per thread
+      float4 va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = i + u * 256;
+        const bool ok = j < P / 4;
+        va[u] = ok ? __ldg(a4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[u] = ok ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float dx = va[u].x - vb[u].x, dy = va[u].y - vb[u].y, dz = va[u].z - vb[u].z, dw = va[u].w - vb[u].w;
+        d2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, d2))));
+        b2 = fmaf(vb[u].x, vb[u].x, fmaf(vb[u].y, vb[u].y, fmaf(vb[u].z, vb[u].z, fmaf(vb[u].w, vb[u].w, b2))));
+        b1 += (vb[u].x + vb[u].y) + (vb[u].z + vb[u].w);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < P; i += 256) {
+      const float x = __ldg(a + base + i), y = __ldg(b + base + i);
+      d2 = fmaf(x - y, x - y, d2);
+      b2 = fmaf(y, y, b2);
+      b1 += y;
+    }
+  }
+  double s0 = warp_sum_d((double)d2), s1 = warp_sum_d((double)b2), s2 = warp_sum_d((double)b1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[warp][0] = s0;
+    red[warp][1] = s1;
+    red[warp][2] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    out[(int64_t)blockIdx.x * 3 + threadIdx.x] = (float)t;
+  }
+}
+
 }  // namespace lns
 
 extern "C" {
+
+int lns_frame_sums(const float* pred, const float* target, int64_t frames, int P, float* out, void* stream) {
+  LNS_REQUIRE(pred && target && out && frames > 0 && P > 0 && frames < (1ll << 31), "lns_frame_sums: bad arguments");
+  lns::frame_sums_kernel<<<(unsigned)frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, target, P, out);
+  return lns::check_launch("frame_sums_kernel");
+}
 
 int lns_nchw_to_nhwc(const float* x, int B, int C, int H, int W, int64_t x_bstride, void* y, int y_dtype,
                      int64_t y_bstride, void* stream) {

@@ -212,3 +212,49 @@ def test_predict_api_matches_reference_signature():
         y = model.predict(x.to(DEV), 2, param.to(DEV), to_x=True)
     assert tuple(y.shape) == (2, 2, 4, 61, 121)
     assert torch.isfinite(y).all()
+
+
+def test_relative_l2_metric_matches_reference_formula():
+    """fused validation metric == relative_lp_loss of the de-normalised tensors
+    (training_utils.py:9-23 restated in fp64; reduce_dim (3,4) frame-wise and (1,3,4) sequence-wise)"""
+    from lns_b200 import metrics
+    g = torch.Generator().manual_seed(21)
+    for shape, mean, std in [((5, 7, 1, 64, 64), 0.3, 1.7), ((3, 4, 4, 61, 121), -0.2, 0.8), ((2, 3, 3, 96, 192), 0.0, 1.0)]:
+        gt = torch.randn(*shape, generator=g)
+        pred = gt + 0.05 * torch.randn(*shape, generator=g)
+        frame, seq = metrics.relative_l2(pred.to(DEV), gt.to(DEV), mean=mean, std=std)
+        a, b = pred.double() * std + mean, gt.double() * std + mean
+
+        def ref(reduce_dim):
+            gt_norm = (b ** 2).sum(dim=reduce_dim).clamp_min(1e-8)
+            return (((a - b) ** 2).sum(dim=reduce_dim) / gt_norm).sqrt()
+        assert torch.allclose(frame.cpu().double(), ref((3, 4)), rtol=2e-5, atol=0)
+        assert torch.allclose(seq.cpu().double(), ref((1, 3, 4)), rtol=2e-5, atol=0)
+    with pytest.raises(ops_mod().LnsError):
+        metrics.frame_sums(torch.zeros(1, 1, 1, 4, 4), torch.zeros(1, 1, 1, 4, 4))  # CPU tensors: no fallback
+
+
+def test_encode_frames_bulk_equals_direct_encode():
+    """bulk pre-encode: chunked, stream-overlapped encode == one direct encode call, bit for bit, and
+    matches the fp64 oracle of the reference encoder at the fp32 bar"""
+    from lns_b200.encode import encode_frames, encode_dataset
+    ops = ops_mod()
+    cfg, model, sd = build("ns2d")
+    g = torch.Generator().manual_seed(23)
+    raw = torch.randn(37, 1, 64, 64, generator=g) * 2.5 + 0.7
+    mean, std = 0.7, 2.5
+    with torch.no_grad(), ops.precision("fp32"):
+        z_bulk = encode_frames(model.autoencoder, raw.numpy(), chunk=8, mean=mean, std=std)
+        xin = raw.to(DEV) * (1.0 / (std + 1e-8)) + (-mean / (std + 1e-8))
+        z_direct = model.autoencoder.encode(xin).cpu().numpy()
+    assert z_bulk.shape == (37, 16, 8, 8)
+    assert (z_bulk == z_direct).all()
+    sd64 = O.to_dtype(sd, torch.float64)
+    z_ref = O.encode(sd64, cfg, (raw.double() - mean) / (std + 1e-8), O.ae_name(cfg))
+    assert O.rel_l2(torch.from_numpy(z_bulk), z_ref).max().item() < 1e-5
+    # the reference's NS2d dataset layout [T, H, W, cases] -> list of [T, Cz, h, w]
+    data = raw[:36, 0].reshape(4, 9, 64, 64).permute(1, 2, 3, 0).numpy()  # 4 cases of 9 frames
+    with torch.no_grad(), ops.precision("fp32"):
+        enc = encode_dataset(model.autoencoder, data, mean, std, chunk=16)
+    assert len(enc) == 4 and enc[0].shape == (9, 16, 8, 8)
+    assert (enc[2] == z_direct[18:27]).all()
