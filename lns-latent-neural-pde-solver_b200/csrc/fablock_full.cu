@@ -89,6 +89,14 @@ __device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r
 __device__ __forceinline__ void ldsm_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// four 8x8 16-bit matrices: lanes 8k..8k+7 give the row addresses of matrix k, register k of lane L holds row L/4, columns
+// 2*(L%4), +1 of matrix k -- exactly a packed mma accumulator fragment
+__device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
 template <bool F16>
 __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   if (F16)
@@ -138,12 +146,14 @@ __device__ __forceinline__ void contract_line_sw(uint32_t U_a, int line, int Wp,
     j = j < n ? j : n - 1;  // padded k rows: multiplied by the zero-padded kernel columns
     const int p = slot(j);
     const uint32_t rowa = U_a + (uint32_t)p * 128u;
-    const int ph = p & 7;
+    const int ph = p & 7, hi = lane >> 4;  // lanes 16-31 address the next channel chunk: two B fragments per ldmatrix.x4
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) fptx::ldsm_x2_trans(rowa + (uint32_t)((nt ^ ph) << 4), bf[kt][nt][0], bf[kt][nt][1]);
+    for (int nt = 0; nt < 8; nt += 2)
+      fptx::ldsm_x4_trans(rowa + (uint32_t)(((nt + hi) ^ ph) << 4), bf[kt][nt][0], bf[kt][nt][1], bf[kt][nt + 1][0], bf[kt][nt + 1][1]);
   }
   __syncwarp();
   const int g = lane >> 2, t = lane & 3;
+  const bool full = (n & 15) == 0;  // every 16-row tile complete: whole-fragment stmatrix stores (4 matrices per instruction)
 #pragma unroll
   for (int mt = 0; mt < KT; ++mt) {
     const int i0 = mt * 16 + g, i1 = i0 + 8;
@@ -151,6 +161,10 @@ __device__ __forceinline__ void contract_line_sw(uint32_t U_a, int line, int Wp,
     const int p0 = slot(v0 ? i0 : 0), p1 = slot(v1 ? i1 : 0);
     const uint32_t r0 = U_a + (uint32_t)p0 * 128u + (uint32_t)t * 4u, r1 = U_a + (uint32_t)p1 * 128u + (uint32_t)t * 4u;
     const int ph0 = p0 & 7, ph1 = p1 & 7;
+    // stmatrix addressing: lane L supplies row (L & 7) of matrix L >> 3 = (channel chunk pair member L >> 4, row half (L >> 3) & 1)
+    const int ps = slot(full ? mt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7) : 0);
+    const uint32_t rs = U_a + (uint32_t)ps * 128u;
+    const int phs = ps & 7, cs = lane >> 4;
     // two halves of the 64 channels: 16 accumulator registers live instead of 32 (the B fragments of the whole line must
     // stay in registers until the last store; with 32 accumulators on top ptxas spilled them at the 128-register cap)
 #pragma unroll
@@ -165,11 +179,19 @@ __device__ __forceinline__ void contract_line_sw(uint32_t U_a, int line, int Wp,
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) fptx::mma16816<F16>(acc[nt], a, bf[kt][nh * 4 + nt][0], bf[kt][nh * 4 + nt][1]);
       }
+      if (full) {
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int c = nh * 4 + nt;
-        if (v0) fptx::st_shared_b32(r0 + (uint32_t)((c ^ ph0) << 4), pack2_h16<F16>(acc[nt][0], acc[nt][1]));
-        if (v1) fptx::st_shared_b32(r1 + (uint32_t)((c ^ ph1) << 4), pack2_h16<F16>(acc[nt][2], acc[nt][3]));
+        for (int nt = 0; nt < 4; nt += 2)
+          fptx::stsm_x4(rs + (uint32_t)(((nh * 4 + nt + cs) ^ phs) << 4), pack2_h16<F16>(acc[nt][0], acc[nt][1]),
+                        pack2_h16<F16>(acc[nt][2], acc[nt][3]), pack2_h16<F16>(acc[nt + 1][0], acc[nt + 1][1]),
+                        pack2_h16<F16>(acc[nt + 1][2], acc[nt + 1][3]));
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int c = nh * 4 + nt;
+          if (v0) fptx::st_shared_b32(r0 + (uint32_t)((c ^ ph0) << 4), pack2_h16<F16>(acc[nt][0], acc[nt][1]));
+          if (v1) fptx::st_shared_b32(r1 + (uint32_t)((c ^ ph1) << 4), pack2_h16<F16>(acc[nt][2], acc[nt][3]));
+        }
       }
     }
   }
@@ -385,14 +407,17 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
           for (int nt = 0; nt < 8; ++nt) fptx::mma16816<F16>(acc[nt], a[ks], wf[ks][nt][0], wf[ks][nt][1]);
         }
         __syncwarp();  // every lane's ldmatrix of the raw rows is done before they are overwritten
-        const int r0 = blk * 16 + g, r1 = r0 + 8;
-        const uint32_t o0 = U_a + (uint32_t)r0 * 128u + (uint32_t)t * 4u, o1 = U_a + (uint32_t)r1 * 128u + (uint32_t)t * 4u;
-        const int ph0 = r0 & 7, ph1 = r1 & 7;
+        // whole-fragment stores: lane L supplies row (L & 7) + 8 * ((L >> 3) & 1) of the block, channel chunk pair member L >> 4
+        const int rs_row = blk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+        const uint32_t rs = U_a + (uint32_t)rs_row * 128u;
+        const int phs = rs_row & 7, cs = lane >> 4;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          const float2 bs = *reinterpret_cast<const float2*>(bias_s + nt * 8 + t * 2);
-          fptx::st_shared_b32(o0 + (uint32_t)((nt ^ ph0) << 4), pack2_h16<F16>(acc[nt][0] + bs.x, acc[nt][1] + bs.y));
-          fptx::st_shared_b32(o1 + (uint32_t)((nt ^ ph1) << 4), pack2_h16<F16>(acc[nt][2] + bs.x, acc[nt][3] + bs.y));
+        for (int nt = 0; nt < 8; nt += 2) {
+          const float2 b0 = *reinterpret_cast<const float2*>(bias_s + nt * 8 + t * 2);
+          const float2 b1 = *reinterpret_cast<const float2*>(bias_s + (nt + 1) * 8 + t * 2);
+          fptx::stsm_x4(rs + (uint32_t)(((nt + cs) ^ phs) << 4), pack2_h16<F16>(acc[nt][0] + b0.x, acc[nt][1] + b0.y),
+                        pack2_h16<F16>(acc[nt][2] + b0.x, acc[nt][3] + b0.y), pack2_h16<F16>(acc[nt + 1][0] + b1.x, acc[nt + 1][1] + b1.y),
+                        pack2_h16<F16>(acc[nt + 1][2] + b1.x, acc[nt + 1][3] + b1.y));
         }
       }
     }
@@ -417,21 +442,33 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
       float sm8[8], sq8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) sm8[j] = sq8[j] = 0.f;
-      for (int s = tid >> 3; s < nslots; s += NTHR / 8) {
-        bool valid = true;
-        if (Wp != W || nslots != H * Wp) {
-          const int y = __float2int_rd(((float)s + 0.5f) * p.inv_wp);
-          valid = y < H && ((s - y * Wp) ^ (y & 7)) < W;
-        }
-        if (valid) {
-          uint32_t w0, w1, w2, w3;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(U_a + sw_off(s, ch)));
-          const uint32_t ww[4] = {w0, w1, w2, w3};
+      auto accum = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+        const uint32_t ww[4] = {w0, w1, w2, w3};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack2_h16<F16>(ww[j]);
-            sm8[2 * j] += f.x; sq8[2 * j] = fmaf(f.x, f.x, sq8[2 * j]);
-            sm8[2 * j + 1] += f.y; sq8[2 * j + 1] = fmaf(f.y, f.y, sq8[2 * j + 1]);
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack2_h16<F16>(ww[j]);
+          sm8[2 * j] += f.x; sq8[2 * j] = fmaf(f.x, f.x, sq8[2 * j]);
+          sm8[2 * j + 1] += f.y; sq8[2 * j + 1] = fmaf(f.y, f.y, sq8[2 * j + 1]);
+        }
+      };
+      if (Wp == W && nslots == H * Wp && (nslots % (NTHR / 2)) == 0) {
+        // no pad rows: four 16-byte loads in flight per thread
+        for (int s = tid >> 3; s < nslots; s += NTHR / 2) {
+          uint32_t w[4][4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[q4][0]), "=r"(w[q4][1]), "=r"(w[q4][2]), "=r"(w[q4][3])
+                         : "r"(U_a + sw_off(s + q4 * (NTHR / 8), ch)));
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) accum(w[q4][0], w[q4][1], w[q4][2], w[q4][3]);
+        }
+      } else {
+        for (int s = tid >> 3; s < nslots; s += NTHR / 8) {
+          const int y = __float2int_rd(((float)s + 0.5f) * p.inv_wp);
+          if (y < H && ((s - y * Wp) ^ (y & 7)) < W) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(U_a + sw_off(s, ch)));
+            accum(w0, w1, w2, w3);
           }
         }
       }
