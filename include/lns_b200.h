@@ -59,8 +59,10 @@ enum {
 enum {
   LNS_ENGINE_SIMT = 0, /* CUDA-core fp32 FMA (validation path; any shape)                                       */
   LNS_ENGINE_UMMA = 1, /* tcgen05 implicit GEMM, per-tap gather (any kernel/stride/dilation/resize, Cin%64==0)  */
-  LNS_ENGINE_HALO = 2  /* tcgen05 implicit GEMM, shared-memory halo + resident filter: same-size 3x3 stride-1     */
+  LNS_ENGINE_HALO = 2, /* tcgen05 implicit GEMM, shared-memory halo + resident filter: same-size 3x3 stride-1     */
                        /* convs with Cin == 64, Cout in {64,128} (the full-resolution layers)                     */
+  LNS_ENGINE_LATENT = 3 /* tcgen05 implicit GEMM for the 8x8 circular latent grid, 128 -> 128 channels, dilation   */
+                        /* 1|2: resident halos of 4 samples, streamed filter (the propagator's 3x3 convs)          */
 };
 
 const char* lns_version(void);

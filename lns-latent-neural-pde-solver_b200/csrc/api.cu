@@ -90,6 +90,7 @@ int lns_conv2d(const LnsConvDesc* d, void* stream) {
   if (rc != LNS_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (d->engine == LNS_ENGINE_HALO) return lns::conv2d_halo(d, s);
+  if (d->engine == LNS_ENGINE_LATENT) return lns::conv2d_latent(d, s);
   if (d->engine == LNS_ENGINE_UMMA) return lns::conv2d_umma(d, s);
   if (d->engine == LNS_ENGINE_SIMT) return lns::conv2d_simt(d, s);
   lns::set_error("lns_conv2d: unknown engine %d", d->engine);

@@ -203,6 +203,8 @@ int conv2d_simt(const LnsConvDesc* d, cudaStream_t stream);
 int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream);
 int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream);
 bool conv_halo_supported(const LnsConvDesc* d);
+int conv2d_latent(const LnsConvDesc* d, cudaStream_t stream);
+bool conv_latent_supported(const LnsConvDesc* d);
 int validate_conv(const LnsConvDesc* d);
 ConvGeom make_geom(const LnsConvDesc* d);
 

@@ -17,7 +17,7 @@ NHWC, NCHW = 0, 1
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAD_ZEROS, PAD_CIRCULAR = 0, 1
 W_SIMT_F32, W_UMMA_BF16, W_UMMA_TF32, W_UMMA_F16 = 0, 1, 2, 3
-ENGINE_SIMT, ENGINE_UMMA, ENGINE_HALO = 0, 1, 2
+ENGINE_SIMT, ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT = 0, 1, 2, 3
 
 _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 H16_DTYPES = (torch.bfloat16, torch.float16)  # the 16-bit storage types of the tensor-core paths
@@ -342,15 +342,20 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
                 and Cout in (64, 128)
                 and pt == pb == pl == pr == dil and 1 <= dil <= 3 and Hout >= 16 and Wout >= 8):
             engine = ENGINE_HALO  # full-resolution layers: shared-memory halo + resident filter
+        elif (engine == ENGINE_UMMA and x.t.dtype in H16_DTYPES and KH == 3 and KW == 3 and stride == 1 and Cin == 128
+                and Cout == 128 and virt is None and (x.H, x.W) == (8, 8) and pt == pb == pl == pr == dil and dil in (1, 2)
+                and tuple(pad_mode) == (PAD_CIRCULAR, PAD_CIRCULAR) and sample_bias is None and pre_add is None
+                and x.B >= 4):
+            engine = ENGINE_LATENT  # the propagator's latent grid: resident halos of 4 samples, streamed filter
     if isinstance(pro, LazyNorm):
         if pro.x is not x:
             raise LnsError("conv2d: the pending normalisation belongs to a different activation")
-        if engine in (ENGINE_UMMA, ENGINE_HALO):
+        if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT):
             x = pro.materialize()  # these engines gather with cp.async (no transform in flight)
             pro = None
         else:
             pro = pro.as_tuple()
-    if engine in (ENGINE_UMMA, ENGINE_HALO) and pro is not None:
+    if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT) and pro is not None:
         x = affine_act(x, pro[0], pro[1], pro[2])
         pro = None
     if out is None:
@@ -371,7 +376,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     d.KH, d.KW, d.stride, d.dil, d.pad_t, d.pad_l = KH, KW, stride, dil, pt, pl
     d.pad_mode_h, d.pad_mode_w = pad_mode
     fmt = W_SIMT_F32
-    if engine in (ENGINE_UMMA, ENGINE_HALO):
+    if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT):
         fmt = {torch.bfloat16: W_UMMA_BF16, torch.float16: W_UMMA_F16}.get(x.t.dtype, W_UMMA_TF32)
     wbuf = filt.get(fmt)
     d.w, d.w_format, d.engine = wbuf.data_ptr(), fmt, engine

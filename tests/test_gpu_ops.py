@@ -677,3 +677,31 @@ def test_fa_axis_kernel_vs_fp64(H, W, B, prec):
             results.append(relerr(K.cpu(), ref))
     print(f"[fa_axis {H}x{W} {prec}] K_x {results[0]:.2e} K_y {results[1]:.2e}")
     assert max(results) < (6e-3 if prec == "bf16" else 8e-4)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("B,dil", [(4, 1), (6, 2), (601, 1), (1187, 2), (5, 1)])
+def test_conv_latent_engine(B, dil, prec):
+    """latent-grid engine (resident halos of 4 samples, interleaved two-sample MMA tiles, streamed filter) vs an fp64 conv
+    of the same 16-bit-rounded operands, full epilogue (bias, GELU, residual); batch sizes that are not multiples of the
+    4-sample super tile and larger than one wave of CTAs"""
+    ops = ops_mod()
+    dt = torch.bfloat16 if prec == "bf16" else torch.float16
+    g = torch.Generator().manual_seed(100 + B + dil)
+    x = torch.randn(B, 128, 8, 8, generator=g)
+    w = torch.randn(128, 128, 3, 3, generator=g) / 34.0
+    b = torch.randn(128, generator=g) * 0.1
+    res = torch.randn(B, 128, 8, 8, generator=g)
+    rd = lambda t: t.to(dt).float()
+    ref = ref_conv(rd(x), rd(w), b, 1, dil, (dil,) * 4, (1, 1), None)
+    ref = F.gelu(ref) + rd(res).double()
+    h = Holder(w, b)
+    with ops.precision(prec):
+        y = ops.conv2d(act_from(x, dt), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4, pad_mode=(1, 1),
+                       act=ops.ACT_GELU, residual=act_from(res, dt), engine=ops.ENGINE_LATENT, out_dtype=torch.float32)
+        y16 = ops.conv2d(act_from(x, dt), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4, pad_mode=(1, 1),
+                         act=ops.ACT_GELU, residual=act_from(res, dt))  # engine chosen by the dispatcher
+    torch.cuda.synchronize()
+    assert relerr(act_to_nchw(y), ref) < 5e-6
+    assert y16.t.dtype == dt
+    assert torch.equal(act_to_nchw(y16), act_to_nchw(y).to(dt).float())  # same values, rounded once

@@ -10,7 +10,8 @@ import torch  # noqa: E402
 from lns_b200 import ops  # noqa: E402
 
 H, W, Cin, Cout, nb, dil = [int(a) for a in (sys.argv[1:7] + ["64", "64", "64", "64", "256", "1"][len(sys.argv[1:7]):])]
-ENGINE = {"umma": ops.ENGINE_UMMA, "halo": ops.ENGINE_HALO}[sys.argv[7] if len(sys.argv) > 7 else "umma"]
+ENGINE = {"umma": ops.ENGINE_UMMA, "halo": ops.ENGINE_HALO, "latent": ops.ENGINE_LATENT}[sys.argv[7] if len(sys.argv) > 7 else "umma"]
+ACT = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 dev = "cuda:0"
 x = ops.Act(torch.randn(nb * H * W * Cin, device=dev).bfloat16(), nb, H, W, Cin)
 wt = torch.nn.Parameter(torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(9 * Cin))
@@ -19,12 +20,12 @@ filt = ops.PackedFilter.of(wt, bs)
 out = ops.Act.empty(nb, H, W, Cout, torch.bfloat16, dev)
 with ops.precision("bf16"):
     for _ in range(3):
-        ops.conv2d(x, filt, dil=dil, pad=(dil,) * 4, pad_mode=(1, 1), out=out, engine=ENGINE)
+        ops.conv2d(x, filt, dil=dil, pad=(dil,) * 4, pad_mode=(1, 1), out=out, engine=ENGINE, act=ACT)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        ops.conv2d(x, filt, dil=dil, pad=(dil,) * 4, pad_mode=(1, 1), out=out, engine=ENGINE)
+        ops.conv2d(x, filt, dil=dil, pad=(dil,) * 4, pad_mode=(1, 1), out=out, engine=ENGINE, act=ACT)
     e1.record()
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
