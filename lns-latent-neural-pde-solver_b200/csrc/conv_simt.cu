@@ -144,6 +144,83 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams p) {
   }
 }
 
+// ---- channel lift: 1x1 conv from a few channels (Cin <= 16) to many (Cout % 8 == 0) -----------------------------------
+// The encoder's first layer (1|3|4 -> 64 channels at full resolution, reading the reference's NCHW fp32 input) and the
+// propagator's in_proj (16 -> 128 on the fp32 latent) are pure HBM streams: K is too small for any GEMM tiling (the generic
+// 64 x BN tile above spent 1.7 ms on a layer whose output takes 83 us to write).  Thread = (pixel, 8 output channels): the
+// pixel's Cin values are read once (a broadcast within the pixel's thread group), the filter sits in shared memory, every
+// thread writes one 16-byte (16-bit output) or 32-byte chunk, a pixel's channels are contiguous across its threads.
+// Same accumulation order as conv_simt_kernel (c ascending, then bias): bit-identical on the fp32 path.
+__global__ void __launch_bounds__(256) lift1x1_kernel(const SimtParams p, int pix_per_block) {
+  extern __shared__ float wl_s[];  // [Cin][Cout] + bias [Cout]
+  const ConvGeom& g = p.g;
+  const int Cin = g.Cin, Cout = g.Cout;
+  for (int e = threadIdx.x; e < Cin * Cout; e += 256) wl_s[e] = __ldg(p.w + e);
+  float* bias_s = wl_s + Cin * Cout;
+  for (int e = threadIdx.x; e < Cout; e += 256) bias_s[e] = p.bias ? __ldg(p.bias + e) : 0.f;
+  __syncthreads();
+  const int CG = Cout >> 3, ppp = 256 / CG;  // channel groups per pixel, pixels per pass
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int HW = g.Hout * g.Wout;
+  const int64_t m_end = min((int64_t)p.M, (int64_t)(blockIdx.x + 1) * pix_per_block);
+  const bool fast = is_h16(p.y_dtype);
+  if (pl >= ppp) return;
+  for (int64_t m = (int64_t)blockIdx.x * pix_per_block + pl; m < m_end; m += ppp) {
+    const int b = (int)(m / HW), pix = (int)(m - (int64_t)b * HW);
+    float xv[16];
+    if (p.x_layout == LNS_NCHW) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < Cin) xv[c] = __ldg(reinterpret_cast<const float*>(p.x) + (int64_t)b * g.x_bstride + (int64_t)c * HW + pix);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 16; c += 4)
+        if (c < Cin) {
+          const float4 t4 = ld4_as_float(p.x, p.x_dtype, (int64_t)b * g.x_bstride + (int64_t)pix * Cin + c);
+          xv[c] = t4.x; xv[c + 1] = t4.y; xv[c + 2] = t4.z; xv[c + 3] = t4.w;
+        }
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c < Cin) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wl_s + c * Cout + cg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(wl_s + c * Cout + cg * 8 + 4);
+        acc[0] = fmaf(xv[c], w0.x, acc[0]); acc[1] = fmaf(xv[c], w0.y, acc[1]);
+        acc[2] = fmaf(xv[c], w0.z, acc[2]); acc[3] = fmaf(xv[c], w0.w, acc[3]);
+        acc[4] = fmaf(xv[c], w1.x, acc[4]); acc[5] = fmaf(xv[c], w1.y, acc[5]);
+        acc[6] = fmaf(xv[c], w1.z, acc[6]); acc[7] = fmaf(xv[c], w1.w, acc[7]);
+      }
+    }
+    const int64_t o = (int64_t)b * g.y_bstride + (int64_t)pix * Cout + cg * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[j] + bias_s[cg * 8 + j];
+      if (p.sample_bias) v += __ldg(p.sample_bias + (int64_t)b * Cout + cg * 8 + j);
+      acc[j] = fast ? apply_act_fast(v, p.act) : apply_act(v, p.act);
+    }
+    if (p.residual) {
+      const int64_t ro = (int64_t)b * p.res_bstride + (int64_t)pix * Cout + cg * 8;
+      const float4 r0 = ld4_as_float(p.residual, p.res_dtype, ro), r1 = ld4_as_float(p.residual, p.res_dtype, ro + 4);
+      acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w;
+      acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
+    }
+    st4_from_float(p.y, p.y_dtype, o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4_from_float(p.y, p.y_dtype, o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+  }
+}
+
+static bool lift_ok(const LnsConvDesc* d) {
+  const bool nhwc_in = d->x_layout == LNS_NHWC;
+  return d->KH == 1 && d->KW == 1 && d->stride == 1 && d->pad_t == 0 && d->pad_l == 0 && d->Hv == d->Hin && d->Wv == d->Win &&
+         d->Hout == d->Hin && d->Wout == d->Win && d->Cin <= 16 && d->Cout % 8 == 0 && d->Cout >= 8 && d->Cout <= 256 &&
+         d->y_layout == LNS_NHWC && d->pro_scale == nullptr && d->pro_act == LNS_ACT_NONE && d->pre_add == nullptr &&
+         d->y_bstride % 4 == 0 && (d->residual == nullptr || d->res_bstride % 4 == 0) &&
+         (nhwc_in ? (d->Cin % 4 == 0 && d->x_bstride % 4 == 0) : !is_h16_host(d->x_dtype));
+}
+
 int conv2d_simt(const LnsConvDesc* d, cudaStream_t stream) {
   LNS_REQUIRE(d->w_format == LNS_W_SIMT_F32, "lns_conv2d(simt): weights must be packed as LNS_W_SIMT_F32");
   SimtParams p;
@@ -160,6 +237,14 @@ int conv2d_simt(const LnsConvDesc* d, cudaStream_t stream) {
   LNS_REQUIRE(M < (1ll << 31), "lns_conv2d(simt): too many output pixels");
   LNS_REQUIRE(!(d->pro_scale && !d->pro_shift), "lns_conv2d: pro_scale without pro_shift");
   p.M = (int)M;
+  if (lift_ok(d)) {
+    const int ppp = 256 / (d->Cout / 8);
+    int ppb = ppp * 8;                                     // 8 passes per block ...
+    while ((M + ppb - 1) / ppb > 148 * 16) ppb *= 2;       // ... more when the grid would exceed 16 blocks per SM
+    const size_t smem = ((size_t)d->Cin * d->Cout + d->Cout) * sizeof(float);
+    lift1x1_kernel<<<(unsigned)((M + ppb - 1) / ppb), 256, smem, stream>>>(p, ppb);
+    return check_launch("lift1x1_kernel");
+  }
   if (d->Cout <= 16) {
     dim3 grid(cdiv(M, 64), cdiv(d->Cout, 16));
     conv_simt_kernel<16><<<grid, 256, 0, stream>>>(p);

@@ -482,7 +482,10 @@ int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
     return launch_umma<256, 3, 4>(p, d->Cout, stream);
   }
   if (d->Cout <= 64) return launch_umma<64, 4, 2>(p, d->Cout, stream);
-  if (d->Cout <= 128) return launch_umma<128, 3, 2>(p, d->Cout, stream);
+  // short K (1x1 convs / linears): the kernel is epilogue bound and the 256-column tile's 144 KB of stages leave ONE CTA per
+  // SM, i.e. no overlap of one tile's epilogue with another's loads; 128-column tiles run 2 CTAs per SM
+  const bool short_k = (int64_t)d->KH * d->KW * d->Cin <= 256;
+  if (d->Cout <= 128 || short_k) return launch_umma<128, 3, 2>(p, d->Cout, stream);
   return launch_umma<256, 3, 2>(p, d->Cout, stream);
 }
 
