@@ -211,6 +211,15 @@ int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, in
 int lns_fablock_core(const void* u, int dtype, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
                      const float* w_in_proj, const float* Kx, const float* Ky, float eps, void* out, void* stream);
 
+/* Propagator FFN in ONE kernel (csrc/ffn_fused.cu):  y = x + W2 . GELU( W1 . (x*scale[b] + shift[b]) )  -- GroupNorm(1,C) apply,
+ * 1x1 conv, GELU, 1x1 conv and the residual add of train_stage2_ns2d.py:44-53 (both convs bias-free, C = hidden = 128).
+ * x, y: NHWC rows [B][HW][128] LNS_BF16 | LNS_F16 with batch strides in elements; scale/shift [B][128] from
+ * lns_group_norm_affine; w1_packed / w2_packed: lns_pack_conv_weight(..., LNS_W_UMMA_BF16 | _F16) images of the two 1x1
+ * filters.  Both GEMMs run on tcgen05 with the hidden activation never leaving the SM. */
+int lns_ffn_fused_supported(int C, int hidden);
+int lns_ffn_fused(const void* x, int dtype, int B, int HW, int C, int64_t x_bstride, const float* scale, const float* shift,
+                  const void* w1_packed, const void* w2_packed, void* y, int64_t y_bstride, void* stream);
+
 /* FABlock2D pooled branch of one axis in ONE kernel (csrc/fa_axis.cu): pooled [B][n][64] fp32 (lns_fablock_prepass) ->
  * K [B][heads][n][n] fp32.  Replaces to_in (1x1 conv), PoolingReducer (Linear, LayerNorm, Linear+GELU, Linear+bias),
  * LowRankKernel.to_qk, the rotary embedding and q k^T (modules/factorized_attention.py:43-94,114-121).  Host-prepared

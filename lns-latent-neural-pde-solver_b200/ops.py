@@ -626,6 +626,29 @@ def fablock_core(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps):
     return out
 
 
+def ffn_fused_supported(x, f1, f2):
+    """x Act, f1/f2 PackedFilters of the two bias-free 1x1 convs"""
+    d1, d2 = f1.dims(), f2.dims()
+    return (fast16() and x.t.dtype == act_dtype() and x.layout == NHWC and x.bstride % 8 == 0 and x.B * x.H * x.W < (1 << 22)
+            and d1[2:] == (1, 1) and d2[2:] == (1, 1) and d1[0] == d2[1] and d1[1] == x.C and d2[0] == x.C
+            and f1.bias() is None and f2.bias() is None
+            and bool(_C.lib().lns_ffn_fused_supported(x.C, d1[0])))
+
+
+def ffn_fused(x, scale, shift, f1, f2):
+    """y = x + W2 . GELU(W1 . (x*scale + shift)): GroupNorm apply + both 1x1 convs + residual in one tcgen05 kernel."""
+    fmt = W_UMMA_F16 if x.t.dtype == torch.float16 else W_UMMA_BF16
+    w1, w2 = f1.get(fmt), f2.get(fmt)
+    out = x.like()
+    tok = _mark(f"ffn_fused C{x.C} @{x.H}x{x.W}")
+    rc = _C.lib().lns_ffn_fused(_ptr(x.t), x.dtype, x.B, x.H * x.W, x.C, x.bstride, _ptr(scale), _ptr(shift), _ptr(w1), _ptr(w2),
+                                _ptr(out.t), out.bstride, _stream())
+    check(rc, "lns_ffn_fused")
+    _done(tok)
+    _state.launches += 1
+    return out
+
+
 def fa_axis_kernel_supported(n, dim, hidden, latent, heads, d):
     return bool(_C.lib().lns_fa_axis_kernel_supported(n, dim, hidden, latent, heads, d))
 

@@ -50,8 +50,18 @@ def dilated_block_fwd(blk, x):
     h = conv_layer(x, c1, pro=lazy_norm(x, gn), act=ops.ACT_GELU)
     h = conv_layer(h, c2, act=ops.ACT_GELU)
     x = conv_layer(h, c3, residual=x)
-    gn2, f1, _, f2 = blk.ffn
-    h = conv_layer(x, f1, pro=lazy_norm(x, gn2), act=ops.ACT_GELU)
+    return ffn_fwd(blk.ffn, x)
+
+
+def ffn_fwd(ffn, x, prescale=None):
+    """x + Conv1(GELU(Conv1(GN1(x * prescale)))): one tcgen05 kernel (statistics kernel + lns_ffn_fused) on the 16-bit paths
+    when the block is 128 -> 128 -> 128 with bias-free 1x1 convs, else three launches."""
+    gn2, f1, _, f2 = ffn
+    if (isinstance(f1, nn.Conv2d) and isinstance(f2, nn.Conv2d) and f1.kernel_size == (1, 1) and f2.kernel_size == (1, 1)
+            and f1.stride == (1, 1) and f2.stride == (1, 1) and ops.ffn_fused_supported(x, filt_of(f1), filt_of(f2))):
+        s, t = norm_affine(x, gn2, prescale=prescale)
+        return ops.ffn_fused(x, s, t, filt_of(f1), filt_of(f2))
+    h = conv_layer(x, f1, pro=lazy_norm(x, gn2, prescale=prescale), act=ops.ACT_GELU)
     return conv_layer(h, f2, residual=x)
 
 
@@ -134,9 +144,7 @@ def cond_block_fwd(blk, x, prepared):
     gn1, _, cz = blk.cond_conv1
     x = conv_layer(h, cz, pro=lazy_norm(h, gn1, ops.ACT_GELU), residual=x)
     # GN1(x * (1 + gate)): per-channel statistics of x rescale exactly, so the gate only enters the finalize kernel
-    gn2, f1, _, f2 = blk.ffn
-    h = conv_layer(x, f1, pro=lazy_norm(x, gn2, prescale=one_plus_gate), act=ops.ACT_GELU)
-    return conv_layer(h, f2, residual=x)
+    return ffn_fwd(blk.ffn, x, prescale=one_plus_gate)
 
 
 class CondSimpleCNN(LnsModule):

@@ -705,3 +705,38 @@ def test_conv_latent_engine(B, dil, prec):
     assert relerr(act_to_nchw(y), ref) < 5e-6
     assert y16.t.dtype == dt
     assert torch.equal(act_to_nchw(y16), act_to_nchw(y).to(dt).float())  # same values, rounded once
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("B,H,W", [(6, 8, 8), (3, 7, 15), (5, 12, 24), (300, 8, 8)])
+def test_ffn_fused_vs_unfused_and_fp64(B, H, W, prec):
+    """propagator FFN in one tcgen05 kernel (GroupNorm apply + 1x1 + GELU + 1x1 + residual) vs the three-launch path and vs
+    an fp64 evaluation of the reference block (train_stage2_ns2d.py:44-53); rows straddle samples when H*W does not divide 128"""
+    ops = ops_mod()
+    from modules.propagator import DilatedResidualBlock, ffn_fwd
+    torch.manual_seed(9)
+    blk = DilatedResidualBlock(128, dilation=2).to(DEV).eval()
+    with torch.no_grad():
+        blk.ffn[0].weight.uniform_(0.5, 1.5)
+        blk.ffn[0].bias.normal_(0, 0.2)
+    dt = torch.bfloat16 if prec == "bf16" else torch.float16
+    g = torch.Generator().manual_seed(50 + B)
+    x = torch.randn(B, 128, H, W, generator=g) * 1.5 + 0.3
+    xr = x.to(dt).double()
+    gn, f1, _, f2 = blk.ffn
+    w = lambda t: t.detach().double().cpu()
+    ref = xr + F.conv2d(F.gelu(F.conv2d(F.group_norm(xr, 1, w(gn.weight), w(gn.bias), gn.eps), w(f1.weight))), w(f2.weight))
+    a = act_from(x, dt)
+    with torch.no_grad(), ops.precision(prec):
+        assert ops.ffn_fused_supported(a, ops.PackedFilter.of(f1.weight, None), ops.PackedFilter.of(f2.weight, None))
+        fused = act_to_nchw(ffn_fwd(blk.ffn, a))
+        orig = ops.ffn_fused_supported
+        ops.ffn_fused_supported = lambda *aa, **kk: False
+        try:
+            unfused = act_to_nchw(ffn_fwd(blk.ffn, a))
+        finally:
+            ops.ffn_fused_supported = orig
+    e_f, e_u = relerr(fused, ref), relerr(unfused, ref)
+    print(f"[ffn {B}x{H}x{W} {prec}] fused vs fp64 {e_f:.2e}, unfused {e_u:.2e}")
+    tol = 8e-3 if prec == "bf16" else 1e-3
+    assert e_f < tol and e_u < tol
