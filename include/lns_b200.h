@@ -176,6 +176,16 @@ int lns_layernorm(const void* x, int x_dtype, int B, int n, int C, const float* 
 int lns_attention(const void* qkv, int dtype, int B, int n, int heads, int dh, float scale, void* out,
                   int out_dtype, void* stream);
 
+/* SABlock in ONE kernel (csrc/sablock_fused.cu):  y = x + proj_out( softmax(q k^T * scale) v ),  q|k|v = Linear(LN(x) + pe)
+ * -- modules/basics.py:384-404 including the LayerNorm, the positional table added after the norm, the three input linears,
+ * the attention core, the output projection and the residual.  x, y: token rows [B][n][128], LNS_BF16 | LNS_F16; wqkv16
+ * [3*heads*64][128] = to_q | to_k | to_v weights stacked, wproj16 [128][heads*64], both in the activation's 16-bit format;
+ * bv / bproj fp32 biases or NULL; pe [>= n][128] fp32 or NULL.  Needs dim = 128, dim_head = 64, n <= 128. */
+int lns_sablock_fused_supported(int n, int dim, int heads, int dim_head);
+int lns_sablock_fused(const void* x, int dtype, int B, int n, int heads, const float* ln_g, const float* ln_b, float ln_eps,
+                      const float* pe, const void* wqkv16, const float* bv, const void* wproj16, const float* bproj,
+                      float scale, void* y, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * FABlock2D pieces  modules/factorized_attention.py:144-159
  * ------------------------------------------------------------------------------------------------ */

@@ -60,6 +60,8 @@ SIGNATURES = {
     "lns_fablock_core_supported": (i32, [i32, i32, i32, i32]),
     "lns_fablock_prepass": (i32, [vp, i32, i32, i32, i32, i32, i64, f32, vp, vp, vp, vp, vp, vp, vp]),
     "lns_fablock_core": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp]),
+    "lns_sablock_fused_supported": (i32, [i32, i32, i32, i32]),
+    "lns_sablock_fused": (i32, [vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp, f32, vp, vp]),
     "lns_ffn_fused_supported": (i32, [i32, i32]),
     "lns_ffn_fused": (i32, [vp, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, i64, vp]),
     "lns_fa_axis_kernel_supported": (i32, [i32, i32, i32, i32, i32, i32]),

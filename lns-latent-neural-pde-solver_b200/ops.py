@@ -626,6 +626,23 @@ def fablock_core(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps):
     return out
 
 
+def sablock_fused_supported(x, heads, dim_head):
+    return (fast16() and x.t.dtype == act_dtype() and x.layout == NHWC and x.contiguous
+            and bool(_C.lib().lns_sablock_fused_supported(x.H * x.W, x.C, heads, dim_head)))
+
+
+def sablock_fused(x, heads, ln_g, ln_b, ln_eps, pe, wqkv16, bv, wproj16, bproj, scale):
+    """Whole SABlock (LN + pe, q|k|v, attention, projection, residual) in one kernel: Act [B,H,W,128] -> Act of the same shape."""
+    out = x.like()
+    tok = _mark("sablock_fused")
+    rc = _C.lib().lns_sablock_fused(_ptr(x.t), x.dtype, x.B, x.H * x.W, heads, _ptr(ln_g), _ptr(ln_b), float(ln_eps), _ptr(pe),
+                                    _ptr(wqkv16), _ptr(bv), _ptr(wproj16), _ptr(bproj), float(scale), _ptr(out.t), _stream())
+    check(rc, "lns_sablock_fused")
+    _done(tok)
+    _state.launches += 1
+    return out
+
+
 def ffn_fused_supported(x, f1, f2):
     """x Act, f1/f2 PackedFilters of the two bias-free 1x1 convs"""
     d1, d2 = f1.dims(), f2.dims()

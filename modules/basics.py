@@ -136,6 +136,23 @@ class SABlock(LnsModule):
             self.__dict__["_lns_qkv"] = f
         return f
 
+    def _fused_operands(self, dt16):
+        """16-bit filter copies / fp32 vectors of lns_sablock_fused, cached until a source parameter changes."""
+        srcs = [self.ln.weight, self.ln.bias, self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_v.bias,
+                self.proj_out.weight, self.proj_out.bias] + ([self.pe] if self.pe is not None else [])
+        key = (dt16,) + tuple(None if t is None else (t.data_ptr(), t._version, str(t.device)) for t in srcs)
+        ent = self.__dict__.get("_lns_sa")
+        if ent is None or ent[0] != key:
+            with torch.no_grad():
+                f = lambda t: None if t is None else t.detach().float().contiguous()  # noqa: E731
+                ent = (key, dict(
+                    ln_g=f(self.ln.weight), ln_b=f(self.ln.bias),
+                    wqkv=torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0).detach().to(dt16).contiguous(),
+                    bv=f(self.to_v.bias), wproj=self.proj_out.weight.detach().to(dt16).contiguous(), bproj=f(self.proj_out.bias),
+                    pe=None if self.pe is None else self.pe.detach().float().reshape(-1, self.dim).contiguous()))
+            self.__dict__["_lns_sa"] = ent
+        return ent[1]
+
     def _fwd(self, x):
         n = x.H * x.W
         pe = None
@@ -143,6 +160,11 @@ class SABlock(LnsModule):
             if n > self.pe.shape[1]:
                 raise LnsError(f"SABlock: {n} tokens exceed the positional table ({self.pe.shape[1]})")
             pe = self.pe.detach()
+        if ops.sablock_fused_supported(x, self.heads, self.dim_head) and self.to_q.bias is None and self.to_k.bias is None:
+            o = self._fused_operands(x.t.dtype)
+            return ops.sablock_fused(x, self.heads, o["ln_g"], o["ln_b"], self.ln.eps,
+                                     None if pe is None else o["pe"], o["wqkv"], o["bv"], o["wproj"], o["bproj"],
+                                     self.dim_head ** (-0.5))
         t = ops.layernorm(x, self.ln.weight, self.ln.bias, self.ln.eps, pe=pe)
         qkv = ops.conv2d(t, self._qkv_filter())
         o = ops.attention(qkv, self.heads, self.dim_head, self.dim_head ** (-0.5))

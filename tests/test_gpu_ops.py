@@ -740,3 +740,49 @@ def test_ffn_fused_vs_unfused_and_fp64(B, H, W, prec):
     print(f"[ffn {B}x{H}x{W} {prec}] fused vs fp64 {e_f:.2e}, unfused {e_u:.2e}")
     tol = 8e-3 if prec == "bf16" else 1e-3
     assert e_f < tol and e_u < tol
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("B,H,W,use_pe", [(5, 8, 8, True), (3, 7, 15, True), (4, 4, 8, False), (301, 8, 8, True), (2, 8, 16, False)])
+def test_sablock_fused_vs_unfused_and_fp64(B, H, W, use_pe, prec):
+    """whole SABlock in one kernel vs the four-launch path and vs an fp64 evaluation of the reference block
+    (modules/basics.py:384-404); one and two samples per CTA, token counts that are not multiples of 16"""
+    ops = ops_mod()
+    from modules.basics import SABlock
+    torch.manual_seed(11)
+    blk = SABlock(128, 8, 64, use_pe=use_pe, block_size=128).to(DEV).eval()
+    with torch.no_grad():
+        for lin in (blk.to_q, blk.to_k, blk.to_v, blk.proj_out):
+            lin.weight.normal_(0, 0.08)
+        blk.to_v.bias.normal_(0, 0.1)
+        blk.proj_out.bias.normal_(0, 0.1)
+        blk.ln.weight.uniform_(0.5, 1.5)
+        blk.ln.bias.normal_(0, 0.2)
+    dt = torch.bfloat16 if prec == "bf16" else torch.float16
+    g = torch.Generator().manual_seed(60 + B)
+    x = torch.randn(B, 128, H, W, generator=g)
+    n = H * W
+    w = lambda t: t.detach().double().cpu()
+    xt = x.to(dt).double().flatten(2).transpose(1, 2)  # [B, n, 128]
+    tn = F.layer_norm(xt, (128,), w(blk.ln.weight), w(blk.ln.bias), blk.ln.eps)
+    if use_pe:
+        tn = tn + w(blk.pe)[:, :n]
+    q, k, v = tn @ w(blk.to_q.weight).t(), tn @ w(blk.to_k.weight).t(), tn @ w(blk.to_v.weight).t() + w(blk.to_v.bias)
+    sp = lambda t: t.view(B, n, 8, 64).transpose(1, 2)
+    att = F.softmax(sp(q) @ sp(k).transpose(-1, -2) * 64 ** -0.5, dim=-1) @ sp(v)
+    ref = (att.transpose(1, 2).reshape(B, n, 512) @ w(blk.proj_out.weight).t() + w(blk.proj_out.bias) + xt)
+    ref = ref.transpose(1, 2).reshape(B, 128, H, W)
+    a = act_from(x, dt)
+    with torch.no_grad(), ops.precision(prec):
+        assert ops.sablock_fused_supported(a, 8, 64)
+        fused = act_to_nchw(blk._fwd(a))
+        orig = ops.sablock_fused_supported
+        ops.sablock_fused_supported = lambda *aa, **kk: False
+        try:
+            unfused = act_to_nchw(blk._fwd(a))
+        finally:
+            ops.sablock_fused_supported = orig
+    e_f, e_u = relerr(fused, ref), relerr(unfused, ref)
+    print(f"[sablock {B}x{H}x{W} pe={use_pe} {prec}] fused vs fp64 {e_f:.2e}, unfused {e_u:.2e}")
+    tol = 6e-3 if prec == "bf16" else 8e-4
+    assert e_f < tol and e_u < tol
