@@ -17,7 +17,10 @@
 // Pipelines: halo ring (HS stages; full = 128 async cp.async arrivals, empty = tcgen05.commit) and four TMEM
 // accumulators (full = tcgen05.commit, empty = 128 epilogue arrivals): epilogue, MMA issue, tensor pipe and halo loads
 // of different tiles all overlap.
+#include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -51,6 +54,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// 16-byte copy from a 64-bit global ADDRESS; `zero` = ignore the source and write zeros (the address must still be valid)
+__device__ __forceinline__ void cp_async16_zf(uint32_t dst, uint64_t src, bool zero) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+      "}" ::"r"(dst),
+      "l"(src), "r"((uint32_t)zero)
+      : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -61,6 +75,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA tensor store shared -> global (4-D tiled map, box = one staged tile), tracked by the issuing thread's bulk groups
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
@@ -166,6 +191,8 @@ struct HaloParams {
   int halo_bytes;      // per stage, multiple of 1024
   int stages;          // halo ring depth
   int resize;          // 0 none, 1 exact 2x nearest, 2 general nearest
+  int nbuf;            // output staging buffers per epilogue warp (4 KB each): 2 when they fit, else 1
+  int tma_store;       // 16-bit outputs leave through one TMA tensor store per staged tile (tmap_y is valid)
   float inv_hw, inv_hv, inv_wv;
   int debug;  // LNS_HALO_DEBUG bits (timing experiments only): 1 skip halo copies, 2 skip epilogue, 4 skip MMAs
 };
@@ -173,18 +200,84 @@ struct HaloParams {
 // kIssuers MMA issue warps (tile it -> issuer it % kIssuers), kAccs TMEM accumulator buffers (tile it -> it % kAccs)
 constexpr int kTileH = 16, kTileW = 8;
 
+// One producer warp fills one halo stage for output tile (tx, ty) of sample b.
+// Copy schedule: a halo row is HW pixels x 8 sixteen-byte chunks = HW*8 (80 / 96 / 112) slots; lane l owns slots l, l+32,
+// l+64(, l+96) of EVERY row, i.e. fixed halo columns hx = (l + 32*sub) >> 3 and the fixed chunk l & 7.  Per tile the lane
+// evaluates its <= 4 column terms (as 64-bit column base addresses) and row term `lane` once; per row it needs one shuffle
+// (the row term) and per copy a 64-bit add and a predicate.  Everything about the destination is a compile-time constant
+// plus a per-lane term.  (ncu source view of the previous version -- two shuffles, a 64-bit pointer select and a wrapping
+// (hy, hx) walk per copy: 38 SASS instructions per pass x 45 passes per tile issued by ONE warp -- showed the producers
+// 62% of their time in the copy loop with BOTH the MMA issuers and the epilogue waiting on them: ~8000 cycles of producer
+// issue per tile against 1184 tensor-pipe cycles.)
+template <int DIL>
+__device__ __forceinline__ void halo_fill(const HaloParams& p, int tx, int ty, int b, int lane, uint32_t st, uint32_t empty_bar,
+                                          bool wait_empty, uint32_t empty_parity, bool docopy) {
+  constexpr int HW = kTileW + 2 * DIL, HH = kTileH + 2 * DIL;
+  constexpr int NSLOT = HW * 8, NSUB = (NSLOT + 31) / 32;
+  const ConvGeom& g = p.g;
+  const int chunk = lane & 7;
+  // source terms (BYTES): row term of halo row `lane` (HH <= 22); -1 marks "outside -> zero fill"
+  int rowterm;
+  {
+    int yv = ty * kTileH - DIL + lane;
+    if (g.circ_h) {
+      yv += (yv < 0) ? g.Hv : 0;
+      yv -= (yv >= g.Hv) ? g.Hv : 0;
+    }
+    const bool yok = (unsigned)yv < (unsigned)g.Hv;
+    if (p.resize == 1) yv >>= 1;
+    else if (p.resize == 2) yv = __float2int_rd(((float)(yv * g.Hin) + 0.5f) * p.inv_hv);
+    rowterm = yok ? yv * g.Win * 128 : -1;
+  }
+  // sample base + this lane's chunk (+ column term) as 64-bit addresses; the plain base is also the valid dummy source of
+  // a zero-filled copy
+  const uint64_t xb64 = reinterpret_cast<uint64_t>(p.x + (int64_t)b * g.x_bstride + chunk * 8);
+  uint64_t cbase[NSUB];
+  bool cok[NSUB];
+#pragma unroll
+  for (int sub = 0; sub < NSUB; ++sub) {
+    int xv = tx * kTileW - DIL + ((lane + 32 * sub) >> 3);
+    if (g.circ_w) {
+      xv += (xv < 0) ? g.Wv : 0;
+      xv -= (xv >= g.Wv) ? g.Wv : 0;
+    }
+    cok[sub] = (unsigned)xv < (unsigned)g.Wv;
+    if (p.resize == 1) xv >>= 1;
+    else if (p.resize == 2) xv = __float2int_rd(((float)(xv * g.Win) + 0.5f) * p.inv_wv);
+    cbase[sub] = xb64 + (cok[sub] ? (uint64_t)(uint32_t)(xv * 128) : 0ull);
+    asm volatile("" : "+l"(cbase[sub]));  // opaque: one 64-bit add per copy, no re-derivation from the parts
+  }
+  if (wait_empty) hptx::mbar_wait(empty_bar, empty_parity);
+  if (!docopy) return;
+#pragma unroll
+  for (int hy = 0; hy < HH; ++hy) {
+    const int rt = __shfl_sync(0xFFFFFFFFu, rowterm, hy);
+    const bool rok = rt >= 0;
+    const uint64_t rtc = rok ? (uint64_t)(uint32_t)rt : 0ull;
+#pragma unroll
+    for (int sub = 0; sub < NSUB; ++sub) {
+      const int sl = lane + 32 * sub;
+      const int q = hy * HW + (sl >> 3);  // halo pixel = shared-memory row
+      const uint32_t dst = st + (uint32_t)q * 128u + (uint32_t)((chunk ^ (q & 7)) << 4);
+      if ((sub + 1) * 32 <= NSLOT || sl < NSLOT) hptx::cp_async16_zf(dst, cbase[sub] + rtc, !(rok && cok[sub]));
+    }
+  }
+}
+
 template <int NT, int kIssuers, int kAccs>
-__global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(const HaloParams p) {
+__global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
+    conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmap_y) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (hptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - hptx::smem_u32(smem_raw));
   constexpr uint32_t kWBytes = 9u * NT * 128u;
   const uint32_t w_base = smem_base;
   const uint32_t halo_base = smem_base + kWBytes;
-  const uint32_t stage_out = halo_base + (uint32_t)p.stages * (uint32_t)p.halo_bytes;  // 4 warps x 4 KB output staging
+  const uint32_t stage_out = halo_base + (uint32_t)p.stages * (uint32_t)p.halo_bytes;  // 4 warps x nbuf x 4 KB output staging
+  const uint32_t stage_bytes = 4u * (uint32_t)p.nbuf * 4096u;
   // bias folded into the GEMM: one extra K=16 MMA per tile, A = a "ones" tile (8 rows, every row group aliases it through
   // SBO = 0) with 1.0 in k = 0, 1; B = [Cout][k] with bias split as bf16 hi (k = 0) + lo (k = 1): hi + lo is exact to 2^-17.
-  const uint32_t bias_b = stage_out + 4u * 4096u;          // NT x 128 B, swizzled K-major like the filter
+  const uint32_t bias_b = stage_out + stage_bytes;         // NT x 128 B, swizzled K-major like the filter
   const uint32_t ones_a = bias_b + (uint32_t)NT * 128u;    // 8 x 128 B
   const uint32_t bar_base = ones_a + 1024u;
   // barriers: w, halo_full[4], halo_empty[4], acc_full[4], acc_empty[4]; then the TMEM slot
@@ -195,7 +288,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
   auto acc_empty = [&](int a) { return bar_base + 8u * (13 + a); };
   const uint32_t tmem_slot = bar_base + 8u * 17;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + 4 * 4096 + NT * 128 + 1024 + 8 * 17);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + stage_bytes + NT * 128 + 1024 + 8 * 17);
 
   const ConvGeom& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -218,7 +311,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
     hptx::tmem_relinquish();
   }
   if (p.bias) {
-    uint8_t* bb = smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + 4 * 4096;
+    uint8_t* bb = smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + stage_bytes;
     for (int e = tid; e < NT * 8; e += blockDim.x) {  // 16-byte chunks of the bias B tile
       const int n = e >> 3, ch = e & 7;
       uint4 v = make_uint4(0, 0, 0, 0);
@@ -255,22 +348,15 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
       for (int tap = 0; tap < 9; ++tap)
         hptx::bulk_g2s(w_base + (uint32_t)tap * NT * 128u, p.w + (int64_t)tap * g.Cout * 64, (uint32_t)NT * 128u, w_bar);
     }
-    // The halo is a rectangle and the source index map is separable: offset(hy, hx) = rowterm(hy) + colterm(hx).
-    // Per tile, lane l of every producer warp evaluates rowterm(l) and colterm(l) once (wrap / zero padding / nearest
-    // resize; -1 marks "outside -> zero fill"); every 16-byte copy then costs two shuffles and an add.  (The first
-    // version recomputed the full map per pixel: an 80-instruction dependent chain x 12 passes per tile made the
-    // producers -- not the tensor pipe -- the bottleneck: 25% tensor-pipe active in the round-1 profile.)
+    // The halo is a rectangle and the source index map is separable: offset(hy, hx) = rowterm(hy) + colterm(hx) (wrap / zero
+    // padding / nearest resize; "outside" -> zero fill).
     // One producer WARP per tile: warp w (< HS) takes tiles it = w, w+HS, ... and therefore always fills ring stage w.
     // (One warp per STAGE matters: mbarrier parity waits are only race free when the waits on a barrier are issued in phase
     // order by one agent.)  The per-tile fixed work (tile decode, separable terms, barrier round trip) is paid once per tile
-    // by one warp instead of by all four, and HS tiles are in flight independently.  8 lanes x 16 B per pixel, 4 pixels/pass.
-    const int chunk = lane & 7;
-    const int npx = p.HH * p.HW;
-    const int q_first = lane >> 3;                      // pixel of pass 0; +4 per pass
-    const int step_y = 4 / p.HW, step_x = 4 - step_y * p.HW;
-    const int hy_first = q_first / p.HW, hx_first = q_first - hy_first * p.HW;
-    const int npass = (npx + 3) >> 2;
-    // incremental tile decode: tile = (b * tiles_y + ty) * tiles_x + tx advances by 4 * gridDim.x per visit of this warp
+    // by one warp instead of by all four, and HS tiles are in flight independently.
+    // Copy schedule (halo_fill<DIL> above): per-lane fixed halo columns, one shuffle per halo row, ~5 instructions per copy.
+    const bool docopy = !(p.debug & 1);
+    // incremental tile decode: tile = (b * tiles_y + ty) * tiles_x + tx advances by HS * gridDim.x per visit of this warp
     int tile = (warp < HS) ? blockIdx.x + warp * (int)gridDim.x : p.ntiles;  // warps >= HS have no stage: idle
     int tx = tile % p.tiles_x, t2 = tile / p.tiles_x;
     int ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
@@ -279,50 +365,10 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
     const int adv_y = adv_t2 % p.tiles_y, adv_b = adv_t2 / p.tiles_y;
     for (int it = warp; tile < p.ntiles; it += HS, tile += adv) {
       const int s = warp;  // == it % HS
-      // separable source terms, one halo row / column per lane (HH <= 22, HW <= 14)
-      int rowterm, colterm;
-      {
-        int yv = ty * kTileH - g.dil + lane, xv = tx * kTileW - g.dil + lane;
-        if (g.circ_h) {
-          yv += (yv < 0) ? g.Hv : 0;
-          yv -= (yv >= g.Hv) ? g.Hv : 0;
-        }
-        if (g.circ_w) {
-          xv += (xv < 0) ? g.Wv : 0;
-          xv -= (xv >= g.Wv) ? g.Wv : 0;
-        }
-        const bool yok = (unsigned)yv < (unsigned)g.Hv, xok = (unsigned)xv < (unsigned)g.Wv;
-        if (p.resize == 1) {
-          yv >>= 1;
-          xv >>= 1;
-        } else if (p.resize == 2) {
-          yv = __float2int_rd(((float)(yv * g.Hin) + 0.5f) * p.inv_hv);
-          xv = __float2int_rd(((float)(xv * g.Win) + 0.5f) * p.inv_wv);
-        }
-        rowterm = yok ? yv * g.Win * 64 : -1;
-        colterm = xok ? xv * 64 : -1;
-      }
-      if (it >= HS) hptx::mbar_wait(halo_empty(s), ((it / HS) & 1) ^ 1);
       const uint32_t st = halo_base + (uint32_t)s * (uint32_t)p.halo_bytes;
-      const __nv_bfloat16* xb = p.x + (int64_t)b * g.x_bstride + chunk * 8;
-      int hy = hy_first, hx = hx_first;
-      int q = q_first;
-#pragma unroll 4
-      for (int pass = 0; pass < npass; ++pass, q += 4) {
-        const int rt = __shfl_sync(0xFFFFFFFFu, rowterm, hy & 31);
-        const int ct = __shfl_sync(0xFFFFFFFFu, colterm, hx & 31);
-        if (q < npx && !(p.debug & 1)) {
-          const bool ok = (rt | ct) >= 0;
-          const void* src = ok ? (const void*)(xb + (rt + ct)) : (const void*)p.x;
-          hptx::cp_async16(st + (uint32_t)q * 128u + (uint32_t)((chunk ^ (q & 7)) << 4), src, ok ? 16u : 0u);
-        }
-        hy += step_y;
-        hx += step_x;
-        if (hx >= p.HW) {
-          hx -= p.HW;
-          ++hy;
-        }
-      }
+      if (g.dil == 1) halo_fill<1>(p, tx, ty, b, lane, st, halo_empty(s), it >= HS, ((it / HS) & 1) ^ 1, docopy);
+      else if (g.dil == 2) halo_fill<2>(p, tx, ty, b, lane, st, halo_empty(s), it >= HS, ((it / HS) & 1) ^ 1, docopy);
+      else halo_fill<3>(p, tx, ty, b, lane, st, halo_empty(s), it >= HS, ((it / HS) & 1) ^ 1, docopy);
       hptx::cp_async_arrive_noinc(halo_full(s));
       // next tile of this warp
       tx += adv_x;
@@ -391,8 +437,9 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
     const bool y16 = is_h16(p.y_dtype);
     const int m = quad * 32 + lane;
     const int ty_l = m >> 3, tx_l = m & 7;
-    const uint32_t my_stage = stage_out + (uint32_t)(warp - (4 + kIssuers)) * 4096u;
-    const uint32_t my_row_st = my_stage + (uint32_t)lane * 128u;
+    const uint32_t my_stage0 = stage_out + (uint32_t)(warp - (4 + kIssuers)) * (uint32_t)p.nbuf * 4096u;
+    const bool tma = p.tma_store != 0;
+    uint32_t nstore = 0;  // staged tiles written by this warp so far (selects the staging buffer)
     const int rd_row = lane >> 3, rd_chunk = lane & 7;  // read-back: 4 rows per pass, 8 lanes x 16 B per row
     int it = 0;
     int tx, ty, b;
@@ -418,6 +465,18 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
       hptx::tc_fence_after();
       const uint32_t t_lane = tmem_acc + (uint32_t)(a * NT) + ((uint32_t)(quad * 32) << 16);
       for (int cg = 0; cg < ((p.debug & 2) ? 0 : g.Cout); cg += 64) {
+        // staging buffer of this (tile, channel group): with the TMA store the buffer is still being READ by the store issued
+        // nbuf groups ago -- lane 0 (the issuer, whose bulk groups track it) waits for that read before anyone overwrites it
+        const uint32_t my_stage = my_stage0 + ((p.nbuf == 2) ? (nstore & 1u) * 4096u : 0u);
+        const uint32_t my_row_st = my_stage + (uint32_t)lane * 128u;
+        ++nstore;
+        if (tma && y16) {
+          if (lane == 0) {
+            if (p.nbuf == 2) hptx::bulk_wait_read1();
+            else hptx::bulk_wait_read0();
+          }
+          __syncwarp();
+        }
 #pragma unroll
         for (int cc = 0; cc < 64; cc += 32) {
           const int c0 = cg + cc;
@@ -477,7 +536,18 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         }
-        if (y16) {
+        if (y16 && tma) {
+          // one TMA tensor store per staged tile: box = 64 channels x 8 pixels x 4 image rows, SWIZZLE_128B (the staged rows
+          // are in TMEM-lane order = (image row, pixel) order, chunk-swizzled by row & 7 = the map's shared-memory layout);
+          // partial tiles are clipped by the TMA unit
+          hptx::fence_proxy_async();
+          __syncwarp();
+          const int yq = ty * kTileH + quad * 4, xq = tx * kTileW;
+          if (lane == 0) {
+            if (yq < g.Hout && xq < g.Wout) hptx::tma_store_4d(&tmap_y, my_stage, cg, xq, yq, b);
+            hptx::bulk_commit();  // one group per staging, empty or not: wait_group.read N then counts stagings
+          }
+        } else if (y16) {
           __syncwarp();
           // staged row r = 4*pass + rd_row of this warp's quadrant = tile row quad*4 + pass/2, tile col 4*(pass&1) + rd_row
           const int yq = ty * kTileH + quad * 4, xq = tx * kTileW + rd_row;
@@ -505,6 +575,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1) conv_halo_kernel(c
       if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
       b += eadv_b;
     }
+    if (tma && lane == 0) hptx::bulk_wait_all();  // the staging buffers must outlive the stores that read them
   }
 
   hptx::tc_fence_before();
@@ -524,8 +595,40 @@ bool conv_halo_supported(const LnsConvDesc* d) {
          d->dil <= d->Hv && d->dil <= d->Wv;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// 4-D map of a 16-bit NHWC output [B][Hout][Wout][Cout] (batch stride in elements) whose box is one epilogue warp's staged
+// tile: 64 channels x kTileW pixels x 4 image rows, SWIZZLE_128B
+static bool make_y_tmap(CUtensorMap* tm, const LnsConvDesc* d) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wout, (cuuint64_t)d->Hout, (cuuint64_t)d->B};
+  const cuuint64_t strides[3] = {(cuuint64_t)d->Cout * 2ull, (cuuint64_t)d->Wout * d->Cout * 2ull, (cuuint64_t)d->y_bstride * 2ull};
+  const cuuint32_t box[4] = {64u, (cuuint32_t)kTileW, 4u, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = enc(tm, d->y_dtype == LNS_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->y, dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 template <int NT, int KI, int KA>
-static int launch_halo(const HaloParams& p, int smem_bytes, int grid, cudaStream_t stream) {
+static int launch_halo(const HaloParams& p, const CUtensorMap& tmap_y, int smem_bytes, int grid, cudaStream_t stream) {
   auto kern = conv_halo_kernel<NT, KI, KA>;
   static bool once = false;
   if (!once) {
@@ -536,7 +639,7 @@ static int launch_halo(const HaloParams& p, int smem_bytes, int grid, cudaStream
     }
     once = true;
   }
-  kern<<<grid, 32 * (4 + KI + 4), smem_bytes, stream>>>(p);
+  kern<<<grid, 32 * (4 + KI + 4), smem_bytes, stream>>>(p, tmap_y);
   return check_launch("conv_halo_kernel");
 }
 
@@ -580,7 +683,13 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
     p.debug = dbg ? atoi(dbg) : 0;
   }
   const int NT = d->Cout;
-  const int fixed = 9 * NT * 128 + 4 * 4096 /*output staging*/ + NT * 128 + 1024 /*bias + ones tiles*/ + 256 + 1024;
+  // output staging: two 4 KB buffers per epilogue warp when four halo stages still fit next to them, else one
+  p.nbuf = 2;
+  int fixed = 9 * NT * 128 + 4 * p.nbuf * 4096 /*output staging*/ + NT * 128 + 1024 /*bias + ones tiles*/ + 256 + 1024;
+  if ((227 * 1024 - fixed) / p.halo_bytes < 4) {
+    p.nbuf = 1;
+    fixed -= 4 * 4096;
+  }
   int stages = (227 * 1024 - fixed) / p.halo_bytes;
   if (stages > 4) stages = 4;
   LNS_REQUIRE(stages >= 2, "lns_conv2d(halo): shared memory too small for dilation %d with Cout %d", d->dil, d->Cout);
@@ -598,19 +707,36 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
     sms = cached;
   }
   int grid = p.ntiles < sms ? p.ntiles : sms;
+  // 16-bit outputs leave through TMA tensor stores (LNS_HALO_TMA=0: the staged read-back + st.global path)
+  CUtensorMap tmap_y;
+  memset(&tmap_y, 0, sizeof(tmap_y));
+  p.tma_store = 0;
+  {
+    const char* c = getenv("LNS_HALO_TMA");
+    const bool want = c ? atoi(c) != 0 : true;
+    if (want && is_h16_host(d->y_dtype) && d->Cout % 64 == 0 && ((int64_t)d->y_bstride * 2) % 16 == 0 && make_y_tmap(&tmap_y, d))
+      p.tma_store = 1;
+  }
+  if (getenv("LNS_HALO_VERBOSE"))
+    fprintf(stderr,
+            "conv_halo: B=%d %dx%d->%dx%d Cout=%d dil=%d resize=%d tma_store=%d nbuf=%d stages=%d grid=%d x=%p xbs=%lld y=%p ybs=%lld "
+            "act=%d bias=%d sbias=%d pre=%d res=%d xdt=%d ydt=%d circ=%d%d\n",
+            d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->dil, p.resize, p.tma_store, p.nbuf, stages, grid, d->x,
+            (long long)d->x_bstride, d->y, (long long)d->y_bstride, d->act, d->bias != nullptr, d->sample_bias != nullptr,
+            d->pre_add != nullptr, d->residual != nullptr, d->x_dtype, d->y_dtype, p.g.circ_h, p.g.circ_w);
   int cfg = 0;
   {
     const char* c = getenv("LNS_HALO_CFG");  // tuning: 0 = 1 issuer / 2 accumulators, 1 = 1/4, 2 = 2/4 (default, fastest on B200)
     cfg = c ? atoi(c) : 2;
   }
   if (NT == 64) {
-    if (cfg == 1) return launch_halo<64, 1, 4>(p, smem, grid, stream);
-    if (cfg == 2) return launch_halo<64, 2, 4>(p, smem, grid, stream);
-    return launch_halo<64, 1, 2>(p, smem, grid, stream);
+    if (cfg == 1) return launch_halo<64, 1, 4>(p, tmap_y, smem, grid, stream);
+    if (cfg == 2) return launch_halo<64, 2, 4>(p, tmap_y, smem, grid, stream);
+    return launch_halo<64, 1, 2>(p, tmap_y, smem, grid, stream);
   }
-  if (cfg == 1) return launch_halo<128, 1, 4>(p, smem, grid, stream);
-  if (cfg == 2) return launch_halo<128, 2, 4>(p, smem, grid, stream);
-  return launch_halo<128, 1, 2>(p, smem, grid, stream);
+  if (cfg == 1) return launch_halo<128, 1, 4>(p, tmap_y, smem, grid, stream);
+  if (cfg == 2) return launch_halo<128, 2, 4>(p, tmap_y, smem, grid, stream);
+  return launch_halo<128, 1, 2>(p, tmap_y, smem, grid, stream);
 }
 
 }  // namespace lns
