@@ -82,6 +82,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
                "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src)
                : "memory");
 }
+// TMA tensor load global -> shared (4-D tiled map), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -193,6 +200,7 @@ struct HaloParams {
   int resize;          // 0 none, 1 exact 2x nearest, 2 general nearest
   int nbuf;            // output staging buffers per epilogue warp (4 KB each): 2 when they fit, else 1
   int tma_store;       // 16-bit outputs leave through one TMA tensor store per staged tile (tmap_y is valid)
+  int tma_res;         // the 16-bit residual tile arrives through one TMA tensor load per epilogue warp (tmap_r is valid)
   float inv_hw, inv_hv, inv_wv;
   int debug;  // LNS_HALO_DEBUG bits (timing experiments only): 1 skip halo copies, 2 skip epilogue, 4 skip MMAs
 };
@@ -266,7 +274,7 @@ __device__ __forceinline__ void halo_fill(const HaloParams& p, int tx, int ty, i
 
 template <int NT, int kIssuers, int kAccs>
 __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
-    conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmap_y) {
+    conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (hptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - hptx::smem_u32(smem_raw));
@@ -275,20 +283,23 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
   const uint32_t halo_base = smem_base + kWBytes;
   const uint32_t stage_out = halo_base + (uint32_t)p.stages * (uint32_t)p.halo_bytes;  // 4 warps x nbuf x 4 KB output staging
   const uint32_t stage_bytes = 4u * (uint32_t)p.nbuf * 4096u;
+  const uint32_t res_stage0 = stage_out + stage_bytes;     // 4 warps x 4 KB residual tiles (only with tma_res)
+  const uint32_t res_bytes = p.tma_res ? 4u * 4096u : 0u;
   // bias folded into the GEMM: one extra K=16 MMA per tile, A = a "ones" tile (8 rows, every row group aliases it through
   // SBO = 0) with 1.0 in k = 0, 1; B = [Cout][k] with bias split as bf16 hi (k = 0) + lo (k = 1): hi + lo is exact to 2^-17.
-  const uint32_t bias_b = stage_out + stage_bytes;         // NT x 128 B, swizzled K-major like the filter
+  const uint32_t bias_b = stage_out + stage_bytes + res_bytes;         // NT x 128 B, swizzled K-major like the filter
   const uint32_t ones_a = bias_b + (uint32_t)NT * 128u;    // 8 x 128 B
   const uint32_t bar_base = ones_a + 1024u;
-  // barriers: w, halo_full[4], halo_empty[4], acc_full[4], acc_empty[4]; then the TMEM slot
+  // barriers: w, halo_full[4], halo_empty[4], acc_full[4], acc_empty[4]; then the TMEM slot; then res_full[4 epilogue warps]
   const uint32_t w_bar = bar_base;
   auto halo_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto halo_empty = [&](int s) { return bar_base + 8u * (5 + s); };
   auto acc_full = [&](int a) { return bar_base + 8u * (9 + a); };
   auto acc_empty = [&](int a) { return bar_base + 8u * (13 + a); };
   const uint32_t tmem_slot = bar_base + 8u * 17;
+  auto res_full = [&](int w) { return bar_base + 8u * (18 + w); };
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + stage_bytes + NT * 128 + 1024 + 8 * 17);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + stage_bytes + res_bytes + NT * 128 + 1024 + 8 * 17);
 
   const ConvGeom& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -304,6 +315,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
       hptx::mbar_init(acc_full(a), 1);
       hptx::mbar_init(acc_empty(a), 128);
     }
+    for (int w = 0; w < 4; ++w) hptx::mbar_init(res_full(w), 1);
     hptx::fence_mbar_init();
   }
   if (warp == 4) {
@@ -311,7 +323,7 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
     hptx::tmem_relinquish();
   }
   if (p.bias) {
-    uint8_t* bb = smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + stage_bytes;
+    uint8_t* bb = smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + stage_bytes + res_bytes;
     for (int e = tid; e < NT * 8; e += blockDim.x) {  // 16-byte chunks of the bias B tile
       const int n = e >> 3, ch = e & 7;
       uint4 v = make_uint4(0, 0, 0, 0);
@@ -440,6 +452,15 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
     const uint32_t my_stage0 = stage_out + (uint32_t)(warp - (4 + kIssuers)) * (uint32_t)p.nbuf * 4096u;
     const bool tma = p.tma_store != 0;
     uint32_t nstore = 0;  // staged tiles written by this warp so far (selects the staging buffer)
+    // residual through TMA (Cout = 64 only: one channel group per tile): the warp's 32 pixel rows x 128 B land in its own
+    // 4 KB tile, in the same row order and swizzle as the output staging, while the accumulator is still being computed.
+    // (Reading the residual straight from global memory cost 16 dependent 8-byte loads per thread, each touching 32 lines:
+    // the `res` layers ran 2.3x slower than the same layer without a residual.)
+    const bool tres = p.tma_res != 0;
+    const int ew = warp - (4 + kIssuers);
+    const uint32_t my_res = res_stage0 + (uint32_t)ew * 4096u;
+    const uint32_t my_res_row = my_res + (uint32_t)lane * 128u;
+    uint32_t res_phase = 0;
     const int rd_row = lane >> 3, rd_chunk = lane & 7;  // read-back: 4 rows per pass, 8 lanes x 16 B per row
     int it = 0;
     int tx, ty, b;
@@ -461,6 +482,14 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
       const int64_t yrow = (int64_t)b * g.y_bstride + pix * g.Cout;
       const int64_t prow = (int64_t)b * p.pre_add_bstride + pix * g.Cout;
       const int64_t rrow = (int64_t)b * p.res_bstride + pix * g.Cout;
+      const bool res_box = tres && (ty * kTileH + quad * 4) < g.Hout && (tx * kTileW) < g.Wout;  // warp uniform
+      if (res_box) {
+        __syncwarp();  // every lane has finished reading the previous tile's residual
+        if (lane == 0) {
+          hptx::mbar_expect_tx(res_full(ew), 4096u);
+          hptx::tma_load_4d(&tmap_r, my_res, res_full(ew), 0, tx * kTileW, ty * kTileH + quad * 4, b);
+        }
+      }
       hptx::mbar_wait(acc_full(a), (it / kAccs) & 1);
       hptx::tc_fence_after();
       const uint32_t t_lane = tmem_acc + (uint32_t)(a * NT) + ((uint32_t)(quad * 32) << 16);
@@ -508,7 +537,27 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
           }
-          if (row_ok && p.residual) {
+          if (tres) {
+            if (res_box) {
+              if (cc == 0) {
+                hptx::mbar_wait(res_full(ew), res_phase);
+                res_phase ^= 1u;
+              }
+#pragma unroll
+              for (int h4 = 0; h4 < 4; ++h4) {
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                             : "r"(my_res_row + (uint32_t)((((cc >> 3) + h4) ^ (lane & 7)) << 4)));
+                const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = (p.res_dtype == LNS_F16) ? unpack2_h16<true>(ww[j]) : unpack2_h16<false>(ww[j]);
+                  v[h4 * 8 + 2 * j] += f.x;
+                  v[h4 * 8 + 2 * j + 1] += f.y;
+                }
+              }
+            }
+          } else if (row_ok && p.residual) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 t = ld4_as_float(p.residual, p.res_dtype, rrow + c0 + j);
@@ -614,21 +663,22 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // 4-D map of a 16-bit NHWC output [B][Hout][Wout][Cout] (batch stride in elements) whose box is one epilogue warp's staged
 // tile: 64 channels x kTileW pixels x 4 image rows, SWIZZLE_128B
-static bool make_y_tmap(CUtensorMap* tm, const LnsConvDesc* d) {
+static bool make_y_tmap(CUtensorMap* tm, const LnsConvDesc* d, const void* base, int dtype, int64_t bstride) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wout, (cuuint64_t)d->Hout, (cuuint64_t)d->B};
-  const cuuint64_t strides[3] = {(cuuint64_t)d->Cout * 2ull, (cuuint64_t)d->Wout * d->Cout * 2ull, (cuuint64_t)d->y_bstride * 2ull};
+  const cuuint64_t strides[3] = {(cuuint64_t)d->Cout * 2ull, (cuuint64_t)d->Wout * d->Cout * 2ull, (cuuint64_t)bstride * 2ull};
   const cuuint32_t box[4] = {64u, (cuuint32_t)kTileW, 4u, 1u};
   const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  const CUresult r = enc(tm, d->y_dtype == LNS_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->y, dims,
+  const CUresult r = enc(tm, dtype == LNS_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
 template <int NT, int KI, int KA>
-static int launch_halo(const HaloParams& p, const CUtensorMap& tmap_y, int smem_bytes, int grid, cudaStream_t stream) {
+static int launch_halo(const HaloParams& p, const CUtensorMap& tmap_y, const CUtensorMap& tmap_r, int smem_bytes, int grid,
+                       cudaStream_t stream) {
   auto kern = conv_halo_kernel<NT, KI, KA>;
   static bool once = false;
   if (!once) {
@@ -639,7 +689,7 @@ static int launch_halo(const HaloParams& p, const CUtensorMap& tmap_y, int smem_
     }
     once = true;
   }
-  kern<<<grid, 32 * (4 + KI + 4), smem_bytes, stream>>>(p, tmap_y);
+  kern<<<grid, 32 * (4 + KI + 4), smem_bytes, stream>>>(p, tmap_y, tmap_r);
   return check_launch("conv_halo_kernel");
 }
 
@@ -694,7 +744,6 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
   if (stages > 4) stages = 4;
   LNS_REQUIRE(stages >= 2, "lns_conv2d(halo): shared memory too small for dilation %d with Cout %d", d->dil, d->Cout);
   p.stages = stages;
-  const int smem = fixed + stages * p.halo_bytes;
   int sms = 148;
   {
     static int cached = 0;
@@ -714,29 +763,44 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
   {
     const char* c = getenv("LNS_HALO_TMA");
     const bool want = c ? atoi(c) != 0 : true;
-    if (want && is_h16_host(d->y_dtype) && d->Cout % 64 == 0 && ((int64_t)d->y_bstride * 2) % 16 == 0 && make_y_tmap(&tmap_y, d))
+    if (want && is_h16_host(d->y_dtype) && d->Cout % 64 == 0 && ((int64_t)d->y_bstride * 2) % 16 == 0 &&
+        make_y_tmap(&tmap_y, d, d->y, d->y_dtype, d->y_bstride))
       p.tma_store = 1;
+  }
+  // a 16-bit residual arrives through TMA tensor loads when its 16 KB of tiles fit next to the 4-stage ring (Cout = 64)
+  CUtensorMap tmap_r;
+  memset(&tmap_r, 0, sizeof(tmap_r));
+  p.tma_res = 0;
+  int smem = fixed + stages * p.halo_bytes;
+  {
+    const char* c = getenv("LNS_HALO_TMA_RES");
+    const bool want = c ? atoi(c) != 0 : true;
+    if (want && d->residual && is_h16_host(d->res_dtype) && d->Cout == 64 && smem + 4 * 4096 <= 227 * 1024 &&
+        ((int64_t)d->res_bstride * 2) % 16 == 0 && make_y_tmap(&tmap_r, d, d->residual, d->res_dtype, d->res_bstride)) {
+      p.tma_res = 1;
+      smem += 4 * 4096;
+    }
   }
   if (getenv("LNS_HALO_VERBOSE"))
     fprintf(stderr,
             "conv_halo: B=%d %dx%d->%dx%d Cout=%d dil=%d resize=%d tma_store=%d nbuf=%d stages=%d grid=%d x=%p xbs=%lld y=%p ybs=%lld "
-            "act=%d bias=%d sbias=%d pre=%d res=%d xdt=%d ydt=%d circ=%d%d\n",
+            "act=%d bias=%d sbias=%d pre=%d res=%d tma_res=%d xdt=%d ydt=%d circ=%d%d\n",
             d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->dil, p.resize, p.tma_store, p.nbuf, stages, grid, d->x,
             (long long)d->x_bstride, d->y, (long long)d->y_bstride, d->act, d->bias != nullptr, d->sample_bias != nullptr,
-            d->pre_add != nullptr, d->residual != nullptr, d->x_dtype, d->y_dtype, p.g.circ_h, p.g.circ_w);
+            d->pre_add != nullptr, d->residual != nullptr, p.tma_res, d->x_dtype, d->y_dtype, p.g.circ_h, p.g.circ_w);
   int cfg = 0;
   {
     const char* c = getenv("LNS_HALO_CFG");  // tuning: 0 = 1 issuer / 2 accumulators, 1 = 1/4, 2 = 2/4 (default, fastest on B200)
     cfg = c ? atoi(c) : 2;
   }
   if (NT == 64) {
-    if (cfg == 1) return launch_halo<64, 1, 4>(p, tmap_y, smem, grid, stream);
-    if (cfg == 2) return launch_halo<64, 2, 4>(p, tmap_y, smem, grid, stream);
-    return launch_halo<64, 1, 2>(p, tmap_y, smem, grid, stream);
+    if (cfg == 1) return launch_halo<64, 1, 4>(p, tmap_y, tmap_r, smem, grid, stream);
+    if (cfg == 2) return launch_halo<64, 2, 4>(p, tmap_y, tmap_r, smem, grid, stream);
+    return launch_halo<64, 1, 2>(p, tmap_y, tmap_r, smem, grid, stream);
   }
-  if (cfg == 1) return launch_halo<128, 1, 4>(p, tmap_y, smem, grid, stream);
-  if (cfg == 2) return launch_halo<128, 2, 4>(p, tmap_y, smem, grid, stream);
-  return launch_halo<128, 1, 2>(p, tmap_y, smem, grid, stream);
+  if (cfg == 1) return launch_halo<128, 1, 4>(p, tmap_y, tmap_r, smem, grid, stream);
+  if (cfg == 2) return launch_halo<128, 2, 4>(p, tmap_y, tmap_r, smem, grid, stream);
+  return launch_halo<128, 1, 2>(p, tmap_y, tmap_r, smem, grid, stream);
 }
 
 }  // namespace lns
