@@ -4,6 +4,8 @@
 //
 // GEMM view: M = B*Hout*Wout output pixels, N = Cout, K = KH*KW*Cin.  64 x BN tile per CTA, 16-deep K chunks,
 // 4 x (BN/16) accumulators per thread, fp32 FMA accumulation in a fixed order (deterministic, batch independent).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lns {
@@ -239,7 +241,13 @@ int conv2d_simt(const LnsConvDesc* d, cudaStream_t stream) {
   p.M = (int)M;
   if (lift_ok(d)) {
     const int ppp = 256 / (d->Cout / 8);
-    int ppb = ppp * 8;                                     // 8 passes per block ...
+    static int passes = 0;
+    if (!passes) {
+      const char* c = getenv("LNS_LIFT_PASSES");
+      passes = c ? atoi(c) : 8;
+      if (passes < 1) passes = 1;
+    }
+    int ppb = ppp * passes;                                // 8 passes per block ...
     while ((M + ppb - 1) / ppb > 148 * 16) ppb *= 2;       // ... more when the grid would exceed 16 blocks per SM
     const size_t smem = ((size_t)d->Cin * d->Cout + d->Cout) * sizeof(float);
     lift1x1_kernel<<<(unsigned)((M + ppb - 1) / ppb), 256, smem, stream>>>(p, ppb);
