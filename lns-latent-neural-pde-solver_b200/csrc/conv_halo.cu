@@ -272,6 +272,204 @@ __device__ __forceinline__ void halo_fill(const HaloParams& p, int tx, int ty, i
   }
 }
 
+// The epilogue warps' loop, compiled twice per kernel: TRES = the 16-bit residual arrives by TMA (see below).  Two
+// instantiations rather than a runtime flag: with both paths in one body the residual-free layers lost 20 % (1076 -> 854
+// TFLOP/s at 64 -> 64 @ 64x64) to the register pressure of the residual path.
+template <int NT, int kIssuers, int kAccs, bool TRES>
+__device__ __forceinline__ void halo_epilogue(const HaloParams& p, const CUtensorMap& tmap_y, const CUtensorMap& tmap_r, uint32_t tmem_acc,
+                                              uint32_t stage_out, uint32_t res_stage0, uint32_t acc_full0, uint32_t acc_empty0,
+                                              uint32_t res_full0, int warp, int lane) {
+  const ConvGeom& g = p.g;
+  auto acc_full = [&](int a) { return acc_full0 + 8u * a; };
+  auto acc_empty = [&](int a) { return acc_empty0 + 8u * a; };
+  auto res_full = [&](int w) { return res_full0 + 8u * w; };
+  // TMEM lane = tile pixel (row m = 8*tile_row + tile_col), so a thread owns one pixel's channels.  Writing them
+  // straight to global memory makes every store instruction touch 32 different 128-byte lines.  bf16 outputs are
+  // therefore staged per 64-channel group through a per-warp 32 x 128 B tile (16-byte chunks XOR-swizzled with the
+  // row so both the row-wise writes and the line-wise reads are conflict free) and leave as full-line stores:
+  // 8 consecutive rows = 8 consecutive pixels = 1 KB contiguous in NHWC.
+  const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+  const bool y16 = is_h16(p.y_dtype);
+  const int m = quad * 32 + lane;
+  const int ty_l = m >> 3, tx_l = m & 7;
+  const uint32_t my_stage0 = stage_out + (uint32_t)(warp - (4 + kIssuers)) * (uint32_t)p.nbuf * 4096u;
+  const bool tma = p.tma_store != 0;
+  uint32_t nstore = 0;  // staged tiles written by this warp so far (selects the staging buffer)
+  // residual through TMA (Cout = 64 only: one channel group per tile): the warp's 32 pixel rows x 128 B land in its own
+  // 4 KB tile, in the same row order and swizzle as the output staging, while the accumulator is still being computed.
+  // (Reading the residual straight from global memory cost 16 dependent 8-byte loads per thread, each touching 32 lines:
+  // the `res` layers ran 2.3x slower than the same layer without a residual.)
+  constexpr bool tres = TRES;
+  const int ew = warp - (4 + kIssuers);
+  const uint32_t my_res = res_stage0 + (uint32_t)ew * 4096u;
+  const uint32_t my_res_row = my_res + (uint32_t)lane * 128u;
+  uint32_t res_phase = 0;
+  const int rd_row = lane >> 3, rd_chunk = lane & 7;  // read-back: 4 rows per pass, 8 lanes x 16 B per row
+  int it = 0;
+  int tx, ty, b;
+  {
+    const int t0 = blockIdx.x;
+    tx = t0 % p.tiles_x;
+    const int t2 = t0 / p.tiles_x;
+    ty = t2 % p.tiles_y;
+    b = t2 / p.tiles_y;
+  }
+  const int eadv = (int)gridDim.x;
+  const int eadv_x = eadv % p.tiles_x, eadv_t2 = eadv / p.tiles_x;
+  const int eadv_y = eadv_t2 % p.tiles_y, eadv_b = eadv_t2 / p.tiles_y;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int a = it % kAccs;
+    const int yo = ty * kTileH + ty_l, xo = tx * kTileW + tx_l;
+    const bool row_ok = yo < g.Hout && xo < g.Wout;
+    const int64_t pix = (int64_t)yo * g.Wout + xo;
+    const int64_t yrow = (int64_t)b * g.y_bstride + pix * g.Cout;
+    const int64_t prow = (int64_t)b * p.pre_add_bstride + pix * g.Cout;
+    const int64_t rrow = (int64_t)b * p.res_bstride + pix * g.Cout;
+    const bool res_box = tres && (ty * kTileH + quad * 4) < g.Hout && (tx * kTileW) < g.Wout;  // warp uniform
+    if (res_box) {
+      __syncwarp();  // every lane has finished reading the previous tile's residual
+      if (lane == 0) {
+        hptx::mbar_expect_tx(res_full(ew), 4096u);
+        hptx::tma_load_4d(&tmap_r, my_res, res_full(ew), 0, tx * kTileW, ty * kTileH + quad * 4, b);
+      }
+    }
+    hptx::mbar_wait(acc_full(a), (it / kAccs) & 1);
+    hptx::tc_fence_after();
+    const uint32_t t_lane = tmem_acc + (uint32_t)(a * NT) + ((uint32_t)(quad * 32) << 16);
+    for (int cg = 0; cg < ((p.debug & 2) ? 0 : g.Cout); cg += 64) {
+      // staging buffer of this (tile, channel group): with the TMA store the buffer is still being READ by the store issued
+      // nbuf groups ago -- lane 0 (the issuer, whose bulk groups track it) waits for that read before anyone overwrites it
+      const uint32_t my_stage = my_stage0 + ((p.nbuf == 2) ? (nstore & 1u) * 4096u : 0u);
+      const uint32_t my_row_st = my_stage + (uint32_t)lane * 128u;
+      ++nstore;
+      if (tma && y16) {
+        if (lane == 0) {
+          if (p.nbuf == 2) hptx::bulk_wait_read1();
+          else hptx::bulk_wait_read0();
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 32) {
+        const int c0 = cg + cc;
+        uint32_t raw[32];
+        __syncwarp();
+        hptx::tmem_ld32(t_lane + (uint32_t)c0, raw);
+        hptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        // (bias: already in the accumulator -- folded into the GEMM by the issue warps)
+        if (row_ok) {
+          if (p.sample_bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 t = __ldg(reinterpret_cast<const float4*>(p.sample_bias + (int64_t)b * g.Cout + c0 + j));
+              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+            }
+          }
+          if (p.pre_add) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 t = ld4_as_float(p.pre_add, p.pre_add_dtype, prow + c0 + j);
+              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+            }
+          }
+        }
+        if (p.act != LNS_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
+        }
+        if (tres) {
+          if (res_box) {
+            if (cc == 0) {
+              hptx::mbar_wait(res_full(ew), res_phase);
+              res_phase ^= 1u;
+            }
+#pragma unroll
+            for (int h4 = 0; h4 < 4; ++h4) {
+              uint32_t w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                           : "r"(my_res_row + (uint32_t)((((cc >> 3) + h4) ^ (lane & 7)) << 4)));
+              const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = (p.res_dtype == LNS_F16) ? unpack2_h16<true>(ww[j]) : unpack2_h16<false>(ww[j]);
+                v[h4 * 8 + 2 * j] += f.x;
+                v[h4 * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          }
+        } else if (row_ok && p.residual) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 t = ld4_as_float(p.residual, p.res_dtype, rrow + c0 + j);
+            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          }
+        }
+        if (y16) {
+#pragma unroll
+          for (int h4 = 0; h4 < 4; ++h4) {
+            uint32_t pk[4];
+            if (p.y_dtype == LNS_F16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pk[j] = pack2_h16<true>(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pk[j] = pack2_h16<false>(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
+            }
+            const int ch = (cc >> 3) + h4;  // 16-byte chunk index inside the 128-byte staged row
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_st + (uint32_t)((ch ^ (lane & 7)) << 4)),
+                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          }
+        } else if (row_ok) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yrow + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      if (y16 && tma) {
+        // one TMA tensor store per staged tile: box = 64 channels x 8 pixels x 4 image rows, SWIZZLE_128B (the staged rows
+        // are in TMEM-lane order = (image row, pixel) order, chunk-swizzled by row & 7 = the map's shared-memory layout);
+        // partial tiles are clipped by the TMA unit
+        hptx::fence_proxy_async();
+        __syncwarp();
+        const int yq = ty * kTileH + quad * 4, xq = tx * kTileW;
+        if (lane == 0) {
+          if (yq < g.Hout && xq < g.Wout) hptx::tma_store_4d(&tmap_y, my_stage, cg, xq, yq, b);
+          hptx::bulk_commit();  // one group per staging, empty or not: wait_group.read N then counts stagings
+        }
+      } else if (y16) {
+        __syncwarp();
+        // staged row r = 4*pass + rd_row of this warp's quadrant = tile row quad*4 + pass/2, tile col 4*(pass&1) + rd_row
+        const int yq = ty * kTileH + quad * 4, xq = tx * kTileW + rd_row;
+        __nv_bfloat16* qbase = reinterpret_cast<__nv_bfloat16*>(p.y) + (int64_t)b * g.y_bstride +
+                               ((int64_t)yq * g.Wout + xq) * g.Cout + cg + rd_chunk * 8;
+        const int64_t row_stride = (int64_t)g.Wout * g.Cout;
+        const bool interior = (ty + 1) * kTileH <= g.Hout && (tx + 1) * kTileW <= g.Wout;  // warp uniform
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+          const int r = pass * 4 + rd_row;
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                       : "r"(my_stage + (uint32_t)r * 128u + (uint32_t)((rd_chunk ^ (r & 7)) << 4)));
+          if (interior || (yq + (pass >> 1) < g.Hout && xq + 4 * (pass & 1) < g.Wout))
+            *reinterpret_cast<uint4*>(qbase + (pass >> 1) * row_stride + (pass & 1) * 4 * g.Cout) = make_uint4(w0, w1, w2, w3);
+        }
+        __syncwarp();
+      }
+    }
+    hptx::tc_fence_before();
+    hptx::mbar_arrive(acc_empty(a));
+    tx += eadv_x;
+    if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+    ty += eadv_y;
+    if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
+    b += eadv_b;
+  }
+  if (tma && lane == 0) hptx::bulk_wait_all();  // the staging buffers must outlive the stores that read them
+}
+
 template <int NT, int kIssuers, int kAccs>
 __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
     conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r) {
@@ -440,191 +638,10 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
     __syncwarp();
   } else {
     // ============================== epilogue (last 4 warps) ==============================
-    // TMEM lane = tile pixel (row m = 8*tile_row + tile_col), so a thread owns one pixel's channels.  Writing them
-    // straight to global memory makes every store instruction touch 32 different 128-byte lines.  bf16 outputs are
-    // therefore staged per 64-channel group through a per-warp 32 x 128 B tile (16-byte chunks XOR-swizzled with the
-    // row so both the row-wise writes and the line-wise reads are conflict free) and leave as full-line stores:
-    // 8 consecutive rows = 8 consecutive pixels = 1 KB contiguous in NHWC.
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const bool y16 = is_h16(p.y_dtype);
-    const int m = quad * 32 + lane;
-    const int ty_l = m >> 3, tx_l = m & 7;
-    const uint32_t my_stage0 = stage_out + (uint32_t)(warp - (4 + kIssuers)) * (uint32_t)p.nbuf * 4096u;
-    const bool tma = p.tma_store != 0;
-    uint32_t nstore = 0;  // staged tiles written by this warp so far (selects the staging buffer)
-    // residual through TMA (Cout = 64 only: one channel group per tile): the warp's 32 pixel rows x 128 B land in its own
-    // 4 KB tile, in the same row order and swizzle as the output staging, while the accumulator is still being computed.
-    // (Reading the residual straight from global memory cost 16 dependent 8-byte loads per thread, each touching 32 lines:
-    // the `res` layers ran 2.3x slower than the same layer without a residual.)
-    const bool tres = p.tma_res != 0;
-    const int ew = warp - (4 + kIssuers);
-    const uint32_t my_res = res_stage0 + (uint32_t)ew * 4096u;
-    const uint32_t my_res_row = my_res + (uint32_t)lane * 128u;
-    uint32_t res_phase = 0;
-    const int rd_row = lane >> 3, rd_chunk = lane & 7;  // read-back: 4 rows per pass, 8 lanes x 16 B per row
-    int it = 0;
-    int tx, ty, b;
-    {
-      const int t0 = blockIdx.x;
-      tx = t0 % p.tiles_x;
-      const int t2 = t0 / p.tiles_x;
-      ty = t2 % p.tiles_y;
-      b = t2 / p.tiles_y;
-    }
-    const int eadv = (int)gridDim.x;
-    const int eadv_x = eadv % p.tiles_x, eadv_t2 = eadv / p.tiles_x;
-    const int eadv_y = eadv_t2 % p.tiles_y, eadv_b = eadv_t2 / p.tiles_y;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int a = it % kAccs;
-      const int yo = ty * kTileH + ty_l, xo = tx * kTileW + tx_l;
-      const bool row_ok = yo < g.Hout && xo < g.Wout;
-      const int64_t pix = (int64_t)yo * g.Wout + xo;
-      const int64_t yrow = (int64_t)b * g.y_bstride + pix * g.Cout;
-      const int64_t prow = (int64_t)b * p.pre_add_bstride + pix * g.Cout;
-      const int64_t rrow = (int64_t)b * p.res_bstride + pix * g.Cout;
-      const bool res_box = tres && (ty * kTileH + quad * 4) < g.Hout && (tx * kTileW) < g.Wout;  // warp uniform
-      if (res_box) {
-        __syncwarp();  // every lane has finished reading the previous tile's residual
-        if (lane == 0) {
-          hptx::mbar_expect_tx(res_full(ew), 4096u);
-          hptx::tma_load_4d(&tmap_r, my_res, res_full(ew), 0, tx * kTileW, ty * kTileH + quad * 4, b);
-        }
-      }
-      hptx::mbar_wait(acc_full(a), (it / kAccs) & 1);
-      hptx::tc_fence_after();
-      const uint32_t t_lane = tmem_acc + (uint32_t)(a * NT) + ((uint32_t)(quad * 32) << 16);
-      for (int cg = 0; cg < ((p.debug & 2) ? 0 : g.Cout); cg += 64) {
-        // staging buffer of this (tile, channel group): with the TMA store the buffer is still being READ by the store issued
-        // nbuf groups ago -- lane 0 (the issuer, whose bulk groups track it) waits for that read before anyone overwrites it
-        const uint32_t my_stage = my_stage0 + ((p.nbuf == 2) ? (nstore & 1u) * 4096u : 0u);
-        const uint32_t my_row_st = my_stage + (uint32_t)lane * 128u;
-        ++nstore;
-        if (tma && y16) {
-          if (lane == 0) {
-            if (p.nbuf == 2) hptx::bulk_wait_read1();
-            else hptx::bulk_wait_read0();
-          }
-          __syncwarp();
-        }
-#pragma unroll
-        for (int cc = 0; cc < 64; cc += 32) {
-          const int c0 = cg + cc;
-          uint32_t raw[32];
-          __syncwarp();
-          hptx::tmem_ld32(t_lane + (uint32_t)c0, raw);
-          hptx::tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          // (bias: already in the accumulator -- folded into the GEMM by the issue warps)
-          if (row_ok) {
-            if (p.sample_bias) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 t = __ldg(reinterpret_cast<const float4*>(p.sample_bias + (int64_t)b * g.Cout + c0 + j));
-                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-              }
-            }
-            if (p.pre_add) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 t = ld4_as_float(p.pre_add, p.pre_add_dtype, prow + c0 + j);
-                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-              }
-            }
-          }
-          if (p.act != LNS_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
-          }
-          if (tres) {
-            if (res_box) {
-              if (cc == 0) {
-                hptx::mbar_wait(res_full(ew), res_phase);
-                res_phase ^= 1u;
-              }
-#pragma unroll
-              for (int h4 = 0; h4 < 4; ++h4) {
-                uint32_t w0, w1, w2, w3;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                             : "r"(my_res_row + (uint32_t)((((cc >> 3) + h4) ^ (lane & 7)) << 4)));
-                const uint32_t ww[4] = {w0, w1, w2, w3};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = (p.res_dtype == LNS_F16) ? unpack2_h16<true>(ww[j]) : unpack2_h16<false>(ww[j]);
-                  v[h4 * 8 + 2 * j] += f.x;
-                  v[h4 * 8 + 2 * j + 1] += f.y;
-                }
-              }
-            }
-          } else if (row_ok && p.residual) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 t = ld4_as_float(p.residual, p.res_dtype, rrow + c0 + j);
-              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-            }
-          }
-          if (y16) {
-#pragma unroll
-            for (int h4 = 0; h4 < 4; ++h4) {
-              uint32_t pk[4];
-              if (p.y_dtype == LNS_F16) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pk[j] = pack2_h16<true>(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pk[j] = pack2_h16<false>(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
-              }
-              const int ch = (cc >> 3) + h4;  // 16-byte chunk index inside the 128-byte staged row
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_st + (uint32_t)((ch ^ (lane & 7)) << 4)),
-                           "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-            }
-          } else if (row_ok) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yrow + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-        }
-        if (y16 && tma) {
-          // one TMA tensor store per staged tile: box = 64 channels x 8 pixels x 4 image rows, SWIZZLE_128B (the staged rows
-          // are in TMEM-lane order = (image row, pixel) order, chunk-swizzled by row & 7 = the map's shared-memory layout);
-          // partial tiles are clipped by the TMA unit
-          hptx::fence_proxy_async();
-          __syncwarp();
-          const int yq = ty * kTileH + quad * 4, xq = tx * kTileW;
-          if (lane == 0) {
-            if (yq < g.Hout && xq < g.Wout) hptx::tma_store_4d(&tmap_y, my_stage, cg, xq, yq, b);
-            hptx::bulk_commit();  // one group per staging, empty or not: wait_group.read N then counts stagings
-          }
-        } else if (y16) {
-          __syncwarp();
-          // staged row r = 4*pass + rd_row of this warp's quadrant = tile row quad*4 + pass/2, tile col 4*(pass&1) + rd_row
-          const int yq = ty * kTileH + quad * 4, xq = tx * kTileW + rd_row;
-          __nv_bfloat16* qbase = reinterpret_cast<__nv_bfloat16*>(p.y) + (int64_t)b * g.y_bstride +
-                                 ((int64_t)yq * g.Wout + xq) * g.Cout + cg + rd_chunk * 8;
-          const int64_t row_stride = (int64_t)g.Wout * g.Cout;
-          const bool interior = (ty + 1) * kTileH <= g.Hout && (tx + 1) * kTileW <= g.Wout;  // warp uniform
-#pragma unroll
-          for (int pass = 0; pass < 8; ++pass) {
-            const int r = pass * 4 + rd_row;
-            uint32_t w0, w1, w2, w3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                         : "r"(my_stage + (uint32_t)r * 128u + (uint32_t)((rd_chunk ^ (r & 7)) << 4)));
-            if (interior || (yq + (pass >> 1) < g.Hout && xq + 4 * (pass & 1) < g.Wout))
-              *reinterpret_cast<uint4*>(qbase + (pass >> 1) * row_stride + (pass & 1) * 4 * g.Cout) = make_uint4(w0, w1, w2, w3);
-          }
-          __syncwarp();
-        }
-      }
-      hptx::tc_fence_before();
-      hptx::mbar_arrive(acc_empty(a));
-      tx += eadv_x;
-      if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
-      ty += eadv_y;
-      if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
-      b += eadv_b;
-    }
-    if (tma && lane == 0) hptx::bulk_wait_all();  // the staging buffers must outlive the stores that read them
+    if (p.tma_res)
+      halo_epilogue<NT, kIssuers, kAccs, true>(p, tmap_y, tmap_r, tmem_acc, stage_out, res_stage0, acc_full(0), acc_empty(0), res_full(0), warp, lane);
+    else
+      halo_epilogue<NT, kIssuers, kAccs, false>(p, tmap_y, tmap_r, tmem_acc, stage_out, res_stage0, acc_full(0), acc_empty(0), res_full(0), warp, lane);
   }
 
   hptx::tc_fence_before();

@@ -15,6 +15,8 @@
 //     block feeds BOTH MMA tiles: L2 -> SM traffic per 128-pixel tile 590 KB -> (102 + 295) / 2 = 199 KB.
 // Warp roles (320 threads): warps 0-3 halo producers, warp 4 MMA issuer + TMEM owner, warps 5-8 epilogue, warp 9 filter
 // ring producer.  Four 128-column accumulators: the epilogue of super tile i overlaps tile i+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lns {
@@ -95,7 +97,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 namespace {
 constexpr int kLatThreads = 320;
-constexpr int kBStages = 3;
+constexpr int kBMax = 8;     // most filter-ring stages (barrier slots); the launch uses as many as fit, at least 3
 constexpr uint32_t kBBytes = 128u * 128u;  // one (tap, slab) filter block: 128 output channels x 64 input channels x 2 B
 
 __device__ __forceinline__ uint64_t desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
@@ -121,24 +123,177 @@ struct LatentParams {
   int HWd;             // halo width = height = 8 + 2*dil
   int plane_bytes;     // one (tile, slab) halo plane: HWd * 2 * HWd rows x 128 B (a multiple of 1024)
   int x_f16;
+  int bstages;         // filter ring depth (3 .. kBMax)
   float inv_hwd;
 };
 }  // namespace
+
+// Epilogue of the four epilogue warps, compiled twice: RES16 = a 16-bit residual travels through the staging tile (see below).
+// (Two instantiations, not a runtime flag: the eight parked residual vectors of the RES16 path otherwise cost the GELU
+// loop of the residual-free layers its registers -- 44 -> 59 us per launch when both shared one body.)
+template <bool RES16>
+__device__ __forceinline__ void latent_epilogue(const LatentParams& p, uint32_t tmem_acc, uint32_t stage_out, uint32_t acc_full0,
+                                                uint32_t acc_empty0, int warp, int lane) {
+  auto acc_full = [&](int a) { return acc_full0 + 8u * a; };
+  auto acc_empty = [&](int a) { return acc_empty0 + 8u * a; };
+  const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+  const int m = quad * 32 + lane;
+  const int yo = m >> 4, s_of = (m >> 3) & 1, xo = m & 7;
+  const bool y16 = is_h16(p.y_dtype);
+  const uint32_t my_stage = stage_out + (uint32_t)(warp - 5) * 4096u;
+  const uint32_t my_row_st = my_stage + (uint32_t)lane * 128u;
+  const int rd_row = lane >> 3, rd_chunk = lane & 7;
+  // 16-bit residual: the warp's 32 rows x 128 B of the NEXT (tile, channel group) are fetched one step ahead with
+  // coalesced 16-byte loads (8 lanes per pixel row: full 128-byte lines) and parked in registers; they go through the
+  // output staging tile (written before the accumulator is read, each thread then reads ITS row and overwrites it with the
+  // result).  Reading the residual row by row straight from global memory -- 16 dependent 8-byte loads per thread, 32
+  // lines per instruction -- made the `res` layers 45% slower than the same layer without a residual.
+  uint4 rq[8];
+  auto res_issue = [&](int sup_, int t_, int cg_) {
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int mm = quad * 32 + pass * 4 + rd_row;
+      const int bb = sup_ * 4 + t_ * 2 + ((mm >> 3) & 1);
+      rq[pass] = make_uint4(0u, 0u, 0u, 0u);
+      if (bb < p.B)
+        rq[pass] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + (int64_t)bb * p.res_bstride +
+                                                        (int64_t)((mm >> 4) * 8 + (mm & 7)) * 128 + cg_ + rd_chunk * 8));
+    }
+  };
+  if (RES16 && (int)blockIdx.x < p.nsuper) res_issue(blockIdx.x, 0, 0);
+  int it = 0;
+  for (int sup = blockIdx.x; sup < p.nsuper; sup += gridDim.x, ++it) {
+    const int a = it & 1;
+    lptx::mbar_wait(acc_full(a), (uint32_t)((it >> 1) & 1));
+    lptx::tc_fence_after();
+    for (int t = 0; t < 2; ++t) {
+      const int b = sup * 4 + t * 2 + s_of;
+      const bool row_ok = b < p.B;
+      const int64_t pix = yo * 8 + xo;
+      const int64_t yrow = (int64_t)b * p.y_bstride + pix * 128;
+      const int64_t rrow = (int64_t)b * p.res_bstride + pix * 128;
+      const uint32_t t_lane = tmem_acc + (uint32_t)((a * 2 + t) * 128) + ((uint32_t)(quad * 32) << 16);
+      for (int cg = 0; cg < 128; cg += 64) {
+        if (RES16) {
+          // (the staging tile is free: the previous step's read-back ended with a __syncwarp)
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int r = pass * 4 + rd_row;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_stage + (uint32_t)r * 128u + (uint32_t)((rd_chunk ^ (r & 7)) << 4)),
+                         "r"(rq[pass].x), "r"(rq[pass].y), "r"(rq[pass].z), "r"(rq[pass].w) : "memory");
+          }
+          __syncwarp();
+          if (cg == 0) res_issue(sup, t, 64);
+          else if (t == 0) res_issue(sup, 1, 0);
+          else if (sup + (int)gridDim.x < p.nsuper) res_issue(sup + (int)gridDim.x, 0, 0);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 64; cc += 32) {
+          const int c0 = cg + cc;
+          uint32_t raw[32];
+          __syncwarp();
+          lptx::tmem_ld32(t_lane + (uint32_t)c0, raw);
+          lptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            }
+          }
+          if (p.act != LNS_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
+          }
+          if (RES16) {
+#pragma unroll
+            for (int h4 = 0; h4 < 4; ++h4) {
+              uint32_t w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                           : "r"(my_row_st + (uint32_t)((((cc >> 3) + h4) ^ (lane & 7)) << 4)));
+              const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = (p.res_dtype == LNS_F16) ? unpack2_h16<true>(ww[j]) : unpack2_h16<false>(ww[j]);
+                v[h4 * 8 + 2 * j] += f.x;
+                v[h4 * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          } else if (row_ok && p.residual) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 rr = ld4_as_float(p.residual, p.res_dtype, rrow + c0 + j);
+              v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
+            }
+          }
+          if (y16) {
+#pragma unroll
+            for (int h4 = 0; h4 < 4; ++h4) {
+              uint32_t pk[4];
+              if (p.y_dtype == LNS_F16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pk[j] = pack2_h16<true>(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pk[j] = pack2_h16<false>(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
+              }
+              const int ch = (cc >> 3) + h4;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_st + (uint32_t)((ch ^ (lane & 7)) << 4)),
+                           "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+            }
+          } else if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yrow + c0);
+            if (p.y_dtype == LNS_TF32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+        if (y16) {
+          __syncwarp();
+          // staged row r of this warp = accumulator row quad*32 + r: 8 consecutive rows = the 8 pixels of image row
+          // (y, s); each pass moves 4 rows x 128 B (one 64-channel group of 4 pixels: full 128-byte lines)
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int r = pass * 4 + rd_row;
+            const int mm = quad * 32 + r;
+            const int bb = sup * 4 + t * 2 + ((mm >> 3) & 1);
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(my_stage + (uint32_t)r * 128u + (uint32_t)((rd_chunk ^ (r & 7)) << 4)));
+            if (bb < p.B)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.y) + (int64_t)bb * p.y_bstride +
+                                        (int64_t)((mm >> 4) * 8 + (mm & 7)) * 128 + cg + rd_chunk * 8) = make_uint4(w0, w1, w2, w3);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    lptx::tc_fence_before();
+    lptx::mbar_arrive(acc_empty(a));
+  }
+}
 
 __global__ void __launch_bounds__(kLatThreads, 1) conv_latent_kernel(const LatentParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (lptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - lptx::smem_u32(smem_raw));
   const uint32_t halo_a = base;                                         // [tile 2][slab 2] planes
-  const uint32_t b_ring = halo_a + 4u * (uint32_t)p.plane_bytes;        // kBStages x 16 KB
-  const uint32_t stage_out = b_ring + kBStages * kBBytes;               // 4 warps x 4 KB output staging
+  const int BS = p.bstages;
+  const uint32_t b_ring = halo_a + 4u * (uint32_t)p.plane_bytes;        // BS x 16 KB
+  const uint32_t stage_out = b_ring + (uint32_t)BS * kBBytes;             // 4 warps x 4 KB output staging
   const uint32_t bar_base = stage_out + 4u * 4096u;
   const uint32_t halo_full = bar_base, halo_empty = bar_base + 8;
   auto b_full = [&](int s) { return bar_base + 16u + 8u * s; };
-  auto b_empty = [&](int s) { return bar_base + 16u + 8u * (kBStages + s); };
-  auto acc_full = [&](int a) { return bar_base + 16u + 8u * (2 * kBStages + a); };
-  auto acc_empty = [&](int a) { return bar_base + 16u + 8u * (2 * kBStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 16u + 8u * (2 * kBStages + 4);
+  auto b_empty = [&](int s) { return bar_base + 16u + 8u * (kBMax + s); };
+  auto acc_full = [&](int a) { return bar_base + 16u + 8u * (2 * kBMax + a); };
+  auto acc_empty = [&](int a) { return bar_base + 16u + 8u * (2 * kBMax + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 16u + 8u * (2 * kBMax + 4);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = p.dil, HWd = p.HWd;
@@ -146,7 +301,7 @@ __global__ void __launch_bounds__(kLatThreads, 1) conv_latent_kernel(const Laten
   if (tid == 0) {
     lptx::mbar_init(halo_full, 128);
     lptx::mbar_init(halo_empty, 1);
-    for (int s = 0; s < kBStages; ++s) {
+    for (int s = 0; s < kBMax; ++s) {
       lptx::mbar_init(b_full(s), 1);
       lptx::mbar_init(b_empty(s), 1);
     }
@@ -192,16 +347,16 @@ __global__ void __launch_bounds__(kLatThreads, 1) conv_latent_kernel(const Laten
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (p.x_f16 ? 0u : ((1u << 7) | (1u << 10))) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t sbo = (uint32_t)HWd * 128u;
-      int bkb = 0, it = 0;
+      int s = 0, it = 0;
+      uint32_t bphase = 0;  // filter ring position: stage s, phase bit flips on every wrap
       for (int sup = blockIdx.x; sup < p.nsuper; sup += gridDim.x, ++it) {
         const int a = it & 1;
         if (it >= 2) lptx::mbar_wait(acc_empty(a), (uint32_t)(((it >> 1) - 1) & 1));
         lptx::mbar_wait(halo_full, (uint32_t)(it & 1));
         lptx::fence_proxy_async();
         lptx::tc_fence_after();
-        for (int kb = 0; kb < 18; ++kb, ++bkb) {
-          const int s = bkb % kBStages;
-          lptx::mbar_wait(b_full(s), (uint32_t)((bkb / kBStages) & 1));
+        for (int kb = 0; kb < 18; ++kb) {
+          lptx::mbar_wait(b_full(s), bphase);
           lptx::tc_fence_after();
           const int tap = kb >> 1, sl = kb & 1, ky = tap / 3, kx = tap - ky * 3;
           const uint64_t bdesc = desc_sbo(b_ring + (uint32_t)s * kBBytes, 1024u);
@@ -215,6 +370,10 @@ __global__ void __launch_bounds__(kLatThreads, 1) conv_latent_kernel(const Laten
               lptx::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           lptx::umma_commit(b_empty(s));
+          if (++s == BS) {
+            s = 0;
+            bphase ^= 1u;
+          }
         }
         lptx::umma_commit(halo_empty);
         lptx::umma_commit(acc_full(a));
@@ -226,115 +385,25 @@ __global__ void __launch_bounds__(kLatThreads, 1) conv_latent_kernel(const Laten
     // the 18 (tap, slab) blocks of every super tile through the ring; always the same 295 KB: L2 hits.  Runs ahead of the
     // MMAs by the ring depth, independent of the halo producers.
     if (lane == 0) {
-      int bkb = 0;
+      int s = 0;
+      uint32_t wrap = 0;  // completed trips around the ring
       for (int sup = blockIdx.x; sup < p.nsuper; sup += gridDim.x) {
-        for (int kb = 0; kb < 18; ++kb, ++bkb) {
-          const int s = bkb % kBStages;
-          if (bkb >= kBStages) lptx::mbar_wait(b_empty(s), (uint32_t)(((bkb / kBStages) - 1) & 1));
+        for (int kb = 0; kb < 18; ++kb) {
+          if (wrap > 0) lptx::mbar_wait(b_empty(s), (wrap - 1u) & 1u);
           lptx::mbar_expect_tx(b_full(s), kBBytes);
           lptx::bulk_g2s(b_ring + (uint32_t)s * kBBytes, p.w + (int64_t)kb * 128 * 64, kBBytes, b_full(s));
+          if (++s == BS) {
+            s = 0;
+            ++wrap;
+          }
         }
       }
     }
     __syncwarp();
   } else {
     // ============================== epilogue (warps 5-8) ==============================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int m = quad * 32 + lane;
-    const int yo = m >> 4, s_of = (m >> 3) & 1, xo = m & 7;
-    const bool y16 = is_h16(p.y_dtype);
-    const uint32_t my_stage = stage_out + (uint32_t)(warp - 5) * 4096u;
-    const uint32_t my_row_st = my_stage + (uint32_t)lane * 128u;
-    const int rd_row = lane >> 3, rd_chunk = lane & 7;
-    int it = 0;
-    for (int sup = blockIdx.x; sup < p.nsuper; sup += gridDim.x, ++it) {
-      const int a = it & 1;
-      lptx::mbar_wait(acc_full(a), (uint32_t)((it >> 1) & 1));
-      lptx::tc_fence_after();
-      for (int t = 0; t < 2; ++t) {
-        const int b = sup * 4 + t * 2 + s_of;
-        const bool row_ok = b < p.B;
-        const int64_t pix = yo * 8 + xo;
-        const int64_t yrow = (int64_t)b * p.y_bstride + pix * 128;
-        const int64_t rrow = (int64_t)b * p.res_bstride + pix * 128;
-        const uint32_t t_lane = tmem_acc + (uint32_t)((a * 2 + t) * 128) + ((uint32_t)(quad * 32) << 16);
-        for (int cg = 0; cg < 128; cg += 64) {
-#pragma unroll
-          for (int cc = 0; cc < 64; cc += 32) {
-            const int c0 = cg + cc;
-            uint32_t raw[32];
-            __syncwarp();
-            lptx::tmem_ld32(t_lane + (uint32_t)c0, raw);
-            lptx::tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-              }
-            }
-            if (p.act != LNS_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
-            }
-            if (row_ok && p.residual) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 rr = ld4_as_float(p.residual, p.res_dtype, rrow + c0 + j);
-                v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
-              }
-            }
-            if (y16) {
-#pragma unroll
-              for (int h4 = 0; h4 < 4; ++h4) {
-                uint32_t pk[4];
-                if (p.y_dtype == LNS_F16) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) pk[j] = pack2_h16<true>(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) pk[j] = pack2_h16<false>(v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
-                }
-                const int ch = (cc >> 3) + h4;
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_st + (uint32_t)((ch ^ (lane & 7)) << 4)),
-                             "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-              }
-            } else if (row_ok) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yrow + c0);
-              if (p.y_dtype == LNS_TF32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-          }
-          if (y16) {
-            __syncwarp();
-            // staged row r of this warp = accumulator row quad*32 + r: 8 consecutive rows = the 8 pixels of image row
-            // (y, s); each pass moves 4 rows x 128 B (one 64-channel group of 4 pixels: full 128-byte lines)
-#pragma unroll
-            for (int pass = 0; pass < 8; ++pass) {
-              const int r = pass * 4 + rd_row;
-              const int mm = quad * 32 + r;
-              const int bb = sup * 4 + t * 2 + ((mm >> 3) & 1);
-              uint32_t w0, w1, w2, w3;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                           : "r"(my_stage + (uint32_t)r * 128u + (uint32_t)((rd_chunk ^ (r & 7)) << 4)));
-              if (bb < p.B)
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.y) + (int64_t)bb * p.y_bstride +
-                                          (int64_t)((mm >> 4) * 8 + (mm & 7)) * 128 + cg + rd_chunk * 8) = make_uint4(w0, w1, w2, w3);
-            }
-            __syncwarp();
-          }
-        }
-      }
-      lptx::tc_fence_before();
-      lptx::mbar_arrive(acc_empty(a));
-    }
+    if (p.residual != nullptr && is_h16(p.res_dtype)) latent_epilogue<true>(p, tmem_acc, stage_out, acc_full(0), acc_empty(0), warp, lane);
+    else latent_epilogue<false>(p, tmem_acc, stage_out, acc_full(0), acc_empty(0), warp, lane);
   }
 
   lptx::tc_fence_before();
@@ -378,8 +447,24 @@ int conv2d_latent(const LnsConvDesc* d, cudaStream_t stream) {
   LNS_REQUIRE(p.plane_bytes % 1024 == 0, "lns_conv2d(latent): internal: halo plane not 1024-byte aligned");
   p.x_f16 = d->x_dtype == LNS_F16 ? 1 : 0;
   p.inv_hwd = 1.0f / (float)p.HWd;
-  const int smem = 4 * p.plane_bytes + kBStages * (int)kBBytes + 4 * 4096 + 256 + 1024;
-  LNS_REQUIRE(smem <= 227 * 1024, "lns_conv2d(latent): %d B of shared memory", smem);
+  // filter ring depth: 3 stages by default.  LNS_LATENT_RING raises it up to what the shared memory left by the halos allows
+  // (dil 1: 6): measured on B200 a 6-stage ring is SLOWER (43 -> 52 us per launch at 1184 samples) -- the kernel is not
+  // bound by the filter stream's latency, and the extra 48 KB of shared memory shrink the L1 the epilogue's loads hit.
+  const int fixed = 4 * p.plane_bytes + 4 * 4096 + 256 + 1024;
+  int bst = (227 * 1024 - fixed) / (int)kBBytes;
+  {
+    static int cap = 0;
+    if (!cap) {
+      const char* c = getenv("LNS_LATENT_RING");
+      cap = c ? atoi(c) : 3;
+      if (cap < 3) cap = 3;
+      if (cap > kBMax) cap = kBMax;
+    }
+    if (bst > cap) bst = cap;
+  }
+  LNS_REQUIRE(bst >= 3, "lns_conv2d(latent): shared memory too small for a 3-stage filter ring at dilation %d", d->dil);
+  p.bstages = bst;
+  const int smem = fixed + bst * (int)kBBytes;
   {
     static bool once = false;
     if (!once) {
