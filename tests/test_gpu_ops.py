@@ -425,7 +425,8 @@ def test_pointwise_projection(dtype):
     dst = ops.Act(out.view(-1)[Co * H * W:], B, H, W, Co, bstride=2 * Co * H * W, layout=ops.NCHW)
     ops.conv2d(act_from(x, dtype), ops.PackedFilter.of(h.weight, h.bias),
                pro=(sc.to(DEV).reshape(-1), sh.to(DEV).reshape(-1), ops.ACT_SILU), out=dst, out_layout=ops.NCHW)
-    assert relerr(out[:, 1].cpu(), ref) < 3e-6
+    # bf16 storage: Swish through tanh.approx.f32 (one special-function op per element, abs error < 2^-10.9)
+    assert relerr(out[:, 1].cpu(), ref) < (3e-6 if dtype == torch.float32 else 3e-4)
     assert float(out[:, 0].abs().max()) == 0.0
 
 
