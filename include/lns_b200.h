@@ -268,6 +268,12 @@ int lns_nhwc_to_nchw(const void* x, int x_dtype, int B, int H, int W, int C, int
 int lns_pointwise_proj(const void* x, int dtype, int B, int HW, int C, int64_t x_bstride, const float* w,
                        const float* bias, int Cout, const float* scale, const float* shift, int act, float* y,
                        int64_t y_bstride, void* stream);
+/* the same with a two-level output index for the rollout engine: the B samples are `B / group` rollout steps of `group`
+ * trajectories each (step-major), sample s is written at y + (s % group) * y_bstride + (s / group) * y_gstride -- slot
+ * (trajectory, step) of the [B, K, C, Ly, Lx] result of LatentDynamics.predict (torch.stack(dim=1), train_stage2_ns2d.py:157) */
+int lns_pointwise_proj_steps(const void* x, int dtype, int B, int HW, int C, int64_t x_bstride, const float* w,
+                             const float* bias, int Cout, const float* scale, const float* shift, int act, float* y,
+                             int64_t y_bstride, int group, int64_t y_gstride, void* stream);
 /* sinusoidal embedding cat(cos(p f), sin(p f)), f_i = exp(-ln(max_period) i / (dim/2))
  * modules/cond_utils.py:19-38 */
 int lns_fourier_embedding(const float* param, int B, int dim, float max_period, float* out, void* stream);

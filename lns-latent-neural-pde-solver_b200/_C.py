@@ -51,6 +51,7 @@ SIGNATURES = {
     "lns_group_norm_act_supported": (i32, [i32, i32, i32]),
     "lns_group_norm_act": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, f32, vp, vp, vp, i32, vp, i32, i64, vp]),
     "lns_pointwise_proj": (i32, [vp, i32, i32, i32, i32, i64, vp, vp, i32, vp, vp, i32, vp, i64, vp]),
+    "lns_pointwise_proj_steps": (i32, [vp, i32, i32, i32, i32, i64, vp, vp, i32, vp, vp, i32, vp, i64, i32, i64, vp]),
     "lns_affine_act": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, i32, vp, i32, i64, vp]),
     "lns_layernorm": (i32, [vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp]),
     "lns_attention": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, i32, vp]),

@@ -12,7 +12,8 @@ template <int COUT>
 __global__ void __launch_bounds__(256) pointwise_proj_kernel(const void* __restrict__ x, int dtype, int HW, int C, int64_t x_bstride,
                                                               const float* __restrict__ w, const float* __restrict__ bias,
                                                               const float* __restrict__ scale, const float* __restrict__ shift,
-                                                              int act, float* __restrict__ y, int64_t y_bstride) {
+                                                              int act, float* __restrict__ y, int64_t y_bstride, int group,
+                                                              int64_t y_gstride) {
   // 8 lanes per pixel: a warp instruction reads 4 whole pixels' channel chunks (full lines), each lane owns a strided set
   // of 4-channel groups, the COUT partial dot products are combined with 3 shuffles; 32 pixels per 256-thread CTA pass.
   extern __shared__ float sm[];  // w [COUT][C], scale [C], shift [C]
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) pointwise_proj_kernel(const void* __restr
       float v = acc[0];
 #pragma unroll
       for (int n = 1; n < COUT; ++n) v = (sub == n) ? acc[n] : v;
-      y[(int64_t)b * y_bstride + (int64_t)sub * HW + pix] = v + (bias ? bias[sub] : 0.f);
+      y[(int64_t)(b % group) * y_bstride + (int64_t)(b / group) * y_gstride + (int64_t)sub * HW + pix] = v + (bias ? bias[sub] : 0.f);
     }
   }
 }
@@ -85,7 +86,8 @@ template <int COUT, bool F16>
 __global__ void __launch_bounds__(256) pointwise_proj64_kernel(const uint16_t* __restrict__ x, int HW, int64_t x_bstride,
                                                                 const float* __restrict__ w, const float* __restrict__ bias,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
-                                                                int act, float* __restrict__ y, int64_t y_bstride) {
+                                                                int act, float* __restrict__ y, int64_t y_bstride, int group,
+                                                                int64_t y_gstride) {
   const int b = blockIdx.y;
   const int sub = threadIdx.x & 7;
   const int pix0 = blockIdx.x * 256 + (threadIdx.x >> 3);  // + 32 per pass
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256) pointwise_proj64_kernel(const uint16_t* _
       float v = acc[0];
 #pragma unroll
       for (int n = 1; n < COUT; ++n) v = (sub == n) ? acc[n] : v;
-      y[(int64_t)b * y_bstride + (int64_t)sub * HW + pix] = v + my_bias;
+      y[(int64_t)(b % group) * y_bstride + (int64_t)(b / group) * y_gstride + (int64_t)sub * HW + pix] = v + my_bias;
     }
   }
 }
@@ -387,8 +389,10 @@ __global__ void __launch_bounds__(256) gn_act_small_kernel(const void* __restric
 
 extern "C" {
 
-int lns_pointwise_proj(const void* x, int dtype, int B, int HW, int C, int64_t x_bstride, const float* w, const float* bias,
-                       int Cout, const float* scale, const float* shift, int act, float* y, int64_t y_bstride, void* stream) {
+int lns_pointwise_proj_steps(const void* x, int dtype, int B, int HW, int C, int64_t x_bstride, const float* w, const float* bias,
+                             int Cout, const float* scale, const float* shift, int act, float* y, int64_t y_bstride, int group,
+                             int64_t y_gstride, void* stream) {
+  LNS_REQUIRE(group >= 1, "lns_pointwise_proj_steps: group must be >= 1");
   LNS_REQUIRE(x && w && y && B > 0 && HW > 0 && C > 0 && C % 4 == 0 && C <= 512 && Cout >= 1 && Cout <= 4 && B <= 65535,
               "lns_pointwise_proj: bad arguments (C=%d, Cout=%d)", C, Cout);
   LNS_REQUIRE(x_bstride % 4 == 0, "lns_pointwise_proj: batch stride must be a multiple of 4");
@@ -403,8 +407,8 @@ int lns_pointwise_proj(const void* x, int dtype, int B, int HW, int C, int64_t x
     const bool f16 = dtype == LNS_F16;
 #define LNS_PROJ64(N)                                                                                                              \
   do {                                                                                                                             \
-    if (f16) lns::pointwise_proj64_kernel<N, true><<<grid, 256, 0, s>>>(xh, HW, x_bstride, w, bias, scale, shift, act, y, y_bstride); \
-    else lns::pointwise_proj64_kernel<N, false><<<grid, 256, 0, s>>>(xh, HW, x_bstride, w, bias, scale, shift, act, y, y_bstride);    \
+    if (f16) lns::pointwise_proj64_kernel<N, true><<<grid, 256, 0, s>>>(xh, HW, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); \
+    else lns::pointwise_proj64_kernel<N, false><<<grid, 256, 0, s>>>(xh, HW, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); \
   } while (0)
     switch (Cout) {
       case 1: LNS_PROJ64(1); break;
@@ -416,12 +420,17 @@ int lns_pointwise_proj(const void* x, int dtype, int B, int HW, int C, int64_t x
     return lns::check_launch("pointwise_proj64_kernel");
   }
   switch (Cout) {
-    case 1: lns::pointwise_proj_kernel<1><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride); break;
-    case 2: lns::pointwise_proj_kernel<2><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride); break;
-    case 3: lns::pointwise_proj_kernel<3><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride); break;
-    default: lns::pointwise_proj_kernel<4><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride); break;
+    case 1: lns::pointwise_proj_kernel<1><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); break;
+    case 2: lns::pointwise_proj_kernel<2><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); break;
+    case 3: lns::pointwise_proj_kernel<3><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); break;
+    default: lns::pointwise_proj_kernel<4><<<grid, 256, smem, s>>>(x, dtype, HW, C, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); break;
   }
   return lns::check_launch("pointwise_proj_kernel");
+}
+
+int lns_pointwise_proj(const void* x, int dtype, int B, int HW, int C, int64_t x_bstride, const float* w, const float* bias,
+                       int Cout, const float* scale, const float* shift, int act, float* y, int64_t y_bstride, void* stream) {
+  return lns_pointwise_proj_steps(x, dtype, B, HW, C, x_bstride, w, bias, Cout, scale, shift, act, y, y_bstride, B > 0 ? B : 1, 0, stream);
 }
 
 int lns_group_norm_act_supported(int H, int W, int C) {

@@ -125,13 +125,16 @@ class Act:
     """A [B,H,W,C] activation living in `t` (element (0,0,0,0) at t.data_ptr()); channel-last unless layout=NCHW.
     `bstride` is the distance between samples in elements (lets the K latent states of a rollout interleave as
     [B,K,...] without copies)."""
-    __slots__ = ("t", "B", "H", "W", "C", "bstride", "layout", "tf32")
+    __slots__ = ("t", "B", "H", "W", "C", "bstride", "layout", "tf32", "group", "gstride")
 
-    def __init__(self, t, B, H, W, C, bstride=None, layout=NHWC, tf32=False):
+    def __init__(self, t, B, H, W, C, bstride=None, layout=NHWC, tf32=False, group=None, gstride=0):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
         self.bstride = H * W * C if bstride is None else bstride
         self.layout = layout
         self.tf32 = tf32  # fp32 words holding TF32-rounded values: kernels round to nearest TF32 when they write it
+        # two-level sample index (output of the decoder's projection only): sample s lives at
+        # (s % group) * bstride + (s // group) * gstride -- `B // group` rollout steps of `group` trajectories, step-major
+        self.group, self.gstride = group, gstride
 
     @property
     def dtype(self):
@@ -369,6 +372,8 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     else:
         if (out.B, out.H, out.W, out.C) != (x.B, Hout, Wout, Cout):
             raise LnsError(f"conv2d: out shape {(out.B, out.H, out.W, out.C)} != {(x.B, Hout, Wout, Cout)}")
+        if out.group is not None:
+            raise LnsError("conv2d: a step-grouped output is only supported by the output projection (lns_pointwise_proj_steps)")
     d = ConvDesc()
     d.x, d.x_dtype, d.x_layout = x.t.data_ptr(), x.dtype, x.layout
     d.B, d.Hin, d.Win, d.Cin, d.x_bstride = x.B, x.H, x.W, x.C, x.bstride
@@ -424,8 +429,15 @@ def _pointwise_proj(x, filt, use_bias, pro, out):
         pro = pro.as_tuple()
     sc, sh, pa = (pro if pro is not None else (None, None, ACT_NONE))
     tok = _mark(f"proj @{x.H}x{x.W}")
-    rc = _C.lib().lns_pointwise_proj(_ptr(x.t), x.dtype, x.B, x.H * x.W, Cin, x.bstride, _ptr(wt), _ptr(bias), Cout,
-                                     _ptr(sc), _ptr(sh), pa, _ptr(out.t), out.bstride, _stream())
+    if out.group is not None:
+        if out.B % out.group != 0:
+            raise LnsError(f"proj: {out.B} samples are not whole steps of {out.group} trajectories")
+        rc = _C.lib().lns_pointwise_proj_steps(_ptr(x.t), x.dtype, x.B, x.H * x.W, Cin, x.bstride, _ptr(wt), _ptr(bias), Cout,
+                                               _ptr(sc), _ptr(sh), pa, _ptr(out.t), out.bstride, out.group, out.gstride,
+                                               _stream())
+    else:
+        rc = _C.lib().lns_pointwise_proj(_ptr(x.t), x.dtype, x.B, x.H * x.W, Cin, x.bstride, _ptr(wt), _ptr(bias), Cout,
+                                         _ptr(sc), _ptr(sh), pa, _ptr(out.t), out.bstride, _stream())
     check(rc, "lns_pointwise_proj")
     _done(tok)
     _state.launches += 1

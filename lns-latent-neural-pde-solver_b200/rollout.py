@@ -4,11 +4,16 @@ Reference semantics: ``LatentDynamics.predict(x, steps, to_x)`` (train_stage2_ns
 train_stage2_twophase_conditional.py:177-193).  Differences in execution, not in results:
   * the K latent states are written by the propagator's output projection directly into a resident
     [B, K, h, w, Cz] fp32 stack (batch-strided output, no torch.stack copy);
-  * decode never feeds back into the loop, so the K decodes run after the loop as one batch of B*K samples (in chunks),
-    and the decoder's last 1x1 conv writes NCHW fp32 straight into the [B, K, C, Ly, Lx] result;
+  * decode never feeds back into the loop, so the K decodes are batched: the latent stack is step-major and every S steps
+    their B*S samples are decoded as one launch group ON A SECOND STREAM, overlapping the rest of the propagator loop (whose
+    launches are small and latency-bound: ~1 ms per step for ~0.25 ms of tensor work); the decoder's output projection
+    writes NCHW fp32 straight into slot [b][t] of the [B, K, C, Ly, Lx] result (lns_pointwise_proj_steps).
+    LNS_ROLLOUT_PIPELINE=0 restores the serial order (all steps, then the decode in chunks);
   * everything that depends only on the conditioning parameter is computed once, not per step;
   * the whole sequence is captured in a CUDA graph and replayed (no Python / launch overhead per step).
 """
+import os
+
 import torch
 
 from . import ops
@@ -54,6 +59,9 @@ class Rollout:
         self.x_static = torch.zeros(self.B, self.Cin, self.Ly, self.Lx, dtype=torch.float32, device=self.device)
         self.param_static = torch.zeros(self.B, dtype=torch.float32, device=self.device) if self.conditional else None
         self.decode_chunk = decode_chunk
+        self.pipeline = os.environ.get("LNS_ROLLOUT_PIPELINE", "1") != "0"
+        self.steps_per_group = 0
+        self._side = None
         self.use_graph = use_graph
         self.graph = None
         self.out = None
@@ -68,23 +76,50 @@ class Rollout:
             z0 = self.ae._encode(Act.from_nchw(self.x_static))            # [B,h,w,Cz] fp32
             h, w, Cz = z0.H, z0.W, z0.C
             hwc = h * w * Cz
+            n = B * K
+            chw = self.C * self.Ly * self.Lx
             if self.zs is None:
                 self.zs = torch.empty(B * K * hwc, dtype=torch.float32, device=self.device)
                 self.h, self.w = h, w
+                # pipelined decode (to_x): the latent stack is STEP-major [K][B][h][w][Cz]; as soon as S steps exist their
+                # B*S samples are decoded on a second stream while the (latency-bound, small-launch) propagator goes on
+                self.steps_per_group = self._steps_per_group(n) if self.to_x and self.pipeline else 0
+                if self.to_x:
+                    self.out = torch.empty(B, K, self.C, self.Ly, self.Lx, dtype=torch.float32, device=self.device)
+            S = self.steps_per_group
             prepared = self._cond_cnn_prepare(self.prop, self.param_static) if self.conditional else None
+            main = torch.cuda.current_stream(self.device)
+            if S:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.device)
+                self._side.wait_stream(main)  # fork (inside a capture this makes the side stream part of the graph)
+                out_flat = self.out.view(-1)
             z_in = z0
             for t in range(K):
-                z_out = Act(self.zs[t * hwc:], B, h, w, Cz, bstride=K * hwc)  # slot t of every trajectory
+                if S:
+                    z_out = Act(self.zs[t * B * hwc:], B, h, w, Cz)                 # step t of every trajectory, contiguous
+                else:
+                    z_out = Act(self.zs[t * hwc:], B, h, w, Cz, bstride=K * hwc)    # slot t of every trajectory
                 if self.conditional:
                     self._cond_cnn_fwd(self.prop, z_in, prepared, out=z_out)
                 else:
                     self._simple_cnn_fwd(self.prop, z_in, out=z_out)
                 z_in = z_out
-            n = B * K
-            if self.to_x:
-                chw = self.C * self.Ly * self.Lx
-                if self.out is None:
-                    self.out = torch.empty(B, K, self.C, self.Ly, self.Lx, dtype=torch.float32, device=self.device)
+                if S and ((t + 1) % S == 0 or t == K - 1):
+                    t0 = (t // S) * S
+                    ns = t + 1 - t0
+                    done = torch.cuda.Event()
+                    done.record(main)
+                    self._side.wait_event(done)
+                    with torch.cuda.stream(self._side):
+                        zin = Act(self.zs[t0 * B * hwc:], ns * B, h, w, Cz)
+                        # sample (step t0 + j, trajectory b) of the group -> slot [b][t0 + j] of the [B, K, C, Ly, Lx] result
+                        dst = Act(out_flat[t0 * chw:], ns * B, self.Ly, self.Lx, self.C, bstride=K * chw, layout=ops.NCHW,
+                                  group=B, gstride=chw)
+                        self.ae._decode(zin, out=dst)
+            if S:
+                main.wait_stream(self._side)  # join
+            elif self.to_x:
                 out_flat = self.out.view(-1)
                 chunk = self.decode_chunk or self._default_chunk(n)
                 for c0 in range(0, n, chunk):
@@ -99,6 +134,12 @@ class Rollout:
                                                     hwc, ops._stream())
                 ops.check(rc, "lns_nhwc_to_nchw")
                 ops._state.launches += 1
+
+    def _steps_per_group(self, n):
+        """Rollout steps per pipelined decode group: about one default decode chunk, but at least four groups per rollout so
+        that the decode of the early steps overlaps the propagator of the later ones."""
+        chunk = self.decode_chunk or self._default_chunk(n)
+        return max(1, min(int(round(chunk / self.B)), -(-self.K // 4)))
 
     def _default_chunk(self, n):
         """Samples per decode launch group: about 16 M output pixels per channel, split evenly over the B*K samples and
@@ -154,4 +195,6 @@ class Rollout:
 
     def latents(self):
         """The resident latent stack as [B, K, h, w, Cz] fp32 (channel-last)."""
+        if self.steps_per_group:
+            return self.zs.view(self.K, self.B, self.h, self.w, self.Cz).transpose(0, 1)
         return self.zs.view(self.B, self.K, self.h, self.w, self.Cz)
