@@ -4,6 +4,8 @@ import collections
 import os
 import sys
 
+os.environ.setdefault("LNS_ROLLOUT_PIPELINE", "0")  # serial order: with the decode pipelined on a second stream the per-call events overlap
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
