@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) pointwise_proj_kernel(const void* __restr
   }
   __syncthreads();
   const int sub = threadIdx.x & 7;
+  float* __restrict__ yb = y + (int64_t)(b % group) * y_bstride + (int64_t)(b / group) * y_gstride;  // this sample's output planes
   const int pix0 = blockIdx.x * 256;  // 256 pixels per CTA, 8 passes of 32
 #pragma unroll 2
   for (int pass = 0; pass < 8; ++pass) {
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256) pointwise_proj_kernel(const void* __restr
       float v = acc[0];
 #pragma unroll
       for (int n = 1; n < COUT; ++n) v = (sub == n) ? acc[n] : v;
-      y[(int64_t)(b % group) * y_bstride + (int64_t)(b / group) * y_gstride + (int64_t)sub * HW + pix] = v + (bias ? bias[sub] : 0.f);
+      yb[(int64_t)sub * HW + pix] = v + (bias ? bias[sub] : 0.f);
     }
   }
 }
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(256) pointwise_proj64_kernel(const uint16_t* _
     }
   }
   const float my_bias = (bias && sub < COUT) ? __ldg(bias + sub) : 0.f;
+  float* __restrict__ yb = y + (int64_t)(b % group) * y_bstride + (int64_t)(b / group) * y_gstride;  // this sample's output planes
 #pragma unroll
   for (int pass = 0; pass < 8; ++pass) {
     const int pix = pix0 + pass * 32;
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(256) pointwise_proj64_kernel(const uint16_t* _
       float v = acc[0];
 #pragma unroll
       for (int n = 1; n < COUT; ++n) v = (sub == n) ? acc[n] : v;
-      y[(int64_t)(b % group) * y_bstride + (int64_t)(b / group) * y_gstride + (int64_t)sub * HW + pix] = v + my_bias;
+      yb[(int64_t)sub * HW + pix] = v + my_bias;
     }
   }
 }
