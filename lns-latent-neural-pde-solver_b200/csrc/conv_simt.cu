@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(256) lift1x1_kernel(const SimtParams p, int pi
   }
 }
 
-// v2 of the channel lift for NHWC inputs with Cin % 4 == 0 and Cout % 4 == 0 (the propagator's in_proj 16 -> 128 and the
-// decoder's 16 -> 128 on the fp32 latent).  The ncu profile of the kernel above (18.1 M warp instructions, 65 % of the stall
+// v2 of the channel lift for Cout % 4 == 0 (the encoder's NCHW fp32 input lift 1|3|4 -> 64, the propagator's in_proj 16 -> 128
+// and the decoder's 16 -> 128 on the fp32 NHWC latent).  The ncu profile of the kernel above (18.1 M warp instructions, 65 % of the stall
 // samples on the shared-memory scoreboard for 75 776 pixels) showed it re-loading its 16 x 8 filter values from shared memory
 // for EVERY pixel -- one FMA per loaded value -- and paying one global round trip per pixel pass.  Here a thread owns 4
 // output channels for the whole kernel and keeps their Cin x 4 filter values (and bias) in registers; the CTA's 128 input
@@ -230,14 +230,25 @@ __global__ void __launch_bounds__(256) lift1x1_v2_kernel(const SimtParams p) {
   const int HW = g.Hout * g.Wout;
   const int64_t m0 = (int64_t)blockIdx.x * kLiftPix;
   const int npx = (int)min((int64_t)kLiftPix, (int64_t)p.M - m0);
-  // stage the input pixels: Cin / 4 float4 per pixel, consecutive threads -> consecutive 16-byte pieces
-  const int q4 = Cin >> 2;
-  for (int e = threadIdx.x; e < npx * q4; e += 256) {
-    const int pi = e / q4, c = (e - pi * q4) * 4;
-    const int64_t m = m0 + pi;
-    const int b = (int)(m / HW), pix = (int)(m - (int64_t)b * HW);
-    const float4 t4 = ld4_as_float(p.x, p.x_dtype, (int64_t)b * g.x_bstride + (int64_t)pix * Cin + c);
-    *reinterpret_cast<float4*>(xs + pi * 16 + c) = t4;
+  const int q4 = (Cin + 3) >> 2;
+  if (p.x_layout == LNS_NCHW) {
+    // the reference's NCHW fp32 input (encoder lift, Cin = 1 | 3 | 4): consecutive threads -> consecutive pixels of one plane;
+    // channels up to the next multiple of 4 are zero (their filter registers are zero too: fma(0, 0, a) == a)
+    for (int e = threadIdx.x; e < npx * q4 * 4; e += 256) {
+      const int c = e / npx, pi = e - c * npx;
+      const int64_t m = m0 + pi;
+      const int b = (int)(m / HW), pix = (int)(m - (int64_t)b * HW);
+      xs[pi * 16 + c] = c < Cin ? __ldg(reinterpret_cast<const float*>(p.x) + (int64_t)b * g.x_bstride + (int64_t)c * HW + pix) : 0.f;
+    }
+  } else {
+    // NHWC: Cin / 4 float4 per pixel, consecutive threads -> consecutive 16-byte pieces
+    for (int e = threadIdx.x; e < npx * q4; e += 256) {
+      const int pi = e / q4, c = (e - pi * q4) * 4;
+      const int64_t m = m0 + pi;
+      const int b = (int)(m / HW), pix = (int)(m - (int64_t)b * HW);
+      const float4 t4 = ld4_as_float(p.x, p.x_dtype, (int64_t)b * g.x_bstride + (int64_t)pix * Cin + c);
+      *reinterpret_cast<float4*>(xs + pi * 16 + c) = t4;
+    }
   }
   const int TPP = Cout >> 2, ppp = 256 / TPP;  // threads per pixel, pixels per pass
   const int cq = threadIdx.x % TPP, pl = threadIdx.x / TPP;
@@ -322,7 +333,7 @@ int conv2d_simt(const LnsConvDesc* d, cudaStream_t stream) {
     int ppb = ppp * passes;                                // 8 passes per block ...
     while ((M + ppb - 1) / ppb > 148 * 16) ppb *= 2;       // ... more when the grid would exceed 16 blocks per SM
     const int tpp = d->Cout / 4;
-    if (d->x_layout == LNS_NHWC && d->Cout % 4 == 0 && tpp <= 256 && 256 % tpp == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
+    if (d->Cout % 4 == 0 && tpp <= 256 && 256 % tpp == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
         (!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0) &&
         (!d->sample_bias || (reinterpret_cast<uintptr_t>(d->sample_bias) & 15) == 0)) {
       lift1x1_v2_kernel<<<(unsigned)((M + kLiftPix - 1) / kLiftPix), 256, 0, stream>>>(p);
