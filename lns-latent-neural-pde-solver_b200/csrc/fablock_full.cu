@@ -318,7 +318,10 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
 
   const int g = lane >> 2, t = lane & 3;
   const int nblk = nslots >> 4;             // 16-row blocks of phase A (pad rows included: they cost nothing to skip)
-  const int blk_per_q = (nblk + 3) >> 2;
+  // the raw-input copy and phase A run in NQ pipelined parts of the row range.  Small samples (<= 256 pixels, the 256-thread
+  // variant) use two: with four, a 16x16 sample has 4 blocks per part for 8 warps -- half of them idle through four barriers
+  constexpr int NQ = NTHR == 256 ? 2 : 4;
+  const int blk_per_q = (nblk + NQ - 1) / NQ;
 
   for (int h = 0; h < heads; ++h) {
     // ---- per-(sample, head) setup from the staged fp32 operands: in_proj filter with GroupNorm folded in, its bias, the
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
     // ---- raw input -> pixel rows of U_s (cp.async, four commit groups = four quarters of the row range) ----
     {
       const int ch = tid & 7;
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < NQ; ++q) {
         const int s_end = min(nslots, (q + 1) * blk_per_q * 16);
         for (int s = q * blk_per_q * 16 + (tid >> 3); s < s_end; s += NTHR / 8) {
           const int y = __float2int_rd(((float)s + 0.5f) * p.inv_wp);
@@ -379,10 +382,11 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
 
     // ---- phase A: u_phi_h = u x Ws^T + bias, in place, 16-row blocks per warp (the conv is pointwise: any row order) ----
     uint32_t wf[4][8][2];
-    for (int q = 0; q < 4; ++q) {
-      if (q == 0) asm volatile("cp.async.wait_group 4;" ::: "memory");
-      else if (q == 1) asm volatile("cp.async.wait_group 3;" ::: "memory");
-      else if (q == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    for (int q = 0; q < NQ; ++q) {
+      // groups in flight behind part q: the NQ - 1 - q later parts + the next head's prefetch
+      if (NQ - q == 4) asm volatile("cp.async.wait_group 4;" ::: "memory");
+      else if (NQ - q == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+      else if (NQ - q == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
       else asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncthreads();  // quarter q has landed for every thread (q == 0 also publishes the setup writes)
       if (q == 0) {

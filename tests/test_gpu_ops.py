@@ -787,3 +787,56 @@ def test_sablock_fused_vs_unfused_and_fp64(B, H, W, use_pe, prec):
     print(f"[sablock {B}x{H}x{W} pe={use_pe} {prec}] fused vs fp64 {e_f:.2e}, unfused {e_u:.2e}")
     tol = 6e-3 if prec == "bf16" else 8e-4
     assert e_f < tol and e_u < tol
+
+
+@pytest.mark.parametrize("cin,cout,layout,dtype", [(1, 64, "nchw", torch.float32), (3, 64, "nchw", torch.bfloat16),
+                                                   (4, 64, "nchw", torch.bfloat16), (16, 128, "nhwc", torch.bfloat16),
+                                                   (16, 128, "nhwc", torch.float32), (16, 16, "nhwc", torch.float32)])
+def test_channel_lift_v2(cin, cout, layout, dtype):
+    """1x1 channel lift (filter in registers, inputs staged once per CTA): the encoder's NCHW fp32 input lift and the
+    propagator's / decoder's lift of the fp32 NHWC latent, with bias, Swish and a pixel count that is not a multiple of the
+    128-pixel CTA tile; 16-bit and fp32 outputs"""
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(7 + cin + cout)
+    B, H, W = 5, 9, 13
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / max(1.0, cin ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.2
+    ref = F.silu(F.conv2d(x.double(), w.double(), b.double()))
+    h = Holder(w, b)
+    xa = ops.Act.from_nchw(x.to(DEV)) if layout == "nchw" else act_from(x, torch.float32)
+    with ops.precision("fp32" if dtype == torch.float32 else "bf16"):
+        y = ops.conv2d(xa, ops.PackedFilter.of(h.weight, h.bias), act=ops.ACT_SILU, out_dtype=dtype)
+    torch.cuda.synchronize()
+    assert y.t.dtype == dtype
+    assert relerr(act_to_nchw(y), ref) < (3e-6 if dtype == torch.float32 else 4e-3)  # bf16: output rounding only
+
+
+def test_pointwise_projection_step_grouped_output():
+    """lns_pointwise_proj_steps: the samples are `steps` groups of `B` trajectories (step-major); sample (t, b) must land in
+    slot [b][t] of the [B, K, C, H, W] result -- and nowhere else"""
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(29)
+    Bt, S, K, C, H, W, Co = 3, 2, 5, 64, 12, 20, 2
+    x = torch.randn(S * Bt, C, H, W, generator=g)
+    w = torch.randn(Co, C, 1, 1, generator=g) / 8
+    b = torch.randn(Co, generator=g)
+    sc, sh = torch.rand(S * Bt, C, generator=g) + 0.5, torch.randn(S * Bt, C, generator=g) * 0.2
+    xin = F.silu(x.bfloat16().double() * sc[:, :, None, None].double() + sh[:, :, None, None].double())
+    ref = F.conv2d(xin, w.double(), b.double()).view(S, Bt, Co, H, W)
+    h = Holder(w, b)
+    out = torch.zeros(Bt, K, Co, H, W, device=DEV)
+    t0, chw = 2, Co * H * W  # the group covers steps t0, t0 + 1
+    dst = ops.Act(out.view(-1)[t0 * chw:], S * Bt, H, W, Co, bstride=K * chw, layout=ops.NCHW, group=Bt, gstride=chw)
+    with ops.precision("bf16"):
+        ops.conv2d(act_from(x, torch.bfloat16), ops.PackedFilter.of(h.weight, h.bias),
+                   pro=(sc.to(DEV).reshape(-1), sh.to(DEV).reshape(-1), ops.ACT_SILU), out=dst, out_layout=ops.NCHW)
+    torch.cuda.synchronize()
+    got = out.cpu()
+    for t in range(S):
+        assert relerr(got[:, t0 + t], ref[t]) < 3e-4
+    assert float(got[:, :t0].abs().max()) == 0.0 and float(got[:, t0 + S:].abs().max()) == 0.0
+    with pytest.raises(ops.LnsError):  # any other conv refuses a step-grouped output
+        w3 = Holder(torch.randn(8, C, 1, 1, generator=g), torch.zeros(8))
+        bad = ops.Act(torch.zeros(S * Bt * 8 * H * W, device=DEV), S * Bt, H, W, 8, layout=ops.NCHW, group=Bt, gstride=1)
+        ops.conv2d(act_from(x, torch.bfloat16), ops.PackedFilter.of(w3.weight, w3.bias), out=bad, out_layout=ops.NCHW)

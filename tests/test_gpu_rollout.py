@@ -258,3 +258,30 @@ def test_encode_frames_bulk_equals_direct_encode():
         enc = encode_dataset(model.autoencoder, data, mean, std, chunk=16)
     assert len(enc) == 4 and enc[0].shape == (9, 16, 8, 8)
     assert (enc[2] == z_direct[18:27]).all()
+
+
+@pytest.mark.parametrize("name,prec", [("ns2d", "bf16"), ("ns2d", "fp32"), ("twophase_cond", "bf16"), ("sw", "bf16")])
+def test_pipelined_decode_equals_serial(name, prec):
+    """The decode groups pipelined on a second stream behind the propagator loop (step-major latent stack, output projection
+    writing slot [b][t] directly) return exactly what the serial order returns (all steps, then the decode in chunks) -- as an
+    eager launch sequence and as a captured two-stream CUDA graph; K = 7 is not a multiple of the group size."""
+    from lns_b200.rollout import Rollout
+    cfg, model, _ = build(name)
+    B, K = 4, 7
+    x, param = O.make_inputs(cfg, B, seed=21)
+    x = x.to(DEV)
+    param = param.to(DEV) if param is not None else None
+    with torch.no_grad():
+        serial = Rollout(model, batch=B, steps=K, precision=prec, use_graph=False)
+        serial.pipeline = False
+        ref = serial(x, param).clone()
+        assert serial.steps_per_group == 0
+        zref = serial.latents().clone()
+        for use_graph in (False, True):
+            ro = Rollout(model, batch=B, steps=K, precision=prec, use_graph=use_graph)
+            ro.pipeline = True
+            y1 = ro(x, param).clone()
+            y2 = ro(x, param).clone()
+            assert ro.steps_per_group >= 1 and -(-K // ro.steps_per_group) >= 4  # at least four decode groups
+            assert torch.equal(y1, ref) and torch.equal(y2, ref)
+            assert torch.equal(ro.latents(), zref)
