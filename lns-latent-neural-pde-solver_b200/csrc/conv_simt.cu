@@ -223,6 +223,9 @@ __global__ void __launch_bounds__(256) lift1x1_kernel(const SimtParams p, int pi
 // pixel's Cout / 4 threads write its channels as one contiguous run.
 // Same accumulation order as conv_simt_kernel (c ascending, then bias): bit-identical on the fp32 path.
 constexpr int kLiftPix = 128;  // pixels per CTA
+// Q4 = input channels / 4, rounded up (compile time: the filter registers of absent channels do not exist -- 1 | 3 | 4 input
+// channels need 16 instead of 64 of them, which more than doubles the resident CTAs of the encoder's full-resolution lift)
+template <int Q4>
 __global__ void __launch_bounds__(256) lift1x1_v2_kernel(const SimtParams p) {
   __shared__ __align__(16) float xs[kLiftPix * 16];
   const ConvGeom& g = p.g;
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(256) lift1x1_v2_kernel(const SimtParams p) {
   const int HW = g.Hout * g.Wout;
   const int64_t m0 = (int64_t)blockIdx.x * kLiftPix;
   const int npx = (int)min((int64_t)kLiftPix, (int64_t)p.M - m0);
-  const int q4 = (Cin + 3) >> 2;
+  constexpr int q4 = Q4;
   if (p.x_layout == LNS_NCHW) {
     // the reference's NCHW fp32 input (encoder lift, Cin = 1 | 3 | 4): consecutive threads -> consecutive pixels of one plane;
     // channels up to the next multiple of 4 are zero (their filter registers are zero too: fma(0, 0, a) == a)
@@ -252,9 +255,9 @@ __global__ void __launch_bounds__(256) lift1x1_v2_kernel(const SimtParams p) {
   }
   const int TPP = Cout >> 2, ppp = 256 / TPP;  // threads per pixel, pixels per pass
   const int cq = threadIdx.x % TPP, pl = threadIdx.x / TPP;
-  float4 wr[16];
+  float4 wr[Q4 * 4];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) wr[c] = (c < Cin) ? __ldg(reinterpret_cast<const float4*>(p.w + c * Cout + cq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < Q4 * 4; ++c) wr[c] = (c < Cin) ? __ldg(reinterpret_cast<const float4*>(p.w + c * Cout + cq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + cq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
   const bool fast = is_h16(p.y_dtype);
   __syncthreads();
@@ -265,8 +268,8 @@ __global__ void __launch_bounds__(256) lift1x1_v2_kernel(const SimtParams p) {
   for (int pi = pl; pi < npx; pi += ppp) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-    for (int c4 = 0; c4 < 16; c4 += 4) {
-      if (c4 < Cin) {
+    for (int c4 = 0; c4 < Q4 * 4; c4 += 4) {
+      {
         const float4 xv = *reinterpret_cast<const float4*>(xs + pi * 16 + c4);
         const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
@@ -336,7 +339,13 @@ int conv2d_simt(const LnsConvDesc* d, cudaStream_t stream) {
     if (d->Cout % 4 == 0 && tpp <= 256 && 256 % tpp == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
         (!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0) &&
         (!d->sample_bias || (reinterpret_cast<uintptr_t>(d->sample_bias) & 15) == 0)) {
-      lift1x1_v2_kernel<<<(unsigned)((M + kLiftPix - 1) / kLiftPix), 256, 0, stream>>>(p);
+      const unsigned nblk = (unsigned)((M + kLiftPix - 1) / kLiftPix);
+      switch ((d->Cin + 3) / 4) {
+        case 1: lift1x1_v2_kernel<1><<<nblk, 256, 0, stream>>>(p); break;
+        case 2: lift1x1_v2_kernel<2><<<nblk, 256, 0, stream>>>(p); break;
+        case 3: lift1x1_v2_kernel<3><<<nblk, 256, 0, stream>>>(p); break;
+        default: lift1x1_v2_kernel<4><<<nblk, 256, 0, stream>>>(p); break;
+      }
       return check_launch("lift1x1_v2_kernel");
     }
     const size_t smem = ((size_t)d->Cin * d->Cout + d->Cout) * sizeof(float);
