@@ -491,16 +491,16 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
   const uint32_t bias_b = stage_out + stage_bytes + res_bytes;         // NT x 128 B, swizzled K-major like the filter
   const uint32_t ones_a = bias_b + (uint32_t)NT * 128u;    // 8 x 128 B
   const uint32_t bar_base = ones_a + 1024u;
-  // barriers: w, halo_full[4], halo_empty[4], acc_full[4], acc_empty[4]; then the TMEM slot; then res_full[4 epilogue warps]
+  // barriers: w, halo_full[4], halo_empty[4], acc_full[8], acc_empty[8]; then the TMEM slot; then res_full[4 epilogue warps]
   const uint32_t w_bar = bar_base;
   auto halo_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto halo_empty = [&](int s) { return bar_base + 8u * (5 + s); };
   auto acc_full = [&](int a) { return bar_base + 8u * (9 + a); };
-  auto acc_empty = [&](int a) { return bar_base + 8u * (13 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * 17;
-  auto res_full = [&](int w) { return bar_base + 8u * (18 + w); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (17 + a); };  // up to 8 accumulators
+  const uint32_t tmem_slot = bar_base + 8u * 25;
+  auto res_full = [&](int w) { return bar_base + 8u * (26 + w); };
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + stage_bytes + res_bytes + NT * 128 + 1024 + 8 * 17);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kWBytes + (size_t)p.stages * p.halo_bytes + stage_bytes + res_bytes + NT * 128 + 1024 + 8 * 25);
 
   const ConvGeom& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -769,6 +769,7 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
   }
   int stages = (227 * 1024 - fixed) / p.halo_bytes;
   if (stages > 4) stages = 4;
+  if (stages == 3) stages = 2;  // the issuer count must divide the ring depth (see below)
   LNS_REQUIRE(stages >= 2, "lns_conv2d(halo): shared memory too small for dilation %d with Cout %d", d->dil, d->Cout);
   p.stages = stages;
   int sms = 148;
@@ -815,19 +816,27 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
             d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->dil, p.resize, p.tma_store, p.nbuf, stages, grid, d->x,
             (long long)d->x_bstride, d->y, (long long)d->y_bstride, d->act, d->bias != nullptr, d->sample_bias != nullptr,
             d->pre_add != nullptr, d->residual != nullptr, p.tma_res, d->x_dtype, d->y_dtype, p.g.circ_h, p.g.circ_w);
-  int cfg = 0;
+  // MMA issue warps.  Tile `it` uses ring stage it % stages and accumulator it % 4 and is issued by warp it % kIssuers: every
+  // mbarrier must be waited on by ONE agent in phase order (a parity wait issued a whole phase early passes immediately), so
+  // the issuer count has to divide both the ring depth and the accumulator count.  Measured on B200 at 64->64 @ 64x64 (4
+  // stages): 1 issuer 0.64 ms, 2 issuers 1053 TFLOP/s, 4 issuers 1101 -- the instruction stream of one issuing warp (~100
+  // cycles per tcgen05.mma with its descriptor arithmetic) limits the tensor pipe at N = 64.  (3 issuers measured 1137-1148 but
+  // break the one-agent rule: with a 2-stage ring that configuration dead-locked.)  LNS_HALO_ISSUERS=1|2|4 overrides.
+  LNS_REQUIRE(p.stages == 2 || p.stages == 4, "lns_conv2d(halo): internal: ring depth %d", p.stages);
+  int issuers = p.stages == 4 ? 4 : 2;
   {
-    const char* c = getenv("LNS_HALO_CFG");  // tuning: 0 = 1 issuer / 2 accumulators, 1 = 1/4, 2 = 2/4 (default, fastest on B200)
-    cfg = c ? atoi(c) : 2;
+    const char* c = getenv("LNS_HALO_ISSUERS");
+    const int want = c ? atoi(c) : 0;
+    if ((want == 1 || want == 2 || want == 4) && p.stages % want == 0) issuers = want;
   }
   if (NT == 64) {
-    if (cfg == 1) return launch_halo<64, 1, 4>(p, tmap_y, tmap_r, smem, grid, stream);
-    if (cfg == 2) return launch_halo<64, 2, 4>(p, tmap_y, tmap_r, smem, grid, stream);
-    return launch_halo<64, 1, 2>(p, tmap_y, tmap_r, smem, grid, stream);
+    if (issuers == 4) return launch_halo<64, 4, 4>(p, tmap_y, tmap_r, smem, grid, stream);
+    if (issuers == 2) return launch_halo<64, 2, 4>(p, tmap_y, tmap_r, smem, grid, stream);
+    return launch_halo<64, 1, 4>(p, tmap_y, tmap_r, smem, grid, stream);
   }
-  if (cfg == 1) return launch_halo<128, 1, 4>(p, tmap_y, tmap_r, smem, grid, stream);
-  if (cfg == 2) return launch_halo<128, 2, 4>(p, tmap_y, tmap_r, smem, grid, stream);
-  return launch_halo<128, 1, 2>(p, tmap_y, tmap_r, smem, grid, stream);
+  if (issuers == 4) return launch_halo<128, 4, 4>(p, tmap_y, tmap_r, smem, grid, stream);
+  if (issuers == 2) return launch_halo<128, 2, 4>(p, tmap_y, tmap_r, smem, grid, stream);
+  return launch_halo<128, 1, 4>(p, tmap_y, tmap_r, smem, grid, stream);
 }
 
 }  // namespace lns
