@@ -117,3 +117,25 @@ def test_reference_defects_are_mirrored():
         SimpleResNet(args)  # ResidualBlock without num_dimensions, modules/propagator.py:22-24
     with pytest.raises(TypeError):
         ConditionalResNet(args)
+
+
+def test_rollout_chunking_rules():
+    """Decode chunk = about 16 M output pixels per channel, split evenly, rounded up to a multiple of the SM count; pipelined
+    decode groups = whole rollout steps, about one chunk each, at least four groups per rollout (host logic, no GPU)."""
+    import types
+
+    import torch
+    from lns_b200.rollout import Rollout
+    stub = types.SimpleNamespace(Ly=64, Lx=64, device=torch.device("cpu"), decode_chunk=None, B=1184, K=20)
+    stub._default_chunk = lambda n: Rollout._default_chunk(stub, n)
+    assert Rollout._default_chunk(stub, 1184 * 20) == 4736          # 5 equal chunks of 32 x 148 samples
+    assert Rollout._default_chunk(stub, 1024 * 20) % 148 == 0
+    assert Rollout._default_chunk(stub, 8) == 8                     # never more than the samples there are
+    assert Rollout._steps_per_group(stub, 1184 * 20) == 4           # 4 steps x 1184 trajectories = one chunk
+    stub.B, stub.K = 4, 2
+    assert Rollout._steps_per_group(stub, 8) == 1
+    stub.B, stub.K, stub.Ly, stub.Lx = 64, 20, 96, 192              # shallow water, BASELINE config 2
+    s = Rollout._steps_per_group(stub, 64 * 20)
+    assert 1 <= s <= 5 and -(-20 // s) >= 4
+    stub.decode_chunk = 640
+    assert Rollout._steps_per_group(stub, 64 * 20) == 5
