@@ -294,7 +294,7 @@ def main():
     import torch.distributed as dist
     from lns_b200 import ops
     from lns_b200.configs import get_config
-    from lns_b200.dist import gather_fields, init_from_env
+    from lns_b200.dist import init_from_env
     from lns_b200.latent_dynamics import LatentDynamics
     from lns_b200.rollout import Rollout
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
