@@ -49,7 +49,6 @@ def patched(xa, filt, **kw):
 
 
 ops.conv2d = patched
-import modules._base as mb  # noqa: E402
 with torch.no_grad():
     ro.build()
     torch.cuda.synchronize()
