@@ -294,7 +294,7 @@ def main():
     import torch.distributed as dist
     from lns_b200 import ops
     from lns_b200.configs import get_config
-    from lns_b200.dist import init_from_env
+    from lns_b200.dist import OverlappedGather, init_from_env
     from lns_b200.latent_dynamics import LatentDynamics
     from lns_b200.rollout import Rollout
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -327,24 +327,17 @@ def main():
     gather = world > 1 and not args.no_gather
     # N > 1: the final all-gather of the predicted fields (NCCL over NVLink) of step i runs on NCCL's stream out of a staging
     # copy while the rollout of step i+1 computes; the timed region ends when the last gather has completed.
-    gstate = {"pending": None}
-    if gather:
-        g_stage = torch.empty((B, R, ro.C, ro.Ly, ro.Lx), dtype=torch.float32, device=device)
-        g_full = torch.empty((B * world, R, ro.C, ro.Ly, ro.Lx), dtype=torch.float32, device=device)
+    og = OverlappedGather((B, R, ro.C, ro.Ly, ro.Lx), torch.float32, device) if gather else None
 
     def one_step():
         out = ro(x_dev, p_dev)
-        if gather:
-            if gstate["pending"] is not None:
-                gstate["pending"].wait()       # the gather that reads the staging buffer has finished (stream-level wait)
-            g_stage.copy_(out, non_blocking=True)
-            gstate["pending"] = dist.all_gather_into_tensor(g_full, g_stage, async_op=True)
+        if og is not None:
+            og.submit(out)
         return out
 
     def drain():
-        if gstate["pending"] is not None:
-            gstate["pending"].wait()
-            gstate["pending"] = None
+        if og is not None:
+            og.wait()
 
     def barrier():
         if world > 1:

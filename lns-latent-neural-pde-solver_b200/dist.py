@@ -56,6 +56,34 @@ def gather_fields(local, batch, group=None):
     return torch.cat([buf[r * mx:r * mx + counts[r]] for r in range(world)], 0)
 
 
+class OverlappedGather:
+    """All-gather of equal per-rank results that overlaps the NEXT step's compute: ``submit(local)`` copies the rank's result
+    into a staging buffer (so the producer may overwrite ``local`` at once -- the rollout graph writes into a fixed buffer)
+    and starts the all-gather asynchronously on the backend's own stream; ``wait()`` (also called by the next ``submit``)
+    returns the gathered [world * b, ...] tensor.  Per-rank shards must be equal (use gather_fields for ragged batches)."""
+
+    def __init__(self, local_shape, dtype, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.stage = torch.empty(tuple(local_shape), dtype=dtype, device=device)
+        self.full = torch.empty((local_shape[0] * self.world,) + tuple(local_shape[1:]), dtype=dtype, device=device)
+        self.pending = None
+
+    def submit(self, local):
+        self.wait()  # the previous gather still reads the staging buffer
+        self.stage.copy_(local, non_blocking=True)
+        if self.world == 1:
+            self.full.copy_(self.stage, non_blocking=True)
+        else:
+            self.pending = dist.all_gather_into_tensor(self.full, self.stage, group=self.group, async_op=True)
+
+    def wait(self):
+        if self.pending is not None:
+            self.pending.wait()
+            self.pending = None
+        return self.full
+
+
 class ShardedRollout:
     """Rolls out this rank's slice of a global batch and (optionally) all-gathers the fields."""
 

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lns_b200.dist import gather_fields, shard_bounds
+from lns_b200.dist import OverlappedGather, gather_fields, shard_bounds
 
 
 def test_shard_bounds_cover_the_batch():
@@ -44,6 +44,36 @@ def test_gather_fields_gloo_world2(batch):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def _worker_overlap(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    og = OverlappedGather((3, 2, 4), torch.float32, torch.device("cpu"))
+    ok = True
+    buf = torch.empty(3, 2, 4)  # the producer's fixed output buffer, overwritten every step
+    for step in range(4):
+        buf.copy_(torch.full((3, 2, 4), float(10 * step + rank)))
+        og.submit(buf)
+        buf.fill_(-1.0)          # the next step overwrites the producer buffer while the gather is in flight
+        want = torch.cat([torch.full((3, 2, 4), float(10 * step + r)) for r in range(world)], 0)
+        ok = ok and bool(torch.equal(og.wait(), want))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_overlapped_gather_gloo_world2():
+    """the staging copy decouples the gather of step i from the producer buffer that step i+1 overwrites"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_overlap, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in procs)
