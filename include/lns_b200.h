@@ -53,7 +53,11 @@ enum {
                        /* tcgen05.mma (needs Cin % 64 == 0 and Cout % 16 == 0)                   */
   LNS_W_UMMA_TF32 = 2, /* [tap][Cin/32][Cout][32] fp32 rounded to TF32, same swizzled image, for   */
                        /* tcgen05.mma.kind::tf32 (needs Cin % 32 == 0 and Cout % 16 == 0)         */
-  LNS_W_UMMA_F16 = 3   /* LNS_W_UMMA_BF16's layout with IEEE-half elements (for LNS_F16 activations) */
+  LNS_W_UMMA_F16 = 3,  /* LNS_W_UMMA_BF16's layout with IEEE-half elements (for LNS_F16 activations) */
+  LNS_W_UMMA_F16X2 = 4 /* SPLIT filter: two LNS_W_UMMA_F16 images back to back, hi = rn_f16(w) and lo = rn_f16(w - hi)  */
+                       /* (22 significant bits).  With LNS_F16 activations the conv issues 2 MMAs per K step        */
+                       /* (filter rounding removed); with LNS_F32 activations the kernel splits them the same way in  */
+                       /* its producer and issues 3 MMAs (fp32-class result on the f16 tensor path)                   */
 };
 /* which engine executes lns_conv2d */
 enum {
@@ -61,8 +65,12 @@ enum {
   LNS_ENGINE_UMMA = 1, /* tcgen05 implicit GEMM, per-tap gather (any kernel/stride/dilation/resize, Cin%64==0)  */
   LNS_ENGINE_HALO = 2, /* tcgen05 implicit GEMM, shared-memory halo + resident filter: same-size 3x3 stride-1     */
                        /* convs with Cin == 64, Cout in {64,128} (the full-resolution layers)                     */
-  LNS_ENGINE_LATENT = 3 /* tcgen05 implicit GEMM for the 8x8 circular latent grid, 128 -> 128 channels, dilation   */
-                        /* 1|2: resident halos of 4 samples, streamed filter (the propagator's 3x3 convs)          */
+  LNS_ENGINE_LATENT = 3, /* tcgen05 implicit GEMM for the 8x8 circular latent grid, 128 -> 128 channels, dilation  */
+                         /* 1|2: resident halos of 4 samples, streamed filter (the propagator's 3x3 convs)         */
+  LNS_ENGINE_COARSE = 4  /* tcgen05 implicit GEMM for the coarse levels: same-size 3x3 stride-1 convs, Cin / Cout in */
+                         /* {64,128}, dilation 1-3, any padding / nearest resize, 8x8 output blocks with resident    */
+                         /* halos and a streamed filter.  Input 16-bit, or LNS_F32 = split into f16 hi + lo halo      */
+                         /* planes in the producer (A.W = Ahi.W + Alo.W; with LNS_W_UMMA_F16X2 also + Ahi.Wlo)        */
 };
 
 const char* lns_version(void);

@@ -24,6 +24,38 @@ int check_launch(const char* what) {
   return LNS_OK;
 }
 
+int opt_in_smem(const void* func, int bytes, SmemOptIn& st, const char* what) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaGetDevice: %s", what, cudaGetErrorString(e));
+    return LNS_E_CUDA;
+  }
+  const uint64_t bit = 1ull << (dev & 63);
+  std::atomic<uint64_t>& word = st.done[(dev >> 6) & 3];
+  if (word.load(std::memory_order_acquire) & bit) return LNS_OK;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%d B of dynamic shared memory) on device %d: %s", what, bytes, dev, cudaGetErrorString(e));
+    return LNS_E_CUDA;
+  }
+  word.fetch_or(bit, std::memory_order_release);
+  return LNS_OK;
+}
+
+int device_sm_count() {
+  static std::atomic<int> cache[256];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::atomic<int>& c = cache[dev & 255];
+  int v = c.load(std::memory_order_relaxed);
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    c.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 ConvGeom make_geom(const LnsConvDesc* d) {
   ConvGeom g;
   g.B = d->B; g.Hin = d->Hin; g.Win = d->Win; g.Cin = d->Cin; g.Hv = d->Hv; g.Wv = d->Wv;
@@ -91,6 +123,7 @@ int lns_conv2d(const LnsConvDesc* d, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (d->engine == LNS_ENGINE_HALO) return lns::conv2d_halo(d, s);
   if (d->engine == LNS_ENGINE_LATENT) return lns::conv2d_latent(d, s);
+  if (d->engine == LNS_ENGINE_COARSE) return lns::conv2d_coarse(d, s);
   if (d->engine == LNS_ENGINE_UMMA) return lns::conv2d_umma(d, s);
   if (d->engine == LNS_ENGINE_SIMT) return lns::conv2d_simt(d, s);
   lns::set_error("lns_conv2d: unknown engine %d", d->engine);

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/lns_b200.h"
 
 namespace lns {
@@ -13,6 +15,21 @@ namespace lns {
 // ---- error plumbing ------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);  // cudaGetLastError -> LNS_E_CUDA (+ message) or LNS_OK
+
+// Dynamic shared memory above 48 KB must be opted into per (kernel, DEVICE): one flag bit per device ordinal, set after the
+// first successful cudaFuncSetAttribute on that device (idempotent, so a race between two host threads is harmless).
+struct SmemOptIn {
+  std::atomic<uint64_t> done[4];
+};
+int opt_in_smem(const void* func, int bytes, SmemOptIn& st, const char* what);
+// one static flag set per call site (inside a template: per instantiation)
+#define LNS_OPT_IN_SMEM(kern, bytes, what)                                                     \
+  do {                                                                                         \
+    static lns::SmemOptIn lns_opt_in_state_;                                                   \
+    const int lns_opt_in_rc_ = lns::opt_in_smem(reinterpret_cast<const void*>(kern), (bytes), lns_opt_in_state_, (what)); \
+    if (lns_opt_in_rc_ != LNS_OK) return lns_opt_in_rc_;                                       \
+  } while (0)
+int device_sm_count();  // SM count of the CURRENT device (cached per device ordinal)
 
 #define LNS_REQUIRE(cond, ...)        \
   do {                                \
@@ -204,6 +221,8 @@ int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream);
 int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream);
 bool conv_halo_supported(const LnsConvDesc* d);
 int conv2d_latent(const LnsConvDesc* d, cudaStream_t stream);
+int conv2d_coarse(const LnsConvDesc* d, cudaStream_t stream);
+bool conv_coarse_supported(const LnsConvDesc* d);
 bool conv_latent_supported(const LnsConvDesc* d);
 int validate_conv(const LnsConvDesc* d);
 ConvGeom make_geom(const LnsConvDesc* d);

@@ -473,13 +473,16 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, const CUtenso
   if (tma && lane == 0) hptx::bulk_wait_all();  // the staging buffers must outlive the stores that read them
 }
 
-template <int NT, int kIssuers, int kAccs>
+// WS = 1: SPLIT filter (LNS_W_UMMA_F16X2: hi plane + lo plane, both resident) and two MMAs per (tap, k) -- A.Whi + A.Wlo --
+// so the filter's 16-bit rounding error disappears from the layer (Cout = 64 only: 2 x 72 KB of filter = the Cout = 128 budget).
+template <int NT, int kIssuers, int kAccs, int WS>
 __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
     conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (hptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - hptx::smem_u32(smem_raw));
-  constexpr uint32_t kWBytes = 9u * NT * 128u;
+  constexpr uint32_t kWPlane = 9u * NT * 128u;
+  constexpr uint32_t kWBytes = kWPlane * (1u + WS);
   const uint32_t w_base = smem_base;
   const uint32_t halo_base = smem_base + kWBytes;
   const uint32_t stage_out = halo_base + (uint32_t)p.stages * (uint32_t)p.halo_bytes;  // 4 warps x nbuf x 4 KB output staging
@@ -558,8 +561,11 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
     if (tid == 0) {
       // resident filter: one bulk copy per tap (the packed image is already the swizzled shared-memory layout)
       hptx::mbar_expect_tx(w_bar, kWBytes);
-      for (int tap = 0; tap < 9; ++tap)
+      for (int tap = 0; tap < 9; ++tap) {
         hptx::bulk_g2s(w_base + (uint32_t)tap * NT * 128u, p.w + (int64_t)tap * g.Cout * 64, (uint32_t)NT * 128u, w_bar);
+        if (WS)  // lo plane: 9 * Cout * 64 elements behind the hi plane
+          hptx::bulk_g2s(w_base + kWPlane + (uint32_t)tap * NT * 128u, p.w + (int64_t)(9 + tap) * g.Cout * 64, (uint32_t)NT * 128u, w_bar);
+      }
     }
     // The halo is a rectangle and the source index map is separable: offset(hy, hx) = rowterm(hy) + colterm(hx) (wrap / zero
     // padding / nearest resize; "outside" -> zero fill).
@@ -627,9 +633,13 @@ __global__ void __launch_bounds__(32 * (4 + kIssuers + 4), 1)
           const uint32_t a_lo = st_lo + (uint32_t)ky * row_lo + (uint32_t)kx * col_lo;
           const uint32_t b_lo = w_lo + (uint32_t)tap * ((uint32_t)NT * 128u >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+          for (int k = 0; k < 4; ++k) {
             hptx::umma_bf16_if((p.debug & 4) ? 0u : leader, d_tmem, a_lo + 2u * k, desc_hi_a, b_lo + 2u * k, desc_hi_b, idesc,
                                (tap | k) != 0 ? 1u : 0u);
+            if (WS)
+              hptx::umma_bf16_if((p.debug & 4) ? 0u : leader, d_tmem, a_lo + 2u * k, desc_hi_a, b_lo + (kWPlane >> 4) + 2u * k,
+                                 desc_hi_b, idesc, 1u);
+          }
         }
         if (p.bias)
           hptx::umma_bf16_if(leader, d_tmem, (ones_a & 0x3FFFFu) >> 4, (1u << 14) | (2u << 29) /* SBO = 0 */,
@@ -667,7 +677,8 @@ bool conv_halo_supported(const LnsConvDesc* d) {
          d->pad_t == d->dil && d->pad_l == d->dil && d->Hout == d->Hv && d->Wout == d->Wv && d->dil >= 1 &&
          d->dil <= 3 && is_h16_host(d->x_dtype) && d->x_layout == LNS_NHWC && d->y_layout == LNS_NHWC &&
          d->pro_scale == nullptr && d->pro_act == LNS_ACT_NONE &&
-         d->w_format == (d->x_dtype == LNS_F16 ? LNS_W_UMMA_F16 : LNS_W_UMMA_BF16) &&
+         (d->w_format == (d->x_dtype == LNS_F16 ? LNS_W_UMMA_F16 : LNS_W_UMMA_BF16) ||
+          (d->w_format == LNS_W_UMMA_F16X2 && d->x_dtype == LNS_F16 && d->Cout == 64)) &&
          d->dil <= d->Hv && d->dil <= d->Wv;
 }
 
@@ -703,10 +714,10 @@ static bool make_y_tmap(CUtensorMap* tm, const LnsConvDesc* d, const void* base,
   return r == CUDA_SUCCESS;
 }
 
-template <int NT, int KI, int KA>
+template <int NT, int KI, int KA, int WS = 0>
 static int launch_halo(const HaloParams& p, const CUtensorMap& tmap_y, const CUtensorMap& tmap_r, int smem_bytes, int grid,
                        cudaStream_t stream) {
-  auto kern = conv_halo_kernel<NT, KI, KA>;
+  auto kern = conv_halo_kernel<NT, KI, KA, WS>;
   static bool once = false;
   if (!once) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -760,9 +771,10 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
     p.debug = dbg ? atoi(dbg) : 0;
   }
   const int NT = d->Cout;
+  const int wsplit = d->w_format == LNS_W_UMMA_F16X2 ? 1 : 0;
   // output staging: two 4 KB buffers per epilogue warp when four halo stages still fit next to them, else one
   p.nbuf = 2;
-  int fixed = 9 * NT * 128 + 4 * p.nbuf * 4096 /*output staging*/ + NT * 128 + 1024 /*bias + ones tiles*/ + 256 + 1024;
+  int fixed = (1 + wsplit) * 9 * NT * 128 + 4 * p.nbuf * 4096 /*output staging*/ + NT * 128 + 1024 /*bias + ones tiles*/ + 256 + 1024;
   if ((227 * 1024 - fixed) / p.halo_bytes < 4) {
     p.nbuf = 1;
     fixed -= 4 * 4096;
@@ -828,6 +840,11 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
     const char* c = getenv("LNS_HALO_ISSUERS");
     const int want = c ? atoi(c) : 0;
     if ((want == 1 || want == 2 || want == 4) && p.stages % want == 0) issuers = want;
+  }
+  if (wsplit) {
+    if (issuers == 4) return launch_halo<64, 4, 4, 1>(p, tmap_y, tmap_r, smem, grid, stream);
+    if (issuers == 2) return launch_halo<64, 2, 4, 1>(p, tmap_y, tmap_r, smem, grid, stream);
+    return launch_halo<64, 1, 4, 1>(p, tmap_y, tmap_r, smem, grid, stream);
   }
   if (NT == 64) {
     if (issuers == 4) return launch_halo<64, 4, 4>(p, tmap_y, tmap_r, smem, grid, stream);

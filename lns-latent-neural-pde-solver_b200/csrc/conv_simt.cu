@@ -377,6 +377,7 @@ __global__ void pack_simt_kernel(const float* __restrict__ w, int Cout, int Cin,
 // [tap][Cin/64][Cout][64] bf16; inside each 128-byte row the eight 16-byte chunks are XOR-swizzled with (row & 7),
 // i.e. the image is byte-for-byte what tcgen05's SWIZZLE_128B K-major shared-memory layout expects.
 // (f16 != 0: IEEE-half elements instead of bf16 -- LNS_W_UMMA_F16)
+// (f16 == 2: LNS_W_UMMA_F16X2 -- the hi image followed by the image of lo = rn_f16(w - hi))
 __global__ void pack_umma_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int f16,
                                  uint16_t* __restrict__ out) {
   int64_t total = (int64_t)Cout * Cin * KH * KW;
@@ -393,6 +394,7 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, int Cout, int Cin,
     int chunk = (kk >> 3) ^ (n & 7);
     int64_t o = (((int64_t)tap * slabs + slab) * Cout + n) * 64 + chunk * 8 + (kk & 7);
     out[o] = f16 ? to_h16<true>(v) : to_h16<false>(v);
+    if (f16 == 2) out[total + o] = to_h16<true>(v - from_h16<true>(out[o]));
   }
 }
 
@@ -424,6 +426,7 @@ int64_t lns_packed_weight_bytes(int Cout, int Cin, int KH, int KW, int format) {
   if (format == LNS_W_SIMT_F32) return n * 4;
   if (format == LNS_W_UMMA_BF16 || format == LNS_W_UMMA_F16) return (Cin % 64 == 0 && Cout % 16 == 0) ? n * 2 : -1;
   if (format == LNS_W_UMMA_TF32) return (Cin % 32 == 0 && Cout % 16 == 0) ? n * 4 : -1;
+  if (format == LNS_W_UMMA_F16X2) return (Cin % 64 == 0 && Cout % 16 == 0) ? n * 4 : -1;
   return -1;
 }
 
@@ -435,10 +438,11 @@ int lns_pack_conv_weight(const float* w, int Cout, int Cin, int KH, int KW, int 
   if (blocks > 4096) blocks = 4096;
   if (format == LNS_W_SIMT_F32) {
     lns::pack_simt_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, KH, KW, reinterpret_cast<float*>(out));
-  } else if (format == LNS_W_UMMA_BF16 || format == LNS_W_UMMA_F16) {
+  } else if (format == LNS_W_UMMA_BF16 || format == LNS_W_UMMA_F16 || format == LNS_W_UMMA_F16X2) {
     LNS_REQUIRE(Cin % 64 == 0 && Cout % 16 == 0, "lns_pack_conv_weight: UMMA format needs Cin%%64==0, Cout%%16==0 (got %d,%d)",
                 Cin, Cout);
-    lns::pack_umma_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, KH, KW, format == LNS_W_UMMA_F16 ? 1 : 0,
+    lns::pack_umma_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, KH, KW,
+                                                 format == LNS_W_UMMA_F16X2 ? 2 : (format == LNS_W_UMMA_F16 ? 1 : 0),
                                                  reinterpret_cast<uint16_t*>(out));
   } else if (format == LNS_W_UMMA_TF32) {
     LNS_REQUIRE(Cin % 32 == 0 && Cout % 16 == 0, "lns_pack_conv_weight: TF32 format needs Cin%%32==0, Cout%%16==0 (got %d,%d)",

@@ -50,6 +50,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ int4 ldg_nc16(const int4* p) {
+  int4 v;
+  asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -148,6 +153,7 @@ struct UmmaParams {
   void* y;
   int y_dtype;
   int x_f16;  // 16-bit operands are IEEE half instead of bf16
+  int64_t w_plane_bytes;  // split filter (MODE 1 / 2): distance from the hi plane to the lo plane
   int M;
   int slabs;  // Cin / (128 / ESZ): 128-byte K blocks per pixel
   uint32_t x_bstride8;  // input batch stride in 16-byte units
@@ -157,18 +163,28 @@ struct UmmaParams {
 
 constexpr int kUmmaThreads = 160;  // warps 0-3: producers + epilogue; warp 4: TMEM owner + MMA issuer
 
-template <int NT, int STAGES>
+// MODE 0: one A tile, one B tile per stage (plain operands).
+// MODE 1 ("w2"): 16-bit activations, filter split into two IEEE-half planes (hi = rn(w), lo = rn(w - hi)); stage = [A][Bhi][Blo],
+//         two MMAs per K step (A.Bhi + A.Blo): the filter rounding error disappears, the activation's stays.
+// MODE 2 ("x3"): fp32 activations split IN the producer (hi = rn_f16(a), lo = rn_f16(a - hi)) + the split filter; stage =
+//         [Ahi][Alo][Bhi][Blo], three MMAs per K step (Ahi.Bhi + Alo.Bhi + Ahi.Blo): fp32-class result (the dropped
+//         Alo.Blo term is 2^-22 relative) on the f16 tensor path.
+template <int NT, int STAGES, int MODE = 0>
 struct UmmaSmem {
-  static constexpr int kABytes = 128 * 128;
-  static constexpr int kBBytes = NT * 128;
+  static constexpr int kATile = 128 * 128;
+  static constexpr int kBTile = NT * 128;
+  static constexpr int kABytes = (MODE == 2 ? 2 : 1) * kATile;
+  static constexpr int kBBytes = (MODE == 0 ? 1 : 2) * kBTile;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarOffset + 256 /*barriers + tmem ptr*/ + 1024 /*alignment slack*/;
 };
 
-template <int NT, int STAGES, int ESZ>
+template <int NT, int STAGES, int ESZ, int MODE>
 __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParams p) {
-  using L = UmmaSmem<NT, STAGES>;
+  using L = UmmaSmem<NT, STAGES, MODE>;
+  static_assert(MODE == 0 || ESZ == 2, "split modes use 16-bit operands");
+  constexpr int XSZ = MODE == 2 ? 4 : ESZ;  // bytes per element of the activation in global memory
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must be 1024-byte aligned
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -192,7 +208,8 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), 128);
+      // MODE 2: 128 asynchronous arrivals for the filter copies + 128 plain arrivals after the converted A stores
+      ptx::mbar_init(full_bar(s), MODE == 2 ? 256 : 128);
       ptx::mbar_init(empty_bar(s), 1);
     }
     ptx::mbar_init(accum_bar, 1);
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
     const int chunk = tid & 7;
     const int rbase = tid >> 3;
     const uint32_t sw_chunk = (uint32_t)((chunk ^ (rbase & 7)) << 4);
-    const uint32_t cin8 = (uint32_t)((g.Cin * ESZ) >> 4);  // 16-byte chunks per pixel
+    const uint32_t cin8 = (uint32_t)((g.Cin * XSZ) >> 4);  // 16-byte chunks per pixel
     // my row for the address computation: rbase + 16 * chunk
     int my_yb, my_xb;
     uint32_t my_base;
@@ -281,6 +298,46 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
         if (issued >= STAGES) ptx::mbar_wait(empty_bar(s), ((issued / STAGES) & 1) ^ 1);
         const uint32_t a_dst = smem_base + s * L::kStageBytes;
         const uint32_t b_dst = a_dst + L::kABytes;
+        const int4* wsrc = reinterpret_cast<const int4*>(reinterpret_cast<const uint8_t*>(p.w) + (int64_t)issued * w_kb_stride + (int64_t)n0 * 128);
+        if (MODE == 2) {
+          // filter planes first (asynchronous), then the activation through registers: 8 rows x 32 bytes of fp32 per thread,
+          // all sixteen loads in flight before the first conversion
+          for (int q = tid; q < b_chunks; q += 128) {
+            ptx::cp_async16(b_dst + (uint32_t)q * 16u, wsrc + q, 16u);
+            ptx::cp_async16(b_dst + L::kBTile + (uint32_t)q * 16u,
+                            reinterpret_cast<const int4*>(reinterpret_cast<const uint8_t*>(wsrc) + p.w_plane_bytes) + q, 16u);
+          }
+          ptx::cp_async_arrive_noinc(full_bar(s));
+          const int4* xsrc = reinterpret_cast<const int4*>(p.x) + slab * 16 + chunk * 2;
+          int4 raw[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = soff[i] != 0xFFFFFFFFu;
+            const int4* src = ok ? xsrc + soff[i] : reinterpret_cast<const int4*>(p.x);
+            raw[2 * i] = ptx::ldg_nc16(src);  // volatile asm: keeps the sixteen loads ahead of the first conversion
+            raw[2 * i + 1] = ptx::ldg_nc16(src + 1);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = soff[i] != 0xFFFFFFFFu;
+            const float v[8] = {__int_as_float(raw[2 * i].x), __int_as_float(raw[2 * i].y), __int_as_float(raw[2 * i].z),
+                                __int_as_float(raw[2 * i].w), __int_as_float(raw[2 * i + 1].x), __int_as_float(raw[2 * i + 1].y),
+                                __int_as_float(raw[2 * i + 1].z), __int_as_float(raw[2 * i + 1].w)};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              hi[j] = ok ? pack2_h16<true>(v[2 * j], v[2 * j + 1]) : 0u;
+              const float2 back = unpack2_h16<true>(hi[j]);
+              lo[j] = ok ? pack2_h16<true>(v[2 * j] - back.x, v[2 * j + 1] - back.y) : 0u;
+            }
+            const uint32_t dst = a_dst + (uint32_t)((rbase + 16 * i) * 128) + sw_chunk;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + L::kATile), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+          }
+          ptx::fence_proxy_async();  // generic-proxy stores -> visible to tcgen05.mma's async-proxy reads
+          ptx::mbar_arrive(full_bar(s));
+          continue;
+        }
         const int4* xsrc = reinterpret_cast<const int4*>(p.x) + slab * 8 + chunk;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -288,8 +345,11 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
           const void* src = ok ? (const void*)(xsrc + soff[i]) : (const void*)p.x;
           ptx::cp_async16(a_dst + (uint32_t)((rbase + 16 * i) * 128) + sw_chunk, src, ok ? 16u : 0u);
         }
-        const int4* wsrc = reinterpret_cast<const int4*>(reinterpret_cast<const uint8_t*>(p.w) + (int64_t)issued * w_kb_stride + (int64_t)n0 * 128);
         for (int q = tid; q < b_chunks; q += 128) ptx::cp_async16(b_dst + (uint32_t)q * 16u, wsrc + q, 16u);
+        if (MODE == 1) {
+          const int4* wlo = reinterpret_cast<const int4*>(reinterpret_cast<const uint8_t*>(wsrc) + p.w_plane_bytes);
+          for (int q = tid; q < b_chunks; q += 128) ptx::cp_async16(b_dst + L::kBTile + (uint32_t)q * 16u, wlo + q, 16u);
+        }
         // completion is signalled asynchronously: no thread ever blocks on its own copies, so up to STAGES K blocks
         // of loads are in flight per thread
         ptx::cp_async_arrive_noinc(full_bar(s));
@@ -395,6 +455,10 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
             ptx::umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           else
             ptx::umma_tf32(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          if (MODE == 2)  // Alo . Bhi
+            ptx::umma_bf16(tmem_acc, adesc + (uint64_t)(L::kATile >> 4) + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+          if (MODE != 0)  // Ahi . Blo
+            ptx::umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(L::kBTile >> 4) + (uint64_t)(2 * k), idesc, 1u);
         }
         ptx::umma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
       }
@@ -410,10 +474,10 @@ __global__ void __launch_bounds__(kUmmaThreads) conv_umma_kernel(const UmmaParam
   }
 }
 
-template <int NT, int STAGES, int ESZ>
+template <int NT, int STAGES, int ESZ, int MODE = 0>
 static int launch_umma(const UmmaParams& p, int Cout, cudaStream_t stream) {
-  using L = UmmaSmem<NT, STAGES>;
-  auto kern = conv_umma_kernel<NT, STAGES, ESZ>;
+  using L = UmmaSmem<NT, STAGES, MODE>;
+  auto kern = conv_umma_kernel<NT, STAGES, ESZ, MODE>;
   static bool once = false;  // per template instance (one process per GPU; never repeated under graph capture)
   if (!once) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -430,11 +494,15 @@ static int launch_umma(const UmmaParams& p, int Cout, cudaStream_t stream) {
 
 int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
   const bool tf32 = d->w_format == LNS_W_UMMA_TF32;
+  const bool split = d->w_format == LNS_W_UMMA_F16X2;
+  const bool x3 = split && d->x_dtype == LNS_F32;  // fp32 activations split in the producer: 3 MMAs per K step
   const int esz = tf32 ? 4 : 2, kblk = 128 / esz;  // channels per 128-byte K block
-  const bool f16 = d->w_format == LNS_W_UMMA_F16;
-  LNS_REQUIRE(d->w_format == LNS_W_UMMA_BF16 || f16 || tf32, "lns_conv2d(umma): weights must be packed as LNS_W_UMMA_BF16 / _F16 / _TF32");
-  LNS_REQUIRE(d->x_layout == LNS_NHWC && (tf32 ? !is_h16_host(d->x_dtype) : d->x_dtype == (f16 ? LNS_F16 : LNS_BF16)),
-              "lns_conv2d(umma): input must be NHWC bf16 / f16 (matching the filter format) or NHWC fp32/tf32 (tf32 filter)");
+  const int xsz = (tf32 || x3) ? 4 : 2;            // bytes per activation element in global memory
+  const bool f16 = d->w_format == LNS_W_UMMA_F16 || split;
+  LNS_REQUIRE(d->w_format == LNS_W_UMMA_BF16 || f16 || tf32, "lns_conv2d(umma): weights must be packed as LNS_W_UMMA_BF16 / _F16 / _F16X2 / _TF32");
+  LNS_REQUIRE(d->x_layout == LNS_NHWC && (tf32 ? !is_h16_host(d->x_dtype) : (x3 || d->x_dtype == (f16 ? LNS_F16 : LNS_BF16))),
+              "lns_conv2d(umma): input must be NHWC bf16 / f16 (matching the filter format), NHWC fp32/tf32 (tf32 filter) or NHWC "
+              "f16 / fp32 (split f16x2 filter)");
   LNS_REQUIRE(d->y_layout == LNS_NHWC, "lns_conv2d(umma): output must be NHWC");
   LNS_REQUIRE(d->Cin % kblk == 0 && d->Cout % 16 == 0, "lns_conv2d(umma): needs Cin%%%d==0 and Cout%%16==0 (got %d,%d)", kblk,
               d->Cin, d->Cout);
@@ -451,7 +519,7 @@ int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
   int64_t M = (int64_t)d->B * d->Hout * d->Wout;
   LNS_REQUIRE(M < (1ll << 31), "lns_conv2d(umma): too many output pixels");
   int64_t x_elems = (int64_t)(d->B - 1) * d->x_bstride + (int64_t)d->Hin * d->Win * d->Cin;
-  LNS_REQUIRE(((x_elems * esz) >> 4) < 0xFFFFFFFFll, "lns_conv2d(umma): input too large for 32-bit chunk offsets");
+  LNS_REQUIRE(((x_elems * xsz) >> 4) < 0xFFFFFFFFll, "lns_conv2d(umma): input too large for 32-bit chunk offsets");
 
   UmmaParams p;
   p.g = make_geom(d);
@@ -465,7 +533,8 @@ int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
   p.x_f16 = f16 ? 1 : 0;
   p.M = (int)M;
   p.slabs = d->Cin / kblk;
-  p.x_bstride8 = (uint32_t)((d->x_bstride * esz) >> 4);
+  p.x_bstride8 = (uint32_t)((d->x_bstride * xsz) >> 4);
+  p.w_plane_bytes = (int64_t)d->Cout * d->Cin * d->KH * d->KW * 2;
   p.resize = (d->Hv == d->Hin && d->Wv == d->Win) ? 0 : ((d->Hv == 2 * d->Hin && d->Wv == 2 * d->Win) ? 1 : 2);
   p.inv_wout = 1.0f / (float)d->Wout; p.inv_hout = 1.0f / (float)d->Hout;
   p.inv_hv = 1.0f / (float)d->Hv; p.inv_wv = 1.0f / (float)d->Wv;
@@ -476,6 +545,14 @@ int conv2d_umma(const LnsConvDesc* d, cudaStream_t stream) {
               "lns_conv2d(umma): padding/dilation larger than the grid is not supported");
   LNS_REQUIRE((int64_t)d->Hv * d->Hin < (1 << 21) && (int64_t)d->Wv * d->Win < (1 << 21) && d->Hout < (1 << 20) &&
                   d->Wout < (1 << 20), "lns_conv2d(umma): spatial size too large");
+  if (x3) {  // stage = 2 A tiles + 2 B tiles
+    if (d->Cout <= 64) return launch_umma<64, 2, 2, 2>(p, d->Cout, stream);   // 96 KB: two CTAs per SM
+    return launch_umma<128, 3, 2, 2>(p, d->Cout, stream);                     // 192 KB: one CTA per SM
+  }
+  if (split) {  // stage = A tile + 2 B tiles, twice the MMA work of a plain stage
+    if (d->Cout <= 64) return launch_umma<64, 3, 2, 1>(p, d->Cout, stream);   // 96 KB
+    return launch_umma<128, 2, 2, 1>(p, d->Cout, stream);                     // 96 KB
+  }
   if (tf32) {
     if (d->Cout <= 64) return launch_umma<64, 4, 4>(p, d->Cout, stream);
     if (d->Cout <= 128) return launch_umma<128, 3, 4>(p, d->Cout, stream);

@@ -3,6 +3,7 @@ per library entry point.  PyTorch is used for device memory and streams only; al
 liblns_b200.so.  Nothing here falls back to torch ops: a CPU tensor or a missing library raises."""
 import ctypes
 import math
+import os
 import threading
 from contextlib import contextmanager
 
@@ -16,8 +17,8 @@ TF32 = "tf32"  # storage sentinel: fp32 words holding TF32-rounded values (LNS_T
 NHWC, NCHW = 0, 1
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAD_ZEROS, PAD_CIRCULAR = 0, 1
-W_SIMT_F32, W_UMMA_BF16, W_UMMA_TF32, W_UMMA_F16 = 0, 1, 2, 3
-ENGINE_SIMT, ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT = 0, 1, 2, 3
+W_SIMT_F32, W_UMMA_BF16, W_UMMA_TF32, W_UMMA_F16, W_UMMA_F16X2 = 0, 1, 2, 3, 4
+ENGINE_SIMT, ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT, ENGINE_COARSE = 0, 1, 2, 3, 4
 
 _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 H16_DTYPES = (torch.bfloat16, torch.float16)  # the 16-bit storage types of the tensor-core paths
@@ -39,6 +40,13 @@ class _State(threading.local):
         self.precision = "bf16"
         self.launches = 0
         self.timeline = None  # list of (label, start_event, end_event) when profiling (tools/timeline.py)
+        self.hi_px = 0        # 'fp16s': convs touching a grid of <= hi_px pixels run with split operands on fp32 storage
+        self.hi_exact = int(os.environ.get("LNS_HI_EXACT", "0"))  # experiment: those convs on the fp32 CUDA-core engine instead
+        self.wsplit = False   # 'fp16s': split filters (2 MMAs per K step) on the tcgen05 convs outside the hi region too
+        self.wsplit_policy = os.environ.get("LNS_WSPLIT", "enc")  # where ops.wsplit_region turns that on: enc | all | none
+        self.hi_scale = float(os.environ.get("LNS_HI_SCALE", "1"))  # experiment: 4 = one more resolution level in the hi region
+        self.hi_wsplit = os.environ.get("LNS_HI_WSPLIT", "0") != "0"  # hi layers also split the filter (3 MMAs instead of 2)
+        self.coarse = os.environ.get("LNS_COARSE", "1") != "0"        # use the block-halo engine (conv_coarse.cu) where it applies
 
 
 def _mark(label):
@@ -71,11 +79,16 @@ def set_precision(p):
             (tcgen05.mma.kind::f16 takes either format) with an 11-bit significand: TF32-class rounding error, i.e. the
             16-bit path that meets the 2e-3 per-step bound.  Conversions saturate at +-65504 (the residual stream of a
             trained model must stay inside the half range; norm statistics, softmax and latents are fp32 as in 'bf16').
+    'fp16s': the fp16 path with SPLIT operands where the rounding error is made (tools/precision_study.py): filters as
+            hi + lo IEEE-half pairs everywhere (two MMAs per K step, no filter rounding), and the coarse stages of the
+            autoencoder (ops.hi_region: grids of at most 4x the latent's pixels) on fp32 storage with the activation split
+            into hi + lo halves inside the conv's producer (three MMAs: fp32-class layers on the f16 tensor path).  This is
+            the 16-bit tensor-core mode that meets <= 2e-3 per stage on all four configurations.
     'tf32': fp32 storage rounded to TF32 at every write, tcgen05.mma.kind::tf32 GEMMs with fp32 accumulation (the
             tensor-core path that meets the 2e-3 per-step bound; half the MMA rate and twice the bytes of bf16).
     'fp32': fp32 activations and CUDA-core fp32 FMA GEMMs (the validation path, <=1e-5 vs the reference)."""
-    if p not in ("bf16", "fp16", "fp32", "tf32"):
-        raise ValueError("precision must be 'bf16', 'fp16', 'tf32' or 'fp32'")
+    if p not in ("bf16", "fp16", "fp16s", "fp32", "tf32"):
+        raise ValueError("precision must be 'bf16', 'fp16', 'fp16s', 'tf32' or 'fp32'")
     _state.precision = p
 
 
@@ -92,14 +105,44 @@ def precision(p):
 def act_dtype():
     if _state.precision == "bf16":
         return torch.bfloat16
-    if _state.precision == "fp16":
+    if _state.precision in ("fp16", "fp16s"):
         return torch.float16
     return TF32 if _state.precision == "tf32" else torch.float32
 
 
 def fast16():
-    """True on the 16-bit tensor-core paths ('bf16' / 'fp16'), which share every kernel and fusion decision."""
-    return _state.precision in ("bf16", "fp16")
+    """True on the 16-bit tensor-core paths ('bf16' / 'fp16' / 'fp16s'), which share every kernel and fusion decision."""
+    return _state.precision in ("bf16", "fp16", "fp16s")
+
+
+def split16():
+    """True in the split-operand mode 'fp16s'."""
+    return _state.precision == "fp16s"
+
+
+@contextmanager
+def wsplit_region(kind):
+    """Inside: ('fp16s' only) every tcgen05 conv uses the split filter.  kind = 'enc' (the encoder: it runs once per rollout and
+    its error is carried by the fine levels, where only the filter split is affordable) or 'dec'."""
+    old = _state.wsplit
+    pol = _state.wsplit_policy
+    _state.wsplit = split16() and (pol == "all" or (pol == "enc" and kind == "enc"))
+    try:
+        yield
+    finally:
+        _state.wsplit = old
+
+
+@contextmanager
+def hi_region(px):
+    """Inside: ('fp16s' only) every conv whose input or output grid has at most `px` pixels is a high-precision layer --
+    fp32 activation storage, operands split into hi + lo halves (lns_conv2d with LNS_W_UMMA_F16X2)."""
+    old = _state.hi_px
+    _state.hi_px = int(px * _state.hi_scale) if split16() else 0
+    try:
+        yield
+    finally:
+        _state.hi_px = old
 
 
 def launch_count():
@@ -323,8 +366,12 @@ def _umma_ok(x, Cin, Cout, y_layout):
 
 def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, PAD_ZEROS), virt=None, use_bias=True,
            sample_bias=None, pro=None, act=ACT_NONE, pre_add=None, residual=None, out=None, out_dtype=None,
-           out_layout=NHWC, engine=None):
+           out_layout=NHWC, engine=None, split=None):
     """y = act(conv(pro(resize(x))) + bias + sample_bias + pre_add) + residual.   (lns_conv2d)
+
+    split=True (with engine=ENGINE_UMMA | ENGINE_HALO): use the split filter format LNS_W_UMMA_F16X2 -- f16 activations ->
+    two MMAs per K step, fp32 activations (gather engine only) -> split in the producer, three MMAs.  The 'fp16s' precision
+    mode chooses this per layer by itself.
 
     pad = (top, bottom, left, right) on the virtual input; pad_mode = (mode_h, mode_w); virt = (Hv, Wv) nearest-resize
     target (None: no resize); pro = (scale[B,C], shift[B,C], act) per-(sample,channel) affine applied to x first."""
@@ -339,6 +386,34 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
             and Cin <= 512 and stride == 1 and virt is None and act == ACT_NONE and pre_add is None and residual is None
             and sample_bias is None and (out is None or out.t.dtype == torch.float32) and x.B <= 65535):
         return _pointwise_proj(x, filt, use_bias, pro, out)
+    # 'fp16s': high-precision layers (ops.hi_region) keep fp32 storage and run with split operands
+    hi = engine is None and split16() and _state.hi_px > 0 and min(x.H * x.W, Hout * Wout) <= _state.hi_px
+    if hi and x.t.dtype == torch.float16 and Hout * Wout > _state.hi_px and not isinstance(pro, LazyNorm):
+        hi = False  # a 16-bit activation leaving the region: nothing left to preserve, the ordinary engines are faster
+    split_fmt = bool(split) and engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_COARSE)
+    if hi:
+        if out is None and out_dtype is None and out_layout == NHWC and Hout * Wout <= _state.hi_px:
+            out_dtype = torch.float32
+        if isinstance(pro, LazyNorm) and x.layout == NHWC:
+            if pro.x is not x:
+                raise LnsError("conv2d: the pending normalisation belongs to a different activation")
+            x = pro.materialize(out_dtype=torch.float32)  # the normalised activation is not rounded to 16 bits
+            pro = None
+        elif pro is not None and x.layout == NHWC:
+            x = affine_act(x, pro[0], pro[1], pro[2], out_dtype=torch.float32)
+            pro = None
+        coarse_ok = (KH == 3 and KW == 3 and stride == 1 and Cin in (64, 128) and Cout in (64, 128) and 1 <= dil <= 3
+                     and pt == pb == pl == pr == dil and dil <= min(Hv, Wv) and sample_bias is None and pre_add is None
+                     and pro is None and _state.coarse)
+        if (x.layout == NHWC and out_layout == NHWC and Cin % 64 == 0 and Cout % 16 == 0 and not x.tf32 and not _state.hi_exact
+                and ((x.t.dtype == torch.float32 and x.bstride % 4 == 0) or (x.t.dtype == torch.float16 and x.bstride % 8 == 0))):
+            if coarse_ok:
+                # block-halo engine: the fp32 activation is read once per 8x8 block and split into hi + lo halo planes
+                engine, split_fmt = ENGINE_COARSE, _state.hi_wsplit
+            else:
+                engine, split_fmt = ENGINE_UMMA, True   # gather engine: fp32 input 3 MMAs (x3), f16 input 2 MMAs (w2)
+        else:
+            engine = ENGINE_SIMT                        # tiny-channel layers: exact CUDA-core path
     if engine is None:
         engine = ENGINE_UMMA if _umma_ok(x, Cin, Cout, out_layout) else ENGINE_SIMT
         if (engine == ENGINE_UMMA and x.t.dtype in H16_DTYPES and KH == 3 and KW == 3 and stride == 1 and Cin == 64
@@ -350,15 +425,18 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
                 and tuple(pad_mode) == (PAD_CIRCULAR, PAD_CIRCULAR) and sample_bias is None and pre_add is None
                 and x.B >= 4):
             engine = ENGINE_LATENT  # the propagator's latent grid: resident halos of 4 samples, streamed filter
+        if split16() and _state.wsplit and x.t.dtype == torch.float16 and engine in (ENGINE_UMMA, ENGINE_HALO):
+            # split filter, two MMAs per K step (the halo engine keeps both planes resident only for Cout = 64, dilation 1)
+            split_fmt = engine == ENGINE_UMMA or (Cout == 64 and dil == 1)
     if isinstance(pro, LazyNorm):
         if pro.x is not x:
             raise LnsError("conv2d: the pending normalisation belongs to a different activation")
-        if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT):
+        if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT, ENGINE_COARSE):
             x = pro.materialize()  # these engines gather with cp.async (no transform in flight)
             pro = None
         else:
             pro = pro.as_tuple()
-    if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT) and pro is not None:
+    if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT, ENGINE_COARSE) and pro is not None:
         x = affine_act(x, pro[0], pro[1], pro[2])
         pro = None
     if out is None:
@@ -381,8 +459,12 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     d.KH, d.KW, d.stride, d.dil, d.pad_t, d.pad_l = KH, KW, stride, dil, pt, pl
     d.pad_mode_h, d.pad_mode_w = pad_mode
     fmt = W_SIMT_F32
-    if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT):
+    if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT, ENGINE_COARSE):
         fmt = {torch.bfloat16: W_UMMA_BF16, torch.float16: W_UMMA_F16}.get(x.t.dtype, W_UMMA_TF32)
+        if engine == ENGINE_COARSE and x.t.dtype == torch.float32:  # operands of the in-kernel hi/lo split
+            fmt = W_UMMA_BF16 if _state.precision == "bf16" else W_UMMA_F16
+        if split_fmt:
+            fmt = W_UMMA_F16X2
     wbuf = filt.get(fmt)
     d.w, d.w_format, d.engine = wbuf.data_ptr(), fmt, engine
     bias = filt.bias() if use_bias else None
@@ -404,7 +486,8 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     tok = _mark(f"conv e{engine} {KH}x{KW} s{stride} d{dil} {Cin}->{Cout} @{Hout}x{Wout}"
                 f"{' up' if virt is not None else ''}{' pro' if pro is not None else ''}"
                 f"{' act' if act else ''}{' res' if residual is not None else ''} "
-                f"{'h16' if x.t.dtype in H16_DTYPES else 'f32'}->{'h16' if out.t.dtype in H16_DTYPES else 'f32'}")
+                f"{'h16' if x.t.dtype in H16_DTYPES else 'f32'}->{'h16' if out.t.dtype in H16_DTYPES else 'f32'}"
+                f"{' split' if split_fmt else ''}")
     rc = _C.lib().lns_conv2d(ctypes.byref(d), _stream())
     check(rc, "lns_conv2d")
     _done(tok)
@@ -523,6 +606,14 @@ def affine_act(x, scale, shift, act=ACT_NONE, out_dtype=None):
     _done(tok)
     _state.launches += 1
     return out
+
+
+def as_h16(x):
+    """On the 16-bit paths: an fp32-stored activation (a high-precision stage's output) as a 16-bit copy, for the blocks
+    whose fused kernels take 16-bit input; anything else is returned as it is."""
+    if fast16() and x.layout == NHWC and x.t.dtype == torch.float32 and not x.tf32:
+        return affine_act(x, None, None, ACT_NONE, out_dtype=act_dtype())
+    return x
 
 
 def layernorm(x, gamma, beta, eps, pe=None, out_dtype=None):

@@ -196,5 +196,21 @@ def _flush(x, pro):
 
 
 def latent_dtype(channels):
-    """Storage type of latent-sized tensors: fp32 unless they can feed the tensor-core engine directly (C % 64 == 0)."""
+    """Storage type of latent-sized tensors: fp32 unless they can feed the tensor-core engine directly (C % 64 == 0);
+    always fp32 in the split-operand mode, whose coarse stages keep fp32 storage."""
+    if ops.split16():
+        return torch.float32
     return ops.act_dtype() if channels % 64 == 0 else torch.float32
+
+
+def decoder_hi_px(z):
+    """'fp16s': the decoder's high-precision region = its two coarsest levels (the latent grid and the first x2 level), where
+    tools/precision_study.py / tools/gpu_precision_attrib.py locate 70-80 % of the 16-bit error of a decode."""
+    return 4 * z.H * z.W
+
+
+def encoder_hi_px(layers, x):
+    """Same region seen from the encoder: the grids after its last two down-sampling blocks."""
+    n = sum(1 for m in layers if type(m).__name__.startswith("DownSample"))
+    k = max(n - 1, 0)
+    return (x.H >> k) * (x.W >> k)

@@ -8,7 +8,7 @@ import torch.nn as nn
 
 from lns_b200 import ops
 
-from ._base import LnsModule, run_layers, conv_layer, latent_dtype
+from ._base import LnsModule, run_layers, conv_layer, latent_dtype, encoder_hi_px, decoder_hi_px
 from .basics import ResidualBlock, SABlock, DownSampleBlock, UpSampleBlock, GroupNorm, Swish, FourierBasicBlock
 from .factorized_attention import FABlock2D
 
@@ -108,12 +108,14 @@ class SimpleAutoencoder(LnsModule):
 
     # -- Act-level entry points used by lns_b200.rollout --
     def _encode(self, x_nchw_act, out=None):
-        h = self.encoder._fwd(x_nchw_act)
-        return conv_layer(h, self.quant_conv, out=out, out_dtype=torch.float32 if out is None else None)
+        with ops.hi_region(encoder_hi_px(self.encoder.model, x_nchw_act)), ops.wsplit_region("enc"):
+            h = self.encoder._fwd(x_nchw_act)
+            return conv_layer(h, self.quant_conv, out=out, out_dtype=torch.float32 if out is None else None)
 
     def _decode(self, z, out=None):
-        h = conv_layer(z, self.post_quant_conv, out_dtype=latent_dtype(z.C))
-        return self.decoder._fwd(h, out=out)
+        with ops.hi_region(decoder_hi_px(z)), ops.wsplit_region("dec"):
+            h = conv_layer(z, self.post_quant_conv, out_dtype=latent_dtype(z.C))
+            return self.decoder._fwd(h, out=out)
 
     # -- the reference's tensor API --
     def forward(self, x):

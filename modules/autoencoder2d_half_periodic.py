@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from lns_b200 import ops
 
-from ._base import LnsModule, run_layers, conv_layer, norm_affine, lazy_norm, latent_dtype
+from ._base import LnsModule, run_layers, conv_layer, norm_affine, lazy_norm, latent_dtype, encoder_hi_px, decoder_hi_px
 from .basics import GroupNorm, Swish, FourierBasicBlock, SABlock
 from .factorized_attention import FABlock2D
 
@@ -175,12 +175,14 @@ class SimpleAutoencoder(LnsModule):
         self.post_quant_conv = nn.Conv2d(args.latent_dim, args.latent_dim, 1)
 
     def _encode(self, x_nchw_act, out=None):
-        h = self.encoder._fwd(x_nchw_act)
-        return conv_layer(h, self.quant_conv, out=out, out_dtype=torch.float32 if out is None else None)
+        with ops.hi_region(encoder_hi_px(self.encoder.model, x_nchw_act)), ops.wsplit_region("enc"):
+            h = self.encoder._fwd(x_nchw_act)
+            return conv_layer(h, self.quant_conv, out=out, out_dtype=torch.float32 if out is None else None)
 
     def _decode(self, z, out=None):
-        h = conv_layer(z, self.post_quant_conv, out_dtype=latent_dtype(z.C))
-        return self.decoder._fwd(h, out=out)
+        with ops.hi_region(decoder_hi_px(z)), ops.wsplit_region("dec"):
+            h = conv_layer(z, self.post_quant_conv, out_dtype=latent_dtype(z.C))
+            return self.decoder._fwd(h, out=out)
 
     def forward(self, x):
         return self.decode(self.encode(x))

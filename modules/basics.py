@@ -154,6 +154,7 @@ class SABlock(LnsModule):
         return ent[1]
 
     def _fwd(self, x):
+        x = ops.as_h16(x)
         n = x.H * x.W
         pe = None
         if self.pe is not None:

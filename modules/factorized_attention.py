@@ -112,6 +112,7 @@ class FABlock2D(LnsModule):
             nn.Conv2d(dim_out, dim_out, 1, 1, 0, bias=False))
 
     def _fwd(self, u):
+        u = ops.as_h16(u)
         skip = u
         f32 = torch.float32
         inorm = self.to_out[0]

@@ -840,3 +840,135 @@ def test_pointwise_projection_step_grouped_output():
         w3 = Holder(torch.randn(8, C, 1, 1, generator=g), torch.zeros(8))
         bad = ops.Act(torch.zeros(S * Bt * 8 * H * W, device=DEV), S * Bt, H, W, 8, layout=ops.NCHW, group=Bt, gstride=1)
         ops.conv2d(act_from(x, torch.bfloat16), ops.PackedFilter.of(w3.weight, w3.bias), out=bad, out_layout=ops.NCHW)
+
+
+# ---- split operands (LNS_W_UMMA_F16X2): the building blocks of the 'fp16s' precision mode ------------------------------------
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_umma_split_x3(case):
+    """gather engine, fp32 activations split into f16 hi + lo in the producer, split filter, three MMAs per K step:
+    fp32-class result vs an fp64 conv of the UNROUNDED operands"""
+    ops = ops_mod()
+    B, Cin, Cout, H, W, k, stride, dil, pad, modes, virt = case
+    x, w, b = _conv_case(case, seed=5)
+    ref = ref_conv(x, w, b, stride, dil, pad, modes, virt)
+    h = Holder(w, b)
+    res = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6))
+    with ops.precision("fp16"):
+        y = ops.conv2d(act_from(x, torch.float32), ops.PackedFilter.of(h.weight, h.bias), stride=stride, dil=dil, pad=pad,
+                       pad_mode=modes, virt=virt, engine=ops.ENGINE_UMMA, split=True, out_dtype=torch.float32,
+                       act=ops.ACT_GELU, residual=act_from(res, torch.float32))
+    torch.cuda.synchronize()
+    assert y.t.dtype == torch.float32
+    assert relerr(act_to_nchw(y), F.gelu(ref) + res.double()) < 3e-6
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_umma_split_w2(case):
+    """gather engine, f16 activations, split filter, two MMAs per K step: no filter rounding -- vs an fp64 conv of the
+    f16-rounded activation and the UNROUNDED filter"""
+    ops = ops_mod()
+    B, Cin, Cout, H, W, k, stride, dil, pad, modes, virt = case
+    x, w, b = _conv_case(case, seed=7)
+    ref = ref_conv(x.half().float(), w, b, stride, dil, pad, modes, virt)
+    h = Holder(w, b)
+    with ops.precision("fp16"):
+        y = ops.conv2d(act_from(x, torch.float16), ops.PackedFilter.of(h.weight, h.bias), stride=stride, dil=dil, pad=pad,
+                       pad_mode=modes, virt=virt, engine=ops.ENGINE_UMMA, split=True, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert relerr(act_to_nchw(y), ref) < 3e-6
+
+
+@pytest.mark.parametrize("case", [c for c in HALO_CASES if c[1] == 64 and c[4] == 1])
+def test_conv_halo_split_w2(case):
+    """halo engine with BOTH filter planes resident (Cout = 64) and two MMAs per (tap, k)"""
+    ops = ops_mod()
+    B, Cout, H, W, dil, modes, virt = case
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(B, 64, H, W, generator=g)
+    w = torch.randn(Cout, 64, 3, 3, generator=g) / 24.0
+    b = torch.randn(Cout, generator=g) * 0.1
+    Ho, Wo = virt if virt is not None else (H, W)
+    res = torch.randn(B, Cout, Ho, Wo, generator=g)
+    ref = ref_conv(x.half().float(), w, b, 1, dil, (dil,) * 4, modes, virt)
+    ref = F.gelu(ref) + res.half().double()
+    h = Holder(w, b)
+    with ops.precision("fp16"):
+        y = ops.conv2d(act_from(x, torch.float16), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4,
+                       pad_mode=modes, virt=virt, act=ops.ACT_GELU, residual=act_from(res, torch.float16),
+                       engine=ops.ENGINE_HALO, split=True, out_dtype=torch.float32)
+        y16 = ops.conv2d(act_from(x, torch.float16), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4,
+                         pad_mode=modes, virt=virt, act=ops.ACT_GELU, residual=act_from(res, torch.float16),
+                         engine=ops.ENGINE_HALO, split=True)
+    torch.cuda.synchronize()
+    assert relerr(act_to_nchw(y), ref) < 5e-6
+    assert torch.equal(act_to_nchw(y16), act_to_nchw(y).half().float())
+
+
+# ---- block-halo engine for the coarse levels (LNS_ENGINE_COARSE, csrc/conv_coarse.cu) ---------------------------------------
+COARSE_CASES = [
+    # B, Cin, Cout, H, W, dil, modes(h,w), virt
+    (5, 128, 128, 8, 8, 1, (1, 1), None),        # NS2d latent grid, odd block count (ragged last super tile)
+    (4, 128, 128, 8, 8, 2, (1, 1), None),        # dilation 2, circular
+    (3, 128, 128, 7, 15, 2, (0, 0), None),       # two-phase latent grid: ragged blocks, zeros
+    (2, 128, 128, 12, 24, 3, (0, 1), None),      # shallow-water latent grid: half periodic, dilation 3
+    (3, 64, 64, 16, 16, 1, (1, 1), None),
+    (2, 128, 64, 16, 16, 1, (1, 1), None),
+    (2, 64, 128, 24, 48, 1, (0, 1), None),
+    (3, 128, 128, 8, 8, 1, (1, 1), (16, 16)),    # nearest x2 folded into the halo fill
+    (2, 64, 64, 14, 30, 1, (0, 0), (28, 60)),
+    (2, 64, 64, 28, 60, 1, (0, 0), (61, 121)),   # general nearest to an odd size
+    (300, 128, 128, 8, 8, 1, (1, 1), None),      # more super tiles than SMs: persistent loop, ring wrap-around
+]
+
+
+def _coarse_case(case, seed):
+    B, Cin, Cout, H, W, dil, modes, virt = case
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)
+    b = torch.randn(Cout, generator=g) * 0.1
+    Ho, Wo = virt if virt is not None else (H, W)
+    res = torch.randn(B, Cout, Ho, Wo, generator=g)
+    return x, w, b, res
+
+
+@pytest.mark.parametrize("case", COARSE_CASES)
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_conv_coarse_16bit(case, prec):
+    """16-bit activations (one halo plane per slab) vs an fp64 conv of the same rounded operands; full epilogue"""
+    ops = ops_mod()
+    B, Cin, Cout, H, W, dil, modes, virt = case
+    dt = torch.float16 if prec == "fp16" else torch.bfloat16
+    x, w, b, res = _coarse_case(case, 41)
+    ref = ref_conv(x.to(dt).float(), w.to(dt).float(), b, 1, dil, (dil,) * 4, modes, virt)
+    ref = F.gelu(ref) + res.to(dt).double()
+    h = Holder(w, b)
+    with ops.precision(prec):
+        y = ops.conv2d(act_from(x, dt), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4, pad_mode=modes, virt=virt,
+                       act=ops.ACT_GELU, residual=act_from(res, dt), engine=ops.ENGINE_COARSE, out_dtype=torch.float32)
+        y16 = ops.conv2d(act_from(x, dt), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4, pad_mode=modes, virt=virt,
+                         act=ops.ACT_GELU, residual=act_from(res, dt), engine=ops.ENGINE_COARSE)
+    torch.cuda.synchronize()
+    assert tuple(act_to_nchw(y).shape) == tuple(ref.shape)
+    assert relerr(act_to_nchw(y), ref) < 5e-6
+    assert y16.t.dtype == dt
+    assert torch.equal(act_to_nchw(y16), act_to_nchw(y).to(dt).float())
+
+
+@pytest.mark.parametrize("case", COARSE_CASES)
+@pytest.mark.parametrize("wsplit", [False, True])
+def test_conv_coarse_fp32_split(case, wsplit):
+    """fp32 activations split into f16 hi + lo halo planes in the producer.  Plain filter: no activation rounding (vs fp64 conv of
+    the exact activation and the f16-rounded filter); split filter: fp32-class result vs the exact conv"""
+    ops = ops_mod()
+    B, Cin, Cout, H, W, dil, modes, virt = case
+    x, w, b, res = _coarse_case(case, 43)
+    ref = ref_conv(x, w if wsplit else w.half().float(), b, 1, dil, (dil,) * 4, modes, virt)
+    ref = F.gelu(ref) + res.double()
+    h = Holder(w, b)
+    with ops.precision("fp16"):
+        y = ops.conv2d(act_from(x, torch.float32), ops.PackedFilter.of(h.weight, h.bias), dil=dil, pad=(dil,) * 4, pad_mode=modes,
+                       virt=virt, act=ops.ACT_GELU, residual=act_from(res, torch.float32), engine=ops.ENGINE_COARSE, split=wsplit,
+                       out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert relerr(act_to_nchw(y), ref) < 3e-6

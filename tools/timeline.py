@@ -28,7 +28,7 @@ model = model.to("cuda:0")
 x, p = O.make_inputs(cfg, B, seed=0)
 x = x.to("cuda:0")
 p = p.to("cuda:0") if p is not None else None
-ro = Rollout(model, batch=B, steps=R, to_x=True, precision="bf16", use_graph=False)
+ro = Rollout(model, batch=B, steps=R, to_x=True, precision=os.environ.get("LNS_TL_PREC", "bf16"), use_graph=False)
 with torch.no_grad():
     ro.build()
     torch.cuda.synchronize()
