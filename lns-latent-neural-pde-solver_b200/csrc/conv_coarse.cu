@@ -16,7 +16,7 @@
 // SBO = HWd*128 B covers both (accumulator row m = (y = m>>4, slot = (m>>3)&1, x = m&7)).  A CTA takes a super tile of 1 or 2 MMA
 // tiles (what shared memory allows), keeps their halo planes resident for all nine taps and streams the filter through a ring
 // in (tap, 64-channel slab) blocks that feed every plane of every tile.
-// Warp roles (320 threads): warps 0-3 halo producers, warp 4 MMA issuer + TMEM owner, warps 5-8 epilogue, warp 9 filter ring.
+// Warp roles (448 threads): warps 0-7 halo producers, warp 8 MMA issuer + TMEM owner, warps 9-12 epilogue, warp 13 filter ring.
 #include "common.cuh"
 
 namespace lns {
@@ -85,6 +85,21 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the descriptors given as (lo, hi) 32-bit halves
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -104,16 +119,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 }  // namespace cptx
 
 namespace {
-constexpr int kCoarseThreads = 320;
+constexpr int kCoarseThreads = 448;  // warps 0-7 halo producers, 8 MMA issuer + TMEM owner, 9-12 epilogue, 13 filter ring
+constexpr int kProducers = 256;
 constexpr int kRingMax = 6;  // filter-ring barrier slots
-
-__device__ __forceinline__ uint64_t cdesc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
-  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
-  d |= 1ull << 46;
-  d |= 2ull << 61;
-  return d;
-}
 
 struct CoarseParams {
   ConvGeom g;
@@ -182,20 +190,25 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
   const uint32_t bstage = p.bblock * (p.wsplit ? 2u : 1u);
   const uint32_t b_ring = halo_a + (uint32_t)(T * SL * AP) * (uint32_t)p.plane_bytes;
   const uint32_t bar_base = b_ring + (uint32_t)BS * bstage;
-  const uint32_t halo_full = bar_base, halo_empty = bar_base + 8;
-  auto b_full = [&](int s) { return bar_base + 16u + 8u * s; };
-  auto b_empty = [&](int s) { return bar_base + 16u + 8u * (kRingMax + s); };
-  auto acc_full = [&](int a) { return bar_base + 16u + 8u * (2 * kRingMax + a); };
-  auto acc_empty = [&](int a) { return bar_base + 16u + 8u * (2 * kRingMax + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 16u + 8u * (2 * kRingMax + 4);
+  // one (full, empty) barrier pair per 64-channel slab: the slabs of a super tile are filled and consumed one after the other,
+  // so the fill of slab 1 (or of the next super tile's slab 0) overlaps the MMAs that read the other slab's planes
+  auto halo_full = [&](int sl) { return bar_base + 8u * sl; };
+  auto halo_empty = [&](int sl) { return bar_base + 16u + 8u * sl; };
+  auto b_full = [&](int s) { return bar_base + 32u + 8u * s; };
+  auto b_empty = [&](int s) { return bar_base + 32u + 8u * (kRingMax + s); };
+  auto acc_full = [&](int a) { return bar_base + 32u + 8u * (2 * kRingMax + a); };
+  auto acc_empty = [&](int a) { return bar_base + 32u + 8u * (2 * kRingMax + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 32u + 8u * (2 * kRingMax + 4);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = g.dil, HWd = p.HWd;
   const int nkb = 9 * SL;
 
   if (tid == 0) {
-    cptx::mbar_init(halo_full, 128);
-    cptx::mbar_init(halo_empty, 1);
+    for (int sl = 0; sl < 2; ++sl) {
+      cptx::mbar_init(halo_full(sl), kProducers);
+      cptx::mbar_init(halo_empty(sl), 1);
+    }
     for (int s = 0; s < kRingMax; ++s) {
       cptx::mbar_init(b_full(s), 1);
       cptx::mbar_init(b_empty(s), 1);
@@ -206,7 +219,7 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
     }
     cptx::fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     cptx::tmem_alloc(tmem_slot, 512);
     cptx::tmem_relinquish();
   }
@@ -215,141 +228,159 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
   cptx::tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_gen;
 
-  if (warp < 4) {
-    // ============================== halo producers (128 threads) ==============================
-    const int cpp = 8 * SL;            // chunk tasks per pixel: 8 channels each (16 B of 16-bit data, 32 B of fp32)
-    const int c = tid % cpp, slab = c >> 3, chunk = c & 7;
-    const int pstep = 128 / cpp, p0 = tid / cpp;
+  if (warp < 8) {
+    // ============================== halo producers (256 threads) ==============================
+    // all 256 threads work on ONE slab at a time: 8 chunk tasks per pixel (8 channels each: 16 B of 16-bit data, 32 B of fp32),
+    // 32 pixels per pass
+    const int chunk = tid & 7;
+    constexpr int pstep = kProducers / 8;
+    const int p0 = tid >> 3;
     const int npx = HWd * HWd;
     const int esz = AMODE == 1 ? 4 : 2;
     int it = 0;
     for (int sup = blockIdx.x; sup < p.nsuper; sup += gridDim.x, ++it) {
-      if (it > 0) cptx::mbar_wait(halo_empty, (uint32_t)((it - 1) & 1));  // the MMAs of the previous super tile have read the halos
-      for (int ts = 0; ts < 2 * T; ++ts) {
-        const int gb = sup * 2 * T + ts;
-        if (gb >= p.nblocks) break;  // (rows of missing blocks are never stored)
-        const int b = gb / p.nb;
-        const int rem = gb - b * p.nb;
-        const int by = rem / p.nbx, bx = rem - by * p.nbx;
-        const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x) + ((int64_t)b * g.x_bstride + c * 8) * esz;
-        const uint32_t plane = halo_a + (uint32_t)((((ts >> 1) * SL + slab) * AP)) * (uint32_t)p.plane_bytes;
-        if (AMODE == 0) {
-          for (int q = p0; q < npx; q += pstep) {
-            const int hy = __float2int_rd(((float)q + 0.5f) * p.inv_hwd), hx = q - hy * HWd;
-            const int src = coarse_src(p, by, bx, hy, hx);
-            const int r = hy * (2 * HWd) + (ts & 1) * HWd + hx;
-            cptx::cp_async16(plane + (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4),
-                             xb + (int64_t)(src < 0 ? 0 : src) * g.Cin * 2, src < 0 ? 0u : 16u);
-          }
-        } else {
-          // fp32 -> (hi, lo) halves: four pixels (eight 16-byte loads) in flight per thread
-          for (int q0 = p0; q0 < npx; q0 += 4 * pstep) {
-            int4 raw[8];
-            uint32_t dst[4];
-            bool live[4], ok[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int q = q0 + u * pstep;
-              live[u] = q < npx;
-              const int qq = live[u] ? q : 0;
-              const int hy = __float2int_rd(((float)qq + 0.5f) * p.inv_hwd), hx = qq - hy * HWd;
+      for (int slab = 0; slab < SL; ++slab) {
+        if (it > 0) cptx::mbar_wait(halo_empty(slab), (uint32_t)((it - 1) & 1));  // the previous super tile's MMAs have read this slab
+        for (int ts = 0; ts < 2 * T; ++ts) {
+          const int gb = sup * 2 * T + ts;
+          if (gb >= p.nblocks) break;  // (rows of missing blocks are never stored)
+          const int b = gb / p.nb;
+          const int rem = gb - b * p.nb;
+          const int by = rem / p.nbx, bx = rem - by * p.nbx;
+          const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x) + ((int64_t)b * g.x_bstride + slab * 64 + chunk * 8) * esz;
+          const uint32_t plane = halo_a + (uint32_t)((((ts >> 1) * SL + slab) * AP)) * (uint32_t)p.plane_bytes;
+          if (AMODE == 0) {
+            for (int q = p0; q < npx; q += pstep) {
+              const int hy = __float2int_rd(((float)q + 0.5f) * p.inv_hwd), hx = q - hy * HWd;
               const int src = coarse_src(p, by, bx, hy, hx);
-              ok[u] = src >= 0;
               const int r = hy * (2 * HWd) + (ts & 1) * HWd + hx;
-              dst[u] = plane + (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-              const int4* s4 = reinterpret_cast<const int4*>(xb + (int64_t)(ok[u] ? src : 0) * g.Cin * 4);
-              raw[2 * u] = cptx::ldg_nc16(s4);
-              raw[2 * u + 1] = cptx::ldg_nc16(s4 + 1);
+              cptx::cp_async16(plane + (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4),
+                               xb + (int64_t)(src < 0 ? 0 : src) * g.Cin * 2, src < 0 ? 0u : 16u);
             }
+          } else {
+            // fp32 -> (hi, lo) halves: kU pixels (2 kU 16-byte loads) in flight per thread (dilation 1: 100 halo pixels / 32 per
+            // pass -> one batch of four)
+            constexpr int kU = 4;
+            for (int q0 = p0; q0 < npx; q0 += kU * pstep) {
+              int4 raw[2 * kU];
+              uint32_t dst[kU];
+              bool live[kU], ok[kU];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float v[8] = {__int_as_float(raw[2 * u].x), __int_as_float(raw[2 * u].y), __int_as_float(raw[2 * u].z),
-                                  __int_as_float(raw[2 * u].w), __int_as_float(raw[2 * u + 1].x), __int_as_float(raw[2 * u + 1].y),
-                                  __int_as_float(raw[2 * u + 1].z), __int_as_float(raw[2 * u + 1].w)};
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (p.x_f16) {
-                  hi[j] = ok[u] ? pack2_h16<true>(v[2 * j], v[2 * j + 1]) : 0u;
-                  const float2 back = unpack2_h16<true>(hi[j]);
-                  lo[j] = ok[u] ? pack2_h16<true>(v[2 * j] - back.x, v[2 * j + 1] - back.y) : 0u;
-                } else {
-                  hi[j] = ok[u] ? pack2_h16<false>(v[2 * j], v[2 * j + 1]) : 0u;
-                  const float2 back = unpack2_h16<false>(hi[j]);
-                  lo[j] = ok[u] ? pack2_h16<false>(v[2 * j] - back.x, v[2 * j + 1] - back.y) : 0u;
-                }
+              for (int u = 0; u < kU; ++u) {
+                const int q = q0 + u * pstep;
+                live[u] = q < npx;
+                const int qq = live[u] ? q : 0;
+                const int hy = __float2int_rd(((float)qq + 0.5f) * p.inv_hwd), hx = qq - hy * HWd;
+                const int src = coarse_src(p, by, bx, hy, hx);
+                ok[u] = src >= 0;
+                const int r = hy * (2 * HWd) + (ts & 1) * HWd + hx;
+                dst[u] = plane + (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+                const int4* s4 = reinterpret_cast<const int4*>(xb + (int64_t)(ok[u] ? src : 0) * g.Cin * 4);
+                raw[2 * u] = cptx::ldg_nc16(s4);
+                raw[2 * u + 1] = cptx::ldg_nc16(s4 + 1);
               }
-              if (live[u]) {
-                cptx::st_shared_v4(dst[u], hi[0], hi[1], hi[2], hi[3]);
-                cptx::st_shared_v4(dst[u] + (uint32_t)p.plane_bytes, lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+              for (int u = 0; u < kU; ++u) {
+                const float v[8] = {__int_as_float(raw[2 * u].x), __int_as_float(raw[2 * u].y), __int_as_float(raw[2 * u].z),
+                                    __int_as_float(raw[2 * u].w), __int_as_float(raw[2 * u + 1].x), __int_as_float(raw[2 * u + 1].y),
+                                    __int_as_float(raw[2 * u + 1].z), __int_as_float(raw[2 * u + 1].w)};
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (p.x_f16) {
+                    hi[j] = ok[u] ? pack2_h16<true>(v[2 * j], v[2 * j + 1]) : 0u;
+                    const float2 back = unpack2_h16<true>(hi[j]);
+                    lo[j] = ok[u] ? pack2_h16<true>(v[2 * j] - back.x, v[2 * j + 1] - back.y) : 0u;
+                  } else {
+                    hi[j] = ok[u] ? pack2_h16<false>(v[2 * j], v[2 * j + 1]) : 0u;
+                    const float2 back = unpack2_h16<false>(hi[j]);
+                    lo[j] = ok[u] ? pack2_h16<false>(v[2 * j] - back.x, v[2 * j + 1] - back.y) : 0u;
+                  }
+                }
+                if (live[u]) {
+                  cptx::st_shared_v4(dst[u], hi[0], hi[1], hi[2], hi[3]);
+                  cptx::st_shared_v4(dst[u] + (uint32_t)p.plane_bytes, lo[0], lo[1], lo[2], lo[3]);
+                }
               }
             }
           }
         }
-      }
-      if (AMODE == 0) {
-        cptx::cp_async_arrive_noinc(halo_full);
-      } else {
-        cptx::fence_proxy_async();  // generic-proxy stores -> visible to tcgen05.mma's async-proxy reads
-        cptx::mbar_arrive(halo_full);
+        if (AMODE == 0) {
+          cptx::cp_async_arrive_noinc(halo_full(slab));
+        } else {
+          cptx::fence_proxy_async();  // generic-proxy stores -> visible to tcgen05.mma's async-proxy reads
+          cptx::mbar_arrive(halo_full(slab));
+        }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ============================== MMA issuer ==============================
+    // One thread issues every tcgen05.mma of the CTA: its instruction stream must stay below the tensor pipe's 32 (N = 64) / 64
+    // (N = 128) cycles per MMA.  Descriptors are (lo, hi) 32-bit pairs -- hi (SBO | version | swizzle) is loop invariant, lo is
+    // the 16-byte-unit start address = plane base + tap view + 2k -- so an MMA costs two integer adds, not a 64-bit rebuild.
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (p.x_f16 ? 0u : ((1u << 7) | (1u << 10))) | (((uint32_t)g.Cout >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t sbo = (uint32_t)HWd * 128u;
+      const uint32_t hi_a = (((uint32_t)HWd * 128u) >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t hi_b = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t plane16 = (uint32_t)p.plane_bytes >> 4;
+      const uint32_t halo_lo = (halo_a & 0x3FFFFu) >> 4, ring_lo = (b_ring & 0x3FFFFu) >> 4;
+      const uint32_t bstage16 = bstage >> 4, blo16 = p.bblock >> 4;
       int s = 0, it = 0;
       uint32_t bphase = 0;  // filter ring position: stage s, phase bit flips on every wrap
       for (int sup = blockIdx.x; sup < p.nsuper; sup += gridDim.x, ++it) {
         const int a = it & 1;
         if (it >= 2) cptx::mbar_wait(acc_empty(a), (uint32_t)(((it >> 1) - 1) & 1));
-        cptx::mbar_wait(halo_full, (uint32_t)(it & 1));
-        cptx::fence_proxy_async();
-        cptx::tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
-          cptx::mbar_wait(b_full(s), bphase);
+        for (int sl = 0; sl < SL; ++sl) {
+          cptx::mbar_wait(halo_full(sl), (uint32_t)(it & 1));
+          cptx::fence_proxy_async();
           cptx::tc_fence_after();
-          const int tap = kb / SL, sl = kb - tap * SL, ky = tap / 3, kx = tap - ky * 3;
-          const uint64_t bdesc = cdesc_sbo(b_ring + (uint32_t)s * bstage, 1024u);
-          const uint32_t view = (uint32_t)((ky * d) * (2 * HWd) + kx * d) * 128u;
-          for (int t = 0; t < T; ++t) {
-            const uint32_t d_tmem = tmem_acc + (uint32_t)((a * T + t) * 128);
-            const uint32_t pl = halo_a + (uint32_t)((t * SL + sl) * AP) * (uint32_t)p.plane_bytes + view;
-            for (int hl = 0; hl < AP; ++hl) {
-              const uint64_t adesc = cdesc_sbo(pl + (uint32_t)hl * (uint32_t)p.plane_bytes, sbo);
+          int ky = 0, kx = 0;
+          for (int tap = 0; tap < 9; ++tap) {
+            cptx::mbar_wait(b_full(s), bphase);
+            cptx::tc_fence_after();
+            const uint32_t b_lo = ring_lo + (uint32_t)s * bstage16;
+            const uint32_t view16 = (uint32_t)((ky * d) * (2 * HWd) + kx * d) * 8u;  // 128-byte rows in 16-byte units
+            for (int t = 0; t < T; ++t) {
+              const uint32_t d_tmem = tmem_acc + (uint32_t)((a * T + t) * 128);
+              const uint32_t pl = halo_lo + (uint32_t)((t * SL + sl) * AP) * plane16 + view16;
+              for (int hl = 0; hl < AP; ++hl) {
+                const uint32_t a_lo = pl + (uint32_t)hl * plane16;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                cptx::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | hl | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  cptx::umma_f16_lohi(d_tmem, a_lo + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc, (sl | tap | hl | k) != 0 ? 1u : 0u);
+              }
+              if (p.wsplit) {  // Ahi . Wlo
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cptx::umma_f16_lohi(d_tmem, pl + 2u * k, hi_a, b_lo + blo16 + 2u * k, hi_b, idesc, 1u);
+              }
             }
-            if (p.wsplit) {  // Ahi . Wlo
-              const uint64_t adesc = cdesc_sbo(pl, sbo);
-              const uint64_t blo = bdesc + (uint64_t)(p.bblock >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) cptx::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
+            cptx::umma_commit(b_empty(s));
+            if (++s == BS) {
+              s = 0;
+              bphase ^= 1u;
+            }
+            if (++kx == 3) {
+              kx = 0;
+              ++ky;
             }
           }
-          cptx::umma_commit(b_empty(s));
-          if (++s == BS) {
-            s = 0;
-            bphase ^= 1u;
-          }
+          cptx::umma_commit(halo_empty(sl));  // this slab's planes may be refilled
         }
-        cptx::umma_commit(halo_empty);
         cptx::umma_commit(acc_full(a));
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ============================== filter ring producer (one thread) ==============================
     if (lane == 0) {
       int s = 0;
       uint32_t wrap = 0;  // completed trips around the ring
       for (int sup = blockIdx.x; sup < p.nsuper; sup += gridDim.x) {
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {  // slab-major, like the MMA loop: block (tap, slab) sits at tap * SL + slab
           if (wrap > 0) cptx::mbar_wait(b_empty(s), (wrap - 1u) & 1u);
           cptx::mbar_expect_tx(b_full(s), bstage);
-          const uint16_t* src = p.w + (int64_t)kb * g.Cout * 64;
+          const int sl = kb / 9, tap = kb - sl * 9;
+          const uint16_t* src = p.w + (int64_t)(tap * SL + sl) * g.Cout * 64;
           cptx::bulk_g2s(b_ring + (uint32_t)s * bstage, src, p.bblock, b_full(s));
           if (p.wsplit) cptx::bulk_g2s(b_ring + (uint32_t)s * bstage + p.bblock, src + p.w_plane_elems, p.bblock, b_full(s));
           if (++s == BS) {
@@ -361,7 +392,7 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
     }
     __syncwarp();
   } else {
-    // ============================== epilogue (warps 5-8) ==============================
+    // ============================== epilogue (warps 9-12) ==============================
     // TMEM lane = accumulator row = one output pixel; a thread walks its pixel's channels in 32-column steps: bias, activation,
     // residual, store (a pixel's 32 channels are 64 / 128 contiguous bytes).
     const int quad = warp & 3;
@@ -443,7 +474,7 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
 
   cptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     cptx::tc_fence_after();
     cptx::tmem_dealloc(tmem_acc, 512);
   }

@@ -45,25 +45,31 @@ class _State(threading.local):
         self.wsplit = False   # 'fp16s': split filters (2 MMAs per K step) on the tcgen05 convs outside the hi region too
         self.wsplit_policy = os.environ.get("LNS_WSPLIT", "enc")  # where ops.wsplit_region turns that on: enc | all | none
         self.hi_scale = float(os.environ.get("LNS_HI_SCALE", "1"))  # experiment: 4 = one more resolution level in the hi region
-        self.hi_wsplit = os.environ.get("LNS_HI_WSPLIT", "0") != "0"  # hi layers also split the filter (3 MMAs instead of 2)
+        self.hi_wsplit = os.environ.get("LNS_HI_WSPLIT", "1") != "0"  # hi layers also split the filter (3 MMAs instead of 2)
         self.coarse = os.environ.get("LNS_COARSE", "1") != "0"        # use the block-halo engine (conv_coarse.cu) where it applies
 
 
-def _mark(label):
-    """Profiling hook: returns a closer that records a CUDA-event pair around one library call (eager mode only)."""
+def _mark(label, flops=0.0, nbytes=0.0):
+    """Profiling hook: returns a closer that records a CUDA-event pair around one library call (eager mode only), together with
+    the call's ALGORITHMIC flops (2 x MACs of the reference layer) and bytes (compulsory reads + writes) -- bench.py's roofline."""
     tl = _state.timeline
     if tl is None:
         return None
     e0 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    return (label, e0)
+    return (label, e0, float(flops), float(nbytes))
 
 
 def _done(tok):
     if tok is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        _state.timeline.append((tok[0], tok[1], e1))
+        _state.timeline.append((tok[0], tok[1], e1, tok[2], tok[3]))
+
+
+def _abytes(*acts):
+    """bytes of the given activations (None entries are skipped)"""
+    return float(sum(a.B * a.H * a.W * a.C * a.t.element_size() for a in acts if a is not None))
 
 
 _state = _State()
@@ -364,6 +370,13 @@ def _umma_ok(x, Cin, Cout, y_layout):
     return False
 
 
+def _coarse_fits(Cin, Cout, dil, f32in, wsplit):
+    """shared-memory budget of conv_coarse.cu: the halo planes of one MMA tile + a three-stage filter ring"""
+    hwd = 8 + 2 * dil
+    tile = (Cin // 64) * (2 if f32in else 1) * hwd * 2 * hwd * 128
+    return tile + 3 * Cout * 128 * (2 if wsplit else 1) + 1536 <= 227 * 1024
+
+
 def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, PAD_ZEROS), virt=None, use_bias=True,
            sample_bias=None, pro=None, act=ACT_NONE, pre_add=None, residual=None, out=None, out_dtype=None,
            out_layout=NHWC, engine=None, split=None):
@@ -404,7 +417,8 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
             pro = None
         coarse_ok = (KH == 3 and KW == 3 and stride == 1 and Cin in (64, 128) and Cout in (64, 128) and 1 <= dil <= 3
                      and pt == pb == pl == pr == dil and dil <= min(Hv, Wv) and sample_bias is None and pre_add is None
-                     and pro is None and _state.coarse)
+                     and pro is None and _state.coarse
+                     and _coarse_fits(Cin, Cout, dil, x.t.dtype == torch.float32, _state.hi_wsplit))
         if (x.layout == NHWC and out_layout == NHWC and Cin % 64 == 0 and Cout % 16 == 0 and not x.tf32 and not _state.hi_exact
                 and ((x.t.dtype == torch.float32 and x.bstride % 4 == 0) or (x.t.dtype == torch.float16 and x.bstride % 8 == 0))):
             if coarse_ok:
@@ -487,7 +501,8 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
                 f"{' up' if virt is not None else ''}{' pro' if pro is not None else ''}"
                 f"{' act' if act else ''}{' res' if residual is not None else ''} "
                 f"{'h16' if x.t.dtype in H16_DTYPES else 'f32'}->{'h16' if out.t.dtype in H16_DTYPES else 'f32'}"
-                f"{' split' if split_fmt else ''}")
+                f"{' split' if split_fmt else ''}",
+                flops=2.0 * x.B * Hout * Wout * Cout * KH * KW * Cin, nbytes=_abytes(x, out, residual, pre_add))
     rc = _C.lib().lns_conv2d(ctypes.byref(d), _stream())
     check(rc, "lns_conv2d")
     _done(tok)
@@ -511,7 +526,7 @@ def _pointwise_proj(x, filt, use_bias, pro, out):
     if isinstance(pro, LazyNorm):
         pro = pro.as_tuple()
     sc, sh, pa = (pro if pro is not None else (None, None, ACT_NONE))
-    tok = _mark(f"proj @{x.H}x{x.W}")
+    tok = _mark(f"proj @{x.H}x{x.W}", flops=2.0 * x.B * x.H * x.W * Cin * Cout, nbytes=_abytes(x) + 4.0 * x.B * x.H * x.W * Cout)
     if out.group is not None:
         if out.B % out.group != 0:
             raise LnsError(f"proj: {out.B} samples are not whole steps of {out.group} trajectories")
@@ -549,7 +564,7 @@ def group_norm_affine(x, groups, eps, gamma=None, beta=None, prescale=None):
     shift = torch.empty_like(scale)
     g = gamma.detach().float().contiguous() if gamma is not None else None
     b = beta.detach().float().contiguous() if beta is not None else None
-    tok = _mark(f"gn_stats C{x.C} @{x.H}x{x.W}")
+    tok = _mark(f"gn_stats C{x.C} @{x.H}x{x.W}", nbytes=_abytes(x))
     rc = _C.lib().lns_group_norm_affine(_ptr(x.t), x.dtype, x.B, x.H, x.W, x.C, x.bstride, groups, float(eps), _ptr(g),
                                         _ptr(b), _ptr(prescale), _ptr(part), _ptr(scale), _ptr(shift), _stream())
     check(rc, "lns_group_norm_affine")
@@ -584,7 +599,7 @@ class LazyNorm:
             out = x.like(dtype=out_dtype)
             g = self.gamma.detach().float().contiguous() if self.gamma is not None else None
             b = self.beta.detach().float().contiguous() if self.beta is not None else None
-            tok = _mark(f"gn_act_fused C{x.C} @{x.H}x{x.W}")
+            tok = _mark(f"gn_act_fused C{x.C} @{x.H}x{x.W}", nbytes=_abytes(x, out))
             rc = _C.lib().lns_group_norm_act(_ptr(x.t), x.dtype, x.B, x.H, x.W, x.C, x.bstride, self.groups, float(self.eps),
                                              _ptr(g), _ptr(b), _ptr(self.prescale), self.act, _ptr(out.t), out.dtype,
                                              out.bstride, _stream())
@@ -599,7 +614,7 @@ class LazyNorm:
 def affine_act(x, scale, shift, act=ACT_NONE, out_dtype=None):
     """y = act(x*scale[b,c] + shift[b,c]) as a new contiguous Act."""
     out = x.like(dtype=out_dtype)
-    tok = _mark(f"affine_act C{x.C} @{x.H}x{x.W}")
+    tok = _mark(f"affine_act C{x.C} @{x.H}x{x.W}", nbytes=_abytes(x, out))
     rc = _C.lib().lns_affine_act(_ptr(x.t), x.dtype, x.bstride, x.B, x.H * x.W, x.C, _ptr(scale), _ptr(shift), act,
                                  _ptr(out.t), out.dtype, out.bstride, _stream())
     check(rc, "lns_affine_act")
@@ -707,7 +722,7 @@ def fablock_prepass(u, eps, gamma, beta):
     py = Act.empty(u.B, u.W, 1, u.C, torch.float32, dev)
     g = gamma.detach().float().contiguous() if gamma is not None else None
     b = beta.detach().float().contiguous() if beta is not None else None
-    tok = _mark(f"fablock_prepass @{u.H}x{u.W}")
+    tok = _mark(f"fablock_prepass @{u.H}x{u.W}", nbytes=_abytes(u))
     rc = _C.lib().lns_fablock_prepass(_ptr(u.t), u.dtype, u.B, u.H, u.W, u.C, u.bstride, float(eps), _ptr(g), _ptr(b),
                                       _ptr(scale), _ptr(shift), _ptr(px.t), _ptr(py.t), _stream())
     check(rc, "lns_fablock_prepass")
@@ -737,7 +752,9 @@ def sablock_fused_supported(x, heads, dim_head):
 def sablock_fused(x, heads, ln_g, ln_b, ln_eps, pe, wqkv16, bv, wproj16, bproj, scale):
     """Whole SABlock (LN + pe, q|k|v, attention, projection, residual) in one kernel: Act [B,H,W,128] -> Act of the same shape."""
     out = x.like()
-    tok = _mark("sablock_fused")
+    n_ = x.H * x.W
+    tok = _mark("sablock_fused", flops=x.B * (2.0 * n_ * x.C * 3 * heads * 64 + 4.0 * heads * n_ * n_ * 64 + 2.0 * n_ * heads * 64 * x.C),
+                nbytes=_abytes(x, out))
     rc = _C.lib().lns_sablock_fused(_ptr(x.t), x.dtype, x.B, x.H * x.W, heads, _ptr(ln_g), _ptr(ln_b), float(ln_eps), _ptr(pe),
                                     _ptr(wqkv16), _ptr(bv), _ptr(wproj16), _ptr(bproj), float(scale), _ptr(out.t), _stream())
     check(rc, "lns_sablock_fused")
@@ -778,7 +795,8 @@ def fa_axis_kernel(pooled, heads, w1t, ln_g, ln_b, ln_eps, wf1t, wf2t, bf2, wqk1
     assert pooled.contiguous and pooled.t.dtype == torch.float32 and pooled.C == 64
     n = pooled.H * pooled.W
     K = torch.empty(pooled.B, heads, n, n, dtype=torch.float32, device=pooled.t.device)
-    tok = _mark("fa_axis")
+    tok = _mark("fa_axis", flops=pooled.B * n * (2.0 * 64 * 64 + 4.0 * 64 * 128 + 2.0 * 64 * 2 * heads * 128 + 2.0 * heads * n * 128),
+                nbytes=_abytes(pooled) + 4.0 * pooled.B * heads * n * n)
     rc = _C.lib().lns_fa_axis_kernel(_ptr(pooled.t), dt_code(wqk16.dtype), pooled.B, n, heads, _ptr(w1t), _ptr(ln_g), _ptr(ln_b),
                                      float(ln_eps), _ptr(wf1t), _ptr(wf2t), _ptr(bf2), _ptr(wqk16), _ptr(cos_tab), _ptr(sin_tab),
                                      float(scaling), _ptr(K), _stream())
@@ -800,7 +818,10 @@ def fablock_full(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps, w_out1, w
     wi = w_in_proj.detach().float().contiguous()
     w1 = w_out1.detach().float().reshape(w_out1.shape[0], -1).contiguous()
     w2 = w_out2.detach().float().reshape(w_out2.shape[0], -1).contiguous()
-    tok = _mark(f"fablock_full @{u.H}x{u.W}")
+    hw_ = u.H * u.W
+    tok = _mark(f"fablock_full @{u.H}x{u.W}",
+                flops=u.B * (2.0 * hw_ * 64 * heads * 64 * 2 + 2.0 * heads * (u.H * u.H * u.W + u.H * u.W * u.W) * 64 + 2.0 * hw_ * 64 * 64),
+                nbytes=_abytes(u, out) + 4.0 * u.B * heads * (u.H * u.H + u.W * u.W))
     rc = _C.lib().lns_fablock_full(_ptr(u.t), u.dtype, u.B, u.H, u.W, heads, _ptr(gn_scale), _ptr(gn_shift), _ptr(wi), _ptr(Kx),
                                    _ptr(Ky), float(eps), _ptr(w1), _ptr(w2), _ptr(out.t), _stream())
     check(rc, "lns_fablock_full")

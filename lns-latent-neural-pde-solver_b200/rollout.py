@@ -37,7 +37,7 @@ class Rollout:
     must survive the next call."""
 
     def __init__(self, model, batch, steps, to_x=True, precision=None, use_graph=True, decode_chunk=None,
-                 device=None):
+                 device=None, pipeline=None):
         from modules.propagator import simple_cnn_fwd, cond_cnn_fwd, cond_cnn_prepare  # drop-in package at repo root
         self._simple_cnn_fwd, self._cond_cnn_fwd, self._cond_cnn_prepare = simple_cnn_fwd, cond_cnn_fwd, cond_cnn_prepare
         self.model = model
@@ -59,7 +59,7 @@ class Rollout:
         self.x_static = torch.zeros(self.B, self.Cin, self.Ly, self.Lx, dtype=torch.float32, device=self.device)
         self.param_static = torch.zeros(self.B, dtype=torch.float32, device=self.device) if self.conditional else None
         self.decode_chunk = decode_chunk
-        self.pipeline = os.environ.get("LNS_ROLLOUT_PIPELINE", "1") != "0"
+        self.pipeline = (os.environ.get("LNS_ROLLOUT_PIPELINE", "1") != "0") if pipeline is None else bool(pipeline)
         self.steps_per_group = 0
         self._side = None
         self.use_graph = use_graph

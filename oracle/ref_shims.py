@@ -1,11 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- never imported by the product path.
 
 Loads the *unmodified* reference (BaratiLab/LNS-Latent-Neural-PDE-Solver) from
-``/root/reference`` so that golden vectors can be generated in the build
-container.  ``/root/reference`` does not exist on the GPU box, therefore nothing
-under ``tests/ -m gpu``, ``bench.py`` or ``__graft_entry__.smoke()`` may import
-this file; they use the committed fixtures in ``tests/golden/`` and the
-restatement in ``oracle/lns_oracle.py`` instead.
+``/root/reference`` (build container) or from the git-ignored copy ``oracle/_ref``
+that ``oracle/vendor_ref.py`` stages (GPU box), so that golden vectors can be
+generated and the reference arm of ``bench.py`` (``--impl reference``) can time the
+reference's own ``LatentDynamics.predict``.  Parity tests never depend on it: they
+use the committed fixtures in ``tests/golden/`` and ``oracle/lns_oracle.py``.
 
 The reference does not import as shipped; five shims are
 installed in ``sys.modules`` -- no reference file is modified or copied:
@@ -30,7 +30,19 @@ import types
 
 import yaml
 
-REF = os.environ.get("LNS_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the copy that oracle/vendor_ref.py staged under oracle/_ref
+    (git-ignored, travels with the gpurun snapshot)."""
+    for cand in (os.environ.get("LNS_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "modules")):
+            return cand
+    return "/root/reference"
+
+
+REF = _default_root()
 
 CONFIGS = {
     # name -> (yaml, stage-2 script, AE attribute on LatentDynamics)

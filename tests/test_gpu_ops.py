@@ -962,6 +962,8 @@ def test_conv_coarse_fp32_split(case, wsplit):
     the exact activation and the f16-rounded filter); split filter: fp32-class result vs the exact conv"""
     ops = ops_mod()
     B, Cin, Cout, H, W, dil, modes, virt = case
+    if not ops._coarse_fits(Cin, Cout, dil, True, wsplit):
+        pytest.skip("two fp32-split halo planes per slab do not fit in shared memory at this dilation (gather engine instead)")
     x, w, b, res = _coarse_case(case, 43)
     ref = ref_conv(x, w if wsplit else w.half().float(), b, 1, dil, (dil,) * 4, modes, virt)
     ref = F.gelu(ref) + res.double()

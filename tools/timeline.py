@@ -37,7 +37,7 @@ with torch.no_grad():
     torch.cuda.synchronize()
 tl, ops._state.timeline = ops._state.timeline, None
 agg = collections.defaultdict(lambda: [0, 0.0])
-for label, e0, e1 in tl:
+for label, e0, e1, _fl, _by in tl:
     agg[label][0] += 1
     agg[label][1] += e0.elapsed_time(e1)
 tot = sum(v[1] for v in agg.values())
