@@ -6,17 +6,22 @@
 
 One "step" = one full rollout of the per-GPU batch: autoencoder encode -> R autoregressive propagator steps -> decode of
 all R states (LatentDynamics.predict(x, R, to_x=True) of the reference), i.e. B*R trajectory-steps per GPU per step.
-Default workload = BASELINE.json's NS2d 64x64 large-batch rollout (config 5: R=20, B=1184 = 8 x 148 SMs trajectories per
-GPU -- inside the config's 256..8192 sweep, sized so the per-sample kernels run whole waves --, trajectory-sharded, weak scaling), the configuration the metric's target is quoted on; other configs via --workload.
+Default workload = BASELINE.json's NS2d 64x64 large-batch rollout (config 5: R=20, B=1184 = 8 x 148 SMs trajectories per GPU --
+inside the config's 256..8192 sweep, sized so the per-sample kernels run whole waves --, trajectory-sharded, weak scaling).
+Default precision = 'fp16s', the 16-bit tensor-core mode that meets the north_star's <= 2e-3 per-stage bound (IEEE-half
+operands, split hi+lo operands on the layers that carry the rounding error; `parity` reports the measured error of THIS run).
 
-Output: ONE JSON line (see the contract in the task description) with `value` (inputs resident in HBM, CUDA-graph
-replay, CUDA-event timing, max over ranks), `e2e` (same metric through the public API with pinned host buffers, H2D and
-D2H copies inside the timed region), `roofline` (dominant kernel = the tcgen05 3x3 implicit-GEMM conv, timed alone with
-CUDA events), `cpu_baseline` (the oracle port of the reference timed on the host cores), `clocks`, `gpu_launches`.
-`--impl reference` times the reference's CPU implementation (oracle port; the reference is pure Python/PyTorch) on the
-host cores on a bounded sample of the same workload.
+Output: ONE JSON line with `value` (inputs resident in HBM, CUDA-graph replay, CUDA-event timing, max over ranks), `e2e`
+(same metric through the public API with pinned host buffers, H2D and D2H copies inside the timed region, every timed
+step), `roofline` (the kernel with the largest share of THIS run's step time, from a CUDA-event-bracketed eager pass of the
+same step), `roofline_by_time`, `parity`, `cpu_baseline` (the unmodified reference on the host cores), `eager_gpu_baseline`
+(the unmodified reference in PyTorch eager on the same B200, fp32 and autocast(bfloat16)), `workloads` (the other three
+configurations), `sweep` (NS2d batch sweep), `clocks`, `gpu_launches`.  The extras run on rank 0 at N=1 only.
+`--impl reference` times the reference's own LatentDynamics.predict (oracle/_ref, staged by oracle/vendor_ref.py) on the host
+cores on a bounded sample of the same workload.
 """
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -27,6 +32,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "latent rollout trajectory-steps/sec"
 WORKLOADS = {
     # name: (config, rollout steps R, trajectories per GPU, GFLOP per trajectory-step, label)
     "ns2d": ("ns2d", 20, 1184, 1.4611, "NS2d 64x64 latent rollout, R=20, 1184 trajectories/GPU = 8 per SM (BASELINE config 5)"),
@@ -35,6 +41,9 @@ WORKLOADS = {
     "twophase_cond": ("twophase_cond", 50, 128, 2.4806,
                       "two-phase conditional rollout, R=50, 128 trajectories/GPU (BASELINE config 4)"),
 }
+DTYPE_OF = {"bf16": "bf16", "fp16": "f16", "fp16s": "f16", "tf32": "tf32", "fp32": "f32"}
+CPU_SAMPLE = {"ns2d": 8, "sw": 1, "twophase": 2, "twophase_cond": 1}       # trajectories per CPU call of the reference
+GPU_EAGER_SAMPLE = {"ns2d": 256, "sw": 16, "twophase": 32, "twophase_cond": 32}
 
 
 def parse():
@@ -46,7 +55,8 @@ def parse():
     ap.add_argument("--workload", default="ns2d", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="trajectories per GPU (default: workload's)")
     ap.add_argument("--rollout-steps", type=int, default=None)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "tf32", "fp32"])
+    ap.add_argument("--precision", default="fp16s", choices=["fp16s", "bf16", "fp16", "tf32", "fp32"])
+    ap.add_argument("--quick", action="store_true", help="skip the extras (baselines, other workloads, sweep, per-kernel pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the final all-gather of fields (step i overlaps the rollout of step i+1) for N > 1")
     ap.add_argument("--decode-chunk", type=int, default=None, help="samples per decode launch group (default: engine's)")
@@ -58,49 +68,72 @@ def load_peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
-                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
 
 
-# ---- CPU reference (oracle port) ---------------------------------------------------------------------------------------
-def cpu_reference_throughput(workload, budget_s=20.0, min_runs=2, max_runs=5):
-    """trajectory-steps/s of the reference's CPU path (oracle port: same ATen CPU kernels in the same order as
-    LatentDynamics.predict) on all host cores, on a bounded sample (small batch, full R)."""
-    import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import lns_oracle as O
-    from lns_b200.configs import get_config
-    from lns_b200.latent_dynamics import LatentDynamics
-    cfg_name, R, _, _, _ = WORKLOADS[workload]
-    cfg = get_config(cfg_name)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.manual_seed(1234)
-    sd = O.randomize_zero_init(LatentDynamics(cfg).state_dict())
-    B = {"ns2d": 8, "sw": 1, "twophase": 2, "twophase_cond": 1}[cfg_name]
-    x, param = O.make_inputs(cfg, B, seed=0)
-    t0 = time.perf_counter()
-    O.predict(sd, cfg, x, R, param=param, to_x=True)  # warm-up (also sizes the sample)
-    first = time.perf_counter() - t0
-    runs = max(min_runs, min(max_runs, int(budget_s / max(first, 1e-3))))
-    best = float("inf")
-    for _ in range(runs):
-        t0 = time.perf_counter()
-        O.predict(sd, cfg, x, R, param=param, to_x=True)
-        best = min(best, time.perf_counter() - t0)
-    return {"value": B * R / best, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
-            "sample": f"oracle port of LatentDynamics.predict, fp32, B={B}, R={R}, best of {runs} runs "
-                      f"({best:.2f} s each), torch {torch.__version__} CPU, {cores} threads"}
+def config_block(label, R, B, world, gather, precision, sample_batch=None):
+    """the `config` object -- identical keys on both arms (the reference arm adds its bounded sample)"""
+    c = {"workload": label, "rollout_steps": R, "trajectories_per_gpu": B, "global_batch": B * world,
+         "parallelism": f"trajectory-sharded x{world}" + (", final all-gather of fields (step i overlaps the rollout of step i+1)" if gather else ""),
+         "l2": "per-step working set (activations) is far larger than the 126 MB L2; no explicit flush",
+         "cuda_graph": True, "random_init_weights_seed": 1234, "precision_mode": precision}
+    if sample_batch is not None:
+        c["sample_batch"] = sample_batch
+    return c
 
 
-def parity_check(model, cfg, precision, device):
-    """Teacher-forced per-stage relative L2 of the GPU path (at `precision`) against the fp64 oracle on 2 trajectories: part of
-    the cpu_baseline leg (the oracle is only ever the checker).  Returns {"encode", "propagator_step", "decode"}."""
+# ---- the reference itself, in its own process -------------------------------------------------------------------------------------
+def run_ref_arm(workload, device, batch, R, steps, warmup, autocast=False, budget_s=150.0, timeout=900):
+    """oracle/ref_arm.py in a fresh interpreter with a clean thread environment (torchrun exports OMP_NUM_THREADS=1, which
+    throttled round 1's CPU leg 100x) -> its JSON dict, or {"error": ...}."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT",
+                        "TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE")}
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_arm.py"), "--workload", workload, "--device", device, "--batch", str(batch),
+           "--rollout-steps", str(R), "--steps", str(steps), "--warmup", str(warmup), "--budget-s", str(budget_s)]
+    if autocast:
+        cmd.append("--autocast")
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as ex:  # noqa: BLE001
+        return {"error": repr(ex)[:400]}
+
+
+def cpu_baseline(workload, R, steps=3, warmup=1, budget_s=25.0):
+    d = run_ref_arm(workload, "cpu", CPU_SAMPLE[workload], R, steps, warmup, budget_s=budget_s)
+    if "error" in d:
+        return {"value": None, "unit": "trajectory-steps/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: " + d["error"]}
+    return {"value": round(d["value"], 3), "unit": "trajectory-steps/s", "cores": d["cores"], "kind": d["kind"], "sample": d["sample"],
+            "ms_per_call": round(d["ms_per_step"], 2), "sample_batch": d["sample_batch"]}
+
+
+def eager_gpu_baseline(workload, R):
+    """the same-box GPU bar: the unmodified reference modules in PyTorch eager on this B200 (fp32 and autocast(bfloat16))"""
+    out = {}
+    for key, ac in (("fp32", False), ("autocast_bf16", True)):
+        d = run_ref_arm(workload, "cuda", GPU_EAGER_SAMPLE[workload], R, 3, 1, autocast=ac, budget_s=60.0, timeout=400)
+        out[key] = ({"error": d["error"]} if "error" in d else
+                    {"value": round(d["value"], 1), "unit": "trajectory-steps/s", "ms_per_call": round(d["ms_per_step"], 2),
+                     "sample_batch": d["sample_batch"], "kind": d["kind"], "sample": d["sample"]})
+    return out
+
+
+# ---- parity (the oracle is only ever the checker) ----------------------------------------------------------------------------------
+def parity_check(model, cfg, precision, device, batch=8, drift_steps=0):
+    """Teacher-forced per-stage relative L2 of the GPU path (at `precision`, through the same engines as the timed run: batch >= 8
+    puts the latent-grid conv engine on the checked path) against the fp64 oracle; optionally the free-running drift."""
     import torch
     import lns_oracle as O
     from lns_b200 import ops
+    from lns_b200.rollout import Rollout
     sd64 = O.to_dtype({k: v.detach().cpu() for k, v in model.state_dict().items()}, torch.float64)
-    x, param = O.make_inputs(cfg, 2, seed=77)
+    x, param = O.make_inputs(cfg, batch, seed=77)
     ae = O.ae_name(cfg)
     z_ref = O.encode(sd64, cfg, x.double(), ae)
     cond = O.cond_embedding(sd64, cfg, param.double(), torch.float64) if param is not None else None
@@ -111,9 +144,17 @@ def parity_check(model, cfg, precision, device):
         z1 = model.propagator(z_ref.float().to(device)) if param is None else \
             model.propagator(z_ref.float().to(device), param.to(device))
         y = model.autoencoder.decode(z1_ref.float().to(device))
-    return {"vs": "fp64 oracle of the reference, teacher-forced per stage, 2 trajectories, max rel-L2",
-            "encode": float(O.rel_l2(z.cpu(), z_ref).max()), "propagator_step": float(O.rel_l2(z1.cpu(), z1_ref).max()),
-            "decode": float(O.rel_l2(y.cpu(), y_ref).max())}
+    out = {"vs": f"fp64 oracle of the reference, teacher-forced per stage, {batch} trajectories, max rel-L2 (bound 2e-3; fp32 mode 1e-5)",
+           "encode": float(O.rel_l2(z.cpu(), z_ref).max()), "propagator_step": float(O.rel_l2(z1.cpu(), z1_ref).max()),
+           "decode": float(O.rel_l2(y.cpu(), y_ref).max())}
+    if drift_steps:
+        nb = min(batch, 4)
+        yk_ref = O.predict(sd64, cfg, x[:nb].double(), drift_steps, param=None if param is None else param[:nb].double(), to_x=True)
+        ro = Rollout(model, batch=nb, steps=drift_steps, to_x=True, precision=precision, use_graph=False)
+        with torch.no_grad():
+            yk = ro(x[:nb].to(device), None if param is None else param[:nb].to(device)).cpu()
+        out["free_running_field_rel_l2_per_step"] = [round(float(O.rel_l2(yk[:, t], yk_ref[:, t]).max()), 6) for t in range(drift_steps)]
+    return out
 
 
 # ---- clocks ----------------------------------------------------------------------------------------------------------------
@@ -151,118 +192,115 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ---- dominant-kernel roofline ---------------------------------------------------------------------------------------------
-def conv_roofline(torch, ops, device, peaks, workload, precision="bf16"):
-    """Time the dominant kernel alone (tcgen05 implicit-GEMM 3x3 conv at the workload's largest layer) with CUDA events
-    on the launching stream; operands are larger than L2 so every launch streams from HBM."""
-    import math
-    shapes = {"ns2d": (64, 64, 64, 64, (1, 1)), "sw": (96, 192, 64, 64, (0, 1)),
-              "twophase": (61, 121, 64, 64, (0, 0)), "twophase_cond": (61, 121, 64, 64, (0, 0))}
-    H, W, Cin, Cout, modes = shapes[workload]
-    nb = max(8, (768 << 20) // (H * W * Cin * 2))  # ~768 MB of bf16 input: >> 126 MB L2
-    dt16 = torch.float16 if precision == "fp16" else torch.bfloat16
-    x = ops.Act(torch.randn(nb * H * W * Cin, device=device).to(dt16), nb, H, W, Cin)
-    wt = torch.nn.Parameter(torch.randn(Cout, Cin, 3, 3, device=device) / math.sqrt(9 * Cin))
-    bs = torch.nn.Parameter(torch.zeros(Cout, device=device))
-    filt = ops.PackedFilter.of(wt, bs)
-    out = ops.Act.empty(nb, H, W, Cout, dt16, device)
-    with ops.precision(precision):
-        for _ in range(3):
-            ops.conv2d(x, filt, pad=(1, 1, 1, 1), pad_mode=modes, out=out)
+# ---- per-kernel roofline of THIS run ------------------------------------------------------------------------------------------
+KERNEL_OF = [  # timeline label prefix -> kernel (csrc file)
+    ("conv e0", "conv_simt_kernel / lift1x1 (conv_simt.cu)"), ("conv e1", "conv_umma_kernel (conv_umma.cu, tcgen05 gather engine)"),
+    ("conv e2", "conv_halo_kernel (conv_halo.cu, tcgen05 halo engine)"), ("conv e3", "conv_latent_kernel (conv_latent.cu, tcgen05)"),
+    ("conv e4", "conv_coarse_kernel (conv_coarse.cu, tcgen05 block-halo engine)"), ("fablock_full", "fablock_full_kernel (fablock_full.cu)"),
+    ("fablock_tc", "fablock_tc_kernel (fablock_tc.cu, tcgen05)"), ("fa_axis", "fa_axis_kernel (fa_axis.cu)"),
+    ("sablock_fused", "sablock_fused_kernel (sablock_fused.cu)"), ("ffn_fused", "ffn_fused_kernel (ffn_fused.cu, tcgen05)"),
+    ("proj", "pointwise_proj64_kernel (pointwise.cu)"), ("gn_stats", "gn_affine_small / chan_stats kernels (pointwise.cu, norm.cu)"),
+    ("gn_act_fused", "gn_act_small_kernel (pointwise.cu)"), ("affine_act", "affine_act2_kernel (norm.cu)"),
+    ("fablock_prepass", "fablock_prepass2_kernel (fablock.cu)"),
+]
+
+
+def kernel_name(label):
+    for pre, k in KERNEL_OF:
+        if label.startswith(pre):
+            return k
+    return label.split(" ")[0]
+
+
+def per_kernel_pass(torch, ops, model, B, R, precision, x_dev, p_dev, peaks, decode_chunk):
+    """One eager, serial-order rollout of the SAME step with a CUDA-event pair around every library call (on the launching
+    stream) -> per call-site time, algorithmic flops and bytes.  `roofline` = the call site with the largest time share."""
+    from lns_b200.rollout import Rollout
+    ro = Rollout(model, batch=B, steps=R, to_x=True, precision=precision, use_graph=False, pipeline=False, decode_chunk=decode_chunk)
+    with torch.no_grad():
+        ro.build()
+        ro(x_dev, p_dev)
         torch.cuda.synchronize()
-        reps = 10
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-        ev[0].record()
-        for i in range(reps):
-            ops.conv2d(x, filt, pad=(1, 1, 1, 1), pad_mode=modes, out=out)
-            ev[i + 1].record()
+        ops._state.timeline = []
+        ro(x_dev, p_dev)
         torch.cuda.synchronize()
-    ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
-    t = sum(ms) / len(ms) * 1e-3
-    flops = 2.0 * nb * H * W * Cout * 9 * Cin
-    achieved = flops / t / 1e12
-    traffic = None  # dram read+write bytes per launch from the committed ncu --set full capture of this exact shape
-    tp = os.path.join(ROOT, "profiles", "r01_halo_traffic.json")
-    if workload == "ns2d" and os.path.exists(tp):
-        tj = json.load(open(tp))
-        if tj.get("algorithmic_bytes") == nb * H * W * (Cin + Cout) * 2:
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-    peak = peaks["bf16_tflops"]  # burst figure: this kernel is timed alone
-    return {"bound": "tensor", "kernel": f"conv_halo_kernel<{Cout}> (tcgen05, smem halo + resident filter) 3x3 {Cin}->{Cout} "
-                                        f"@ {H}x{W}, batch {nb}",
-            "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-            "traffic": traffic, "algorithmic_bytes": nb * H * W * (Cin + Cout) * 2, "algorithmic_flops": flops,
-            "avg_launch_ms": round(t * 1e3, 4), "peak_source": peaks["source"],
-            "hbm_gbs_at_algorithmic_bytes": round(nb * H * W * (Cin + Cout) * 2 / t / 1e9, 1)}
+    tl, ops._state.timeline = ops._state.timeline, None
+    agg = collections.OrderedDict()
+    for label, e0, e1, fl, by in tl:
+        a = agg.setdefault(label, [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += e0.elapsed_time(e1)
+        a[2] += fl
+        a[3] += by
+    total = sum(a[1] for a in agg.values())
+    rows = []
+    for label, (n, ms, fl, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        t = ms * 1e-3
+        tf, gbs = fl / t / 1e12, by / t / 1e9
+        # the bound that a perfect kernel of this layer would hit first at the measured peaks
+        t_tensor, t_hbm = fl / (peaks["bf16_tflops_sustained"] * 1e12), by / (peaks["hbm_gbs"] * 1e9)
+        bound = "tensor" if t_tensor >= t_hbm else "hbm"
+        row = {"call_site": label, "kernel": kernel_name(label), "share_of_step": round(ms / total, 4), "launches": n,
+               "avg_launch_ms": round(ms / n, 4), "bound": bound,
+               "achieved": round(tf if bound == "tensor" else gbs, 2), "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+               "peak": peaks["bf16_tflops_sustained"] if bound == "tensor" else peaks["hbm_gbs"],
+               "algorithmic_flops_per_launch": fl / n, "algorithmic_bytes_per_launch": by / n}
+        row["frac"] = round(row["achieved"] / row["peak"], 4)
+        rows.append(row)
+    del ro
+    torch.cuda.empty_cache()
+    return rows, total
 
 
-def time_share(pattern):
-    """share of the step's kernel time of kernels whose name contains `pattern`, from the committed ncu launch list"""
-    tp = os.path.join(ROOT, "profiles", "r01_launches_bench.txt")
-    if not os.path.exists(tp):
-        return None
-    tot = 0.0
-    for ln in open(tp):
-        parts = ln.split()
-        if len(parts) > 3 and parts[1] == "ms" and parts[2].endswith("%") and pattern in ln:
-            tot += float(parts[2].rstrip("%"))
-    return round(tot / 100.0, 4) if tot else None
+def traffic_of(call_site):
+    """DRAM read + write bytes per launch of this call site from the committed `ncu --set full` summary, if one exists"""
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tp):
+        try:
+            return json.load(open(tp)).get(call_site)
+        except Exception:  # noqa: BLE001
+            return None
+    return None
 
 
-def kernels_by_time(torch, ops, device, peaks, roof):
-    """The three kernels with the largest share of the NS2d step's time, each timed alone (CUDA events, operands > L2 or
-    one CTA wave per SM) against the measured bf16 tensor peak.  Shares come from profiles/r01_launches_bench.txt."""
-    import math
-    out = []
+def time_rollout(torch, ro, x_dev, p_dev, steps, warmup=3):
+    for _ in range(warmup):
+        ro(x_dev, p_dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ro(x_dev, p_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
-    def timed(fn, reps=5):
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-        ev[0].record()
-        for i in range(reps):
-            fn()
-            ev[i + 1].record()
-        torch.cuda.synchronize()
-        return sum(ev[i].elapsed_time(ev[i + 1]) for i in range(reps)) / reps * 1e-3
 
-    with torch.no_grad(), ops.precision("bf16"):
-        # FABlock2D whole-block kernel, 32x32, 4736 samples (one decode chunk = 32 per SM)
-        nb, H, W = 4736, 32, 32
-        u = ops.Act(torch.randn(nb * H * W * 64, device=device).bfloat16(), nb, H, W, 64)
-        sc, sh = torch.rand(nb * 64, device=device) + 0.5, torch.randn(nb * 64, device=device) * 0.1
-        w = torch.nn.Parameter(torch.randn(512, 64, device=device) / 8)
-        w1 = torch.nn.Parameter(torch.randn(64, 512, 1, 1, device=device) / 22)
-        w2 = torch.nn.Parameter(torch.randn(64, 64, 1, 1, device=device) / 8)
-        kx = torch.randn(nb, 8, H, H, device=device) / H ** 0.5
-        ky = torch.randn(nb, 8, W, W, device=device) / W ** 0.5
-        t = timed(lambda: ops.fablock_full(u, sc, sh, w, kx, ky, 8, 1e-5, w1, w2))
-        fl = nb * (2.0 * H * W * 64 * 512 * 2 + 2.0 * 8 * (H * H * W + H * W * W) * 64 + 2.0 * H * W * 64 * 64)
-        by = nb * (2 * H * W * 64 * 2 + 8 * (H * H + W * W) * 4)
-        out.append({"kernel": "fablock_full_kernel<512> (FABlock2D per sample, mma.sync phases + tcgen05 to_out, TMEM-resident "
-                              "accumulator) 32x32, batch 4736", "share_of_step": time_share("fablock_full_kernel"),
-                    "bound": "tensor", "achieved": round(fl / t / 1e12, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": round(fl / t / 1e12 / peaks["bf16_tflops"], 4), "avg_launch_ms": round(t * 1e3, 4),
-                    "algorithmic_bytes": by, "hbm_gbs_at_algorithmic_bytes": round(by / t / 1e9, 1)})
-        del u, kx, ky
-        # propagator conv: 3x3 128->128 circular @ 8x8, one propagator step of the bench batch (latent-grid engine)
-        nb, H, W, C = 1184, 8, 8, 128
-        x = ops.Act(torch.randn(nb * H * W * C, device=device).bfloat16(), nb, H, W, C)
-        wt = torch.nn.Parameter(torch.randn(C, C, 3, 3, device=device) / math.sqrt(9 * C))
-        bs = torch.nn.Parameter(torch.zeros(C, device=device))
-        filt = ops.PackedFilter.of(wt, bs)
-        y = ops.Act.empty(nb, H, W, C, torch.bfloat16, device)
-        t = timed(lambda: ops.conv2d(x, filt, pad=(1, 1, 1, 1), pad_mode=(1, 1), act=ops.ACT_GELU, out=y), reps=20)
-        fl = 2.0 * nb * H * W * C * 9 * C
-        out.append({"kernel": "conv_latent_kernel (tcgen05 latent-grid engine: resident halos of 4 samples, streamed filter) 3x3 "
-                              "128->128 circular @ 8x8, batch 1184 (L2-resident: 19 MB in + 19 MB out)",
-                    "share_of_step": time_share("conv_latent_kernel"),
-                    "bound": "tensor", "achieved": round(fl / t / 1e12, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": round(fl / t / 1e12 / peaks["bf16_tflops"], 4), "avg_launch_ms": round(t * 1e3, 4)})
-    out.append({"kernel": roof["kernel"], "share_of_step": time_share("conv_halo_kernel"), "bound": "tensor",
-                "achieved": roof["achieved"], "peak": roof["peak"], "unit": "TFLOP/s", "frac": roof["frac"],
-                "avg_launch_ms": roof["avg_launch_ms"]})
+def side_workload(torch, O, name, precision, device, batch=None, steps=3, parity=True):
+    """value (+ live parity) of another configuration on this GPU: CUDA-graph replay, inputs resident, CUDA events"""
+    from lns_b200.configs import get_config
+    from lns_b200.latent_dynamics import LatentDynamics
+    from lns_b200.rollout import Rollout
+    cfg_name, R, B, gflop, label = WORKLOADS[name]
+    B = batch or B
+    cfg = get_config(cfg_name)
+    torch.manual_seed(1234)
+    model = LatentDynamics(cfg).eval()
+    model.load_state_dict(O.randomize_zero_init(model.state_dict()))
+    model = model.to(device)
+    x, p = O.make_inputs(cfg, B, seed=0)
+    x, p = x.to(device), (p.to(device) if p is not None else None)
+    ro = Rollout(model, batch=B, steps=R, to_x=True, precision=precision, use_graph=True)
+    with torch.no_grad():
+        ro.build()
+        ms = time_rollout(torch, ro, x, p, steps)
+    out = {"workload": label, "value": round(B * R / (ms * 1e-3), 1), "unit": "trajectory-steps/s", "ms_per_step": round(ms, 3),
+           "trajectories_per_gpu": B, "rollout_steps": R, "launches_per_step": int(ro.launches_per_call),
+           "whole_path_tflops": round(B * R / (ms * 1e-3) * gflop / 1e3, 2)}
+    if parity:
+        out["parity"] = parity_check(model, cfg, precision, device, batch=4 if name == "sw" else 8)
+    del ro, model
+    torch.cuda.empty_cache()
     return out
 
 
@@ -276,17 +314,23 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
+        # the reference's own CPU implementation of the path on the host cores (rank 0 only), each step = one predict() on a
+        # bounded sample of the workload
         if rank != 0:
             return 0
-        # bounded sample per step; steps/warmup only scale the repeat count (the CPU path is batch-flat)
-        base = cpu_reference_throughput(args.workload, budget_s=min(60.0, 6.0 * max(1, args.steps)))
-        line = {"metric": "latent rollout trajectory-steps/sec", "impl": "reference", "value": round(base["value"], 3),
-                "unit": "trajectory-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {"workload": label, "rollout_steps": R},
+        sb = CPU_SAMPLE[cfg_name]
+        d = run_ref_arm(cfg_name, "cpu", sb, R, max(1, args.steps), max(0, args.warmup), budget_s=170.0)
+        if "error" in d:
+            print(json.dumps({"impl": "reference", "unavailable": d["error"][:200]}), flush=True)
+            return 0
+        base = {"value": round(d["value"], 3), "unit": "trajectory-steps/s", "cores": d["cores"], "kind": d["kind"], "sample": d["sample"]}
+        line = {"metric": METRIC, "impl": "reference", "value": round(d["value"], 3), "unit": "trajectory-steps/s",
+                "n_gpus": args.gpus, "steps": d["steps_run"], "warmup": args.warmup, "ms_per_step": round(d["ms_per_step"], 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_block(label, R, B, args.gpus, False, "fp32 (reference, CPU)", sample_batch=sb),
                 "cpu_baseline": base,
-                "e2e": {"value": round(base["value"], 3), "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+                "e2e": {"value": round(d["value"], 3), "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
         print(json.dumps(line), flush=True)
         return 0
 
@@ -298,7 +342,7 @@ def main():
     from lns_b200.latent_dynamics import LatentDynamics
     from lns_b200.rollout import Rollout
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import lns_oracle as O  # only for seeded synthetic inputs / zero-init redraw and the cpu_baseline leg
+    import lns_oracle as O  # only for seeded synthetic inputs / zero-init redraw and the parity leg
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU path; use --impl reference for the CPU baseline)")
@@ -344,7 +388,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         one_step()
     drain()
     sampler = ClockSampler(local)
@@ -367,9 +412,9 @@ def main():
         elapsed_ms = float(t.item())
     value = world * B * R * args.steps / (elapsed_ms * 1e-3)
 
-    # end to end through the public API: pinned host input -> H2D -> rollout -> D2H of the predicted fields, EVERY step.
-    # The D2H copy of step i (335 MB, ~6 ms of PCIe time) runs on a copy stream out of a device staging buffer while the
-    # rollout of step i+1 computes (double-buffered, event-ordered); the timed region ends when the last copy has landed.
+    # end to end through the public API: pinned host input -> H2D -> rollout -> D2H of the predicted fields, EVERY timed step.
+    # The D2H copy of step i runs on a copy stream out of a device staging buffer while the rollout of step i+1 computes
+    # (double-buffered, event-ordered); the timed region ends when the last copy has landed.
     out_host = [torch.empty((B, R, ro.C, ro.Ly, ro.Lx), dtype=torch.float32).pin_memory() for _ in range(2)]
     stage = [torch.empty((B, R, ro.C, ro.Ly, ro.Lx), dtype=torch.float32, device=device) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device)
@@ -378,7 +423,7 @@ def main():
     landed = [torch.cuda.Event() for _ in range(2)]
     for ev in landed:
         ev.record(compute)
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, args.steps)
 
     def e2e_step(i):
         s = i & 1
@@ -410,32 +455,62 @@ def main():
     e2e_value = world * B * R * e2e_steps / (e2e_ms * 1e-3)
     h2d = x_pin.numel() * 4 + (p_pin.numel() * 4 if p_pin is not None else 0)
     d2h = out_host[0].numel() * 4
+    del out_host, stage
+    torch.cuda.empty_cache()
 
     if rank == 0:
-        roof = conv_roofline(torch, ops, device, peaks, args.workload, args.precision) if args.precision in ("bf16", "fp16") else None
         tflops = value * gflop_per_ts / 1e3
         line = {
-            "metric": "latent rollout trajectory-steps/sec", "value": round(value, 1), "unit": "trajectory-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": round(value, 1), "unit": "trajectory-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
-            "config": {"workload": label, "rollout_steps": R, "trajectories_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"trajectory-sharded x{world}" + (", final all-gather of fields (step i overlaps the rollout of step i+1)" if gather else ""),
-                       "l2": "per-step working set (activations) is far larger than the 126 MB L2; no explicit flush",
-                       "cuda_graph": True, "random_init_weights_seed": 1234},
+            "vs_baseline": None, "dtype": DTYPE_OF[args.precision], "data": "synthetic",
+            "config": config_block(label, R, B, world, gather, args.precision),
             "whole_path_tflops_per_gpu": round(tflops / world, 2),
             "whole_path_frac_of_bf16_sustained": round(tflops / world / peaks["bf16_tflops_sustained"], 4),
             "e2e": {"value": round(e2e_value, 1), "unit": "trajectory-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(ro.launches_per_call * args.steps),
             "launches_per_step": int(ro.launches_per_call),
-            "clocks": clocks, "roofline": roof,
+            "clocks": clocks, "roofline": None,
         }
-        if roof is not None and args.workload == "ns2d" and args.precision == "bf16":
-            line["roofline_by_time"] = kernels_by_time(torch, ops, device, peaks, roof)
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_throughput(args.workload, budget_s=15.0)
-            line["parity"] = parity_check(model, cfg, args.precision, device)
+        extras = world == 1 and not args.quick
+        if extras:
+            # the kernel with the largest share of THIS run's step (eager, serial order, one CUDA-event pair per library call)
+            rows, total = per_kernel_pass(torch, ops, model, B, R, args.precision, x_dev, p_dev, peaks, args.decode_chunk)
+            top = dict(rows[0])
+            top["traffic"] = traffic_of(top["call_site"])
+            top["peak_source"] = peaks["source"] + " (sustained bf16 / HBM copy: the kernel is timed inside a long step)"
+            top["timed"] = (f"CUDA events around every launch of one eager rollout of this step on the launching stream "
+                            f"({total:.1f} ms in serial order vs {elapsed_ms / args.steps:.1f} ms as a two-stream CUDA graph)")
+            line["roofline"] = top
+            line["roofline_by_time"] = rows[:8]
+            fam = collections.defaultdict(float)
+            for r_ in rows:
+                fam[r_["kernel"]] += r_["share_of_step"]
+            line["share_by_kernel"] = {k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])[:10]}
+            line["parity"] = parity_check(model, cfg, args.precision, device, batch=8, drift_steps=R if cfg_name == "ns2d" else 0)
+            if not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline(cfg_name, R)
+                line["eager_gpu_baseline"] = eager_gpu_baseline(cfg_name, R)
+            del ro
+            torch.cuda.empty_cache()
+            if args.workload == "ns2d":
+                others = {}
+                for w in ("sw", "twophase", "twophase_cond"):
+                    try:
+                        others[w] = side_workload(torch, O, w, args.precision, device)
+                    except Exception as ex:  # noqa: BLE001
+                        others[w] = {"error": repr(ex)[:300]}
+                line["workloads"] = others
+                sweep = {}
+                for nb in (256, 1024, 4096, 8192):
+                    try:
+                        s_ = side_workload(torch, O, "ns2d", args.precision, device, batch=nb, steps=2, parity=False)
+                        sweep[str(nb)] = {"value": s_["value"], "ms_per_step": s_["ms_per_step"]}
+                    except Exception as ex:  # noqa: BLE001
+                        sweep[str(nb)] = {"error": repr(ex)[:200]}
+                line["sweep"] = {"workload": "NS2d 64x64, R=20, trajectories per GPU (BASELINE config 5)", "unit": "trajectory-steps/s", **sweep}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -488,7 +488,7 @@ int lns_attention(const void* qkv, int dtype, int B, int n, int heads, int dh, f
     int n16 = (n + 15) & ~15, nk = (n + 63) & ~63;
     size_t smem_mma = ((size_t)n16 + 2 * (size_t)nk) * lns::kAttStride * sizeof(__nv_bfloat16);
     if (smem_mma <= 227 * 1024) {
-      { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); cudaFuncSetAttribute(lns::attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+      { LNS_OPT_IN_SMEM((lns::attention_mma_kernel<false>), 227 * 1024, "attention"); LNS_OPT_IN_SMEM((lns::attention_mma_kernel<true>), 227 * 1024, "attention"); }
       dim3 grid(heads, B);
       auto kern = dtype == LNS_F16 ? lns::attention_mma_kernel<true> : lns::attention_mma_kernel<false>;
       kern<<<grid, 128, smem_mma, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -499,7 +499,7 @@ int lns_attention(const void* qkv, int dtype, int B, int n, int heads, int dh, f
   }
   size_t smem = ((size_t)n * (dh + 1) + (size_t)n * dh + 8 * dh + 8 * (size_t)n) * sizeof(float);
   LNS_REQUIRE(smem <= 227 * 1024, "lns_attention: n=%d dh=%d needs %zu B shared memory", n, dh, smem);
-  { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+  { LNS_OPT_IN_SMEM((lns::attention_kernel), 227 * 1024, "attention"); }
   int qsplit = 1;
   while ((int64_t)B * heads * qsplit < 296 && qsplit * 8 < n) qsplit *= 2;
   dim3 grid(heads, B, qsplit);
@@ -530,7 +530,7 @@ int lns_lowrank_kernel(const void* qk, int dtype, int B, int n, int heads, int d
     int n16 = (n + 15) & ~15;
     size_t smem_mma = 2 * (size_t)n16 * (d + 8) * sizeof(__nv_bfloat16);
     if (smem_mma <= 227 * 1024) {
-      { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::lowrank_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); cudaFuncSetAttribute(lns::lowrank_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+      { LNS_OPT_IN_SMEM((lns::lowrank_mma_kernel<false>), 227 * 1024, "attention"); LNS_OPT_IN_SMEM((lns::lowrank_mma_kernel<true>), 227 * 1024, "attention"); }
       dim3 grid(heads, B);
       auto kern = dtype == LNS_F16 ? lns::lowrank_mma_kernel<true> : lns::lowrank_mma_kernel<false>;
       kern<<<grid, 128, smem_mma, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -540,7 +540,7 @@ int lns_lowrank_kernel(const void* qk, int dtype, int B, int n, int heads, int d
   }
   size_t smem = 2 * (size_t)n * (d + 1) * sizeof(float);
   LNS_REQUIRE(smem <= 227 * 1024, "lns_lowrank_kernel: n=%d d=%d needs %zu B shared memory", n, d, smem);
-  { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::lowrank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+  { LNS_OPT_IN_SMEM((lns::lowrank_kernel), 227 * 1024, "attention"); }
   dim3 grid(heads, B);
   lns::lowrank_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(qk, dtype, n, heads, d, cos_tab,
                                                                                     sin_tab, scaling, K);
@@ -562,7 +562,7 @@ int lns_axial_contract(const void* u, int dtype, int B, int H, int W, int heads,
     size_t smem_mma = ((size_t)n16 * (n16 + 8) + (size_t)lns::kAxLines * n16 * lns::kAxSlabStride +
                        4 * 16 * (size_t)lns::kAxSlabStride) * sizeof(__nv_bfloat16);
     LNS_REQUIRE(smem_mma <= 227 * 1024, "lns_axial_contract: n=%d needs %zu B shared memory", n, smem_mma);
-    { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::axial_contract_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); cudaFuncSetAttribute(lns::axial_contract_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+    { LNS_OPT_IN_SMEM((lns::axial_contract_mma_kernel<false>), 227 * 1024, "attention"); LNS_OPT_IN_SMEM((lns::axial_contract_mma_kernel<true>), 227 * 1024, "attention"); }
     dim3 grid(lns::cdiv(lines, lns::kAxLines), heads, B);
     auto kern = dtype == LNS_F16 ? lns::axial_contract_mma_kernel<true> : lns::axial_contract_mma_kernel<false>;
     kern<<<grid, 128, smem_mma, s>>>(reinterpret_cast<const __nv_bfloat16*>(u), H, W, heads, K, axis,
@@ -571,7 +571,7 @@ int lns_axial_contract(const void* u, int dtype, int B, int H, int W, int heads,
   }
   size_t smem = ((size_t)n * ch + (size_t)n * n) * sizeof(float);
   LNS_REQUIRE(smem <= 227 * 1024, "lns_axial_contract: n=%d needs %zu B shared memory", n, smem);
-  { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::axial_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once = true; } }
+  { LNS_OPT_IN_SMEM((lns::axial_contract_kernel), 227 * 1024, "attention"); }
   dim3 grid(axis == 0 ? W : H, heads, B);
   lns::axial_contract_kernel<<<grid, 256, smem, s>>>(u, dtype, H, W, heads, ch, K, axis, out, out_dtype);
   return lns::check_launch("axial_contract_kernel");

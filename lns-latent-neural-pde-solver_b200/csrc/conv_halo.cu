@@ -718,15 +718,7 @@ template <int NT, int KI, int KA, int WS = 0>
 static int launch_halo(const HaloParams& p, const CUtensorMap& tmap_y, const CUtensorMap& tmap_r, int smem_bytes, int grid,
                        cudaStream_t stream) {
   auto kern = conv_halo_kernel<NT, KI, KA, WS>;
-  static bool once = false;
-  if (!once) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      set_error("conv_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return LNS_E_CUDA;
-    }
-    once = true;
-  }
+  LNS_OPT_IN_SMEM(kern, 227 * 1024, "conv_halo");  // per (template instance, device)
   kern<<<grid, 32 * (4 + KI + 4), smem_bytes, stream>>>(p, tmap_y, tmap_r);
   return check_launch("conv_halo_kernel");
 }
@@ -766,10 +758,13 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
   p.inv_hw = 1.0f / (float)p.HW;
   p.inv_hv = 1.0f / (float)d->Hv;
   p.inv_wv = 1.0f / (float)d->Wv;
+  p.debug = 0;
+#ifdef LNS_HALO_DEBUG_BUILD  // timing ablations (skip copies / epilogue / MMAs: WRONG results) exist only in a -DLNS_HALO_DEBUG_BUILD build
   {
     const char* dbg = getenv("LNS_HALO_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+#endif
   const int NT = d->Cout;
   const int wsplit = d->w_format == LNS_W_UMMA_F16X2 ? 1 : 0;
   // output staging: two 4 KB buffers per epilogue warp when four halo stages still fit next to them, else one
@@ -784,17 +779,7 @@ int conv2d_halo(const LnsConvDesc* d, cudaStream_t stream) {
   if (stages == 3) stages = 2;  // the issuer count must divide the ring depth (see below)
   LNS_REQUIRE(stages >= 2, "lns_conv2d(halo): shared memory too small for dilation %d with Cout %d", d->dil, d->Cout);
   p.stages = stages;
-  int sms = 148;
-  {
-    static int cached = 0;
-    if (!cached) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-      if (cached <= 0) cached = 148;
-    }
-    sms = cached;
-  }
+  const int sms = device_sm_count();
   int grid = p.ntiles < sms ? p.ntiles : sms;
   // 16-bit outputs leave through TMA tensor stores (LNS_HALO_TMA=0: the staged read-back + st.global path)
   CUtensorMap tmap_y;

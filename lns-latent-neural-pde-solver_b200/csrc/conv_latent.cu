@@ -465,28 +465,8 @@ int conv2d_latent(const LnsConvDesc* d, cudaStream_t stream) {
   LNS_REQUIRE(bst >= 3, "lns_conv2d(latent): shared memory too small for a 3-stage filter ring at dilation %d", d->dil);
   p.bstages = bst;
   const int smem = fixed + bst * (int)kBBytes;
-  {
-    static bool once = false;
-    if (!once) {
-      cudaError_t e = cudaFuncSetAttribute(conv_latent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) {
-        set_error("conv_latent: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        return LNS_E_CUDA;
-      }
-      once = true;
-    }
-  }
-  int sms = 148;
-  {
-    static int cached = 0;
-    if (!cached) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-      if (cached <= 0) cached = 148;
-    }
-    sms = cached;
-  }
+  LNS_OPT_IN_SMEM(conv_latent_kernel, 227 * 1024, "conv_latent");
+  const int sms = device_sm_count();
   const int grid = p.nsuper < sms ? p.nsuper : sms;
   conv_latent_kernel<<<grid, kLatThreads, smem, stream>>>(p);
   return check_launch("conv_latent_kernel");

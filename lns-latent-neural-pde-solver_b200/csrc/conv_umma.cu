@@ -478,15 +478,7 @@ template <int NT, int STAGES, int ESZ, int MODE = 0>
 static int launch_umma(const UmmaParams& p, int Cout, cudaStream_t stream) {
   using L = UmmaSmem<NT, STAGES, MODE>;
   auto kern = conv_umma_kernel<NT, STAGES, ESZ, MODE>;
-  static bool once = false;  // per template instance (one process per GPU; never repeated under graph capture)
-  if (!once) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-    if (e != cudaSuccess) {
-      set_error("conv_umma: cudaFuncSetAttribute(%d B): %s", L::kTotal, cudaGetErrorString(e));
-      return LNS_E_CUDA;
-    }
-    once = true;
-  }
+  LNS_OPT_IN_SMEM(kern, L::kTotal, "conv_umma");  // per (template instance, device); never repeated under graph capture
   dim3 grid(cdiv(p.M, 128), cdiv(Cout, NT));
   kern<<<grid, kUmmaThreads, L::kTotal, stream>>>(p);
   return check_launch("conv_umma_kernel");

@@ -345,12 +345,8 @@ int lns_fa_axis_kernel(const float* pooled, int dtype16, int B, int n, int heads
   p.cos_t = cos_tab; p.sin_t = sin_tab; p.scaling = scaling; p.K = K;
   const size_t smem = lns::fa_axis_smem(n);
   {
-    static bool once = false;
-    if (!once) {
-      cudaFuncSetAttribute(lns::fa_axis_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lns::fa_axis_smem(64));
-      cudaFuncSetAttribute(lns::fa_axis_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lns::fa_axis_smem(64));
-      once = true;
-    }
+    LNS_OPT_IN_SMEM((lns::fa_axis_kernel<false>), (int)lns::fa_axis_smem(64), "fa_axis");
+    LNS_OPT_IN_SMEM((lns::fa_axis_kernel<true>), (int)lns::fa_axis_smem(64), "fa_axis");
   }
   const int grid = (B + p.S - 1) / p.S;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

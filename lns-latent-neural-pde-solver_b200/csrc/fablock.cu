@@ -565,13 +565,9 @@ int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, in
     size_t smem2 = ((size_t)H * C + 8 * (size_t)W * C + 8 * (size_t)C * 2 + 2 * (size_t)C) * sizeof(float);
     if (nx <= 24 && smem2 <= 200 * 1024) {
       {
-        static bool once = false;
-        if (!once) {
-          cudaFuncSetAttribute(lns::fablock_prepass2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-          cudaFuncSetAttribute(lns::fablock_prepass2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-          cudaFuncSetAttribute(lns::fablock_prepass2_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-          once = true;
-        }
+        LNS_OPT_IN_SMEM((lns::fablock_prepass2_kernel<8>), 200 * 1024, "fablock");
+        LNS_OPT_IN_SMEM((lns::fablock_prepass2_kernel<16>), 200 * 1024, "fablock");
+        LNS_OPT_IN_SMEM((lns::fablock_prepass2_kernel<24>), 200 * 1024, "fablock");
       }
       if (nx <= 8)
         lns::fablock_prepass2_kernel<8><<<B, 256, smem2, st>>>(u, dtype, H, W, C, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y);
@@ -586,7 +582,7 @@ int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, in
   LNS_REQUIRE(W <= lns::kPreMaxX * rows, "lns_fablock_prepass: W=%d too wide for C=%d", W, C);
   size_t smem = ((size_t)rows * C + (size_t)H * C + (size_t)W * C + (size_t)rows * C * 2 + 2 * (size_t)C) * sizeof(float);
   LNS_REQUIRE(smem <= 200 * 1024, "lns_fablock_prepass: %dx%dx%d needs %zu B shared memory", H, W, C, smem);
-  { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::fablock_prepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); once = true; } }
+  { LNS_OPT_IN_SMEM((lns::fablock_prepass_kernel), 200 * 1024, "fablock"); }
   lns::fablock_prepass_kernel<<<B, 256, smem, st>>>(u, dtype, H, W, C, bstride, eps, gamma, beta,
                                                     scale, shift, pooled_x, pooled_y);
   return lns::check_launch("fablock_prepass_kernel");
@@ -605,14 +601,10 @@ int lns_fablock_core(const void* u, int dtype, int B, int H, int W, int heads, c
   LNS_REQUIRE((reinterpret_cast<uintptr_t>(u) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "lns_fablock_core: alignment");
   size_t smem = lns::fablock_smem(H, W);
   {
-    static bool once = false;
-    if (!once) {
-      cudaFuncSetAttribute(lns::fablock_core_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(lns::fablock_core_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(lns::fablock_core_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(lns::fablock_core_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      once = true;
-    }
+    LNS_OPT_IN_SMEM((lns::fablock_core_kernel<512, false>), 227 * 1024, "fablock");
+    LNS_OPT_IN_SMEM((lns::fablock_core_kernel<256, false>), 227 * 1024, "fablock");
+    LNS_OPT_IN_SMEM((lns::fablock_core_kernel<512, true>), 227 * 1024, "fablock");
+    LNS_OPT_IN_SMEM((lns::fablock_core_kernel<256, true>), 227 * 1024, "fablock");
   }
   dim3 grid(heads, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

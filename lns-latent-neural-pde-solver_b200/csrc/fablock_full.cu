@@ -679,14 +679,10 @@ int lns_fablock_full(const void* u, int dtype, int B, int H, int W, int heads, c
   const bool big = H * W > 256;
   const size_t smem = lns::full_layout(H, W, p.T, big ? 16 : 8).total + 1024;
   {
-    static bool once = false;
-    if (!once) {
-      cudaFuncSetAttribute(lns::fablock_full_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(lns::fablock_full_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(lns::fablock_full_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(lns::fablock_full_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      once = true;
-    }
+    LNS_OPT_IN_SMEM((lns::fablock_full_kernel<512, false>), 227 * 1024, "fablock_full");
+    LNS_OPT_IN_SMEM((lns::fablock_full_kernel<256, false>), 227 * 1024, "fablock_full");
+    LNS_OPT_IN_SMEM((lns::fablock_full_kernel<512, true>), 227 * 1024, "fablock_full");
+    LNS_OPT_IN_SMEM((lns::fablock_full_kernel<256, true>), 227 * 1024, "fablock_full");
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool f16 = dtype == LNS_F16;

@@ -319,12 +319,8 @@ int lns_ffn_fused(const void* x, int dtype, int B, int HW, int C, int64_t x_bstr
   p.inv_hw = 1.0f / (float)HW;
   const int smem = 6 * (int)lns::kSlab + 64 + 1024;
   {
-    static bool once = false;
-    if (!once) {
-      cudaFuncSetAttribute(lns::ffn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      cudaFuncSetAttribute(lns::ffn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      once = true;
-    }
+    LNS_OPT_IN_SMEM((lns::ffn_fused_kernel<false>), 227 * 1024, "ffn_fused");
+    LNS_OPT_IN_SMEM((lns::ffn_fused_kernel<true>), 227 * 1024, "ffn_fused");
   }
   const int grid = (int)((M + 127) / 128);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -451,7 +451,7 @@ int lns_group_norm_act(const void* x, int dtype, int B, int H, int W, int C, int
   int cg = C / 4;
   const int rows = 256 / cg;
   size_t smem = (((size_t)H * W * C * lns::dtype_size(dtype) + 15) & ~(size_t)15) + ((size_t)rows * C * 2 + 4 * (size_t)C) * sizeof(float);
-  { static bool once = false; if (!once) { cudaFuncSetAttribute(lns::gn_act_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); once = true; } }
+  { LNS_OPT_IN_SMEM((lns::gn_act_small_kernel), 96 * 1024, "pointwise"); }
   lns::gn_act_small_kernel<<<B, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, dtype, H * W, C, bstride, G, eps, gamma,
                                                                                       beta, prescale, act, y, y_dtype, y_bstride,
                                                                                       1.0 / ((double)(C / G) * (double)H * (double)W));

@@ -350,12 +350,8 @@ int lns_sablock_fused(const void* x, int dtype, int B, int n, int heads, const f
   p.scale_log2e = scale * 1.4426950408889634f;
   const size_t smem = lns::sablock_smem();
   {
-    static bool once = false;
-    if (!once) {
-      cudaFuncSetAttribute(lns::sablock_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(lns::sablock_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      once = true;
-    }
+    LNS_OPT_IN_SMEM((lns::sablock_fused_kernel<false>), 227 * 1024, "sablock_fused");
+    LNS_OPT_IN_SMEM((lns::sablock_fused_kernel<true>), 227 * 1024, "sablock_fused");
   }
   const int grid = (B + p.S - 1) / p.S;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

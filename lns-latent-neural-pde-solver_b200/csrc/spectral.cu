@@ -177,13 +177,9 @@ int lns_spectral_conv2d(const void* x, int x_dtype, int B, int H, int W, int Ci,
   size_t smD = ((size_t)m2 * Co + W) * sizeof(float2);
   LNS_REQUIRE(smA <= 227 * 1024 && smB <= 227 * 1024 && smD <= 227 * 1024,
               "lns_spectral_conv2d: shape needs %zu/%zu/%zu B shared memory", smA, smB, smD);
-  static bool once = false;  // (one process per GPU; not repeated so that graph capture never sees it)
-  if (!once) {
-    cudaFuncSetAttribute(lns::spectral_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(lns::spectral_cols_mix, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(lns::spectral_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    once = true;
-  }
+  LNS_OPT_IN_SMEM((lns::spectral_rows_fwd), 227 * 1024, "spectral");
+  LNS_OPT_IN_SMEM((lns::spectral_cols_mix), 227 * 1024, "spectral");
+  LNS_OPT_IN_SMEM((lns::spectral_rows_inv), 227 * 1024, "spectral");
   lns::spectral_rows_fwd<<<dim3(H, B), 256, smA, s>>>(x, x_dtype, H, W, Ci, m2, X1);
   int rc = lns::check_launch("spectral_rows_fwd");
   if (rc) return rc;

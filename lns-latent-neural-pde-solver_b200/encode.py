@@ -33,9 +33,14 @@ def encode_frames(ae, frames, chunk=1024, mean=0.0, std=1.0, eps=1e-8, precision
     out_host = None
     scale, shift = 1.0 / (float(std) + eps), -float(mean) / (float(std) + eps)
     nchunks = (N + chunk - 1) // chunk
+    norm_scale = torch.full((chunk * 4,), scale, dtype=torch.float32, device=device)
+    norm_shift = torch.full((chunk * 4,), shift, dtype=torch.float32, device=device)
 
     def stage(i):
         s, n = i & 1, min(chunk, N - i * chunk)
+        # the H2D copy of chunk i-2 read this pinned buffer asynchronously (it is queued behind the encoder of chunk i-4): the
+        # host may only re-pack the buffer once that copy has completed (never recorded on first use: returns at once)
+        in_ready[s].synchronize()
         stage_in[s][:n].copy_(x[i * chunk:i * chunk + n])           # host pack into pinned memory
         with torch.cuda.stream(copy_in):
             copy_in.wait_event(in_free[s])                           # the encoder has consumed this slot's previous chunk
@@ -51,7 +56,13 @@ def encode_frames(ae, frames, chunk=1024, mean=0.0, std=1.0, eps=1e-8, precision
             compute.wait_event(in_ready[s])
             xin = dev_in[s][:n]
             if scale != 1.0 or shift != 0.0:
-                xin = xin * scale + shift
+                # (x - mean) / (std + eps) on the device with the library's affine kernel: a contiguous NCHW sample is viewed as
+                # rows of 4 elements (C*H*W % 4 == 0 on every configuration), scale / shift are per-(sample, lane) constants
+                per = xin[0].numel()
+                if per % 4 != 0:
+                    raise LnsError("encode_frames: C*H*W must be a multiple of 4")
+                a = ops.Act(xin.reshape(-1), n, 1, per // 4, 4)
+                xin = ops.affine_act(a, norm_scale[:n * 4], norm_shift[:n * 4], ops.ACT_NONE, out_dtype=torch.float32).t.view(xin.shape)
             z = ae.encode(xin)                                       # [n, Cz, h, w] fp32
             in_free[s].record(compute)
             done = torch.cuda.Event()

@@ -8,6 +8,8 @@ import torch.nn as nn
 
 
 class LatentDynamics(nn.Module):
+    _MAX_ROLLOUTS = 4
+
     def __init__(self, args, kind=None):
         super().__init__()
         kind = kind or getattr(args, "kind", None)
@@ -39,7 +41,7 @@ class LatentDynamics(nn.Module):
                 dilation=args.dilation,
                 padding_mode="circular" if kind == "ns2d" else "zeros",
                 periodic_direction="x" if kind == "sw" else None)
-        self._rollouts = {}
+        self._rollouts = {}  # (batch, steps, to_x, device, precision) -> Rollout, at most _MAX_ROLLOUTS, LRU
 
     @property
     def autoencoder(self):
@@ -75,9 +77,14 @@ class LatentDynamics(nn.Module):
             to_x = args[0]
         if x.dim() == 5:  # the SW / conditional scripts squeeze a singleton time axis (train_stage2_SW.py:144)
             x = x.squeeze(1)
-        key = (x.shape[0], steps, bool(to_x), x.device)
-        ro = self._rollouts.get(key)
+        from . import ops
+        key = (x.shape[0], steps, bool(to_x), x.device, ops.get_precision())
+        ro = self._rollouts.pop(key, None)
         if ro is None:
             ro = Rollout(self, batch=x.shape[0], steps=steps, to_x=to_x, use_graph=False)
-            self._rollouts[key] = ro
-        return ro(x, param) if param is not None else ro(x)
+            while len(self._rollouts) >= self._MAX_ROLLOUTS:  # bounded: least recently used engine (and its buffers) goes first
+                self._rollouts.pop(next(iter(self._rollouts)))
+        self._rollouts[key] = ro  # (re-)insert as most recently used
+        out = ro(x, param) if param is not None else ro(x)
+        # the engine returns its static buffer; the reference returns a fresh tensor per call (torch.stack), so does this API
+        return out.clone()

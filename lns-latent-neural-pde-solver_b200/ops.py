@@ -37,7 +37,7 @@ def dt_code(dtype):
 # ---- precision policy --------------------------------------------------------------------------------
 class _State(threading.local):
     def __init__(self):
-        self.precision = "bf16"
+        self.precision = "fp16s"  # the 16-bit tensor-core mode that meets the 2e-3 per-stage bound (set_precision below)
         self.launches = 0
         self.timeline = None  # list of (label, start_event, end_event) when profiling (tools/timeline.py)
         self.hi_px = 0        # 'fp16s': convs touching a grid of <= hi_px pixels run with split operands on fp32 storage
@@ -164,6 +164,15 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def device_of(t):
+    """Context manager: make the device of CUDA tensor `t` current (single-process multi-GPU callers); no-op for CPU tensors,
+    which the ops reject themselves."""
+    if torch.is_tensor(t) and t.is_cuda:
+        return torch.cuda.device(t.device)
+    from contextlib import nullcontext
+    return nullcontext()
+
+
 def _need_cuda(t, what):
     if not t.is_cuda:
         raise LnsError(f"{what}: lns_b200 runs on CUDA tensors only (there is no CPU fallback); got device {t.device}")
@@ -177,6 +186,11 @@ class Act:
     __slots__ = ("t", "B", "H", "W", "C", "bstride", "layout", "tf32", "group", "gstride")
 
     def __init__(self, t, B, H, W, C, bstride=None, layout=NHWC, tf32=False, group=None, gstride=0):
+        if t.is_cuda and t.device.index != torch.cuda.current_device():
+            # kernels are enqueued on the CURRENT device's current stream: a tensor of another GPU would be read through the
+            # wrong context.  The module / Rollout entry points install the guard themselves (ops.device_of).
+            raise LnsError(f"activation on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           f"wrap the call in `with torch.cuda.device({t.device.index})`")
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
         self.bstride = H * W * C if bstride is None else bstride
         self.layout = layout

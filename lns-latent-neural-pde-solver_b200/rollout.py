@@ -68,11 +68,18 @@ class Rollout:
         self.zs = None
         self.launches_per_call = None
         self._built = False
+        self._fp = None
+
+    def _fingerprint(self):
+        """(data_ptr, version) of every parameter and buffer the captured launch sequence depends on.  The graph bakes in the
+        addresses of the packed filter images (built from these tensors during the eager warm-up): after load_state_dict, an
+        optimizer step or .to() a replay would keep using stale -- or freed -- packed weights, so __call__ re-captures."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.model.parameters()) + list(self.model.buffers()))
 
     # ---- the sequence of kernel launches -------------------------------------------------------------------------
     def _run(self):
         B, K = self.B, self.K
-        with ops.precision(self.precision):
+        with torch.cuda.device(self.device), ops.precision(self.precision):
             z0 = self.ae._encode(Act.from_nchw(self.x_static))            # [B,h,w,Cz] fp32
             h, w, Cz = z0.H, z0.W, z0.C
             hwc = h * w * Cz
@@ -156,6 +163,13 @@ class Rollout:
     def build(self):
         if self._built:
             return self
+        with torch.cuda.device(self.device):
+            self._build()
+        self._fp = self._fingerprint()
+        self._built = True
+        return self
+
+    def _build(self):
         # eager warm-up: packs the filters, allocates the resident buffers, counts the launches of one rollout
         for p in self.ae.parameters():
             if p.device != self.device:
@@ -175,22 +189,24 @@ class Rollout:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._run()
-        self._built = True
-        return self
 
     def __call__(self, x, param=None):
         if tuple(x.shape) != tuple(self.x_static.shape):
             raise LnsError(f"Rollout: expected x of shape {tuple(self.x_static.shape)}, got {tuple(x.shape)}")
         if self.conditional and param is None:
             raise LnsError("Rollout: this propagator is conditional, pass `param` [B]")
+        if self._built and self._fingerprint() != self._fp:
+            # a parameter was replaced or modified in place since the capture: re-pack and re-capture (buffers are kept)
+            self._built, self.graph = False, None
         self.build()
-        self.x_static.copy_(x, non_blocking=True)
-        if self.conditional:
-            self.param_static.copy_(param.reshape(-1), non_blocking=True)
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self._run()
+        with torch.cuda.device(self.device):
+            self.x_static.copy_(x, non_blocking=True)
+            if self.conditional:
+                self.param_static.copy_(param.reshape(-1), non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._run()
         return self.out
 
     def latents(self):

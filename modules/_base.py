@@ -35,8 +35,9 @@ class LnsModule(nn.Module):
     def forward(self, x, *args):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
             raise LnsError("lns_b200 modules are inference-only (no backward kernels yet): call under torch.no_grad()")
-        y = self._fwd(ops.nchw_to_act(x), *args)
-        return y.to_nchw()
+        with ops.device_of(x):
+            y = self._fwd(ops.nchw_to_act(x), *args)
+            return y.to_nchw()
 
 
 def run_sequential(layers, x):

@@ -49,7 +49,8 @@ class Encoder(LnsModule):
         return run_layers(self.model, x, final_dtype=torch.float32)  # the latent stays fp32
 
     def forward(self, x):
-        return self._fwd(ops.Act.from_nchw(x)).to_nchw()
+        with ops.device_of(x):
+            return self._fwd(ops.Act.from_nchw(x)).to_nchw()
 
 
 class Decoder(LnsModule):
@@ -92,7 +93,8 @@ class Decoder(LnsModule):
         return run_layers(self.model, x, final_out=out, final_layout=ops.NCHW)
 
     def forward(self, x):
-        return self._fwd(ops.nchw_to_act(x)).to_nchw()
+        with ops.device_of(x):
+            return self._fwd(ops.nchw_to_act(x)).to_nchw()
 
 
 class SimpleAutoencoder(LnsModule):
@@ -122,10 +124,12 @@ class SimpleAutoencoder(LnsModule):
         return self.decode(self.encode(x))
 
     def encode(self, x):
-        return self._encode(ops.Act.from_nchw(x)).to_nchw()
+        with ops.device_of(x):
+            return self._encode(ops.Act.from_nchw(x)).to_nchw()
 
     def decode(self, z):
-        return self._decode(ops.nchw_to_act(z, torch.float32)).to_nchw()
+        with ops.device_of(z):
+            return self._decode(ops.nchw_to_act(z, torch.float32)).to_nchw()
 
     def load_checkpoint(self, path):
         self.load_state_dict(torch.load(path), strict=True)

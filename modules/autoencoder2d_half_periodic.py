@@ -111,7 +111,8 @@ class Encoder(LnsModule):
         return run_layers(self.model, x, final_dtype=latent_dtype(self.model[-1].out_channels))
 
     def forward(self, x):
-        return self._fwd(ops.Act.from_nchw(x)).to_nchw()
+        with ops.device_of(x):
+            return self._fwd(ops.Act.from_nchw(x)).to_nchw()
 
 
 class Decoder(LnsModule):
@@ -163,7 +164,8 @@ class Decoder(LnsModule):
         return run_layers(self.model, x, final_out=out, final_layout=ops.NCHW)
 
     def forward(self, x):
-        return self._fwd(ops.nchw_to_act(x)).to_nchw()
+        with ops.device_of(x):
+            return self._fwd(ops.nchw_to_act(x)).to_nchw()
 
 
 class SimpleAutoencoder(LnsModule):
@@ -188,10 +190,12 @@ class SimpleAutoencoder(LnsModule):
         return self.decode(self.encode(x))
 
     def encode(self, x):
-        return self._encode(ops.Act.from_nchw(x)).to_nchw()
+        with ops.device_of(x):
+            return self._encode(ops.Act.from_nchw(x)).to_nchw()
 
     def decode(self, z):
-        return self._decode(ops.nchw_to_act(z, torch.float32)).to_nchw()
+        with ops.device_of(z):
+            return self._decode(ops.nchw_to_act(z, torch.float32)).to_nchw()
 
     def load_checkpoint(self, path, device=None):
         self.load_state_dict(torch.load(path, map_location=device), strict=True)
