@@ -43,6 +43,13 @@ class LatentDynamics(nn.Module):
                 periodic_direction="x" if kind == "sw" else None)
         self._rollouts = {}  # (batch, steps, to_x, device, precision) -> Rollout, at most _MAX_ROLLOUTS, LRU
 
+    def __getstate__(self):
+        """copy.deepcopy / pickle / torch.save(model): the cached rollout engines (CUDA graphs, streams, static buffers) stay
+        behind; the copy builds its own on first use"""
+        state = self.__dict__.copy()
+        state["_rollouts"] = {}
+        return state
+
     @property
     def autoencoder(self):
         return self.ae if self.kind == "twophase_cond" else self.vq_ae

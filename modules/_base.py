@@ -1,4 +1,6 @@
 """Common plumbing of the drop-in modules."""
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -15,12 +17,27 @@ def pad_modes(padding_mode):
     raise LnsError(f"unsupported padding_mode {padding_mode!r}")
 
 
+_CACHES = weakref.WeakKeyDictionary()
+
+
+def cache_of(mod):
+    """Per-module dictionary of device-side derived data (packed filter images, 16-bit operand copies, rotary tables).  It lives
+    OUTSIDE the module: copy.deepcopy / pickling / torch.save of a model never drag packed images -- or closures over the
+    ORIGINAL module's parameters -- into the copy, which starts with an empty cache of its own."""
+    c = _CACHES.get(mod)
+    if c is None:
+        c = {}
+        _CACHES[mod] = c
+    return c
+
+
 def filt_of(mod):
-    """PackedFilter of an nn.Conv2d / nn.Linear parameter holder (cached on the module)."""
-    f = mod.__dict__.get("_lns_filter")
-    if f is None:
+    """PackedFilter of an nn.Conv2d / nn.Linear parameter holder (cached per module object and per parameter object)."""
+    c = cache_of(mod)
+    f = c.get("filter")
+    if f is None or c.get("filter_src") is not mod.weight:  # (the parameter object itself was replaced: new PackedFilter)
         f = ops.PackedFilter.of(mod.weight, mod.bias)
-        mod.__dict__["_lns_filter"] = f
+        c["filter"], c["filter_src"] = f, mod.weight
     return f
 
 
@@ -130,11 +147,13 @@ def run_layers(layers, x, final_out=None, final_layout=ops.NHWC, final_dtype=Non
             if (ops.fast16() and isinstance(nxt, nn.Conv2d) and nxt.kernel_size == (1, 1)
                     and layer.kernel_size[0] > 1 and nxt.stride == (1, 1) and i + 1 < n - 1
                     and not hasattr(nxt, "periodic_direction")):
-                key = "_lns_composed_%d" % id(nxt)
-                filt = layer.__dict__.get(key)
-                if filt is None:
-                    filt = ops.composed_filter(filt_of(layer), filt_of(nxt))
-                    layer.__dict__[key] = filt
+                c = cache_of(layer)
+                f1, f2 = filt_of(layer), filt_of(nxt)
+                ent = c.get("composed")
+                if ent is None or ent[0] is not f1 or ent[1] is not f2:
+                    ent = (f1, f2, ops.composed_filter(f1, f2))
+                    c["composed"] = ent
+                filt = ent[2]
                 geo = conv_geometry(layer)
                 x = ops.conv2d(x, filt, pro=pro, virt=virt, **geo)
                 pro, virt = None, None

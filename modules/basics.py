@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from lns_b200 import ops
 
-from ._base import LnsModule, LnsError, conv_layer, norm_affine, lazy_norm, pad_modes, filt_of
+from ._base import LnsModule, LnsError, conv_layer, norm_affine, lazy_norm, pad_modes, filt_of, cache_of
 from .cond_utils import zero_module, ConditionedBlock  # noqa: F401  (re-exported like the reference does)
 
 
@@ -129,19 +129,21 @@ class SABlock(LnsModule):
             self._init_weights(m)
 
     def _qkv_filter(self):
-        f = self.__dict__.get("_lns_qkv")
-        if f is None:
-            f = ops.PackedFilter.concat([self.to_q.weight, self.to_k.weight, self.to_v.weight],
-                                        [None, None, self.to_v.bias])
-            self.__dict__["_lns_qkv"] = f
-        return f
+        c = cache_of(self)
+        srcs = (self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_v.bias)
+        ent = c.get("qkv")
+        if ent is None or any(a is not b for a, b in zip(ent[0], srcs)):
+            ent = (srcs, ops.PackedFilter.concat([self.to_q.weight, self.to_k.weight, self.to_v.weight],
+                                                 [None, None, self.to_v.bias]))
+            c["qkv"] = ent
+        return ent[1]
 
     def _fused_operands(self, dt16):
         """16-bit filter copies / fp32 vectors of lns_sablock_fused, cached until a source parameter changes."""
         srcs = [self.ln.weight, self.ln.bias, self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_v.bias,
                 self.proj_out.weight, self.proj_out.bias] + ([self.pe] if self.pe is not None else [])
         key = (dt16,) + tuple(None if t is None else (t.data_ptr(), t._version, str(t.device)) for t in srcs)
-        ent = self.__dict__.get("_lns_sa")
+        ent = cache_of(self).get("sa")
         if ent is None or ent[0] != key:
             with torch.no_grad():
                 f = lambda t: None if t is None else t.detach().float().contiguous()  # noqa: E731
@@ -150,7 +152,7 @@ class SABlock(LnsModule):
                     wqkv=torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0).detach().to(dt16).contiguous(),
                     bv=f(self.to_v.bias), wproj=self.proj_out.weight.detach().to(dt16).contiguous(), bproj=f(self.proj_out.bias),
                     pe=None if self.pe is None else self.pe.detach().float().reshape(-1, self.dim).contiguous()))
-            self.__dict__["_lns_sa"] = ent
+            cache_of(self)["sa"] = ent
         return ent[1]
 
     def _fwd(self, x):
@@ -196,11 +198,11 @@ class SpectralConv2d(LnsModule):
     def _mode_weights(self):
         """[Ci,Co,m1,m2,2] x2 -> [2,m1,m2,Ci,Co,2] (device-side re-layout with torch, cached per parameter version)."""
         key = (self.weights1.data_ptr(), self.weights1._version, self.weights2.data_ptr(), self.weights2._version)
-        ent = self.__dict__.get("_lns_wm")
+        ent = cache_of(self).get("wm")
         if ent is None or ent[0] != key:
             w = torch.stack([self.weights1.detach(), self.weights2.detach()], 0)  # [2,Ci,Co,m1,m2,2]
             ent = (key, w.permute(0, 3, 4, 1, 2, 5).contiguous().float())
-            self.__dict__["_lns_wm"] = ent
+            cache_of(self)["wm"] = ent
         return ent[1]
 
     def _fwd(self, x, emb=None):

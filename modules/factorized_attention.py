@@ -5,7 +5,7 @@ import torch.nn as nn
 
 from lns_b200 import ops
 
-from ._base import LnsModule, LnsError, conv_layer, filt_of, norm_affine
+from ._base import LnsModule, LnsError, conv_layer, filt_of, norm_affine, cache_of
 from .embedding import RotaryEmbedding
 
 
@@ -29,7 +29,7 @@ class LowRankKernel(LnsModule):
 
     def _tables(self, n, device):
         """cos / sin [n, dim_head/2] for pos = linspace(0,1,n) (reference :47), cached per n."""
-        cache = self.__dict__.setdefault("_lns_rot", {})
+        cache = cache_of(self).setdefault("rot", {})
         key = (n, str(device), self.pos_emb.inv_freq._version if self.use_rotary_emb else 0)
         if key not in cache:
             if self.use_rotary_emb:
@@ -144,7 +144,7 @@ class FABlock2D(LnsModule):
         srcs = [self.to_in[0].weight, reducer.to_in.weight, reducer.out_ffn[0].weight, reducer.out_ffn[0].bias,
                 reducer.out_ffn[1].weight, reducer.out_ffn[3].weight, reducer.out_ffn[3].bias, lrk.to_qk.weight]
         key = (dt16,) + tuple((t.data_ptr(), t._version, str(t.device)) for t in srcs)
-        cache = self.__dict__.setdefault("_lns_axis", {})
+        cache = cache_of(self).setdefault("axis", {})
         ent = cache.get(id(reducer))
         if ent is None or ent[0] != key:
             with torch.no_grad():

@@ -6,7 +6,7 @@ from torch import nn
 
 from lns_b200 import ops
 
-from ._base import LnsModule, conv_layer, filt_of
+from ._base import LnsModule, conv_layer, filt_of, cache_of
 from .cond_utils import ConditionedBlock
 
 
@@ -22,7 +22,7 @@ class FreqLinear(LnsModule):
         self.bias = nn.Parameter(torch.zeros(1, 4 * modes1 * modes2, dtype=torch.float32))
 
     def _filter(self):
-        f = self.__dict__.get("_lns_f")
+        f = cache_of(self).get("f")
         if f is None:
             w, b = self.weights, self.bias
 
@@ -33,7 +33,7 @@ class FreqLinear(LnsModule):
                 return b.detach().reshape(-1)
             f = ops.PackedFilter(wfn, bfn, lambda: (ops.PackedFilter._fp(w), ops.PackedFilter._fp(b)),
                                  (w.shape[1], w.shape[0], 1, 1))
-            self.__dict__["_lns_f"] = f
+            cache_of(self)["f"] = f
         return f
 
     def _fwd(self, emb_rows):
@@ -61,11 +61,11 @@ class SpectralConv2d(LnsModule):
 
     def _mode_weights(self):
         key = (self.weights1.data_ptr(), self.weights1._version, self.weights2.data_ptr(), self.weights2._version)
-        ent = self.__dict__.get("_lns_wm")
+        ent = cache_of(self).get("wm")
         if ent is None or ent[0] != key:
             w = torch.stack([self.weights1.detach(), self.weights2.detach()], 0)
             ent = (key, w.permute(0, 3, 4, 1, 2, 5).contiguous().float())
-            self.__dict__["_lns_wm"] = ent
+            cache_of(self)["wm"] = ent
         return ent[1]
 
     def _fwd(self, x, emb_rows):
