@@ -262,6 +262,15 @@ int lns_fablock_full(const void* u, int dtype, int B, int H, int W, int heads, c
                      const float* w_in_proj, const float* Kx, const float* Ky, float eps, const float* w_out1,
                      const float* w_out2, void* out, void* stream);
 
+/* lns_fablock_full with EVERY contraction on tcgen05 (csrc/fablock_tc.cu): in_proj, both axial contractions (block-diagonal
+ * kernel matrices x the pixel rows read as an MN-major operand) and both to_out convolutions are tcgen05.mma batches with
+ * TMEM -> shared-memory drains in between; a 32x32 sample runs on a cluster of two CTAs (rows exchanged through distributed
+ * shared memory), a 16x16 sample on one CTA.  Same arguments and result as lns_fablock_full; covers H == W in {16, 32}. */
+int lns_fablock_tc_supported(int H, int W, int dim, int dim_head, int dim_out);
+int lns_fablock_tc(const void* u, int dtype, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
+                   const float* w_in_proj, const float* Kx, const float* Ky, float eps, const float* w_out1,
+                   const float* w_out2, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * layout / misc
  * ------------------------------------------------------------------------------------------------ */

@@ -69,6 +69,8 @@ SIGNATURES = {
     "lns_fa_axis_kernel": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp, vp]),
     "lns_fablock_full_supported": (i32, [i32, i32, i32, i32, i32]),
     "lns_fablock_full": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp]),
+    "lns_fablock_tc_supported": (i32, [i32, i32, i32, i32, i32]),
+    "lns_fablock_tc": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp]),
     "lns_nchw_to_nhwc": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i64, vp]),
     "lns_nhwc_to_nchw": (i32, [vp, i32, i32, i32, i32, i32, i64, vp, i64, vp]),
     "lns_frame_sums": (i32, [vp, vp, i64, i32, vp, vp]),

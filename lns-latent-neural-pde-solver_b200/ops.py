@@ -47,6 +47,7 @@ class _State(threading.local):
         self.hi_scale = float(os.environ.get("LNS_HI_SCALE", "1"))  # experiment: 4 = one more resolution level in the hi region
         self.hi_wsplit = os.environ.get("LNS_HI_WSPLIT", "1") != "0"  # hi layers also split the filter (3 MMAs instead of 2)
         self.coarse = os.environ.get("LNS_COARSE", "1") != "0"        # use the block-halo engine (conv_coarse.cu) where it applies
+        self.fablock_tc = os.environ.get("LNS_FABLOCK_TC", "1") != "0"  # FABlock2D on tcgen05 (fablock_tc.cu) where it applies
 
 
 def _mark(label, flops=0.0, nbytes=0.0):
@@ -823,6 +824,29 @@ def fa_axis_kernel(pooled, heads, w1t, ln_g, ln_b, ln_eps, wf1t, wf2t, bf2, wqk1
 def fablock_full_supported(x, dim_head, dim_out):
     return (x.t.dtype in H16_DTYPES and x.layout == NHWC and x.contiguous
             and bool(_C.lib().lns_fablock_full_supported(x.H, x.W, x.C, dim_head, dim_out)))
+
+
+def fablock_tc_supported(x, dim_head, dim_out):
+    return (_state.fablock_tc and x.t.dtype in H16_DTYPES and x.layout == NHWC and x.contiguous
+            and bool(_C.lib().lns_fablock_tc_supported(x.H, x.W, x.C, dim_head, dim_out)))
+
+
+def fablock_tc(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps, w_out1, w_out2):
+    """fablock_full with every contraction on tcgen05 (csrc/fablock_tc.cu; 16x16 and 32x32 samples)."""
+    out = u.like()
+    wi = w_in_proj.detach().float().contiguous()
+    w1 = w_out1.detach().float().reshape(w_out1.shape[0], -1).contiguous()
+    w2 = w_out2.detach().float().reshape(w_out2.shape[0], -1).contiguous()
+    hw_ = u.H * u.W
+    tok = _mark(f"fablock_tc @{u.H}x{u.W}",
+                flops=u.B * (2.0 * hw_ * 64 * heads * 64 * 2 + 2.0 * heads * (u.H * u.H * u.W + u.H * u.W * u.W) * 64 + 2.0 * hw_ * 64 * 64),
+                nbytes=_abytes(u, out) + 4.0 * u.B * heads * (u.H * u.H + u.W * u.W))
+    rc = _C.lib().lns_fablock_tc(_ptr(u.t), u.dtype, u.B, u.H, u.W, heads, _ptr(gn_scale), _ptr(gn_shift), _ptr(wi), _ptr(Kx),
+                                 _ptr(Ky), float(eps), _ptr(w1), _ptr(w2), _ptr(out.t), _stream())
+    check(rc, "lns_fablock_tc")
+    _done(tok)
+    _state.launches += 1
+    return out
 
 
 def fablock_full(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps, w_out1, w_out2):

@@ -169,7 +169,10 @@ class SABlock(LnsModule):
                                      None if pe is None else o["pe"], o["wqkv"], o["bv"], o["wproj"], o["bproj"],
                                      self.dim_head ** (-0.5))
         t = ops.layernorm(x, self.ln.weight, self.ln.bias, self.ln.eps, pe=pe)
-        qkv = ops.conv2d(t, self._qkv_filter())
+        # on the 16-bit paths q|k|v stay 16-bit whatever the surrounding stage stores (the split-operand mode keeps the coarse
+        # stage in fp32): the tensor-core attention kernel takes 16-bit rows, and the block contributes < 1 % of the 16-bit error
+        # (tools/precision_study.py) -- an fp32 q|k|v would drop to the CUDA-core attention kernel (30x slower at 288 tokens)
+        qkv = ops.conv2d(t, self._qkv_filter(), out_dtype=ops.act_dtype() if ops.fast16() else None)
         o = ops.attention(qkv, self.heads, self.dim_head, self.dim_head ** (-0.5))
         return ops.conv2d(o, filt_of(self.proj_out), residual=x)
 

@@ -188,7 +188,11 @@ class FABlock2D(LnsModule):
         if (fused and self.to_out[1].bias is None and self.to_out[3].bias is None
                 and ops.fablock_full_supported(u, self.dim_head, self.to_out[3].out_channels)
                 and self.to_out[1].out_channels == 64):
-            # everything up to the block output in one kernel per sample: to_out's convs on tcgen05, accumulators in TMEM
+            # everything up to the block output in one kernel per sample, accumulators in TMEM: all contractions on tcgen05
+            # (16x16 / 32x32), else the mma.sync phases + tcgen05 to_out convs
+            if ops.fablock_tc_supported(u, self.dim_head, self.to_out[3].out_channels):
+                return ops.fablock_tc(u, s, t, self.in_proj.weight, k_x, k_y, self.heads, inorm.eps, self.to_out[1].weight,
+                                      self.to_out[3].weight)
             return ops.fablock_full(u, s, t, self.in_proj.weight, k_x, k_y, self.heads, inorm.eps, self.to_out[1].weight,
                                     self.to_out[3].weight)
         if fused:

@@ -974,3 +974,39 @@ def test_conv_coarse_fp32_split(case, wsplit):
                        out_dtype=torch.float32)
     torch.cuda.synchronize()
     assert relerr(act_to_nchw(y), ref) < 3e-6
+
+
+# ---- FABlock2D with every contraction on tcgen05 (csrc/fablock_tc.cu) -----------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("n,B", [(16, 5), (32, 3), (32, 300)])
+def test_fablock_tc_vs_full_and_oracle(n, B, prec):
+    """tcgen05 whole-block kernel (block-diagonal axial GEMMs, MN-major pixel rows, 2-CTA cluster at 32x32) vs the fp64 oracle
+    of the reference block and vs the mma.sync whole-block kernel"""
+    ops = ops_mod()
+    import lns_oracle as O
+    from modules.factorized_attention import FABlock2D
+    dt = torch.float16 if prec == "fp16" else torch.bfloat16
+    torch.manual_seed(3)
+    blk = FABlock2D(64, 64, 64, 8, 64).to(DEV).eval()
+    g = torch.Generator().manual_seed(45)
+    x = torch.randn(B, 64, n, n, generator=g)
+    a = act_from(x, dt)
+    assert ops.fablock_tc_supported(a, 64, 64)
+    with torch.no_grad(), ops.precision(prec):
+        tc = act_to_nchw(blk._fwd(a))
+        ops._state.fablock_tc = False
+        try:
+            full = act_to_nchw(blk._fwd(a))
+        finally:
+            ops._state.fablock_tc = True
+    nb = min(B, 4)
+    sd = {k: v.cpu().double() for k, v in blk.state_dict().items()}
+    ref = O.fa_block(x[:nb].double(), O.SD(sd))
+    e_tc, e_full = relerr(tc[:nb], ref), relerr(full[:nb], ref)
+    print(f"[FABlock2D {n}x{n} {prec} B={B}] tcgen05 kernel vs fp64 oracle {e_tc:.2e}, mma.sync kernel {e_full:.2e}, tc vs full "
+          f"{relerr(tc, full):.2e}")
+    tol = 4e-3 if prec == "fp16" else 3e-2
+    assert e_tc < tol and relerr(tc, full) < tol
+    # every sample, not only the first ones: per-sample error against the other kernel
+    per = ((tc - full).flatten(1).norm(dim=1) / full.flatten(1).norm(dim=1)).max().item()
+    assert per < tol
