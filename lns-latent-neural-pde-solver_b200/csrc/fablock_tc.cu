@@ -44,7 +44,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy shared-memory writes (this CTA's, or a peer's that a cluster barrier has made visible) -> async proxy (tcgen05.mma).
+// (The unqualified `fence.proxy.async` compiles to MEMBAR.ALL.GPU + the fence: 7 % of the kernel's stall samples in the first profile.)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
@@ -174,10 +176,12 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
   constexpr uint32_t kTmemCols = 2 * T * 64;  // scratch [0, T*64) | to_out accumulator [T*64, 2*T*64)
 
   if (tid == 0) {
-    tptx::mbar_init(barA, 1);
-    tptx::mbar_init(barB, 1);
-    tptx::mbar_init(barC, 1);
-    tptx::mbar_init(barE, 1);
+    // one MMA-issuing thread per 128-row tile (lane 0 of the tile's first warp): the T instruction streams run in parallel, every
+    // phase barrier collects T tcgen05.commit arrivals
+    tptx::mbar_init(barA, T);
+    tptx::mbar_init(barB, T);
+    tptx::mbar_init(barC, T);
+    tptx::mbar_init(barE, T);
     tptx::fence_mbar_init();
   }
   if (warp == 0) {
@@ -220,17 +224,24 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
   };
   // block-diagonal [128 x 128] of the N x N kernel Kmat (fp32, row-major [i][j]) as a K-major A operand in two 64-column slabs
   auto build_bd = [&](uint32_t dst, const float* Kmat) {
-    for (int e = tid; e < 128 * 16; e += NTHR) {
-      const int r = e >> 4, kc = e & 15;
+    constexpr int NIT = 128 * 16 / NTHR;  // 16-byte chunks per thread; all global loads are issued before the first store
+    float4 ka[NIT], kb[NIT];
+#pragma unroll
+    for (int q = 0; q < NIT; ++q) {
+      const int e = tid + q * NTHR, r = e >> 4, kc = e & 15;
       const int line = r / N, i = r - line * N;
       const int kline = (kc * 8) / N, j0 = kc * 8 - kline * N;
-      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+      ka[q] = kb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (kline == line) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(Kmat + i * N + j0));
-        const float4 c = __ldg(reinterpret_cast<const float4*>(Kmat + i * N + j0 + 4));
-        w0 = pack2_h16<F16>(a.x, a.y); w1 = pack2_h16<F16>(a.z, a.w); w2 = pack2_h16<F16>(c.x, c.y); w3 = pack2_h16<F16>(c.z, c.w);
+        ka[q] = __ldg(reinterpret_cast<const float4*>(Kmat + i * N + j0));
+        kb[q] = __ldg(reinterpret_cast<const float4*>(Kmat + i * N + j0 + 4));
       }
-      tptx::st_shared_v4(dst + (uint32_t)(kc >> 3) * 16384u + row_off(r, kc & 7), w0, w1, w2, w3);
+    }
+#pragma unroll
+    for (int q = 0; q < NIT; ++q) {
+      const int e = tid + q * NTHR, r = e >> 4, kc = e & 15;
+      tptx::st_shared_v4(dst + (uint32_t)(kc >> 3) * 16384u + row_off(r, kc & 7), pack2_h16<F16>(ka[q].x, ka[q].y), pack2_h16<F16>(ka[q].z, ka[q].w),
+                         pack2_h16<F16>(kb[q].x, kb[q].y), pack2_h16<F16>(kb[q].z, kb[q].w));
     }
   };
   // descriptor halves: K-major SWIZZLE_128B (8-row groups 1024 B apart) -- also the MN-major form (SBO = 1024, LBO unused)
@@ -268,6 +279,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
 
   const int tile = warp >> 2, quad = warp & 3;
   const int m = quad * 32 + lane;  // accumulator row of this thread in its tile
+  const bool issuer = quad == 0 && lane == 0;  // issues this tile's MMAs
 
   for (int h = 0; h < heads; ++h) {
     const uint32_t X = base + ((h & 1) ? oQ : oP), Y = base + ((h & 1) ? oP : oQ);
@@ -278,15 +290,12 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     tptx::tc_fence_before();
     __syncthreads();
     // ---- phase A: u_phi = raw x Ws^T -> scratch ----
-    if (tid == 0) {
+    if (issuer) {
       tptx::tc_fence_after();
       const uint32_t b_lo = lo16(base + oWs);
+      const uint32_t a_lo = lo16(X + (uint32_t)tile * 16384u);
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const uint32_t a_lo = lo16(X + (uint32_t)t * 16384u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tptx::umma_lohi(tmem + (uint32_t)(t * 64), a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc_kk, k != 0);
-      }
+      for (int k = 0; k < 4; ++k) tptx::umma_lohi(tmem + (uint32_t)(tile * 64), a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc_kk, k != 0);
       tptx::umma_commit(barA);
     }
     __syncwarp();
@@ -309,20 +318,19 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     tptx::tc_fence_before();
     __syncthreads();  // S2
     // ---- phase B: contraction over image rows (lines = image columns): scratch = blockdiag(Kx) x X ----
-    if (tid == 0) {
+    if (issuer) {
       tptx::tc_fence_after();
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t a_lo = lo16(base + oBD0 + (uint32_t)(ks >> 2) * 16384u) + 2u * (ks & 3);
-          const uint32_t b_lo = lo16(X + (uint32_t)t * 16384u + (uint32_t)ks * 2048u);
-          tptx::umma_lohi(tmem + (uint32_t)(t * 64), a_lo, desc_hi, b_lo, desc_hi, idesc_kmn, ks != 0);
-        }
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t a_lo = lo16(base + oBD0 + (uint32_t)(ks >> 2) * 16384u) + 2u * (ks & 3);
+        const uint32_t b_lo = lo16(X + (uint32_t)tile * 16384u + (uint32_t)ks * 2048u);
+        tptx::umma_lohi(tmem + (uint32_t)(tile * 64), a_lo, desc_hi, b_lo, desc_hi, idesc_kmn, ks != 0);
       }
       tptx::umma_commit(barB);
     }
     __syncwarp();
+    // while the tensor core works: the next head's in_proj slice (Ws / bias are no longer read: barA has completed, drain A is over)
+    if (h + 1 < heads) build_ws(h + 1);
     // Y is the buffer phase E of the previous head read (its V rows): free once that GEMM has completed -- here and in the peer
     if (h > 0) {
       tptx::mbar_wait(barE, (uint32_t)((h - 1) & 1));
@@ -365,25 +373,19 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     }
     tptx::fence_proxy_async();  // (the peer's stores came through the generic proxy)
     // ---- phase C: contraction over image columns (lines = image rows): scratch = blockdiag(Ky) x Y ----
-    if (tid == 0) {
+    if (issuer) {
       tptx::tc_fence_after();
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t a_lo = lo16(base + oBD1 + (uint32_t)(ks >> 2) * 16384u) + 2u * (ks & 3);
-          const uint32_t b_lo = lo16(Y + (uint32_t)t * 16384u + (uint32_t)ks * 2048u);
-          tptx::umma_lohi(tmem + (uint32_t)(t * 64), a_lo, desc_hi, b_lo, desc_hi, idesc_kmn, ks != 0);
-        }
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t a_lo = lo16(base + oBD1 + (uint32_t)(ks >> 2) * 16384u) + 2u * (ks & 3);
+        const uint32_t b_lo = lo16(Y + (uint32_t)tile * 16384u + (uint32_t)ks * 2048u);
+        tptx::umma_lohi(tmem + (uint32_t)(tile * 64), a_lo, desc_hi, b_lo, desc_hi, idesc_kmn, ks != 0);
       }
       tptx::umma_commit(barC);
     }
     __syncwarp();
-    // while the tensor core works: the next head's in_proj slice and row kernel (Ws, bias, BD0 are no longer read: barA, barB)
-    if (h + 1 < heads) {
-      build_ws(h + 1);
-      build_bd(base + oBD0, p.Kx + ((int64_t)b * heads + h + 1) * N * N);
-    }
+    // while the tensor core works: the next head's row kernel (BD0 is no longer read: barB has completed)
+    if (h + 1 < heads) build_bd(base + oBD0, p.Kx + ((int64_t)b * heads + h + 1) * N * N);
     tptx::mbar_wait(barC, par);
     tptx::tc_fence_after();
     {  // drain C: 16-bit V rows into X (free: phase B has read it) + per-channel (sum, sum of squares) of the ROUNDED values.
@@ -419,9 +421,14 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     }
     tptx::tc_fence_before();
     __syncthreads();  // S4: Y and BD1 are free (phase C has completed), V rows and the partial statistics are written
-    if (h + 1 < heads) {
-      load_raw(Y);  // next head's raw input (Y is next head's X)
-      build_bd(base + oBD1, p.Ky + ((int64_t)b * heads + h + 1) * N * N);
+    if (h + 1 < heads) load_raw(Y);  // next head's raw input (Y is next head's X): lands during the statistics / phase E
+    // this thread's share of to_out[1]'s slice (folded below): in flight across the statistics exchange
+    float4 wo0[(64 * 8 + NTHR - 1) / NTHR], wo1[(64 * 8 + NTHR - 1) / NTHR];
+#pragma unroll
+    for (int q = 0; q < (64 * 8 + NTHR - 1) / NTHR; ++q) {
+      const int e = tid + q * NTHR, n = e >> 3, kc = e & 7;
+      wo0[q] = __ldg(reinterpret_cast<const float4*>(p.w_out1 + (int64_t)n * C + h * 64 + kc * 8));
+      wo1[q] = __ldg(reinterpret_cast<const float4*>(p.w_out1 + (int64_t)n * C + h * 64 + kc * 8 + 4));
     }
     if (tid < 128) {
       const int c = tid >> 1, which = tid & 1;
@@ -456,10 +463,10 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     }
     __syncthreads();  // S5
     // ---- phase E: fold the normalisation into to_out[1]'s slice, acc += V x W1'^T ----
-    for (int e = tid; e < 64 * 8; e += NTHR) {
-      const int n = e >> 3, kc = e & 7;
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_out1 + (int64_t)n * C + h * 64 + kc * 8));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_out1 + (int64_t)n * C + h * 64 + kc * 8 + 4));
+#pragma unroll
+    for (int q = 0; q < (64 * 8 + NTHR - 1) / NTHR; ++q) {
+      const int e = tid + q * NTHR, n = e >> 3, kc = e & 7;
+      const float4 w0 = wo0[q], w1 = wo1[q];
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
       float sc[8];
       float bsum = 0.f;
@@ -478,19 +485,18 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     tptx::fence_proxy_async();
     tptx::tc_fence_before();
     __syncthreads();  // S6
-    if (tid == 0) {
+    if (issuer) {
       tptx::tc_fence_after();
       const uint32_t b_lo = lo16(base + oWo);
+      const uint32_t a_lo = lo16(X + (uint32_t)tile * 16384u);
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const uint32_t a_lo = lo16(X + (uint32_t)t * 16384u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tptx::umma_lohi(tmem_acc + (uint32_t)(t * 64), a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc_kk, (h | k) != 0);
-      }
+      for (int k = 0; k < 4; ++k)
+        tptx::umma_lohi(tmem_acc + (uint32_t)(tile * 64), a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc_kk, (h | k) != 0);
       tptx::umma_commit(barE);
     }
     __syncwarp();
+    // while phase E runs: the next head's column kernel (BD1 is free since barC)
+    if (h + 1 < heads) build_bd(base + oBD1, p.Ky + ((int64_t)b * heads + h + 1) * N * N);
   }
 
   // ================= after the last head: GELU(acc + b1') -> to_out[3] -> + skip -> out =================
@@ -521,15 +527,12 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
   tptx::fence_proxy_async();
   tptx::tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  if (issuer) {
     tptx::tc_fence_after();
     const uint32_t b_lo = lo16(base + oBD0);
+    const uint32_t a_lo = lo16(Yl + (uint32_t)tile * 16384u);
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const uint32_t a_lo = lo16(Yl + (uint32_t)t * 16384u);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) tptx::umma_lohi(tmem + (uint32_t)(t * 64), a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc_kk, k != 0);
-    }
+    for (int k = 0; k < 4; ++k) tptx::umma_lohi(tmem + (uint32_t)(tile * 64), a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc_kk, k != 0);
     tptx::umma_commit(barA);
   }
   __syncwarp();

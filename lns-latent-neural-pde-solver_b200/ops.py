@@ -47,7 +47,10 @@ class _State(threading.local):
         self.hi_scale = float(os.environ.get("LNS_HI_SCALE", "1"))  # experiment: 4 = one more resolution level in the hi region
         self.hi_wsplit = os.environ.get("LNS_HI_WSPLIT", "1") != "0"  # hi layers also split the filter (3 MMAs instead of 2)
         self.coarse = os.environ.get("LNS_COARSE", "1") != "0"        # use the block-halo engine (conv_coarse.cu) where it applies
-        self.fablock_tc = os.environ.get("LNS_FABLOCK_TC", "1") != "0"  # FABlock2D on tcgen05 (fablock_tc.cu) where it applies
+        # FABlock2D with every contraction on tcgen05 (fablock_tc.cu): correct and tested, but its per-head chain of eight
+        # barrier-separated MMA / drain stages is latency bound at one CTA per SM -- 7.7 ms vs 5.2 ms for the mma.sync kernel at
+        # 4736 x 32x32 (profiles/r02_fablock_tc.md) -- so it is opt-in until the stages are software-pipelined
+        self.fablock_tc = os.environ.get("LNS_FABLOCK_TC", "0") != "0"
 
 
 def _mark(label, flops=0.0, nbytes=0.0):

@@ -991,14 +991,16 @@ def test_fablock_tc_vs_full_and_oracle(n, B, prec):
     g = torch.Generator().manual_seed(45)
     x = torch.randn(B, 64, n, n, generator=g)
     a = act_from(x, dt)
-    assert ops.fablock_tc_supported(a, 64, 64)
-    with torch.no_grad(), ops.precision(prec):
-        tc = act_to_nchw(blk._fwd(a))
-        ops._state.fablock_tc = False
-        try:
+    saved = ops._state.fablock_tc
+    ops._state.fablock_tc = True
+    try:
+        assert ops.fablock_tc_supported(a, 64, 64)
+        with torch.no_grad(), ops.precision(prec):
+            tc = act_to_nchw(blk._fwd(a))
+            ops._state.fablock_tc = False
             full = act_to_nchw(blk._fwd(a))
-        finally:
-            ops._state.fablock_tc = True
+    finally:
+        ops._state.fablock_tc = saved
     nb = min(B, 4)
     sd = {k: v.cpu().double() for k, v in blk.state_dict().items()}
     ref = O.fa_block(x[:nb].double(), O.SD(sd))
