@@ -305,6 +305,12 @@ int lns_channel_gate(const void* x, int dtype, int B, int HW, int C, const float
  * train_stage2_ns2d.py:254-257) of the affinely de-normalised fields follows on the host without the fields ever leaving the
  * device.  One read of both tensors, deterministic. */
 int lns_frame_sums(const float* pred, const float* target, int64_t frames, int P, float* out, void* stream);
+/* The same three sums of the DE-NORMALISED frames for datasets whose de-normalisation is not one affine map -- the two-phase
+ * dataset (dataset/twophase_flow_stage2.py:369-389): per channel c = f % C, v = x*scale[c] + shift[c]; flags[c] & 1 zeroes the
+ * four border lines (Dirichlet walls of the velocity channels); flags[c] & 2 clamps to [clamp_lo, clamp_hi] (vof).  Applied to
+ * prediction and target alike (train_stage2_twophase.py:251-252).  frames = B*K*C frames of H x W values. */
+int lns_frame_sums_denorm(const float* pred, const float* target, int64_t frames, int H, int W, int C, const float* scale,
+                          const float* shift, const int* flags, float clamp_lo, float clamp_hi, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Spectral convolution (FNO layer) as truncated DFTs with the complex mode-weight multiply fused:

@@ -74,6 +74,7 @@ SIGNATURES = {
     "lns_nchw_to_nhwc": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i64, vp]),
     "lns_nhwc_to_nchw": (i32, [vp, i32, i32, i32, i32, i32, i64, vp, i64, vp]),
     "lns_frame_sums": (i32, [vp, vp, i64, i32, vp, vp]),
+    "lns_frame_sums_denorm": (i32, [vp, vp, i64, i32, i32, i32, vp, vp, vp, f32, f32, vp, vp]),
     "lns_fourier_embedding": (i32, [vp, i32, i32, f32, vp, vp]),
     "lns_channel_gate": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp]),
     "lns_spectral_work_bytes": (i64, [i32, i32, i32, i32, i32, i32, i32]),

@@ -104,9 +104,63 @@ __global__ void __launch_bounds__(256) frame_sums_kernel(const float* __restrict
   }
 }
 
+// The same metric behind a NON-affine de-normalisation: the two-phase dataset (dataset/twophase_flow_stage2.py:369-389) scales
+// velocity and pressure with their own statistics, zeroes the velocity on the four closed walls (Dirichlet) and clamps the vof
+// channel to [0, 1 + 1e-8] -- applied to prediction AND target (train_stage2_twophase.py:251-252) before relative_lp_loss.
+// Per frame f (channel c = f % C):  v = x * scale[c] + shift[c];  flags[c] & 1: v = 0 on the border;  flags[c] & 2: clamp(v, lo, hi).
+// out[f] = (sum (p' - t')^2, sum t'^2, sum t') of the de-normalised values.  grid F, block 256, fixed-order reduction.
+__global__ void __launch_bounds__(256) frame_sums_denorm_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int C,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                const int* __restrict__ flags, float lo, float hi,
+                                                                float* __restrict__ out) {
+  __shared__ double red[8][3];
+  const int P = H * W;
+  const int64_t base = (int64_t)blockIdx.x * P;
+  const int c = (int)(blockIdx.x % (unsigned)C);
+  const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+  const int fl = __ldg(flags + c);
+  float d2 = 0.f, b2 = 0.f, b1 = 0.f;
+  for (int i = threadIdx.x; i < P; i += 256) {
+    float x = fmaf(__ldg(a + base + i), sc, sh), y = fmaf(__ldg(b + base + i), sc, sh);
+    if (fl & 1) {
+      const int r = i / W, col = i - r * W;
+      if (r == 0 || r == H - 1 || col == 0 || col == W - 1) x = y = 0.f;
+    }
+    if (fl & 2) {
+      x = fminf(fmaxf(x, lo), hi);
+      y = fminf(fmaxf(y, lo), hi);
+    }
+    d2 = fmaf(x - y, x - y, d2);
+    b2 = fmaf(y, y, b2);
+    b1 += y;
+  }
+  double s0 = warp_sum_d((double)d2), s1 = warp_sum_d((double)b2), s2 = warp_sum_d((double)b1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[warp][0] = s0;
+    red[warp][1] = s1;
+    red[warp][2] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    out[(int64_t)blockIdx.x * 3 + threadIdx.x] = (float)t;
+  }
+}
+
 }  // namespace lns
 
 extern "C" {
+
+int lns_frame_sums_denorm(const float* pred, const float* target, int64_t frames, int H, int W, int C, const float* scale,
+                          const float* shift, const int* flags, float clamp_lo, float clamp_hi, float* out, void* stream) {
+  LNS_REQUIRE(pred && target && out && scale && shift && flags && frames > 0 && H > 0 && W > 0 && C > 0 && frames < (1ll << 31) &&
+                  frames % C == 0, "lns_frame_sums_denorm: bad arguments");
+  lns::frame_sums_denorm_kernel<<<(unsigned)frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, target, H, W, C, scale, shift,
+                                                                                                     flags, clamp_lo, clamp_hi, out);
+  return lns::check_launch("frame_sums_denorm_kernel");
+}
 
 int lns_frame_sums(const float* pred, const float* target, int64_t frames, int P, float* out, void* stream) {
   LNS_REQUIRE(pred && target && out && frames > 0 && P > 0 && frames < (1ll << 31), "lns_frame_sums: bad arguments");

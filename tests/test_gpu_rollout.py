@@ -409,3 +409,73 @@ def test_ops_reject_a_tensor_of_another_device_context():
             ops.Act(t1, 1, 1, 2, 4)
         with ops.device_of(t1):
             ops.Act(t1, 1, 1, 2, 4)
+
+
+def test_relative_l2_twophase_matches_reference_denormalize():
+    """SURVEY 8(f) row 2, two-phase: the fused metric == relative_lp_loss(denormalize(y_hat), denormalize(y)) with the reference's
+    denormalize restated in fp64 (dataset/twophase_flow_stage2.py:369-389: per-field statistics, Dirichlet walls, vof clamp)"""
+    from lns_b200 import metrics
+    g = torch.Generator().manual_seed(27)
+    gt = torch.randn(3, 5, 4, 61, 121, generator=g)
+    gt[:, :, 3] = torch.rand(3, 5, 61, 121, generator=g) * 1.2 - 0.1  # vof partly outside [0, 1]: the clamp matters
+    pred = gt + 0.05 * torch.randn(3, 5, 4, 61, 121, generator=g)
+    st = dict(vel_mean=0.013, vel_std=0.41, prs_mean=101.3, prs_std=7.9)
+
+    def denorm(x):
+        x = x.double().clone()
+        x[..., :2, :, :] = x[..., :2, :, :] * st["vel_std"] + st["vel_mean"]
+        x[..., :2, 0, :] = 0.
+        x[..., :2, -1, :] = 0.
+        x[..., :2, :, 0] = 0.
+        x[..., :2, :, -1] = 0.
+        x[..., 2, :, :] = x[..., 2, :, :] * st["prs_std"] + st["prs_mean"]
+        x[..., 3, :, :] = torch.clamp(x[..., 3, :, :], 0., 1. + 1e-8)
+        return x
+    a, b = denorm(pred), denorm(gt)
+
+    def ref(reduce_dim):
+        gt_norm = (b ** 2).sum(dim=reduce_dim).clamp_min(1e-8)
+        return (((a - b) ** 2).sum(dim=reduce_dim) / gt_norm).sqrt()
+    frame, seq = metrics.relative_l2_twophase(pred.to(DEV), gt.to(DEV), **st)
+    assert torch.allclose(frame.cpu().double(), ref((3, 4)), rtol=3e-5, atol=0)
+    assert torch.allclose(seq.cpu().double(), ref((1, 3, 4)), rtol=3e-5, atol=0)
+
+
+def test_checkpoint_file_round_trip(tmp_path):
+    """a state_dict written with torch.save loads through the reference's own entry point
+    ``SimpleAutoencoder.load_checkpoint(path)`` (strict=True) and reproduces the encoder / decoder bit for bit"""
+    ops = ops_mod()
+    from modules.autoencoder2d import SimpleAutoencoder
+    cfg, model, _ = build("ns2d")
+    path = os.path.join(tmp_path, "ae.pt")
+    torch.save(model.autoencoder.state_dict(), path)
+    torch.manual_seed(99)
+    ae = SimpleAutoencoder(cfg).to(DEV).eval()   # different random init ...
+    ae.load_checkpoint(path)                     # ... replaced by the checkpoint
+    x, _ = O.make_inputs(cfg, 3, seed=35)
+    with torch.no_grad(), ops.precision("fp32"):
+        z0, z1 = model.autoencoder.encode(x.to(DEV)), ae.encode(x.to(DEV))
+        y0, y1 = model.autoencoder.decode(z0), ae.decode(z1)
+    assert torch.equal(z0, z1) and torch.equal(y0, y1)
+    # the whole LatentDynamics too (strict key match both ways)
+    full = os.path.join(tmp_path, "model.pt")
+    torch.save(model.state_dict(), full)
+    from lns_b200.latent_dynamics import LatentDynamics
+    m2 = LatentDynamics(cfg).eval()
+    missing, unexpected = m2.load_state_dict(torch.load(full, map_location="cpu"), strict=True)
+    assert not missing and not unexpected
+
+
+@pytest.mark.parametrize("name", ["ns2d", "twophase_cond"])
+def test_unmodified_reference_script_runs_through_rollout(name):
+    """the UNMODIFIED stage-2 script (its own LatentDynamics / SimpleCNN classes, its YAML) with this
+    repository first on sys.path builds on the drop-in modules and rolls out through Rollout == the repository's own model"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not (os.path.isdir("/root/reference/modules") or os.path.isdir(os.path.join(root, "oracle", "_ref", "modules"))):
+        pytest.skip("reference tree not staged (oracle/vendor_ref.py)")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "run_unmodified_script.py"), name], capture_output=True, text=True,
+                       timeout=600)
+    print(r.stdout[-800:], r.stderr[-1500:])
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK")
