@@ -88,10 +88,11 @@ def lib():
     """The loaded library; raises if it has not been built (no CPU / eager fallback exists)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            raise LnsError(f"{LIB} is missing: build it with `python __graft_entry__.py` "
+        path = os.environ.get("LNS_B200_LIB", LIB)  # (instrumented builds for tools/; the product loads the in-tree library)
+        if not os.path.exists(path):
+            raise LnsError(f"{path} is missing: build it with `python __graft_entry__.py` "
                            "(lns_b200 has no CPU or PyTorch-eager fallback)")
-        l = ctypes.CDLL(LIB)
+        l = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)  # AttributeError if the symbol is not exported
             fn.restype = res

@@ -110,6 +110,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 }  // namespace tptx
 
+// -DLNS_TC_TRACE: thread 0 of CTA 0 records clock64() at every stage boundary of the first heads into p.trace (tools only)
+#ifdef LNS_TC_TRACE
+#define TC_MARK(id) do { if (blockIdx.x == 0 && tid == 0 && p.trace && h < 4) p.trace[h * 16 + (id)] = clock64(); } while (0)
+#else
+#define TC_MARK(id) do { } while (0)
+#endif
+
 namespace {
 struct TcParams {
   const uint16_t* u;       // [B][n][n][64] 16-bit
@@ -123,6 +130,7 @@ struct TcParams {
   const float* w_out2;     // [64][64]
   float eps;
   int heads;
+  long long* trace;        // LNS_TC_TRACE builds only
 };
 
 __device__ __forceinline__ uint32_t row_off(int r, int chunk) { return (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4); }
@@ -284,11 +292,13 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
   for (int h = 0; h < heads; ++h) {
     const uint32_t X = base + ((h & 1) ? oQ : oP), Y = base + ((h & 1) ? oP : oQ);
     const uint32_t par = (uint32_t)(h & 1);
+    TC_MARK(0);
     // ---- S1: raw(h) has landed in X; Ws / bias / BD0 / BD1 of head h are written ----
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     tptx::fence_proxy_async();
     tptx::tc_fence_before();
     __syncthreads();
+    TC_MARK(1);
     // ---- phase A: u_phi = raw x Ws^T -> scratch ----
     if (issuer) {
       tptx::tc_fence_after();
@@ -301,6 +311,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     __syncwarp();
     tptx::mbar_wait(barA, par);
     tptx::tc_fence_after();
+    TC_MARK(2);
     {  // drain A: + bias -> 16-bit -> the same rows of X (the MMAs that read them have completed)
       float v[64];
       ld_row(tmem, tile * 64, quad, v);
@@ -317,6 +328,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     tptx::fence_proxy_async();
     tptx::tc_fence_before();
     __syncthreads();  // S2
+    TC_MARK(3);
     // ---- phase B: contraction over image rows (lines = image columns): scratch = blockdiag(Kx) x X ----
     if (issuer) {
       tptx::tc_fence_after();
@@ -331,6 +343,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     __syncwarp();
     // while the tensor core works: the next head's in_proj slice (Ws / bias are no longer read: barA has completed, drain A is over)
     if (h + 1 < heads) build_ws(h + 1);
+    TC_MARK(4);
     // Y is the buffer phase E of the previous head read (its V rows): free once that GEMM has completed -- here and in the peer
     if (h > 0) {
       tptx::mbar_wait(barE, (uint32_t)((h - 1) & 1));
@@ -342,6 +355,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     }
     tptx::mbar_wait(barB, par);
     tptx::tc_fence_after();
+    TC_MARK(5);
     {  // drain B: row (line xl, image row i) -> row il*N + x of the buffer Y of the CTA that owns image row i (transposed)
       float v[64];
       ld_row(tmem, tile * 64, quad, v);
@@ -372,6 +386,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
       __syncthreads();
     }
     tptx::fence_proxy_async();  // (the peer's stores came through the generic proxy)
+    TC_MARK(6);
     // ---- phase C: contraction over image columns (lines = image rows): scratch = blockdiag(Ky) x Y ----
     if (issuer) {
       tptx::tc_fence_after();
@@ -388,6 +403,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     if (h + 1 < heads) build_bd(base + oBD0, p.Kx + ((int64_t)b * heads + h + 1) * N * N);
     tptx::mbar_wait(barC, par);
     tptx::tc_fence_after();
+    TC_MARK(7);
     {  // drain C: 16-bit V rows into X (free: phase B has read it) + per-channel (sum, sum of squares) of the ROUNDED values.
        // Two passes over the thread's TMEM row (a second tcgen05.ld is cheaper than keeping 128 values live at 512 threads).
       float v[64];
@@ -421,6 +437,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     }
     tptx::tc_fence_before();
     __syncthreads();  // S4: Y and BD1 are free (phase C has completed), V rows and the partial statistics are written
+    TC_MARK(8);
     if (h + 1 < heads) load_raw(Y);  // next head's raw input (Y is next head's X): lands during the statistics / phase E
     // this thread's share of to_out[1]'s slice (folded below): in flight across the statistics exchange
     float4 wo0[(64 * 8 + NTHR - 1) / NTHR], wo1[(64 * 8 + NTHR - 1) / NTHR];
@@ -444,6 +461,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
     } else {
       __syncthreads();
     }
+    TC_MARK(9);
     if (tid < 64) {
       double sm = (double)part_s[tid * 2], ss = (double)part_s[tid * 2 + 1];
       if (CL > 1) {
@@ -462,6 +480,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
       stat_s[tid * 2 + 1] = (float)(-mean * rstd);
     }
     __syncthreads();  // S5
+    TC_MARK(10);
     // ---- phase E: fold the normalisation into to_out[1]'s slice, acc += V x W1'^T ----
 #pragma unroll
     for (int q = 0; q < (64 * 8 + NTHR - 1) / NTHR; ++q) {
@@ -495,6 +514,7 @@ __device__ __forceinline__ void fablock_tc_body(const TcParams& p) {
       tptx::umma_commit(barE);
     }
     __syncwarp();
+    TC_MARK(11);
     // while phase E runs: the next head's column kernel (BD1 is free since barC)
     if (h + 1 < heads) build_bd(base + oBD1, p.Ky + ((int64_t)b * heads + h + 1) * N * N);
   }
@@ -610,6 +630,15 @@ int lns_fablock_tc(const void* u, int dtype, int B, int H, int W, int heads, con
   p.out = reinterpret_cast<uint16_t*>(out);
   p.gn_scale = gn_scale; p.gn_shift = gn_shift; p.w_in = w_in_proj; p.Kx = Kx; p.Ky = Ky;
   p.w_out1 = w_out1; p.w_out2 = w_out2; p.eps = eps; p.heads = heads;
+  p.trace = nullptr;
+#ifdef LNS_TC_TRACE
+  {
+    static long long* dbg = nullptr;
+    if (!dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
+    p.trace = dbg;
+    cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), reinterpret_cast<cudaStream_t>(stream));
+  }
+#endif
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool f16 = dtype == LNS_F16;
   if (H == 16) {
@@ -631,6 +660,21 @@ int lns_fablock_tc(const void* u, int dtype, int B, int H, int W, int heads, con
       lns::fablock_tc32_kernel<false><<<2 * B, 512, smem, st>>>(p);
     }
   }
+#ifdef LNS_TC_TRACE
+  {
+    long long hbuf[64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf, p.trace, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    static int printed = 0;
+    if (printed++ < 2)
+      for (int h = 0; h < 4; ++h) {
+        fprintf(stderr, "fablock_tc trace head %d (%dx%d):", h, H, W);
+        for (int i = 1; i < 12; ++i) fprintf(stderr, " s%d->%d %lld", i - 1, i, hbuf[h * 16 + i] - hbuf[h * 16 + i - 1]);
+        if (h < 3) fprintf(stderr, " | to next head %lld", hbuf[(h + 1) * 16] - hbuf[h * 16 + 11]);
+        fprintf(stderr, "\n");
+      }
+  }
+#endif
   return lns::check_launch("fablock_tc_kernel");
 }
 

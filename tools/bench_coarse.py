@@ -39,7 +39,11 @@ def timed(fn, reps=10):
 
 
 def main():
+    only = os.environ.get("BENCH_COARSE_ONLY")       # substring of the shape name
+    only_cand = os.environ.get("BENCH_COARSE_CAND")  # substring of the candidate label
     for name, B, Cin, Cout, H, W, dil, modes, virt in SHAPES:
+        if only and only not in name:
+            continue
         w = torch.nn.Parameter(torch.randn(Cout, Cin, 3, 3, device=DEV) / math.sqrt(9 * Cin))
         b = torch.nn.Parameter(torch.zeros(Cout, device=DEV))
         filt = ops.PackedFilter.of(w, b)
@@ -58,6 +62,8 @@ def main():
             if (H, W) == (8, 8) and virt is None and modes == (1, 1) and Cin == 128 and Cout == 128:
                 cands.insert(0, ("latent f16", x16, ops.ENGINE_LATENT, False, torch.float16))
             for label, x, eng, split, odt in cands:
+                if only_cand and only_cand not in label:
+                    continue
                 if eng == ops.ENGINE_COARSE and not ops._coarse_fits(Cin, Cout, dil, x.t.dtype == torch.float32, split):
                     continue
                 out = ops.Act.empty(B, Ho, Wo, Cout, odt, DEV)
