@@ -42,7 +42,7 @@ def main():
     only = os.environ.get("BENCH_COARSE_ONLY")       # substring of the shape name
     only_cand = os.environ.get("BENCH_COARSE_CAND")  # substring of the candidate label
     for name, B, Cin, Cout, H, W, dil, modes, virt in SHAPES:
-        if only and only not in name:
+        if only and only != name:
             continue
         w = torch.nn.Parameter(torch.randn(Cout, Cin, 3, 3, device=DEV) / math.sqrt(9 * Cin))
         b = torch.nn.Parameter(torch.zeros(Cout, device=DEV))
