@@ -325,6 +325,35 @@ int64_t lns_spectral_work_bytes(int B, int H, int W, int Ci, int Co, int m1, int
 int lns_spectral_conv2d(const void* x, int x_dtype, int B, int H, int W, int Ci, int Co, int m1, int m2,
                         const float* w_modes, const float* emb, void* work, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Backward kernels of the latent propagator: the training rollout LatentDynamics.forward(z_in, z_out, loss_fn)
+ * (train_stage2_ns2d.py:126-141; SW / two-phase scripts :126-142) back-propagates through t_out steps of SimpleCNN
+ * (train_stage2_ns2d.py:25-87).  These replace what autograd derives from F.conv2d / F.group_norm / F.gelu there.
+ * The DATA gradient of a same-size stride-1 convolution is lns_conv2d with the flipped, transposed filter; everything
+ * else is below.  fp32 NHWC activations; all sums in a fixed order (split partials + ordered reduction, no atomics).
+ *
+ * lns_conv2d_wgrad: dW[o][i][ky][kx] (OIHW fp32, ACCUMULATED into) += sum_{b,y,x} dy[b][y][x][o] *
+ *   pro(x)[b][src(y + ky*dil - pad_t, x + kx*dil - pad_l)][i], where src() is lns_conv2d's index map (zeros / circular per
+ *   axis) and pro = the forward's gather prologue act(x*scale[b][i] + shift[b][i]) (scale/shift NULL: none).  Needs
+ *   2*pad == dil*(k-1), Cin % 4 == 0, Cout % 4 == 0.  work: lns_conv2d_wgrad_work_bytes() bytes of scratch.
+ * lns_chan_sum_accum: grad[c] += sum_{b,pix} dy[b][pix][c]                       (bias gradient)
+ * lns_act_bwd: dx = dy * act'(pre) elementwise (LNS_ACT_GELU exact erf, LNS_ACT_SILU)
+ * lns_group_norm_bwd: x, dy -> dx (+ dskip if not NULL) for GroupNorm(G, C, eps) with weight gamma (NULL: ones); the
+ *   statistics are recomputed from x.  dgamma_part / dbeta_part: [B][C] per-sample partials (both NULL: skipped).
+ *   C must divide 256.
+ * lns_batch_sum_accum: grad[c] += sum_b part[b][c]
+ * ------------------------------------------------------------------------------------------------ */
+int64_t lns_conv2d_wgrad_work_bytes(int B, int H, int W, int Cin, int Cout, int KH, int KW);
+int lns_conv2d_wgrad(const float* x, int64_t x_bstride, const float* pro_scale, const float* pro_shift, int pro_act,
+                     const float* dy, int64_t dy_bstride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int dil,
+                     int pad_t, int pad_l, int pad_mode_h, int pad_mode_w, float* work, float* dW, void* stream);
+int lns_chan_sum_accum(const float* dy, int64_t bstride, int B, int HW, int C, float* grad, void* stream);
+int lns_act_bwd(const float* dy, const float* pre, int64_t n, int act, float* dx, void* stream);
+int lns_group_norm_bwd(const float* x, int64_t x_bstride, const float* dy, int64_t dy_bstride, const float* dskip,
+                       int64_t dskip_bstride, int B, int HW, int C, int G, float eps, const float* gamma, float* dx,
+                       int64_t dx_bstride, float* dgamma_part, float* dbeta_part, void* stream);
+int lns_batch_sum_accum(const float* part, int B, int C, float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -871,6 +871,75 @@ def fablock_full(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps, w_out1, w
     return out
 
 
+# ---- backward kernels (training rollout; csrc/backward.cu) ---------------------------------------------------------
+def _f32_nhwc(a, what):
+    if a.layout != NHWC or a.t.dtype != torch.float32 or a.tf32:
+        raise LnsError(f"{what}: fp32 NHWC activations only")
+
+
+def conv2d_wgrad(x, dy, dW, *, KH, KW, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, PAD_ZEROS), pro=None):
+    """dW (torch fp32 [Cout,Cin,KH,KW], accumulated into) += filter gradient of the same-size stride-1 conv whose forward read
+    pro(x) (pro = (scale[B,Cin] | None, shift | None, act)) and whose output gradient is dy.  (lns_conv2d_wgrad)"""
+    _f32_nhwc(x, "conv2d_wgrad")
+    _f32_nhwc(dy, "conv2d_wgrad")
+    if (x.B, x.H, x.W) != (dy.B, dy.H, dy.W) or tuple(dW.shape) != (dy.C, x.C, KH, KW) or not dW.is_contiguous():
+        raise LnsError("conv2d_wgrad: shape mismatch")
+    nbytes = _C.lib().lns_conv2d_wgrad_work_bytes(x.B, x.H, x.W, x.C, dy.C, KH, KW)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=x.t.device)
+    sc, sh, pa = pro if pro is not None else (None, None, ACT_NONE)
+    tok = _mark(f"wgrad {KH}x{KW} d{dil} {x.C}->{dy.C} @{x.H}x{x.W}", flops=2.0 * x.B * x.H * x.W * dy.C * KH * KW * x.C,
+                nbytes=_abytes(x, dy))
+    rc = _C.lib().lns_conv2d_wgrad(_ptr(x.t), x.bstride, _ptr(sc), _ptr(sh), pa, _ptr(dy.t), dy.bstride, x.B, x.H, x.W, x.C, dy.C,
+                                   KH, KW, dil, pad[0], pad[2], pad_mode[0], pad_mode[1], _ptr(work), _ptr(dW), _stream())
+    check(rc, "lns_conv2d_wgrad")
+    _done(tok)
+    _state.launches += 2
+
+
+def chan_sum_accum(dy, grad):
+    """grad[c] += sum over samples and pixels of dy (bias gradient)."""
+    _f32_nhwc(dy, "chan_sum_accum")
+    rc = _C.lib().lns_chan_sum_accum(_ptr(dy.t), dy.bstride, dy.B, dy.H * dy.W, dy.C, _ptr(grad), _stream())
+    check(rc, "lns_chan_sum_accum")
+    _state.launches += 1
+
+
+def act_bwd(dy, pre, act):
+    """dy * act'(pre) as a new Act (contiguous fp32 operands)."""
+    _f32_nhwc(dy, "act_bwd")
+    _f32_nhwc(pre, "act_bwd")
+    if not (dy.contiguous and pre.contiguous) or (dy.B, dy.H, dy.W, dy.C) != (pre.B, pre.H, pre.W, pre.C):
+        raise LnsError("act_bwd: contiguous activations of equal shape only")
+    out = dy.like()
+    rc = _C.lib().lns_act_bwd(_ptr(dy.t), _ptr(pre.t), dy.B * dy.H * dy.W * dy.C, act, _ptr(out.t), _stream())
+    check(rc, "lns_act_bwd")
+    _state.launches += 1
+    return out
+
+
+def group_norm_bwd(x, dy, groups, eps, gamma, dskip=None, dgamma=None, dbeta=None):
+    """Gradient of GroupNorm(groups, C, eps)(x) w.r.t. x (+ dskip), and dgamma / dbeta accumulated into the given [C] tensors."""
+    _f32_nhwc(x, "group_norm_bwd")
+    _f32_nhwc(dy, "group_norm_bwd")
+    out = x.like()
+    part_g = part_b = None
+    if dgamma is not None:
+        part_g = torch.empty(x.B * x.C, dtype=torch.float32, device=x.t.device)
+        part_b = torch.empty_like(part_g)
+    g = gamma.detach().float().contiguous() if gamma is not None else None
+    rc = _C.lib().lns_group_norm_bwd(_ptr(x.t), x.bstride, _ptr(dy.t), dy.bstride, _ptr(dskip.t) if dskip is not None else None,
+                                     dskip.bstride if dskip is not None else 0, x.B, x.H * x.W, x.C, groups, float(eps), _ptr(g),
+                                     _ptr(out.t), out.bstride, _ptr(part_g), _ptr(part_b), _stream())
+    check(rc, "lns_group_norm_bwd")
+    _state.launches += 1
+    if dgamma is not None:
+        for part, grad in ((part_g, dgamma), (part_b, dbeta)):
+            rc = _C.lib().lns_batch_sum_accum(_ptr(part), x.B, x.C, _ptr(grad), _stream())
+            check(rc, "lns_batch_sum_accum")
+            _state.launches += 1
+    return out
+
+
 # ---- misc ----------------------------------------------------------------------------------------------------
 def fourier_embedding(param, dim, max_period=10000.0):
     """param: torch fp32 [B] on CUDA -> torch fp32 [B, dim]"""

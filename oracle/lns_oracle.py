@@ -454,3 +454,36 @@ def make_inputs(cfg, batch, seed=0):
     if cfg.kind == "twophase_cond":
         param = torch.rand(batch, generator=g)
     return x, param
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# training rollout (LatentDynamics.forward: train_stage2_ns2d.py:126-141, _SW.py / _twophase.py :126-142)
+# ------------------------------------------------------------------------------------------------------------------
+def train_rollout(sd, cfg, z0, t_out, prefix="propagator."):
+    """z_pred [b, t_out, c, h, w]: t_out autoregressive propagator steps from z0 [b, c, h, w] (differentiable: the gradient
+    oracle is torch autograd of this restatement, pinned against autograd of the unmodified reference by
+    tests/golden/train_grads.pt)."""
+    z, out = z0, []
+    for _ in range(t_out):
+        z = propagator_step(sd, cfg, z, None, prefix)
+        out.append(z)
+    return torch.stack(out, dim=1)
+
+
+def train_inputs(cfg, batch, t_out, seed=0):
+    """Seeded latent input z_in [b, 1, c, h, w] and target z_out [b, t_out, c, h, w] of the training rollout."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    h = cfg.latent_resolution
+    w = h * getattr(cfg, "hw_ratio", 1)
+    if cfg.kind in ("twophase", "twophase_cond"):
+        h, w = 7, 15
+    z_in = torch.randn(batch, 1, cfg.latent_dim, h, w, generator=g)
+    z_out = torch.randn(batch, t_out, cfg.latent_dim, h, w, generator=g)
+    return z_in, z_out
+
+
+def grad_probe(name, shape, dtype=torch.float64):
+    """Fixed pseudo-random direction per parameter (seeded by its name): goldens store <grad, probe> instead of full gradients."""
+    seed = int.from_bytes(name.encode(), "little") % (2 ** 31 - 1)
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g, dtype=dtype)

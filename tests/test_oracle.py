@@ -90,3 +90,28 @@ def test_upsample_phase_decomposition(circular):
         got = U.conv_up2_by_phases(x, w, b, circular)
         assert got.shape == ref.shape == (2, 5, 2 * H, 2 * W)
         assert (got - ref).abs().max().item() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["ns2d", "sw", "twophase"])
+def test_oracle_training_gradients_vs_reference(name, golden_dir):
+    """Gradient oracle (torch autograd of O.train_rollout, fp64) vs loss / parameter gradients of the unmodified reference's
+    LatentDynamics.forward(z_in, z_out, F.smooth_l1_loss) (tests/golden/train_grads.pt, oracle/make_golden_train.py)."""
+    import torch.nn.functional as F
+    from lns_b200.configs import get_config
+    from lns_b200.latent_dynamics import LatentDynamics
+    fix = torch.load(os.path.join(golden_dir, "train_grads.pt"))[name]
+    cfg = get_config(name)
+    torch.manual_seed(1234)
+    sd = O.randomize_zero_init(LatentDynamics(cfg).state_dict())
+    sd64 = {k: v.double().requires_grad_(k.startswith("propagator.")) for k, v in sd.items()}
+    z_in, z_out = O.train_inputs(cfg, fix["batch"], fix["t_out"], seed=0)
+    loss = F.smooth_l1_loss(O.train_rollout(sd64, cfg, z_in[:, 0].double(), fix["t_out"]), z_out.double())
+    loss.backward()
+    assert abs(float(loss) - fix["loss"]) < 1e-12
+    for k, n in fix["norm"].items():
+        g = sd64["propagator." + k].grad
+        assert abs(float(g.norm()) - n) <= 1e-9 * max(n, 1e-30), k
+        pr = float((g * O.grad_probe(k, g.shape)).sum())
+        assert abs(pr - fix["probe"][k]) <= 1e-9 * max(n, 1e-30) * g.numel() ** 0.5, k
+        if k in fix["full"]:
+            assert (g - fix["full"][k]).abs().max().item() <= 1e-10 * max(n, 1e-30), k
