@@ -21,6 +21,7 @@ configurations), `sweep` (NS2d batch sweep), `clocks`, `gpu_launches`.  The extr
 cores on a bounded sample of the same workload.
 """
 import argparse
+import importlib.util
 import collections
 import json
 import os
@@ -511,6 +512,16 @@ def main():
                     except Exception as ex:  # noqa: BLE001
                         sweep[str(nb)] = {"error": repr(ex)[:200]}
                 line["sweep"] = {"workload": "NS2d 64x64, R=20, trajectories per GPU (BASELINE config 5)", "unit": "trajectory-steps/s", **sweep}
+            # stand-alone legs outside the rollout: the spectral block (BASELINE config 4's wording) and the training rollout
+            # (SURVEY 8(f) row 3); tools/bench_spectral.py, tools/bench_train.py
+            for key, fname, kw in (("spectral", "bench_spectral.py", {"peak": peaks["hbm_gbs"]}), ("training", "bench_train.py", {})):
+                try:
+                    spec = importlib.util.spec_from_file_location(key + "_bench", os.path.join(ROOT, "tools", fname))
+                    mod = importlib.util.module_from_spec(spec)
+                    spec.loader.exec_module(mod)
+                    line[key] = mod.run(**kw)
+                except Exception as ex:  # noqa: BLE001
+                    line[key] = {"error": repr(ex)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

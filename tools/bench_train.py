@@ -1,0 +1,75 @@
+"""Training-rollout benchmark: one optimisation step = LatentDynamics.forward(z_in, z_out,
+smooth_l1) + backward + AdamW.step at the reference's training shape (configs/ns2d_stage2_prop.yml: batch 32, out_tw 2) and at a
+throughput batch, next to the same step in PyTorch eager on the same GPU (autograd of the oracle's restatement, fp32)."""
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p_ in (ROOT, os.path.join(ROOT, "oracle")):
+    if p_ not in sys.path:
+        sys.path.insert(0, p_)
+
+
+def _timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def run(cases=((32, 2), (1024, 2)), iters=10, eager=True):
+    import lns_oracle as O
+    from lns_b200 import ops
+    from lns_b200.configs import get_config
+    from lns_b200.latent_dynamics import LatentDynamics
+    cfg = get_config("ns2d")
+    out = {"workload": "NS2d latent training step: forward(z_in, z_out, smooth_l1) + backward + AdamW (configs/ns2d_stage2_prop.yml)",
+           "unit": "trajectory-steps/s", "cases": []}
+    for B, T in cases:
+        torch.manual_seed(1234)
+        model = LatentDynamics(cfg)
+        model.load_state_dict(O.randomize_zero_init(model.state_dict()))
+        model = model.cuda()
+        for p in model.autoencoder.parameters():
+            p.requires_grad_(False)
+        opt = torch.optim.AdamW(model.propagator.parameters(), lr=1e-5)
+        z_in, z_out = O.train_inputs(cfg, B, T, seed=0)
+        z_in, z_out = z_in.cuda(), z_out.cuda()
+        row = {"batch": B, "t_out": T}
+        for prec in ("fp16s", "fp32"):
+            def step():
+                opt.zero_grad(set_to_none=True)
+                with ops.precision(prec):
+                    loss = model(z_in, z_out, F.smooth_l1_loss)
+                    loss.backward()
+                opt.step()
+            n0 = ops.launch_count()
+            ms = _timed(step, iters)
+            row[prec] = {"ms_per_iter": round(ms, 3), "value": round(B * T / ms * 1e3, 1)}
+        if eager:
+            sd = {k: v.detach().clone().requires_grad_(k.startswith("propagator.")) for k, v in model.state_dict().items()}
+            params = [v for k, v in sd.items() if k.startswith("propagator.")]
+            opt2 = torch.optim.AdamW(params, lr=1e-5)
+
+            def estep():
+                opt2.zero_grad(set_to_none=True)
+                F.smooth_l1_loss(O.train_rollout(sd, cfg, z_in[:, 0], T), z_out).backward()
+                opt2.step()
+            ms = _timed(estep, iters)
+            row["torch_eager_fp32_same_gpu"] = {"ms_per_iter": round(ms, 3), "value": round(B * T / ms * 1e3, 1)}
+        out["cases"].append(row)
+    return out
+
+
+if __name__ == "__main__":
+    print(json.dumps(run()))
