@@ -74,10 +74,15 @@ def load_peaks():
             "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
 
 
+def _gather_label():
+    return ("copy-engine pushes into CUDA symmetric memory (lns_b200.dist.P2PGather)" if os.environ.get("LNS_GATHER", "p2p") == "p2p"
+            else "NCCL all_gather_into_tensor")
+
+
 def config_block(label, R, B, world, gather, precision, sample_batch=None):
     """the `config` object -- identical keys on both arms (the reference arm adds its bounded sample)"""
     c = {"workload": label, "rollout_steps": R, "trajectories_per_gpu": B, "global_batch": B * world,
-         "parallelism": f"trajectory-sharded x{world}" + (", final all-gather of fields (step i overlaps the rollout of step i+1)" if gather else ""),
+         "parallelism": f"trajectory-sharded x{world}" + (f", final all-gather of fields by {_gather_label()} (step i overlaps the rollout of step i+1)" if gather else ""),
          "l2": "per-step working set (activations) is far larger than the 126 MB L2; no explicit flush",
          "cuda_graph": True, "random_init_weights_seed": 1234, "precision_mode": precision}
     if sample_batch is not None:
@@ -339,7 +344,7 @@ def main():
     import torch.distributed as dist
     from lns_b200 import ops
     from lns_b200.configs import get_config
-    from lns_b200.dist import OverlappedGather, init_from_env
+    from lns_b200.dist import OverlappedGather, init_from_env, make_gather
     from lns_b200.latent_dynamics import LatentDynamics
     from lns_b200.rollout import Rollout
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -372,7 +377,7 @@ def main():
     gather = world > 1 and not args.no_gather
     # N > 1: the final all-gather of the predicted fields (NCCL over NVLink) of step i runs on NCCL's stream out of a staging
     # copy while the rollout of step i+1 computes; the timed region ends when the last gather has completed.
-    og = OverlappedGather((B, R, ro.C, ro.Ly, ro.Lx), torch.float32, device) if gather else None
+    og = make_gather((B, R, ro.C, ro.Ly, ro.Lx), torch.float32, device) if gather else None
 
     def one_step():
         out = ro(x_dev, p_dev)

@@ -84,6 +84,63 @@ class OverlappedGather:
         return self.full
 
 
+class P2PGather:
+    """The same contract as OverlappedGather, with the transfer OFF the SMs: every rank's [world * b, ...] result buffer is
+    CUDA symmetric memory (torch.distributed._symmetric_memory: one allocation mapped into every peer of the node), and
+    ``submit`` PUSHES the rank's shard into slot `rank` of every peer's buffer with plain device-to-device copies on a side
+    stream -- the copy engines move the bytes over NVLink / NVSwitch while the next rollout owns all SMs and no NCCL kernel
+    competes with the decode launches, which are sized to whole 148-SM waves (the NCCL all-gather cost 1.8 ms of a
+    97 ms step at 8 GPUs).  Two tiny device-side barriers on the side stream order the exchange: one before the pushes (every
+    peer has finished reading the previous result) and one after (every shard has landed everywhere)."""
+
+    def __init__(self, local_shape, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.b = local_shape[0]
+        full_shape = (self.b * self.world,) + tuple(local_shape[1:])
+        self.stage = torch.empty(tuple(local_shape), dtype=dtype, device=device)
+        self.full = symm.empty(full_shape, dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.full, self.group)
+        # slot `rank` of every peer's result buffer, as local tensors
+        self.slots = [self.hdl.get_buffer(r, full_shape, dtype)[self.rank * self.b:(self.rank + 1) * self.b] for r in range(self.world)]
+        self.stream = torch.cuda.Stream(device)
+        self.staged = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        self.pending = False
+
+    def submit(self, local):
+        cur = torch.cuda.current_stream(self.stage.device)
+        self.wait()
+        self.stage.copy_(local, non_blocking=True)
+        self.staged.record(cur)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.staged)   # (also orders this rank's reads of the previous result before the barrier)
+            self.hdl.barrier(channel=0)
+            for r in range(self.world):
+                self.slots[(self.rank + r) % self.world].copy_(self.stage, non_blocking=True)
+            self.hdl.barrier(channel=1)
+            self.done.record(self.stream)
+        self.pending = True
+
+    def wait(self):
+        if self.pending:
+            torch.cuda.current_stream(self.stage.device).wait_event(self.done)
+            self.pending = False
+        return self.full
+
+
+def make_gather(local_shape, dtype, device, group=None):
+    """The overlapped gather of the node: copy-engine pushes into symmetric memory (P2PGather) on CUDA + NCCL unless
+    LNS_GATHER=nccl, the NCCL all-gather (OverlappedGather) otherwise (gloo / single rank / LNS_GATHER=nccl)."""
+    want = os.environ.get("LNS_GATHER", "p2p")
+    if (want == "p2p" and dist.is_initialized() and dist.get_world_size(group) > 1 and torch.device(device).type == "cuda"
+            and dist.get_backend(group) == "nccl"):
+        return P2PGather(local_shape, dtype, device, group)
+    return OverlappedGather(local_shape, dtype, device, group)
+
+
 class ShardedRollout:
     """Rolls out this rank's slice of a global batch and (optionally) all-gathers the fields."""
 

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lns_b200.dist import OverlappedGather, gather_fields, shard_bounds
+from lns_b200.dist import OverlappedGather, gather_fields, make_gather, shard_bounds
 
 
 def test_shard_bounds_cover_the_batch():
@@ -55,8 +55,8 @@ def test_gather_fields_gloo_world2(batch):
 def _worker_overlap(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    og = OverlappedGather((3, 2, 4), torch.float32, torch.device("cpu"))
-    ok = True
+    og = make_gather((3, 2, 4), torch.float32, torch.device("cpu"))  # gloo / CPU: the collective transport, never the P2P one
+    ok = isinstance(og, OverlappedGather)
     buf = torch.empty(3, 2, 4)  # the producer's fixed output buffer, overwritten every step
     for step in range(4):
         buf.copy_(torch.full((3, 2, 4), float(10 * step + rank)))
