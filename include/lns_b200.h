@@ -129,9 +129,16 @@ typedef struct LnsConvDesc {
   int32_t y_dtype, y_layout;
   int32_t Hout, Wout, Cout;
   int64_t y_bstride;
+  /* optional by-product (LNS_ENGINE_COARSE only, else must be NULL): per-channel partial sums of the OUTPUT as stored,
+   * stats[b][chunk][c] = (sum, sum of squares) over the chunk's pixels, chunk = 4 * (8x8 block of the sample) + epilogue warp,
+   * lns_conv_stats_chunks(Hout, Wout) chunks per sample -- the statistics of the GroupNorm that follows (lns_norm_finalize)
+   * without another read of the tensor (modules/basics.py:246-252: GroupNorm -> Swish -> Conv, twice per ResidualBlock) */
+  float* stats;
 } LnsConvDesc;
 
 int lns_conv2d(const LnsConvDesc* d, void* stream);
+/* chunks per sample of LnsConvDesc.stats */
+int lns_conv_stats_chunks(int Hout, int Wout);
 
 /* Bytes of the packed image of an OIHW fp32 filter [Cout][Cin][KH][KW] in `format`. */
 int64_t lns_packed_weight_bytes(int Cout, int Cin, int KH, int KW, int format);

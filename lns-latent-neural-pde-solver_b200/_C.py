@@ -33,6 +33,7 @@ class ConvDesc(ctypes.Structure):
         ("y", vp), ("y_dtype", i32), ("y_layout", i32),
         ("Hout", i32), ("Wout", i32), ("Cout", i32),
         ("y_bstride", i64),
+        ("stats", vp),
     ]
 
 
@@ -42,6 +43,7 @@ SIGNATURES = {
     "lns_last_error": (ctypes.c_char_p, []),
     "lns_device_info": (i32, [ctypes.POINTER(i32)] * 3),
     "lns_conv2d": (i32, [ctypes.POINTER(ConvDesc), vp]),
+    "lns_conv_stats_chunks": (i32, [i32, i32]),
     "lns_packed_weight_bytes": (i64, [i32, i32, i32, i32, i32]),
     "lns_pack_conv_weight": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "lns_chan_stats_chunks": (i32, [i32, i32]),

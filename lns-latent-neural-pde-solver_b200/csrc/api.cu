@@ -117,10 +117,16 @@ int lns_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   return LNS_OK;
 }
 
+int lns_conv_stats_chunks(int Hout, int Wout) { return ((Hout + 7) / 8) * ((Wout + 7) / 8) * 4; }
+
 int lns_conv2d(const LnsConvDesc* d, void* stream) {
   int rc = lns::validate_conv(d);
   if (rc != LNS_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d->stats && d->engine != LNS_ENGINE_COARSE) {
+    lns::set_error("lns_conv2d: output statistics (LnsConvDesc.stats) are produced by LNS_ENGINE_COARSE only");
+    return LNS_E_UNSUPPORTED;
+  }
   if (d->engine == LNS_ENGINE_HALO) return lns::conv2d_halo(d, s);
   if (d->engine == LNS_ENGINE_LATENT) return lns::conv2d_latent(d, s);
   if (d->engine == LNS_ENGINE_COARSE) return lns::conv2d_coarse(d, s);

@@ -128,12 +128,16 @@ struct CoarseParams {
   const void* x;       // NHWC 16-bit (AMODE 0) or fp32 (AMODE 1)
   const uint16_t* w;   // packed [tap 9][slab][Cout][64] swizzled; split filter: the lo image w_plane_elems further
   const float* bias;
+  const float* pro_scale;  // fp32 input only: per-(sample, channel) affine + activation applied in the producer, before the
+  const float* pro_shift;  // hi | lo split (the GroupNorm apply + Swish of the previous layer never exist as a tensor)
+  int pro_act;
   int act;
   const void* residual;
   int res_dtype;
   int64_t res_bstride;
   void* y;
   int y_dtype;
+  float* stats;        // [B][nb * 4][Cout][2] per-channel partial sums of the stored output, or null
   int x_f16;           // operands are IEEE half (else bf16)
   int slabs;           // Cin / 64
   int nbx, nby, nb;    // 8x8 blocks per sample: columns, rows, total
@@ -249,6 +253,14 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
           const int by = rem / p.nbx, bx = rem - by * p.nbx;
           const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x) + ((int64_t)b * g.x_bstride + slab * 64 + chunk * 8) * esz;
           const uint32_t plane = halo_a + (uint32_t)((((ts >> 1) * SL + slab) * AP)) * (uint32_t)p.plane_bytes;
+          float psc[8], psh[8];
+          if (AMODE == 1 && p.pro_scale) {
+            const float4* s4 = reinterpret_cast<const float4*>(p.pro_scale + (int64_t)b * g.Cin + slab * 64 + chunk * 8);
+            const float4* t4 = reinterpret_cast<const float4*>(p.pro_shift + (int64_t)b * g.Cin + slab * 64 + chunk * 8);
+            const float4 sa = __ldg(s4), sb = __ldg(s4 + 1), ta = __ldg(t4), tb = __ldg(t4 + 1);
+            psc[0] = sa.x; psc[1] = sa.y; psc[2] = sa.z; psc[3] = sa.w; psc[4] = sb.x; psc[5] = sb.y; psc[6] = sb.z; psc[7] = sb.w;
+            psh[0] = ta.x; psh[1] = ta.y; psh[2] = ta.z; psh[3] = ta.w; psh[4] = tb.x; psh[5] = tb.y; psh[6] = tb.z; psh[7] = tb.w;
+          }
           if (AMODE == 0) {
             for (int q = p0; q < npx; q += pstep) {
               const int hy = __float2int_rd(((float)q + 0.5f) * p.inv_hwd), hx = q - hy * HWd;
@@ -281,9 +293,17 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
               }
 #pragma unroll
               for (int u = 0; u < kU; ++u) {
-                const float v[8] = {__int_as_float(raw[2 * u].x), __int_as_float(raw[2 * u].y), __int_as_float(raw[2 * u].z),
-                                    __int_as_float(raw[2 * u].w), __int_as_float(raw[2 * u + 1].x), __int_as_float(raw[2 * u + 1].y),
-                                    __int_as_float(raw[2 * u + 1].z), __int_as_float(raw[2 * u + 1].w)};
+                float v[8] = {__int_as_float(raw[2 * u].x), __int_as_float(raw[2 * u].y), __int_as_float(raw[2 * u].z),
+                              __int_as_float(raw[2 * u].w), __int_as_float(raw[2 * u + 1].x), __int_as_float(raw[2 * u + 1].y),
+                              __int_as_float(raw[2 * u + 1].z), __int_as_float(raw[2 * u + 1].w)};
+                if (p.pro_scale) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], psc[j], psh[j]);
+                }
+                if (p.pro_act != LNS_ACT_NONE) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = apply_act_fast(v[j], p.pro_act);
+                }
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -420,50 +440,90 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
         const int64_t yrow = (int64_t)b * g.y_bstride + pix * g.Cout;
         const int64_t rrow = (int64_t)b * p.res_bstride + pix * g.Cout;
         const uint32_t t_lane = tmem_acc + (uint32_t)((a * T + t) * 128) + ((uint32_t)(quad * 32) << 16);
+        const bool blk_ok = gb < p.nblocks;
+        const int blk_in_sample = blk_ok ? gb - b * p.nb : 0;
         for (int c0 = 0; c0 < g.Cout; c0 += 32) {
           uint32_t raw[32];
           __syncwarp();
           cptx::tmem_ld32(t_lane + (uint32_t)c0, raw);
           cptx::tmem_ld_wait();
-          if (!row_ok) continue;
+          if (!row_ok && !p.stats) continue;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (p.bias) {
+          if (row_ok) {
+            if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+              }
+            }
+            if (p.act != LNS_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
+            }
+            if (p.residual) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 rr = ld4_as_float(p.residual, p.res_dtype, rrow + c0 + j);
+                v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
+              }
+            }
+            if (y16) {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.y) + yrow + c0);
+#pragma unroll
+              for (int h4 = 0; h4 < 4; ++h4) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pk[j] = pack2_rt(p.y_dtype, v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
+                dst[h4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (p.stats) {  // statistics of the values as stored
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack2_rt(p.y_dtype, pk[j]);
+                    v[h4 * 8 + 2 * j] = f.x; v[h4 * 8 + 2 * j + 1] = f.y;
+                  }
+                }
+              }
+            } else {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yrow + c0);
+              if (p.y_dtype == LNS_TF32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
           }
-          if (p.act != LNS_ACT_NONE) {
+          if (p.stats) {
+            // per-channel (sum, sum of squares) over the warp's 16 pixels of this block: a halving butterfly over lane bits
+            // 4, 2, 1, 0 (bit 3 = the block slot is not reduced) -- 30 shuffles per quantity instead of 128; the lane ends up with
+            // channels c0 + 16 b4 + 8 b2 + 4 b1 + 2 b0 + {0, 1}
+            float s[32], q[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
-          }
-          if (p.residual) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 rr = ld4_as_float(p.residual, p.res_dtype, rrow + c0 + j);
-              v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
-            }
-          }
-          if (y16) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.y) + yrow + c0);
-#pragma unroll
-            for (int h4 = 0; h4 < 4; ++h4) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) pk[j] = pack2_rt(p.y_dtype, v[h4 * 8 + 2 * j], v[h4 * 8 + 2 * j + 1]);
-              dst[h4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          } else {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yrow + c0);
-            if (p.y_dtype == LNS_TF32) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+            for (int j = 0; j < 32; ++j) {
+              s[j] = row_ok ? v[j] : 0.f;
+              q[j] = s[j] * s[j];
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int step = 0; step < 4; ++step) {
+              const int half = 16 >> step;                     // values kept per lane after this step
+              const int bit = step == 0 ? 16 : (8 >> step);   // lane bit exchanged: 16, 4, 2, 1
+              const bool up = (lane & bit) != 0;
+#pragma unroll
+              for (int j = 0; j < half; ++j) {
+                const float ks = up ? s[j + half] : s[j], ss = up ? s[j] : s[j + half];
+                const float kq = up ? q[j + half] : q[j], sq = up ? q[j] : q[j + half];
+                s[j] = ks + __shfl_xor_sync(0xffffffffu, ss, bit);
+                q[j] = kq + __shfl_xor_sync(0xffffffffu, sq, bit);
+              }
+            }
+            if (blk_ok) {
+              const int cb = c0 + ((lane >> 4) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+              float* dst = p.stats + ((((int64_t)b * p.nb + blk_in_sample) * 4 + quad) * g.Cout + cb) * 2;
+              *reinterpret_cast<float4*>(dst) = make_float4(s[0], q[0], s[1], q[1]);
+            }
           }
         }
       }
@@ -483,9 +543,11 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
 bool conv_coarse_supported(const LnsConvDesc* d) {
   if (!(d->KH == 3 && d->KW == 3 && d->stride == 1 && (d->Cin == 64 || d->Cin == 128) && (d->Cout == 64 || d->Cout == 128) &&
         d->dil >= 1 && d->dil <= 3 && d->pad_t == d->dil && d->pad_l == d->dil && d->Hout == d->Hv && d->Wout == d->Wv &&
-        d->dil <= d->Hv && d->dil <= d->Wv && d->x_layout == LNS_NHWC && d->y_layout == LNS_NHWC && d->pro_scale == nullptr &&
-        d->pro_act == LNS_ACT_NONE && d->sample_bias == nullptr && d->pre_add == nullptr))
+        d->dil <= d->Hv && d->dil <= d->Wv && d->x_layout == LNS_NHWC && d->y_layout == LNS_NHWC && d->sample_bias == nullptr && d->pre_add == nullptr))
     return false;
+  // the gather prologue (per-sample affine + activation) exists in the fp32 producer only (16-bit inputs arrive by cp.async)
+  if ((d->pro_scale != nullptr || d->pro_act != LNS_ACT_NONE) && d->x_dtype != LNS_F32) return false;
+  if ((d->pro_scale == nullptr) != (d->pro_shift == nullptr)) return false;
   if (d->x_dtype == LNS_F16) return d->w_format == LNS_W_UMMA_F16 || d->w_format == LNS_W_UMMA_F16X2;
   if (d->x_dtype == LNS_BF16) return d->w_format == LNS_W_UMMA_BF16;
   if (d->x_dtype == LNS_F32) return d->w_format == LNS_W_UMMA_F16 || d->w_format == LNS_W_UMMA_F16X2 || d->w_format == LNS_W_UMMA_BF16;
@@ -495,7 +557,7 @@ bool conv_coarse_supported(const LnsConvDesc* d) {
 int conv2d_coarse(const LnsConvDesc* d, cudaStream_t stream) {
   LNS_REQUIRE(conv_coarse_supported(d),
               "lns_conv2d(coarse): needs a same-size 3x3 stride-1 conv, Cin/Cout in {64,128}, pad = dil <= 3, NHWC input (16-bit, or "
-              "fp32 = split into hi+lo halves), UMMA-packed weights (plain or split), no prologue / sample bias / pre-add");
+              "fp32 = split into hi+lo halves), UMMA-packed weights (plain or split), no sample bias / pre-add (prologue: fp32 input only)");
   const bool f32in = d->x_dtype == LNS_F32;
   const int esz = f32in ? 4 : 2;
   LNS_REQUIRE((d->x_bstride * esz) % 16 == 0 && d->y_bstride % 8 == 0, "lns_conv2d(coarse): batch strides must keep 16-byte alignment");
@@ -509,9 +571,14 @@ int conv2d_coarse(const LnsConvDesc* d, cudaStream_t stream) {
   p.x = d->x;
   p.w = reinterpret_cast<const uint16_t*>(d->w);
   p.bias = d->bias;
+  p.pro_scale = d->pro_scale; p.pro_shift = d->pro_shift; p.pro_act = d->pro_act;
+  if (d->pro_scale) LNS_REQUIRE(((reinterpret_cast<uintptr_t>(d->pro_scale) | reinterpret_cast<uintptr_t>(d->pro_shift)) & 15) == 0,
+                                "lns_conv2d(coarse): prologue scale / shift alignment");
   p.act = d->act;
   p.residual = d->residual; p.res_dtype = d->res_dtype; p.res_bstride = d->res_bstride;
   p.y = d->y; p.y_dtype = d->y_dtype;
+  p.stats = d->stats;
+  if (d->stats) LNS_REQUIRE((reinterpret_cast<uintptr_t>(d->stats) & 15) == 0, "lns_conv2d(coarse): stats alignment");
   p.x_f16 = d->w_format == LNS_W_UMMA_BF16 ? 0 : 1;
   p.slabs = d->Cin / 64;
   p.nbx = cdiv(d->Wout, 8); p.nby = cdiv(d->Hout, 8); p.nb = p.nbx * p.nby;

@@ -57,44 +57,54 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const void* __restrict_
   }
 }
 
-// grid B, block 256: one WARP per group (lanes stride over the group's channels, fixed-order shuffle reduction in fp64)
+// grid B, block 256.  Pass 1: thread per channel sums its chunks (coalesced float2 loads, fixed order, fp64).  Pass 2: one thread
+// per group combines the group's channels in channel order (fp64) into mean / rstd.  Pass 3: thread per channel writes the
+// folded affine.  (The first version gave a whole warp to each group: with 4 channels per group 28 of 32 lanes idled through
+// dependent loads and fp64 shuffles -- 52 us for 4736 samples; this one is bandwidth-trivial.)
 __global__ void __launch_bounds__(256) norm_finalize_kernel(const float2* __restrict__ partial, int nchunk, int C, int HW,
                                                              int G, float eps, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta,
                                                              const float* __restrict__ prescale,
                                                              float* __restrict__ scale, float* __restrict__ shift) {
+  extern __shared__ double fin_sm[];  // [C][2] channel sums | [G][2] mean, rstd
+  double* csum = fin_sm;
+  double* gst = fin_sm + 2 * C;
   const int b = blockIdx.x;
   const int cpg = C / G;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int gi = warp; gi < G; gi += 8) {
-    double sum = 0.0, sumsq = 0.0;
-    for (int j = lane; j < cpg; j += 32) {
-      int c = gi * cpg + j;
-      double cs = 0.0, css = 0.0;
-      for (int k = 0; k < nchunk; ++k) {
-        float2 v = partial[((int64_t)b * nchunk + k) * C + c];
-        cs += (double)v.x;
-        css += (double)v.y;
-      }
-      double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
-      sum += ps * cs;
-      sumsq += ps * ps * css;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double cs = 0.0, css = 0.0;
+    for (int k = 0; k < nchunk; ++k) {
+      const float2 v = partial[((int64_t)b * nchunk + k) * C + c];
+      cs += (double)v.x;
+      css += (double)v.y;
     }
-    sum = warp_sum_d(sum);
-    sumsq = warp_sum_d(sumsq);
-    double n = (double)cpg * (double)HW;
-    double mean = sum / n;
+    const double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
+    csum[2 * c] = ps * cs;
+    csum[2 * c + 1] = ps * ps * css;
+  }
+  __syncthreads();
+  for (int gi = threadIdx.x; gi < G; gi += 256) {
+    double sum = 0.0, sumsq = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      sum += csum[2 * (gi * cpg + j)];
+      sumsq += csum[2 * (gi * cpg + j) + 1];
+    }
+    const double n = (double)cpg * (double)HW;
+    const double mean = sum / n;
     double var = sumsq / n - mean * mean;
     if (var < 0.0) var = 0.0;
-    double rstd = 1.0 / sqrt(var + (double)eps);
-    for (int j = lane; j < cpg; j += 32) {
-      int c = gi * cpg + j;
-      double ga = gamma ? (double)gamma[c] : 1.0;
-      double be = beta ? (double)beta[c] : 0.0;
-      double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
-      scale[(int64_t)b * C + c] = (float)(ps * rstd * ga);
-      shift[(int64_t)b * C + c] = (float)(be - mean * rstd * ga);
-    }
+    gst[2 * gi] = mean;
+    gst[2 * gi + 1] = 1.0 / sqrt(var + (double)eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int gi = c / cpg;
+    const double mean = gst[2 * gi], rstd = gst[2 * gi + 1];
+    const double ga = gamma ? (double)gamma[c] : 1.0;
+    const double be = beta ? (double)beta[c] : 0.0;
+    const double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
+    scale[(int64_t)b * C + c] = (float)(ps * rstd * ga);
+    shift[(int64_t)b * C + c] = (float)(be - mean * rstd * ga);
   }
 }
 
@@ -240,7 +250,8 @@ int lns_chan_stats(const void* x, int dtype, int B, int H, int W, int C, int64_t
 int lns_norm_finalize(const float* partial, int B, int nchunk, int C, int HW, int G, float eps, const float* gamma,
                       const float* beta, const float* prescale, float* scale, float* shift, void* stream) {
   LNS_REQUIRE(partial && scale && shift && B > 0 && C > 0 && G > 0 && C % G == 0, "lns_norm_finalize: bad arguments");
-  lns::norm_finalize_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  LNS_REQUIRE((size_t)(2 * C + 2 * G) * sizeof(double) <= 48 * 1024, "lns_norm_finalize: C = %d too large", C);
+  lns::norm_finalize_kernel<<<B, 256, (size_t)(2 * C + 2 * G) * sizeof(double), reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float2*>(partial), nchunk, C, HW, G, eps, gamma, beta, prescale, scale, shift);
   return lns::check_launch("norm_finalize_kernel");
 }

@@ -47,6 +47,8 @@ class _State(threading.local):
         self.hi_scale = float(os.environ.get("LNS_HI_SCALE", "1"))  # experiment: 4 = one more resolution level in the hi region
         self.hi_wsplit = os.environ.get("LNS_HI_WSPLIT", "1") != "0"  # hi layers also split the filter (3 MMAs instead of 2)
         self.coarse = os.environ.get("LNS_COARSE", "1") != "0"        # use the block-halo engine (conv_coarse.cu) where it applies
+        self.coarse_pro = os.environ.get("LNS_COARSE_PRO", "1") != "0"  # ... and let its fp32 producer apply the pending norm + act
+        self.coarse_stats = os.environ.get("LNS_COARSE_STATS", "1") != "0"  # ... and its epilogue emit the next GroupNorm's statistics
         # FABlock2D with every contraction on tcgen05 (fablock_tc.cu): correct and tested, but its per-head chain of eight
         # barrier-separated MMA / drain stages is latency bound at one CTA per SM -- 7.7 ms vs 5.2 ms for the mma.sync kernel at
         # 4736 x 32x32 (profiles/r02_fablock_tc.md) -- so it is opt-in until the stages are software-pipelined
@@ -187,7 +189,7 @@ class Act:
     """A [B,H,W,C] activation living in `t` (element (0,0,0,0) at t.data_ptr()); channel-last unless layout=NCHW.
     `bstride` is the distance between samples in elements (lets the K latent states of a rollout interleave as
     [B,K,...] without copies)."""
-    __slots__ = ("t", "B", "H", "W", "C", "bstride", "layout", "tf32", "group", "gstride")
+    __slots__ = ("t", "B", "H", "W", "C", "bstride", "layout", "tf32", "group", "gstride", "stats")
 
     def __init__(self, t, B, H, W, C, bstride=None, layout=NHWC, tf32=False, group=None, gstride=0):
         if t.is_cuda and t.device.index != torch.cuda.current_device():
@@ -202,6 +204,9 @@ class Act:
         # two-level sample index (output of the decoder's projection only): sample s lives at
         # (s % group) * bstride + (s // group) * gstride -- `B // group` rollout steps of `group` trajectories, step-major
         self.group, self.gstride = group, gstride
+        # (partial [B][nchunk][C][2] fp32, nchunk): per-channel sums of this activation emitted by the kernel that produced it
+        # (conv_coarse.cu epilogue) -- a following GroupNorm only runs lns_norm_finalize
+        self.stats = None
 
     @property
     def dtype(self):
@@ -425,7 +430,19 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     if hi:
         if out is None and out_dtype is None and out_layout == NHWC and Hout * Wout <= _state.hi_px:
             out_dtype = torch.float32
-        if isinstance(pro, LazyNorm) and x.layout == NHWC:
+        coarse_ok = (KH == 3 and KW == 3 and stride == 1 and Cin in (64, 128) and Cout in (64, 128) and 1 <= dil <= 3
+                     and pt == pb == pl == pr == dil and dil <= min(Hv, Wv) and sample_bias is None and pre_add is None
+                     and _state.coarse and x.layout == NHWC and out_layout == NHWC and not x.tf32 and not _state.hi_exact
+                     and _coarse_fits(Cin, Cout, dil, x.t.dtype == torch.float32, _state.hi_wsplit))
+        # the block-halo engine's fp32 producer applies the pending per-sample affine + activation itself (conv_coarse.cu): the
+        # GroupNorm-applied tensor is never written -- only its statistics kernel runs
+        fuse_pro = (coarse_ok and pro is not None and x.t.dtype == torch.float32 and x.bstride % 4 == 0 and _state.coarse_pro)
+        if fuse_pro:
+            if isinstance(pro, LazyNorm):
+                if pro.x is not x:
+                    raise LnsError("conv2d: the pending normalisation belongs to a different activation")
+                pro = pro.as_tuple()
+        elif isinstance(pro, LazyNorm) and x.layout == NHWC:
             if pro.x is not x:
                 raise LnsError("conv2d: the pending normalisation belongs to a different activation")
             x = pro.materialize(out_dtype=torch.float32)  # the normalised activation is not rounded to 16 bits
@@ -433,10 +450,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
         elif pro is not None and x.layout == NHWC:
             x = affine_act(x, pro[0], pro[1], pro[2], out_dtype=torch.float32)
             pro = None
-        coarse_ok = (KH == 3 and KW == 3 and stride == 1 and Cin in (64, 128) and Cout in (64, 128) and 1 <= dil <= 3
-                     and pt == pb == pl == pr == dil and dil <= min(Hv, Wv) and sample_bias is None and pre_add is None
-                     and pro is None and _state.coarse
-                     and _coarse_fits(Cin, Cout, dil, x.t.dtype == torch.float32, _state.hi_wsplit))
+        coarse_ok = coarse_ok and (pro is None or fuse_pro)
         if (x.layout == NHWC and out_layout == NHWC and Cin % 64 == 0 and Cout % 16 == 0 and not x.tf32 and not _state.hi_exact
                 and ((x.t.dtype == torch.float32 and x.bstride % 4 == 0) or (x.t.dtype == torch.float16 and x.bstride % 8 == 0))):
             if coarse_ok:
@@ -446,6 +460,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
                 engine, split_fmt = ENGINE_UMMA, True   # gather engine: fp32 input 3 MMAs (x3), f16 input 2 MMAs (w2)
         else:
             engine = ENGINE_SIMT                        # tiny-channel layers: exact CUDA-core path
+    fused_pro = engine == ENGINE_COARSE and pro is not None and x.t.dtype == torch.float32 and not isinstance(pro, LazyNorm)
     if engine is None:
         engine = ENGINE_UMMA if _umma_ok(x, Cin, Cout, out_layout) else ENGINE_SIMT
         if (engine == ENGINE_UMMA and x.t.dtype in H16_DTYPES and KH == 3 and KW == 3 and stride == 1 and Cin == 64
@@ -468,7 +483,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
             pro = None
         else:
             pro = pro.as_tuple()
-    if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT, ENGINE_COARSE) and pro is not None:
+    if engine in (ENGINE_UMMA, ENGINE_HALO, ENGINE_LATENT, ENGINE_COARSE) and pro is not None and not fused_pro:
         x = affine_act(x, pro[0], pro[1], pro[2])
         pro = None
     if out is None:
@@ -515,6 +530,12 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
         d.residual, d.res_dtype, d.res_bstride = residual.t.data_ptr(), residual.dtype, residual.bstride
     d.y, d.y_dtype, d.y_layout = out.t.data_ptr(), out.dtype, out.layout
     d.Hout, d.Wout, d.Cout, d.y_bstride = Hout, Wout, Cout, out.bstride
+    if hi and engine == ENGINE_COARSE and _state.coarse_stats and out.layout == NHWC and out.group is None:
+        # the statistics of the GroupNorm that follows, from the epilogue's registers
+        nchunk = _C.lib().lns_conv_stats_chunks(Hout, Wout)
+        part = torch.empty(x.B * nchunk * Cout * 2, dtype=torch.float32, device=x.t.device)
+        d.stats = part.data_ptr()
+        out.stats = (part, nchunk)
     tok = _mark(f"conv e{engine} {KH}x{KW} s{stride} d{dil} {Cin}->{Cout} @{Hout}x{Wout}"
                 f"{' up' if virt is not None else ''}{' pro' if pro is not None else ''}"
                 f"{' act' if act else ''}{' res' if residual is not None else ''} "
@@ -574,14 +595,24 @@ def chan_stats(x):
 def group_norm_affine(x, groups, eps, gamma=None, beta=None, prescale=None):
     """GroupNorm(groups) statistics of (x * prescale) folded with gamma/beta into per-(sample,channel) (scale, shift).
     One fused kernel for samples of <= 1024 pixels, statistics + finalize kernels above that."""
-    nchunk = _C.lib().lns_chan_stats_chunks(x.H, x.W)
-    part = None
-    if nchunk > 1:
-        part = torch.empty(x.B * nchunk * x.C * 2, dtype=torch.float32, device=x.t.device)
     scale = torch.empty(x.B * x.C, dtype=torch.float32, device=x.t.device)
     shift = torch.empty_like(scale)
     g = gamma.detach().float().contiguous() if gamma is not None else None
     b = beta.detach().float().contiguous() if beta is not None else None
+    if x.stats is not None:
+        # the producing kernel left per-channel partial sums: only the finalize runs (no read of x)
+        part, nchunk = x.stats
+        tok = _mark(f"gn_finalize C{x.C} @{x.H}x{x.W}", nbytes=4.0 * part.numel())
+        rc = _C.lib().lns_norm_finalize(_ptr(part), x.B, nchunk, x.C, x.H * x.W, groups, float(eps), _ptr(g), _ptr(b), _ptr(prescale),
+                                        _ptr(scale), _ptr(shift), _stream())
+        check(rc, "lns_norm_finalize")
+        _done(tok)
+        _state.launches += 1
+        return scale, shift
+    nchunk = _C.lib().lns_chan_stats_chunks(x.H, x.W)
+    part = None
+    if nchunk > 1:
+        part = torch.empty(x.B * nchunk * x.C * 2, dtype=torch.float32, device=x.t.device)
     tok = _mark(f"gn_stats C{x.C} @{x.H}x{x.W}", nbytes=_abytes(x))
     rc = _C.lib().lns_group_norm_affine(_ptr(x.t), x.dtype, x.B, x.H, x.W, x.C, x.bstride, groups, float(eps), _ptr(g),
                                         _ptr(b), _ptr(prescale), _ptr(part), _ptr(scale), _ptr(shift), _stream())
@@ -612,7 +643,7 @@ class LazyNorm:
 
     def materialize(self, out_dtype=None):
         x = self.x
-        if (self._affine is None and x.layout == NHWC
+        if (self._affine is None and x.layout == NHWC and x.stats is None
                 and _C.lib().lns_group_norm_act_supported(x.H, x.W, x.C) and x.bstride % 4 == 0):
             out = x.like(dtype=out_dtype)
             g = self.gamma.detach().float().contiguous() if self.gamma is not None else None

@@ -49,7 +49,9 @@ def test_pure_host_entry_points():
     assert lib.lns_packed_weight_bytes(128, 128, 3, 3, ops.W_UMMA_BF16) == 128 * 128 * 9 * 2
     assert lib.lns_packed_weight_bytes(128, 16, 1, 1, ops.W_UMMA_BF16) == -1  # Cin % 64 != 0 -> not packable
     assert lib.lns_packed_weight_bytes(1, 64, 1, 1, ops.W_SIMT_F32) == 256
-    assert lib.lns_spectral_work_bytes(2, 61, 121, 64, 64, 16, 31) == 2 * 61 * 31 * 128 * 8
+    # X1 | Z planar rows (B H 2 m2 (Ci + Co)) + X2 | Y mode-major (2 m1 m2 B 2 (Ci + Co)) fp32
+    assert lib.lns_spectral_work_bytes(2, 61, 121, 64, 64, 16, 31) == (2 * 61 * 2 * 31 * 128 + 2 * 16 * 31 * 2 * 2 * 128) * 4
+    assert lib.lns_conv_stats_chunks(8, 8) == 4 and lib.lns_conv_stats_chunks(16, 16) == 16 and lib.lns_conv_stats_chunks(7, 15) == 8
 
 
 def test_invalid_arguments_are_errors_not_fallbacks():
