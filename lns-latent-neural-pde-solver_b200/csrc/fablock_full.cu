@@ -212,6 +212,8 @@ struct FullParams {
   __nv_bfloat16* out;      // [B][H][W][64]
   int Wp, T, tmem_cols;
   float inv_wp;
+  int k16;      // Kx / Ky slices can be staged with 16-byte copies
+  int lgwp;     // log2(Wp) when W == Wp is a power of two and the sample fills its tiles exactly (no pad rows), else -1
 };
 
 struct FullSmem {
@@ -282,11 +284,18 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
     for (int e = tid; e < 64 * 64 / 4; e += NTHR)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st_a + (uint32_t)e * 16u), "l"(wsrc + e * 4) : "memory");
     const float* kxsrc = p.Kx + ((int64_t)b * heads + hh) * H * H;
-    for (int e = tid; e < H * H; e += NTHR)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(st_a + (uint32_t)(64 * 64 + e) * 4u), "l"(kxsrc + e) : "memory");
     const float* kysrc = p.Ky + ((int64_t)b * heads + hh) * W * W;
-    for (int e = tid; e < W * W; e += NTHR)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(st_a + (uint32_t)(64 * 64 + H * H + e) * 4u), "l"(kysrc + e) : "memory");
+    if (p.k16) {  // H*H and W*W multiples of 4, 16-byte aligned bases: 16-byte copies (a quarter of the instructions)
+      for (int e = tid; e < H * H / 4; e += NTHR)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st_a + (uint32_t)(64 * 64 + e * 4) * 4u), "l"(kxsrc + e * 4) : "memory");
+      for (int e = tid; e < W * W / 4; e += NTHR)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st_a + (uint32_t)(64 * 64 + H * H + e * 4) * 4u), "l"(kysrc + e * 4) : "memory");
+    } else {
+      for (int e = tid; e < H * H; e += NTHR)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(st_a + (uint32_t)(64 * 64 + e) * 4u), "l"(kxsrc + e) : "memory");
+      for (int e = tid; e < W * W; e += NTHR)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(st_a + (uint32_t)(64 * 64 + H * H + e) * 4u), "l"(kysrc + e) : "memory");
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   prefetch_head(0);
@@ -364,6 +373,19 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
     // ---- raw input -> pixel rows of U_s (cp.async, four commit groups = four quarters of the row range) ----
     {
       const int ch = tid & 7;
+      if (p.lgwp >= 0) {
+        // no pad rows, power-of-two width: slot s holds pixel (y, x) = (s >> lg, (s & (Wp - 1)) ^ (y & 7)), i.e. source pixel index
+        // s ^ ((s >> lg) & 7); the slot's swizzle phase s & 7 is loop invariant (the stride is a multiple of 8)
+        const uint32_t dst0 = U_a + (uint32_t)((ch ^ ((tid >> 3) & 7)) << 4);
+        const uint8_t* src0 = reinterpret_cast<const uint8_t*>(ub) + ch * 16;
+        for (int q = 0; q < NQ; ++q) {
+          const int s_end = min(nslots, (q + 1) * blk_per_q * 16);
+          for (int s = q * blk_per_q * 16 + (tid >> 3); s < s_end; s += NTHR / 8)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)s * 128u),
+                         "l"(src0 + (size_t)(s ^ ((s >> p.lgwp) & 7)) * 128u) : "memory");
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+      } else
       for (int q = 0; q < NQ; ++q) {
         const int s_end = min(nslots, (q + 1) * blk_per_q * 16);
         for (int s = q * blk_per_q * 16 + (tid >> 3); s < s_end; s += NTHR / 8) {
@@ -404,7 +426,11 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
         for (int ks = 0; ks < 4; ++ks) fptx::ldsm_x4(U_a + sw_off(pr, ks * 2 + (lane >> 4)), a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
         float acc[8][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        for (int nt = 0; nt < 8; ++nt) {  // the bias is the accumulator's initial value (columns 2t, 2t + 1 of both row halves)
+          const float2 bb = *reinterpret_cast<const float2*>(bias_s + nt * 8 + t * 2);
+          acc[nt][0] = acc[nt][2] = bb.x;
+          acc[nt][1] = acc[nt][3] = bb.y;
+        }
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
@@ -417,11 +443,9 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
         const int phs = rs_row & 7, cs = lane >> 4;
 #pragma unroll
         for (int nt = 0; nt < 8; nt += 2) {
-          const float2 b0 = *reinterpret_cast<const float2*>(bias_s + nt * 8 + t * 2);
-          const float2 b1 = *reinterpret_cast<const float2*>(bias_s + (nt + 1) * 8 + t * 2);
-          fptx::stsm_x4(rs + (uint32_t)(((nt + cs) ^ phs) << 4), pack2_h16<F16>(acc[nt][0] + b0.x, acc[nt][1] + b0.y),
-                        pack2_h16<F16>(acc[nt][2] + b0.x, acc[nt][3] + b0.y), pack2_h16<F16>(acc[nt + 1][0] + b1.x, acc[nt + 1][1] + b1.y),
-                        pack2_h16<F16>(acc[nt + 1][2] + b1.x, acc[nt + 1][3] + b1.y));
+          fptx::stsm_x4(rs + (uint32_t)(((nt + cs) ^ phs) << 4), pack2_h16<F16>(acc[nt][0], acc[nt][1]),
+                        pack2_h16<F16>(acc[nt][2], acc[nt][3]), pack2_h16<F16>(acc[nt + 1][0], acc[nt + 1][1]),
+                        pack2_h16<F16>(acc[nt + 1][2], acc[nt + 1][3]));
         }
       }
     }
@@ -673,6 +697,13 @@ int lns_fablock_full(const void* u, int dtype, int B, int H, int W, int heads, c
   p.Wp = (W + 7) & ~7;
   p.T = (H * p.Wp + 127) / 128;
   p.inv_wp = 1.0f / (float)p.Wp;
+  p.k16 = ((H * H) % 4 == 0 && (W * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(Kx) & 15) == 0 && (reinterpret_cast<uintptr_t>(Ky) & 15) == 0) ? 1 : 0;
+  p.lgwp = -1;
+  if (p.Wp == W && (W & (W - 1)) == 0 && H * W == p.T * 128) {
+    int lg = 0;
+    while ((1 << lg) < W) ++lg;
+    p.lgwp = lg;
+  }
   int cols = 32;
   while (cols < p.T * 64) cols <<= 1;
   p.tmem_cols = cols;
