@@ -342,7 +342,11 @@ int lns_spectral_conv2d(const void* x, int x_dtype, int B, int H, int W, int Ci,
  * lns_conv2d_wgrad: dW[o][i][ky][kx] (OIHW fp32, ACCUMULATED into) += sum_{b,y,x} dy[b][y][x][o] *
  *   pro(x)[b][src(y + ky*dil - pad_t, x + kx*dil - pad_l)][i], where src() is lns_conv2d's index map (zeros / circular per
  *   axis) and pro = the forward's gather prologue act(x*scale[b][i] + shift[b][i]) (scale/shift NULL: none).  Needs
- *   2*pad == dil*(k-1), Cin % 4 == 0, Cout % 4 == 0.  work: lns_conv2d_wgrad_work_bytes() bytes of scratch.
+ *   2*pad == dil*(k-1), Cin % 4 == 0, Cout % 4 == 0.  work: lns_conv2d_wgrad_work_bytes() bytes of scratch.  tensor_core = 1: the
+ *   products run on mma.sync.m16n8k16 IEEE-half with both operands split hi + lo (3 MMAs, 22-bit operands; dy must be scaled
+ *   into the half range), 0: CUDA-core fp32 FMA.  Every
+ *   accumulating function multiplies its sum by out_scale first (1 / loss scale of a scaled backward pass).
+ * lns_absmax: *out_bits (zero-initialised by the caller) = bit pattern of max |x| -- chooses the loss scale
  * lns_chan_sum_accum: grad[c] += sum_{b,pix} dy[b][pix][c]                       (bias gradient)
  * lns_act_bwd: dx = dy * act'(pre) elementwise (LNS_ACT_GELU exact erf, LNS_ACT_SILU)
  * lns_group_norm_bwd: x, dy -> dx (+ dskip if not NULL) for GroupNorm(G, C, eps) with weight gamma (NULL: ones); the
@@ -353,13 +357,17 @@ int lns_spectral_conv2d(const void* x, int x_dtype, int B, int H, int W, int Ci,
 int64_t lns_conv2d_wgrad_work_bytes(int B, int H, int W, int Cin, int Cout, int KH, int KW);
 int lns_conv2d_wgrad(const float* x, int64_t x_bstride, const float* pro_scale, const float* pro_shift, int pro_act,
                      const float* dy, int64_t dy_bstride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int dil,
-                     int pad_t, int pad_l, int pad_mode_h, int pad_mode_w, float* work, float* dW, void* stream);
-int lns_chan_sum_accum(const float* dy, int64_t bstride, int B, int HW, int C, float* grad, void* stream);
+                     int pad_t, int pad_l, int pad_mode_h, int pad_mode_w, int tensor_core, float out_scale, float* work, float* dW,
+                     void* stream);
+int lns_chan_sum_slices(int B); /* work of lns_chan_sum_accum: lns_chan_sum_slices(B) * C floats */
+int lns_chan_sum_accum(const float* dy, int64_t bstride, int B, int HW, int C, float out_scale, float* work, float* grad,
+                       void* stream);
 int lns_act_bwd(const float* dy, const float* pre, int64_t n, int act, float* dx, void* stream);
 int lns_group_norm_bwd(const float* x, int64_t x_bstride, const float* dy, int64_t dy_bstride, const float* dskip,
                        int64_t dskip_bstride, int B, int HW, int C, int G, float eps, const float* gamma, float* dx,
                        int64_t dx_bstride, float* dgamma_part, float* dbeta_part, void* stream);
-int lns_batch_sum_accum(const float* part, int B, int C, float* grad, void* stream);
+int lns_batch_sum_accum(const float* part, int B, int C, float out_scale, float* grad, void* stream);
+int lns_absmax(const float* x, int64_t n, uint32_t* out_bits, void* stream);
 
 #ifdef __cplusplus
 }

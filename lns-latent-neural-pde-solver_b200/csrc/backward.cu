@@ -107,26 +107,176 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams p) {
   }
 }
 
+// Tensor-core flavour: mma.sync.m16n8k16 on IEEE-half operands, BOTH operands split into hi + lo halves (a = rn(v), lo =
+// rn(v - hi): 22 significant bits; three MMAs per product block, fp32 accumulation -- the split of csrc/conv_coarse.cu).  The
+// split happens ONCE per element when a stage is written to shared memory, as packed pairs of two consecutive pixels (the K
+// dimension), so that a fragment register is one 32-bit shared-memory load.  128 x 128 (o x i) tile, 32 pixels per stage, the
+// next stage's global loads in flight during the MMAs; warp w owns rows 32 (w & 3) .. + 32 and columns 64 (w >> 2) .. + 64.
+// Callers scale dy into the half range (loss scaling, lns_b200/train.py).
+constexpr int kTKc = 32, kTT = 128, kLdP = kTT + 8;  // row stride 136 words: conflict-free fragment loads (bank = 8 t + g)
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack2_h16<true>(a, b);
+  const float2 back = unpack2_h16<true>(hi);
+  lo = pack2_h16<true>(a - back.x, b - back.y);
+}
+__device__ __forceinline__ void bw_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(256) wgrad_tc_kernel(const WgradParams p) {
+  __shared__ __align__(16) uint32_t dyh[kTKc / 2][kLdP], dyl[kTKc / 2][kLdP], xh[kTKc / 2][kLdP], xl[kTKc / 2][kLdP];
+  const ConvGeom& g = p.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile_o = blockIdx.x % p.tiles_o, tile_i = blockIdx.x / p.tiles_o;
+  const int tap = blockIdx.y, split = blockIdx.z;
+  const int ky = tap / g.KW, kx = tap % g.KW;
+  const int o0 = tile_o * kTT, i0 = tile_i * kTT;
+  const int HW = g.Hout * g.Wout;
+  const int64_t k_begin = (int64_t)split * p.pix_per_split;
+  const int64_t k_end = min(p.npix, k_begin + p.pix_per_split);
+  // loader: item = (pixel pair, 4-channel column); 16 pairs x 32 columns = 512 items per operand, two per thread
+  const int lc4 = (tid & 31) * 4;
+  const int gq = lane >> 2, t = lane & 3;
+  const int m0 = (warp & 3) * 32, n0 = (warp >> 2) * 64;
+  float acc[2][8][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
+  const bool o_ok = o0 + lc4 < g.Cout, i_ok = i0 + lc4 < g.Cin;
+  float4 dv[2][2], xv[2][2];  // [item][pixel of the pair], RAW: the prologue is applied when the stage is written (after the
+  int bsel[2][2];             // MMAs of the previous stage), so that these loads stay in flight; bsel = sample index, -1 = zero
+  const int kb32 = (int)k_begin, ke32 = (int)k_end;  // (npix < 2^31 is checked by the launcher: 32-bit index arithmetic)
+  auto load = [&](int k0) {
+    // A warp loads four pixels per stage (pairs warp and warp + 8).  Lane j < 4 does the index arithmetic of pixel j (two
+    // divisions, the padding map) and the warp reads the three results by shuffle: a quarter of the instructions of letting every
+    // lane redo all four (the ncu source page had 46 % of this kernel's samples in that arithmetic).
+    int my_b = -1, my_rem = 0, my_src = -1;
+    {
+      const int j = lane & 3;
+      const int pix = k0 + ((tid >> 5) + (j >> 1) * 8) * 2 + (j & 1);
+      if (pix < ke32) {
+        my_b = pix / HW;
+        my_rem = pix - my_b * HW;
+        const int yo = my_rem / g.Wout, xo = my_rem - yo * g.Wout;
+        int ysrc, xsrc;
+        if (conv_src(g, yo + ky * g.dil - g.pad_t, xo + kx * g.dil - g.pad_l, ysrc, xsrc)) my_src = ysrc * g.Win + xsrc;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int b = __shfl_sync(0xffffffffu, my_b, it * 2 + h);
+        const int rem = __shfl_sync(0xffffffffu, my_rem, it * 2 + h);
+        const int src = __shfl_sync(0xffffffffu, my_src, it * 2 + h);
+        dv[it][h] = xv[it][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bsel[it][h] = -1;
+        if (b >= 0) {
+          if (o_ok) dv[it][h] = __ldg(reinterpret_cast<const float4*>(p.dy + (int64_t)b * p.dy_bstride + (int64_t)rem * g.Cout + o0 + lc4));
+          if (i_ok && src >= 0) {
+            xv[it][h] = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)b * p.x_bstride + (int64_t)src * g.Cin + i0 + lc4));
+            bsel[it][h] = b;
+          }
+        }
+      }
+    }
+  };
+  auto prologue = [&](float4 v, int b) -> float4 {
+    if (b < 0) return v;  // zero padding / outside the slice: stays zero
+    if (p.pro_scale) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pro_scale + (int64_t)b * g.Cin + i0 + lc4));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pro_shift + (int64_t)b * g.Cin + i0 + lc4));
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    }
+    if (p.pro_act != LNS_ACT_NONE) {  // the forward engines on this path use the same fast forms (conv_coarse.cu)
+      v.x = apply_act_fast(v.x, p.pro_act); v.y = apply_act_fast(v.y, p.pro_act);
+      v.z = apply_act_fast(v.z, p.pro_act); v.w = apply_act_fast(v.w, p.pro_act);
+    }
+    return v;
+  };
+  if (kb32 < ke32) load(kb32);
+  for (int k0 = kb32; k0 < ke32; k0 += kTKc) {
+    __syncthreads();  // the previous stage has been consumed
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int pair = (tid >> 5) + it * 8;
+      uint4 h4, l4;
+      split_pack(dv[it][0].x, dv[it][1].x, h4.x, l4.x); split_pack(dv[it][0].y, dv[it][1].y, h4.y, l4.y);
+      split_pack(dv[it][0].z, dv[it][1].z, h4.z, l4.z); split_pack(dv[it][0].w, dv[it][1].w, h4.w, l4.w);
+      *reinterpret_cast<uint4*>(&dyh[pair][lc4]) = h4;
+      *reinterpret_cast<uint4*>(&dyl[pair][lc4]) = l4;
+      const float4 x0 = prologue(xv[it][0], bsel[it][0]), x1 = prologue(xv[it][1], bsel[it][1]);
+      split_pack(x0.x, x1.x, h4.x, l4.x); split_pack(x0.y, x1.y, h4.y, l4.y);
+      split_pack(x0.z, x1.z, h4.z, l4.z); split_pack(x0.w, x1.w, h4.w, l4.w);
+      *reinterpret_cast<uint4*>(&xh[pair][lc4]) = h4;
+      *reinterpret_cast<uint4*>(&xl[pair][lc4]) = l4;
+    }
+    __syncthreads();
+    if (k0 + kTKc < ke32) load(k0 + kTKc);  // in flight during the MMAs below
+#pragma unroll
+    for (int ks = 0; ks < kTKc / 16; ++ks) {
+      // A[m = o][k = pixel]: fragment registers (g, 2t..), (g + 8, 2t..), (g, 2t + 8..), (g + 8, 2t + 8..) = pair rows t, t + 4
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int m = m0 + mt * 16 + gq;
+        ah[mt][0] = dyh[ks * 8 + t][m]; ah[mt][1] = dyh[ks * 8 + t][m + 8]; ah[mt][2] = dyh[ks * 8 + t + 4][m]; ah[mt][3] = dyh[ks * 8 + t + 4][m + 8];
+        al[mt][0] = dyl[ks * 8 + t][m]; al[mt][1] = dyl[ks * 8 + t][m + 8]; al[mt][2] = dyl[ks * 8 + t + 4][m]; al[mt][3] = dyl[ks * 8 + t + 4][m + 8];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int n = n0 + nt * 8 + gq;
+        const uint32_t bh0 = xh[ks * 8 + t][n], bh1 = xh[ks * 8 + t + 4][n], bl0 = xl[ks * 8 + t][n], bl1 = xl[ks * 8 + t + 4][n];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          bw_mma(acc[mt][nt], al[mt], bh0, bh1);
+          bw_mma(acc[mt][nt], ah[mt], bl0, bl1);
+          bw_mma(acc[mt][nt], ah[mt], bh0, bh1);
+        }
+      }
+    }
+  }
+  const int taps = g.KH * g.KW;
+  float* out = p.part + ((int64_t)split * taps + tap) * g.Cout * g.Cin;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int o = o0 + m0 + mt * 16 + gq + half * 8;
+      if (o >= g.Cout) continue;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int i = i0 + n0 + nt * 8 + 2 * t;
+        if (i < g.Cin) out[(int64_t)o * g.Cin + i] = acc[mt][nt][half * 2];
+        if (i + 1 < g.Cin) out[(int64_t)o * g.Cin + i + 1] = acc[mt][nt][half * 2 + 1];
+      }
+    }
+}
+
 // dW[o][i][tap] += sum over the splits, in split order
-__global__ void wgrad_reduce_kernel(const float* part, int nsplit, int taps, int Cout, int Cin, float* dW) {
+__global__ void wgrad_reduce_kernel(const float* part, int nsplit, int taps, int Cout, int Cin, float out_scale, float* dW) {
   const int64_t n = (int64_t)taps * Cout * Cin;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int sp = 0; sp < nsplit; ++sp) s += part[(int64_t)sp * n + e];
     const int tap = (int)(e / ((int64_t)Cout * Cin));
     const int64_t oi = e - (int64_t)tap * Cout * Cin;
-    dW[oi * taps + tap] += s;
+    dW[oi * taps + tap] += s * out_scale;
   }
 }
 
-// grid (ceil(C / 32)), block 256 = 32 channels x 8 pixel lanes: grad[c] += sum_pix dy[pix][c] (fixed order)
-__global__ void __launch_bounds__(256) chan_sum_kernel(const float* dy, int64_t bstride, int B, int HW, int C, float* grad) {
+// grid (ceil(C / 32), NS), block 256 = 32 channels x 8 pixel lanes: part[slice][c] = sum over the slice's samples and all
+// pixels of dy (fixed order); lns_chan_sum_accum then reduces the NS slices with batch_sum_kernel.  (The first version ran
+// ceil(C / 32) CTAs in all: 1.7 ms per bias gradient at 1024 samples.)
+__global__ void __launch_bounds__(256) chan_sum_kernel(const float* dy, int64_t bstride, int B, int HW, int C, float* part) {
   __shared__ float red[8][32];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
   if (c < C)
-    for (int b = 0; b < B; ++b) {
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
       const float* src = dy + (int64_t)b * bstride + c;
       float sb = 0.f;
       for (int pix = pl; pix < HW; pix += 8) sb += __ldg(src + (int64_t)pix * C);
@@ -138,7 +288,7 @@ __global__ void __launch_bounds__(256) chan_sum_kernel(const float* dy, int64_t 
     float t = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += red[j][cl];
-    grad[c] += t;
+    part[(int64_t)blockIdx.y * C + c] = t;
   }
 }
 
@@ -240,13 +390,33 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const float* x, int64_t x_b
   }
 }
 
-// grad[c] += sum_b part[b][c], in batch order; one thread per channel
-__global__ void batch_sum_kernel(const float* part, int B, int C, float* grad) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// grad[c] += out_scale * sum_b part[b][c]; grid ceil(C / 32), block 256 = 32 channels x 8 batch lanes, fixed order
+__global__ void __launch_bounds__(256) batch_sum_kernel(const float* part, int B, int C, float out_scale, float* grad) {
+  __shared__ float red[8][32];
+  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
-  for (int b = 0; b < B; ++b) s += __ldg(part + (int64_t)b * C + c);
-  grad[c] += s;
+  if (c < C)
+    for (int b = bl; b < B; b += 8) s += __ldg(part + (int64_t)b * C + c);
+  red[bl][cl] = s;
+  __syncthreads();
+  if (bl == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][cl];
+    grad[c] += t * out_scale;
+  }
+}
+
+// out (one uint32 word, zero-initialised by the caller) = bit pattern of max |x| (non-negative floats order like integers)
+__global__ void absmax_kernel(const float* x, int64_t n, uint32_t* out) {
+  float m = 0.f;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(x[e]);
+    m = (v > m || v != v) ? v : m;  // NaN propagates (its bit pattern is above every finite value)
+  }
+  m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
 int wgrad_splits(int64_t npix, int tiles, int taps) {
@@ -272,7 +442,8 @@ int64_t lns_conv2d_wgrad_work_bytes(int B, int H, int W, int Cin, int Cout, int 
 
 int lns_conv2d_wgrad(const float* x, int64_t x_bstride, const float* pro_scale, const float* pro_shift, int pro_act,
                      const float* dy, int64_t dy_bstride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int dil,
-                     int pad_t, int pad_l, int pad_mode_h, int pad_mode_w, float* work, float* dW, void* stream) {
+                     int pad_t, int pad_l, int pad_mode_h, int pad_mode_w, int tensor_core, float out_scale, float* work, float* dW,
+                     void* stream) {
   LNS_REQUIRE(x && dy && work && dW && B > 0 && H > 0 && W > 0, "lns_conv2d_wgrad: bad arguments");
   LNS_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "lns_conv2d_wgrad: Cin and Cout must be multiples of 4 (got %d, %d)", Cin, Cout);
   LNS_REQUIRE(x_bstride % 4 == 0 && dy_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
@@ -289,7 +460,8 @@ int lns_conv2d_wgrad(const float* x, int64_t x_bstride, const float* pro_scale, 
   g.KH = KH; g.KW = KW; g.stride = 1; g.dil = dil; g.pad_t = pad_t; g.pad_l = pad_l;
   g.circ_h = pad_mode_h == LNS_PAD_CIRCULAR; g.circ_w = pad_mode_w == LNS_PAD_CIRCULAR;
   g.Hout = H; g.Wout = W; g.Cout = Cout; g.x_bstride = x_bstride; g.y_bstride = dy_bstride;
-  const int tiles_o = (Cout + lns::kTO - 1) / lns::kTO, tiles_i = (Cin + lns::kTI - 1) / lns::kTI;
+  const int tile = tensor_core ? lns::kTT : lns::kTO;
+  const int tiles_o = (Cout + tile - 1) / tile, tiles_i = (Cin + tile - 1) / tile;
   const int taps = KH * KW;
   p.npix = (int64_t)B * H * W;
   p.nsplit = lns::wgrad_splits(p.npix, tiles_o * tiles_i, taps);
@@ -297,18 +469,32 @@ int lns_conv2d_wgrad(const float* x, int64_t x_bstride, const float* pro_scale, 
   p.part = work;
   p.tiles_o = tiles_o;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  lns::wgrad_kernel<<<dim3(tiles_o * tiles_i, taps, p.nsplit), 256, 0, st>>>(p);
+  if (tensor_core) {
+    LNS_REQUIRE(p.npix < (1ll << 31) - lns::kTKc, "lns_conv2d_wgrad: too many pixels for the tensor-core path");
+    p.pix_per_split = ((p.npix + p.nsplit - 1) / p.nsplit + lns::kTKc - 1) / lns::kTKc * lns::kTKc;
+    lns::wgrad_tc_kernel<<<dim3(tiles_o * tiles_i, taps, p.nsplit), 256, 0, st>>>(p);
+  } else {
+    lns::wgrad_kernel<<<dim3(tiles_o * tiles_i, taps, p.nsplit), 256, 0, st>>>(p);
+  }
   int rc = lns::check_launch("wgrad_kernel");
   if (rc != LNS_OK) return rc;
   const int64_t n = (int64_t)taps * Cout * Cin;
-  lns::wgrad_reduce_kernel<<<lns::cdiv(n, 256), 256, 0, st>>>(work, p.nsplit, taps, Cout, Cin, dW);
+  lns::wgrad_reduce_kernel<<<lns::cdiv(n, 256), 256, 0, st>>>(work, p.nsplit, taps, Cout, Cin, out_scale, dW);
   return lns::check_launch("wgrad_reduce_kernel");
 }
 
-int lns_chan_sum_accum(const float* dy, int64_t bstride, int B, int HW, int C, float* grad, void* stream) {
-  LNS_REQUIRE(dy && grad && B > 0 && HW > 0 && C > 0, "lns_chan_sum_accum: bad arguments");
-  lns::chan_sum_kernel<<<(C + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, bstride, B, HW, C, grad);
-  return lns::check_launch("chan_sum_kernel");
+int lns_chan_sum_slices(int B) { return B < 128 ? B : 128; }
+
+int lns_chan_sum_accum(const float* dy, int64_t bstride, int B, int HW, int C, float out_scale, float* work, float* grad,
+                       void* stream) {
+  LNS_REQUIRE(dy && grad && work && B > 0 && HW > 0 && C > 0, "lns_chan_sum_accum: bad arguments");
+  const int ns = lns_chan_sum_slices(B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  lns::chan_sum_kernel<<<dim3((C + 31) / 32, ns), 256, 0, st>>>(dy, bstride, B, HW, C, work);
+  int rc = lns::check_launch("chan_sum_kernel");
+  if (rc != LNS_OK) return rc;
+  lns::batch_sum_kernel<<<(C + 31) / 32, 256, 0, st>>>(work, ns, C, out_scale, grad);
+  return lns::check_launch("batch_sum_kernel");
 }
 
 int lns_act_bwd(const float* dy, const float* pre, int64_t n, int act, float* dx, void* stream) {
@@ -335,9 +521,18 @@ int lns_group_norm_bwd(const float* x, int64_t x_bstride, const float* dy, int64
   return lns::check_launch("gn_bwd_kernel");
 }
 
-int lns_batch_sum_accum(const float* part, int B, int C, float* grad, void* stream) {
+int lns_absmax(const float* x, int64_t n, uint32_t* out_bits, void* stream) {
+  LNS_REQUIRE(x && out_bits && n > 0, "lns_absmax: bad arguments");
+  int blocks = lns::cdiv(n, 1024);
+  const int cap = lns::device_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  lns::absmax_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n, out_bits);
+  return lns::check_launch("absmax_kernel");
+}
+
+int lns_batch_sum_accum(const float* part, int B, int C, float out_scale, float* grad, void* stream) {
   LNS_REQUIRE(part && grad && B > 0 && C > 0, "lns_batch_sum_accum: bad arguments");
-  lns::batch_sum_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, B, C, grad);
+  lns::batch_sum_kernel<<<(C + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, B, C, out_scale, grad);
   return lns::check_launch("batch_sum_kernel");
 }
 

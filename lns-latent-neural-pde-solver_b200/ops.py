@@ -908,9 +908,11 @@ def _f32_nhwc(a, what):
         raise LnsError(f"{what}: fp32 NHWC activations only")
 
 
-def conv2d_wgrad(x, dy, dW, *, KH, KW, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, PAD_ZEROS), pro=None):
-    """dW (torch fp32 [Cout,Cin,KH,KW], accumulated into) += filter gradient of the same-size stride-1 conv whose forward read
-    pro(x) (pro = (scale[B,Cin] | None, shift | None, act)) and whose output gradient is dy.  (lns_conv2d_wgrad)"""
+def conv2d_wgrad(x, dy, dW, *, KH, KW, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, PAD_ZEROS), pro=None, tensor_core=False,
+                 out_scale=1.0):
+    """dW (torch fp32 [Cout,Cin,KH,KW], accumulated into) += out_scale * filter gradient of the same-size stride-1 conv whose
+    forward read pro(x) (pro = (scale[B,Cin] | None, shift | None, act)) and whose output gradient is dy.  tensor_core: TF32
+    mma.sync with hi + lo split operands (fp32-class) instead of CUDA-core FMAs.  (lns_conv2d_wgrad)"""
     _f32_nhwc(x, "conv2d_wgrad")
     _f32_nhwc(dy, "conv2d_wgrad")
     if (x.B, x.H, x.W) != (dy.B, dy.H, dy.W) or tuple(dW.shape) != (dy.C, x.C, KH, KW) or not dW.is_contiguous():
@@ -921,18 +923,21 @@ def conv2d_wgrad(x, dy, dW, *, KH, KW, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZE
     tok = _mark(f"wgrad {KH}x{KW} d{dil} {x.C}->{dy.C} @{x.H}x{x.W}", flops=2.0 * x.B * x.H * x.W * dy.C * KH * KW * x.C,
                 nbytes=_abytes(x, dy))
     rc = _C.lib().lns_conv2d_wgrad(_ptr(x.t), x.bstride, _ptr(sc), _ptr(sh), pa, _ptr(dy.t), dy.bstride, x.B, x.H, x.W, x.C, dy.C,
-                                   KH, KW, dil, pad[0], pad[2], pad_mode[0], pad_mode[1], _ptr(work), _ptr(dW), _stream())
+                                   KH, KW, dil, pad[0], pad[2], pad_mode[0], pad_mode[1], 1 if tensor_core else 0, float(out_scale),
+                                   _ptr(work), _ptr(dW), _stream())
     check(rc, "lns_conv2d_wgrad")
     _done(tok)
     _state.launches += 2
 
 
-def chan_sum_accum(dy, grad):
-    """grad[c] += sum over samples and pixels of dy (bias gradient)."""
+def chan_sum_accum(dy, grad, out_scale=1.0):
+    """grad[c] += out_scale * sum over samples and pixels of dy (bias gradient)."""
     _f32_nhwc(dy, "chan_sum_accum")
-    rc = _C.lib().lns_chan_sum_accum(_ptr(dy.t), dy.bstride, dy.B, dy.H * dy.W, dy.C, _ptr(grad), _stream())
+    work = torch.empty(_C.lib().lns_chan_sum_slices(dy.B) * dy.C, dtype=torch.float32, device=dy.t.device)
+    rc = _C.lib().lns_chan_sum_accum(_ptr(dy.t), dy.bstride, dy.B, dy.H * dy.W, dy.C, float(out_scale), _ptr(work), _ptr(grad),
+                                     _stream())
     check(rc, "lns_chan_sum_accum")
-    _state.launches += 1
+    _state.launches += 2
 
 
 def act_bwd(dy, pre, act):
@@ -948,8 +953,18 @@ def act_bwd(dy, pre, act):
     return out
 
 
-def group_norm_bwd(x, dy, groups, eps, gamma, dskip=None, dgamma=None, dbeta=None):
-    """Gradient of GroupNorm(groups, C, eps)(x) w.r.t. x (+ dskip), and dgamma / dbeta accumulated into the given [C] tensors."""
+def absmax(t):
+    """max |t| of a contiguous fp32 CUDA tensor as a Python float (one kernel + a 4-byte read back: it synchronises)."""
+    out = torch.zeros(1, dtype=torch.int32, device=t.device)
+    rc = _C.lib().lns_absmax(_ptr(t), t.numel(), _ptr(out), _stream())
+    check(rc, "lns_absmax")
+    _state.launches += 1
+    return float(out.view(torch.float32).item())
+
+
+def group_norm_bwd(x, dy, groups, eps, gamma, dskip=None, dgamma=None, dbeta=None, out_scale=1.0):
+    """Gradient of GroupNorm(groups, C, eps)(x) w.r.t. x (+ dskip), and out_scale * (dgamma, dbeta) accumulated into the given
+    [C] tensors."""
     _f32_nhwc(x, "group_norm_bwd")
     _f32_nhwc(dy, "group_norm_bwd")
     out = x.like()
@@ -965,7 +980,7 @@ def group_norm_bwd(x, dy, groups, eps, gamma, dskip=None, dgamma=None, dbeta=Non
     _state.launches += 1
     if dgamma is not None:
         for part, grad in ((part_g, dgamma), (part_b, dbeta)):
-            rc = _C.lib().lns_batch_sum_accum(_ptr(part), x.B, x.C, _ptr(grad), _stream())
+            rc = _C.lib().lns_batch_sum_accum(_ptr(part), x.B, x.C, float(out_scale), _ptr(grad), _stream())
             check(rc, "lns_batch_sum_accum")
             _state.launches += 1
     return out

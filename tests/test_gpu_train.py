@@ -50,7 +50,8 @@ def ref_conv(x, w, b, mode, dil):
                                    (5, 8, 8, 16, 128, 1, 1, "zeros"), (5, 8, 8, 128, 16, 1, 1, "zeros"),
                                    (130, 8, 8, 128, 128, 3, 1, "circular")])
 @pytest.mark.parametrize("with_pro", [False, True])
-def test_conv_wgrad_and_bias_grad(shape, with_pro):
+@pytest.mark.parametrize("tc", [False, True])
+def test_conv_wgrad_and_bias_grad(shape, with_pro, tc):
     ops = ops_mod()
     B, H, W, Ci, Co, k, dil, mode = shape
     g = torch.Generator().manual_seed(B * 31 + Ci + dil)
@@ -67,11 +68,22 @@ def test_conv_wgrad_and_bias_grad(shape, with_pro):
     db = torch.full((Co,), -1.0, dtype=torch.float32, device=DEV)
     pro = (sc.float().to(DEV).contiguous(), sh.float().to(DEV).contiguous(), ops.ACT_GELU) if with_pro else None
     dya = nhwc(dy)
-    ops.conv2d_wgrad(nhwc(x), dya, dW, KH=k, KW=k, dil=dil, pad=(p, p, p, p), pad_mode=PAD[mode], pro=pro)
-    ops.chan_sum_accum(dya, db)
+    # tc: TF32 mma.sync with hi + lo split operands; out_scale: the 1 / loss-scale factor of a scaled backward pass
+    ops.conv2d_wgrad(nhwc(x), dya, dW, KH=k, KW=k, dil=dil, pad=(p, p, p, p), pad_mode=PAD[mode], pro=pro, tensor_core=tc,
+                     out_scale=0.5 if tc else 1.0)
+    ops.chan_sum_accum(dya, db, out_scale=0.5 if tc else 1.0)
     torch.cuda.synchronize()
-    assert rel(dW - 0.25, w.grad) < 3e-6
-    assert rel(db + 1.0, b.grad) < 3e-6
+    f = 0.5 if tc else 1.0
+    assert rel(dW - 0.25, f * w.grad) < (5e-6 if tc else 3e-6)
+    assert rel(db + 1.0, f * b.grad) < 3e-6
+
+
+def test_absmax():
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(2)
+    t = torch.randn(3, 5, 16, 8, 8, generator=g) * 1e-5
+    t[1, 2, 3, 4, 5] = -7.25e-3
+    assert ops.absmax(t.to(DEV).contiguous()) == pytest.approx(7.25e-3, rel=1e-7)
 
 
 @pytest.mark.parametrize("act", ["gelu", "silu"])
@@ -102,7 +114,7 @@ def test_group_norm_bwd(case, skip):
     dgam = torch.zeros(C, dtype=torch.float32, device=DEV)
     dbet = torch.zeros(C, dtype=torch.float32, device=DEV)
     out = ops.group_norm_bwd(nhwc(x.detach()), nhwc(dy), G, eps, gamma.detach().float().to(DEV), dskip=nhwc(ds) if skip else None,
-                             dgamma=dgam, dbeta=dbet)
+                             dgamma=dgam, dbeta=dbet, out_scale=1.0)
     got = out.to_torch_nhwc().permute(0, 3, 1, 2)
     want = x.grad + (ds if skip else 0)
     assert rel(got, want) < 3e-6
