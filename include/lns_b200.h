@@ -368,6 +368,12 @@ int lns_group_norm_bwd(const float* x, int64_t x_bstride, const float* dy, int64
                        int64_t dx_bstride, float* dgamma_part, float* dbeta_part, void* stream);
 int lns_batch_sum_accum(const float* part, int B, int C, float out_scale, float* grad, void* stream);
 int lns_absmax(const float* x, int64_t n, uint32_t* out_bits, void* stream);
+/* conditional propagator (train_stage2_twophase_conditional.py:66-75): out[b][c] (+)= sum_pix dy[b][pix][c] * (x ? x[b][pix][c] : 1)
+ * -- gradient of the per-sample shift Linear(emb) (x NULL) and of the gate (1 + g) (x = the gated activation); C divides 256.
+ * lns_scale_add: out = x * scale[b][c] + skip (scale / skip may be NULL), contiguous fp32 [B][HW][C] */
+int lns_pixel_dot(const float* dy, int64_t dy_bstride, const float* x, int64_t x_bstride, int B, int HW, int C, int accumulate,
+                  float* out, void* stream);
+int lns_scale_add(const float* x, const float* scale, const float* skip, int B, int HW, int C, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,8 @@ SIGNATURES = {
     "lns_group_norm_bwd": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp, vp, i64, vp, vp, vp]),
     "lns_batch_sum_accum": (i32, [vp, i32, i32, f32, vp, vp]),
     "lns_absmax": (i32, [vp, i64, vp, vp]),
+    "lns_pixel_dot": (i32, [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp]),
+    "lns_scale_add": (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),
 }
 
 _lib = None

@@ -419,6 +419,49 @@ __global__ void absmax_kernel(const float* x, int64_t n, uint32_t* out) {
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
+// grid B, block 256 (needs 256 % C == 0): out[b][c] (+)= sum_pix dy[b][pix][c] * (x ? x[b][pix][c] : 1), pixels in a fixed order.
+// x == null: gradient of a per-sample bias broadcast over the pixels; x != null: gradient of a per-(sample, channel) gate.
+__global__ void __launch_bounds__(256) pixel_dot_kernel(const float* dy, int64_t dy_bstride, const float* x, int64_t x_bstride, int HW,
+                                                         int C, int accumulate, float* out) {
+  __shared__ float red[256];
+  const int b = blockIdx.x, c = threadIdx.x % C, lp = threadIdx.x / C, np = 256 / C;
+  const float* dyb = dy + (int64_t)b * dy_bstride;
+  const float* xb = x ? x + (int64_t)b * x_bstride : nullptr;
+  float s = 0.f;
+  for (int pix = lp; pix < HW; pix += np) {
+    const float d = __ldg(dyb + (int64_t)pix * C + c);
+    s = xb ? fmaf(d, __ldg(xb + (int64_t)pix * C + c), s) : s + d;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+    for (int j = 0; j < np; ++j) t += red[j * C + threadIdx.x];
+    float* o = out + (int64_t)b * C + threadIdx.x;
+    *o = accumulate ? *o + t : t;
+  }
+}
+
+// out = x * (scale ? scale[b][c] : 1) + (skip ? skip : 0), elementwise over [B][HW][C]
+__global__ void scale_add_kernel(const float4* x, const float* scale, const float4* skip, int64_t per_sample4, int C, int64_t total4,
+                                 float4* out) {
+  const int c4n = C >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(x + i);
+    if (scale) {
+      const int64_t b = i / per_sample4;
+      const int c = (int)((i - b * per_sample4) % c4n) * 4;
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + b * C + c));
+      v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+    }
+    if (skip) {
+      const float4 k = __ldg(skip + i);
+      v.x += k.x; v.y += k.y; v.z += k.z; v.w += k.w;
+    }
+    out[i] = v;
+  }
+}
+
 int wgrad_splits(int64_t npix, int tiles, int taps) {
   // enough CTAs for ~4 per SM, at least 256 pixels per slice
   const int sms = device_sm_count();
@@ -519,6 +562,26 @@ int lns_group_norm_bwd(const float* x, int64_t x_bstride, const float* dy, int64
   lns::gn_bwd_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_bstride, dy, dy_bstride, dskip, dskip_bstride, HW, C,
                                                                               G, eps, gamma, dx, dx_bstride, dgamma_part, dbeta_part);
   return lns::check_launch("gn_bwd_kernel");
+}
+
+int lns_pixel_dot(const float* dy, int64_t dy_bstride, const float* x, int64_t x_bstride, int B, int HW, int C, int accumulate,
+                  float* out, void* stream) {
+  LNS_REQUIRE(dy && out && B > 0 && HW > 0 && C > 0 && C <= 256 && 256 % C == 0, "lns_pixel_dot: bad arguments (C must divide 256)");
+  lns::pixel_dot_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, dy_bstride, x, x_bstride, HW, C, accumulate, out);
+  return lns::check_launch("pixel_dot_kernel");
+}
+
+int lns_scale_add(const float* x, const float* scale, const float* skip, int B, int HW, int C, float* out, void* stream) {
+  LNS_REQUIRE(x && out && B > 0 && HW > 0 && C > 0 && C % 4 == 0, "lns_scale_add: bad arguments");
+  LNS_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(skip) |
+                reinterpret_cast<uintptr_t>(scale)) & 15) == 0, "lns_scale_add: pointers must be 16-byte aligned");
+  const int64_t per4 = (int64_t)HW * C / 4, total4 = per4 * B;
+  int blocks = lns::cdiv(total4, 256);
+  const int cap = lns::device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  lns::scale_add_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), scale, reinterpret_cast<const float4*>(skip), per4, C, total4, reinterpret_cast<float4*>(out));
+  return lns::check_launch("scale_add_kernel");
 }
 
 int lns_absmax(const float* x, int64_t n, uint32_t* out_bits, void* stream) {

@@ -73,13 +73,12 @@ class LatentDynamics(nn.Module):
         """Reference signature: forward(z_in, z_out, loss_fn) (train_stage2_ns2d.py:126-141): teacher-free rollout training --
         t_out autoregressive propagator steps from z_in [b, 1, c, h, w], loss_fn(z_pred [b, t_out, c, h, w], z_out).  The rollout
         and its back-propagation run on the library's kernels as one autograd node (lns_b200.train)."""
-        if self.kind == "twophase_cond":
-            raise NotImplementedError("the conditional propagator has no backward kernels yet (forward(z_in, z_out, param, loss_fn))")
         loss_fn = args[-1]
+        param = args[0] if self.kind == "twophase_cond" else None   # forward(z_in, z_out, param, loss_fn) (conditional script :160)
         if z_in.shape[1] != 1:
             raise ValueError("z_in must hold exactly one input frame: [b, 1, c, h, w]")
         from .train import rollout_train
-        z_pred = rollout_train(self.propagator, z_in[:, 0], z_out.shape[1])
+        z_pred = rollout_train(self.propagator, z_in[:, 0], z_out.shape[1], param=param)
         return loss_fn(z_pred, z_out)
 
     @torch.no_grad()

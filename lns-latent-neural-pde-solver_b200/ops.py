@@ -962,6 +962,30 @@ def absmax(t):
     return float(out.view(torch.float32).item())
 
 
+def pixel_dot(dy, x, out, accumulate=True):
+    """out[b][c] (+)= sum over pixels of dy * x (x None: of dy): gradients of a per-sample shift / gate.  out: torch fp32 [B*C]."""
+    _f32_nhwc(dy, "pixel_dot")
+    if x is not None:
+        _f32_nhwc(x, "pixel_dot")
+    rc = _C.lib().lns_pixel_dot(_ptr(dy.t), dy.bstride, _ptr(x.t) if x is not None else None, x.bstride if x is not None else 0,
+                                dy.B, dy.H * dy.W, dy.C, 1 if accumulate else 0, _ptr(out), _stream())
+    check(rc, "lns_pixel_dot")
+    _state.launches += 1
+
+
+def scale_add(x, scale=None, skip=None):
+    """x * scale[b][c] + skip as a new contiguous fp32 Act."""
+    _f32_nhwc(x, "scale_add")
+    if not x.contiguous or (skip is not None and not skip.contiguous):
+        raise LnsError("scale_add: contiguous activations only")
+    out = x.like()
+    rc = _C.lib().lns_scale_add(_ptr(x.t), _ptr(scale), _ptr(skip.t) if skip is not None else None, x.B, x.H * x.W, x.C, _ptr(out.t),
+                                _stream())
+    check(rc, "lns_scale_add")
+    _state.launches += 1
+    return out
+
+
 def group_norm_bwd(x, dy, groups, eps, gamma, dskip=None, dgamma=None, dbeta=None, out_scale=1.0):
     """Gradient of GroupNorm(groups, C, eps)(x) w.r.t. x (+ dskip), and out_scale * (dgamma, dbeta) accumulated into the given
     [C] tensors."""

@@ -3,7 +3,10 @@
     LatentDynamics.forward(z_in, z_out, loss_fn)          train_stage2_ns2d.py:126-141, train_stage2_SW.py:126-142,
         z_pred = stack_t propagator^t(z_in);  loss_fn(z_pred, z_out)      train_stage2_twophase.py:126-142
 
-i.e. back-propagation through t_out autoregressive steps of ``SimpleCNN`` (train_stage2_ns2d.py:25-87).  The whole rollout is
+i.e. back-propagation through t_out autoregressive steps of ``SimpleCNN`` (train_stage2_ns2d.py:25-87), and the conditional
+variant ``forward(z_in, z_out, param, loss_fn)`` (train_stage2_twophase_conditional.py:160-175, blocks :25-75): there the
+step-invariant conditioning network (embedding MLP, per-block shift Linear and gate cond_conv2) runs once per rollout, the
+gradients that reach its outputs are summed over the steps by lns_pixel_dot and back-propagated once.  The whole rollout is
 ONE autograd node: its forward runs the steps on the library's conv / norm kernels and keeps, per step, only what the backward
 needs (block inputs, pre-activations and their GELU outputs, the folded GroupNorm affines); its backward walks the steps in reverse on the kernels of
 csrc/backward.cu -- filter gradients (lns_conv2d_wgrad, accumulating over steps into one buffer per parameter), GroupNorm /
@@ -25,6 +28,7 @@ import math
 import ctypes
 
 import torch
+import torch.nn as nn
 
 from . import _C, ops
 from .ops import Act, LnsError
@@ -87,6 +91,19 @@ def step_fwd(net, z, tape):
     return cl(a, net.out_proj[1], pro=(so, to, ops.ACT_NONE), out_dtype=_F32)
 
 
+def _geo(mod):
+    """stride / dilation / padding of an nn.Conv2d holder; an nn.Linear is a 1x1 convolution on [B, 1, 1, C] rows"""
+    if isinstance(mod, nn.Linear):
+        return dict(stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(ops.PAD_ZEROS, ops.PAD_ZEROS))
+    return _mods().conv_geometry(mod)
+
+
+def _fwd(x, mod, **kw):
+    geo = _geo(mod)
+    geo.update(kw)
+    return ops.conv2d(x, _mods().filt_of(mod), out_dtype=_F32, **geo)
+
+
 def _dgrad_filter(conv):
     """PackedFilter of the adjoint convolution: W'[i][o][ky][kx] = W[o][i][KH-1-ky][KW-1-kx] (data movement only)."""
     B_ = _mods()
@@ -94,9 +111,14 @@ def _dgrad_filter(conv):
     f = c.get("dgrad_filter")
     if f is None or c.get("dgrad_src") is not conv.weight:
         w = conv.weight
-        Cout, Cin, KH, KW = w.shape
-        f = ops.PackedFilter(lambda: w.detach().flip(2, 3).transpose(0, 1).contiguous(), None,
-                             lambda: (ops.PackedFilter._fp(w),), (Cin, Cout, KH, KW))
+        if w.dim() == 2:
+            Cout, Cin = w.shape
+            f = ops.PackedFilter(lambda: w.detach().t()[:, :, None, None].contiguous(), None,
+                                 lambda: (ops.PackedFilter._fp(w),), (Cin, Cout, 1, 1))
+        else:
+            Cout, Cin, KH, KW = w.shape
+            f = ops.PackedFilter(lambda: w.detach().flip(2, 3).transpose(0, 1).contiguous(), None,
+                                 lambda: (ops.PackedFilter._fp(w),), (Cin, Cout, KH, KW))
         c["dgrad_filter"], c["dgrad_src"] = f, w
     return f
 
@@ -110,19 +132,19 @@ class _Bw:
 
 
 def _dgrad(conv, dy, bw, residual=None):
-    geo = _mods().conv_geometry(conv)
+    geo = _geo(conv)
     # tensor-core mode: engine chosen by ops.conv2d inside the hi region (fp32 storage, split operands); else the exact engine
     return ops.conv2d(dy, _dgrad_filter(conv), use_bias=False, residual=residual, out_dtype=_F32,
                       engine=None if bw.tc else ops.ENGINE_SIMT, **geo)
 
 
 def _wgrad(conv, x, pro, dy, bw):
-    geo = _mods().conv_geometry(conv)
+    geo = _geo(conv)
     gw = bw.G.get(id(conv.weight))
     if gw is not None:
-        kh, kw = conv.kernel_size
-        ops.conv2d_wgrad(x, dy, gw, KH=kh, KW=kw, dil=geo["dil"], pad=geo["pad"], pad_mode=geo["pad_mode"], pro=pro,
-                         tensor_core=bw.tc, out_scale=bw.inv)
+        kh, kw = (1, 1) if isinstance(conv, nn.Linear) else conv.kernel_size
+        ops.conv2d_wgrad(x, dy, gw.view(gw.shape[0], gw.shape[1], kh, kw), KH=kh, KW=kw, dil=geo["dil"], pad=geo["pad"],
+                         pad_mode=geo["pad_mode"], pro=pro, tensor_core=bw.tc, out_scale=bw.inv)
     if conv.bias is not None and id(conv.bias) in bw.G:
         ops.chan_sum_accum(dy, bw.G[id(conv.bias)], out_scale=bw.inv)
 
@@ -161,32 +183,157 @@ def step_bwd(net, tape, dzo, bw, extra=None):
     return _dgrad(net.in_proj, da, bw, residual=extra)
 
 
+
+# ---- conditional propagator (train_stage2_twophase_conditional.py:25-121) ---------------------------------------------------
+def _gelu(x):
+    return ops.affine_act(x, None, None, ops.ACT_GELU, out_dtype=_F32)
+
+
+class _CondTape:
+    """Step-invariant conditioning network of one rollout: cond = MLP(fourier_embedding(param)); per block shift =
+    Linear(cond) and gate = cond_conv2(shift) (reference :66-75, :114-116), with what its backward needs."""
+    __slots__ = ("emb", "e1pre", "e1", "cond", "blocks")
+
+
+def cond_prepare_fwd(net, param):
+    from modules.cond_utils import fourier_embedding
+    ct = _CondTape()
+    ct.emb = ops.rows_act(fourier_embedding(param, dim=net.cond_emb_dim))
+    l1, _, l2 = net.cond_emb_proj
+    ct.e1pre = _fwd(ct.emb, l1)
+    ct.e1 = _gelu(ct.e1pre)
+    ct.cond = _fwd(ct.e1, l2)
+    ct.blocks = []
+    for blk in net.net:
+        shift = _fwd(ct.cond, blk.cond_emb)                                     # [B,1,1,C]
+        gn, c1, _, c2 = blk.cond_conv2
+        sg, tg = _affine(shift, gn)
+        g1pre = _fwd(shift, c1, pro=(sg, tg, ops.ACT_NONE))
+        g1 = _gelu(g1pre)
+        gate = _fwd(g1, c2)
+        ones = torch.ones_like(gate.t)
+        onep = ops.affine_act(gate, ones, ones, ops.ACT_NONE, out_dtype=_F32)   # 1 + gate
+        ct.blocks.append((shift, sg, tg, g1pre, g1, onep))
+    return ct
+
+
+def cond_step_fwd(net, z, ct, tape):
+    """One conditional SimpleCNN step (reference :66-75 per block, :117-121), recording the tape."""
+    a = _fwd(z, net.in_proj)
+    tape.z = z
+    for blk, cb in zip(net.net, ct.blocks):
+        shift, onep = cb[0], cb[5]
+        gn1, c1, _, c2 = blk.conv1
+        s1, t1 = _affine(a, gn1)
+        p1 = _fwd(a, c1, pro=(s1, t1, ops.ACT_NONE))
+        h1 = _gelu(p1)
+        p2 = _fwd(h1, c2, sample_bias=shift.t)
+        gnb, _, cz = blk.cond_conv1
+        sb, tb = _affine(p2, gnb)
+        nb = ops.affine_act(p2, sb, tb, ops.ACT_NONE, out_dtype=_F32)
+        hb = _gelu(nb)
+        x2 = _fwd(hb, cz, residual=a)
+        hin = ops.scale_add(x2, scale=onep.t)                                   # x2 * (1 + gate)
+        gn2, f1, _, f2 = blk.ffn
+        s2, t2 = _affine(hin, gn2)
+        q1 = _fwd(hin, f1, pro=(s2, t2, ops.ACT_NONE))
+        hq = _gelu(q1)
+        x3 = _fwd(hq, f2, residual=x2)
+        tape.blocks.append((a, s1, t1, p1, h1, p2, nb, hb, x2, hin, s2, t2, q1, hq))
+        a = x3
+    so, to = _affine(a, net.out_proj[0])
+    tape.last = (a, so, to)
+    return _fwd(a, net.out_proj[1], pro=(so, to, ops.ACT_NONE))
+
+
+def cond_step_bwd(net, ct, tape, dzo, bw, acc, extra=None):
+    """Backward of cond_step_fwd; acc[i] = (dshift [B*C], dgate [B*C]) accumulate the gradients that reach block i's
+    conditioning vectors (summed over the rollout steps, back-propagated once by cond_prepare_bwd)."""
+    a, so, to = tape.last
+    _wgrad(net.out_proj[1], a, (so, to, ops.ACT_NONE), dzo, bw)
+    da = _gn_bwd(net.out_proj[0], a, _dgrad(net.out_proj[1], dzo, bw), None, bw)
+    for i in range(len(net.net) - 1, -1, -1):
+        blk, cb = net.net[i], ct.blocks[i]
+        onep = cb[5]
+        x, s1, t1, p1, h1, p2, nb, hb, x2, hin, s2, t2, q1, hq = tape.blocks[i]
+        gn1, c1, _, c2 = blk.conv1
+        gnb, _, cz = blk.cond_conv1
+        gn2, f1, _, f2 = blk.ffn
+        # x3 = x2 + f2(gelu(q1)),  q1 = f1(GN2(x2 * (1 + gate)))
+        _wgrad(f2, hq, None, da, bw)
+        dq1 = ops.act_bwd(_dgrad(f2, da, bw), q1, ops.ACT_GELU)
+        _wgrad(f1, hin, (s2, t2, ops.ACT_NONE), dq1, bw)
+        dhin = _gn_bwd(gn2, hin, _dgrad(f1, dq1, bw), None, bw)
+        ops.pixel_dot(dhin, x2, acc[i][1])                                      # d (1 + gate)
+        dx2 = ops.scale_add(dhin, scale=onep.t, skip=da)
+        # x2 = x + cz(gelu(GNb(p2))),  p2 = c2(gelu(p1)) + shift,  p1 = c1(GN1(x))
+        _wgrad(cz, hb, None, dx2, bw)
+        dnb = ops.act_bwd(_dgrad(cz, dx2, bw), nb, ops.ACT_GELU)
+        dp2 = _gn_bwd(gnb, p2, dnb, None, bw)
+        ops.pixel_dot(dp2, None, acc[i][0])                                     # d shift
+        _wgrad(c2, h1, None, dp2, bw)
+        dp1 = ops.act_bwd(_dgrad(c2, dp2, bw), p1, ops.ACT_GELU)
+        _wgrad(c1, x, (s1, t1, ops.ACT_NONE), dp1, bw)
+        da = _gn_bwd(gn1, x, _dgrad(c1, dp1, bw), dx2, bw)
+    _wgrad(net.in_proj, tape.z, None, da, bw)
+    return _dgrad(net.in_proj, da, bw, residual=extra)
+
+
+def cond_prepare_bwd(net, ct, acc, bw):
+    """Back-propagate the accumulated shift / gate gradients through cond_conv2, the per-block Linear and the embedding MLP."""
+    B = ct.cond.B
+    dcond = None
+    for i in range(len(net.net) - 1, -1, -1):
+        blk = net.net[i]
+        shift, sg, tg, g1pre, g1, _ = ct.blocks[i]
+        C = shift.C
+        dshift_acc = Act(acc[i][0], B, 1, 1, C)
+        dgate = Act(acc[i][1], B, 1, 1, C)
+        gn, c1, _, c2 = blk.cond_conv2
+        _wgrad(c2, g1, None, dgate, bw)
+        dg1pre = ops.act_bwd(_dgrad(c2, dgate, bw), g1pre, ops.ACT_GELU)
+        _wgrad(c1, shift, (sg, tg, ops.ACT_NONE), dg1pre, bw)
+        dshift = _gn_bwd(gn, shift, _dgrad(c1, dg1pre, bw), dshift_acc, bw)
+        _wgrad(blk.cond_emb, ct.cond, None, dshift, bw)
+        dcond = _dgrad(blk.cond_emb, dshift, bw, residual=dcond)
+    l1, _, l2 = net.cond_emb_proj
+    _wgrad(l2, ct.e1, None, dcond, bw)
+    de1pre = ops.act_bwd(_dgrad(l2, dcond, bw), ct.e1pre, ops.ACT_GELU)
+    _wgrad(l1, ct.emb, None, de1pre, bw)
+
+
 def _check_net(net):
-    ok = (hasattr(net, "in_proj") and hasattr(net, "net") and hasattr(net, "out_proj") and not hasattr(net, "cond_emb_proj")
-          and all(hasattr(b, "conv") and hasattr(b, "ffn") and len(b.conv) == 6 and len(b.ffn) == 4 for b in net.net))
-    if not ok:
-        raise NotImplementedError("the training rollout is implemented for the unconditional SimpleCNN propagator "
-                                  "(train_stage2_ns2d.py / _SW.py / _twophase.py); the conditional variant has no backward yet")
+    """-> True for the conditional propagator, False for the unconditional one; raises for anything else."""
+    base = hasattr(net, "in_proj") and hasattr(net, "net") and hasattr(net, "out_proj")
+    if base and hasattr(net, "cond_emb_proj"):
+        if all(hasattr(b, "conv1") and hasattr(b, "cond_conv1") and hasattr(b, "cond_conv2") and hasattr(b, "cond_emb")
+               and hasattr(b, "ffn") for b in net.net):
+            return True
+    elif base and all(hasattr(b, "conv") and hasattr(b, "ffn") and len(b.conv) == 6 and len(b.ffn) == 4 for b in net.net):
+        return False
+    raise NotImplementedError("the training rollout is implemented for the SimpleCNN propagators of the stage-2 scripts "
+                              "(train_stage2_ns2d.py / _SW.py / _twophase.py and the conditional _twophase_conditional.py)")
 
 
 class _RolloutFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, net, z0, t_out, *params):
+    def forward(ctx, net, z0, t_out, param, *params):
         ops._need_cuda(z0, "rollout_train")
         B, C, h, w = z0.shape
         z_pred = torch.empty(B, t_out, C, h, w, dtype=_F32, device=z0.device)
         tapes = []
         with ops.device_of(z0), _region():
             z = ops.nchw_to_act(z0.detach(), _F32)
+            ct = cond_prepare_fwd(net, param.detach().float().contiguous()) if param is not None else None
             for t in range(t_out):
                 tape = _Tape()
-                z = step_fwd(net, z, tape)
+                z = cond_step_fwd(net, z, ct, tape) if ct is not None else step_fwd(net, z, tape)
                 tapes.append(tape)
                 dst = ctypes.c_void_p(z_pred.data_ptr() + t * C * h * w * 4)
                 rc = _C.lib().lns_nhwc_to_nchw(ops._ptr(z.t), z.dtype, B, h, w, C, z.bstride, dst, t_out * C * h * w, ops._stream())
                 _C.check(rc, "lns_nhwc_to_nchw")
                 ops._state.launches += 1
-        ctx.net, ctx.tapes, ctx.params, ctx.shape = net, tapes, params, (B, t_out, C, h, w)
+        ctx.net, ctx.tapes, ctx.params, ctx.shape, ctx.ct = net, tapes, params, (B, t_out, C, h, w), ct
         ctx.need_z0 = z0.requires_grad
         ctx.precision = ops.get_precision()
         return z_pred
@@ -216,23 +363,34 @@ class _RolloutFn(torch.autograd.Function):
                 ops._state.launches += 1
                 return ops.affine_act(out, sc, zs, ops.ACT_NONE, out_dtype=_F32) if sc is not None else out
 
+            ct = ctx.ct
+            acc = None
+            if ct is not None:
+                Cp = ct.blocks[0][0].C
+                acc = [(torch.zeros(B * Cp, dtype=_F32, device=dz_pred.device), torch.zeros(B * Cp, dtype=_F32, device=dz_pred.device))
+                       for _ in net.net]
             dz = loss_grad(T - 1)
             for t in range(T - 1, -1, -1):
-                dz = step_bwd(net, tapes[t], dz, bw, extra=loss_grad(t - 1) if t > 0 else None)
+                ex = loss_grad(t - 1) if t > 0 else None
+                dz = cond_step_bwd(net, ct, tapes[t], dz, bw, acc, extra=ex) if ct is not None else step_bwd(net, tapes[t], dz, bw, extra=ex)
+            if ct is not None:
+                cond_prepare_bwd(net, ct, acc, bw)
             dz0 = None
             if ctx.need_z0:
                 if sc is not None:
                     sc.fill_(1.0 / S)
                     dz = ops.affine_act(dz, sc, zs, ops.ACT_NONE, out_dtype=_F32)
                 dz0 = dz.to_nchw()
-        ctx.tapes = None
-        return (None, dz0, None) + tuple(G.get(id(p)) for p in params)
+        ctx.tapes = ctx.ct = None
+        return (None, dz0, None, None) + tuple(G.get(id(p)) for p in params)
 
 
-def rollout_train(net, z0, t_out):
-    """z_pred [B, t_out, C, h, w] = the t_out autoregressive steps of `net` (a SimpleCNN) from z0 [B, C, h, w], differentiable
-    w.r.t. the propagator's parameters (and z0)."""
-    _check_net(net)
+def rollout_train(net, z0, t_out, param=None):
+    """z_pred [B, t_out, C, h, w] = the t_out autoregressive steps of `net` (a SimpleCNN of the stage-2 scripts; the conditional
+    one takes `param` [B]) from z0 [B, C, h, w], differentiable w.r.t. the propagator's parameters (and z0)."""
+    cond = _check_net(net)
+    if cond != (param is not None):
+        raise LnsError("rollout_train: `param` goes with the conditional propagator (and only with it)")
     if z0.dim() != 4:
         raise LnsError("rollout_train: z0 must be [B, C, h, w]")
-    return _RolloutFn.apply(net, z0.contiguous().float(), int(t_out), *list(net.parameters()))
+    return _RolloutFn.apply(net, z0.contiguous().float(), int(t_out), param, *list(net.parameters()))

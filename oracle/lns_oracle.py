@@ -459,13 +459,14 @@ def make_inputs(cfg, batch, seed=0):
 # ------------------------------------------------------------------------------------------------------------------
 # training rollout (LatentDynamics.forward: train_stage2_ns2d.py:126-141, _SW.py / _twophase.py :126-142)
 # ------------------------------------------------------------------------------------------------------------------
-def train_rollout(sd, cfg, z0, t_out, prefix="propagator."):
+def train_rollout(sd, cfg, z0, t_out, prefix="propagator.", param=None):
     """z_pred [b, t_out, c, h, w]: t_out autoregressive propagator steps from z0 [b, c, h, w] (differentiable: the gradient
     oracle is torch autograd of this restatement, pinned against autograd of the unmodified reference by
-    tests/golden/train_grads.pt)."""
+    tests/golden/train_grads.pt).  `param` [b]: the conditional model (train_stage2_twophase_conditional.py:160-175)."""
     z, out = z0, []
+    cond = cond_embedding(sd, cfg, param, z0.dtype, prefix) if param is not None else None
     for _ in range(t_out):
-        z = propagator_step(sd, cfg, z, None, prefix)
+        z = propagator_step(sd, cfg, z, cond, prefix)
         out.append(z)
     return torch.stack(out, dim=1)
 

@@ -19,7 +19,7 @@ import ref_shims  # noqa: E402
 import lns_oracle as O  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
-CASES = {"ns2d": (3, 3), "sw": (2, 2), "twophase": (2, 2)}  # (batch, t_out)
+CASES = {"ns2d": (3, 3), "sw": (2, 2), "twophase": (2, 2), "twophase_cond": (2, 2)}  # (batch, t_out)
 
 
 def main():
@@ -36,7 +36,16 @@ def main():
         for p in m64.parameters():
             p.requires_grad_(p is not None)
         m64.zero_grad()
-        loss = m64(z_in.double(), z_out.double(), F.smooth_l1_loss)
+        if name == "twophase_cond":
+            # the reference's fourier_embedding always returns fp32 (modules/cond_utils.py:34): cast it up for the fp64 copy
+            script = ref_shims.load_script(name)
+            orig = script.fourier_embedding
+            script.fourier_embedding = lambda t, dim: orig(t, dim).double()
+            param = torch.linspace(0.3, 0.9, B)
+            loss = m64(z_in.double(), z_out.double(), param.double(), F.smooth_l1_loss)
+            script.fourier_embedding = orig
+        else:
+            loss = m64(z_in.double(), z_out.double(), F.smooth_l1_loss)
         loss.backward()
         entry = {"batch": B, "t_out": T, "loss": float(loss), "norm": {}, "probe": {}, "full": {}}
         for k, p in m64.propagator.named_parameters():

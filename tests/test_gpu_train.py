@@ -135,10 +135,10 @@ def build(name):
     return _cache[name]
 
 
-def oracle_grads(cfg, sd, z_in, z_out, loss_fn):
+def oracle_grads(cfg, sd, z_in, z_out, loss_fn, param=None):
     sd64 = {k: v.double().requires_grad_(k.startswith("propagator.")) for k, v in sd.items()}
     z0 = z_in[:, 0].double().requires_grad_(True)
-    loss = loss_fn(O.train_rollout(sd64, cfg, z0, z_out.shape[1]), z_out.double())
+    loss = loss_fn(O.train_rollout(sd64, cfg, z0, z_out.shape[1], param=None if param is None else param.double()), z_out.double())
     loss.backward()
     return float(loss), {k[len("propagator."):]: v.grad for k, v in sd64.items() if k.startswith("propagator.")}, z0.grad
 
@@ -148,7 +148,7 @@ def rel_loss(pred, gt):  # training_utils.py:9-23 with reduce_all=True
     return d.sqrt().mean()
 
 
-@pytest.mark.parametrize("name,B,T", [("ns2d", 3, 3), ("sw", 2, 2), ("twophase", 2, 2), ("ns2d", 12, 2)])
+@pytest.mark.parametrize("name,B,T", [("ns2d", 3, 3), ("sw", 2, 2), ("twophase", 2, 2), ("ns2d", 12, 2), ("twophase_cond", 3, 2)])
 @pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("fp16s", 5e-5)])
 def test_training_rollout_gradients(name, B, T, mode, tol):
     """loss and d loss / d parameter of LatentDynamics.forward vs fp64 autograd of the oracle (every parameter of the propagator)."""
@@ -156,14 +156,18 @@ def test_training_rollout_gradients(name, B, T, mode, tol):
     cfg, model, sd = build(name)
     z_in, z_out = O.train_inputs(cfg, B, T, seed=B)
     loss_fn = F.smooth_l1_loss if B != 12 else rel_loss
-    want_loss, want, _ = oracle_grads(cfg, sd, z_in, z_out, loss_fn)
+    param = torch.linspace(0.25, 0.85, B) if name == "twophase_cond" else None
+    want_loss, want, _ = oracle_grads(cfg, sd, z_in, z_out, loss_fn, param)
     for p in model.parameters():
         p.requires_grad_(True)
     for p in model.autoencoder.parameters():
         p.requires_grad_(False)
     model.zero_grad(set_to_none=True)
     with ops.precision(mode):
-        loss = model(z_in.to(DEV), z_out.to(DEV), loss_fn)
+        if param is None:
+            loss = model(z_in.to(DEV), z_out.to(DEV), loss_fn)
+        else:
+            loss = model(z_in.to(DEV), z_out.to(DEV), param.to(DEV), loss_fn)
         loss.backward()
     torch.cuda.synchronize()
     assert abs(loss.item() - want_loss) <= tol * abs(want_loss)
@@ -222,7 +226,17 @@ def test_training_step_reduces_loss():
     assert losses[-1] < 0.8 * losses[0]
 
 
-def test_conditional_training_not_implemented():
-    cfg, model, _ = build("twophase_cond")
-    with pytest.raises(NotImplementedError):
-        model(torch.zeros(2, 1, 64, 7, 15, device=DEV), torch.zeros(2, 2, 64, 7, 15, device=DEV), torch.zeros(2, device=DEV), F.mse_loss)
+def test_pixel_dot_and_scale_add():
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(9)
+    B, C, H, W = 3, 128, 7, 15
+    dy = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    sc = torch.randn(B, C, generator=g, dtype=torch.float64)
+    out = torch.full((B * C,), 2.0, dtype=torch.float32, device=DEV)
+    ops.pixel_dot(nhwc(dy), nhwc(x), out, accumulate=True)
+    assert rel(out.view(B, C) - 2.0, (dy * x).sum(dim=(2, 3))) < 3e-6
+    ops.pixel_dot(nhwc(dy), None, out, accumulate=False)
+    assert rel(out.view(B, C), dy.sum(dim=(2, 3))) < 3e-6
+    y = ops.scale_add(nhwc(dy), scale=sc.float().to(DEV).reshape(-1).contiguous(), skip=nhwc(x))
+    assert rel(y.to_torch_nhwc().permute(0, 3, 1, 2), dy * sc[:, :, None, None] + x) < 1e-6

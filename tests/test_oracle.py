@@ -92,7 +92,7 @@ def test_upsample_phase_decomposition(circular):
         assert (got - ref).abs().max().item() < 1e-12
 
 
-@pytest.mark.parametrize("name", ["ns2d", "sw", "twophase"])
+@pytest.mark.parametrize("name", ["ns2d", "sw", "twophase", "twophase_cond"])
 def test_oracle_training_gradients_vs_reference(name, golden_dir):
     """Gradient oracle (torch autograd of O.train_rollout, fp64) vs loss / parameter gradients of the unmodified reference's
     LatentDynamics.forward(z_in, z_out, F.smooth_l1_loss) (tests/golden/train_grads.pt, oracle/make_golden_train.py)."""
@@ -105,13 +105,16 @@ def test_oracle_training_gradients_vs_reference(name, golden_dir):
     sd = O.randomize_zero_init(LatentDynamics(cfg).state_dict())
     sd64 = {k: v.double().requires_grad_(k.startswith("propagator.")) for k, v in sd.items()}
     z_in, z_out = O.train_inputs(cfg, fix["batch"], fix["t_out"], seed=0)
-    loss = F.smooth_l1_loss(O.train_rollout(sd64, cfg, z_in[:, 0].double(), fix["t_out"]), z_out.double())
+    param = torch.linspace(0.3, 0.9, fix["batch"]).double() if name == "twophase_cond" else None
+    loss = F.smooth_l1_loss(O.train_rollout(sd64, cfg, z_in[:, 0].double(), fix["t_out"], param=param), z_out.double())
     loss.backward()
-    assert abs(float(loss) - fix["loss"]) < 1e-12
+    # (the conditional model's sinusoidal embedding is computed in fp32 by the reference: ~1e-8 there)
+    tol = 1e-6 if name == "twophase_cond" else 1e-9
+    assert abs(float(loss) - fix["loss"]) < tol * 1e-3
     for k, n in fix["norm"].items():
         g = sd64["propagator." + k].grad
-        assert abs(float(g.norm()) - n) <= 1e-9 * max(n, 1e-30), k
+        assert abs(float(g.norm()) - n) <= tol * max(n, 1e-30), k
         pr = float((g * O.grad_probe(k, g.shape)).sum())
-        assert abs(pr - fix["probe"][k]) <= 1e-9 * max(n, 1e-30) * g.numel() ** 0.5, k
+        assert abs(pr - fix["probe"][k]) <= tol * max(n, 1e-30) * g.numel() ** 0.5, k
         if k in fix["full"]:
-            assert (g - fix["full"][k]).abs().max().item() <= 1e-10 * max(n, 1e-30), k
+            assert (g - fix["full"][k]).abs().max().item() <= tol * max(n, 1e-30), k
