@@ -129,10 +129,11 @@ typedef struct LnsConvDesc {
   int32_t y_dtype, y_layout;
   int32_t Hout, Wout, Cout;
   int64_t y_bstride;
-  /* optional by-product (LNS_ENGINE_COARSE only, else must be NULL): per-channel partial sums of the OUTPUT as stored,
-   * stats[b][chunk][c] = (sum, sum of squares) over the chunk's pixels, chunk = 4 * (8x8 block of the sample) + epilogue warp,
-   * lns_conv_stats_chunks(Hout, Wout) chunks per sample -- the statistics of the GroupNorm that follows (lns_norm_finalize)
-   * without another read of the tensor (modules/basics.py:246-252: GroupNorm -> Swish -> Conv, twice per ResidualBlock) */
+  /* optional by-product (LNS_ENGINE_COARSE only, else must be NULL): per-channel CENTRED partial sums of the OUTPUT as stored,
+   * stats[b][chunk][c] = (sum d, sum d^2, pivot, count) as float4 with d = y - pivot over the chunk's pixels, chunk =
+   * 4 * (8x8 block of the sample) + epilogue warp, lns_conv_stats_chunks(Hout, Wout) chunks per sample -- the statistics of the
+   * GroupNorm that follows (lns_norm_finalize_centred) without another read of the tensor (modules/basics.py:246-252:
+   * GroupNorm -> Swish -> Conv, twice per ResidualBlock) */
   float* stats;
 } LnsConvDesc;
 
@@ -164,6 +165,10 @@ int lns_chan_stats(const void* x, int dtype, int B, int H, int W, int C, int64_t
 int lns_norm_finalize(const float* partial, int B, int nchunk, int C, int HW, int G, float eps,
                       const float* gamma, const float* beta, const float* prescale, float* scale,
                       float* shift, void* stream);
+/* same from the centred partials of LnsConvDesc.stats ([b][chunk][c] float4 = sum d, sum d^2, pivot, count) */
+int lns_norm_finalize_centred(const float* partial, int B, int nchunk, int C, int HW, int G, float eps,
+                              const float* gamma, const float* beta, const float* prescale, float* scale,
+                              float* shift, void* stream);
 /* statistics + finalize in one call: one fused kernel when the sample has <= 1024 pixels (lns_chan_stats_chunks == 1),
  * otherwise lns_chan_stats + lns_norm_finalize through `partial_ws` (B*nchunk*C*2 floats; may be NULL when nchunk == 1) */
 int lns_group_norm_affine(const void* x, int dtype, int B, int H, int W, int C, int64_t bstride, int G, float eps,

@@ -49,6 +49,7 @@ SIGNATURES = {
     "lns_chan_stats_chunks": (i32, [i32, i32]),
     "lns_chan_stats": (i32, [vp, i32, i32, i32, i32, i32, i64, vp, vp]),
     "lns_norm_finalize": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
+    "lns_norm_finalize_centred": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
     "lns_group_norm_affine": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, f32, vp, vp, vp, vp, vp, vp, vp]),
     "lns_group_norm_act_supported": (i32, [i32, i32, i32]),
     "lns_group_norm_act": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, f32, vp, vp, vp, i32, vp, i32, i64, vp]),

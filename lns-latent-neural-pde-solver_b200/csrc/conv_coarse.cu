@@ -137,7 +137,7 @@ struct CoarseParams {
   int64_t res_bstride;
   void* y;
   int y_dtype;
-  float* stats;        // [B][nb * 4][Cout][2] per-channel partial sums of the stored output, or null
+  float* stats;        // [B][nb * 4][Cout][4] per-channel centred partial sums (sum d, sum d^2, pivot, count) of the stored output, or null
   int x_f16;           // operands are IEEE half (else bf16)
   int slabs;           // Cin / 64
   int nbx, nby, nb;    // 8x8 blocks per sample: columns, rows, total
@@ -497,13 +497,19 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
             }
           }
           if (p.stats) {
-            // per-channel (sum, sum of squares) over the warp's 16 pixels of this block: a halving butterfly over lane bits
-            // 4, 2, 1, 0 (bit 3 = the block slot is not reduced) -- 30 shuffles per quantity instead of 128; the lane ends up with
-            // channels c0 + 16 b4 + 8 b2 + 4 b1 + 2 b0 + {0, 1}
-            float s[32], q[32];
+            // per-channel statistics over the warp's 16 pixels of this block, CENTRED on a pivot (the channel's value at the
+            // chunk's first pixel): (sum d, sum d^2, pivot, count) with d = v - pivot.  Squaring the raw values instead loses
+            // E[x^2] / var * 2^-24 of the variance -- 7e-4 of rstd on groups whose mean is 50 sigma (measured in the decoder's 16x16
+            // level), which showed as a 1.5x larger 20-step drift.  Reduction: a halving butterfly over lane bits 4, 2, 1, 0 (bit
+            // 3 = the block slot is not reduced), 30 shuffles per quantity instead of 128; the lane ends up with channels
+            // c0 + 16 b4 + 8 b2 + 4 b1 + 2 b0 + {0, 1}.
+            float s[32], q[32], pv[32];
+            const int src_lane = lane & 8;  // first row of this slot in the warp (always a valid pixel if any row of the chunk is)
+            const float cnt = (float)__popc(__ballot_sync(0xffffffffu, row_ok) & (slot ? 0xff00ff00u : 0x00ff00ffu));
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              s[j] = row_ok ? v[j] : 0.f;
+              pv[j] = __shfl_sync(0xffffffffu, v[j], src_lane);
+              s[j] = row_ok ? v[j] - pv[j] : 0.f;
               q[j] = s[j] * s[j];
             }
 #pragma unroll
@@ -517,12 +523,14 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) conv_coarse_kernel(const Co
                 const float kq = up ? q[j + half] : q[j], sq = up ? q[j] : q[j + half];
                 s[j] = ks + __shfl_xor_sync(0xffffffffu, ss, bit);
                 q[j] = kq + __shfl_xor_sync(0xffffffffu, sq, bit);
+                pv[j] = up ? pv[j + half] : pv[j];               // (the pivot is uniform over the slot's lanes: a select, no shuffle)
               }
             }
             if (blk_ok) {
               const int cb = c0 + ((lane >> 4) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
-              float* dst = p.stats + ((((int64_t)b * p.nb + blk_in_sample) * 4 + quad) * g.Cout + cb) * 2;
-              *reinterpret_cast<float4*>(dst) = make_float4(s[0], q[0], s[1], q[1]);
+              float4* dst = reinterpret_cast<float4*>(p.stats + ((((int64_t)b * p.nb + blk_in_sample) * 4 + quad) * g.Cout + cb) * 4);
+              dst[0] = make_float4(s[0], q[0], pv[0], cnt);
+              dst[1] = make_float4(s[1], q[1], pv[1], cnt);
             }
           }
         }

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const void* __restrict_
 // per group combines the group's channels in channel order (fp64) into mean / rstd.  Pass 3: thread per channel writes the
 // folded affine.  (The first version gave a whole warp to each group: with 4 channels per group 28 of 32 lanes idled through
 // dependent loads and fp64 shuffles -- 52 us for 4736 samples; this one is bandwidth-trivial.)
+template <bool PIV>
 __global__ void __launch_bounds__(256) norm_finalize_kernel(const float2* __restrict__ partial, int nchunk, int C, int HW,
                                                              int G, float eps, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta,
@@ -74,9 +75,17 @@ __global__ void __launch_bounds__(256) norm_finalize_kernel(const float2* __rest
   for (int c = threadIdx.x; c < C; c += 256) {
     double cs = 0.0, css = 0.0;
     for (int k = 0; k < nchunk; ++k) {
-      const float2 v = partial[((int64_t)b * nchunk + k) * C + c];
-      cs += (double)v.x;
-      css += (double)v.y;
+      if (PIV) {
+        // centred partials (sum d, sum d^2, pivot p, count n), x = p + d: exact recombination in fp64
+        const float4 v = reinterpret_cast<const float4*>(partial)[((int64_t)b * nchunk + k) * C + c];
+        const double sd = (double)v.x, pp = (double)v.z, n = (double)v.w;
+        cs += sd + n * pp;
+        css += (double)v.y + 2.0 * pp * sd + n * pp * pp;
+      } else {
+        const float2 v = partial[((int64_t)b * nchunk + k) * C + c];
+        cs += (double)v.x;
+        css += (double)v.y;
+      }
     }
     const double ps = prescale ? (double)prescale[(int64_t)b * C + c] : 1.0;
     csum[2 * c] = ps * cs;
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(256) norm_finalize_kernel(const float2* __rest
     }
     const double n = (double)cpg * (double)HW;
     const double mean = sum / n;
-    double var = sumsq / n - mean * mean;
+    double var = sumsq / n - mean * mean;  // fp64: the cancellation costs E[x^2] / var * 2^-53
     if (var < 0.0) var = 0.0;
     gst[2 * gi] = mean;
     gst[2 * gi + 1] = 1.0 / sqrt(var + (double)eps);
@@ -251,7 +260,17 @@ int lns_norm_finalize(const float* partial, int B, int nchunk, int C, int HW, in
                       const float* beta, const float* prescale, float* scale, float* shift, void* stream) {
   LNS_REQUIRE(partial && scale && shift && B > 0 && C > 0 && G > 0 && C % G == 0, "lns_norm_finalize: bad arguments");
   LNS_REQUIRE((size_t)(2 * C + 2 * G) * sizeof(double) <= 48 * 1024, "lns_norm_finalize: C = %d too large", C);
-  lns::norm_finalize_kernel<<<B, 256, (size_t)(2 * C + 2 * G) * sizeof(double), reinterpret_cast<cudaStream_t>(stream)>>>(
+  lns::norm_finalize_kernel<false><<<B, 256, (size_t)(2 * C + 2 * G) * sizeof(double), reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(partial), nchunk, C, HW, G, eps, gamma, beta, prescale, scale, shift);
+  return lns::check_launch("norm_finalize_kernel");
+}
+
+int lns_norm_finalize_centred(const float* partial, int B, int nchunk, int C, int HW, int G, float eps, const float* gamma,
+                              const float* beta, const float* prescale, float* scale, float* shift, void* stream) {
+  LNS_REQUIRE(partial && scale && shift && B > 0 && C > 0 && G > 0 && C % G == 0, "lns_norm_finalize_centred: bad arguments");
+  LNS_REQUIRE((size_t)(2 * C + 2 * G) * sizeof(double) <= 48 * 1024, "lns_norm_finalize_centred: C = %d too large", C);
+  LNS_REQUIRE((reinterpret_cast<uintptr_t>(partial) & 15) == 0, "lns_norm_finalize_centred: partials must be 16-byte aligned");
+  lns::norm_finalize_kernel<true><<<B, 256, (size_t)(2 * C + 2 * G) * sizeof(double), reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float2*>(partial), nchunk, C, HW, G, eps, gamma, beta, prescale, scale, shift);
   return lns::check_launch("norm_finalize_kernel");
 }

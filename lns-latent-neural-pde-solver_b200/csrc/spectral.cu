@@ -501,9 +501,13 @@ int launch_dft(DftParams& p, cudaStream_t st, const char* what) {
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   int64_t grid = (int64_t)device_sm_count() * per_sm;
   if (grid > p.ntasks) grid = p.ntasks;
-  static const bool x1 = getenv("LNS_SPECTRAL_TF32X1") != nullptr;  // experiment: single TF32 pass (1e-3-class error)
-  if (x1) dft_gemm_kernel<false><<<(int)grid, kDftThreads, smem, st>>>(p);
-  else dft_gemm_kernel<true><<<(int)grid, kDftThreads, smem, st>>>(p);
+#ifdef LNS_SPECTRAL_X1_BUILD  // experiment (a -DLNS_SPECTRAL_X1_BUILD build only): single TF32 pass, 1e-3-class error
+  if (getenv("LNS_SPECTRAL_TF32X1")) {
+    dft_gemm_kernel<false><<<(int)grid, kDftThreads, smem, st>>>(p);
+    return check_launch(what);
+  }
+#endif
+  dft_gemm_kernel<true><<<(int)grid, kDftThreads, smem, st>>>(p);
   return check_launch(what);
 }
 

@@ -533,7 +533,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
     if hi and engine == ENGINE_COARSE and _state.coarse_stats and out.layout == NHWC and out.group is None:
         # the statistics of the GroupNorm that follows, from the epilogue's registers
         nchunk = _C.lib().lns_conv_stats_chunks(Hout, Wout)
-        part = torch.empty(x.B * nchunk * Cout * 2, dtype=torch.float32, device=x.t.device)
+        part = torch.empty(x.B * nchunk * Cout * 4, dtype=torch.float32, device=x.t.device)
         d.stats = part.data_ptr()
         out.stats = (part, nchunk)
     tok = _mark(f"conv e{engine} {KH}x{KW} s{stride} d{dil} {Cin}->{Cout} @{Hout}x{Wout}"
@@ -603,9 +603,9 @@ def group_norm_affine(x, groups, eps, gamma=None, beta=None, prescale=None):
         # the producing kernel left per-channel partial sums: only the finalize runs (no read of x)
         part, nchunk = x.stats
         tok = _mark(f"gn_finalize C{x.C} @{x.H}x{x.W}", nbytes=4.0 * part.numel())
-        rc = _C.lib().lns_norm_finalize(_ptr(part), x.B, nchunk, x.C, x.H * x.W, groups, float(eps), _ptr(g), _ptr(b), _ptr(prescale),
-                                        _ptr(scale), _ptr(shift), _stream())
-        check(rc, "lns_norm_finalize")
+        rc = _C.lib().lns_norm_finalize_centred(_ptr(part), x.B, nchunk, x.C, x.H * x.W, groups, float(eps), _ptr(g), _ptr(b),
+                                                _ptr(prescale), _ptr(scale), _ptr(shift), _stream())
+        check(rc, "lns_norm_finalize_centred")
         _done(tok)
         _state.launches += 1
         return scale, shift
