@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) axial_contract_kernel(const void* __restr
 // grid (ceil(lines/8), heads, B), block 128: a CTA stages K (bf16) and 8 line slabs in shared memory with cp.async,
 // each warp owns 2 lines; mma.sync.m16n8k16 (bf16 x bf16 -> fp32) with ldmatrix / ldmatrix.trans operand fetch; results
 // go through a per-warp staging tile so that every global store is a full 128-byte channel row.
-constexpr int kAxLines = 8;      // lines per CTA
+constexpr int kAxLines = 8;      // lines per CTA (LPC = 4 for long lines: three CTAs per SM instead of one)
 constexpr int kAxSlabStride = 72;  // bf16 elements per slab row (64 + 8 pad: conflict-free ldmatrix)
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -184,7 +184,7 @@ __device__ __forceinline__ void mma_h16_16816(float* c, const uint32_t* a, uint3
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <bool F16>
+template <bool F16, int LPC>
 __global__ void __launch_bounds__(128) axial_contract_mma_kernel(const __nv_bfloat16* __restrict__ u, int H, int W, int heads,
                                                                   const float* __restrict__ Kmat, int axis,
                                                                   __nv_bfloat16* __restrict__ out) {
@@ -195,21 +195,44 @@ __global__ void __launch_bounds__(128) axial_contract_mma_kernel(const __nv_bflo
   const int kstride = n16 + 8;
   __nv_bfloat16* K_s = reinterpret_cast<__nv_bfloat16*>(smraw);
   __nv_bfloat16* slab = K_s + (size_t)n16 * kstride;                             // [kAxLines][n16][72]
-  __nv_bfloat16* stage = slab + (size_t)kAxLines * n16 * kAxSlabStride;            // [4 warps][16][72]
+  __nv_bfloat16* stage = slab + (size_t)LPC * n16 * kAxSlabStride;            // [4 warps][16][72]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int line0 = blockIdx.x * kAxLines, h = blockIdx.y, b = blockIdx.z;
+  const int line0 = blockIdx.x * LPC, h = blockIdx.y, b = blockIdx.z;
   const int C = heads * 64;
   const int64_t sbase = (int64_t)b * H * W * C + h * 64;
 
   // K (fp32) -> bf16, zero padded to n16 x n16
   const float* Kg = Kmat + ((int64_t)b * heads + h) * n * n;
-  for (int e = tid; e < n16 * n16; e += 128) {
-    int i = e / n16, j = e - i * n16;
-    float v = (i < n && j < n) ? __ldg(Kg + i * n + j) : 0.f;
-    reinterpret_cast<uint16_t*>(K_s)[i * kstride + j] = to_h16<F16>(v);
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(Kg) & 15) == 0) {
+    // 16-byte loads, four in flight per thread (the scalar loop below is one dependent 4-byte load per element: at n = 96 that
+    // was 72 exposed global-memory latencies per CTA, most of the kernel's 3.7 ms per launch on the 48x96 shallow-water level)
+    const int q16 = n16 >> 2, total = n16 * q16;
+    for (int e0 = tid; e0 < total; e0 += 4 * 128) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * 128;
+        const int i = e / q16, j = (e - i * q16) * 4;
+        v[u] = (e < total && i < n && j < n) ? __ldg(reinterpret_cast<const float4*>(Kg + i * n + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * 128;
+        if (e < total) {
+          const int i = e / q16, j = (e - i * q16) * 4;
+          *reinterpret_cast<uint2*>(K_s + i * kstride + j) = make_uint2(pack2_h16<F16>(v[u].x, v[u].y), pack2_h16<F16>(v[u].z, v[u].w));
+        }
+      }
+    }
+  } else {
+    for (int e = tid; e < n16 * n16; e += 128) {
+      int i = e / n16, j = e - i * n16;
+      float v = (i < n && j < n) ? __ldg(Kg + i * n + j) : 0.f;
+      reinterpret_cast<uint16_t*>(K_s)[i * kstride + j] = to_h16<F16>(v);
+    }
   }
   // slabs: 8 x 16-byte chunks per (line, j) row
-  const int nl = min(kAxLines, lines - line0);
+  const int nl = min(LPC, lines - line0);
   for (int e = tid; e < nl * n16 * 8; e += 128) {
     int ch = e & 7;
     int r = e >> 3;
@@ -230,7 +253,7 @@ __global__ void __launch_bounds__(128) axial_contract_mma_kernel(const __nv_bflo
 
   __nv_bfloat16* my_stage = stage + (size_t)warp * 16 * kAxSlabStride;
   const int ktiles = n16 >> 4;
-  for (int l = warp * 2; l < warp * 2 + 2 && l < nl; ++l) {
+  for (int l = warp * (LPC / 4); l < (warp + 1) * (LPC / 4) && l < nl; ++l) {
     const __nv_bfloat16* sl = slab + (size_t)l * n16 * kAxSlabStride;
     const int line = line0 + l;
     for (int mt = 0; mt < ktiles; ++mt) {
@@ -559,12 +582,22 @@ int lns_axial_contract(const void* u, int dtype, int B, int H, int W, int heads,
     // tensor-core path (the bf16 rollout)
     int n16 = (n + 15) & ~15;
     int lines = axis == 0 ? W : H;
-    size_t smem_mma = ((size_t)n16 * (n16 + 8) + (size_t)lns::kAxLines * n16 * lns::kAxSlabStride +
+    // long lines (n16 >= 64: the 48x96 shallow-water level): 4 lines per CTA so that three CTAs share an SM -- with 8 the 130 KB
+    // slab left ONE 4-warp CTA per SM and every load / ldmatrix latency exposed (3.4 ms per launch at 320 x 48x96 x 512)
+    const int lpc = n16 >= 64 ? 4 : lns::kAxLines;
+    size_t smem_mma = ((size_t)n16 * (n16 + 8) + (size_t)lpc * n16 * lns::kAxSlabStride +
                        4 * 16 * (size_t)lns::kAxSlabStride) * sizeof(__nv_bfloat16);
     LNS_REQUIRE(smem_mma <= 227 * 1024, "lns_axial_contract: n=%d needs %zu B shared memory", n, smem_mma);
-    { LNS_OPT_IN_SMEM((lns::axial_contract_mma_kernel<false>), 227 * 1024, "attention"); LNS_OPT_IN_SMEM((lns::axial_contract_mma_kernel<true>), 227 * 1024, "attention"); }
-    dim3 grid(lns::cdiv(lines, lns::kAxLines), heads, B);
-    auto kern = dtype == LNS_F16 ? lns::axial_contract_mma_kernel<true> : lns::axial_contract_mma_kernel<false>;
+    {
+      LNS_OPT_IN_SMEM((lns::axial_contract_mma_kernel<false, 8>), 227 * 1024, "attention");
+      LNS_OPT_IN_SMEM((lns::axial_contract_mma_kernel<true, 8>), 227 * 1024, "attention");
+      LNS_OPT_IN_SMEM((lns::axial_contract_mma_kernel<false, 4>), 227 * 1024, "attention");
+      LNS_OPT_IN_SMEM((lns::axial_contract_mma_kernel<true, 4>), 227 * 1024, "attention");
+    }
+    dim3 grid(lns::cdiv(lines, lpc), heads, B);
+    const bool f16 = dtype == LNS_F16;
+    auto kern = lpc == 4 ? (f16 ? lns::axial_contract_mma_kernel<true, 4> : lns::axial_contract_mma_kernel<false, 4>)
+                         : (f16 ? lns::axial_contract_mma_kernel<true, 8> : lns::axial_contract_mma_kernel<false, 8>);
     kern<<<grid, 128, smem_mma, s>>>(reinterpret_cast<const __nv_bfloat16*>(u), H, W, heads, K, axis,
                                                                reinterpret_cast<__nv_bfloat16*>(out));
     return lns::check_launch("axial_contract_mma_kernel");
