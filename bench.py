@@ -74,8 +74,11 @@ def load_peaks():
             "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
 
 
+_GATHER_KIND = [None]  # class name of the gather object bench.py actually built (P2PGather | OverlappedGather)
+
+
 def _gather_label():
-    return ("copy-engine pushes into CUDA symmetric memory (lns_b200.dist.P2PGather)" if os.environ.get("LNS_GATHER", "p2p") == "p2p"
+    return ("copy-engine pushes into CUDA symmetric memory (lns_b200.dist.P2PGather)" if _GATHER_KIND[0] == "P2PGather"
             else "NCCL all_gather_into_tensor")
 
 
@@ -378,6 +381,7 @@ def main():
     # N > 1: the final all-gather of the predicted fields (NCCL over NVLink) of step i runs on NCCL's stream out of a staging
     # copy while the rollout of step i+1 computes; the timed region ends when the last gather has completed.
     og = make_gather((B, R, ro.C, ro.Ly, ro.Lx), torch.float32, device) if gather else None
+    _GATHER_KIND[0] = type(og).__name__ if og is not None else None
 
     def one_step():
         out = ro(x_dev, p_dev)

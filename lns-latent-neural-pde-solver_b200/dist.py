@@ -137,7 +137,20 @@ def make_gather(local_shape, dtype, device, group=None):
     want = os.environ.get("LNS_GATHER", "p2p")
     if (want == "p2p" and dist.is_initialized() and dist.get_world_size(group) > 1 and torch.device(device).type == "cuda"
             and dist.get_backend(group) == "nccl"):
-        return P2PGather(local_shape, dtype, device, group)
+        # symmetric memory needs peer access between every pair of ranks of the group (one NVLink / NVSwitch node); where the
+        # rendezvous is refused (no P2P, a group spanning nodes) EVERY rank takes the NCCL transport -- the vote keeps them in step
+        try:
+            og = P2PGather(local_shape, dtype, device, group)
+            ok = 1
+        except Exception as ex:  # noqa: BLE001
+            og, ok = None, 0
+            err = repr(ex)[:200]
+        vote = torch.tensor([ok], device=device)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN, group=group)
+        if int(vote.item()) == 1:
+            return og
+        if dist.get_rank(group) == 0:
+            print(f"lns_b200.dist: symmetric-memory gather unavailable ({err if not ok else 'on another rank'}); using NCCL", flush=True)
     return OverlappedGather(local_shape, dtype, device, group)
 
 
