@@ -362,17 +362,22 @@ int lns_spectral_conv2d(const void* x, int x_dtype, int B, int H, int W, int Ci,
 int64_t lns_conv2d_wgrad_work_bytes(int B, int H, int W, int Cin, int Cout, int KH, int KW);
 int lns_conv2d_wgrad(const float* x, int64_t x_bstride, const float* pro_scale, const float* pro_shift, int pro_act,
                      const float* dy, int64_t dy_bstride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int dil,
-                     int pad_t, int pad_l, int pad_mode_h, int pad_mode_w, int tensor_core, float out_scale, float* work, float* dW,
-                     void* stream);
+                     int pad_t, int pad_l, int pad_mode_h, int pad_mode_w, int tensor_core, float out_scale,
+                     const float* out_scale_dev, float* work, float* dW, void* stream);
 int lns_chan_sum_slices(int B); /* work of lns_chan_sum_accum: lns_chan_sum_slices(B) * C floats */
-int lns_chan_sum_accum(const float* dy, int64_t bstride, int B, int HW, int C, float out_scale, float* work, float* grad,
-                       void* stream);
+int lns_chan_sum_accum(const float* dy, int64_t bstride, int B, int HW, int C, float out_scale, const float* out_scale_dev,
+                       float* work, float* grad, void* stream);
 int lns_act_bwd(const float* dy, const float* pre, int64_t n, int act, float* dx, void* stream);
 int lns_group_norm_bwd(const float* x, int64_t x_bstride, const float* dy, int64_t dy_bstride, const float* dskip,
                        int64_t dskip_bstride, int B, int HW, int C, int G, float eps, const float* gamma, float* dx,
                        int64_t dx_bstride, float* dgamma_part, float* dbeta_part, void* stream);
-int lns_batch_sum_accum(const float* part, int B, int C, float out_scale, float* grad, void* stream);
+int lns_batch_sum_accum(const float* part, int B, int C, float out_scale, const float* out_scale_dev, float* grad, void* stream);
 int lns_absmax(const float* x, int64_t n, uint32_t* out_bits, void* stream);
+/* device-side loss scale (no host synchronisation: the scaled backward pass can be captured in a CUDA graph): s2[0] = S, s2[1] =
+ * 1 / S, S = the power of two that brings the absmax (bit pattern from lns_absmax) to about `target`; lns_scale_by: out = x * (*s).
+ * The accumulating functions above multiply by out_scale * (out_scale_dev ? *out_scale_dev : 1). */
+int lns_loss_scale(const uint32_t* absmax_bits, float target, float* s2, void* stream);
+int lns_scale_by(const float* x, const float* scalar_dev, int64_t n, float* out, void* stream);
 /* conditional propagator (train_stage2_twophase_conditional.py:66-75): out[b][c] (+)= sum_pix dy[b][pix][c] * (x ? x[b][pix][c] : 1)
  * -- gradient of the per-sample shift Linear(emb) (x NULL) and of the gate (1 + g) (x = the gated activation); C divides 256.
  * lns_scale_add: out = x * scale[b][c] + skip (scale / skip may be NULL), contiguous fp32 [B][HW][C] */

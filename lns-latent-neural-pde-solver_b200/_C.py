@@ -83,12 +83,14 @@ SIGNATURES = {
     "lns_spectral_work_bytes": (i64, [i32, i32, i32, i32, i32, i32, i32]),
     "lns_spectral_conv2d": (i32, [vp] + [i32] * 8 + [vp] * 5),
     "lns_conv2d_wgrad_work_bytes": (i64, [i32] * 7),
-    "lns_conv2d_wgrad": (i32, [vp, i64, vp, vp, i32, vp, i64] + [i32] * 13 + [f32, vp, vp, vp]),
+    "lns_conv2d_wgrad": (i32, [vp, i64, vp, vp, i32, vp, i64] + [i32] * 13 + [f32, vp, vp, vp, vp]),
     "lns_chan_sum_slices": (i32, [i32]),
-    "lns_chan_sum_accum": (i32, [vp, i64, i32, i32, i32, f32, vp, vp, vp]),
+    "lns_chan_sum_accum": (i32, [vp, i64, i32, i32, i32, f32, vp, vp, vp, vp]),
     "lns_act_bwd": (i32, [vp, vp, i64, i32, vp, vp]),
     "lns_group_norm_bwd": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp, vp, i64, vp, vp, vp]),
-    "lns_batch_sum_accum": (i32, [vp, i32, i32, f32, vp, vp]),
+    "lns_batch_sum_accum": (i32, [vp, i32, i32, f32, vp, vp, vp]),
+    "lns_loss_scale": (i32, [vp, f32, vp, vp]),
+    "lns_scale_by": (i32, [vp, vp, i64, vp, vp]),
     "lns_absmax": (i32, [vp, i64, vp, vp]),
     "lns_pixel_dot": (i32, [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp]),
     "lns_scale_add": (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),

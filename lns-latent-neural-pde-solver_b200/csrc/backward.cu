@@ -256,8 +256,10 @@ __global__ void __launch_bounds__(256) wgrad_tc_kernel(const WgradParams p) {
 }
 
 // dW[o][i][tap] += sum over the splits, in split order
-__global__ void wgrad_reduce_kernel(const float* part, int nsplit, int taps, int Cout, int Cin, float out_scale, float* dW) {
+__global__ void wgrad_reduce_kernel(const float* part, int nsplit, int taps, int Cout, int Cin, float out_scale,
+                                    const float* out_scale_dev, float* dW) {
   const int64_t n = (int64_t)taps * Cout * Cin;
+  if (out_scale_dev) out_scale *= __ldg(out_scale_dev);
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int sp = 0; sp < nsplit; ++sp) s += part[(int64_t)sp * n + e];
@@ -391,8 +393,10 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const float* x, int64_t x_b
 }
 
 // grad[c] += out_scale * sum_b part[b][c]; grid ceil(C / 32), block 256 = 32 channels x 8 batch lanes, fixed order
-__global__ void __launch_bounds__(256) batch_sum_kernel(const float* part, int B, int C, float out_scale, float* grad) {
+__global__ void __launch_bounds__(256) batch_sum_kernel(const float* part, int B, int C, float out_scale, const float* out_scale_dev,
+                                                        float* grad) {
   __shared__ float red[8][32];
+  if (out_scale_dev) out_scale *= __ldg(out_scale_dev);
   const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
@@ -405,6 +409,29 @@ __global__ void __launch_bounds__(256) batch_sum_kernel(const float* part, int B
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += red[j][cl];
     grad[c] += t * out_scale;
+  }
+}
+
+// s2[0] = S, s2[1] = 1 / S with S = the power of two that brings max |x| (given as its bit pattern) to about `target`; S = 1 for
+// zero / non-finite inputs.  Device-side so that a loss-scaled backward pass needs no host synchronisation (CUDA-graph capture).
+__global__ void loss_scale_kernel(const uint32_t* absmax_bits, float target, float* s2) {
+  const float amax = __uint_as_float(*absmax_bits);
+  float S = 1.0f;
+  if (amax > 0.f && amax < 3.0e38f) {
+    int e = (int)floorf(log2f(target / amax));
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    S = exp2f((float)e);
+  }
+  s2[0] = S;
+  s2[1] = 1.0f / S;
+}
+
+// out = x * (*scalar), elementwise
+__global__ void scale_by_kernel(const float4* x, const float* scalar, int64_t n4, float4* out) {
+  const float sc = __ldg(scalar);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    out[i] = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
   }
 }
 
@@ -485,8 +512,8 @@ int64_t lns_conv2d_wgrad_work_bytes(int B, int H, int W, int Cin, int Cout, int 
 
 int lns_conv2d_wgrad(const float* x, int64_t x_bstride, const float* pro_scale, const float* pro_shift, int pro_act,
                      const float* dy, int64_t dy_bstride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int dil,
-                     int pad_t, int pad_l, int pad_mode_h, int pad_mode_w, int tensor_core, float out_scale, float* work, float* dW,
-                     void* stream) {
+                     int pad_t, int pad_l, int pad_mode_h, int pad_mode_w, int tensor_core, float out_scale,
+                     const float* out_scale_dev, float* work, float* dW, void* stream) {
   LNS_REQUIRE(x && dy && work && dW && B > 0 && H > 0 && W > 0, "lns_conv2d_wgrad: bad arguments");
   LNS_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "lns_conv2d_wgrad: Cin and Cout must be multiples of 4 (got %d, %d)", Cin, Cout);
   LNS_REQUIRE(x_bstride % 4 == 0 && dy_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
@@ -522,21 +549,21 @@ int lns_conv2d_wgrad(const float* x, int64_t x_bstride, const float* pro_scale, 
   int rc = lns::check_launch("wgrad_kernel");
   if (rc != LNS_OK) return rc;
   const int64_t n = (int64_t)taps * Cout * Cin;
-  lns::wgrad_reduce_kernel<<<lns::cdiv(n, 256), 256, 0, st>>>(work, p.nsplit, taps, Cout, Cin, out_scale, dW);
+  lns::wgrad_reduce_kernel<<<lns::cdiv(n, 256), 256, 0, st>>>(work, p.nsplit, taps, Cout, Cin, out_scale, out_scale_dev, dW);
   return lns::check_launch("wgrad_reduce_kernel");
 }
 
 int lns_chan_sum_slices(int B) { return B < 128 ? B : 128; }
 
-int lns_chan_sum_accum(const float* dy, int64_t bstride, int B, int HW, int C, float out_scale, float* work, float* grad,
-                       void* stream) {
+int lns_chan_sum_accum(const float* dy, int64_t bstride, int B, int HW, int C, float out_scale, const float* out_scale_dev,
+                       float* work, float* grad, void* stream) {
   LNS_REQUIRE(dy && grad && work && B > 0 && HW > 0 && C > 0, "lns_chan_sum_accum: bad arguments");
   const int ns = lns_chan_sum_slices(B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   lns::chan_sum_kernel<<<dim3((C + 31) / 32, ns), 256, 0, st>>>(dy, bstride, B, HW, C, work);
   int rc = lns::check_launch("chan_sum_kernel");
   if (rc != LNS_OK) return rc;
-  lns::batch_sum_kernel<<<(C + 31) / 32, 256, 0, st>>>(work, ns, C, out_scale, grad);
+  lns::batch_sum_kernel<<<(C + 31) / 32, 256, 0, st>>>(work, ns, C, out_scale, out_scale_dev, grad);
   return lns::check_launch("batch_sum_kernel");
 }
 
@@ -584,6 +611,23 @@ int lns_scale_add(const float* x, const float* scale, const float* skip, int B, 
   return lns::check_launch("scale_add_kernel");
 }
 
+int lns_loss_scale(const uint32_t* absmax_bits, float target, float* s2, void* stream) {
+  LNS_REQUIRE(absmax_bits && s2 && target > 0.f, "lns_loss_scale: bad arguments");
+  lns::loss_scale_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(absmax_bits, target, s2);
+  return lns::check_launch("loss_scale_kernel");
+}
+
+int lns_scale_by(const float* x, const float* scalar_dev, int64_t n, float* out, void* stream) {
+  LNS_REQUIRE(x && scalar_dev && out && n > 0 && n % 4 == 0, "lns_scale_by: bad arguments (n must be a multiple of 4)");
+  LNS_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "lns_scale_by: pointers must be 16-byte aligned");
+  int blocks = lns::cdiv(n / 4, 256);
+  const int cap = lns::device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  lns::scale_by_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(x), scalar_dev, n / 4,
+                                                                                  reinterpret_cast<float4*>(out));
+  return lns::check_launch("scale_by_kernel");
+}
+
 int lns_absmax(const float* x, int64_t n, uint32_t* out_bits, void* stream) {
   LNS_REQUIRE(x && out_bits && n > 0, "lns_absmax: bad arguments");
   int blocks = lns::cdiv(n, 1024);
@@ -593,9 +637,9 @@ int lns_absmax(const float* x, int64_t n, uint32_t* out_bits, void* stream) {
   return lns::check_launch("absmax_kernel");
 }
 
-int lns_batch_sum_accum(const float* part, int B, int C, float out_scale, float* grad, void* stream) {
+int lns_batch_sum_accum(const float* part, int B, int C, float out_scale, const float* out_scale_dev, float* grad, void* stream) {
   LNS_REQUIRE(part && grad && B > 0 && C > 0, "lns_batch_sum_accum: bad arguments");
-  lns::batch_sum_kernel<<<(C + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, B, C, out_scale, grad);
+  lns::batch_sum_kernel<<<(C + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, B, C, out_scale, out_scale_dev, grad);
   return lns::check_launch("batch_sum_kernel");
 }
 

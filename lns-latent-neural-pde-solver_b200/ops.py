@@ -275,6 +275,16 @@ def nchw_to_act(x, dtype=None):
 
 
 # ---- weights ---------------------------------------------------------------------------------------------
+_PACK_EPOCH = [0]  # process-wide (not thread-local: autograd's backward thread must see the same value)
+
+
+def invalidate_packed():
+    """Make every PackedFilter re-lay its filter at its next use.  Parameter updates are normally detected through the tensors'
+    version counters; a CAPTURED training step needs the packing kernels inside the graph (the weights change between replays
+    while the captured launch sequence does not), so it invalidates before every forward (lns_b200.train.GraphedTrainStep)."""
+    _PACK_EPOCH[0] += 1
+
+
 class PackedFilter:
     """Device-side re-laid copies of one conv / linear filter (OIHW fp32 source), built lazily per format and
     rebuilt when a source parameter changes (load_state_dict, .to(), optimizer step).  `key_fn` is a cheap fingerprint
@@ -324,7 +334,7 @@ class PackedFilter:
         return PackedFilter(wfn, bfn, lambda: tuple(PackedFilter._fp(t) for t in list(weights) + list(biases)), shape)
 
     def key(self):
-        return self._key_fn() if self._key_fn is not None else None
+        return (self._key_fn(), _PACK_EPOCH[0]) if self._key_fn is not None else None
 
     def dims(self):
         if self._shape is None:
@@ -909,7 +919,7 @@ def _f32_nhwc(a, what):
 
 
 def conv2d_wgrad(x, dy, dW, *, KH, KW, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, PAD_ZEROS), pro=None, tensor_core=False,
-                 out_scale=1.0):
+                 out_scale=1.0, out_scale_dev=None):
     """dW (torch fp32 [Cout,Cin,KH,KW], accumulated into) += out_scale * filter gradient of the same-size stride-1 conv whose
     forward read pro(x) (pro = (scale[B,Cin] | None, shift | None, act)) and whose output gradient is dy.  tensor_core: TF32
     mma.sync with hi + lo split operands (fp32-class) instead of CUDA-core FMAs.  (lns_conv2d_wgrad)"""
@@ -924,18 +934,18 @@ def conv2d_wgrad(x, dy, dW, *, KH, KW, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZE
                 nbytes=_abytes(x, dy))
     rc = _C.lib().lns_conv2d_wgrad(_ptr(x.t), x.bstride, _ptr(sc), _ptr(sh), pa, _ptr(dy.t), dy.bstride, x.B, x.H, x.W, x.C, dy.C,
                                    KH, KW, dil, pad[0], pad[2], pad_mode[0], pad_mode[1], 1 if tensor_core else 0, float(out_scale),
-                                   _ptr(work), _ptr(dW), _stream())
+                                   _ptr(out_scale_dev), _ptr(work), _ptr(dW), _stream())
     check(rc, "lns_conv2d_wgrad")
     _done(tok)
     _state.launches += 2
 
 
-def chan_sum_accum(dy, grad, out_scale=1.0):
+def chan_sum_accum(dy, grad, out_scale=1.0, out_scale_dev=None):
     """grad[c] += out_scale * sum over samples and pixels of dy (bias gradient)."""
     _f32_nhwc(dy, "chan_sum_accum")
     work = torch.empty(_C.lib().lns_chan_sum_slices(dy.B) * dy.C, dtype=torch.float32, device=dy.t.device)
-    rc = _C.lib().lns_chan_sum_accum(_ptr(dy.t), dy.bstride, dy.B, dy.H * dy.W, dy.C, float(out_scale), _ptr(work), _ptr(grad),
-                                     _stream())
+    rc = _C.lib().lns_chan_sum_accum(_ptr(dy.t), dy.bstride, dy.B, dy.H * dy.W, dy.C, float(out_scale), _ptr(out_scale_dev),
+                                     _ptr(work), _ptr(grad), _stream())
     check(rc, "lns_chan_sum_accum")
     _state.launches += 2
 
@@ -986,7 +996,32 @@ def scale_add(x, scale=None, skip=None):
     return out
 
 
-def group_norm_bwd(x, dy, groups, eps, gamma, dskip=None, dgamma=None, dbeta=None, out_scale=1.0):
+def loss_scale(t, target=64.0):
+    """Device-side loss scale of a contiguous fp32 CUDA tensor: -> torch fp32 [2] = (S, 1 / S), S = the power of two that brings
+    max |t| to about `target` (no host synchronisation)."""
+    bits = torch.zeros(1, dtype=torch.int32, device=t.device)
+    s2 = torch.empty(2, dtype=torch.float32, device=t.device)
+    rc = _C.lib().lns_absmax(_ptr(t), t.numel(), _ptr(bits), _stream())
+    check(rc, "lns_absmax")
+    rc = _C.lib().lns_loss_scale(_ptr(bits), float(target), _ptr(s2), _stream())
+    check(rc, "lns_loss_scale")
+    _state.launches += 2
+    return s2
+
+
+def scale_by(x, scalar_dev):
+    """x * (*scalar_dev) as a new contiguous fp32 Act (scalar_dev: a one-element fp32 CUDA tensor / view)."""
+    _f32_nhwc(x, "scale_by")
+    if not x.contiguous:
+        raise LnsError("scale_by: contiguous activations only")
+    out = x.like()
+    rc = _C.lib().lns_scale_by(_ptr(x.t), _ptr(scalar_dev), x.B * x.H * x.W * x.C, _ptr(out.t), _stream())
+    check(rc, "lns_scale_by")
+    _state.launches += 1
+    return out
+
+
+def group_norm_bwd(x, dy, groups, eps, gamma, dskip=None, dgamma=None, dbeta=None, out_scale=1.0, out_scale_dev=None):
     """Gradient of GroupNorm(groups, C, eps)(x) w.r.t. x (+ dskip), and out_scale * (dgamma, dbeta) accumulated into the given
     [C] tensors."""
     _f32_nhwc(x, "group_norm_bwd")
@@ -1004,7 +1039,7 @@ def group_norm_bwd(x, dy, groups, eps, gamma, dskip=None, dgamma=None, dbeta=Non
     _state.launches += 1
     if dgamma is not None:
         for part, grad in ((part_g, dgamma), (part_b, dbeta)):
-            rc = _C.lib().lns_batch_sum_accum(_ptr(part), x.B, x.C, float(out_scale), _ptr(grad), _stream())
+            rc = _C.lib().lns_batch_sum_accum(_ptr(part), x.B, x.C, float(out_scale), _ptr(out_scale_dev), _ptr(grad), _stream())
             check(rc, "lns_batch_sum_accum")
             _state.launches += 1
     return out

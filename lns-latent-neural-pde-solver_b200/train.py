@@ -20,8 +20,9 @@ per K step on fp32 storage, the mechanism of ops.hi_region), and so does the bac
 tcgen05 engines, filter gradients on TF32 mma.sync with hi + lo split operands (lns_conv2d_wgrad, tensor_core = 1).
 Gradients are 1e-4 ... 1e-7 in magnitude -- below the IEEE-half normal range, where the hi + lo split of an UNSCALED gradient
 loses its low bits (measured: 1.6e-4 per layer instead of 3e-6) -- so that backward pass is LOSS-SCALED: the incoming gradient
-is multiplied by a power of two S chosen from its max |.| (lns_absmax; target 64, three decades of headroom below the half
-maximum), every gradient in flight carries S, and the accumulating kernels multiply by 1/S (exact).
+is multiplied by a power of two S chosen ON THE DEVICE from its max |.| (lns_absmax + lns_loss_scale; target 64, three decades
+of headroom below the half maximum), every gradient in flight carries S, and the accumulating kernels multiply by 1/S (exact).
+No step of either pass synchronises with the host, so a whole training step can be captured in a CUDA graph (GraphedTrainStep).
 The precision mode is thread-local and autograd runs backward on its own thread: the mode of the forward call is recorded
 in the node and re-installed there."""
 import math
@@ -124,7 +125,8 @@ def _dgrad_filter(conv):
 
 
 class _Bw:
-    """Per-backward-pass settings: gradient buffers, tensor-core engines on / off, 1 / loss scale."""
+    """Per-backward-pass settings: gradient buffers, tensor-core engines on / off, 1 / loss scale (a one-element device tensor
+    or None: the scale is chosen on the device, so the pass never synchronises with the host)."""
     __slots__ = ("G", "tc", "inv")
 
     def __init__(self, G, tc, inv):
@@ -144,16 +146,16 @@ def _wgrad(conv, x, pro, dy, bw):
     if gw is not None:
         kh, kw = (1, 1) if isinstance(conv, nn.Linear) else conv.kernel_size
         ops.conv2d_wgrad(x, dy, gw.view(gw.shape[0], gw.shape[1], kh, kw), KH=kh, KW=kw, dil=geo["dil"], pad=geo["pad"],
-                         pad_mode=geo["pad_mode"], pro=pro, tensor_core=bw.tc, out_scale=bw.inv)
+                         pad_mode=geo["pad_mode"], pro=pro, tensor_core=bw.tc, out_scale_dev=bw.inv)
     if conv.bias is not None and id(conv.bias) in bw.G:
-        ops.chan_sum_accum(dy, bw.G[id(conv.bias)], out_scale=bw.inv)
+        ops.chan_sum_accum(dy, bw.G[id(conv.bias)], out_scale_dev=bw.inv)
 
 
 def _gn_bwd(norm, x, dy, dskip, bw):
     g = _gn(norm)
     return ops.group_norm_bwd(x, dy, g.num_groups, g.eps, g.weight, dskip=dskip,
                               dgamma=bw.G.get(id(g.weight)) if g.weight is not None else None,
-                              dbeta=bw.G.get(id(g.bias)) if g.bias is not None else None, out_scale=bw.inv)
+                              dbeta=bw.G.get(id(g.bias)) if g.bias is not None else None, out_scale_dev=bw.inv)
 
 
 def step_bwd(net, tape, dzo, bw, extra=None):
@@ -346,14 +348,8 @@ class _RolloutFn(torch.autograd.Function):
         G = {id(p): torch.zeros_like(p, dtype=_F32, memory_format=torch.contiguous_format) for p in params if p.requires_grad}
         with ops.device_of(dz_pred), ops.precision(ctx.precision), _region():
             tc = ops.split16()
-            S = 1.0
-            if tc:
-                amax = ops.absmax(dz_pred)
-                if amax > 0.0 and math.isfinite(amax):
-                    S = 2.0 ** max(-60, min(60, math.floor(math.log2(64.0 / amax))))
-            bw = _Bw(G, tc, 1.0 / S)
-            sc = torch.full((B * C,), S, dtype=_F32, device=dz_pred.device) if S != 1.0 else None
-            zs = torch.zeros_like(sc) if sc is not None else None
+            s2 = ops.loss_scale(dz_pred) if tc else None     # device tensor (S, 1 / S): no host round trip, graph-capturable
+            bw = _Bw(G, tc, s2[1:] if tc else None)
 
             def loss_grad(t):
                 out = Act.empty(B, h, w, C, _F32, dz_pred.device)
@@ -361,7 +357,7 @@ class _RolloutFn(torch.autograd.Function):
                 rc = _C.lib().lns_nchw_to_nhwc(src, B, C, h, w, T * C * h * w, ops._ptr(out.t), out.dtype, out.bstride, ops._stream())
                 _C.check(rc, "lns_nchw_to_nhwc")
                 ops._state.launches += 1
-                return ops.affine_act(out, sc, zs, ops.ACT_NONE, out_dtype=_F32) if sc is not None else out
+                return ops.scale_by(out, s2[0:1]) if tc else out
 
             ct = ctx.ct
             acc = None
@@ -377,10 +373,7 @@ class _RolloutFn(torch.autograd.Function):
                 cond_prepare_bwd(net, ct, acc, bw)
             dz0 = None
             if ctx.need_z0:
-                if sc is not None:
-                    sc.fill_(1.0 / S)
-                    dz = ops.affine_act(dz, sc, zs, ops.ACT_NONE, out_dtype=_F32)
-                dz0 = dz.to_nchw()
+                dz0 = (ops.scale_by(dz, s2[1:]) if tc else dz).to_nchw()
         ctx.tapes = ctx.ct = None
         return (None, dz0, None, None) + tuple(G.get(id(p)) for p in params)
 
@@ -394,3 +387,51 @@ def rollout_train(net, z0, t_out, param=None):
     if z0.dim() != 4:
         raise LnsError("rollout_train: z0 must be [B, C, h, w]")
     return _RolloutFn.apply(net, z0.contiguous().float(), int(t_out), param, *list(net.parameters()))
+
+
+class GraphedTrainStep:
+    """One training step -- LatentDynamics.forward(z_in, z_out[, param], loss_fn) + backward [+ optimizer.step()] -- captured once
+    as a CUDA graph and replayed: at the reference's training shape (configs/ns2d_stage2_prop.yml: batch 32, out_tw 2) the eager
+    step is ~400 launches of 5-40 us kernels, i.e. launch bound.  Inputs are copied into static buffers; `.grad` tensors are
+    static (zeroed inside the graph).  `optimizer`: a capturable torch optimizer (e.g. AdamW(..., capturable=True)) to put
+    `step()` inside the graph, or None to leave it to the caller."""
+
+    def __init__(self, model, z_in, z_out, loss_fn, param=None, optimizer=None, precision=None, warmup=3):
+        self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.precision = precision or ops.get_precision()
+        self.z_in, self.z_out = z_in.clone(), z_out.clone()
+        self.param = param.clone() if param is not None else None
+        self.params = [p for p in model.propagator.parameters() if p.requires_grad]
+        side = torch.cuda.Stream(z_in.device)
+        side.wait_stream(torch.cuda.current_stream(z_in.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):       # warm-up off the capture stream: packs filters, sizes the allocator pools, creates .grad
+                self._one()
+        torch.cuda.current_stream(z_in.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._one()
+        # the filter images cached during capture live in the graph's pool and hold data only while a replay is running:
+        # eager callers (predict, an eager training step) must not find them
+        ops.invalidate_packed()
+
+    def _one(self):
+        ops.invalidate_packed()   # the filter re-layout kernels must be part of the captured sequence: weights change between replays
+        for p in self.params:
+            if p.grad is not None:
+                p.grad.zero_()
+        with ops.precision(self.precision):
+            args = (self.z_in, self.z_out) + ((self.param,) if self.param is not None else ()) + (self.loss_fn,)
+            loss = self.model(*args)
+            loss.backward()
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return loss
+
+    def __call__(self, z_in, z_out, param=None):
+        self.z_in.copy_(z_in, non_blocking=True)
+        self.z_out.copy_(z_out, non_blocking=True)
+        if self.param is not None:
+            self.param.copy_(param, non_blocking=True)
+        self.graph.replay()
+        return self.loss

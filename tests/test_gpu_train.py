@@ -240,3 +240,41 @@ def test_pixel_dot_and_scale_add():
     assert rel(out.view(B, C), dy.sum(dim=(2, 3))) < 3e-6
     y = ops.scale_add(nhwc(dy), scale=sc.float().to(DEV).reshape(-1).contiguous(), skip=nhwc(x))
     assert rel(y.to_torch_nhwc().permute(0, 3, 1, 2), dy * sc[:, :, None, None] + x) < 1e-6
+
+
+def test_graphed_train_step_matches_eager_and_follows_weight_updates():
+    """The whole step as a CUDA graph: gradients equal the eager step's bit for bit, and after an optimizer update (outside the
+    graph) the replay uses the NEW weights (the filter packing kernels are inside the captured sequence)."""
+    ops = ops_mod()
+    from lns_b200.train import GraphedTrainStep
+    cfg = get_config("ns2d")
+    torch.manual_seed(11)
+    model = LatentDynamics(cfg).to(DEV)
+    for p in model.autoencoder.parameters():
+        p.requires_grad_(False)
+    z_in, z_out = O.train_inputs(cfg, 32, 2, seed=4)
+    z_in, z_out = z_in.to(DEV), (0.1 * z_out).to(DEV)
+    opt = torch.optim.SGD(model.propagator.parameters(), lr=1e-2)
+
+    def eager():
+        model.zero_grad(set_to_none=True)
+        with ops.precision("fp16s"):
+            loss = model(z_in, z_out, F.smooth_l1_loss)
+            loss.backward()
+        return loss.item(), [p.grad.clone() for p in model.propagator.parameters()]
+
+    step = GraphedTrainStep(model, z_in, z_out, F.smooth_l1_loss, precision="fp16s")
+    for it in range(2):
+        want_loss, want = eager()
+        loss = step(z_in, z_out)
+        torch.cuda.synchronize()
+        assert loss.item() == want_loss
+        for p, g in zip(model.propagator.parameters(), want):
+            assert torch.equal(p.grad, g)
+        opt.step()   # weights change: the next replay (and the next eager step) must see them
+    z2 = z_in * 1.5  # new inputs through the static buffers
+    loss = step(z2, z_out)
+    with ops.precision("fp16s"):
+        ref = model(z2, z_out, F.smooth_l1_loss)
+    torch.cuda.synchronize()
+    assert loss.item() == ref.item()

@@ -53,9 +53,18 @@ def run(cases=((32, 2), (1024, 2)), iters=10, eager=True):
                     loss = model(z_in, z_out, F.smooth_l1_loss)
                     loss.backward()
                 opt.step()
-            n0 = ops.launch_count()
             ms = _timed(step, iters)
             row[prec] = {"ms_per_iter": round(ms, 3), "value": round(B * T / ms * 1e3, 1)}
+        # the same step (forward + backward + AdamW) captured once as a CUDA graph and replayed (lns_b200.train.GraphedTrainStep)
+        try:
+            from lns_b200.train import GraphedTrainStep
+            optg = torch.optim.AdamW(model.propagator.parameters(), lr=1e-5, capturable=True)
+            gs = GraphedTrainStep(model, z_in, z_out, F.smooth_l1_loss, optimizer=optg, precision="fp16s")
+            ms = _timed(lambda: gs(z_in, z_out), iters)
+            row["fp16s_cuda_graph"] = {"ms_per_iter": round(ms, 3), "value": round(B * T / ms * 1e3, 1)}
+            del gs
+        except Exception as ex:  # noqa: BLE001
+            row["fp16s_cuda_graph"] = {"error": repr(ex)[:200]}
         if eager:
             sd = {k: v.detach().clone().requires_grad_(k.startswith("propagator.")) for k, v in model.state_dict().items()}
             params = [v for k, v in sd.items() if k.startswith("propagator.")]
