@@ -141,3 +141,40 @@ def test_rollout_chunking_rules():
     assert 1 <= s <= 5 and -(-20 // s) >= 4
     stub.decode_chunk = 640
     assert Rollout._steps_per_group(stub, 64 * 20) == 5
+
+
+def test_training_rollout_host_logic():
+    """lns_b200.train on the CPU: which propagators it recognises, that the conditional flag and `param` must agree, that CPU
+    tensors fail loudly (no fallback), and that the null-argument checks of the backward entry points answer LNS_E_INVALID."""
+    import torch
+    import torch.nn.functional as F
+    from lns_b200 import _C, ops, train
+    from lns_b200.configs import get_config
+    from lns_b200.latent_dynamics import LatentDynamics
+    plain = LatentDynamics(get_config("ns2d")).propagator
+    cond = LatentDynamics(get_config("twophase_cond")).propagator
+    assert train._check_net(plain) is False and train._check_net(cond) is True
+    with pytest.raises(NotImplementedError):
+        train._check_net(torch.nn.Linear(4, 4))
+    z = torch.zeros(2, 16, 8, 8)
+    with pytest.raises(ops.LnsError):
+        train.rollout_train(plain, z, 2, param=torch.zeros(2))      # param with the unconditional propagator
+    with pytest.raises(ops.LnsError):
+        train.rollout_train(cond, torch.zeros(2, 64, 7, 15), 2)     # the conditional one without it
+    with pytest.raises(ops.LnsError):
+        train.rollout_train(plain, z, 2)                            # CPU tensor: there is no CPU path
+    model = LatentDynamics(get_config("ns2d"))
+    with pytest.raises(ValueError):
+        model(torch.zeros(2, 2, 16, 8, 8), torch.zeros(2, 2, 16, 8, 8), F.mse_loss)   # more than one input frame
+    lib = _C.lib()
+    assert lib.lns_conv2d_wgrad_work_bytes(4, 8, 8, 128, 128, 3, 3) == 64 * 9 * 128 * 128 * 4
+    assert lib.lns_conv2d_wgrad_work_bytes(0, 8, 8, 128, 128, 3, 3) == -1
+    assert lib.lns_chan_sum_slices(7) == 7 and lib.lns_chan_sum_slices(4096) == 128
+    assert lib.lns_conv2d_wgrad(None, 0, None, None, 0, None, 0, 1, 8, 8, 4, 4, 3, 3, 1, 1, 1, 0, 0, 0, 1.0, None, None, None, None) == -1
+    assert lib.lns_group_norm_bwd(None, 0, None, 0, None, 0, 1, 64, 128, 1, 1e-5, None, None, 0, None, None, None) == -1
+    assert lib.lns_act_bwd(None, None, 4, 2, None, None) == -1
+    assert lib.lns_pixel_dot(None, 0, None, 0, 1, 1, 128, 1, None, None) == -1
+    assert lib.lns_scale_add(None, None, None, 1, 1, 4, None, None) == -1
+    assert lib.lns_absmax(None, 4, None, None) == -1 and lib.lns_loss_scale(None, 64.0, None, None) == -1
+    assert lib.lns_norm_finalize_centred(None, 1, 1, 4, 1, 1, 1e-5, None, None, None, None, None, None) == -1
+    assert b"lns_" in lib.lns_last_error()
