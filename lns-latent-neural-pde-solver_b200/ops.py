@@ -46,6 +46,8 @@ class _State(threading.local):
         self.wsplit_policy = os.environ.get("LNS_WSPLIT", "enc")  # where ops.wsplit_region turns that on: enc | all | none
         self.hi_scale = float(os.environ.get("LNS_HI_SCALE", "1"))  # experiment: 4 = one more resolution level in the hi region
         self.hi_wsplit = os.environ.get("LNS_HI_WSPLIT", "1") != "0"  # hi layers also split the filter (3 MMAs instead of 2)
+        # experiment: split the filter only on the COARSEST level of the region (grids of <= hi_px / 4 pixels)
+        self.hi_wsplit_coarsest = os.environ.get("LNS_HI_WSPLIT", "1") == "coarsest"
         self.coarse = os.environ.get("LNS_COARSE", "1") != "0"        # use the block-halo engine (conv_coarse.cu) where it applies
         self.coarse_pro = os.environ.get("LNS_COARSE_PRO", "1") != "0"  # ... and let its fp32 producer apply the pending norm + act
         self.coarse_stats = os.environ.get("LNS_COARSE_STATS", "1") != "0"  # ... and its epilogue emit the next GroupNorm's statistics
@@ -444,6 +446,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
                      and pt == pb == pl == pr == dil and dil <= min(Hv, Wv) and sample_bias is None and pre_add is None
                      and _state.coarse and x.layout == NHWC and out_layout == NHWC and not x.tf32 and not _state.hi_exact
                      and _coarse_fits(Cin, Cout, dil, x.t.dtype == torch.float32, _state.hi_wsplit))
+        hi_w = _state.hi_wsplit and (not _state.hi_wsplit_coarsest or 4 * min(x.H * x.W, Hout * Wout) <= _state.hi_px)
         # the block-halo engine's fp32 producer applies the pending per-sample affine + activation itself (conv_coarse.cu): the
         # GroupNorm-applied tensor is never written -- only its statistics kernel runs
         fuse_pro = (coarse_ok and pro is not None and x.t.dtype == torch.float32 and x.bstride % 4 == 0 and _state.coarse_pro)
@@ -465,7 +468,7 @@ def conv2d(x, filt, *, stride=1, dil=1, pad=(0, 0, 0, 0), pad_mode=(PAD_ZEROS, P
                 and ((x.t.dtype == torch.float32 and x.bstride % 4 == 0) or (x.t.dtype == torch.float16 and x.bstride % 8 == 0))):
             if coarse_ok:
                 # block-halo engine: the fp32 activation is read once per 8x8 block and split into hi + lo halo planes
-                engine, split_fmt = ENGINE_COARSE, _state.hi_wsplit
+                engine, split_fmt = ENGINE_COARSE, hi_w
             else:
                 engine, split_fmt = ENGINE_UMMA, True   # gather engine: fp32 input 3 MMAs (x3), f16 input 2 MMAs (w2)
         else:
