@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams p) {
 // rn(v - hi): 22 significant bits; three MMAs per product block, fp32 accumulation -- the split of csrc/conv_coarse.cu).  The
 // split happens ONCE per element when a stage is written to shared memory, as packed pairs of two consecutive pixels (the K
 // dimension), so that a fragment register is one 32-bit shared-memory load.  128 x 128 (o x i) tile, 32 pixels per stage, the
-// next stage's global loads in flight during the MMAs; warp w owns rows 32 (w & 3) .. + 32 and columns 64 (w >> 2) .. + 64.
+// next stage's global loads in flight during the MMAs; 16 warps, warp w owns rows 32 (w & 3) .. + 32 and columns 32 (w >> 2) .. + 32.
 // Callers scale dy into the half range (loss scaling, lns_b200/train.py).
 constexpr int kTKc = 32, kTT = 128, kLdP = kTT + 8;  // row stride 136 words: conflict-free fragment loads (bank = 8 t + g)
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -124,7 +124,7 @@ __device__ __forceinline__ void bw_mma(float* c, const uint32_t* a, uint32_t b0,
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__global__ void __launch_bounds__(256) wgrad_tc_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(512) wgrad_tc_kernel(const WgradParams p) {
   __shared__ __align__(16) uint32_t dyh[kTKc / 2][kLdP], dyl[kTKc / 2][kLdP], xh[kTKc / 2][kLdP], xl[kTKc / 2][kLdP];
   const ConvGeom& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -135,27 +135,27 @@ __global__ void __launch_bounds__(256) wgrad_tc_kernel(const WgradParams p) {
   const int HW = g.Hout * g.Wout;
   const int64_t k_begin = (int64_t)split * p.pix_per_split;
   const int64_t k_end = min(p.npix, k_begin + p.pix_per_split);
-  // loader: item = (pixel pair, 4-channel column); 16 pairs x 32 columns = 512 items per operand, two per thread
+  // loader: item = (pixel pair, 4-channel column); 16 pairs x 32 columns = 512 items per operand, one per thread (warp w = pair w)
   const int lc4 = (tid & 31) * 4;
   const int gq = lane >> 2, t = lane & 3;
-  const int m0 = (warp & 3) * 32, n0 = (warp >> 2) * 64;
-  float acc[2][8][4];
+  const int m0 = (warp & 3) * 32, n0 = (warp >> 2) * 32;
+  float acc[2][4][4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
   const bool o_ok = o0 + lc4 < g.Cout, i_ok = i0 + lc4 < g.Cin;
-  float4 dv[2][2], xv[2][2];  // [item][pixel of the pair], RAW: the prologue is applied when the stage is written (after the
-  int bsel[2][2];             // MMAs of the previous stage), so that these loads stay in flight; bsel = sample index, -1 = zero
+  float4 dv[1][2], xv[1][2];  // [item][pixel of the pair], RAW: the prologue is applied when the stage is written (after the
+  int bsel[1][2];             // MMAs of the previous stage), so that these loads stay in flight; bsel = sample index, -1 = zero
   const int kb32 = (int)k_begin, ke32 = (int)k_end;  // (npix < 2^31 is checked by the launcher: 32-bit index arithmetic)
   auto load = [&](int k0) {
-    // A warp loads four pixels per stage (pairs warp and warp + 8).  Lane j < 4 does the index arithmetic of pixel j (two
-    // divisions, the padding map) and the warp reads the three results by shuffle: a quarter of the instructions of letting every
-    // lane redo all four (the ncu source page had 46 % of this kernel's samples in that arithmetic).
+    // A warp loads the two pixels of ONE pair per stage.  Lane j < 2 does the index arithmetic of pixel j (two divisions, the
+    // padding map) and the warp reads the three results by shuffle (the ncu source page of the first version had 46 % of the
+    // samples in that arithmetic, redone by every lane for every pixel).
     int my_b = -1, my_rem = 0, my_src = -1;
     {
-      const int j = lane & 3;
-      const int pix = k0 + ((tid >> 5) + (j >> 1) * 8) * 2 + (j & 1);
+      const int j = lane & 1;
+      const int pix = k0 + (tid >> 5) * 2 + j;
       if (pix < ke32) {
         my_b = pix / HW;
         my_rem = pix - my_b * HW;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) wgrad_tc_kernel(const WgradParams p) {
       }
     }
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < 1; ++it) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int b = __shfl_sync(0xffffffffu, my_b, it * 2 + h);
@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(256) wgrad_tc_kernel(const WgradParams p) {
   for (int k0 = kb32; k0 < ke32; k0 += kTKc) {
     __syncthreads();  // the previous stage has been consumed
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int pair = (tid >> 5) + it * 8;
+    for (int it = 0; it < 1; ++it) {
+      const int pair = tid >> 5;
       uint4 h4, l4;
       split_pack(dv[it][0].x, dv[it][1].x, h4.x, l4.x); split_pack(dv[it][0].y, dv[it][1].y, h4.y, l4.y);
       split_pack(dv[it][0].z, dv[it][1].z, h4.z, l4.z); split_pack(dv[it][0].w, dv[it][1].w, h4.w, l4.w);
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) wgrad_tc_kernel(const WgradParams p) {
         al[mt][0] = dyl[ks * 8 + t][m]; al[mt][1] = dyl[ks * 8 + t][m + 8]; al[mt][2] = dyl[ks * 8 + t + 4][m]; al[mt][3] = dyl[ks * 8 + t + 4][m + 8];
       }
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 4; ++nt) {
         const int n = n0 + nt * 8 + gq;
         const uint32_t bh0 = xh[ks * 8 + t][n], bh1 = xh[ks * 8 + t + 4][n], bl0 = xl[ks * 8 + t][n], bl1 = xl[ks * 8 + t + 4][n];
 #pragma unroll
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) wgrad_tc_kernel(const WgradParams p) {
       const int o = o0 + m0 + mt * 16 + gq + half * 8;
       if (o >= g.Cout) continue;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 4; ++nt) {
         const int i = i0 + n0 + nt * 8 + 2 * t;
         if (i < g.Cin) out[(int64_t)o * g.Cin + i] = acc[mt][nt][half * 2];
         if (i + 1 < g.Cin) out[(int64_t)o * g.Cin + i + 1] = acc[mt][nt][half * 2 + 1];
@@ -542,7 +542,7 @@ int lns_conv2d_wgrad(const float* x, int64_t x_bstride, const float* pro_scale, 
   if (tensor_core) {
     LNS_REQUIRE(p.npix < (1ll << 31) - lns::kTKc, "lns_conv2d_wgrad: too many pixels for the tensor-core path");
     p.pix_per_split = ((p.npix + p.nsplit - 1) / p.nsplit + lns::kTKc - 1) / lns::kTKc * lns::kTKc;
-    lns::wgrad_tc_kernel<<<dim3(tiles_o * tiles_i, taps, p.nsplit), 256, 0, st>>>(p);
+    lns::wgrad_tc_kernel<<<dim3(tiles_o * tiles_i, taps, p.nsplit), 512, 0, st>>>(p);
   } else {
     lns::wgrad_kernel<<<dim3(tiles_o * tiles_i, taps, p.nsplit), 256, 0, st>>>(p);
   }
