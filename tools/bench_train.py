@@ -77,6 +77,30 @@ def run(cases=((32, 2), (1024, 2)), iters=10, eager=True):
             ms = _timed(estep, iters)
             row["torch_eager_fp32_same_gpu"] = {"ms_per_iter": round(ms, 3), "value": round(B * T / ms * 1e3, 1)}
         out["cases"].append(row)
+    # the other three stage-2 scripts at their own training shapes (configs/*_stage2*_prop.yml: batch 32, out_tw 5), graphed step
+    out["other_configs"] = {}
+    for name in ("sw", "twophase", "twophase_cond"):
+        try:
+            from lns_b200.train import GraphedTrainStep
+            c2 = get_config(name)
+            torch.manual_seed(1234)
+            m2 = LatentDynamics(c2)
+            m2.load_state_dict(O.randomize_zero_init(m2.state_dict()))
+            m2 = m2.cuda()
+            for p in m2.autoencoder.parameters():
+                p.requires_grad_(False)
+            zi, zo = O.train_inputs(c2, 32, 5, seed=0)
+            zi, zo = zi.cuda(), zo.cuda()
+            par = torch.linspace(0.3, 0.9, 32).cuda() if name == "twophase_cond" else None
+            optg = torch.optim.AdamW(m2.propagator.parameters(), lr=1e-5, capturable=True)
+            gs = GraphedTrainStep(m2, zi, zo, F.smooth_l1_loss, param=par, optimizer=optg, precision="fp16s")
+            ms = _timed((lambda: gs(zi, zo, par)) if par is not None else (lambda: gs(zi, zo)), iters)
+            out["other_configs"][name] = {"batch": 32, "t_out": 5, "fp16s_cuda_graph_ms_per_iter": round(ms, 3),
+                                          "value": round(32 * 5 / ms * 1e3, 1)}
+            del gs, m2
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            out["other_configs"][name] = {"error": repr(ex)[:200]}
     return out
 
 
