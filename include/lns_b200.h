@@ -240,6 +240,12 @@ int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, in
                         float* pooled_y, void* stream);
 int lns_fablock_core(const void* u, int dtype, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
                      const float* w_in_proj, const float* Kx, const float* Ky, float eps, void* out, void* stream);
+/* lns_fablock_prepass that ALSO writes `staged` [B][H*W][64] (same 16-bit dtype as u): the normalised sample GN(u) as the
+ * byte image of lns_fablock_full_staged's shared-memory tile (pixel row s = pixel s ^ ((s >> log2 W) & 7), 16-byte chunk ch
+ * at ch ^ (s & 7)), so that kernel fetches a head's input with linear bulk copies.  C = 64, H, W in {16, 32}. */
+int lns_fablock_prepass_staged(const void* u, int dtype, int B, int H, int W, int C, int64_t bstride, float eps,
+                               const float* gamma, const float* beta, float* scale, float* shift, float* pooled_x,
+                               float* pooled_y, void* staged, void* stream);
 
 /* Propagator FFN in ONE kernel (csrc/ffn_fused.cu):  y = x + W2 . GELU( W1 . (x*scale[b] + shift[b]) )  -- GroupNorm(1,C) apply,
  * 1x1 conv, GELU, 1x1 conv and the residual add of train_stage2_ns2d.py:44-53 (both convs bias-free, C = hidden = 128).
@@ -273,6 +279,16 @@ int lns_fablock_full_supported(int H, int W, int dim, int dim_head, int dim_out)
 int lns_fablock_full(const void* u, int dtype, int B, int H, int W, int heads, const float* gn_scale, const float* gn_shift,
                      const float* w_in_proj, const float* Kx, const float* Ky, float eps, const float* w_out1,
                      const float* w_out2, void* out, void* stream);
+/* lns_fablock_full on pre-staged operands with a producer warp (csrc/fablock_full.cu, fablock_full2_kernel): same
+ * mathematics (modules/factorized_attention.py:146-159), but the GroupNorm is applied by lns_fablock_prepass_staged (u_staged),
+ * the in_proj slices arrive as 16-bit rows padded to 72 elements (w_in16 [heads][64][72], dtype of u, prepared once per
+ * parameter version) and to_out.1.weight head-major (w1h [heads][64 out][64 in] fp32): every operand of a head is a bulk
+ * copy issued by one producer lane, which also issues the tcgen05.mma of to_out[1]; u is the RAW input (skip connection).
+ * H, W in {16, 32}. */
+int lns_fablock_full_staged_supported(int H, int W, int dim, int dim_head, int dim_out);
+int lns_fablock_full_staged(const void* u_staged, const void* u, int dtype, int B, int H, int W, int heads,
+                            const void* w_in16, const float* Kx, const float* Ky, float eps, const float* w1h,
+                            const float* w_out2, void* out, void* stream);
 
 /* lns_fablock_full with EVERY contraction on tcgen05 (csrc/fablock_tc.cu): in_proj, both axial contractions (block-diagonal
  * kernel matrices x the pixel rows read as an MN-major operand) and both to_out convolutions are tcgen05.mma batches with

@@ -64,6 +64,7 @@ SIGNATURES = {
     "lns_fablock_core_supported": (i32, [i32, i32, i32, i32]),
     "lns_fablock_prepass": (i32, [vp, i32, i32, i32, i32, i32, i64, f32, vp, vp, vp, vp, vp, vp, vp]),
     "lns_fablock_core": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp]),
+    "lns_fablock_prepass_staged": (i32, [vp, i32, i32, i32, i32, i32, i64, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "lns_sablock_fused_supported": (i32, [i32, i32, i32, i32]),
     "lns_sablock_fused": (i32, [vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp, f32, vp, vp]),
     "lns_ffn_fused_supported": (i32, [i32, i32]),
@@ -72,6 +73,8 @@ SIGNATURES = {
     "lns_fa_axis_kernel": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp, vp]),
     "lns_fablock_full_supported": (i32, [i32, i32, i32, i32, i32]),
     "lns_fablock_full": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp]),
+    "lns_fablock_full_staged_supported": (i32, [i32, i32, i32, i32, i32]),
+    "lns_fablock_full_staged": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp]),
     "lns_fablock_tc_supported": (i32, [i32, i32, i32, i32, i32]),
     "lns_fablock_tc": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp]),
     "lns_nchw_to_nhwc": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i64, vp]),

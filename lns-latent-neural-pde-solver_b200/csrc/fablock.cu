@@ -441,7 +441,8 @@ template <int NX>
 __global__ void __launch_bounds__(256) fablock_prepass2_kernel(const void* __restrict__ u, int dtype, int H, int W, int C, int64_t bstride,
                                                                 float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 float* __restrict__ scale, float* __restrict__ shift,
-                                                                float* __restrict__ pooled_x, float* __restrict__ pooled_y) {
+                                                                float* __restrict__ pooled_x, float* __restrict__ pooled_y,
+                                                                uint16_t* __restrict__ staged, int lgw) {
   extern __shared__ float smf[];
   float* rowsum = smf;                           // [H][C]
   float* colpart = rowsum + (size_t)H * C;       // [8 warps][W][C]
@@ -541,6 +542,28 @@ __global__ void __launch_bounds__(256) fablock_prepass2_kernel(const void* __res
     for (int w = 0; w < 8; ++w) a += colpart[(size_t)w * W * C + e];
     pooled_y[(int64_t)b * W * C + e] = fmaf(a * invH, ab[c * 2], ab[c * 2 + 1]);
   }
+  // Staged copy for lns_fablock_full_staged (C = 64, 16-bit, power-of-two W, no pad rows): the NORMALISED sample as the byte
+  // image of that kernel's shared-memory tile -- row s holds pixel s ^ ((s >> lgw) & 7) (x ^= y & 7 inside every image row),
+  // 16-byte chunk ch of a row sits at chunk ch ^ (s & 7) (tcgen05's SWIZZLE_128B) -- so that a head's input is a linear bulk
+  // copy.  The second read of the sample hits L1 / L2 (this CTA has just read it).
+  if (staged != nullptr) {
+    const uint16_t* u16 = reinterpret_cast<const uint16_t*>(u) + (int64_t)b * bstride;
+    uint16_t* dst = staged + (int64_t)b * H * W * 64;
+    for (int e = threadIdx.x; e < H * W * 8; e += 256) {
+      const int sl = e >> 3, ch = e & 7;
+      const int src = sl ^ ((sl >> lgw) & 7);
+      const uint4 raw = *reinterpret_cast<const uint4*>(u16 + (int64_t)src * 64 + ch * 8);
+      const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack2_rt(dtype, rw[j]);
+        const int c = ch * 8 + 2 * j;
+        o[j] = pack2_rt(dtype, fmaf(f.x, ab[c * 2], ab[c * 2 + 1]), fmaf(f.y, ab[c * 2 + 2], ab[c * 2 + 3]));
+      }
+      *reinterpret_cast<uint4*>(dst + (int64_t)sl * 64 + ((ch ^ (sl & 7)) << 3)) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
 }
 
 static size_t fablock_smem(int H, int W) {
@@ -553,9 +576,18 @@ static size_t fablock_smem(int H, int W) {
 
 extern "C" {
 
-int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, int64_t bstride, float eps, const float* gamma,
-                        const float* beta, float* scale, float* shift, float* pooled_x, float* pooled_y, void* stream) {
+static int fablock_prepass_impl(const void* u, int dtype, int B, int H, int W, int C, int64_t bstride, float eps, const float* gamma,
+                                const float* beta, float* scale, float* shift, float* pooled_x, float* pooled_y, void* staged_v,
+                                void* stream) {
   LNS_REQUIRE(u && scale && shift && pooled_x && pooled_y && B > 0 && H > 0 && W > 0, "lns_fablock_prepass: bad arguments");
+  uint16_t* staged = reinterpret_cast<uint16_t*>(staged_v);
+  int lgw = 0;
+  if (staged) {
+    LNS_REQUIRE(lns::is_h16_host(dtype) && C == 64 && (H == 16 || H == 32) && (W == 16 || W == 32) && bstride % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(u) & 15) == 0 && (reinterpret_cast<uintptr_t>(staged) & 15) == 0,
+                "lns_fablock_prepass_staged: needs 16-bit [B][16|32][16|32][64] input, 16-byte aligned");
+    lgw = W == 32 ? 5 : 4;
+  }
   int cg = C / 4;
   LNS_REQUIRE(C % 4 == 0 && C >= 4 && C <= 256 && (cg & (cg - 1)) == 0, "lns_fablock_prepass: C must be a power of two in [4,256]");
   LNS_REQUIRE(bstride % 4 == 0, "lns_fablock_prepass: batch stride must be a multiple of 4");
@@ -570,14 +602,15 @@ int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, in
         LNS_OPT_IN_SMEM((lns::fablock_prepass2_kernel<24>), 200 * 1024, "fablock");
       }
       if (nx <= 8)
-        lns::fablock_prepass2_kernel<8><<<B, 256, smem2, st>>>(u, dtype, H, W, C, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y);
+        lns::fablock_prepass2_kernel<8><<<B, 256, smem2, st>>>(u, dtype, H, W, C, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y, staged, lgw);
       else if (nx <= 16)
-        lns::fablock_prepass2_kernel<16><<<B, 256, smem2, st>>>(u, dtype, H, W, C, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y);
+        lns::fablock_prepass2_kernel<16><<<B, 256, smem2, st>>>(u, dtype, H, W, C, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y, staged, lgw);
       else
-        lns::fablock_prepass2_kernel<24><<<B, 256, smem2, st>>>(u, dtype, H, W, C, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y);
+        lns::fablock_prepass2_kernel<24><<<B, 256, smem2, st>>>(u, dtype, H, W, C, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y, staged, lgw);
       return lns::check_launch("fablock_prepass2_kernel");
     }
   }
+  LNS_REQUIRE(staged == nullptr, "lns_fablock_prepass_staged: shape not covered by the staging pre-pass");
   int rows = 256 / cg;
   LNS_REQUIRE(W <= lns::kPreMaxX * rows, "lns_fablock_prepass: W=%d too wide for C=%d", W, C);
   size_t smem = ((size_t)rows * C + (size_t)H * C + (size_t)W * C + (size_t)rows * C * 2 + 2 * (size_t)C) * sizeof(float);
@@ -586,6 +619,18 @@ int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, in
   lns::fablock_prepass_kernel<<<B, 256, smem, st>>>(u, dtype, H, W, C, bstride, eps, gamma, beta,
                                                     scale, shift, pooled_x, pooled_y);
   return lns::check_launch("fablock_prepass_kernel");
+}
+
+int lns_fablock_prepass(const void* u, int dtype, int B, int H, int W, int C, int64_t bstride, float eps, const float* gamma,
+                        const float* beta, float* scale, float* shift, float* pooled_x, float* pooled_y, void* stream) {
+  return fablock_prepass_impl(u, dtype, B, H, W, C, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y, nullptr, stream);
+}
+
+int lns_fablock_prepass_staged(const void* u, int dtype, int B, int H, int W, int C, int64_t bstride, float eps, const float* gamma,
+                               const float* beta, float* scale, float* shift, float* pooled_x, float* pooled_y, void* staged,
+                               void* stream) {
+  LNS_REQUIRE(staged, "lns_fablock_prepass_staged: staged must not be null");
+  return fablock_prepass_impl(u, dtype, B, H, W, C, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y, staged, stream);
 }
 
 int lns_fablock_core_supported(int H, int W, int dim, int dim_head) {

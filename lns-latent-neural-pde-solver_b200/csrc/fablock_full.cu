@@ -198,6 +198,13 @@ __device__ __forceinline__ void contract_line_sw(uint32_t U_a, int line, int Wp,
   __syncwarp();
 }
 
+// -DLNS_FULL_TRACE: per-phase cycle counts of one CTA (tools/bench_fablock.py with LNS_B200_LIB pointing at the trace build)
+#ifdef LNS_FULL_TRACE
+#define LNS_FT(i) do { if (tid == 0 && blockIdx.x == 0 && h < 4) p.trace[h * 16 + (i)] = clock64(); } while (0)
+#else
+#define LNS_FT(i) do { } while (0)
+#endif
+
 struct FullParams {
   const __nv_bfloat16* u;  // [B][H][W][64] 16-bit (opaque)
   int H, W, heads;
@@ -214,6 +221,7 @@ struct FullParams {
   float inv_wp;
   int k16;      // Kx / Ky slices can be staged with 16-byte copies
   int lgwp;     // log2(Wp) when W == Wp is a power of two and the sample fills its tiles exactly (no pad rows), else -1
+  long long* trace;  // -DLNS_FULL_TRACE builds only (tools): clock64() of thread 0 of one CTA at the phase boundaries
 };
 
 struct FullSmem {
@@ -333,6 +341,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
   const int blk_per_q = (nblk + NQ - 1) / NQ;
 
   for (int h = 0; h < heads; ++h) {
+    LNS_FT(0);
     // ---- per-(sample, head) setup from the staged fp32 operands: in_proj filter with GroupNorm folded in, its bias, the
     // two kernel matrices (no global-memory latency here; overlaps the previous head's tensor-core GEMM) ----
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -364,12 +373,14 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
       for (int j = lane; j < H16; j += 32) Kx_s[i * kxs + j] = to_h16<F16>((i < H && j < H) ? stkx_s[i * H + j] : 0.f);
     for (int i = warp; i < W16; i += nwarp)
       for (int j = lane; j < W16; j += 32) Ky_s[i * kys + j] = to_h16<F16>((i < W && j < W) ? stky_s[i * W + j] : 0.f);
+    LNS_FT(1);
     // the previous head's tcgen05 GEMM reads U_s and Wo_s[(h-1)&1]: U_s may only be overwritten once it has completed
     if (h > 0) {
       fptx::mbar_wait(bar, (uint32_t)((h - 1) & 1));
       fptx::tc_fence_after();
     }
     __syncthreads();  // the staging area has been consumed by every thread: it may be refilled
+    LNS_FT(2);
     // ---- raw input -> pixel rows of U_s (cp.async, four commit groups = four quarters of the row range) ----
     {
       const int ch = tid & 7;
@@ -402,6 +413,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
     }
     prefetch_head(h + 1 < heads ? h + 1 : h);  // fifth group in flight; lands during phases A-C (last head: harmless refetch)
 
+    LNS_FT(3);
     // ---- phase A: u_phi_h = u x Ws^T + bias, in place, 16-row blocks per warp (the conv is pointwise: any row order) ----
     uint32_t wf[4][8][2];
     for (int q = 0; q < NQ; ++q) {
@@ -450,6 +462,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
       }
     }
     __syncthreads();
+    LNS_FT(4);
 
     // ---- phase B: contraction over H, one image column per warp at a time ----
     for (int m = warp; m < W; m += nwarp) {
@@ -457,12 +470,14 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
       else contract_line_sw<2, 0, F16>(U_a, m, Wp, H, Kx_a, kxs, lane);
     }
     __syncthreads();
+    LNS_FT(5);
     // ---- phase C: contraction over W, one image row per warp ----
     for (int i = warp; i < H; i += nwarp) {
       if (W16 == 16) contract_line_sw<1, 1, F16>(U_a, i, Wp, W, Ky_a, kys, lane);
       else contract_line_sw<2, 1, F16>(U_a, i, Wp, W, Ky_a, kys, lane);
     }
     __syncthreads();
+    LNS_FT(6);
     // ---- phase D: InstanceNorm statistics of this head's 64 channels, from the 16-bit values the GEMM will read (a separate
     // pass over shared memory: carrying 32 running sums through phase C cost 300 B of register spills per thread) ----
     {
@@ -516,6 +531,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
       }
     }
     __syncthreads();
+    LNS_FT(7);
     if (tid < 64) {
       double sm = 0.0, ss = 0.0;
       for (int w = 0; w < nwarp; ++w) {
@@ -534,6 +550,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
       stat_s[tid * 2 + 1] = (float)(-mean * rstd);
     }
     __syncthreads();
+    LNS_FT(8);
     // ---- phase E: fold the normalisation into to_out[1]'s filter slice and issue this head's tensor-core GEMM ----
     const uint32_t Wo_a = base + L.Wo + (uint32_t)(h & 1) * 8192u;
     for (int e = tid; e < 64 * 8; e += NTHR) {
@@ -559,6 +576,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
     fptx::fence_proxy_async();  // generic-proxy writes of U_s / Wo_s -> visible to the tensor core's async-proxy reads
     fptx::tc_fence_before();
     __syncthreads();
+    LNS_FT(9);
     if (tid == 0) {
       fptx::tc_fence_after();
       const uint64_t bdesc = desc_sw128(Wo_a);
@@ -570,6 +588,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
       }
       fptx::umma_commit(bar);
     }
+    LNS_FT(10);
   }
 
   // ================= after the last head: GELU(acc + b1') -> to_out[3] -> + skip -> out =================
@@ -664,6 +683,443 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
   }
 }
 
+
+// ====================================================================================================================
+// fablock_full2_kernel: the same block on PRE-STAGED operands with a producer warp (round 2, third session).
+//
+// The phase trace of fablock_full_kernel (-DLNS_FULL_TRACE, 32x32: 30.8k cycles per head) showed 8.5k cycles per head in
+// which the tensor pipes idle: 3.4k per-(sample, head) operand set-up (GroupNorm folded into the in_proj slice, its bias, Kx /
+// Ky conversion), 2.7k issuing 26 cp.async per thread for the raw input and the next head's operands (LSU bound), and 2.2k in
+// which 511 threads wait at a block barrier for thread 0 to push 32 tcgen05.mma through the (shared-memory bound) tensor
+// queue.  Here
+//   * lns_fablock_prepass_staged writes the NORMALISED input once per sample as the byte image of U_s (pixel permutation +
+//     128-byte swizzle applied): the in_proj slice is sample independent (16-bit, prepared once per parameter version, no
+//     bias), and a head's input is four linear 32 KB bulk copies;
+//   * one extra warp (lane 0) is the producer: it issues every bulk copy (input quarters, in_proj slice, Kx | Ky, the fp32
+//     to_out[1] slice) and every tcgen05.mma, and talks to the 16 compute warps through mbarriers only -- the compute warps
+//     synchronise among themselves with a named barrier and never wait for an instruction issue;
+//   * the head's tcgen05 GEMM is committed per quarter of the pixel rows, so the next head's input quarter q is refilled as soon
+//     as the MMAs that read quarter q have completed, and phase A of the next head starts on quarter 0 while the tensor core
+//     is still working on quarters 1-3.
+// Needs H, W in {16, 32} (power-of-two width, no pad rows, no padded kernel-matrix tiles).
+struct Full2Params {
+  const uint16_t* us;      // staged input [B][H*W][64] 16-bit: GroupNorm applied, pixel rows in U_s order, chunks swizzled
+  const __nv_bfloat16* u;  // the block's RAW input [B][H][W][64] (skip connection)
+  int H, W, heads;
+  const uint16_t* w_in16;  // [heads][64][kWS] 16-bit in_proj slices (rows padded to kWS)
+  const float* Kx;         // [B][heads][H][H]
+  const float* Ky;         // [B][heads][W][W]
+  float eps;
+  const float* w1h;        // [heads][64 out][64 in] fp32: to_out[1] slices, head-major
+  const float* w_out2;     // [64][64]
+  __nv_bfloat16* out;      // [B][H][W][64]
+  int T, tmem_cols, lgw;
+  long long* trace;
+};
+
+struct Full2Smem {
+  uint32_t U, Wo, W2, Ws, Kst, W1st, Kx, Ky, obias, red, stat, bar, slot, total;
+};
+__host__ __device__ inline Full2Smem full2_layout(int H, int W, int T, int nwarp) {
+  Full2Smem L;
+  uint32_t o = 0;
+  L.U = o; o += (uint32_t)T * 16384u;
+  L.Wo = o; o += 2u * 8192u;
+  L.W2 = o; o += 8192u;
+  L.Ws = o; o += 64u * kWS * 2u;
+  L.Kst = o; o += (uint32_t)(H * H + W * W) * 4u;
+  L.W1st = o; o += 64u * 64u * 4u;
+  L.Kx = o; o += (uint32_t)(H * (H + 8) * 2);
+  L.Ky = o; o += (uint32_t)(W * (W + 8) * 2);
+  o = (o + 15u) & ~15u;
+  L.obias = o; o += 64u * 4u;
+  L.red = o; o += (uint32_t)nwarp * 64u * 2u * 4u;
+  L.stat = o; o += 64u * 2u * 4u;
+  L.bar = o; o += 16u * 8u;
+  L.slot = o; o += 8u;
+  L.total = o;
+  return L;
+}
+
+namespace fptx {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void named_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
+}  // namespace fptx
+
+#ifdef LNS_FULL_TRACE
+#define LNS_FT2(i) do { if (tid == 0 && blockIdx.x == 0 && h < 4) p.trace[h * 16 + (i)] = clock64(); } while (0)
+#else
+#define LNS_FT2(i) do { } while (0)
+#endif
+
+// grid B (one CTA per sample), block NTHR compute threads + one producer warp
+template <int NTHR, bool F16>
+__global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_kernel(const Full2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (fptx::s32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - fptx::s32(smem_raw));
+  constexpr int nwarp = NTHR / 32;
+  constexpr int NQ = NTHR == 256 ? 2 : 4;  // parts of the pixel-row range: input copies, phase A and the MMA commits
+  const int H = p.H, W = p.W, T = p.T, heads = p.heads;
+  const Full2Smem L = full2_layout(H, W, T, nwarp);
+  const int HW = H * W;  // = pixel rows of U_s (no pad rows)
+  const int kxs = H + 8, kys = W + 8;
+  const uint32_t U_a = base + L.U, W2_a = base + L.W2, Ws_a = base + L.Ws, Kx_a = base + L.Kx, Ky_a = base + L.Ky;
+  const uint32_t Kst_a = base + L.Kst, W1st_a = base + L.W1st;
+  const uint32_t bar0 = base + L.bar;
+  auto bar_u = [&](int q) { return bar0 + (uint32_t)q * 8u; };          // input quarter q has landed (tx)
+  const uint32_t bar_ops = bar0 + 32u;                                   // in_proj slice + Kx | Ky have landed (tx)
+  const uint32_t bar_w1 = bar0 + 40u;                                    // to_out[1] slice has landed (tx)
+  const uint32_t bar_opfree = bar0 + 48u;                                // compute warps are done with Ws / Kst (nwarp arrivals)
+  const uint32_t bar_e = bar0 + 56u;                                     // compute warps have written U_s / Wo_s of this head
+  auto bar_mma = [&](int q) { return bar0 + 64u + (uint32_t)q * 8u; };  // the head's MMAs on quarter q have completed
+  const uint32_t bar_fin = bar0 + 96u;
+  uint16_t* Kx_s = reinterpret_cast<uint16_t*>(gen + L.Kx);
+  uint16_t* Ky_s = reinterpret_cast<uint16_t*>(gen + L.Ky);
+  float* obias_s = reinterpret_cast<float*>(gen + L.obias);
+  float* red_s = reinterpret_cast<float*>(gen + L.red);
+  float* stat_s = reinterpret_cast<float*>(gen + L.stat);
+  volatile uint32_t* slot_gen = reinterpret_cast<volatile uint32_t*>(gen + L.slot);
+  const float* stkx_s = reinterpret_cast<const float*>(gen + L.Kst);  // [H][H]
+  const float* stky_s = stkx_s + H * H;                                // [W][W]
+  const float* w1st_s = reinterpret_cast<const float*>(gen + L.W1st);  // [64 out][64 in]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const __nv_bfloat16* ub = p.u + (int64_t)b * HW * 64;
+
+  if (tid == 0) {
+    for (int q = 0; q < 4; ++q) {
+      fptx::mbar_init(bar_u(q), 1);
+      fptx::mbar_init(bar_mma(q), 1);
+    }
+    fptx::mbar_init(bar_ops, 1);
+    fptx::mbar_init(bar_w1, 1);
+    fptx::mbar_init(bar_opfree, nwarp);
+    fptx::mbar_init(bar_e, nwarp);
+    fptx::mbar_init(bar_fin, 1);
+    fptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    fptx::tmem_alloc(base + L.slot, (uint32_t)p.tmem_cols);
+    fptx::tmem_relinquish();
+  }
+  if (tid < 64) obias_s[tid] = 0.f;
+  // to_out[3] filter -> 16-bit swizzled K-major B operand [64 n][64 k]
+  for (int e = tid; e < 64 * 8; e += NTHR + 32) {
+    const int n = e >> 3, kc = e & 7;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_out2 + n * 64 + kc * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_out2 + n * 64 + kc * 8 + 4));
+    fptx::st_shared_v4(W2_a + sw_off(n, kc), pack2_h16<F16>(w0.x, w0.y), pack2_h16<F16>(w0.z, w0.w), pack2_h16<F16>(w1.x, w1.y),
+                       pack2_h16<F16>(w1.z, w1.w));
+  }
+  fptx::tc_fence_before();
+  __syncthreads();  // the only block-wide barrier: from here on the producer warp and the compute warps meet at mbarriers
+  fptx::tc_fence_after();
+  const uint32_t tmem_acc = *slot_gen;
+  // instruction descriptor, kind::f16: D = f32, A/B = bf16 (1) or f16 (0), K-major, N = 64, M = 128
+  const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t qbytes = (uint32_t)HW * 128u / NQ;
+  const int tl_per_q = T / NQ;
+
+  if (warp == nwarp) {
+    // ======================= producer warp: bulk copies + tcgen05.mma issue, one lane =======================
+    if (lane == 0) {
+      const uint8_t* usb = reinterpret_cast<const uint8_t*>(p.us) + (size_t)b * HW * 128u;
+      const uint32_t kxb = (uint32_t)(H * H) * 4u, kyb = (uint32_t)(W * W) * 4u;
+      auto issue_ops = [&](int hh) {
+        fptx::mbar_expect_tx(bar_ops, 64u * kWS * 2u + kxb + kyb);
+        fptx::bulk_g2s(Ws_a, p.w_in16 + (size_t)hh * 64 * kWS, 64u * kWS * 2u, bar_ops);
+        fptx::bulk_g2s(Kst_a, p.Kx + ((int64_t)b * heads + hh) * H * H, kxb, bar_ops);
+        fptx::bulk_g2s(Kst_a + kxb, p.Ky + ((int64_t)b * heads + hh) * W * W, kyb, bar_ops);
+      };
+      auto issue_w1 = [&](int hh) {
+        fptx::mbar_expect_tx(bar_w1, 64u * 64u * 4u);
+        fptx::bulk_g2s(W1st_a, p.w1h + (size_t)hh * 64 * 64, 64u * 64u * 4u, bar_w1);
+      };
+      auto issue_u = [&](int q) {
+        fptx::mbar_expect_tx(bar_u(q), qbytes);
+        fptx::bulk_g2s(U_a + (uint32_t)q * qbytes, usb + (size_t)q * qbytes, qbytes, bar_u(q));
+      };
+      issue_ops(0);
+      for (int q = 0; q < NQ; ++q) issue_u(q);
+      issue_w1(0);
+      for (int h = 0; h < heads; ++h) {
+        const uint32_t par = (uint32_t)(h & 1);
+        if (h + 1 < heads) {
+          fptx::mbar_wait(bar_opfree, par);  // every compute warp holds its in_proj fragments and has converted Kx | Ky
+          issue_ops(h + 1);
+        }
+        fptx::mbar_wait(bar_e, par);  // U_s holds the head's u_phi, Wo_s[h & 1] the folded to_out[1] slice
+        fptx::tc_fence_after();
+        if (h + 1 < heads) issue_w1(h + 1);
+        const uint64_t bdesc = desc_sw128(base + L.Wo + (uint32_t)(h & 1) * 8192u);
+        for (int q = 0; q < NQ; ++q) {
+          for (int tl = q * tl_per_q; tl < (q + 1) * tl_per_q; ++tl) {
+            const uint64_t adesc = desc_sw128(U_a + (uint32_t)tl * 16384u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              fptx::umma_f16(tmem_acc + (uint32_t)(tl * 64), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (h | k) != 0 ? 1u : 0u);
+          }
+          fptx::umma_commit(bar_mma(q));
+        }
+        if (h + 1 < heads)
+          for (int q = 0; q < NQ; ++q) {
+            fptx::mbar_wait(bar_mma(q), par);  // the tensor core has read quarter q: refill it with the next head's input
+            issue_u(q);
+          }
+      }
+    }
+    return;
+  }
+
+  // =================================== compute warps ===================================
+  const int t = lane & 3;
+  (void)t;
+  const int nblk = HW >> 4;
+  const int blk_per_q = nblk / NQ;
+  for (int h = 0; h < heads; ++h) {
+    const uint32_t par = (uint32_t)(h & 1);
+    LNS_FT2(0);
+    fptx::mbar_wait(bar_ops, par);
+    for (int i = warp; i < H; i += nwarp)
+      for (int j = lane; j < H; j += 32) Kx_s[i * kxs + j] = to_h16<F16>(stkx_s[i * H + j]);
+    for (int i = warp; i < W; i += nwarp)
+      for (int j = lane; j < W; j += 32) Ky_s[i * kys + j] = to_h16<F16>(stky_s[i * W + j]);
+    uint32_t wf[4][8][2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+        fptx::ldsm_x2(Ws_a + (uint32_t)(((nt * 8 + (lane & 7)) * kWS + ks * 16 + ((lane >> 3) & 1) * 8) * 2), wf[ks][nt][0], wf[ks][nt][1]);
+    __syncwarp();
+    if (lane == 0) fptx::mbar_arrive(bar_opfree);
+    LNS_FT2(1);
+    // ---- phase A: u_phi_h = u_n x W_in[h]^T, in place, 16-row blocks per warp; quarter q as soon as it has landed ----
+    for (int q = 0; q < NQ; ++q) {
+      fptx::mbar_wait(bar_u(q), par);
+      if (q == 0) LNS_FT2(2);
+      for (int blk = q * blk_per_q + warp; blk < (q + 1) * blk_per_q; blk += nwarp) {
+        const int pr = blk * 16 + (lane & 15);
+        uint32_t a[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) fptx::ldsm_x4(U_a + sw_off(pr, ks * 2 + (lane >> 4)), a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
+        float acc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) fptx::mma16816<F16>(acc[nt], a[ks], wf[ks][nt][0], wf[ks][nt][1]);
+        }
+        __syncwarp();  // every lane's ldmatrix of the raw rows is done before they are overwritten
+        const int rs_row = blk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+        const uint32_t rs = U_a + (uint32_t)rs_row * 128u;
+        const int phs = rs_row & 7, cs = lane >> 4;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt += 2) {
+          fptx::stsm_x4(rs + (uint32_t)(((nt + cs) ^ phs) << 4), pack2_h16<F16>(acc[nt][0], acc[nt][1]),
+                        pack2_h16<F16>(acc[nt][2], acc[nt][3]), pack2_h16<F16>(acc[nt + 1][0], acc[nt + 1][1]),
+                        pack2_h16<F16>(acc[nt + 1][2], acc[nt + 1][3]));
+        }
+      }
+    }
+    fptx::named_sync<NTHR>();  // (also publishes Kx_s / Ky_s)
+    LNS_FT2(3);
+    // ---- phase B: contraction over H, one image column per warp at a time ----
+    for (int m = warp; m < W; m += nwarp) {
+      if (H == 16) contract_line_sw<1, 0, F16>(U_a, m, W, H, Kx_a, kxs, lane);
+      else contract_line_sw<2, 0, F16>(U_a, m, W, H, Kx_a, kxs, lane);
+    }
+    fptx::named_sync<NTHR>();
+    LNS_FT2(4);
+    // ---- phase C: contraction over W, one image row per warp ----
+    for (int i = warp; i < H; i += nwarp) {
+      if (W == 16) contract_line_sw<1, 1, F16>(U_a, i, W, W, Ky_a, kys, lane);
+      else contract_line_sw<2, 1, F16>(U_a, i, W, W, Ky_a, kys, lane);
+    }
+    fptx::named_sync<NTHR>();
+    LNS_FT2(5);
+    // ---- phase D: InstanceNorm statistics of this head's 64 channels, from the 16-bit values the GEMM will read ----
+    {
+      const int ch = tid & 7;
+      float sm8[8], sq8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sm8[j] = sq8[j] = 0.f;
+      for (int s = tid >> 3; s < HW; s += NTHR / 2) {  // four 16-byte loads in flight per thread
+        uint32_t w[4][4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[q4][0]), "=r"(w[q4][1]), "=r"(w[q4][2]), "=r"(w[q4][3])
+                       : "r"(U_a + sw_off(s + q4 * (NTHR / 8), ch)));
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2_h16<F16>(w[q4][j]);
+            sm8[2 * j] += f.x; sq8[2 * j] = fmaf(f.x, f.x, sq8[2 * j]);
+            sm8[2 * j + 1] += f.y; sq8[2 * j + 1] = fmaf(f.y, f.y, sq8[2 * j + 1]);
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // the 4 pixel lanes of a warp that share this channel chunk
+        sm8[j] += __shfl_xor_sync(0xffffffffu, sm8[j], 8);
+        sm8[j] += __shfl_xor_sync(0xffffffffu, sm8[j], 16);
+        sq8[j] += __shfl_xor_sync(0xffffffffu, sq8[j], 8);
+        sq8[j] += __shfl_xor_sync(0xffffffffu, sq8[j], 16);
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          red_s[(warp * 64 + ch * 8 + j) * 2 + 0] = sm8[j];
+          red_s[(warp * 64 + ch * 8 + j) * 2 + 1] = sq8[j];
+        }
+      }
+    }
+    fptx::named_sync<NTHR>();
+    LNS_FT2(6);
+    if (tid < 64) {
+      double sm = 0.0, ss = 0.0;
+      for (int w = 0; w < nwarp; ++w) {
+        sm += (double)red_s[(w * 64 + tid) * 2 + 0];
+        ss += (double)red_s[(w * 64 + tid) * 2 + 1];
+      }
+      const double inv_n = 1.0 / (double)HW;
+      const double mean = sm * inv_n;
+      double var = ss * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double ve = var + (double)p.eps;
+      double rstd = (double)rsqrtf((float)ve);
+      rstd = rstd * (1.5 - 0.5 * ve * rstd * rstd);
+      rstd = rstd * (1.5 - 0.5 * ve * rstd * rstd);
+      stat_s[tid * 2 + 0] = (float)rstd;
+      stat_s[tid * 2 + 1] = (float)(-mean * rstd);
+    }
+    fptx::mbar_wait(bar_w1, par);
+    fptx::named_sync<NTHR>();
+    LNS_FT2(7);
+    // ---- phase E: fold the normalisation into to_out[1]'s slice (staged in shared memory); the producer issues the GEMM ----
+    const uint32_t Wo_a = base + L.Wo + (uint32_t)(h & 1) * 8192u;
+    for (int e = tid; e < 64 * 8; e += NTHR) {
+      const int n = e >> 3, kc = e & 7;
+      const float4 w0 = *reinterpret_cast<const float4*>(w1st_s + n * 64 + kc * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(w1st_s + n * 64 + kc * 8 + 4);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      float sc[8];
+      float bsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j] = wv[j] * stat_s[(kc * 8 + j) * 2 + 0];
+        bsum = fmaf(wv[j], stat_s[(kc * 8 + j) * 2 + 1], bsum);
+      }
+      fptx::st_shared_v4(Wo_a + sw_off(n, kc), pack2_h16<F16>(sc[0], sc[1]), pack2_h16<F16>(sc[2], sc[3]), pack2_h16<F16>(sc[4], sc[5]),
+                         pack2_h16<F16>(sc[6], sc[7]));
+      bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
+      bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
+      bsum += __shfl_xor_sync(0xffffffffu, bsum, 4);
+      if (kc == 0) obias_s[n] += bsum;
+    }
+    fptx::fence_proxy_async();  // generic-proxy writes of U_s / Wo_s -> visible to the tensor core's async-proxy reads
+    fptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) fptx::mbar_arrive(bar_e);
+    LNS_FT2(8);
+  }
+
+  // ================= after the last head: GELU(acc + b1') -> to_out[3] -> + skip -> out =================
+  fptx::mbar_wait(bar_mma(NQ - 1), (uint32_t)((heads - 1) & 1));
+  fptx::tc_fence_after();
+  fptx::named_sync<NTHR>();  // obias_s of the last head is complete
+  const int quad = warp & 3, sub = warp >> 2, nsub = nwarp >> 2;
+  for (int tl = sub; tl < T; tl += nsub) {
+    const int pr = tl * 128 + quad * 32 + lane;
+    const uint32_t row_a = U_a + (uint32_t)pr * 128u;
+    const int ph = pr & 7;
+#pragma unroll
+    for (int cc = 0; cc < 64; cc += 32) {
+      uint32_t raw[32];
+      fptx::tmem_ld32(tmem_acc + (uint32_t)(tl * 64 + cc) + ((uint32_t)(quad * 32) << 16), raw);
+      fptx::tmem_ld_wait();
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_gelu_fast(__uint_as_float(raw[c8 * 8 + j]) + obias_s[cc + c8 * 8 + j]);
+        fptx::st_shared_v4(row_a + (uint32_t)((((cc >> 3) + c8) ^ ph) << 4), pack2_h16<F16>(v[0], v[1]), pack2_h16<F16>(v[2], v[3]),
+                           pack2_h16<F16>(v[4], v[5]), pack2_h16<F16>(v[6], v[7]));
+      }
+    }
+  }
+  fptx::fence_proxy_async();
+  fptx::tc_fence_before();
+  fptx::named_sync<NTHR>();
+  if (tid == 0) {
+    fptx::tc_fence_after();
+    const uint64_t bdesc = desc_sw128(W2_a);
+    for (int tl = 0; tl < T; ++tl) {
+      const uint64_t adesc = desc_sw128(U_a + (uint32_t)tl * 16384u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        fptx::umma_f16(tmem_acc + (uint32_t)(tl * 64), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+    }
+    fptx::umma_commit(bar_fin);
+  }
+  fptx::mbar_wait(bar_fin, 0u);
+  fptx::tc_fence_after();
+  // epilogue 2: + skip (the block's raw input, fp32 add), 16-bit result back into the pixel's own row of U_s
+  for (int tl = sub; tl < T; tl += nsub) {
+    const int pr = tl * 128 + quad * 32 + lane;
+    const int src = pr ^ ((pr >> p.lgw) & 7);  // the pixel that lives in row pr
+    const uint4* skip = reinterpret_cast<const uint4*>(ub + (int64_t)src * 64);
+    const uint32_t row_a = U_a + (uint32_t)pr * 128u;
+    const int ph = pr & 7;
+#pragma unroll
+    for (int cc = 0; cc < 64; cc += 32) {
+      uint32_t raw[32];
+      fptx::tmem_ld32(tmem_acc + (uint32_t)(tl * 64 + cc) + ((uint32_t)(quad * 32) << 16), raw);
+      uint4 sk[4];
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) sk[c8] = __ldg(skip + (cc >> 3) + c8);
+      fptx::tmem_ld_wait();
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        const uint32_t sw[4] = {sk[c8].x, sk[c8].y, sk[c8].z, sk[c8].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 s2 = unpack2_h16<F16>(sw[j]);
+          o[j] = pack2_h16<F16>(__uint_as_float(raw[c8 * 8 + 2 * j]) + s2.x, __uint_as_float(raw[c8 * 8 + 2 * j + 1]) + s2.y);
+        }
+        fptx::st_shared_v4(row_a + (uint32_t)((((cc >> 3) + c8) ^ ph) << 4), o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  fptx::tc_fence_before();
+  fptx::named_sync<NTHR>();
+  // copy-out: 8 lanes x 16 B per pixel row -> full 128-byte lines of the NHWC output
+  {
+    const int ch = tid & 7;
+    uint8_t* ob = reinterpret_cast<uint8_t*>(p.out + (int64_t)b * HW * 64) + ch * 16;
+    for (int s = tid >> 3; s < HW; s += NTHR / 8) {
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(U_a + sw_off(s, ch)));
+      *reinterpret_cast<uint4*>(ob + (size_t)(s ^ ((s >> p.lgw) & 7)) * 128u) = make_uint4(w0, w1, w2, w3);
+    }
+  }
+  if (warp == 0) {
+    fptx::tc_fence_after();
+    fptx::tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+  }
+}
+
 }  // namespace lns
 
 extern "C" {
@@ -704,6 +1160,15 @@ int lns_fablock_full(const void* u, int dtype, int B, int H, int W, int heads, c
     while ((1 << lg) < W) ++lg;
     p.lgwp = lg;
   }
+  p.trace = nullptr;
+#ifdef LNS_FULL_TRACE
+  {
+    static long long* dbg = nullptr;
+    if (!dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
+    p.trace = dbg;
+    cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), reinterpret_cast<cudaStream_t>(stream));
+  }
+#endif
   int cols = 32;
   while (cols < p.T * 64) cols <<= 1;
   p.tmem_cols = cols;
@@ -724,7 +1189,93 @@ int lns_fablock_full(const void* u, int dtype, int B, int H, int W, int heads, c
     auto kern = f16 ? lns::fablock_full_kernel<256, true> : lns::fablock_full_kernel<256, false>;
     kern<<<B, 256, smem, st>>>(p);
   }
+#ifdef LNS_FULL_TRACE
+  {
+    long long hbuf[64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf, p.trace, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    static int printed = 0;
+    if (printed++ < 2)
+      for (int h = 1; h < 4; ++h) {
+        fprintf(stderr, "fablock_full trace head %d (%dx%d):", h, H, W);
+        for (int i = 1; i < 11; ++i) fprintf(stderr, " s%d->%d %lld", i - 1, i, hbuf[h * 16 + i] - hbuf[h * 16 + i - 1]);
+        fprintf(stderr, " | head total %lld\n", hbuf[h * 16 + 10] - hbuf[(h - 1) * 16 + 10]);
+      }
+  }
+#endif
   return lns::check_launch("fablock_full_kernel");
+}
+
+int lns_fablock_full_staged_supported(int H, int W, int dim, int dim_head, int dim_out) {
+  if (dim != 64 || dim_head != 64 || dim_out != 64) return 0;
+  if ((H != 16 && H != 32) || (W != 16 && W != 32)) return 0;
+  return 1;
+}
+
+int lns_fablock_full_staged(const void* u_staged, const void* u, int dtype, int B, int H, int W, int heads, const void* w_in16,
+                            const float* Kx, const float* Ky, float eps, const float* w1h, const float* w_out2, void* out,
+                            void* stream) {
+  LNS_REQUIRE(u_staged && u && w_in16 && Kx && Ky && w1h && w_out2 && out && B > 0 && heads > 0, "lns_fablock_full_staged: bad arguments");
+  LNS_REQUIRE(lns::is_h16_host(dtype), "lns_fablock_full_staged: u/out must be LNS_BF16 or LNS_F16 (got dtype %d)", dtype);
+  LNS_REQUIRE(lns_fablock_full_staged_supported(H, W, 64, 64, 64), "lns_fablock_full_staged: %dx%d not covered (use lns_fablock_full)", H, W);
+  LNS_REQUIRE((reinterpret_cast<uintptr_t>(u_staged) & 15) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_in16) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(w1h) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_out2) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(Kx) & 15) == 0 && (reinterpret_cast<uintptr_t>(Ky) & 15) == 0,
+              "lns_fablock_full_staged: pointers must be 16-byte aligned");
+  lns::Full2Params p;
+  p.us = reinterpret_cast<const uint16_t*>(u_staged);
+  p.u = reinterpret_cast<const __nv_bfloat16*>(u);
+  p.H = H; p.W = W; p.heads = heads;
+  p.w_in16 = reinterpret_cast<const uint16_t*>(w_in16);
+  p.Kx = Kx; p.Ky = Ky; p.eps = eps; p.w1h = w1h; p.w_out2 = w_out2;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.T = H * W / 128;
+  p.lgw = W == 32 ? 5 : 4;
+  p.trace = nullptr;
+#ifdef LNS_FULL_TRACE
+  {
+    static long long* dbg = nullptr;
+    if (!dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
+    p.trace = dbg;
+    cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), reinterpret_cast<cudaStream_t>(stream));
+  }
+#endif
+  int cols = 32;
+  while (cols < p.T * 64) cols <<= 1;
+  p.tmem_cols = cols;
+  const bool big = H * W > 256;
+  const size_t smem = lns::full2_layout(H, W, p.T, big ? 16 : 8).total + 1024;
+  {
+    LNS_OPT_IN_SMEM((lns::fablock_full2_kernel<512, false>), 227 * 1024, "fablock_full_staged");
+    LNS_OPT_IN_SMEM((lns::fablock_full2_kernel<256, false>), 227 * 1024, "fablock_full_staged");
+    LNS_OPT_IN_SMEM((lns::fablock_full2_kernel<512, true>), 227 * 1024, "fablock_full_staged");
+    LNS_OPT_IN_SMEM((lns::fablock_full2_kernel<256, true>), 227 * 1024, "fablock_full_staged");
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool f16 = dtype == LNS_F16;
+  if (big) {
+    auto kern = f16 ? lns::fablock_full2_kernel<512, true> : lns::fablock_full2_kernel<512, false>;
+    kern<<<B, 512 + 32, smem, st>>>(p);
+  } else {
+    auto kern = f16 ? lns::fablock_full2_kernel<256, true> : lns::fablock_full2_kernel<256, false>;
+    kern<<<B, 256 + 32, smem, st>>>(p);
+  }
+#ifdef LNS_FULL_TRACE
+  {
+    long long hbuf[64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf, p.trace, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    static int printed = 0;
+    if (printed++ < 2)
+      for (int h = 1; h < 4; ++h) {
+        fprintf(stderr, "fablock_full2 trace head %d (%dx%d):", h, H, W);
+        for (int i = 1; i < 9; ++i) fprintf(stderr, " s%d->%d %lld", i - 1, i, hbuf[h * 16 + i] - hbuf[h * 16 + i - 1]);
+        fprintf(stderr, " | head total %lld\n", hbuf[h * 16 + 8] - hbuf[(h - 1) * 16 + 8]);
+      }
+  }
+#endif
+  return lns::check_launch("fablock_full2_kernel");
 }
 
 }  // extern "C"

@@ -55,6 +55,9 @@ class _State(threading.local):
         # barrier-separated MMA / drain stages is latency bound at one CTA per SM -- 7.7 ms vs 5.2 ms for the mma.sync kernel at
         # 4736 x 32x32 (profiles/r02_fablock_tc.md) -- so it is opt-in until the stages are software-pipelined
         self.fablock_tc = os.environ.get("LNS_FABLOCK_TC", "0") != "0"
+        # FABlock2D whole-block kernel on pre-staged operands with a producer warp (fablock_full2_kernel); LNS_FABLOCK_STAGED=0
+        # falls back to the in-kernel staging version (fablock_full_kernel)
+        self.fablock_staged = os.environ.get("LNS_FABLOCK_STAGED", "0") != "0"
 
 
 def _mark(label, flops=0.0, nbytes=0.0):
@@ -775,8 +778,9 @@ def fablock_core_supported(x, dim_head):
             and bool(_C.lib().lns_fablock_core_supported(x.H, x.W, x.C, dim_head)))
 
 
-def fablock_prepass(u, eps, gamma, beta):
-    """-> (scale [B*C], shift [B*C], pooled_x Act [B,H,1,C] fp32, pooled_y Act [B,W,1,C] fp32) in one read of u."""
+def fablock_prepass(u, eps, gamma, beta, staged=False):
+    """-> (scale [B*C], shift [B*C], pooled_x Act [B,H,1,C] fp32, pooled_y Act [B,W,1,C] fp32) in one read of u.
+    staged=True: also the normalised sample as the shared-memory image fablock_full_staged reads (fifth value)."""
     dev = u.t.device
     scale = torch.empty(u.B * u.C, dtype=torch.float32, device=dev)
     shift = torch.empty_like(scale)
@@ -784,6 +788,15 @@ def fablock_prepass(u, eps, gamma, beta):
     py = Act.empty(u.B, u.W, 1, u.C, torch.float32, dev)
     g = gamma.detach().float().contiguous() if gamma is not None else None
     b = beta.detach().float().contiguous() if beta is not None else None
+    if staged:
+        st = torch.empty(u.B * u.H * u.W * u.C, dtype=u.t.dtype, device=dev)
+        tok = _mark(f"fablock_prepass @{u.H}x{u.W}", nbytes=2 * _abytes(u))
+        rc = _C.lib().lns_fablock_prepass_staged(_ptr(u.t), u.dtype, u.B, u.H, u.W, u.C, u.bstride, float(eps), _ptr(g), _ptr(b),
+                                                 _ptr(scale), _ptr(shift), _ptr(px.t), _ptr(py.t), _ptr(st), _stream())
+        check(rc, "lns_fablock_prepass_staged")
+        _done(tok)
+        _state.launches += 1
+        return scale, shift, px, py, st
     tok = _mark(f"fablock_prepass @{u.H}x{u.W}", nbytes=_abytes(u))
     rc = _C.lib().lns_fablock_prepass(_ptr(u.t), u.dtype, u.B, u.H, u.W, u.C, u.bstride, float(eps), _ptr(g), _ptr(b),
                                       _ptr(scale), _ptr(shift), _ptr(px.t), _ptr(py.t), _stream())
@@ -910,6 +923,39 @@ def fablock_full(u, gn_scale, gn_shift, w_in_proj, Kx, Ky, heads, eps, w_out1, w
     rc = _C.lib().lns_fablock_full(_ptr(u.t), u.dtype, u.B, u.H, u.W, heads, _ptr(gn_scale), _ptr(gn_shift), _ptr(wi), _ptr(Kx),
                                    _ptr(Ky), float(eps), _ptr(w1), _ptr(w2), _ptr(out.t), _stream())
     check(rc, "lns_fablock_full")
+    _done(tok)
+    _state.launches += 1
+    return out
+
+
+def fablock_full_staged_supported(x, dim_head, dim_out):
+    return (_state.fablock_staged and x.t.dtype in H16_DTYPES and x.layout == NHWC and x.contiguous
+            and bool(_C.lib().lns_fablock_full_staged_supported(x.H, x.W, x.C, dim_head, dim_out)))
+
+
+def fablock_staged_operands(w_in_proj, w_out1, heads, dt16):
+    """Sample-independent operands of fablock_full_staged: in_proj slices as 16-bit rows padded to 72 elements, to_out[1]
+    head-major in fp32 (prepare once per parameter version)."""
+    with torch.no_grad():
+        wi = w_in_proj.detach().float().reshape(heads, 64, 64)
+        w_in16 = torch.zeros(heads, 64, 72, dtype=dt16, device=wi.device)
+        w_in16[:, :, :64] = wi.to(dt16)
+        w1h = w_out1.detach().float().reshape(64, heads, 64).permute(1, 0, 2).contiguous()
+    return w_in16.contiguous(), w1h
+
+
+def fablock_full_staged(u_staged, u, w_in16, Kx, Ky, heads, eps, w1h, w_out2):
+    """fablock_full on pre-staged operands (csrc/fablock_full.cu, producer-warp kernel): u_staged from fablock_prepass(staged=True),
+    (w_in16, w1h) from fablock_staged_operands; u is the raw block input (skip connection)."""
+    out = u.like()
+    w2 = w_out2.detach().float().reshape(w_out2.shape[0], -1).contiguous()
+    hw_ = u.H * u.W
+    tok = _mark(f"fablock_full @{u.H}x{u.W}",
+                flops=u.B * (2.0 * hw_ * 64 * heads * 64 * 2 + 2.0 * heads * (u.H * u.H * u.W + u.H * u.W * u.W) * 64 + 2.0 * hw_ * 64 * 64),
+                nbytes=_abytes(u, out) + 4.0 * u.B * heads * (u.H * u.H + u.W * u.W))
+    rc = _C.lib().lns_fablock_full_staged(_ptr(u_staged), _ptr(u.t), u.dtype, u.B, u.H, u.W, heads, _ptr(w_in16), _ptr(Kx), _ptr(Ky),
+                                          float(eps), _ptr(w1h), _ptr(w2), _ptr(out.t), _stream())
+    check(rc, "lns_fablock_full_staged")
     _done(tok)
     _state.launches += 1
     return out

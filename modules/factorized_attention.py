@@ -118,9 +118,16 @@ class FABlock2D(LnsModule):
         inorm = self.to_out[0]
         fused = (ops.fast16() and self.in_proj.out_channels == self.heads * 64
                  and ops.fablock_core_supported(u, self.dim_head) and inorm.weight is None)
+        staged = None
         if fused:
-            # one read of u: GroupNorm(1) affine + both pooled tensors (means commute with the per-channel affine)
-            s, t, mx, my = ops.fablock_prepass(u, self.in_norm.eps, self.in_norm.weight, self.in_norm.bias)
+            # one read of u: GroupNorm(1) affine + both pooled tensors (means commute with the per-channel affine); when the
+            # producer-warp whole-block kernel takes the shape, also the normalised sample as that kernel's shared-memory image
+            if (self.to_out[1].bias is None and self.to_out[3].bias is None and self.to_out[1].out_channels == 64
+                    and ops.fablock_full_staged_supported(u, self.dim_head, self.to_out[3].out_channels)
+                    and not ops.fablock_tc_supported(u, self.dim_head, self.to_out[3].out_channels)):
+                s, t, mx, my, staged = ops.fablock_prepass(u, self.in_norm.eps, self.in_norm.weight, self.in_norm.bias, staged=True)
+            else:
+                s, t, mx, my = ops.fablock_prepass(u, self.in_norm.eps, self.in_norm.weight, self.in_norm.bias)
         else:
             s, t = norm_affine(u, self.in_norm)
             un = ops.affine_act(u, s, t, ops.ACT_NONE)
@@ -131,13 +138,13 @@ class FABlock2D(LnsModule):
         if fused:
             kk = self._axis_kernels(mx, my)
             if kk is not None:
-                return self._finish(u, skip, s, t, kk[0], kk[1], inorm, fused)
+                return self._finish(u, skip, s, t, kk[0], kk[1], inorm, fused, staged=staged)
         pd = ops.act_dtype() if fused else f32
         px = ops.conv2d(mx, filt_of(self.to_in[0]), out_dtype=pd)   # rows indexed by H
         py = ops.conv2d(my, filt_of(self.to_in[0]), out_dtype=pd)   # rows indexed by W
         k_x = self.low_rank_kernel_x._fwd(self.to_x[0]._fwd(px))
         k_y = self.low_rank_kernel_y._fwd(self.to_y[1]._fwd(py))
-        return self._finish(u, skip, s, t, k_x, k_y, inorm, fused, un=None if fused else un)
+        return self._finish(u, skip, s, t, k_x, k_y, inorm, fused, un=None if fused else un, staged=staged)
 
     def _axis_operands(self, reducer, lrk, dt16):
         """Host-prepared operands of lns_fa_axis_kernel for one axis, cached until a source parameter changes."""
@@ -184,7 +191,22 @@ class FABlock2D(LnsModule):
                                           o["wf2t"], o["bf2"], o["wqk16"], cos_t, sin_t, lrk.scaling))
         return out
 
-    def _finish(self, u, skip, s, t, k_x, k_y, inorm, fused, un=None):
+    def _staged_operands(self, dt16):
+        """(w_in16, w1h) of ops.fablock_full_staged, cached until in_proj / to_out[1] change."""
+        srcs = [self.in_proj.weight, self.to_out[1].weight]
+        key = (dt16,) + tuple((w.data_ptr(), w._version, str(w.device)) for w in srcs)
+        cache = cache_of(self)
+        ent = cache.get("staged")
+        if ent is None or ent[0] != key:
+            ent = (key, ops.fablock_staged_operands(self.in_proj.weight, self.to_out[1].weight, self.heads, dt16))
+            cache["staged"] = ent
+        return ent[1]
+
+    def _finish(self, u, skip, s, t, k_x, k_y, inorm, fused, un=None, staged=None):
+        if staged is not None and k_x.dtype == torch.float32 and k_y.dtype == torch.float32:
+            w_in16, w1h = self._staged_operands(u.t.dtype)
+            return ops.fablock_full_staged(staged, u, w_in16, k_x.contiguous(), k_y.contiguous(), self.heads, inorm.eps, w1h,
+                                           self.to_out[3].weight)
         if (fused and self.to_out[1].bias is None and self.to_out[3].bias is None
                 and ops.fablock_full_supported(u, self.dim_head, self.to_out[3].out_channels)
                 and self.to_out[1].out_channels == 64):

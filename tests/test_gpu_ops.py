@@ -1012,3 +1012,45 @@ def test_fablock_tc_vs_full_and_oracle(n, B, prec):
     # every sample, not only the first ones: per-sample error against the other kernel
     per = ((tc - full).flatten(1).norm(dim=1) / full.flatten(1).norm(dim=1)).max().item()
     assert per < tol
+
+
+# ---- FABlock2D whole-block kernel on pre-staged operands with a producer warp (csrc/fablock_full.cu, fablock_full2_kernel) --------
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("H,W,B", [(16, 16, 5), (32, 32, 3), (32, 32, 300), (16, 16, 700), (16, 32, 4), (32, 16, 4)])
+def test_fablock_staged_vs_full_and_oracle(H, W, B, prec):
+    """producer-warp whole-block kernel (normalised input staged by the pre-pass, bulk copies, tcgen05 issue off the compute warps)
+    vs the fp64 oracle of the reference block (modules/factorized_attention.py:144-159) and vs the in-kernel-staging kernel"""
+    ops = ops_mod()
+    import lns_oracle as O
+    from modules.factorized_attention import FABlock2D
+    dt = torch.float16 if prec == "fp16" else torch.bfloat16
+    torch.manual_seed(3)
+    blk = FABlock2D(64, 64, 64, 8, 64).to(DEV).eval()
+    with torch.no_grad():  # a non-trivial GroupNorm affine: the staged path applies it in the pre-pass
+        blk.in_norm.weight.uniform_(0.5, 1.5)
+        blk.in_norm.bias.uniform_(-0.3, 0.3)
+    g = torch.Generator().manual_seed(46)
+    x = torch.randn(B, 64, H, W, generator=g) * 1.7 + 0.4
+    a = act_from(x, dt)
+    saved = ops._state.fablock_staged
+    ops._state.fablock_staged = True
+    try:
+        assert ops.fablock_full_staged_supported(a, 64, 64)
+        with torch.no_grad(), ops.precision(prec):
+            st = act_to_nchw(blk._fwd(a))
+            st2 = act_to_nchw(blk._fwd(a))
+            ops._state.fablock_staged = False
+            full = act_to_nchw(blk._fwd(a))
+    finally:
+        ops._state.fablock_staged = saved
+    assert torch.equal(st, st2)  # deterministic (fixed-order reductions, no atomics)
+    nb = min(B, 4)
+    sd = {k: v.cpu().double() for k, v in blk.state_dict().items()}
+    ref = O.fa_block(x[:nb].double(), O.SD(sd))
+    e_st, e_full = relerr(st[:nb], ref), relerr(full[:nb], ref)
+    print(f"[FABlock2D {H}x{W} {prec} B={B}] staged kernel vs fp64 oracle {e_st:.2e}, in-kernel staging {e_full:.2e}, staged vs full "
+          f"{relerr(st, full):.2e}")
+    tol = 4e-3 if prec == "fp16" else 3e-2
+    assert e_st < tol and relerr(st, full) < tol
+    per = ((st - full).flatten(1).norm(dim=1) / full.flatten(1).norm(dim=1)).max().item()
+    assert per < tol
