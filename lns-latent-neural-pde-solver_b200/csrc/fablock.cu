@@ -549,19 +549,27 @@ __global__ void __launch_bounds__(256) fablock_prepass2_kernel(const void* __res
   if (staged != nullptr) {
     const uint16_t* u16 = reinterpret_cast<const uint16_t*>(u) + (int64_t)b * bstride;
     uint16_t* dst = staged + (int64_t)b * H * W * 64;
-    for (int e = threadIdx.x; e < H * W * 8; e += 256) {
-      const int sl = e >> 3, ch = e & 7;
-      const int src = sl ^ ((sl >> lgw) & 7);
-      const uint4 raw = *reinterpret_cast<const uint4*>(u16 + (int64_t)src * 64 + ch * 8);
-      const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-      uint32_t o[4];
+    // H * W * 8 chunks of 16 bytes, a multiple of 4 * 256: four independent loads in flight per thread
+    for (int e0 = threadIdx.x; e0 < H * W * 8; e0 += 4 * 256) {
+      uint4 raw[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack2_rt(dtype, rw[j]);
-        const int c = ch * 8 + 2 * j;
-        o[j] = pack2_rt(dtype, fmaf(f.x, ab[c * 2], ab[c * 2 + 1]), fmaf(f.y, ab[c * 2 + 2], ab[c * 2 + 3]));
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 256, sl = e >> 3, ch = e & 7;
+        raw[k] = __ldg(reinterpret_cast<const uint4*>(u16 + (int64_t)(sl ^ ((sl >> lgw) & 7)) * 64 + ch * 8));
       }
-      *reinterpret_cast<uint4*>(dst + (int64_t)sl * 64 + ((ch ^ (sl & 7)) << 3)) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 256, sl = e >> 3, ch = e & 7;
+        const uint32_t rw[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack2_rt(dtype, rw[j]);
+          const float4 a4 = *reinterpret_cast<const float4*>(ab + (ch * 8 + 2 * j) * 2);  // scale, shift of two channels
+          o[j] = pack2_rt(dtype, fmaf(f.x, a4.x, a4.y), fmaf(f.y, a4.z, a4.w));
+        }
+        *reinterpret_cast<uint4*>(dst + (int64_t)sl * 64 + ((ch ^ (sl & 7)) << 3)) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 }

@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
 
 
 // ====================================================================================================================
-// fablock_full2_kernel: the same block on PRE-STAGED operands with a producer warp (round 2, third session).
+// fablock_full2_kernel: the same block on PRE-STAGED operands with a producer thread (round 2, third session).
 //
 // The phase trace of fablock_full_kernel (-DLNS_FULL_TRACE, 32x32: 30.8k cycles per head) showed 8.5k cycles per head in
 // which the tensor pipes idle: 3.4k per-(sample, head) operand set-up (GroupNorm folded into the in_proj slice, its bias, Kx /
@@ -695,9 +695,10 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full_kernel
 //   * lns_fablock_prepass_staged writes the NORMALISED input once per sample as the byte image of U_s (pixel permutation +
 //     128-byte swizzle applied): the in_proj slice is sample independent (16-bit, prepared once per parameter version, no
 //     bias), and a head's input is four linear 32 KB bulk copies;
-//   * one extra warp (lane 0) is the producer: it issues every bulk copy (input quarters, in_proj slice, Kx | Ky, the fp32
-//     to_out[1] slice) and every tcgen05.mma, and talks to the 16 compute warps through mbarriers only -- the compute warps
-//     synchronise among themselves with a named barrier and never wait for an instruction issue;
+//   * thread 0 is the producer: it issues every bulk copy (input quarters, in_proj slice, Kx | Ky, the fp32 to_out[1] slice)
+//     and every tcgen05.mma at two points of the head loop and meets the other warps at mbarriers only -- no warp waits at a
+//     block barrier for an instruction issue (a 17th producer warp was tried first: correct at 32x32, but five warps on one
+//     scheduler cap the kernel at 96 registers, and two co-resident 9-warp CTAs at 16x16 produced wrong samples);
 //   * the head's tcgen05 GEMM is committed per quarter of the pixel rows, so the next head's input quarter q is refilled as soon
 //     as the MMAs that read quarter q have completed, and phase A of the next head starts on quarter 0 while the tensor core
 //     is still working on quarters 1-3.
@@ -751,8 +752,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "r"(bytes), "r"(bar)
                : "memory");
 }
-template <int N>
-__device__ __forceinline__ void named_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 }  // namespace fptx
 
 #ifdef LNS_FULL_TRACE
@@ -761,9 +760,9 @@ __device__ __forceinline__ void named_sync() { asm volatile("bar.sync 1, %0;" ::
 #define LNS_FT2(i) do { } while (0)
 #endif
 
-// grid B (one CTA per sample), block NTHR compute threads + one producer warp
+// grid B (one CTA per sample), block NTHR threads (512 for > 256 pixels, else 256; two CTAs per SM at 16x16)
 template <int NTHR, bool F16>
-__global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_kernel(const Full2Params p) {
+__global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) fablock_full2_kernel(const Full2Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (fptx::s32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - fptx::s32(smem_raw));
@@ -779,8 +778,8 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
   auto bar_u = [&](int q) { return bar0 + (uint32_t)q * 8u; };          // input quarter q has landed (tx)
   const uint32_t bar_ops = bar0 + 32u;                                   // in_proj slice + Kx | Ky have landed (tx)
   const uint32_t bar_w1 = bar0 + 40u;                                    // to_out[1] slice has landed (tx)
-  const uint32_t bar_opfree = bar0 + 48u;                                // compute warps are done with Ws / Kst (nwarp arrivals)
-  const uint32_t bar_e = bar0 + 56u;                                     // compute warps have written U_s / Wo_s of this head
+  const uint32_t bar_opfree = bar0 + 48u;                                // every warp is done with Ws / Kst (nwarp arrivals)
+  const uint32_t bar_e = bar0 + 56u;                                     // every warp has written U_s / Wo_s of this head
   auto bar_mma = [&](int q) { return bar0 + 64u + (uint32_t)q * 8u; };  // the head's MMAs on quarter q have completed
   const uint32_t bar_fin = bar0 + 96u;
   uint16_t* Kx_s = reinterpret_cast<uint16_t*>(gen + L.Kx);
@@ -814,7 +813,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
   }
   if (tid < 64) obias_s[tid] = 0.f;
   // to_out[3] filter -> 16-bit swizzled K-major B operand [64 n][64 k]
-  for (int e = tid; e < 64 * 8; e += NTHR + 32) {
+  for (int e = tid; e < 64 * 8; e += NTHR) {
     const int n = e >> 3, kc = e & 7;
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_out2 + n * 64 + kc * 8));
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_out2 + n * 64 + kc * 8 + 4));
@@ -822,7 +821,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
                        pack2_h16<F16>(w1.z, w1.w));
   }
   fptx::tc_fence_before();
-  __syncthreads();  // the only block-wide barrier: from here on the producer warp and the compute warps meet at mbarriers
+  __syncthreads();
   fptx::tc_fence_after();
   const uint32_t tmem_acc = *slot_gen;
   // instruction descriptor, kind::f16: D = f32, A/B = bf16 (1) or f16 (0), K-major, N = 64, M = 128
@@ -830,58 +829,40 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
   const uint32_t qbytes = (uint32_t)HW * 128u / NQ;
   const int tl_per_q = T / NQ;
 
-  if (warp == nwarp) {
-    // ======================= producer warp: bulk copies + tcgen05.mma issue, one lane =======================
-    if (lane == 0) {
-      const uint8_t* usb = reinterpret_cast<const uint8_t*>(p.us) + (size_t)b * HW * 128u;
-      const uint32_t kxb = (uint32_t)(H * H) * 4u, kyb = (uint32_t)(W * W) * 4u;
-      auto issue_ops = [&](int hh) {
-        fptx::mbar_expect_tx(bar_ops, 64u * kWS * 2u + kxb + kyb);
-        fptx::bulk_g2s(Ws_a, p.w_in16 + (size_t)hh * 64 * kWS, 64u * kWS * 2u, bar_ops);
-        fptx::bulk_g2s(Kst_a, p.Kx + ((int64_t)b * heads + hh) * H * H, kxb, bar_ops);
-        fptx::bulk_g2s(Kst_a + kxb, p.Ky + ((int64_t)b * heads + hh) * W * W, kyb, bar_ops);
-      };
-      auto issue_w1 = [&](int hh) {
-        fptx::mbar_expect_tx(bar_w1, 64u * 64u * 4u);
-        fptx::bulk_g2s(W1st_a, p.w1h + (size_t)hh * 64 * 64, 64u * 64u * 4u, bar_w1);
-      };
-      auto issue_u = [&](int q) {
-        fptx::mbar_expect_tx(bar_u(q), qbytes);
-        fptx::bulk_g2s(U_a + (uint32_t)q * qbytes, usb + (size_t)q * qbytes, qbytes, bar_u(q));
-      };
-      issue_ops(0);
-      for (int q = 0; q < NQ; ++q) issue_u(q);
-      issue_w1(0);
-      for (int h = 0; h < heads; ++h) {
-        const uint32_t par = (uint32_t)(h & 1);
-        if (h + 1 < heads) {
-          fptx::mbar_wait(bar_opfree, par);  // every compute warp holds its in_proj fragments and has converted Kx | Ky
-          issue_ops(h + 1);
-        }
-        fptx::mbar_wait(bar_e, par);  // U_s holds the head's u_phi, Wo_s[h & 1] the folded to_out[1] slice
-        fptx::tc_fence_after();
-        if (h + 1 < heads) issue_w1(h + 1);
-        const uint64_t bdesc = desc_sw128(base + L.Wo + (uint32_t)(h & 1) * 8192u);
-        for (int q = 0; q < NQ; ++q) {
-          for (int tl = q * tl_per_q; tl < (q + 1) * tl_per_q; ++tl) {
-            const uint64_t adesc = desc_sw128(U_a + (uint32_t)tl * 16384u);
+  // ---- producer duties: thread 0 only, at points of the head loop where the other warps are not waiting for it ----
+  const uint8_t* usb = reinterpret_cast<const uint8_t*>(p.us) + (size_t)b * HW * 128u;
+  const uint32_t kxb = (uint32_t)(H * H) * 4u, kyb = (uint32_t)(W * W) * 4u;
+  auto issue_ops = [&](int hh) {
+    fptx::mbar_expect_tx(bar_ops, 64u * kWS * 2u + kxb + kyb);
+    fptx::bulk_g2s(Ws_a, p.w_in16 + (size_t)hh * 64 * kWS, 64u * kWS * 2u, bar_ops);
+    fptx::bulk_g2s(Kst_a, p.Kx + ((int64_t)b * heads + hh) * H * H, kxb, bar_ops);
+    fptx::bulk_g2s(Kst_a + kxb, p.Ky + ((int64_t)b * heads + hh) * W * W, kyb, bar_ops);
+  };
+  auto issue_w1 = [&](int hh) {
+    fptx::mbar_expect_tx(bar_w1, 64u * 64u * 4u);
+    fptx::bulk_g2s(W1st_a, p.w1h + (size_t)hh * 64 * 64, 64u * 64u * 4u, bar_w1);
+  };
+  auto issue_u = [&](int q) {
+    fptx::mbar_expect_tx(bar_u(q), qbytes);
+    fptx::bulk_g2s(U_a + (uint32_t)q * qbytes, usb + (size_t)q * qbytes, qbytes, bar_u(q));
+  };
+  auto issue_mma = [&](int h, int q) {  // the head's to_out[1] GEMM on the pixel rows of quarter q, committed on its own barrier
+    const uint64_t bdesc = desc_sw128(base + L.Wo + (uint32_t)(h & 1) * 8192u);
+    for (int tl = q * tl_per_q; tl < (q + 1) * tl_per_q; ++tl) {
+      const uint64_t adesc = desc_sw128(U_a + (uint32_t)tl * 16384u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              fptx::umma_f16(tmem_acc + (uint32_t)(tl * 64), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (h | k) != 0 ? 1u : 0u);
-          }
-          fptx::umma_commit(bar_mma(q));
-        }
-        if (h + 1 < heads)
-          for (int q = 0; q < NQ; ++q) {
-            fptx::mbar_wait(bar_mma(q), par);  // the tensor core has read quarter q: refill it with the next head's input
-            issue_u(q);
-          }
-      }
+      for (int k = 0; k < 4; ++k)
+        fptx::umma_f16(tmem_acc + (uint32_t)(tl * 64), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (h | k) != 0 ? 1u : 0u);
     }
-    return;
+    fptx::umma_commit(bar_mma(q));
+  };
+  if (tid == 0) {
+    issue_ops(0);
+    for (int q = 0; q < NQ; ++q) issue_u(q);
+    issue_w1(0);
   }
+  __syncwarp();
 
-  // =================================== compute warps ===================================
   const int t = lane & 3;
   (void)t;
   const int nblk = HW >> 4;
@@ -902,6 +883,15 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
         fptx::ldsm_x2(Ws_a + (uint32_t)(((nt * 8 + (lane & 7)) * kWS + ks * 16 + ((lane >> 3) & 1) * 8) * 2), wf[ks][nt][0], wf[ks][nt][1]);
     __syncwarp();
     if (lane == 0) fptx::mbar_arrive(bar_opfree);
+    if (tid == 0 && h + 1 < heads) {
+      fptx::mbar_wait(bar_opfree, par);  // every warp holds its in_proj fragments and has converted Kx | Ky: refill for head h + 1
+      // generic-proxy READS of Ws / Kst by the other warps (ordered before this point by the mbarrier) -> async-proxy WRITES of the
+      // bulk copies: the ISSUING thread needs its own proxy fence.  Without it about 1 sample in 10^4 came out wrong at 16x16
+      // (two CTAs per SM; never seen at 32x32) -- tools/dbg_staged3.py counts them over many launches.
+      fptx::fence_proxy_async();
+      issue_ops(h + 1);
+    }
+    __syncwarp();
     LNS_FT2(1);
     // ---- phase A: u_phi_h = u_n x W_in[h]^T, in place, 16-row blocks per warp; quarter q as soon as it has landed ----
     for (int q = 0; q < NQ; ++q) {
@@ -932,21 +922,21 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
         }
       }
     }
-    fptx::named_sync<NTHR>();  // (also publishes Kx_s / Ky_s)
+    __syncthreads();  // (also publishes Kx_s / Ky_s)
     LNS_FT2(3);
     // ---- phase B: contraction over H, one image column per warp at a time ----
     for (int m = warp; m < W; m += nwarp) {
       if (H == 16) contract_line_sw<1, 0, F16>(U_a, m, W, H, Kx_a, kxs, lane);
       else contract_line_sw<2, 0, F16>(U_a, m, W, H, Kx_a, kxs, lane);
     }
-    fptx::named_sync<NTHR>();
+    __syncthreads();
     LNS_FT2(4);
     // ---- phase C: contraction over W, one image row per warp ----
     for (int i = warp; i < H; i += nwarp) {
       if (W == 16) contract_line_sw<1, 1, F16>(U_a, i, W, W, Ky_a, kys, lane);
       else contract_line_sw<2, 1, F16>(U_a, i, W, W, Ky_a, kys, lane);
     }
-    fptx::named_sync<NTHR>();
+    __syncthreads();
     LNS_FT2(5);
     // ---- phase D: InstanceNorm statistics of this head's 64 channels, from the 16-bit values the GEMM will read ----
     {
@@ -984,7 +974,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
         }
       }
     }
-    fptx::named_sync<NTHR>();
+    __syncthreads();
     LNS_FT2(6);
     if (tid < 64) {
       double sm = 0.0, ss = 0.0;
@@ -1004,7 +994,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
       stat_s[tid * 2 + 1] = (float)(-mean * rstd);
     }
     fptx::mbar_wait(bar_w1, par);
-    fptx::named_sync<NTHR>();
+    __syncthreads();
     LNS_FT2(7);
     // ---- phase E: fold the normalisation into to_out[1]'s slice (staged in shared memory); the producer issues the GEMM ----
     const uint32_t Wo_a = base + L.Wo + (uint32_t)(h & 1) * 8192u;
@@ -1031,13 +1021,36 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
     fptx::tc_fence_before();
     __syncwarp();
     if (lane == 0) fptx::mbar_arrive(bar_e);
+    if (tid == 0) {
+      // The other warps go on to the next head's operand set-up and wait for its input; nobody waits for this thread except
+      // through the data it moves.  MMAs of quarter q + 1 are queued before quarter q's completion is awaited, so the tensor
+      // core stays fed while the input of the next head streams in behind it.
+      fptx::mbar_wait(bar_e, par);
+      fptx::fence_proxy_async();  // (as above: the other warps' reads of W1st, their writes of U_s / Wo_s -> bulk copies / MMAs issued here)
+      fptx::tc_fence_after();
+      const bool more = h + 1 < heads;
+      if (more) issue_w1(h + 1);
+      issue_mma(h, 0);
+      for (int q = 1; q < NQ; ++q) {
+        issue_mma(h, q);
+        if (more) {
+          fptx::mbar_wait(bar_mma(q - 1), par);
+          issue_u(q - 1);
+        }
+      }
+      if (more) {
+        fptx::mbar_wait(bar_mma(NQ - 1), par);
+        issue_u(NQ - 1);
+      }
+    }
+    __syncwarp();
     LNS_FT2(8);
   }
 
   // ================= after the last head: GELU(acc + b1') -> to_out[3] -> + skip -> out =================
   fptx::mbar_wait(bar_mma(NQ - 1), (uint32_t)((heads - 1) & 1));
   fptx::tc_fence_after();
-  fptx::named_sync<NTHR>();  // obias_s of the last head is complete
+  __syncthreads();  // obias_s of the last head is complete
   const int quad = warp & 3, sub = warp >> 2, nsub = nwarp >> 2;
   for (int tl = sub; tl < T; tl += nsub) {
     const int pr = tl * 128 + quad * 32 + lane;
@@ -1060,7 +1073,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
   }
   fptx::fence_proxy_async();
   fptx::tc_fence_before();
-  fptx::named_sync<NTHR>();
+  __syncthreads();
   if (tid == 0) {
     fptx::tc_fence_after();
     const uint64_t bdesc = desc_sw128(W2_a);
@@ -1103,7 +1116,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR == 256 ? 2 : 1) fablock_full2_
     }
   }
   fptx::tc_fence_before();
-  fptx::named_sync<NTHR>();
+  __syncthreads();
   // copy-out: 8 lanes x 16 B per pixel row -> full 128-byte lines of the NHWC output
   {
     const int ch = tid & 7;
@@ -1256,10 +1269,10 @@ int lns_fablock_full_staged(const void* u_staged, const void* u, int dtype, int 
   const bool f16 = dtype == LNS_F16;
   if (big) {
     auto kern = f16 ? lns::fablock_full2_kernel<512, true> : lns::fablock_full2_kernel<512, false>;
-    kern<<<B, 512 + 32, smem, st>>>(p);
+    kern<<<B, 512, smem, st>>>(p);
   } else {
     auto kern = f16 ? lns::fablock_full2_kernel<256, true> : lns::fablock_full2_kernel<256, false>;
-    kern<<<B, 256 + 32, smem, st>>>(p);
+    kern<<<B, 256, smem, st>>>(p);
   }
 #ifdef LNS_FULL_TRACE
   {

@@ -57,7 +57,7 @@ class _State(threading.local):
         self.fablock_tc = os.environ.get("LNS_FABLOCK_TC", "0") != "0"
         # FABlock2D whole-block kernel on pre-staged operands with a producer warp (fablock_full2_kernel); LNS_FABLOCK_STAGED=0
         # falls back to the in-kernel staging version (fablock_full_kernel)
-        self.fablock_staged = os.environ.get("LNS_FABLOCK_STAGED", "0") != "0"
+        self.fablock_staged = os.environ.get("LNS_FABLOCK_STAGED", "1") != "0"
 
 
 def _mark(label, flops=0.0, nbytes=0.0):
