@@ -205,7 +205,7 @@ class ClockSampler:
 KERNEL_OF = [  # timeline label prefix -> kernel (csrc file)
     ("conv e0", "conv_simt_kernel / lift1x1 (conv_simt.cu)"), ("conv e1", "conv_umma_kernel (conv_umma.cu, tcgen05 gather engine)"),
     ("conv e2", "conv_halo_kernel (conv_halo.cu, tcgen05 halo engine)"), ("conv e3", "conv_latent_kernel (conv_latent.cu, tcgen05)"),
-    ("conv e4", "conv_coarse_kernel (conv_coarse.cu, tcgen05 block-halo engine)"), ("fablock_full", "fablock_full_kernel (fablock_full.cu)"),
+    ("conv e4", "conv_coarse_kernel (conv_coarse.cu, tcgen05 block-halo engine)"), ("fablock_full", "fablock_full2_kernel (fablock_full.cu; fablock_full_kernel for shapes outside 16/32)"),
     ("fablock_tc", "fablock_tc_kernel (fablock_tc.cu, tcgen05)"), ("fa_axis", "fa_axis_kernel (fa_axis.cu)"),
     ("sablock_fused", "sablock_fused_kernel (sablock_fused.cu)"), ("ffn_fused", "ffn_fused_kernel (ffn_fused.cu, tcgen05)"),
     ("proj", "pointwise_proj64_kernel (pointwise.cu)"), ("gn_stats", "gn_affine_small / chan_stats kernels (pointwise.cu, norm.cu)"),

@@ -1,4 +1,6 @@
-"""Whole-block FABlock2D kernel in isolation (for ncu): python tools/ncu_fablock_full.py [H W batch]"""
+"""Whole-block FABlock2D kernel in isolation (for ncu): python tools/ncu_fablock_full.py [H W batch]
+Runs the default path (pre-staged operands + producer thread, fablock_full2_kernel); LNS_FABLOCK_STAGED=0: the in-kernel-staging
+kernel (fablock_full_kernel)."""
 import os
 import sys
 
@@ -10,22 +12,31 @@ from lns_b200 import ops  # noqa: E402
 
 H, W, nb = [int(a) for a in (sys.argv[1:4] + ["32", "32", "1024"][len(sys.argv[1:4]):])]
 dev = "cuda:0"
-u = ops.Act(torch.randn(nb * H * W * 64, device=dev).bfloat16(), nb, H, W, 64)
-sc = torch.rand(nb * 64, device=dev) + 0.5
-sh = torch.randn(nb * 64, device=dev) * 0.1
+dt = torch.float16
+u = ops.Act(torch.randn(nb * H * W * 64, device=dev).to(dt), nb, H, W, 64)
+gamma, beta = torch.rand(64, device=dev) + 0.5, torch.randn(64, device=dev) * 0.1
 w = torch.nn.Parameter(torch.randn(512, 64, device=dev) / 8)
 w1 = torch.nn.Parameter(torch.randn(64, 512, 1, 1, device=dev) / 22)
 w2 = torch.nn.Parameter(torch.randn(64, 64, 1, 1, device=dev) / 8)
 kx = torch.randn(nb, 8, H, H, device=dev) / H ** 0.5
 ky = torch.randn(nb, 8, W, W, device=dev) / W ** 0.5
-for _ in range(2):
-    ops.fablock_full(u, sc, sh, w, kx, ky, 8, 1e-5, w1, w2)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(3):
-    ops.fablock_full(u, sc, sh, w, kx, ky, 8, 1e-5, w1, w2)
-e1.record()
-torch.cuda.synchronize()
+staged = ops._state.fablock_staged
+with torch.no_grad(), ops.precision("fp16"):
+    if staged:
+        sc, sh, _, _, st = ops.fablock_prepass(u, 1e-5, gamma, beta, staged=True)
+        w_in16, w1h = ops.fablock_staged_operands(w, w1, 8, dt)
+        run = lambda: ops.fablock_full_staged(st, u, w_in16, kx, ky, 8, 1e-5, w1h, w2)  # noqa: E731
+    else:
+        sc, sh, _, _ = ops.fablock_prepass(u, 1e-5, gamma, beta)
+        run = lambda: ops.fablock_full(u, sc, sh, w, kx, ky, 8, 1e-5, w1, w2)  # noqa: E731
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
-print(f"fablock_full {H}x{W} batch {nb}: {ms:.3f} ms; {nb / ms:.0f} samples/ms")
+print(f"fablock_full ({'staged' if staged else 'in-kernel staging'}) {H}x{W} batch {nb}: {ms:.3f} ms; {nb / ms:.0f} samples/ms")
