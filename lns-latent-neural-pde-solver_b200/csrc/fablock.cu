@@ -574,6 +574,205 @@ __global__ void __launch_bounds__(256) fablock_prepass2_kernel(const void* __res
   }
 }
 
+// v3 of the pre-pass, for the shapes lns_fablock_full_staged covers (C = 64, 16-bit, H, W in {16, 32}): the sample arrives in
+// shared memory through bulk copies (one instruction for up to 128 KB) and every later pass reads it from there -- the
+// statistics / pooled sums, and the normalised + permuted + swizzled copy the whole-block kernel fetches per head.  v2 read the
+// sample twice through the LSU (once for the statistics with two loads in flight per row, once from L2 for the staged copy) and
+// ran at 1.2 GB in 0.53 ms; the HBM floor of one read + one write is 0.19 ms.
+//   pass A  thread = (pixel lane, 16-byte chunk), pixels pixel lane + k * NTHR/8: its image column is fixed, so it carries the
+//           column partial (= its share of sum x) and sum x^2 of 8 channels in registers
+//   pass B  warp = image rows, lane = (x mod 4, chunk): row sums, finished with two shuffles per channel
+//   then    GroupNorm(1, 64) in fp64 by warp 0 (per-channel partials rounded to fp32 like the generic statistics kernels),
+//           pooled outputs, and the staged copy straight from shared memory.
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR) fablock_prepass3_kernel(const uint16_t* __restrict__ u, int dtype, int H, int W, int lgw, int64_t bstride,
+                                                                float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ scale, float* __restrict__ shift,
+                                                                float* __restrict__ pooled_x, float* __restrict__ pooled_y,
+                                                                uint16_t* __restrict__ staged) {
+  extern __shared__ __align__(128) uint8_t sm3[];
+  constexpr int nwarp = NTHR / 32, NPL = NTHR / 8;
+  const int HW = H * W, NP = NPL / W;  // NP row groups contribute to one image column in pass A
+  const uint8_t* S = sm3;                                                  // [HW][64] 16-bit, as in global memory
+  float* colpart = reinterpret_cast<float*>(sm3 + (size_t)HW * 128);       // [NP][W][64]
+  float* rowsum = colpart + (size_t)NP * W * 64;                           // [H][64]
+  float* tot = rowsum + (size_t)H * 64;                                    // [nwarp][64][2]
+  float* ab = tot + (size_t)nwarp * 64 * 2;                                // [64][2] scale, shift
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(ab + 128);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const uint32_t S_a = (uint32_t)__cvta_generic_to_shared(sm3), bar = (uint32_t)__cvta_generic_to_shared(mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)HW * 128u, part = bytes / 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(u + (int64_t)b * bstride);
+    for (int q = 0; q < 4; ++q)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(S_a + q * part),
+                   "l"(src + (size_t)q * part), "r"(part), "r"(bar)
+                   : "memory");
+  }
+  __syncthreads();  // the barrier is initialised for every waiter
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LNSP3_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+      "@p bra LNSP3_DONE_%=;\n\t"
+      "bra LNSP3_WAIT_%=;\n\t"
+      "LNSP3_DONE_%=:\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+  const int ch = lane & 7;
+  // ---- pass A: column partials + sum x^2 ----
+  {
+    const int pl = tid >> 3;
+    float cs[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = sq[j] = 0.f;
+    for (int p0 = pl; p0 < HW; p0 += 4 * NPL) {  // four 16-byte loads in flight
+      uint4 raw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) raw[k] = *reinterpret_cast<const uint4*>(S + (size_t)(p0 + k * NPL) * 128 + ch * 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t rw[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack2_rt(dtype, rw[j]);
+          cs[2 * j] += f.x; sq[2 * j] = fmaf(f.x, f.x, sq[2 * j]);
+          cs[2 * j + 1] += f.y; sq[2 * j + 1] = fmaf(f.y, f.y, sq[2 * j + 1]);
+        }
+      }
+    }
+    const int x = pl & (W - 1), rg = pl >> lgw;
+    float* cp = colpart + ((size_t)rg * W + x) * 64 + ch * 8;
+    *reinterpret_cast<float4*>(cp) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+    *reinterpret_cast<float4*>(cp + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // the 4 pixel lanes of the warp that share this chunk
+      cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+      cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+      sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 8);
+      sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        tot[((size_t)warp * 64 + ch * 8 + j) * 2 + 0] = cs[j];
+        tot[((size_t)warp * 64 + ch * 8 + j) * 2 + 1] = sq[j];
+      }
+    }
+  }
+  // ---- pass B: row sums ----
+  {
+    const int xq = lane >> 3;
+    for (int y = warp; y < H; y += nwarp) {
+      float rs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rs[j] = 0.f;
+      for (int x0 = xq; x0 < W; x0 += 16) {
+        uint4 raw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) raw[k] = *reinterpret_cast<const uint4*>(S + (size_t)(y * W + x0 + 4 * k) * 128 + ch * 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t rw[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2_rt(dtype, rw[j]);
+            rs[2 * j] += f.x;
+            rs[2 * j + 1] += f.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        rs[j] += __shfl_xor_sync(0xffffffffu, rs[j], 8);
+        rs[j] += __shfl_xor_sync(0xffffffffu, rs[j], 16);
+      }
+      if (lane < 8) {
+        *reinterpret_cast<float4*>(rowsum + (size_t)y * 64 + ch * 8) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+        *reinterpret_cast<float4*>(rowsum + (size_t)y * 64 + ch * 8 + 4) = make_float4(rs[4], rs[5], rs[6], rs[7]);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- GroupNorm(1, 64): one group over all channels; warp 0 reduces (fixed order) ----
+  if (tid < 32) {
+    double sum = 0.0, sumsq = 0.0;
+    for (int c = tid; c < 64; c += 32) {
+      double a = 0.0, a2 = 0.0;
+      for (int w = 0; w < nwarp; ++w) {
+        a += (double)tot[((size_t)w * 64 + c) * 2 + 0];
+        a2 += (double)tot[((size_t)w * 64 + c) * 2 + 1];
+      }
+      sum += (double)(float)a;  // per-channel sums rounded to fp32 like the generic statistics kernels
+      sumsq += (double)(float)a2;
+    }
+    sum = warp_sum_d(sum);
+    sumsq = warp_sum_d(sumsq);
+    const double n = 64.0 * (double)HW;
+    const double mean = sum / n;
+    double var = sumsq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    for (int c = tid; c < 64; c += 32) {
+      const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+      const float sc = (float)(rstd * ga), sh = (float)(be - mean * rstd * ga);
+      ab[c * 2 + 0] = sc;
+      ab[c * 2 + 1] = sh;
+      scale[(int64_t)b * 64 + c] = sc;
+      shift[(int64_t)b * 64 + c] = sh;
+    }
+  }
+  __syncthreads();
+  const float invW = 1.f / (float)W, invH = 1.f / (float)H;
+  for (int e = tid; e < H * 64; e += NTHR) {
+    const int c = e & 63;
+    pooled_x[(int64_t)b * H * 64 + e] = fmaf(rowsum[e] * invW, ab[c * 2], ab[c * 2 + 1]);
+  }
+  for (int e = tid; e < W * 64; e += NTHR) {
+    const int c = e & 63;
+    float a = 0.f;
+    for (int r = 0; r < NP; ++r) a += colpart[(size_t)r * W * 64 + e];
+    pooled_y[(int64_t)b * W * 64 + e] = fmaf(a * invH, ab[c * 2], ab[c * 2 + 1]);
+  }
+  // ---- staged copy: row sl of the image = pixel sl ^ ((sl >> lgw) & 7), chunk ch at ch ^ (sl & 7), normalised ----
+  {
+    uint16_t* dst = staged + (int64_t)b * HW * 64;
+    float4 a4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a4[j] = *reinterpret_cast<const float4*>(ab + (ch * 8 + 2 * j) * 2);  // scale, shift of two channels
+    for (int sl0 = tid >> 3; sl0 < HW; sl0 += 4 * NPL) {
+      uint4 raw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int sl = sl0 + k * NPL;
+        raw[k] = *reinterpret_cast<const uint4*>(S + (size_t)(sl ^ ((sl >> lgw) & 7)) * 128 + ch * 16);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int sl = sl0 + k * NPL;
+        const uint32_t rw[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack2_rt(dtype, rw[j]);
+          o[j] = pack2_rt(dtype, fmaf(f.x, a4[j].x, a4[j].y), fmaf(f.y, a4[j].z, a4[j].w));
+        }
+        *reinterpret_cast<uint4*>(dst + (int64_t)sl * 64 + ((ch ^ (sl & 7)) << 3)) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+static size_t prepass3_smem(int H, int W, int nthr) {
+  const int np = (nthr / 8) / W;
+  return (size_t)H * W * 128 + ((size_t)np * W * 64 + (size_t)H * 64 + (size_t)(nthr / 32) * 64 * 2 + 128) * sizeof(float) + 16;
+}
+
 static size_t fablock_smem(int H, int W) {
   const int HW = H * W, H16 = (H + 15) & ~15, W16 = (W + 15) & ~15;
   size_t bf = (size_t)H * (W * kUS + 8) + 64 * kUS + (size_t)H16 * (H16 + 8) + (size_t)W16 * (W16 + 8);
@@ -600,6 +799,19 @@ static int fablock_prepass_impl(const void* u, int dtype, int B, int H, int W, i
   LNS_REQUIRE(C % 4 == 0 && C >= 4 && C <= 256 && (cg & (cg - 1)) == 0, "lns_fablock_prepass: C must be a power of two in [4,256]");
   LNS_REQUIRE(bstride % 4 == 0, "lns_fablock_prepass: batch stride must be a multiple of 4");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (staged && !getenv("LNS_PREPASS_V2")) {  // (LNS_PREPASS_V2: the LSU pre-pass below also for the staged case, for comparison)
+    const uint16_t* u16 = reinterpret_cast<const uint16_t*>(u);
+    if (H * W > 256) {
+      const size_t smem3 = lns::prepass3_smem(H, W, 512);
+      { LNS_OPT_IN_SMEM((lns::fablock_prepass3_kernel<512>), 200 * 1024, "fablock"); }
+      lns::fablock_prepass3_kernel<512><<<B, 512, smem3, st>>>(u16, dtype, H, W, lgw, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y, staged);
+    } else {
+      const size_t smem3 = lns::prepass3_smem(H, W, 256);
+      { LNS_OPT_IN_SMEM((lns::fablock_prepass3_kernel<256>), 200 * 1024, "fablock"); }
+      lns::fablock_prepass3_kernel<256><<<B, 256, smem3, st>>>(u16, dtype, H, W, lgw, bstride, eps, gamma, beta, scale, shift, pooled_x, pooled_y, staged);
+    }
+    return lns::check_launch("fablock_prepass3_kernel");
+  }
   if (C <= 128) {
     const int npl = 128 / C, nx = (W + npl - 1) / npl;
     size_t smem2 = ((size_t)H * C + 8 * (size_t)W * C + 8 * (size_t)C * 2 + 2 * (size_t)C) * sizeof(float);

@@ -1054,3 +1054,46 @@ def test_fablock_staged_vs_full_and_oracle(H, W, B, prec):
     assert e_st < tol and relerr(st, full) < tol
     per = ((st - full).flatten(1).norm(dim=1) / full.flatten(1).norm(dim=1)).max().item()
     assert per < tol
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("H,W,B", [(16, 16, 7), (32, 32, 5), (16, 32, 3), (32, 16, 3), (32, 32, 300)])
+def test_fablock_prepass_staged_v3_vs_v2_and_torch(H, W, B, prec):
+    """bulk-copy-fed pre-pass (sample resident in shared memory) vs the LSU pre-pass and vs torch: GroupNorm(1, 64) affine,
+    both pooled tensors (modules/factorized_attention.py:86-94,113), and the staged copy = GN(u) in the whole-block kernel's
+    shared-memory order (row s = pixel s ^ ((s >> log2 W) & 7), 16-byte chunk ch at ch ^ (s & 7))"""
+    import os
+    ops = ops_mod()
+    dt = torch.float16 if prec == "fp16" else torch.bfloat16
+    g = torch.Generator().manual_seed(47)
+    x = torch.randn(B, 64, H, W, generator=g) * 1.3 + 0.7
+    gamma = (torch.rand(64, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(64, generator=g) * 0.2).to(DEV)
+    a = act_from(x, dt)
+    with torch.no_grad(), ops.precision(prec):
+        s3, t3, px3, py3, st3 = ops.fablock_prepass(a, 1e-5, gamma, beta, staged=True)
+        os.environ["LNS_PREPASS_V2"] = "1"
+        try:
+            s2, t2, px2, py2, st2 = ops.fablock_prepass(a, 1e-5, gamma, beta, staged=True)
+        finally:
+            del os.environ["LNS_PREPASS_V2"]
+    torch.cuda.synchronize()
+    xr = a.t.float().view(B, H, W, 64).double()  # the 16-bit values the kernels read
+    mean = xr.mean(dim=(1, 2, 3), keepdim=True)
+    var = xr.var(dim=(1, 2, 3), unbiased=False, keepdim=True)
+    xn = (xr - mean) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()
+    assert relerr(px3.t.view(B, H, 64), xn.mean(dim=2)) < 2e-6 and relerr(py3.t.view(B, W, 64), xn.mean(dim=1)) < 2e-6
+    for v3, v2 in ((s3, s2), (t3, t2), (px3.t, px2.t), (py3.t, py2.t)):
+        assert relerr(v3, v2) < 1e-6
+    # staged copy: undo the permutation + swizzle and compare with GN(u)
+    lg = 5 if W == 32 else 4
+    sl = torch.arange(H * W, device=DEV)
+    src = sl ^ ((sl >> lg) & 7)
+    chunk = torch.arange(8, device=DEV)
+    pos = (chunk[None, :] ^ (sl[:, None] & 7))  # [HW][8]: where chunk ch of row sl sits
+    st = st3.view(B, H * W, 8, 8).float()
+    un = torch.empty_like(st)
+    un[:, src[:, None].expand(-1, 8), chunk[None, :].expand(H * W, -1)] = st[:, sl[:, None].expand(-1, 8), pos]
+    tol = 1.2e-3 if prec == "fp16" else 9e-3  # one rounding to 16 bits
+    assert relerr(un.view(B, H, W, 64), xn) < tol
+    assert (st3.float() - st2.float()).abs().max() <= 2 ** (-8 if prec == "fp16" else -5)  # at most one 16-bit ulp apart
