@@ -95,7 +95,7 @@ int validate_conv(const LnsConvDesc* d) {
 
 extern "C" {
 
-const char* lns_version(void) { return "lns_b200 0.2 (sm_100a)"; }
+const char* lns_version(void) { return "lns_b200 0.2.1 (sm_100a)"; }
 const char* lns_last_error(void) { return lns::g_err; }
 
 int lns_device_info(int* sm_count, int* cc_major, int* cc_minor) {
