@@ -178,3 +178,26 @@ def test_training_rollout_host_logic():
     assert lib.lns_absmax(None, 4, None, None) == -1 and lib.lns_loss_scale(None, 64.0, None, None) == -1
     assert lib.lns_norm_finalize_centred(None, 1, 1, 4, 1, 1, 1e-5, None, None, None, None, None, None) == -1
     assert b"lns_" in lib.lns_last_error()
+
+
+def test_fablock_staged_host_logic():
+    """Host side of the pre-staged FABlock2D path (modules/factorized_attention.py:144-159): operand preparation, the shapes the
+    staged entry points accept, and that nothing falls back on bad arguments."""
+    torch.manual_seed(5)
+    heads = 8
+    w_in = torch.randn(heads * 64, 64, 1, 1)
+    w_out1 = torch.randn(64, heads * 64, 1, 1)
+    w_in16, w1h = ops.fablock_staged_operands(w_in, w_out1, heads, torch.float16)
+    assert w_in16.shape == (heads, 64, 72) and w_in16.dtype == torch.float16 and w_in16.is_contiguous()
+    assert torch.equal(w_in16[:, :, :64], w_in.reshape(heads, 64, 64).half()) and float(w_in16[:, :, 64:].abs().max()) == 0.0
+    assert w1h.shape == (heads, 64, 64) and w1h.dtype == torch.float32 and w1h.is_contiguous()
+    # w1h[h][o][c] = to_out[1].weight[o][h * 64 + c]
+    assert torch.equal(w1h[3, 5], w_out1.reshape(64, heads * 64)[5, 3 * 64:4 * 64])
+    lib = _C.lib()
+    for H, W, ok in ((16, 16, 1), (32, 32, 1), (16, 32, 1), (32, 16, 1), (24, 48, 0), (8, 8, 0), (31, 16, 0), (64, 64, 0)):
+        assert lib.lns_fablock_full_staged_supported(H, W, 64, 64, 64) == ok
+    assert lib.lns_fablock_full_staged_supported(32, 32, 128, 64, 64) == 0 and lib.lns_fablock_full_staged_supported(32, 32, 64, 32, 64) == 0
+    # null pointers / unsupported shapes answer with an error code, never a fallback
+    assert lib.lns_fablock_full_staged(None, None, 2, 1, 32, 32, 8, None, None, None, 1e-5, None, None, None, None) != 0
+    assert lib.lns_fablock_prepass_staged(None, 2, 1, 32, 32, 64, 32 * 32 * 64, 1e-5, None, None, None, None, None, None, None, None) != 0
+    assert b"lns_fablock" in lib.lns_last_error()
