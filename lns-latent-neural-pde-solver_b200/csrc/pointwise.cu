@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) pointwise_proj_kernel(const void* __restr
 // trips per CTA.  Here lane `sub` of a pixel's 8 lanes owns channels 8*sub .. 8*sub+7 for the whole CTA: the eight 16-byte
 // input loads of its eight pixels are issued FIRST (128 bytes in flight per thread), the per-thread affine / weights (8 + 8
 // + 8*COUT registers) are loaded straight from global memory while they fly, there is no shared memory and no barrier.
-template <int COUT, bool F16>
+template <int COUT, bool F16, bool TANH>
 __global__ void __launch_bounds__(256) pointwise_proj64_kernel(const uint16_t* __restrict__ x, int HW, int64_t x_bstride,
                                                                 const float* __restrict__ w, const float* __restrict__ bias,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) pointwise_proj64_kernel(const uint16_t* _
     raw[pass] = make_uint4(0u, 0u, 0u, 0u);
     if (pix < HW) raw[pass] = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)pix * 64));
   }
-  const bool tanh_silu = !F16 && act == LNS_ACT_SILU;  // bf16 storage: x*sigmoid(x) = h + h*tanh(h), h = x/2 (see above)
+  const bool tanh_silu = TANH && act == LNS_ACT_SILU;  // x*sigmoid(x) = h + h*tanh(h), h = x/2 (see above): one SFU op per element
   const float half = tanh_silu ? 0.5f : 1.f;
   float sc[8], sh[8], wr[COUT][8];
 #pragma unroll
@@ -407,10 +407,15 @@ int lns_pointwise_proj_steps(const void* x, int dtype, int B, int HW, int C, int
       (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
     const uint16_t* xh = reinterpret_cast<const uint16_t*>(x);
     const bool f16 = dtype == LNS_F16;
+    // Swish through one tanh.approx on fp16 storage too (default): with ex2 + rcp the kernel is bound by the 16 SFU results per
+    // clock per SM (0.72 ms at 4736 x 64x64 against 0.45 ms of HBM time), with tanh 0.48 ms; the measured decode parity does
+    // not move (NS2d 1.24848e-3, shallow water 1.4365e-3 either way).  LNS_PROJ_SFU2=1 selects the ex2 + rcp form.
+    const bool tanh16 = getenv("LNS_PROJ_SFU2") == nullptr;
 #define LNS_PROJ64(N)                                                                                                              \
   do {                                                                                                                             \
-    if (f16) lns::pointwise_proj64_kernel<N, true><<<grid, 256, 0, s>>>(xh, HW, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); \
-    else lns::pointwise_proj64_kernel<N, false><<<grid, 256, 0, s>>>(xh, HW, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); \
+    if (f16 && tanh16) lns::pointwise_proj64_kernel<N, true, true><<<grid, 256, 0, s>>>(xh, HW, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); \
+    else if (f16) lns::pointwise_proj64_kernel<N, true, false><<<grid, 256, 0, s>>>(xh, HW, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); \
+    else lns::pointwise_proj64_kernel<N, false, true><<<grid, 256, 0, s>>>(xh, HW, x_bstride, w, bias, scale, shift, act, y, y_bstride, group, y_gstride); \
   } while (0)
     switch (Cout) {
       case 1: LNS_PROJ64(1); break;
