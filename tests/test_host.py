@@ -201,3 +201,30 @@ def test_fablock_staged_host_logic():
     assert lib.lns_fablock_full_staged(None, None, 2, 1, 32, 32, 8, None, None, None, 1e-5, None, None, None, None) != 0
     assert lib.lns_fablock_prepass_staged(None, 2, 1, 32, 32, 64, 32 * 32 * 64, 1e-5, None, None, None, None, None, None, None, None) != 0
     assert b"lns_fablock" in lib.lns_last_error()
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (32, 32), (16, 32), (32, 16)])
+def test_fablock_staged_layout_properties(H, W):
+    """The staged FABlock2D image (csrc/fablock.cu fablock_prepass3_kernel -> csrc/fablock_full.cu): row s holds pixel
+    s ^ ((s >> log2 W) & 7), 16-byte chunk ch sits at ch ^ (s & 7).  Properties the whole-block kernel relies on: the row map is a
+    bijection that keeps the image row, a COLUMN walk (fixed x, 8 consecutive y) and a ROW walk (8 consecutive x) both touch all 8
+    swizzle phases (conflict-free ldmatrix in both contraction directions), and a 128-row MMA tile is 128 consecutive rows."""
+    lg = W.bit_length() - 1
+    s = torch.arange(H * W)
+    src = s ^ ((s >> lg) & 7)
+    assert sorted(src.tolist()) == list(range(H * W))            # bijection
+    assert torch.equal(src >> lg, s >> lg)                       # x is permuted inside its image row only
+    row_of = torch.empty_like(s)
+    row_of[src] = s                                              # pixel index -> staged row
+    for x in range(0, W, 5):
+        for y0 in range(0, H - 7):
+            phases = {int(row_of[(y0 + k) * W + x]) & 7 for k in range(8)}
+            assert len(phases) == 8
+    for y in range(H):
+        for x0 in range(0, W, 8):
+            phases = {int(row_of[y * W + x0 + k]) & 7 for k in range(8)}
+            assert len(phases) == 8
+    # chunk swizzle: an involution per row, the 8 chunks of a row stay inside its 128 bytes
+    for srow in (0, 5, H * W - 1):
+        pos = [(ch ^ (srow & 7)) for ch in range(8)]
+        assert sorted(pos) == list(range(8)) and [p ^ (srow & 7) for p in pos] == list(range(8))
