@@ -1,4 +1,4 @@
-"""FABlock2D whole-block kernels timed alone (CUDA events): in-kernel staging (fablock_full) vs pre-staged operands + producer warp
+"""FABlock2D whole-block kernels timed alone (CUDA events): in-kernel staging (fablock_full) vs pre-staged operands + producer thread
 (fablock_full_staged), and the pre-pass with / without the staged copy.
     python tools/bench_fablock_staged.py [batch]"""
 import os
@@ -48,5 +48,5 @@ for n in (32, 16):
             t_st = timed(lambda: ops.fablock_full_staged(st, u, w_in16, kx, ky, 8, 1e-5, w1h, w2))
             t_p0 = timed(lambda: ops.fablock_prepass(u, 1e-5, gamma, beta))
             t_p1 = timed(lambda: ops.fablock_prepass(u, 1e-5, gamma, beta, staged=True))
-        print(f"FABlock2D {n}x{n} x{nb} {prec}: in-kernel staging {t_full:.3f} ms ({fl / t_full / 1e9:.0f} TFLOP/s) | staged + producer warp "
+        print(f"FABlock2D {n}x{n} x{nb} {prec}: in-kernel staging {t_full:.3f} ms ({fl / t_full / 1e9:.0f} TFLOP/s) | staged + producer thread "
               f"{t_st:.3f} ms ({fl / t_st / 1e9:.0f} TFLOP/s) | rel diff {d:.2e} | pre-pass {t_p0:.3f} -> {t_p1:.3f} ms", flush=True)
